@@ -1,0 +1,533 @@
+"""CPU oracle for the KVStore gradient path -- TEST INFRASTRUCTURE, NOT PRODUCT.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
+``--impl reference`` legs may import this module.  The product path
+(``incubator-mxnet_b200``) never does.
+
+Two layers:
+
+* thin ctypes bindings over ``oracle/libkvoracle.so`` (``kv_oracle.c``: the C
+  restatement of the reference kernels, each citing its reference file:line) and,
+  when present, ``oracle/_ref/libkvref.so`` (the reference's own mshadow
+  arithmetic, see ``ref_harness.cc``);
+* :class:`OracleKVStore`, a numpy model of ``KVStoreLocal``
+  (src/kvstore/kvstore_local.h:70-552) + ``CommDevice`` / ``CommCPU``
+  (src/kvstore/comm.h) + the Python ``Updater``/``Optimizer`` bookkeeping
+  (python/mxnet/optimizer/updater.py:39-93, optimizer.py:320-352, sgd.py:156-234,
+  adam.py:149-186).  Pinned against the reference's known-answer tests in
+  tests/test_oracle_golden.py.
+"""
+import ctypes
+import math
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+_REF = None
+
+c_f32p = ctypes.POINTER(ctypes.c_float)
+c_i64p = ctypes.POINTER(ctypes.c_int64)
+c_u16p = ctypes.POINTER(ctypes.c_uint16)
+c_u8p = ctypes.POINTER(ctypes.c_uint8)
+
+
+def build():
+    """(Re)build the oracle .so (and oracle/_ref when /root/reference exists)."""
+    subprocess.check_call(["make", "-C", _HERE, "--no-print-directory"], stdout=subprocess.DEVNULL)
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(_HERE, "libkvoracle.so")
+        if not os.path.exists(path):
+            build()
+        _LIB = ctypes.CDLL(path)
+        _LIB.kvo_adam_lr.restype = ctypes.c_double
+        _LIB.kvo_adam_lr.argtypes = [ctypes.c_double] * 3 + [ctypes.c_int]
+        _LIB.kvo_unique_i64.restype = ctypes.c_int64
+        _LIB.kvo_rsp_sum_f32.restype = ctypes.c_int64
+    return _LIB
+
+
+def ref_lib():
+    """The reference-arithmetic harness, or None when it was never built."""
+    global _REF
+    if _REF is None:
+        path = os.path.join(_HERE, "_ref", "libkvref.so")
+        if os.path.exists(path):
+            _REF = ctypes.CDLL(path)
+    return _REF
+
+
+def _ptr(a, ct):
+    return a.ctypes.data_as(ct)
+
+
+def _ptr_array(arrs):
+    return (ctypes.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+
+
+_F = ctypes.c_float
+_I64 = ctypes.c_int64
+
+_SUM_DEVICE = {
+    np.dtype(np.float32): "kvo_sum_device_f32", np.dtype(np.float64): "kvo_sum_device_f64",
+    np.dtype(np.int32): "kvo_sum_device_i32", np.dtype(np.int64): "kvo_sum_device_i64",
+    np.dtype(np.uint8): "kvo_sum_device_u8", np.dtype(np.int8): "kvo_sum_device_i8",
+    np.dtype(np.float16): "kvo_sum_device_f16",
+}
+
+
+def sum_device(srcs, bf16=False):
+    """CommDevice dense reduce order (comm.h:525-548 + ndarray_function-inl.h:457-486).
+    ``bf16=True``: inputs are uint16 bf16 bit patterns (fp32 accumulate, one RNE)."""
+    srcs = [np.ascontiguousarray(s) for s in srcs]
+    out = np.empty_like(srcs[0])
+    if bf16:
+        assert srcs[0].dtype == np.uint16
+        fn = lib().kvo_sum_device_bf16
+    else:
+        fn = getattr(lib(), _SUM_DEVICE[srcs[0].dtype])
+    fn(ctypes.c_int(len(srcs)), _ptr_array(srcs), _I64(srcs[0].size), ctypes.c_void_p(out.ctypes.data))
+    return out
+
+
+def sum_device_lp_f32out(srcs, kind):
+    """fp32 sum of fp16 (kind=1) / bf16 (kind=2) inputs given as uint16 bit patterns."""
+    srcs = [np.ascontiguousarray(s).view(np.uint16) for s in srcs]
+    out = np.empty(srcs[0].shape, np.float32)
+    fn = lib().kvo_sum_device_f16_f32out if kind == 1 else lib().kvo_sum_device_bf16_f32out
+    fn(ctypes.c_int(len(srcs)), _ptr_array(srcs), _I64(srcs[0].size), _ptr(out, c_f32p))
+    return out
+
+
+def sum_cpu(srcs, nthreads=4, bigarray_bound=1000 * 1000):
+    """CommCPU reduce (comm.h:359-411).  Returns a new array (srcs[0] is copied first,
+    like CopyFromTo(src[0], &buf_merged))."""
+    bufs = [np.array(s, dtype=np.float32, copy=True, order="C") for s in srcs]
+    lib().kvo_sum_cpu_f32(ctypes.c_int(len(bufs)), _ptr_array(bufs), _I64(bufs[0].size),
+                          ctypes.c_int(nthreads), _I64(bigarray_bound))
+    return bufs[0]
+
+
+def sum_cpu_inplace(bufs, nthreads=4, bigarray_bound=1000 * 1000):
+    """In-place CommCPU reduce into bufs[0] (no staging copy) -- the timed kernel of
+    the CPU baseline."""
+    lib().kvo_sum_cpu_f32(ctypes.c_int(len(bufs)), _ptr_array(bufs), _I64(bufs[0].size),
+                          ctypes.c_int(nthreads), _I64(bigarray_bound))
+
+
+def ref_sum_device(srcs):
+    r = ref_lib()
+    srcs = [np.ascontiguousarray(s) for s in srcs]
+    out = np.empty_like(srcs[0])
+    name = {np.dtype(np.float32): "kvref_sum_device_f32", np.dtype(np.float64): "kvref_sum_device_f64",
+            np.dtype(np.int32): "kvref_sum_device_i32", np.dtype(np.float16): "kvref_sum_device_f16"}[srcs[0].dtype]
+    getattr(r, name)(ctypes.c_int(len(srcs)), _ptr_array(srcs), _I64(srcs[0].size),
+                     ctypes.c_void_p(out.ctypes.data))
+    return out
+
+
+def ref_sum_cpu(srcs, nthreads=4, bigarray_bound=1000 * 1000):
+    bufs = [np.array(s, dtype=np.float32, copy=True, order="C") for s in srcs]
+    ref_lib().kvref_sum_cpu_f32(ctypes.c_int(len(bufs)), _ptr_array(bufs), _I64(bufs[0].size),
+                                ctypes.c_int(nthreads), _I64(bigarray_bound))
+    return bufs[0]
+
+
+# ---------------------------------------------------------------------------
+# bf16 helpers (bit patterns in uint16)
+# ---------------------------------------------------------------------------
+def f32_to_bf16(a):
+    u = np.ascontiguousarray(a, np.float32).view(np.uint32).astype(np.uint64)
+    nan = (u & 0x7FFFFFFF) > 0x7F800000
+    r = ((u + 0x7FFF + ((u >> 16) & 1)) >> 16).astype(np.uint16)
+    r[nan] = ((u[nan] >> 16) | 0x40).astype(np.uint16)
+    return r
+
+
+def bf16_to_f32(h):
+    return (np.ascontiguousarray(h, np.uint16).astype(np.uint32) << 16).view(np.float32)
+
+
+# ---------------------------------------------------------------------------
+# optimizer kernels (in place on numpy arrays)
+# ---------------------------------------------------------------------------
+def _clip(c):
+    return _F(-1.0 if c is None else c)
+
+
+def sgd_update(w, g, lr, wd=0.0, rescale=1.0, clip=None):
+    lib().kvo_sgd_update_f32(_I64(w.size), _ptr(w, c_f32p), _ptr(w, c_f32p), _ptr(g, c_f32p),
+                             _F(lr), _F(wd), _F(rescale), _clip(clip))
+
+
+def sgd_mom_update(w, g, mom, lr, wd=0.0, momentum=0.0, rescale=1.0, clip=None):
+    lib().kvo_sgd_mom_update_f32(_I64(w.size), _ptr(w, c_f32p), _ptr(mom, c_f32p), _ptr(w, c_f32p),
+                                 _ptr(g, c_f32p), _F(lr), _F(wd), _F(momentum), _F(rescale), _clip(clip))
+
+
+def mp_sgd_update(w_lp, lp_kind, w32, g32, lr, wd=0.0, rescale=1.0, clip=None):
+    lib().kvo_mp_sgd_update(_I64(w32.size), ctypes.c_void_p(w_lp.ctypes.data if w_lp is not None else 0),
+                            ctypes.c_int(lp_kind), _ptr(w32, c_f32p), _ptr(g32, c_f32p),
+                            _F(lr), _F(wd), _F(rescale), _clip(clip))
+
+
+def mp_sgd_mom_update(w_lp, lp_kind, w32, mom, g32, lr, wd=0.0, momentum=0.0, rescale=1.0, clip=None):
+    lib().kvo_mp_sgd_mom_update(_I64(w32.size), ctypes.c_void_p(w_lp.ctypes.data if w_lp is not None else 0),
+                                ctypes.c_int(lp_kind), _ptr(w32, c_f32p), _ptr(mom, c_f32p),
+                                _ptr(g32, c_f32p), _F(lr), _F(wd), _F(momentum), _F(rescale), _clip(clip))
+
+
+def adam_update(w, g, mean, var, lr, wd=0.0, beta1=0.9, beta2=0.999, eps=1e-8, rescale=1.0, clip=None):
+    lib().kvo_adam_update_f32(_I64(w.size), _ptr(w, c_f32p), _ptr(mean, c_f32p), _ptr(var, c_f32p),
+                              _ptr(w, c_f32p), _ptr(g, c_f32p), _F(lr), _F(wd), _F(beta1), _F(beta2),
+                              _F(eps), _F(rescale), _clip(clip))
+
+
+def mp_adam_update(w_lp, lp_kind, w32, mean, var, g32, lr, wd=0.0, beta1=0.9, beta2=0.999, eps=1e-8,
+                   rescale=1.0, clip=None):
+    lib().kvo_mp_adam_update(_I64(w32.size), ctypes.c_void_p(w_lp.ctypes.data if w_lp is not None else 0),
+                             ctypes.c_int(lp_kind), _ptr(w32, c_f32p), _ptr(mean, c_f32p),
+                             _ptr(var, c_f32p), _ptr(g32, c_f32p), _F(lr), _F(wd), _F(beta1), _F(beta2),
+                             _F(eps), _F(rescale), _clip(clip))
+
+
+def mp_adamw_update(w_lp, lp_kind, w32, mean, var, g32, lr, eta=1.0, wd=0.0, beta1=0.9, beta2=0.999,
+                    eps=1e-8, rescale=1.0, clip=None):
+    lib().kvo_mp_adamw_update(_I64(w32.size), ctypes.c_void_p(w_lp.ctypes.data if w_lp is not None else 0),
+                              ctypes.c_int(lp_kind), _ptr(w32, c_f32p), _ptr(mean, c_f32p),
+                              _ptr(var, c_f32p), _ptr(g32, c_f32p), _F(lr), _F(eta), _F(wd), _F(beta1),
+                              _F(beta2), _F(eps), _F(rescale), _clip(clip))
+
+
+def test_update(w, g, lr, wd=0.0, rescale=1.0):
+    lib().kvo_test_update_f32(_I64(w.size), _ptr(w, c_f32p), _ptr(g, c_f32p), _F(lr), _F(wd), _F(rescale))
+
+
+def adam_lr(lr, beta1, beta2, t):
+    return lib().kvo_adam_lr(lr, beta1, beta2, t)
+
+
+# ---------------------------------------------------------------------------
+# row-sparse
+# ---------------------------------------------------------------------------
+class RowSparse(object):
+    """(indices int64 sorted unique [nnz], data [nnz, L...], shape) -- MXNet's
+    row_sparse NDArray (include/mxnet/ndarray.h:61-66)."""
+
+    def __init__(self, indices, data, shape):
+        self.indices = np.ascontiguousarray(indices, np.int64)
+        self.data = np.ascontiguousarray(data, np.float32)
+        self.shape = tuple(shape)
+
+    @staticmethod
+    def from_dense(a):
+        a = np.asarray(a, np.float32)
+        nz = np.where(np.any(a.reshape(a.shape[0], -1) != 0, axis=1))[0]
+        return RowSparse(nz, a[nz], a.shape)
+
+    def todense(self):
+        out = np.zeros(self.shape, np.float32)
+        if len(self.indices):
+            out[self.indices] = self.data.reshape((len(self.indices),) + self.shape[1:])
+        return out
+
+    def copy(self):
+        return RowSparse(self.indices.copy(), self.data.copy(), self.shape)
+
+
+def unique(ids):
+    a = np.array(ids, dtype=np.int64, copy=True).reshape(-1)
+    n = lib().kvo_unique_i64(_ptr(a, c_i64p), _I64(a.size))
+    return a[:n].copy()
+
+
+def rsp_sum(rsps):
+    L = int(np.prod(rsps[0].shape[1:]))
+    n = len(rsps)
+    tot = sum(len(r.indices) for r in rsps)
+    out_idx = np.empty(max(tot, 1), np.int64)
+    out_val = np.empty((max(tot, 1), L), np.float32)
+    idxs = [r.indices for r in rsps]
+    vals = [r.data.reshape(-1, L) if len(r.indices) else np.zeros((0, L), np.float32) for r in rsps]
+    vals = [np.ascontiguousarray(v) for v in vals]
+    nnz = np.array([len(r.indices) for r in rsps], np.int64)
+    nu = lib().kvo_rsp_sum_f32(ctypes.c_int(n), _ptr_array(idxs), _ptr_array(vals), _ptr(nnz, c_i64p),
+                               _I64(L), _ptr(out_idx, c_i64p), _ptr(out_val, c_f32p))
+    return RowSparse(out_idx[:nu].copy(), out_val[:nu].copy(), rsps[0].shape)
+
+
+def sparse_retain(src, ids):
+    L = int(np.prod(src.shape[1:]))
+    ids = np.ascontiguousarray(ids, np.int64).reshape(-1)
+    out_idx = np.empty(max(len(ids), 1), np.int64)
+    out_val = np.empty((max(len(ids), 1), L), np.float32)
+    sval = np.ascontiguousarray(src.data.reshape(-1, L))
+    lib().kvo_sparse_retain_f32(_ptr(src.indices, c_i64p), _ptr(sval, c_f32p), _I64(len(src.indices)),
+                                _I64(L), _ptr(ids, c_i64p), _I64(len(ids)), _ptr(out_idx, c_i64p),
+                                _ptr(out_val, c_f32p))
+    return RowSparse(out_idx[:len(ids)].copy(), out_val[:len(ids)].copy(), src.shape)
+
+
+def sgd_rsp_lazy(w, grad, lr, wd=0.0, rescale=1.0, clip=None, mom=None, momentum=0.0):
+    L = int(np.prod(w.shape[1:]))
+    gv = np.ascontiguousarray(grad.data.reshape(-1, L))
+    if mom is None:
+        lib().kvo_sgd_rsp_lazy_f32(_ptr(w, c_f32p), _I64(L), _ptr(grad.indices, c_i64p), _ptr(gv, c_f32p),
+                                   _I64(len(grad.indices)), _F(lr), _F(wd), _F(rescale), _clip(clip))
+    else:
+        lib().kvo_sgd_mom_rsp_lazy_f32(_ptr(w, c_f32p), _ptr(mom, c_f32p), _I64(L),
+                                       _ptr(grad.indices, c_i64p), _ptr(gv, c_f32p),
+                                       _I64(len(grad.indices)), _F(lr), _F(wd), _F(momentum), _F(rescale),
+                                       _clip(clip))
+
+
+def adam_rsp_lazy(w, grad, mean, var, lr, wd=0.0, beta1=0.9, beta2=0.999, eps=1e-8, rescale=1.0, clip=None):
+    L = int(np.prod(w.shape[1:]))
+    gv = np.ascontiguousarray(grad.data.reshape(-1, L))
+    lib().kvo_adam_rsp_lazy_f32(_ptr(w, c_f32p), _ptr(mean, c_f32p), _ptr(var, c_f32p), _I64(L),
+                                _ptr(grad.indices, c_i64p), _ptr(gv, c_f32p), _I64(len(grad.indices)),
+                                _F(lr), _F(wd), _F(beta1), _F(beta2), _F(eps), _F(rescale), _clip(clip))
+
+
+# ---------------------------------------------------------------------------
+# gradient compression
+# ---------------------------------------------------------------------------
+def quantize_2bit(grad, residual, thr):
+    E = grad.size
+    out = np.zeros(((E + 15) // 16) * 4, np.uint8)
+    lib().kvo_quantize_2bit(_I64(E), _ptr(grad, c_f32p), _ptr(residual, c_f32p), _ptr(out, c_u8p), _F(thr))
+    return out
+
+
+def dequantize_2bit(comp, E, thr):
+    out = np.empty(E, np.float32)
+    lib().kvo_dequantize_2bit(_I64(E), _ptr(comp, c_u8p), _ptr(out, c_f32p), _F(thr))
+    return out
+
+
+def quantize_1bit(grad, residual, thr):
+    E = grad.size
+    out = np.zeros(((E + 31) // 32) * 4, np.uint8)
+    lib().kvo_quantize_1bit(_I64(E), _ptr(grad, c_f32p), _ptr(residual, c_f32p), _ptr(out, c_u8p), _F(thr))
+    return out
+
+
+def dequantize_1bit(comp, E, thr):
+    out = np.empty(E, np.float32)
+    lib().kvo_dequantize_1bit(_I64(E), _ptr(comp, c_u8p), _ptr(out, c_f32p), _F(thr))
+    return out
+
+
+# ---------------------------------------------------------------------------
+# Optimizer bookkeeping (python/mxnet/optimizer/optimizer.py) + Updater
+# ---------------------------------------------------------------------------
+class OracleOptimizer(object):
+    """Hyper-parameter bookkeeping of mx.optimizer.Optimizer: per-index update
+    counts (optimizer.py:_update_count), lr/wd multipliers (_get_lr/_get_wd),
+    rescale_grad, clip_gradient, multi_precision."""
+
+    def __init__(self, name, learning_rate=None, wd=0.0, rescale_grad=1.0, clip_gradient=None,
+                 momentum=0.0, beta1=0.9, beta2=0.999, epsilon=1e-8, eta=1.0, multi_precision=False,
+                 lr_mult=None, wd_mult=None, lazy_update=True):
+        self.name = name.lower()
+        if learning_rate is None:
+            learning_rate = 0.001 if self.name in ("adam", "adamw") else 0.01
+        self.lr = learning_rate
+        self.wd = wd
+        self.rescale_grad = rescale_grad
+        self.clip_gradient = clip_gradient
+        self.momentum = momentum
+        self.beta1, self.beta2, self.epsilon, self.eta = beta1, beta2, epsilon, eta
+        self.multi_precision = multi_precision
+        self.lr_mult = dict(lr_mult or {})
+        self.wd_mult = dict(wd_mult or {})
+        self.lazy_update = lazy_update
+        self.count = {}
+        self.states = {}
+
+    def _lr(self, index):
+        return self.lr * self.lr_mult.get(index, 1.0)
+
+    def _wd(self, index):
+        return self.wd * self.wd_mult.get(index, 1.0)
+
+    def update(self, index, weight, grad):
+        """Updater.__call__ (updater.py:39-93): create state on first sight, then one
+        fused step.  ``weight`` is a float32 ndarray updated in place; ``grad`` is a
+        float32 ndarray or RowSparse."""
+        self.count[index] = t = self.count.get(index, 0) + 1
+        lr, wd = self._lr(index), self._wd(index)
+        n = self.name
+        sparse = isinstance(grad, RowSparse)
+        if n == "test":
+            test_update(weight, grad if not sparse else grad.todense(), lr, wd, self.rescale_grad)
+        elif n == "sgd":
+            if self.momentum != 0.0 and index not in self.states:
+                self.states[index] = np.zeros_like(weight)
+            mom = self.states.get(index)
+            if sparse:
+                sgd_rsp_lazy(weight, grad, lr, wd, self.rescale_grad, self.clip_gradient, mom, self.momentum)
+            elif mom is None:
+                sgd_update(weight, grad, lr, wd, self.rescale_grad, self.clip_gradient)
+            else:
+                sgd_mom_update(weight, grad, mom, lr, wd, self.momentum, self.rescale_grad, self.clip_gradient)
+        elif n == "adam":
+            if index not in self.states:
+                self.states[index] = (np.zeros_like(weight), np.zeros_like(weight))
+            mean, var = self.states[index]
+            lr = adam_lr(lr, self.beta1, self.beta2, t)
+            if sparse:
+                adam_rsp_lazy(weight, grad, mean, var, lr, wd, self.beta1, self.beta2, self.epsilon,
+                              self.rescale_grad, self.clip_gradient)
+            else:
+                adam_update(weight, grad, mean, var, lr, wd, self.beta1, self.beta2, self.epsilon,
+                            self.rescale_grad, self.clip_gradient)
+        elif n == "adamw":
+            if index not in self.states:
+                self.states[index] = (np.zeros_like(weight), np.zeros_like(weight))
+            mean, var = self.states[index]
+            mp_adamw_update(None, 0, weight, mean, var, grad, lr, self.eta, wd, self.beta1, self.beta2,
+                            self.epsilon, self.rescale_grad, self.clip_gradient)
+        else:
+            raise ValueError("unknown optimizer " + n)
+
+
+class OracleKVStore(object):
+    """numpy model of KVStoreLocal (kvstore_local.h).  ``type`` decides the reduce
+    association: names containing 'device' use CommDevice order, others CommCPU
+    (kvstore.cc:42-85)."""
+
+    def __init__(self, type="local"):
+        self.type = type
+        self.device = "device" in type.lower()
+        self.local = {}
+        self.key_type = None
+        self.updater = None
+        self.optimizer = None
+        self.nthreads = 4
+
+    # -- helpers -----------------------------------------------------------
+    def _set_key_type(self, k):
+        kt = str if isinstance(k, str) else int
+        if self.key_type is None:
+            self.key_type = kt
+        if self.key_type is not kt:
+            raise ValueError("Mixed key types are not allowed")  # kvstore_local.h:344-347
+
+    @staticmethod
+    def _flatten(keys, vals):
+        """_ctype_key_value (python/mxnet/kvstore/base.py:32-65): key-major flattening."""
+        if isinstance(keys, (list, tuple)):
+            assert len(keys) == len(vals)
+            ks, vs = [], []
+            for k, v in zip(keys, vals):
+                k2, v2 = OracleKVStore._flatten(k, v)
+                ks += k2
+                vs += v2
+            return ks, vs
+        if isinstance(vals, (np.ndarray, RowSparse)):
+            return [keys], [vals]
+        return [keys] * len(vals), list(vals)
+
+    @staticmethod
+    def _group(keys, vals):
+        """GroupKVPairs (kvstore_local.h:440-469): sort by key, group equal keys."""
+        order = sorted(range(len(keys)), key=lambda i: keys[i])
+        uniq, grouped = [], []
+        for i in order:
+            if not uniq or keys[i] != uniq[-1]:
+                uniq.append(keys[i])
+                grouped.append([vals[i]])
+            else:
+                grouped[-1].append(vals[i])
+        return uniq, grouped
+
+    def _reduce(self, vals):
+        if len(vals) == 1:            # comm.h:128-131 / :514-516
+            return vals[0]
+        if isinstance(vals[0], RowSparse):
+            return rsp_sum(vals)
+        if self.device:
+            return sum_device(vals)
+        return sum_cpu(vals, self.nthreads).reshape(vals[0].shape)
+
+    # -- API ---------------------------------------------------------------
+    def init(self, key, value):
+        ks, vs = self._flatten(key, value)
+        for k, v in zip(ks, vs):
+            self._set_key_type(k)
+            if k in self.local:
+                raise ValueError("duplicate init of key %s" % str(k))   # kvstore_local.h:230-233
+            self.local[k] = v.copy()
+
+    def set_updater(self, fn):
+        self.updater = fn
+
+    def set_optimizer(self, opt):
+        self.optimizer = opt
+        self.updater = lambda k, recv, local: opt.update(k, local, recv)
+
+    def push(self, key, value, priority=0):
+        ks, vs = self._flatten(key, value)
+        for k in ks:
+            self._set_key_type(k)
+        uniq, grouped = self._group(ks, vs)
+        for k, g in zip(uniq, grouped):
+            merged = self._reduce(g)
+            if k not in self.local:
+                raise KeyError("key %s has not been inited" % str(k))
+            if self.updater is not None:
+                local = self.local[k]
+                if isinstance(local, RowSparse):
+                    dense = local.todense()
+                    self.updater(k, merged, dense)
+                    self.local[k] = RowSparse.from_dense(dense)
+                else:
+                    self.updater(k, merged, local)
+            else:
+                self.local[k] = merged.copy()     # kvstore_local.h:279-284
+
+    def pull(self, key, out, priority=0, ignore_sparse=True):
+        ks, vs = self._flatten(key, out)
+        for k in ks:
+            self._set_key_type(k)
+        uniq, grouped = self._group(ks, vs)
+        for k, g in zip(uniq, grouped):
+            if k not in self.local:
+                raise KeyError("key %s has not been inited" % str(k))
+            src = self.local[k]
+            for o in g:
+                if isinstance(o, RowSparse):
+                    if ignore_sparse:
+                        continue                  # kvstore_local.h:396-407
+                    s = src if isinstance(src, RowSparse) else RowSparse.from_dense(src)
+                    o.indices, o.data = s.indices.copy(), s.data.copy()
+                else:
+                    o[...] = src.todense() if isinstance(src, RowSparse) else src
+
+    def pushpull(self, key, value, out=None, priority=0):
+        self.push(key, value, priority)
+        self.pull(key, out if out is not None else value, priority)
+
+    def broadcast(self, key, value, out, priority=0):
+        self.init(key, value)
+        self.pull(key, out, priority)
+
+    def row_sparse_pull(self, key, out, row_ids, priority=0):
+        ks, vs = self._flatten(key, out)
+        _, rs = self._flatten(key, row_ids)
+        for k, o, r in zip(ks, vs, rs):
+            self._set_key_type(k)
+            if not isinstance(o, RowSparse):
+                raise ValueError("Expected row_sparse storage type for row_sparse_pull values")
+            src = self.local[k]
+            if not isinstance(src, RowSparse):
+                raise ValueError("PullRowSparse expects row_sparse src NDArray")
+            ret = sparse_retain(src, unique(r))
+            o.indices, o.data = ret.indices, ret.data.reshape((len(ret.indices),) + src.shape[1:])

@@ -1,0 +1,186 @@
+/*
+ * mxkv_b200.h -- C ABI of the B200-native KVStore engine.
+ *
+ * Drop-in boundary: every MX* symbol below has the signature, argument meaning and
+ * error behaviour (0 = ok, -1 = error, message via MXGetLastError(), never throws) of
+ * the function of the same name in the reference's include/mxnet/c_api.h, so a language
+ * binding that today resolves these symbols in libmxnet.so can resolve them here
+ * (INTEGRATION.md shows the ctypes side).  The reference line each one replaces is
+ * cited next to it.  MXKVB200* symbols are extensions that have no reference
+ * counterpart (fused optimizer registration, stream hand-off, one-process-per-GPU
+ * bootstrap, symmetric allocation).
+ *
+ * Plain C: opaque handles, pointers and sizes only.
+ */
+#ifndef MXKV_B200_H_
+#define MXKV_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+#ifndef __cplusplus
+#include <stdbool.h>
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MXKV_DLL __attribute__((visibility("default")))
+
+typedef void* NDArrayHandle;           /* c_api.h:67  */
+typedef void* KVStoreHandle;           /* c_api.h:93  */
+typedef void* DLManagedTensorHandle;   /* c_api.h:108 */
+typedef uint32_t mx_uint;
+
+/* ---- errors / library info ---------------------------------------------- */
+MXKV_DLL const char* MXGetLastError(void);                           /* c_api.h:233 */
+MXKV_DLL int MXGetGPUCount(int* out);                                /* c_api.h:502 */
+MXKV_DLL int MXGetVersion(int* out);                                 /* c_api.h:528 */
+
+/* ---- NDArray (the subset the KVStore path needs) ------------------------ */
+/* dev_type: 1 cpu, 2 gpu, 3 cpu_pinned (include/mxnet/base.h:94-99); dtype: mshadow type flag
+ * (3rdparty/mshadow/mshadow/base.h:352-366): 0 f32, 1 f64, 2 f16, 3 u8, 4 i32, 5 i8, 6 i64, 12 bf16 */
+MXKV_DLL int MXNDArrayCreateNone(NDArrayHandle* out);                /* c_api.h:576 */
+MXKV_DLL int MXNDArrayCreate(const uint32_t* shape, uint32_t ndim, int dev_type, int dev_id,
+                             int delay_alloc, int dtype, NDArrayHandle* out);            /* c_api.h:592 */
+MXKV_DLL int MXNDArrayCreate64(const int64_t* shape, int ndim, int dev_type, int dev_id,
+                               int delay_alloc, int dtype, NDArrayHandle* out);          /* c_api.h:615 */
+/* storage_type 1 = row_sparse (include/mxnet/ndarray.h:61-66); aux_shape[0] = row capacity */
+MXKV_DLL int MXNDArrayCreateSparseEx64(int storage_type, const int64_t* shape, int ndim, int dev_type,
+                                       int dev_id, int delay_alloc, int dtype, uint32_t num_aux,
+                                       int* aux_type, int* aux_ndims, const int64_t* aux_shape,
+                                       NDArrayHandle* out);                              /* c_api.h:674 */
+MXKV_DLL int MXNDArrayFree(NDArrayHandle handle);                                        /* c_api.h:842 */
+MXKV_DLL int MXNDArraySyncCopyFromCPU(NDArrayHandle handle, const void* data, size_t size); /* c_api.h:778 */
+MXKV_DLL int MXNDArraySyncCopyToCPU(NDArrayHandle handle, void* data, size_t size);       /* c_api.h:792 */
+/* i = -1: data, i >= 0: aux array i of a sparse source (c_api.h:803) */
+MXKV_DLL int MXNDArraySyncCopyFromNDArray(NDArrayHandle handle_dst, const NDArrayHandle handle_src,
+                                          const int i);
+MXKV_DLL int MXNDArrayWaitToRead(NDArrayHandle handle);                                  /* c_api.h:820 */
+MXKV_DLL int MXNDArrayWaitToWrite(NDArrayHandle handle);                                 /* c_api.h:828 */
+MXKV_DLL int MXNDArrayWaitAll(void);                                                     /* c_api.h:835 */
+MXKV_DLL int MXNDArrayGetStorageType(NDArrayHandle handle, int* out_storage_type);       /* c_api.h:903 */
+MXKV_DLL int MXNDArrayGetShape(NDArrayHandle handle, int* out_dim, const int** out_pdata);       /* c_api.h:942 */
+MXKV_DLL int MXNDArrayGetShape64(NDArrayHandle handle, int* out_dim, const int64_t** out_pdata); /* c_api.h:955 */
+MXKV_DLL int MXNDArrayGetData(NDArrayHandle handle, void** out_pdata);                   /* c_api.h:965 */
+MXKV_DLL int MXNDArrayToDLPack(NDArrayHandle handle, DLManagedTensorHandle* out_dlpack); /* c_api.h:976 */
+MXKV_DLL int MXNDArrayFromDLPack(DLManagedTensorHandle dlpack, const bool transient_handle,
+                                 NDArrayHandle* out_handle);                             /* c_api.h:993 */
+MXKV_DLL int MXNDArrayCallDLPackDeleter(DLManagedTensorHandle dlpack);                   /* c_api.h:1002 */
+MXKV_DLL int MXNDArrayGetDType(NDArrayHandle handle, int* out_dtype);                    /* c_api.h:1010 */
+MXKV_DLL int MXNDArrayGetAuxType(NDArrayHandle handle, uint32_t i, int* out_type);       /* c_api.h:1022 */
+MXKV_DLL int MXNDArrayGetAuxNDArray(NDArrayHandle handle, uint32_t i, NDArrayHandle* out); /* c_api.h:1046 */
+MXKV_DLL int MXNDArrayGetDataNDArray(NDArrayHandle handle, NDArrayHandle* out);          /* c_api.h:1066 */
+MXKV_DLL int MXNDArrayGetContext(NDArrayHandle handle, int* out_dev_type, int* out_dev_id); /* c_api.h:1075 */
+MXKV_DLL int MXNDArrayReshape64(NDArrayHandle handle, int ndim, int64_t* dims, bool reverse,
+                                NDArrayHandle* out);                                     /* c_api.h:927 */
+
+/* ---- KVStore (c_api.h Part 6, :2391-2825; impl src/c_api/c_api.cc:2771-3204) --- */
+MXKV_DLL int MXKVStoreCreate(const char* type, KVStoreHandle* out);                      /* c_api.h:2402 */
+MXKV_DLL int MXKVStoreSetGradientCompression(KVStoreHandle handle, uint32_t num_params,
+                                             const char** keys, const char** vals);      /* c_api.h:2412 */
+MXKV_DLL int MXKVStoreFree(KVStoreHandle handle);                                        /* c_api.h:2422 */
+MXKV_DLL int MXKVStoreInit(KVStoreHandle handle, uint32_t num, const int* keys, NDArrayHandle* vals);      /* :2431 */
+MXKV_DLL int MXKVStoreInitEx(KVStoreHandle handle, uint32_t num, const char** keys, NDArrayHandle* vals);  /* :2444 */
+MXKV_DLL int MXKVStorePush(KVStoreHandle handle, uint32_t num, const int* keys, NDArrayHandle* vals,
+                           int priority);                                                /* c_api.h:2458 */
+MXKV_DLL int MXKVStorePushEx(KVStoreHandle handle, uint32_t num, const char** keys, NDArrayHandle* vals,
+                             int priority);                                              /* c_api.h:2472 */
+MXKV_DLL int MXKVStorePullWithSparse(KVStoreHandle handle, uint32_t num, const int* keys,
+                                     NDArrayHandle* vals, int priority, bool ignore_sparse);   /* :2487 */
+MXKV_DLL int MXKVStorePullWithSparseEx(KVStoreHandle handle, uint32_t num, const char** keys,
+                                       NDArrayHandle* vals, int priority, bool ignore_sparse); /* :2503 */
+MXKV_DLL int MXKVStorePull(KVStoreHandle handle, uint32_t num, const int* keys, NDArrayHandle* vals,
+                           int priority);                                                /* c_api.h:2517 */
+MXKV_DLL int MXKVStorePullEx(KVStoreHandle handle, uint32_t num, const char** keys, NDArrayHandle* vals,
+                             int priority);                                              /* c_api.h:2531 */
+MXKV_DLL int MXKVStorePullRowSparse(KVStoreHandle handle, uint32_t num, const int* keys,
+                                    NDArrayHandle* vals, const NDArrayHandle* row_ids, int priority);   /* :2550 */
+MXKV_DLL int MXKVStorePullRowSparseEx(KVStoreHandle handle, uint32_t num, const char** keys,
+                                      NDArrayHandle* vals, const NDArrayHandle* row_ids, int priority); /* :2568 */
+MXKV_DLL int MXKVStoreBroadcast(KVStoreHandle handle, mx_uint vnum, const int* vkeys, mx_uint onum,
+                                const int* okeys, NDArrayHandle* vals, NDArrayHandle* outs,
+                                int priority);                                           /* c_api.h:2587 */
+MXKV_DLL int MXKVStoreBroadcastEx(KVStoreHandle handle, mx_uint vnum, const char** vkeys, mx_uint onum,
+                                  const char** okeys, NDArrayHandle* vals, NDArrayHandle* outs,
+                                  int priority);                                         /* c_api.h:2608 */
+MXKV_DLL int MXKVStorePushPull(KVStoreHandle handle, mx_uint vnum, const int* vkeys, mx_uint onum,
+                               const int* okeys, NDArrayHandle* vals, NDArrayHandle* outs,
+                               int priority);                                            /* c_api.h:2629 */
+MXKV_DLL int MXKVStorePushPullEx(KVStoreHandle handle, mx_uint vnum, const char** vkeys, mx_uint onum,
+                                 const char** okeys, NDArrayHandle* vals, NDArrayHandle* outs,
+                                 int priority);                                          /* c_api.h:2650 */
+/* updater callbacks: the callee must free both NDArray handles (c_api.h:2661) */
+typedef void(MXKVStoreUpdater)(int key, NDArrayHandle recv, NDArrayHandle local, void* handle);
+typedef void(MXKVStoreStrUpdater)(const char* key, NDArrayHandle recv, NDArrayHandle local, void* handle);
+MXKV_DLL int MXKVStoreSetUpdater(KVStoreHandle handle, MXKVStoreUpdater updater, void* updater_handle);  /* :2683 */
+MXKV_DLL int MXKVStoreSetUpdaterEx(KVStoreHandle handle, MXKVStoreUpdater updater,
+                                   MXKVStoreStrUpdater str_updater, void* updater_handle);               /* :2696 */
+MXKV_DLL int MXKVStoreGetType(KVStoreHandle handle, const char** type);                  /* c_api.h:2711 */
+MXKV_DLL int MXKVStoreGetRank(KVStoreHandle handle, int* ret);                           /* c_api.h:2724 */
+MXKV_DLL int MXKVStoreGetGroupSize(KVStoreHandle handle, int* ret);                      /* c_api.h:2735 */
+MXKV_DLL int MXKVStoreIsWorkerNode(int* ret);                                            /* c_api.h:2743 */
+MXKV_DLL int MXKVStoreIsServerNode(int* ret);                                            /* c_api.h:2751 */
+MXKV_DLL int MXKVStoreIsSchedulerNode(int* ret);                                         /* c_api.h:2759 */
+MXKV_DLL int MXKVStoreBarrier(KVStoreHandle handle);                                     /* c_api.h:2767 */
+MXKV_DLL int MXKVStoreSetBarrierBeforeExit(KVStoreHandle handle, const int barrier_before_exit); /* :2777 */
+MXKV_DLL int MXKVStoreGetNumDeadNode(KVStoreHandle handle, const int node_id, int* number,
+                                     const int timeout_sec);                             /* c_api.h:2822 */
+
+/* ---- B200 extensions ------------------------------------------------------ */
+/* Fused optimizer: what Python's Updater + sgd_update/adam_update ops do per key in the
+ * reference (python/mxnet/optimizer/updater.py:39-93) happens inside the reduce kernel.
+ * name: "sgd" | "adam" | "adamw" | "test"; kwargs use the reference's hyper-parameter names
+ * (learning_rate, wd, momentum, rescale_grad, clip_gradient, beta1, beta2, epsilon, eta,
+ * multi_precision). */
+MXKV_DLL int MXKVB200SetOptimizer(KVStoreHandle handle, const char* name, uint32_t num_params,
+                                  const char** keys, const char** vals);
+MXKV_DLL int MXKVB200SetLearningRate(KVStoreHandle handle, double lr);
+/* per-key multipliers (Optimizer.set_lr_mult / set_wd_mult); pass str_key = NULL for int keys */
+MXKV_DLL int MXKVB200SetOptimizerMult(KVStoreHandle handle, int key, const char* str_key,
+                                      float lr_mult, float wd_mult);
+/* which: 0 stored value, 1 fp32 master weight, 2 state0 (momentum | mean), 3 state1 (variance).
+ * Returns a NEW handle aliasing engine memory (free it with MXNDArrayFree); *out = NULL when the
+ * state does not exist. */
+MXKV_DLL int MXKVB200GetState(KVStoreHandle handle, int key, const char* str_key, int which,
+                              NDArrayHandle* out);
+MXKV_DLL int MXKVB200SetState(KVStoreHandle handle, int key, const char* str_key, int which,
+                              NDArrayHandle value);
+MXKV_DLL int MXKVB200GetUpdateCount(KVStoreHandle handle, int key, const char* str_key, int64_t* out);
+MXKV_DLL int MXKVB200SetUpdateCount(KVStoreHandle handle, int key, const char* str_key, int64_t count);
+
+/* Wrap device/host memory owned by the embedding framework (no copy, no ownership). */
+MXKV_DLL int MXKVB200NDArrayFromPtr(void* data, const int64_t* shape, int ndim, int dev_type, int dev_id,
+                                    int dtype, NDArrayHandle* out);
+/* Stream the embedding framework computes on for GPU dev_id (default: the legacy default
+ * stream).  Engine work is ordered after what is queued there at call time. */
+MXKV_DLL int MXKVB200SetStream(int dev_id, void* cuda_stream);
+/* The engine's own CUDA stream for GPU dev_id (cudaStream_t), e.g. to record timing events on the
+ * stream the kernels are launched on. */
+MXKV_DLL int MXKVB200GetEngineStream(int dev_id, void** out);
+/* auto_fence = 1 (default): after every call the framework stream waits for the engine stream.
+ * 0: the caller issues MXKVB200Fence itself (one stream-wait per training step instead of one
+ * per key; nothing blocks the host either way). */
+MXKV_DLL int MXKVB200SetAutoFence(int auto_fence);
+MXKV_DLL int MXKVB200Fence(int dev_id);
+MXKV_DLL int MXKVB200GetLaunchCount(int64_t* out);
+MXKV_DLL int MXKVB200SetTwoShotBytes(int64_t bytes);
+
+/* [begin, end) of the elements rank `rank` of `world` reduces and updates for a key of `size`
+ * elements on the sharded (two-shot) path.  Pure host function. */
+MXKV_DLL int MXKVB200ShardRange(int64_t size, int world, int rank, int64_t* begin, int64_t* end);
+
+/* One process per GPU.  allgather(send, bytes, recv, ctx) must gather `bytes` from every rank
+ * into recv (rank-major) on the host and return 0; it is used for bootstrap only (IPC handles,
+ * allocation agreement), never on the data path. */
+typedef int (*MXKVB200AllGatherFn)(const void* send, size_t bytes, void* recv, void* ctx);
+MXKV_DLL int MXKVB200CommInit(int rank, int world, int dev_id, MXKVB200AllGatherFn allgather, void* ctx);
+MXKV_DLL int MXKVB200CommDestroy(void);
+/* Collective: every rank calls it in the same order with the same shape.  The array lives in the
+ * peer-mapped arena, so push/pushpull read and write it over NVLink without staging. */
+MXKV_DLL int MXKVB200NDArrayCreateSymmetric(const int64_t* shape, int ndim, int dtype, NDArrayHandle* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* MXKV_B200_H_ */

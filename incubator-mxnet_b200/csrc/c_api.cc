@@ -1,0 +1,568 @@
+// c_api.cc -- extern "C" shims: marshal C arrays into the engine and translate exceptions
+// into the 0 / -1 + MXGetLastError() contract (API_BEGIN/API_END,
+// include/mxnet/c_api_error.h:40-58; KVStore marshalling src/c_api/c_api.cc:2771-3204).
+#include "../../include/mxkv_b200.h"
+#include <algorithm>
+#include <cstring>
+#include "dlpack_abi.h"
+#include "kvstore.h"
+
+using namespace mxkv;
+
+#define API_BEGIN() try {
+#define API_END()                                                      \
+  } catch (const std::exception& e) {                                  \
+    ::mxkv::SetLastError(e.what());                                    \
+    return -1;                                                         \
+  } catch (...) {                                                      \
+    ::mxkv::SetLastError("unknown C++ exception");                     \
+    return -1;                                                         \
+  }                                                                    \
+  return 0;
+
+namespace {
+struct NDHandle : public NDArray {
+  // per-handle scratch for MXNDArrayGetShape* return pointers (the reference keeps them in
+  // thread-local storage, MXAPIThreadLocalEntry)
+  std::vector<int> shape32;
+  std::vector<int64_t> shape64;
+  explicit NDHandle(const NDArray& a) : NDArray(a) {}
+  NDHandle() {}
+};
+inline NDHandle* ND(NDArrayHandle h) {
+  MXKV_CHECK(h != nullptr) << "null NDArrayHandle";
+  return static_cast<NDHandle*>(h);
+}
+inline KVStore* KV(KVStoreHandle h) {
+  MXKV_CHECK(h != nullptr) << "null KVStoreHandle";
+  return static_cast<KVStore*>(h);
+}
+std::vector<NDArray> Vals(NDArrayHandle* vals, uint32_t n) {
+  std::vector<NDArray> v(n);
+  for (uint32_t i = 0; i < n; ++i) v[i] = *ND(vals[i]);
+  return v;
+}
+std::vector<NDArray*> Outs(NDArrayHandle* vals, uint32_t n) {
+  std::vector<NDArray*> v(n);
+  for (uint32_t i = 0; i < n; ++i) v[i] = ND(vals[i]);
+  return v;
+}
+std::vector<int> IKeys(const int* keys, uint32_t n) { return std::vector<int>(keys, keys + n); }
+std::vector<std::string> SKeys(const char** keys, uint32_t n) {
+  std::vector<std::string> v(n);
+  for (uint32_t i = 0; i < n; ++i) v[i] = keys[i];
+  return v;
+}
+}  // namespace
+
+extern "C" {
+
+const char* MXGetLastError(void) { return ::mxkv::GetLastError(); }
+
+int MXGetGPUCount(int* out) {
+  API_BEGIN();
+  *out = Runtime::Get()->NumDevices();
+  API_END();
+}
+
+int MXGetVersion(int* out) {
+  API_BEGIN();
+  *out = 20000;   // MXNET_VERSION of the reference snapshot (include/mxnet/base.h:62-68)
+  API_END();
+}
+
+// ---------------------------------------------------------------------------
+// NDArray
+// ---------------------------------------------------------------------------
+int MXNDArrayCreateNone(NDArrayHandle* out) {
+  API_BEGIN();
+  *out = new NDHandle();
+  API_END();
+}
+
+int MXNDArrayCreate64(const int64_t* shape, int ndim, int dev_type, int dev_id, int delay_alloc, int dtype,
+                      NDArrayHandle* out) {
+  API_BEGIN();
+  (void)delay_alloc;
+  std::vector<int64_t> s(shape, shape + ndim);
+  *out = new NDHandle(NDArray::Empty(s, Context{dev_type, dev_id}, dtype));
+  API_END();
+}
+
+int MXNDArrayCreate(const uint32_t* shape, uint32_t ndim, int dev_type, int dev_id, int delay_alloc, int dtype,
+                    NDArrayHandle* out) {
+  std::vector<int64_t> s(shape, shape + ndim);
+  return MXNDArrayCreate64(s.data(), static_cast<int>(ndim), dev_type, dev_id, delay_alloc, dtype, out);
+}
+
+int MXNDArrayCreateSparseEx64(int storage_type, const int64_t* shape, int ndim, int dev_type, int dev_id,
+                              int delay_alloc, int dtype, uint32_t num_aux, int* aux_type, int* aux_ndims,
+                              const int64_t* aux_shape, NDArrayHandle* out) {
+  API_BEGIN();
+  (void)delay_alloc;
+  MXKV_CHECK(storage_type == kRowSparseStorage) << "only row_sparse sparse arrays are supported (got stype "
+                                                << storage_type << ")";
+  MXKV_CHECK(num_aux == 1) << "row_sparse has exactly one aux array";
+  MXKV_CHECK(aux_type == nullptr || aux_type[0] == kInt64) << "row_sparse indices must be int64";
+  std::vector<int64_t> s(shape, shape + ndim);
+  int64_t cap = 0;
+  if (aux_ndims != nullptr && aux_ndims[0] >= 1 && aux_shape != nullptr) cap = aux_shape[0];
+  if (cap <= 0) cap = s.empty() ? 0 : s[0];
+  *out = new NDHandle(NDArray::EmptyRowSparse(s, Context{dev_type, dev_id}, dtype, cap));
+  API_END();
+}
+
+int MXNDArrayFree(NDArrayHandle handle) {
+  API_BEGIN();
+  delete static_cast<NDHandle*>(handle);
+  API_END();
+}
+
+int MXNDArraySyncCopyFromCPU(NDArrayHandle handle, const void* data, size_t size) {
+  API_BEGIN();
+  ND(handle)->SyncCopyFromCPU(data, size);
+  API_END();
+}
+
+int MXNDArraySyncCopyToCPU(NDArrayHandle handle, void* data, size_t size) {
+  API_BEGIN();
+  ND(handle)->SyncCopyToCPU(data, size);
+  API_END();
+}
+
+int MXNDArraySyncCopyFromNDArray(NDArrayHandle handle_dst, const NDArrayHandle handle_src, const int i) {
+  API_BEGIN();
+  NDHandle* dst = ND(handle_dst);
+  NDHandle* src = ND(handle_src);
+  NDArray s = *src;
+  if (src->stype() == kRowSparseStorage) s = (i < 0) ? src->data_nd() : src->aux_idx();
+  NDArray d = *dst;
+  if (dst->stype() == kRowSparseStorage) {
+    // filling a row_sparse destination: i < 0 data, i >= 0 indices; the row count follows the source
+    const int64_t rows = s.shape().empty() ? 0 : s.shape()[0];
+    MXKV_CHECK(rows <= dst->cap_rows()) << "row_sparse destination holds " << dst->cap_rows() << " rows, source has "
+                                       << rows;
+    dst->set_nnz(rows);
+    d = (i < 0) ? dst->data_nd() : dst->aux_idx();
+  }
+  CopyFromTo(s.Reshape({s.size()}), d.Reshape({d.size()}));
+  d.WaitToRead();
+  API_END();
+}
+
+int MXNDArrayWaitToRead(NDArrayHandle handle) {
+  API_BEGIN();
+  ND(handle)->WaitToRead();
+  API_END();
+}
+
+int MXNDArrayWaitToWrite(NDArrayHandle handle) {
+  API_BEGIN();
+  ND(handle)->WaitToWrite();
+  API_END();
+}
+
+int MXNDArrayWaitAll(void) {
+  API_BEGIN();
+  Runtime::Get()->WaitAll();
+  API_END();
+}
+
+int MXNDArrayGetStorageType(NDArrayHandle handle, int* out_storage_type) {
+  API_BEGIN();
+  NDHandle* a = ND(handle);
+  *out_storage_type = a->is_none() ? kUndefinedStorage : a->stype();
+  API_END();
+}
+
+int MXNDArrayGetShape64(NDArrayHandle handle, int* out_dim, const int64_t** out_pdata) {
+  API_BEGIN();
+  NDHandle* a = ND(handle);
+  a->shape64 = a->shape();
+  *out_dim = static_cast<int>(a->shape64.size());
+  *out_pdata = a->shape64.data();
+  API_END();
+}
+
+int MXNDArrayGetShape(NDArrayHandle handle, int* out_dim, const int** out_pdata) {
+  API_BEGIN();
+  NDHandle* a = ND(handle);
+  a->shape32.assign(a->shape().begin(), a->shape().end());
+  *out_dim = static_cast<int>(a->shape32.size());
+  *out_pdata = a->shape32.data();
+  API_END();
+}
+
+int MXNDArrayGetData(NDArrayHandle handle, void** out_pdata) {
+  API_BEGIN();
+  *out_pdata = ND(handle)->data();
+  API_END();
+}
+
+int MXNDArrayToDLPack(NDArrayHandle handle, DLManagedTensorHandle* out_dlpack) {
+  API_BEGIN();
+  *out_dlpack = ND(handle)->ToDLPack();
+  API_END();
+}
+
+int MXNDArrayFromDLPack(DLManagedTensorHandle dlpack, const bool transient_handle, NDArrayHandle* out_handle) {
+  API_BEGIN();
+  *out_handle = new NDHandle(NDArray::FromDLPack(static_cast<DLManagedTensor*>(dlpack), transient_handle));
+  API_END();
+}
+
+int MXNDArrayCallDLPackDeleter(DLManagedTensorHandle dlpack) {
+  API_BEGIN();
+  DLManagedTensor* t = static_cast<DLManagedTensor*>(dlpack);
+  if (t != nullptr && t->deleter != nullptr) t->deleter(t);
+  API_END();
+}
+
+int MXNDArrayGetDType(NDArrayHandle handle, int* out_dtype) {
+  API_BEGIN();
+  NDHandle* a = ND(handle);
+  *out_dtype = a->is_none() ? -1 : a->dtype();
+  API_END();
+}
+
+int MXNDArrayGetAuxType(NDArrayHandle handle, uint32_t i, int* out_type) {
+  API_BEGIN();
+  MXKV_CHECK(ND(handle)->stype() == kRowSparseStorage && i == 0) << "no such aux array";
+  *out_type = kInt64;
+  API_END();
+}
+
+int MXNDArrayGetAuxNDArray(NDArrayHandle handle, uint32_t i, NDArrayHandle* out) {
+  API_BEGIN();
+  MXKV_CHECK(ND(handle)->stype() == kRowSparseStorage && i == 0) << "no such aux array";
+  *out = new NDHandle(ND(handle)->aux_idx());
+  API_END();
+}
+
+int MXNDArrayGetDataNDArray(NDArrayHandle handle, NDArrayHandle* out) {
+  API_BEGIN();
+  NDHandle* a = ND(handle);
+  *out = new NDHandle(a->stype() == kRowSparseStorage ? a->data_nd() : *a);
+  API_END();
+}
+
+int MXNDArrayGetContext(NDArrayHandle handle, int* out_dev_type, int* out_dev_id) {
+  API_BEGIN();
+  NDHandle* a = ND(handle);
+  if (a->is_none()) { *out_dev_type = 0; *out_dev_id = 0; }
+  else { *out_dev_type = a->ctx().dev_type; *out_dev_id = a->ctx().dev_id; }
+  API_END();
+}
+
+int MXNDArrayReshape64(NDArrayHandle handle, int ndim, int64_t* dims, bool reverse, NDArrayHandle* out) {
+  API_BEGIN();
+  (void)reverse;
+  std::vector<int64_t> s(dims, dims + ndim);
+  NDHandle* a = ND(handle);
+  int64_t known = 1, unknown = -1;
+  for (int i = 0; i < ndim; ++i) {
+    if (s[i] == -1) { MXKV_CHECK(unknown < 0) << "only one dimension can be inferred"; unknown = i; }
+    else known *= s[i];
+  }
+  if (unknown >= 0) { MXKV_CHECK(known > 0 && a->size() % known == 0) << "cannot infer dimension"; s[unknown] = a->size() / known; }
+  *out = new NDHandle(a->Reshape(s));
+  API_END();
+}
+
+// ---------------------------------------------------------------------------
+// KVStore
+// ---------------------------------------------------------------------------
+int MXKVStoreCreate(const char* type, KVStoreHandle* out) {
+  API_BEGIN();
+  MXKV_CHECK(type != nullptr) << "null kvstore type";
+  *out = new KVStore(type);
+  API_END();
+}
+
+int MXKVStoreSetGradientCompression(KVStoreHandle handle, uint32_t num_params, const char** keys,
+                                    const char** vals) {
+  API_BEGIN();
+  std::vector<std::pair<std::string, std::string>> kw;
+  for (uint32_t i = 0; i < num_params; ++i) kw.emplace_back(keys[i], vals[i]);
+  KV(handle)->SetGradientCompression(kw);
+  API_END();
+}
+
+int MXKVStoreFree(KVStoreHandle handle) {
+  API_BEGIN();
+  delete static_cast<KVStore*>(handle);
+  API_END();
+}
+
+int MXKVStoreInit(KVStoreHandle handle, uint32_t num, const int* keys, NDArrayHandle* vals) {
+  API_BEGIN();
+  KV(handle)->Init(IKeys(keys, num), Vals(vals, num));
+  API_END();
+}
+
+int MXKVStoreInitEx(KVStoreHandle handle, uint32_t num, const char** keys, NDArrayHandle* vals) {
+  API_BEGIN();
+  KV(handle)->Init(SKeys(keys, num), Vals(vals, num));
+  API_END();
+}
+
+int MXKVStorePush(KVStoreHandle handle, uint32_t num, const int* keys, NDArrayHandle* vals, int priority) {
+  API_BEGIN();
+  KV(handle)->Push(IKeys(keys, num), Vals(vals, num), priority);
+  API_END();
+}
+
+int MXKVStorePushEx(KVStoreHandle handle, uint32_t num, const char** keys, NDArrayHandle* vals, int priority) {
+  API_BEGIN();
+  KV(handle)->Push(SKeys(keys, num), Vals(vals, num), priority);
+  API_END();
+}
+
+int MXKVStorePullWithSparse(KVStoreHandle handle, uint32_t num, const int* keys, NDArrayHandle* vals, int priority,
+                            bool ignore_sparse) {
+  API_BEGIN();
+  KV(handle)->Pull(IKeys(keys, num), Outs(vals, num), priority, ignore_sparse);
+  API_END();
+}
+
+int MXKVStorePullWithSparseEx(KVStoreHandle handle, uint32_t num, const char** keys, NDArrayHandle* vals,
+                              int priority, bool ignore_sparse) {
+  API_BEGIN();
+  KV(handle)->Pull(SKeys(keys, num), Outs(vals, num), priority, ignore_sparse);
+  API_END();
+}
+
+int MXKVStorePull(KVStoreHandle handle, uint32_t num, const int* keys, NDArrayHandle* vals, int priority) {
+  return MXKVStorePullWithSparse(handle, num, keys, vals, priority, true);   // c_api.cc:2860-2875
+}
+
+int MXKVStorePullEx(KVStoreHandle handle, uint32_t num, const char** keys, NDArrayHandle* vals, int priority) {
+  return MXKVStorePullWithSparseEx(handle, num, keys, vals, priority, true);
+}
+
+int MXKVStorePullRowSparse(KVStoreHandle handle, uint32_t num, const int* keys, NDArrayHandle* vals,
+                           const NDArrayHandle* row_ids, int priority) {
+  API_BEGIN();
+  std::vector<std::pair<NDArray*, NDArray>> vr(num);
+  for (uint32_t i = 0; i < num; ++i) vr[i] = {ND(vals[i]), *ND(row_ids[i])};
+  KV(handle)->PullRowSparse(IKeys(keys, num), vr, priority);
+  API_END();
+}
+
+int MXKVStorePullRowSparseEx(KVStoreHandle handle, uint32_t num, const char** keys, NDArrayHandle* vals,
+                             const NDArrayHandle* row_ids, int priority) {
+  API_BEGIN();
+  std::vector<std::pair<NDArray*, NDArray>> vr(num);
+  for (uint32_t i = 0; i < num; ++i) vr[i] = {ND(vals[i]), *ND(row_ids[i])};
+  KV(handle)->PullRowSparse(SKeys(keys, num), vr, priority);
+  API_END();
+}
+
+int MXKVStoreBroadcast(KVStoreHandle handle, mx_uint vnum, const int* vkeys, mx_uint onum, const int* okeys,
+                       NDArrayHandle* vals, NDArrayHandle* outs, int priority) {
+  API_BEGIN();
+  KV(handle)->Broadcast(IKeys(vkeys, vnum), IKeys(okeys, onum), Vals(vals, vnum), Outs(outs, onum), priority);
+  API_END();
+}
+
+int MXKVStoreBroadcastEx(KVStoreHandle handle, mx_uint vnum, const char** vkeys, mx_uint onum, const char** okeys,
+                         NDArrayHandle* vals, NDArrayHandle* outs, int priority) {
+  API_BEGIN();
+  KV(handle)->Broadcast(SKeys(vkeys, vnum), SKeys(okeys, onum), Vals(vals, vnum), Outs(outs, onum), priority);
+  API_END();
+}
+
+int MXKVStorePushPull(KVStoreHandle handle, mx_uint vnum, const int* vkeys, mx_uint onum, const int* okeys,
+                      NDArrayHandle* vals, NDArrayHandle* outs, int priority) {
+  API_BEGIN();
+  KV(handle)->PushPull(IKeys(vkeys, vnum), IKeys(okeys, onum), Vals(vals, vnum), Outs(outs, onum), priority);
+  API_END();
+}
+
+int MXKVStorePushPullEx(KVStoreHandle handle, mx_uint vnum, const char** vkeys, mx_uint onum, const char** okeys,
+                        NDArrayHandle* vals, NDArrayHandle* outs, int priority) {
+  API_BEGIN();
+  KV(handle)->PushPull(SKeys(vkeys, vnum), SKeys(okeys, onum), Vals(vals, vnum), Outs(outs, onum), priority);
+  API_END();
+}
+
+int MXKVStoreSetUpdater(KVStoreHandle handle, MXKVStoreUpdater updater, void* updater_handle) {
+  API_BEGIN();
+  KV(handle)->SetUpdater(reinterpret_cast<UpdaterFn>(updater), nullptr, updater_handle);
+  API_END();
+}
+
+int MXKVStoreSetUpdaterEx(KVStoreHandle handle, MXKVStoreUpdater updater, MXKVStoreStrUpdater str_updater,
+                          void* updater_handle) {
+  API_BEGIN();
+  KV(handle)->SetUpdater(reinterpret_cast<UpdaterFn>(updater), reinterpret_cast<StrUpdaterFn>(str_updater),
+                         updater_handle);
+  API_END();
+}
+
+int MXKVStoreGetType(KVStoreHandle handle, const char** type) {
+  API_BEGIN();
+  *type = KV(handle)->type().c_str();   // borrowed, lives as long as the store (c_api.cc:3113-3118)
+  API_END();
+}
+
+int MXKVStoreGetRank(KVStoreHandle handle, int* ret) {
+  API_BEGIN();
+  *ret = KV(handle)->rank();
+  API_END();
+}
+
+int MXKVStoreGetGroupSize(KVStoreHandle handle, int* ret) {
+  API_BEGIN();
+  *ret = KV(handle)->group_size();
+  API_END();
+}
+
+int MXKVStoreIsWorkerNode(int* ret) { *ret = 1; return 0; }       // kvstore.h:389-419: local stores are workers
+int MXKVStoreIsServerNode(int* ret) { *ret = 0; return 0; }
+int MXKVStoreIsSchedulerNode(int* ret) { *ret = 0; return 0; }
+
+int MXKVStoreBarrier(KVStoreHandle handle) {
+  API_BEGIN();
+  KV(handle)->Barrier();
+  API_END();
+}
+
+int MXKVStoreSetBarrierBeforeExit(KVStoreHandle handle, const int barrier_before_exit) {
+  API_BEGIN();
+  (void)KV(handle); (void)barrier_before_exit;
+  API_END();
+}
+
+int MXKVStoreGetNumDeadNode(KVStoreHandle handle, const int node_id, int* number, const int timeout_sec) {
+  API_BEGIN();
+  (void)KV(handle); (void)node_id; (void)timeout_sec;
+  *number = 0;   // kvstore.h:431-435: single-node stores have no dead nodes
+  API_END();
+}
+
+// ---------------------------------------------------------------------------
+// extensions
+// ---------------------------------------------------------------------------
+int MXKVB200SetOptimizer(KVStoreHandle handle, const char* name, uint32_t num_params, const char** keys,
+                         const char** vals) {
+  API_BEGIN();
+  std::vector<std::pair<std::string, std::string>> kw;
+  for (uint32_t i = 0; i < num_params; ++i) kw.emplace_back(keys[i], vals[i]);
+  KV(handle)->SetOptimizer(name, kw);
+  API_END();
+}
+
+int MXKVB200SetLearningRate(KVStoreHandle handle, double lr) {
+  API_BEGIN();
+  KV(handle)->SetLearningRate(lr);
+  API_END();
+}
+
+int MXKVB200SetOptimizerMult(KVStoreHandle handle, int key, const char* str_key, float lr_mult, float wd_mult) {
+  API_BEGIN();
+  KV(handle)->SetOptimizerMult(str_key != nullptr, key, str_key ? str_key : "", lr_mult, wd_mult);
+  API_END();
+}
+
+int MXKVB200GetState(KVStoreHandle handle, int key, const char* str_key, int which, NDArrayHandle* out) {
+  API_BEGIN();
+  NDArray a = KV(handle)->GetState(str_key != nullptr, key, str_key ? str_key : "", which);
+  *out = a.is_none() ? nullptr : new NDHandle(a);
+  API_END();
+}
+
+int MXKVB200SetState(KVStoreHandle handle, int key, const char* str_key, int which, NDArrayHandle value) {
+  API_BEGIN();
+  KV(handle)->SetState(str_key != nullptr, key, str_key ? str_key : "", which, *ND(value));
+  API_END();
+}
+
+int MXKVB200GetUpdateCount(KVStoreHandle handle, int key, const char* str_key, int64_t* out) {
+  API_BEGIN();
+  *out = KV(handle)->GetUpdateCount(str_key != nullptr, key, str_key ? str_key : "");
+  API_END();
+}
+
+int MXKVB200SetUpdateCount(KVStoreHandle handle, int key, const char* str_key, int64_t count) {
+  API_BEGIN();
+  KV(handle)->SetUpdateCount(str_key != nullptr, key, str_key ? str_key : "", count);
+  API_END();
+}
+
+int MXKVB200NDArrayFromPtr(void* data, const int64_t* shape, int ndim, int dev_type, int dev_id, int dtype,
+                           NDArrayHandle* out) {
+  API_BEGIN();
+  std::vector<int64_t> s(shape, shape + ndim);
+  if (dev_type == kGPU) Runtime::Get()->Dev(dev_id);
+  *out = new NDHandle(NDArray::FromExternal(data, s, Context{dev_type, dev_id}, dtype));
+  API_END();
+}
+
+int MXKVB200SetStream(int dev_id, void* cuda_stream) {
+  API_BEGIN();
+  Runtime::Get()->SetUserStream(dev_id, static_cast<cudaStream_t>(cuda_stream));
+  API_END();
+}
+
+int MXKVB200GetEngineStream(int dev_id, void** out) {
+  API_BEGIN();
+  *out = Runtime::Get()->Dev(dev_id).stream;
+  API_END();
+}
+
+int MXKVB200SetAutoFence(int auto_fence) {
+  API_BEGIN();
+  Runtime::Get()->auto_fence = auto_fence != 0;
+  API_END();
+}
+
+int MXKVB200Fence(int dev_id) {
+  API_BEGIN();
+  Runtime::Get()->Fence(dev_id);
+  API_END();
+}
+
+int MXKVB200GetLaunchCount(int64_t* out) {
+  API_BEGIN();
+  *out = Runtime::Get()->launches;
+  API_END();
+}
+
+int MXKVB200SetTwoShotBytes(int64_t bytes) {
+  API_BEGIN();
+  Runtime::Get()->twoshot_bytes = bytes;
+  API_END();
+}
+
+int MXKVB200ShardRange(int64_t size, int world, int rank, int64_t* begin, int64_t* end) {
+  API_BEGIN();
+  MXKV_CHECK(world >= 1 && rank >= 0 && rank < world && size >= 0) << "bad shard query";
+  const int64_t L = ShardLen(size, world);
+  *begin = std::min<int64_t>(size, L * rank);
+  *end = std::min<int64_t>(size, L * (rank + 1));
+  API_END();
+}
+
+int MXKVB200CommInit(int rank, int world, int dev_id, MXKVB200AllGatherFn allgather, void* ctx) {
+  API_BEGIN();
+  Runtime::Get()->InitProcessGroup(rank, world, dev_id, reinterpret_cast<AllGatherFn>(allgather), ctx);
+  API_END();
+}
+
+int MXKVB200CommDestroy(void) {
+  API_BEGIN();
+  Runtime::Get()->DestroyProcessGroup();
+  API_END();
+}
+
+int MXKVB200NDArrayCreateSymmetric(const int64_t* shape, int ndim, int dtype, NDArrayHandle* out) {
+  API_BEGIN();
+  ProcessGroup* pg = Runtime::Get()->pg();
+  std::vector<int64_t> s(shape, shape + ndim);
+  const int dev = pg ? pg->dev() : 0;
+  *out = new NDHandle(NDArray::Empty(s, Context{kGPU, dev}, dtype, /*symmetric=*/pg != nullptr));
+  API_END();
+}
+
+}  // extern "C"

@@ -1,0 +1,518 @@
+// kernels.cu -- sm_100a kernels of the KVStore gradient path.
+//
+// kv_dense_kernel: ONE kernel does what the reference spreads over
+//   n x CopyFromTo (cudaMemcpyPeerAsync, src/ndarray/ndarray_function.cu:68-99)
+//   + ElementwiseSum (src/ndarray/ndarray_function-inl.h:443-489)
+//   + the Python updater -> sgd_update / sgd_mom_update / mp_sgd_* / adam_update /
+//     _mp_adamw_update (src/operator/optimizer_op-inl.h, contrib/adamw-inl.h)
+//   + n x CopyFromTo broadcast (src/kvstore/comm.h:607-625):
+// every thread streams 16-byte vectors of the n gradient replicas straight from
+// the GPUs that own them (NVLink peer loads), sums them in the reference's
+// association order in fp32, applies the optimizer on the fp32 master and writes
+// the new weight to every destination replica (local or peer stores).  Ranks
+// rendezvous through flag words in peer-mapped signal pads; no host round trip,
+// no intermediate buffer, no second pass over HBM.
+//
+// Arithmetic uses __fmul_rn/__fadd_rn/... so ptxas cannot contract a*b+c into an
+// FMA: results are bit-identical to the CPU oracle (oracle/kv_oracle.c), which
+// restates the reference source operation by operation.
+#include "kernels.h"
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
+
+namespace mxkv {
+
+constexpr int kThreads = 512;
+
+// ---------------------------------------------------------------------------
+// memory helpers
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint4 ld16(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st16(void* p, const uint4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};"
+               :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void st_flag_volatile(uint32_t* p, uint32_t v) {
+  asm volatile("st.volatile.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_flag_volatile(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_flag_release(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_flag_acquire(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// ---------------------------------------------------------------------------
+// cross-GPU rendezvous.  Block b of every rank pairs with block b of every other
+// rank: thread i<world stores the block's next flag value into rank i's pad and
+// spins on the slot rank i writes in ours.  Separate start/end slots so a fast
+// rank's next start cannot overwrite a slow rank's pending end.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void barrier_start(const SyncArgs& s) {
+  const uint32_t flag = s.self[kSigFlagOff + blockIdx.x] + 1;
+  if (threadIdx.x < s.world) {
+    uint32_t* peer = s.peers[threadIdx.x] + kSigStartOff + blockIdx.x * kMaxRanks + s.rank;
+    const uint32_t* mine = s.self + kSigStartOff + blockIdx.x * kMaxRanks + threadIdx.x;
+    st_flag_volatile(peer, flag);
+    while (ld_flag_volatile(mine) != flag) {}
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) s.self[kSigFlagOff + blockIdx.x] = flag;
+}
+
+// release == true: this block stored into peer memory; make those stores visible
+// system-wide before signalling (two-shot all-gather half).
+__device__ __forceinline__ void barrier_end(const SyncArgs& s, bool release) {
+  __syncthreads();
+  const uint32_t flag = s.self[kSigFlagOff + blockIdx.x] + 1;
+  if (threadIdx.x < s.world) {
+    uint32_t* peer = s.peers[threadIdx.x] + kSigEndOff + blockIdx.x * kMaxRanks + s.rank;
+    const uint32_t* mine = s.self + kSigEndOff + blockIdx.x * kMaxRanks + threadIdx.x;
+    if (release) {
+      st_flag_release(peer, flag);
+      while (ld_flag_acquire(mine) != flag) {}
+    } else {
+      st_flag_volatile(peer, flag);
+      while (ld_flag_volatile(mine) != flag) {}
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) s.self[kSigFlagOff + blockIdx.x] = flag;
+}
+
+// ---------------------------------------------------------------------------
+// packets: a 16-byte vector or a single element, exposed as N floats
+// ---------------------------------------------------------------------------
+template <typename T> struct Cvt;
+template <> struct Cvt<float> {
+  __device__ static __forceinline__ float to(float v) { return v; }
+  __device__ static __forceinline__ float from(float v) { return v; }
+};
+template <> struct Cvt<__half> {
+  __device__ static __forceinline__ float to(__half v) { return __half2float(v); }
+  __device__ static __forceinline__ __half from(float v) { return __float2half_rn(v); }
+};
+template <> struct Cvt<__nv_bfloat16> {
+  __device__ static __forceinline__ float to(__nv_bfloat16 v) { return __bfloat162float(v); }
+  __device__ static __forceinline__ __nv_bfloat16 from(float v) { return __float2bfloat16_rn(v); }
+};
+
+__device__ __forceinline__ uint2 ld8(const void* p) {
+  uint2 v;
+  asm volatile("ld.global.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st8(void* p, const uint2& v) {
+  asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1,%2};" :: "l"(p), "r"(v.x), "r"(v.y) : "memory");
+}
+
+// Packet<T, N>: N consecutive elements (N*sizeof(T) in {16, 8} bytes, or N == 1)
+template <typename T, int N, int BYTES = N * sizeof(T)> struct Packet;
+template <typename T, int N_> struct Packet<T, N_, 16> {
+  static constexpr int N = N_;
+  uint4 raw;
+  __device__ __forceinline__ void load(const void* base, int64_t elem) {
+    raw = ld16(reinterpret_cast<const T*>(base) + elem);
+  }
+  __device__ __forceinline__ void unpack(float (&f)[N]) const {
+    const T* t = reinterpret_cast<const T*>(&raw);
+#pragma unroll
+    for (int i = 0; i < N; ++i) f[i] = Cvt<T>::to(t[i]);
+  }
+  __device__ static __forceinline__ void store(void* base, int64_t elem, const float (&f)[N]) {
+    uint4 v;
+    T* t = reinterpret_cast<T*>(&v);
+#pragma unroll
+    for (int i = 0; i < N; ++i) t[i] = Cvt<T>::from(f[i]);
+    st16(reinterpret_cast<T*>(base) + elem, v);
+  }
+};
+template <typename T, int N_> struct Packet<T, N_, 8> {
+  static constexpr int N = N_;
+  uint2 raw;
+  __device__ __forceinline__ void load(const void* base, int64_t elem) {
+    raw = ld8(reinterpret_cast<const T*>(base) + elem);
+  }
+  __device__ __forceinline__ void unpack(float (&f)[N]) const {
+    const T* t = reinterpret_cast<const T*>(&raw);
+#pragma unroll
+    for (int i = 0; i < N; ++i) f[i] = Cvt<T>::to(t[i]);
+  }
+  __device__ static __forceinline__ void store(void* base, int64_t elem, const float (&f)[N]) {
+    uint2 v;
+    T* t = reinterpret_cast<T*>(&v);
+#pragma unroll
+    for (int i = 0; i < N; ++i) t[i] = Cvt<T>::from(f[i]);
+    st8(reinterpret_cast<T*>(base) + elem, v);
+  }
+};
+template <typename T, int BYTES> struct Packet<T, 1, BYTES> {
+  static constexpr int N = 1;
+  T raw;
+  __device__ __forceinline__ void load(const void* base, int64_t elem) {
+    raw = reinterpret_cast<const T*>(base)[elem];
+  }
+  __device__ __forceinline__ void unpack(float (&f)[1]) const { f[0] = Cvt<T>::to(raw); }
+  __device__ static __forceinline__ void store(void* base, int64_t elem, const float (&f)[1]) {
+    reinterpret_cast<T*>(base)[elem] = Cvt<T>::from(f[0]);
+  }
+};
+
+// fp32 packets for master weights / optimizer state (N floats, N in {1,4,8})
+template <int N> __device__ __forceinline__ void ldf(const float* p, int64_t e, float (&f)[N]) {
+  if (N == 1) {
+    f[0] = p[e];
+  } else {
+#pragma unroll
+    for (int i = 0; i < N; i += 4) {
+      uint4 v = ld16(p + e + i);
+      f[i] = __uint_as_float(v.x); f[i + 1] = __uint_as_float(v.y);
+      f[i + 2] = __uint_as_float(v.z); f[i + 3] = __uint_as_float(v.w);
+    }
+  }
+}
+template <int N> __device__ __forceinline__ void stf(float* p, int64_t e, const float (&f)[N]) {
+  if (N == 1) {
+    p[e] = f[0];
+  } else {
+#pragma unroll
+    for (int i = 0; i < N; i += 4) {
+      uint4 v = make_uint4(__float_as_uint(f[i]), __float_as_uint(f[i + 1]),
+                           __float_as_uint(f[i + 2]), __float_as_uint(f[i + 3]));
+      st16(p + e + i, v);
+    }
+  }
+}
+
+struct Hyper {
+  float lr, wd, eta, rescale, clip, momentum, beta1, beta2, eps;
+};
+
+__device__ __forceinline__ float clipf(float x, float b) {   // mshadow_op::clip, mshadow_op.h:999-1009
+  return x > b ? b : (x < -b ? -b : x);
+}
+
+// one element of the fused update; returns the new weight.  Operation order is
+// the reference source's, see the OptKind comments in kernels.h.
+template <int OPT>
+__device__ __forceinline__ float update_one(float g, float w, float& s0, float& s1, const Hyper& h) {
+  if (OPT == OPT_SGD) {
+    float r = __fmul_rn(h.rescale, g);
+    if (h.clip >= 0.0f) r = clipf(r, h.clip);
+    r = __fadd_rn(r, __fmul_rn(h.wd, w));
+    return __fsub_rn(w, __fmul_rn(h.lr, r));
+  } else if (OPT == OPT_SGD_MOM) {
+    float r = __fmul_rn(h.rescale, g);
+    if (h.clip >= 0.0f) r = clipf(r, h.clip);
+    r = __fadd_rn(r, __fmul_rn(h.wd, w));
+    float m = __fmul_rn(s0, h.momentum);
+    m = __fsub_rn(m, __fmul_rn(h.lr, r));
+    s0 = m;
+    return __fadd_rn(w, m);
+  } else if (OPT == OPT_ADAM) {
+    float r = __fmul_rn(g, h.rescale);
+    if (h.clip >= 0.0f) r = clipf(r, h.clip);
+    r = __fadd_rn(r, __fmul_rn(w, h.wd));
+    const float m = __fadd_rn(__fmul_rn(h.beta1, s0), __fmul_rn(__fsub_rn(1.f, h.beta1), r));
+    const float v = __fadd_rn(__fmul_rn(h.beta2, s1),
+                              __fmul_rn(__fmul_rn(__fsub_rn(1.f, h.beta2), r), r));
+    s0 = m; s1 = v;
+    return __fsub_rn(w, __fdiv_rn(__fmul_rn(h.lr, m), __fadd_rn(__fsqrt_rn(v), h.eps)));
+  } else if (OPT == OPT_ADAMW) {
+    float sg = __fmul_rn(h.rescale, g);
+    if (h.clip >= 0.0f) sg = clipf(sg, h.clip);
+    const float m = __fadd_rn(__fmul_rn(h.beta1, s0), __fmul_rn(__fsub_rn(1.0f, h.beta1), sg));
+    const float v = __fadd_rn(__fmul_rn(h.beta2, s1),
+                              __fmul_rn(__fsub_rn(1.0f, h.beta2), __fmul_rn(sg, sg)));
+    s0 = m; s1 = v;
+    const float step = __fadd_rn(__fdiv_rn(__fmul_rn(h.lr, m), __fadd_rn(__fsqrt_rn(v), h.eps)),
+                                 __fmul_rn(h.wd, w));
+    return __fsub_rn(w, __fmul_rn(h.eta, step));
+  } else if (OPT == OPT_TEST) {
+    const float gr = __fmul_rn(h.rescale, g);
+    const float s = __fadd_rn(gr, __fmul_rn(h.wd, w));
+    return __fsub_rn(w, __fmul_rn(h.lr, s));
+  }
+  return g;  // OPT_NONE
+}
+
+// ---------------------------------------------------------------------------
+// one packet: gather n sources, sum in order, update, scatter
+// ---------------------------------------------------------------------------
+template <typename T, int OPT, bool MP, int N>
+__device__ __forceinline__ void process_packet(const TensorWork& tw, int64_t e, const Hyper& h,
+                                               int order, bool native_half_add) {
+  typedef Packet<T, N> P;
+  constexpr int kBatch = 4;
+  float acc[N];
+  float grp[N];
+  const int n = tw.n_src;
+  for (int k0 = 0; k0 < n; k0 += kBatch) {
+    P buf[kBatch];
+#pragma unroll
+    for (int j = 0; j < kBatch; ++j)
+      if (k0 + j < n) buf[j].load(tw.src[k0 + j], e);
+#pragma unroll
+    for (int j = 0; j < kBatch; ++j) {
+      const int k = k0 + j;
+      if (k < n) {
+        float x[N];
+        buf[j].unpack(x);
+        if (k == 0) {
+#pragma unroll
+          for (int i = 0; i < N; ++i) acc[i] = x[i];
+        } else if (order == ORDER_DEVICE) {
+#pragma unroll
+          for (int i = 0; i < N; ++i) {
+            float s = __fadd_rn(acc[i], x[i]);
+            if (native_half_add) s = Cvt<T>::to(Cvt<T>::from(s));
+            acc[i] = s;
+          }
+        } else {  // ORDER_COMMCPU: in0 += ((in1+in2)+in3)+in4 per group of four
+          const int pos = (k - 1) & 3;
+#pragma unroll
+          for (int i = 0; i < N; ++i) grp[i] = (pos == 0) ? x[i] : __fadd_rn(grp[i], x[i]);
+          if (pos == 3 || k == n - 1) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) acc[i] = __fadd_rn(acc[i], grp[i]);
+          }
+        }
+      }
+    }
+  }
+
+  float wnew[N];
+  if (OPT == OPT_NONE) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) wnew[i] = acc[i];
+  } else {
+    float w[N], s0[N], s1[N];
+    if (MP) {
+      ldf<N>(tw.w32, e, w);
+    } else {
+      P pw;
+      pw.load(tw.w, e);
+      pw.unpack(w);
+    }
+    if (OPT == OPT_SGD_MOM || OPT == OPT_ADAM || OPT == OPT_ADAMW) ldf<N>(tw.s0, e, s0);
+    if (OPT == OPT_ADAM || OPT == OPT_ADAMW) ldf<N>(tw.s1, e, s1);
+#pragma unroll
+    for (int i = 0; i < N; ++i) wnew[i] = update_one<OPT>(acc[i], w[i], s0[i], s1[i], h);
+    if (OPT == OPT_SGD_MOM || OPT == OPT_ADAM || OPT == OPT_ADAMW) stf<N>(tw.s0, e, s0);
+    if (OPT == OPT_ADAM || OPT == OPT_ADAMW) stf<N>(tw.s1, e, s1);
+    if (MP) stf<N>(tw.w32, e, wnew);
+  }
+  const int m = tw.n_out;
+  for (int j = 0; j < m; ++j) P::store(tw.out[j], e, wnew);
+}
+
+template <typename T, int OPT, bool MP>
+__global__ void __launch_bounds__(kThreads, 2)
+kv_dense_kernel(DenseLaunch L) {
+  __shared__ TensorWork tw;
+  const bool sync = L.sync.mode != SYNC_NONE;
+  if (sync) barrier_start(L.sync);
+
+  // 16-bit gradients with fp32 master/state: 4-element packets (8 B of gradient against
+  // 16 B of every fp32 stream) keep the kernel inside 64 registers.
+  constexpr int NV = (OPT != OPT_NONE && sizeof(T) == 2) ? 4 : 16 / sizeof(T);
+  const bool native_half_add = (sizeof(T) == 2) && !L.fp32_accum && (OPT == OPT_NONE);
+  int cur = -1;
+  for (int64_t c = blockIdx.x; c < L.total_chunks; c += gridDim.x) {
+    // chunk -> work entry (uniform across the block)
+    int lo = 0, hi = L.nworks - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (L.chunk_prefix[mid] <= c) lo = mid; else hi = mid - 1;
+    }
+    if (lo != cur) {
+      __syncthreads();
+      const uint4* src = reinterpret_cast<const uint4*>(L.works + lo);
+      uint4* dst = reinterpret_cast<uint4*>(&tw);
+      for (int i = threadIdx.x; i < static_cast<int>(sizeof(TensorWork) / 16); i += kThreads)
+        dst[i] = src[i];
+      __syncthreads();
+      cur = lo;
+    }
+    Hyper h;
+    h.lr = tw.lr; h.wd = tw.wd; h.eta = tw.eta;
+    h.rescale = L.rescale; h.clip = L.clip; h.momentum = L.momentum;
+    h.beta1 = L.beta1; h.beta2 = L.beta2; h.eps = L.eps;
+
+    const int64_t cb = tw.begin + (c - L.chunk_prefix[lo]) * kChunkElems;
+    const int64_t ce = (cb + kChunkElems < tw.end) ? cb + kChunkElems : tw.end;
+    if (tw.pad_ & 1) {  // every pointer 16-byte aligned and begin % 8 == 0
+      const int64_t nvec = (ce - cb) / NV;
+      for (int64_t v = threadIdx.x; v < nvec; v += kThreads)
+        process_packet<T, OPT, MP, NV>(tw, cb + v * NV, h, L.order, native_half_add);
+      for (int64_t e = cb + nvec * NV + threadIdx.x; e < ce; e += kThreads)
+        process_packet<T, OPT, MP, 1>(tw, e, h, L.order, native_half_add);
+    } else {
+      for (int64_t e = cb + threadIdx.x; e < ce; e += kThreads)
+        process_packet<T, OPT, MP, 1>(tw, e, h, L.order, native_half_add);
+    }
+  }
+
+  if (sync) barrier_end(L.sync, L.sync.mode == SYNC_WRITE_PEERS);
+}
+
+// ---------------------------------------------------------------------------
+// plain typed sum for the dtypes the reference's ElementwiseSum also accepts
+// (MSHADOW_TYPE_SWITCH: f64, u8, i32, i8, i64); native arithmetic, device order.
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kThreads, 2)
+kv_sum_typed_kernel(DenseLaunch L) {
+  __shared__ TensorWork tw;
+  const bool sync = L.sync.mode != SYNC_NONE;
+  if (sync) barrier_start(L.sync);
+  int cur = -1;
+  for (int64_t c = blockIdx.x; c < L.total_chunks; c += gridDim.x) {
+    int lo = 0, hi = L.nworks - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (L.chunk_prefix[mid] <= c) lo = mid; else hi = mid - 1;
+    }
+    if (lo != cur) {
+      __syncthreads();
+      const uint4* src = reinterpret_cast<const uint4*>(L.works + lo);
+      uint4* dst = reinterpret_cast<uint4*>(&tw);
+      for (int i = threadIdx.x; i < static_cast<int>(sizeof(TensorWork) / 16); i += kThreads)
+        dst[i] = src[i];
+      __syncthreads();
+      cur = lo;
+    }
+    const int64_t cb = tw.begin + (c - L.chunk_prefix[lo]) * kChunkElems;
+    const int64_t ce = (cb + kChunkElems < tw.end) ? cb + kChunkElems : tw.end;
+    for (int64_t e = cb + threadIdx.x; e < ce; e += kThreads) {
+      T acc = reinterpret_cast<const T*>(tw.src[0])[e];
+      for (int k = 1; k < tw.n_src; ++k) acc = static_cast<T>(acc + reinterpret_cast<const T*>(tw.src[k])[e]);
+      for (int j = 0; j < tw.n_out; ++j) reinterpret_cast<T*>(tw.out[j])[e] = acc;
+    }
+  }
+  if (sync) barrier_end(L.sync, L.sync.mode == SYNC_WRITE_PEERS);
+}
+
+__global__ void kv_fill_kernel(uint4* p, uint32_t word, size_t n16, uint8_t* tail, int ntail, uint8_t b) {
+  const uint4 v = make_uint4(word, word, word, word);
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n16;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    p[i] = v;
+  if (blockIdx.x == 0 && threadIdx.x < ntail) tail[threadIdx.x] = b;
+}
+
+// ---------------------------------------------------------------------------
+// host launchers
+// ---------------------------------------------------------------------------
+typedef void (*DenseKernelFn)(DenseLaunch);
+
+template <typename T>
+static DenseKernelFn pick_fused(int opt, bool mp) {
+  if (mp) {
+    switch (opt) {
+      case OPT_SGD: return kv_dense_kernel<T, OPT_SGD, true>;
+      case OPT_SGD_MOM: return kv_dense_kernel<T, OPT_SGD_MOM, true>;
+      case OPT_ADAM: return kv_dense_kernel<T, OPT_ADAM, true>;
+      case OPT_ADAMW: return kv_dense_kernel<T, OPT_ADAMW, true>;
+      case OPT_TEST: return kv_dense_kernel<T, OPT_TEST, true>;
+      default: return nullptr;
+    }
+  }
+  return nullptr;
+}
+
+static DenseKernelFn pick_kernel(const DenseLaunch& L) {
+  const bool mp = L.multi_precision != 0;
+  switch (L.dtype) {
+    case kFloat32:
+      switch (L.opt) {
+        case OPT_NONE: return kv_dense_kernel<float, OPT_NONE, false>;
+        case OPT_SGD: return mp ? kv_dense_kernel<float, OPT_SGD, true> : kv_dense_kernel<float, OPT_SGD, false>;
+        case OPT_SGD_MOM: return mp ? kv_dense_kernel<float, OPT_SGD_MOM, true> : kv_dense_kernel<float, OPT_SGD_MOM, false>;
+        case OPT_ADAM: return mp ? kv_dense_kernel<float, OPT_ADAM, true> : kv_dense_kernel<float, OPT_ADAM, false>;
+        case OPT_ADAMW: return mp ? kv_dense_kernel<float, OPT_ADAMW, true> : kv_dense_kernel<float, OPT_ADAMW, false>;
+        case OPT_TEST: return mp ? kv_dense_kernel<float, OPT_TEST, true> : kv_dense_kernel<float, OPT_TEST, false>;
+        default: return nullptr;
+      }
+    case kFloat16:
+      if (L.opt == OPT_NONE) return kv_dense_kernel<__half, OPT_NONE, false>;
+      return pick_fused<__half>(L.opt, mp);
+    case kBfloat16:
+      if (L.opt == OPT_NONE) return kv_dense_kernel<__nv_bfloat16, OPT_NONE, false>;
+      return pick_fused<__nv_bfloat16>(L.opt, mp);
+    case kFloat64: return L.opt == OPT_NONE ? kv_sum_typed_kernel<double> : nullptr;
+    case kInt32: return L.opt == OPT_NONE ? kv_sum_typed_kernel<int32_t> : nullptr;
+    case kInt64: return L.opt == OPT_NONE ? kv_sum_typed_kernel<int64_t> : nullptr;
+    case kUint8: return L.opt == OPT_NONE ? kv_sum_typed_kernel<uint8_t> : nullptr;
+    case kInt8: return L.opt == OPT_NONE ? kv_sum_typed_kernel<int8_t> : nullptr;
+    default: return nullptr;
+  }
+}
+
+static int g_num_sms[64] = {0};
+
+static int sm_count(int device) {
+  if (device < 0 || device >= 64) return 148;
+  if (g_num_sms[device] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || n <= 0) n = 148;
+    g_num_sms[device] = n;
+  }
+  return g_num_sms[device];
+}
+
+int DenseMaxGrid(int device) {
+  // __launch_bounds__(512, 2): two resident blocks per SM for every instantiation
+  int g = 2 * sm_count(device);
+  return g > kMaxBlocks ? kMaxBlocks : g;
+}
+
+int LaunchDense(const DenseLaunch& L, cudaStream_t stream) {
+  DenseKernelFn fn = pick_kernel(L);
+  if (fn == nullptr) return static_cast<int>(cudaErrorInvalidValue);
+  int grid = L.grid;
+  if (grid < 1) grid = 1;
+  if (grid > kMaxBlocks) grid = kMaxBlocks;
+  fn<<<grid, kThreads, 0, stream>>>(L);
+  return static_cast<int>(cudaGetLastError());
+}
+
+template <typename T>
+__global__ void kv_cast_f32_kernel(const T* __restrict__ src, float* __restrict__ dst, int64_t n) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    dst[i] = Cvt<T>::to(src[i]);
+}
+
+int LaunchCastToF32(const void* src, int dtype, float* dst, int64_t n, cudaStream_t s) {
+  if (n == 0) return 0;
+  const int threads = 256;
+  int64_t blocks = (n + threads - 1) / threads;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  switch (dtype) {
+    case kFloat32: kv_cast_f32_kernel<float><<<blocks, threads, 0, s>>>(static_cast<const float*>(src), dst, n); break;
+    case kFloat16: kv_cast_f32_kernel<__half><<<blocks, threads, 0, s>>>(static_cast<const __half*>(src), dst, n); break;
+    case kBfloat16: kv_cast_f32_kernel<__nv_bfloat16><<<blocks, threads, 0, s>>>(static_cast<const __nv_bfloat16*>(src), dst, n); break;
+    default: return static_cast<int>(cudaErrorInvalidValue);
+  }
+  return static_cast<int>(cudaGetLastError());
+}
+
+int LaunchFill(void* ptr, int value_byte, size_t bytes, cudaStream_t s) {
+  if (bytes == 0) return 0;
+  return static_cast<int>(cudaMemsetAsync(ptr, value_byte, bytes, s));
+}
+
+}  // namespace mxkv

@@ -1,0 +1,101 @@
+// kernels.h -- device work descriptors and launcher entry points shared between
+// the host runtime (engine.cc) and the sm_100a kernels (kernels.cu).
+//
+// One launch of the dense kernel processes a *work list*: every entry is one key
+// (or the shard of a key this rank owns) with up to kMaxSrc gradient sources and
+// up to kMaxOut destinations.  Sources/destinations are plain global pointers:
+// local HBM, or another GPU's HBM mapped over NVLink (cudaDeviceEnablePeerAccess
+// in single-process mode, cudaIpcOpenMemHandle in one-process-per-GPU mode).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mxkv {
+
+constexpr int kMaxSrc = 16;      // values per key in one push (reference tests use 4; 8 GPUs => 8)
+constexpr int kMaxOut = 24;      // n store replicas + n user outputs + merge buffers
+constexpr int kMaxRanks = 8;     // one NVSwitch domain
+constexpr int kMaxBlocks = 1184; // 148 SMs x 8
+constexpr int kChunkElems = 8192;
+
+// mshadow type flags, 3rdparty/mshadow/mshadow/base.h:352-366
+enum DType : int {
+  kFloat32 = 0, kFloat64 = 1, kFloat16 = 2, kUint8 = 3, kInt32 = 4, kInt8 = 5, kInt64 = 6,
+  kBool = 7, kInt16 = 8, kUint16 = 9, kUint32 = 10, kUint64 = 11, kBfloat16 = 12
+};
+
+enum OptKind : int {
+  OPT_NONE = 0,     // out = sum(src)                        (push without updater / allreduce)
+  OPT_SGD = 1,      // SGDKernel / MP_SGDKernel              optimizer_op-inl.h:377-390,642-658
+  OPT_SGD_MOM = 2,  // SGDMomKernel / MP_SGDMomKernel        optimizer_op-inl.h:590-606,681-701
+  OPT_ADAM = 3,     // AdamUpdateKernel                      optimizer_op-inl.h:1246-1269
+  OPT_ADAMW = 4,    // MPAdamWKernel                         contrib/adamw-inl.h:101-124
+  OPT_TEST = 5      // mx.optimizer.Test                     python/mxnet/optimizer/optimizer.py:570-577
+};
+
+enum SumOrder : int {
+  ORDER_DEVICE = 0,  // ((in0+in1)+in2)+...                  ndarray_function-inl.h:457-486
+  ORDER_COMMCPU = 1  // in0 + (((in1+in2)+in3)+in4), groups of 4   comm.h:359-393
+};
+
+enum SyncMode : int {
+  SYNC_NONE = 0,      // all pointers local to this launch's device
+  SYNC_READ_PEERS = 1,  // one-shot: peers' sources are read, only own memory is written
+  SYNC_WRITE_PEERS = 2  // two-shot: peers' sources are read AND peers' destinations are written
+};
+
+struct alignas(16) TensorWork {
+  const void* src[kMaxSrc];
+  void* out[kMaxOut];
+  const void* w;     // current weight in the key dtype (non-MP optimizers); may alias an out[]
+  float* w32;        // fp32 master weight (multi-precision); updated in place
+  float* s0;         // momentum | adam mean
+  float* s1;         // adam variance
+  int64_t begin;     // element range [begin, end) of the key handled by this launch
+  int64_t end;
+  float lr;          // per-key learning rate (lr_mult, scheduler, Adam bias correction folded in)
+  float wd;          // per-key weight decay
+  float eta;         // AdamW schedule multiplier
+  int n_src;
+  int n_out;
+  int pad_;
+};
+
+struct SyncArgs {
+  uint32_t* self;                // this rank's signal pad
+  uint32_t* peers[kMaxRanks];    // every rank's signal pad as mapped into this device's address space
+  int world;
+  int rank;
+  int mode;                      // SyncMode
+};
+
+// signal pad layout in uint32 words
+constexpr int kSigStartOff = 0;
+constexpr int kSigEndOff = kMaxBlocks * kMaxRanks;
+constexpr int kSigFlagOff = 2 * kMaxBlocks * kMaxRanks;
+constexpr size_t kSignalPadBytes = (2 * kMaxBlocks * kMaxRanks + kMaxBlocks) * sizeof(uint32_t);
+
+struct DenseLaunch {
+  const TensorWork* works;       // device pointer, nworks entries
+  const int64_t* chunk_prefix;   // device pointer, nworks+1 entries (exclusive prefix of chunk counts)
+  int nworks;
+  int64_t total_chunks;
+  int dtype;                     // DType of src/out/w
+  int opt;                       // OptKind
+  int multi_precision;           // 1: w32 is the master, out is a cast copy
+  int order;                     // SumOrder
+  int fp32_accum;                // fp16 only: 1 = accumulate in fp32, 0 = round every add (reference)
+  float rescale, clip, momentum, beta1, beta2, eps;
+  SyncArgs sync;
+  int grid;                      // blocks to launch (identical on every rank of a collective)
+};
+
+// returns cudaError_t as int; never throws
+int LaunchDense(const DenseLaunch& L, cudaStream_t stream);
+int DenseMaxGrid(int device);   // resident-block capacity of the dense kernel on `device`
+
+int LaunchFill(void* ptr, int value_byte, size_t bytes, cudaStream_t s);
+// dst[i] = float(src[i]) for float32/float16/bfloat16 sources (fp32 master-weight creation)
+int LaunchCastToF32(const void* src, int dtype, float* dst, int64_t n, cudaStream_t s);
+
+}  // namespace mxkv

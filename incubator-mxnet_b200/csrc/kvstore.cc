@@ -1,0 +1,1057 @@
+// kvstore.cc -- see kvstore.h for the reference mapping.
+#include "kvstore.h"
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <set>
+
+namespace mxkv {
+
+static std::string Lower(std::string s) {
+  std::transform(s.begin(), s.end(), s.begin(), ::tolower);
+  return s;
+}
+
+// KVStore::Create, src/kvstore/kvstore.cc:42-85: substring dispatch on the lower-cased
+// type.  'device' selects the on-GPU reduce (CommDevice association order); the other
+// local types select CommCPU's association order -- the arithmetic still runs on the GPU.
+KVStore::KVStore(const std::string& type) : type_(type) {
+  const std::string t = Lower(type);
+  MXKV_CHECK(t.find("dist") == std::string::npos)
+      << "distributed kvstore types ('" << type << "') are out of scope of this library";
+  MXKV_CHECK(t.find("nccl") == std::string::npos)
+      << "kvstore type 'nccl' is not provided; use 'device'";
+  device_mode_ = t.find("device") != std::string::npos;
+  order_ = device_mode_ ? ORDER_DEVICE : ORDER_COMMCPU;
+}
+
+KVStore::~KVStore() {
+  try { Runtime::Get()->WaitAll(); } catch (...) {}
+}
+
+int KVStore::rank() const {
+  ProcessGroup* pg = Runtime::Get()->pg();
+  return pg ? pg->rank() : 0;
+}
+int KVStore::group_size() const {
+  ProcessGroup* pg = Runtime::Get()->pg();
+  return pg ? pg->world() : 1;
+}
+
+void KVStore::Barrier() {
+  Runtime::Get()->WaitAll();
+  ProcessGroup* pg = Runtime::Get()->pg();
+  if (pg) pg->Barrier();
+}
+
+// ---------------------------------------------------------------------------
+// key bookkeeping (kvstore_local.h:95-116, 344-347, 471-479)
+// ---------------------------------------------------------------------------
+void KVStore::SetKeyType(KeyType t) {
+  if (key_type_ == kUndefinedKey) key_type_ = t;
+  MXKV_CHECK(key_type_ == t) << "Mixed key types are not allowed";
+}
+
+void KVStore::LookupKeys(const std::vector<std::string>& str_keys, std::vector<int>* keys) {
+  keys->resize(str_keys.size());
+  for (size_t i = 0; i < str_keys.size(); ++i) {
+    auto it = str_key_dict_.find(str_keys[i]);
+    MXKV_CHECK(it != str_key_dict_.end()) << "key " << str_keys[i] << " doesn't exist. Did you init?";
+    (*keys)[i] = it->second;
+  }
+}
+
+void KVStore::NewStrKeys(const std::vector<std::string>& str_keys, std::vector<int>* keys) {
+  keys->resize(str_keys.size());
+  for (size_t i = 0; i < str_keys.size(); ++i) {
+    MXKV_CHECK(str_key_dict_.find(str_keys[i]) == str_key_dict_.end())
+        << "duplicate init of key " << str_keys[i];
+    const int key = next_str_key_++;
+    str_key_dict_[str_keys[i]] = key;
+    reverse_str_key_dict_[key] = str_keys[i];
+    (*keys)[i] = key;
+  }
+}
+
+int KVStore::ResolveKey(bool str_key, int ikey, const std::string& skey) {
+  if (!str_key) return ikey;
+  auto it = str_key_dict_.find(skey);
+  MXKV_CHECK(it != str_key_dict_.end()) << "key " << skey << " doesn't exist. Did you init?";
+  return it->second;
+}
+
+KeyState& KVStore::GetKey(int key) {
+  auto it = keys_.find(key);
+  MXKV_CHECK(it != keys_.end()) << "key " << key << " has not been inited";
+  return it->second;
+}
+
+// ---------------------------------------------------------------------------
+// public entry points: key-type handling then *Impl, as kvstore_local.h:95-219
+// ---------------------------------------------------------------------------
+#define LOCK() std::lock_guard<std::recursive_mutex> lk__(mu_)
+
+void KVStore::Init(const std::vector<int>& keys, const std::vector<NDArray>& vals) {
+  LOCK(); SetKeyType(kIntKey); InitImpl(keys, vals);
+}
+void KVStore::Init(const std::vector<std::string>& str_keys, const std::vector<NDArray>& vals) {
+  LOCK(); SetKeyType(kStringKey);
+  std::vector<int> keys; NewStrKeys(str_keys, &keys); InitImpl(keys, vals);
+}
+void KVStore::Push(const std::vector<int>& keys, const std::vector<NDArray>& vals, int priority) {
+  LOCK(); SetKeyType(kIntKey); PushImpl(keys, vals, priority);
+}
+void KVStore::Push(const std::vector<std::string>& str_keys, const std::vector<NDArray>& vals, int priority) {
+  LOCK(); SetKeyType(kStringKey);
+  std::vector<int> keys; LookupKeys(str_keys, &keys); PushImpl(keys, vals, priority);
+}
+void KVStore::Pull(const std::vector<int>& keys, const std::vector<NDArray*>& outs, int priority, bool ignore_sparse) {
+  LOCK(); SetKeyType(kIntKey); PullImpl(keys, outs, priority, ignore_sparse);
+}
+void KVStore::Pull(const std::vector<std::string>& str_keys, const std::vector<NDArray*>& outs, int priority,
+                   bool ignore_sparse) {
+  LOCK(); SetKeyType(kStringKey);
+  std::vector<int> keys; LookupKeys(str_keys, &keys); PullImpl(keys, outs, priority, ignore_sparse);
+}
+void KVStore::PushPull(const std::vector<int>& vkeys, const std::vector<int>& okeys,
+                       const std::vector<NDArray>& vals, const std::vector<NDArray*>& outs, int priority) {
+  LOCK(); SetKeyType(kIntKey); PushPullImpl(vkeys, okeys, vals, outs, priority);
+}
+void KVStore::PushPull(const std::vector<std::string>& svkeys, const std::vector<std::string>& sokeys,
+                       const std::vector<NDArray>& vals, const std::vector<NDArray*>& outs, int priority) {
+  LOCK(); SetKeyType(kStringKey);
+  std::vector<int> vkeys, okeys; LookupKeys(svkeys, &vkeys); LookupKeys(sokeys, &okeys);
+  PushPullImpl(vkeys, okeys, vals, outs, priority);
+}
+void KVStore::Broadcast(const std::vector<int>& vkeys, const std::vector<int>& okeys,
+                        const std::vector<NDArray>& vals, const std::vector<NDArray*>& outs, int priority) {
+  LOCK(); SetKeyType(kIntKey);
+  InitImpl(vkeys, vals); PullImpl(okeys, outs, priority, true);   // kvstore_local.h:349-356
+}
+void KVStore::Broadcast(const std::vector<std::string>& svkeys, const std::vector<std::string>& sokeys,
+                        const std::vector<NDArray>& vals, const std::vector<NDArray*>& outs, int priority) {
+  LOCK(); SetKeyType(kStringKey);
+  std::vector<int> vkeys, okeys; NewStrKeys(svkeys, &vkeys); LookupKeys(sokeys, &okeys);
+  InitImpl(vkeys, vals); PullImpl(okeys, outs, priority, true);
+}
+void KVStore::PullRowSparse(const std::vector<int>& keys,
+                            const std::vector<std::pair<NDArray*, NDArray>>& vr, int priority) {
+  LOCK(); SetKeyType(kIntKey); PullRowSparseImpl(keys, vr, priority);
+}
+void KVStore::PullRowSparse(const std::vector<std::string>& str_keys,
+                            const std::vector<std::pair<NDArray*, NDArray>>& vr, int priority) {
+  LOCK(); SetKeyType(kStringKey);
+  std::vector<int> keys; LookupKeys(str_keys, &keys); PullRowSparseImpl(keys, vr, priority);
+}
+
+void KVStore::SetUpdater(UpdaterFn fn, StrUpdaterFn sfn, void* handle) {
+  LOCK();
+  updater_ = fn; str_updater_ = sfn; updater_handle_ = handle;
+}
+
+void KVStore::SetGradientCompression(const std::vector<std::pair<std::string, std::string>>& kwargs) {
+  LOCK();
+  // GradientCompression::SetParams, src/kvstore/gradient_compression.cc:45-60
+  for (auto& kv : kwargs) {
+    if (kv.first == "type") {
+      MXKV_CHECK(kv.second == "1bit" || kv.second == "2bit" || kv.second == "none")
+          << "Unknown type for gradient compression " << kv.second;
+      gc_type_ = kv.second;
+    } else if (kv.first == "threshold") {
+      gc_threshold_ = std::stof(kv.second);
+      MXKV_CHECK(gc_threshold_ > 0 || gc_type_ == "1bit") << "threshold must be greater than 0";
+    } else {
+      MXKV_FATAL() << "Cannot find argument '" << kv.first << "' for gradient compression";
+    }
+  }
+  MXKV_CHECK(gc_type_ == "none")
+      << "gradient compression ('" << gc_type_ << "') is not implemented on this path yet (SURVEY 8f rank 2)";
+}
+
+// ---------------------------------------------------------------------------
+// optimizer registry
+// ---------------------------------------------------------------------------
+void KVStore::SetOptimizer(const std::string& name, const std::vector<std::pair<std::string, std::string>>& kwargs) {
+  LOCK();
+  OptimizerConfig c;
+  const std::string n = Lower(name);
+  c.enabled = true;
+  if (n == "sgd") { c.kind = OPT_SGD; c.lr = 0.01; }
+  else if (n == "adam") { c.kind = OPT_ADAM; c.lr = 0.001; }
+  else if (n == "adamw") { c.kind = OPT_ADAMW; c.lr = 0.001; }
+  else if (n == "test") { c.kind = OPT_TEST; c.lr = 0.01; }
+  else MXKV_FATAL() << "optimizer '" << name << "' has no fused kernel; register a Python updater instead";
+  for (auto& kv : kwargs) {
+    const std::string& k = kv.first;
+    const std::string& v = kv.second;
+    if (k == "learning_rate" || k == "lr") c.lr = std::stod(v);
+    else if (k == "wd") c.wd = std::stod(v);
+    else if (k == "momentum") c.momentum = std::stof(v);
+    else if (k == "beta1") c.beta1 = std::stod(v);
+    else if (k == "beta2") c.beta2 = std::stod(v);
+    else if (k == "epsilon") c.eps = std::stof(v);
+    else if (k == "eta") c.eta = std::stof(v);
+    else if (k == "rescale_grad") c.rescale = std::stof(v);
+    else if (k == "clip_gradient") c.clip = (v == "None" || v.empty()) ? -1.f : std::stof(v);
+    else if (k == "correct_bias") c.correct_bias = (v == "True" || v == "true" || v == "1");
+    else if (k == "multi_precision") c.multi_precision = (v == "True" || v == "true" || v == "1");
+    else MXKV_FATAL() << "unknown optimizer argument '" << k << "'";
+  }
+  if (c.kind == OPT_SGD && c.momentum != 0.f) c.kind = OPT_SGD_MOM;   // sgd.py:213-224
+  c.lr_mult = opt_.lr_mult;
+  c.wd_mult = opt_.wd_mult;
+  opt_ = c;
+}
+
+void KVStore::SetOptimizerMult(bool str_key, int ikey, const std::string& skey, float lr_mult, float wd_mult) {
+  LOCK();
+  const int key = ResolveKey(str_key, ikey, skey);
+  opt_.lr_mult[key] = lr_mult;
+  opt_.wd_mult[key] = wd_mult;
+}
+
+float KVStore::KeyLR(const KeyState& ks) const {
+  // Optimizer._get_lr (optimizer.py) then, for Adam, the host-side bias correction of
+  // adam.py:166-175 -- all in double like Python, rounded to float once.
+  double lr = opt_.lr;
+  auto it = opt_.lr_mult.find(ks.key);
+  if (it != opt_.lr_mult.end()) lr *= it->second;
+  if (opt_.kind == OPT_ADAM || (opt_.kind == OPT_ADAMW && opt_.correct_bias)) {   // adamW.py:175-182
+    const double t = static_cast<double>(ks.count);
+    const double coef1 = 1. - std::pow(opt_.beta1, t);
+    const double coef2 = 1. - std::pow(opt_.beta2, t);
+    lr *= std::sqrt(coef2) / coef1;
+  }
+  return static_cast<float>(lr);
+}
+
+float KVStore::KeyWD(const KeyState& ks) const {
+  double wd = opt_.wd;
+  auto it = opt_.wd_mult.find(ks.key);
+  if (it != opt_.wd_mult.end()) wd *= it->second;
+  return static_cast<float>(wd);
+}
+
+// ---------------------------------------------------------------------------
+// replicas
+// ---------------------------------------------------------------------------
+int KVStore::DefaultDevice() {
+  Runtime* rt = Runtime::Get();
+  if (rt->pg()) return rt->pg()->dev();
+  MXKV_CHECK(rt->NumDevices() > 0)
+      << "no CUDA device is visible: the B200 KVStore has no CPU fallback (build/run it on a GPU box)";
+  return 0;
+}
+
+Replica* KVStore::FindReplica(KeyState& ks, int dev) {
+  for (auto& r : ks.reps) if (r.dev == dev) return &r;
+  return nullptr;
+}
+
+Replica& KVStore::FreshReplica(KeyState& ks) {
+  for (auto& r : ks.reps) if (r.fresh) return r;
+  MXKV_FATAL() << "key " << ks.key << " has no valid replica";
+}
+
+Replica& KVStore::EnsureReplica(KeyState& ks, int dev) {
+  if (Replica* r = FindReplica(ks, dev)) {
+    if (!r->fresh) {
+      Replica& src = FreshReplica(ks);
+      CopyFromTo(src.local, r->local);
+      r->fresh = true;
+    }
+    return *r;
+  }
+  Runtime* rt = Runtime::Get();
+  MXKV_CHECK(!(ks.has_state && !ks.reps.empty() && updater_ == nullptr))
+      << "key " << ks.key << ": the set of GPUs changed after fused optimizer state was created";
+  if (rt->pg()) MXKV_CHECK(dev == rt->pg()->dev()) << "in one-process-per-GPU mode arrays must live on GPU "
+                                                   << rt->pg()->dev();
+  Replica nr;
+  nr.dev = dev;
+  nr.local = NDArray::Empty(ks.shape, Context{kGPU, dev}, ks.dtype, /*symmetric=*/rt->pg() != nullptr);
+  if (!ks.reps.empty()) {
+    CopyFromTo(FreshReplica(ks).local, nr.local);
+  } else {
+    MXKV_CHECK(!ks.init_value.is_none()) << "key " << ks.key << " has no initial value";
+    CopyFromTo(ks.init_value, nr.local);
+    // the pageable H2D copy above is synchronous w.r.t. the host buffer; safe to drop it
+    rt->WaitDevice(dev);
+    ks.init_value = NDArray();
+  }
+  ks.reps.push_back(nr);
+  return ks.reps.back();
+}
+
+void KVStore::EnsureState(KeyState& ks, Replica& r, bool mp) {
+  Runtime* rt = Runtime::Get();
+  const bool sym = rt->pg() != nullptr;
+  const Context ctx{kGPU, r.dev};
+  DeviceGuard g(r.dev);
+  cudaStream_t s = rt->Dev(r.dev).stream;
+  const bool need_s0 = opt_.kind == OPT_SGD_MOM || opt_.kind == OPT_ADAM || opt_.kind == OPT_ADAMW;
+  const bool need_s1 = opt_.kind == OPT_ADAM || opt_.kind == OPT_ADAMW;
+  if (mp && r.w32.is_none()) {
+    r.w32 = NDArray::Empty(ks.shape, ctx, kFloat32, sym);
+    // create_state_multi_precision: weight_master_copy = weight.astype(float32) (optimizer.py:341-352)
+    MXKV_CHECK(ks.dtype == kFloat32 || ks.dtype == kFloat16 || ks.dtype == kBfloat16)
+        << "multi_precision needs a floating-point key";
+    const int rc = LaunchCastToF32(r.local.data(), ks.dtype, static_cast<float*>(r.w32.data()), ks.size, s);
+    MXKV_CHECK(rc == 0) << "cast kernel launch failed: " << cudaGetErrorString(static_cast<cudaError_t>(rc));
+    rt->launches++;
+  }
+  if (need_s0 && r.s0.is_none()) {
+    r.s0 = NDArray::Empty(ks.shape, ctx, kFloat32, sym);
+    CUDA_CALL(cudaMemsetAsync(r.s0.data(), 0, r.s0.nbytes(), s));
+  }
+  if (need_s1 && r.s1.is_none()) {
+    r.s1 = NDArray::Empty(ks.shape, ctx, kFloat32, sym);
+    CUDA_CALL(cudaMemsetAsync(r.s1.data(), 0, r.s1.nbytes(), s));
+  }
+  ks.has_state = true;
+}
+
+// ---------------------------------------------------------------------------
+// Init (kvstore_local.h:227-238).  The reference parks the value in pinned host memory
+// until the first push reveals the devices; so do we, except that a GPU-resident value
+// immediately becomes the first replica.  One-process-per-GPU mode: rank 0's value wins
+// (the contract of KVStoreBase.broadcast, python/mxnet/kvstore/base.py:77-96).
+// ---------------------------------------------------------------------------
+void KVStore::InitImpl(const std::vector<int>& keys, const std::vector<NDArray>& vals) {
+  MXKV_CHECK(keys.size() == vals.size()) << "Init: " << keys.size() << " keys but " << vals.size() << " values";
+  Runtime* rt = Runtime::Get();
+  ProcessGroup* pg = rt->pg();
+  for (size_t i = 0; i < keys.size(); ++i) {
+    MXKV_CHECK(keys_.find(keys[i]) == keys_.end())
+        << "duplicate init of key " << keys[i]
+        << ". Please double check if you called kv.init or kv.broadcast with this key multiple times";
+    const NDArray& v = vals[i];
+    MXKV_CHECK(!v.is_none()) << "Init: empty value for key " << keys[i];
+    KeyState ks;
+    ks.key = keys[i];
+    ks.shape = v.shape();
+    ks.dtype = v.dtype();
+    ks.stype = v.stype();
+    ks.size = v.size();
+    if (v.stype() == kRowSparseStorage) {
+      keys_[keys[i]] = ks;
+      InitRowSparseKey(keys_[keys[i]], v);
+      continue;
+    }
+    MXKV_CHECK(v.stype() == kDefaultStorage) << "Init: unsupported storage type " << v.stype();
+    const Context c = v.ctx();
+    if (c.is_gpu() || pg != nullptr) {
+      const int dev = pg ? pg->dev() : c.dev_id;
+      if (c.is_gpu()) rt->AcquireUser(c.dev_id);
+      ks.init_value = v;   // EnsureReplica copies from it (D2D / H2D / peer)
+      keys_[keys[i]] = ks;
+      KeyState& k2 = keys_[keys[i]];
+      Replica& r = EnsureReplica(k2, dev);
+      if (pg && pg->world() > 1) {
+        // every rank adopts rank 0's value: one-shot read of rank 0's replica
+        DeviceState& d = rt->Dev(dev);
+        TensorWork tw;
+        std::memset(&tw, 0, sizeof(tw));
+        tw.src[0] = r.local.peer_data(0);
+        tw.n_src = 1;
+        tw.out[0] = r.local.data();
+        tw.n_out = 1;
+        tw.begin = 0; tw.end = k2.size;
+        tw.pad_ = 1;
+        int64_t prefix[2] = {0, (k2.size + kChunkElems - 1) / kChunkElems};
+        if (prefix[1] == 0) prefix[1] = 1;
+        const size_t bytes = sizeof(TensorWork) + sizeof(prefix);
+        const size_t off = d.ring.Alloc(bytes);
+        std::memcpy(d.ring.host(off), &tw, sizeof(tw));
+        std::memcpy(d.ring.host(off) + sizeof(tw), prefix, sizeof(prefix));
+        DeviceGuard g(dev);
+        CUDA_CALL(cudaMemcpyAsync(d.ring.dev(off), d.ring.host(off), bytes, cudaMemcpyHostToDevice, d.stream));
+        DenseLaunch L;
+        std::memset(&L, 0, sizeof(L));
+        L.works = reinterpret_cast<const TensorWork*>(d.ring.dev(off));
+        L.chunk_prefix = reinterpret_cast<const int64_t*>(d.ring.dev(off) + sizeof(tw));
+        L.nworks = 1; L.total_chunks = prefix[1];
+        L.dtype = k2.dtype; L.opt = OPT_NONE; L.order = ORDER_DEVICE; L.fp32_accum = 1;
+        L.sync.self = d.signal_pad;
+        for (int q = 0; q < pg->world(); ++q) L.sync.peers[q] = pg->signal_pad(q);
+        L.sync.world = pg->world(); L.sync.rank = pg->rank(); L.sync.mode = SYNC_READ_PEERS;
+        L.grid = static_cast<int>(std::min<int64_t>(d.max_grid, prefix[1]));
+        // rank 0 must not have its replica overwritten while peers read it: it copies onto itself
+        const int rc = LaunchDense(L, d.stream);
+        MXKV_CHECK(rc == 0) << "kernel launch failed: " << cudaGetErrorString(static_cast<cudaError_t>(rc));
+        rt->launches++;
+        d.ring.Commit(off, bytes, d.stream);
+      }
+      rt->ReleaseToUser(dev);
+    } else {
+      // host value, devices unknown yet: keep a private host copy (values[i].Copy(pinned_ctx_))
+      rt->WaitAll();
+      ks.init_value = NDArray::Empty(v.shape(), Context{kCPU, 0}, v.dtype());
+      std::memcpy(ks.init_value.data(), v.data(), v.nbytes());
+      keys_[keys[i]] = ks;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// GroupKVPairs (kvstore_local.h:440-469): std::sort on the key only, then group
+// ---------------------------------------------------------------------------
+template <typename V>
+static void GroupPairs(const std::vector<int>& keys, const std::vector<V>& vals,
+                       std::vector<int>* uniq, std::vector<std::vector<V>>* grouped,
+                       const std::function<bool(int, const V&)>& valid) {
+  MXKV_CHECK(keys.size() == vals.size()) << keys.size() << " keys but " << vals.size() << " values";
+  std::vector<std::pair<int, int>> idx(keys.size());
+  for (size_t i = 0; i < keys.size(); ++i) idx[i] = {keys[i], static_cast<int>(i)};
+  std::stable_sort(idx.begin(), idx.end(),
+                   [](const std::pair<int, int>& a, const std::pair<int, int>& b) { return a.first < b.first; });
+  bool have = false;
+  int pre = 0;
+  for (auto& p : idx) {
+    if (!valid(p.first, vals[p.second])) continue;
+    if (!have || p.first != pre) {
+      uniq->push_back(p.first);
+      grouped->push_back({vals[p.second]});
+      pre = p.first; have = true;
+    } else {
+      grouped->back().push_back(vals[p.second]);
+    }
+  }
+}
+
+void KVStore::PushImpl(const std::vector<int>& keys, const std::vector<NDArray>& vals, int priority) {
+  (void)priority;
+  std::vector<int> uniq;
+  std::vector<std::vector<NDArray>> grouped;
+  GroupPairs<NDArray>(keys, vals, &uniq, &grouped, [](int, const NDArray& nd) {
+    MXKV_CHECK(nd.stype() == kDefaultStorage || nd.stype() == kRowSparseStorage)
+        << "Unexpected storage type detected during kvstore push: " << nd.stype();
+    return true;
+  });
+  std::vector<Group> dense;
+  for (size_t i = 0; i < uniq.size(); ++i) {
+    KeyState& ks = GetKey(uniq[i]);
+    if (grouped[i][0].stype() == kRowSparseStorage || ks.stype == kRowSparseStorage) {
+      PushRowSparse(ks, grouped[i]);
+      continue;
+    }
+    Group g;
+    g.key = uniq[i];
+    g.vals = grouped[i];
+    dense.push_back(g);
+  }
+  if (!dense.empty()) ReduceUpdate(dense, false);
+}
+
+void KVStore::PullImpl(const std::vector<int>& keys, const std::vector<NDArray*>& outs, int priority,
+                       bool ignore_sparse) {
+  (void)priority;
+  std::vector<int> uniq;
+  std::vector<std::vector<NDArray*>> grouped;
+  GroupPairs<NDArray*>(keys, outs, &uniq, &grouped, [this, ignore_sparse](int key, NDArray* const& nd) {
+    if (nd->stype() == kDefaultStorage || !ignore_sparse) return true;
+    if (warnings_printed_.insert(key).second) {
+      fprintf(stderr, "Warning: non-default weights detected during kvstore pull. This call has been "
+                      "ignored. Please make sure to use kv.row_sparse_pull() or module.prepare() with row_ids.\n");
+    }
+    return false;
+  });
+  Runtime* rt = Runtime::Get();
+  std::set<int> touched;
+  for (size_t i = 0; i < uniq.size(); ++i) {
+    KeyState& ks = GetKey(uniq[i]);
+    if (ks.stype == kRowSparseStorage) {
+      PullDenseFromRowSparse(ks, grouped[i]);
+      continue;
+    }
+    for (NDArray* o : grouped[i]) {
+      MXKV_CHECK(o->stype() == kDefaultStorage) << "pull into a sparse array is not supported for dense keys";
+      MXKV_CHECK(o->size() == ks.size) << "pull: output has " << o->size() << " elements, key " << ks.key
+                                       << " has " << ks.size;
+      MXKV_CHECK(o->dtype() == ks.dtype) << "pull: dtype mismatch for key " << ks.key;
+      const Context c = o->ctx();
+      if (c.is_gpu()) {
+        if (touched.insert(c.dev_id).second) rt->AcquireUser(c.dev_id);
+        if (rt->pg() == nullptr || c.dev_id == rt->pg()->dev()) {
+          Replica& r = EnsureReplica(ks, c.dev_id);   // comm.h:607-625, but from the local replica
+          CopyFromTo(r.local, *o);
+          continue;
+        }
+      }
+      if (ks.reps.empty()) {
+        if (!c.is_gpu()) {            // never touched a GPU: host -> host
+          CopyFromTo(ks.init_value, *o);
+          continue;
+        }
+        EnsureReplica(ks, DefaultDevice());
+      }
+      CopyFromTo(FreshReplica(ks).local, *o);
+    }
+  }
+  for (int d : touched) rt->ReleaseToUser(d);
+}
+
+void KVStore::PushPullImpl(const std::vector<int>& vkeys, const std::vector<int>& okeys,
+                           const std::vector<NDArray>& vals, const std::vector<NDArray*>& outs, int priority) {
+  // fused path when the pushed and the pulled key sets coincide and everything is dense;
+  // otherwise literally Push then Pull (kvstore_local.h:358-365).
+  std::vector<int> vu, ou;
+  std::vector<std::vector<NDArray>> vg;
+  std::vector<std::vector<NDArray*>> og;
+  bool dense = true;
+  GroupPairs<NDArray>(vkeys, vals, &vu, &vg, [&dense](int, const NDArray& nd) {
+    if (nd.stype() != kDefaultStorage) dense = false;
+    return true;
+  });
+  GroupPairs<NDArray*>(okeys, outs, &ou, &og, [&dense](int, NDArray* const& nd) {
+    if (nd->stype() != kDefaultStorage) dense = false;
+    return true;
+  });
+  bool fusable = dense && vu == ou && updater_ == nullptr;
+  if (fusable) {
+    for (int k : vu) if (GetKey(k).stype != kDefaultStorage) fusable = false;
+  }
+  if (!fusable) {
+    PushImpl(vkeys, vals, priority);
+    PullImpl(okeys, outs, priority, true);
+    return;
+  }
+  std::vector<Group> groups(vu.size());
+  for (size_t i = 0; i < vu.size(); ++i) {
+    groups[i].key = vu[i];
+    groups[i].vals = vg[i];
+    groups[i].outs = og[i];
+  }
+  ReduceUpdate(groups, true);
+}
+
+// ---------------------------------------------------------------------------
+// the hot path
+// ---------------------------------------------------------------------------
+// two-shot partition: rank p owns elements [p*L, (p+1)*L) clipped to the key, L = ceil(size/n)
+// rounded up to 128 elements so that every shard starts 16-byte aligned for any dtype
+int64_t ShardLen(int64_t size, int world) {
+  int64_t shard = (size + world - 1) / world;
+  return (shard + 127) / 128 * 128;
+}
+
+namespace {
+struct Dest {
+  void* ptr[kMaxRanks];   // address as seen by participant p (MP: peer mapping; SP: same everywhere)
+  int owner;              // participant index that owns the memory, -1: none
+};
+struct LaunchClassKey {
+  int sync_mode, dtype, mp;
+  bool operator<(const LaunchClassKey& o) const {
+    if (sync_mode != o.sync_mode) return sync_mode < o.sync_mode;
+    if (dtype != o.dtype) return dtype < o.dtype;
+    return mp < o.mp;
+  }
+};
+struct PostCopy { NDArray src; NDArray dst; };
+inline bool Overlap(const void* a, size_t an, const void* b, size_t bn) {
+  const char* x = static_cast<const char*>(a);
+  const char* y = static_cast<const char*>(b);
+  return x < y + bn && y < x + an;
+}
+inline bool Aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+}  // namespace
+
+void KVStore::ReduceUpdate(std::vector<Group>& groups, bool write_outs) {
+  Runtime* rt = Runtime::Get();
+  ProcessGroup* pg = rt->pg();
+  const bool mp_mode = pg != nullptr;
+  const bool callback = updater_ != nullptr;
+  const bool fused = opt_.enabled && !callback;
+
+  // participant slot -> device; SP: discovered from the first key, MP: this rank only is local
+  struct LaunchClass {
+    std::vector<std::vector<TensorWork>> per_part;   // [participant] -> work list
+    int64_t max_chunks = 0;                          // chunk count of the busiest rank (same on every rank)
+  };
+  std::map<LaunchClassKey, LaunchClass> classes;
+  std::vector<int> part_dev;      // device of participant p (SP) / own device at index rank (MP)
+  std::vector<PostCopy> post;
+  std::vector<void*> temps;       // cudaMallocAsync'ed staging, freed after the launches
+  std::vector<int> temp_dev;
+  std::set<int> touched;
+  std::vector<KeyState*> callback_keys;
+  auto touch = [&](int dev) { if (dev >= 0 && touched.insert(dev).second) rt->AcquireUser(dev); };
+
+  int n_part = 0;
+  bool collective = false;
+  int root_dev = -1;
+
+  for (size_t gi = 0; gi < groups.size(); ++gi) {
+    Group& g = groups[gi];
+    KeyState& ks = GetKey(g.key);
+    MXKV_CHECK(ks.stype == kDefaultStorage) << "key " << g.key << " is row_sparse; dense push not allowed";
+    const size_t esize = DTypeSize(ks.dtype);
+    const int n_src = static_cast<int>(g.vals.size());
+    MXKV_CHECK(n_src >= 1 && n_src <= kMaxSrc) << "push of " << n_src << " values for one key (max " << kMaxSrc << ")";
+    for (auto& v : g.vals) {
+      MXKV_CHECK(v.size() == ks.size) << "push: value has " << v.size() << " elements, key " << ks.key
+                                      << " was initialised with " << ks.size;
+      MXKV_CHECK(v.dtype() == ks.dtype) << "push: dtype mismatch for key " << ks.key
+                                        << " (Only support input/output with the same data type)";
+    }
+
+    // ---- placement ------------------------------------------------------
+    std::vector<int> devs;        // per source; -1 = host
+    for (auto& v : g.vals) devs.push_back(v.ctx().is_gpu() ? v.ctx().dev_id : -1);
+    std::vector<int> key_part;    // participant devices for this key
+    bool key_collective = false;
+    if (mp_mode) {
+      MXKV_CHECK(n_src == 1) << "one-process-per-GPU mode: push exactly one value per key per rank";
+      MXKV_CHECK(devs[0] < 0 || devs[0] == pg->dev()) << "value must live on GPU " << pg->dev() << " or on the host";
+      key_part.assign(pg->world(), pg->dev());
+      key_collective = pg->world() > 1;
+    } else {
+      bool all_gpu = true, distinct = true;
+      std::set<int> seen;
+      for (int d : devs) {
+        if (d < 0) { all_gpu = false; continue; }
+        if (!seen.insert(d).second) distinct = false;
+      }
+      if (all_gpu && distinct && n_src >= 2 && n_src <= kMaxRanks) {
+        rt->EnablePeerAccess(devs);
+        bool p2p = true;
+        for (int a : devs) for (int b : devs) if (!rt->PeerOK(a, b)) p2p = false;
+        key_collective = p2p;
+      }
+      if (key_collective) {
+        key_part = devs;
+      } else {
+        int rd = -1;
+        for (int d : devs) if (d >= 0) { rd = d; break; }
+        if (rd < 0) {
+          for (NDArray* o : g.outs) if (o->ctx().is_gpu()) { rd = o->ctx().dev_id; break; }
+        }
+        if (rd < 0 && !ks.reps.empty()) rd = ks.reps[0].dev;
+        if (rd < 0) rd = DefaultDevice();
+        key_part.assign(1, rd);
+      }
+    }
+    if (gi == 0) {
+      part_dev = key_part; n_part = static_cast<int>(key_part.size()); collective = key_collective;
+      root_dev = key_part[0];
+    } else {
+      MXKV_CHECK(key_part == part_dev && key_collective == collective)
+          << "all keys of one push/pushpull call must use the same set of devices";
+    }
+    const int my_first = mp_mode ? pg->rank() : 0;
+    const int my_last = mp_mode ? pg->rank() : n_part - 1;
+
+    // ---- replicas -------------------------------------------------------
+    std::vector<Replica*> rep(n_part, nullptr);
+    for (int p = my_first; p <= my_last; ++p) {
+      touch(part_dev[p]);
+      rep[p] = &EnsureReplica(ks, part_dev[p]);
+    }
+    // EnsureReplica may reallocate ks.reps: re-resolve pointers
+    for (int p = my_first; p <= my_last; ++p) rep[p] = FindReplica(ks, part_dev[p]);
+
+    const bool lowp = ks.dtype == kFloat16 || ks.dtype == kBfloat16;
+    const bool mp = fused && (opt_.multi_precision || lowp);
+    if (fused) {
+      MXKV_CHECK(ks.dtype == kFloat32 || lowp) << "fused optimizers need float32/float16/bfloat16 keys";
+      for (int p = my_first; p <= my_last; ++p) EnsureState(ks, *rep[p], mp);
+    }
+
+    const bool two_shot = collective && static_cast<int64_t>(ks.size * esize) >= rt->twoshot_bytes &&
+                          ks.size >= static_cast<int64_t>(n_part) * 128;
+    if (fused && collective) {
+      const int want = two_shot ? n_part : 0;
+      if (ks.count > 0 && ks.state_world != want) GatherState(ks);
+      ks.state_world = want;
+    }
+
+    // ---- sources as addressable pointers ----------------------------------
+    // srcptr[p][k]: address of source k for the kernel running as participant p
+    std::vector<std::vector<const void*>> srcptr(n_part, std::vector<const void*>(collective ? n_part : n_src));
+    if (mp_mode) {
+      const NDArray& v = g.vals[0];
+      NDArray sym_src;
+      if (v.symmetric() && collective) {
+        sym_src = v;
+      } else if (collective) {
+        Replica& r = *rep[pg->rank()];
+        if (r.stage.is_none()) r.stage = NDArray::Empty(ks.shape, Context{kGPU, pg->dev()}, ks.dtype, true);
+        CopyFromTo(v, r.stage);                       // D2D or H2D
+        sym_src = r.stage;
+      }
+      if (collective) {
+        for (int k = 0; k < n_part; ++k) srcptr[pg->rank()][k] = sym_src.peer_data(k);
+      } else {
+        if (devs[0] < 0) {
+          void* t = nullptr;
+          DeviceGuard dg(pg->dev());
+          CUDA_CALL(cudaMallocAsync(&t, v.nbytes() ? v.nbytes() : 16, rt->Dev(pg->dev()).stream));
+          temps.push_back(t); temp_dev.push_back(pg->dev());
+          CopyBytes(v.data(), v.ctx(), t, Context{kGPU, pg->dev()}, v.nbytes());
+          srcptr[pg->rank()][0] = t;
+        } else {
+          srcptr[pg->rank()][0] = v.data();
+        }
+      }
+    } else if (collective) {
+      for (int p = 0; p < n_part; ++p)
+        for (int k = 0; k < n_part; ++k) srcptr[p][k] = g.vals[k].data();
+    } else {
+      for (int k = 0; k < n_src; ++k) {
+        const NDArray& v = g.vals[k];
+        const bool direct = devs[k] == root_dev || (devs[k] >= 0 && (rt->EnablePeerAccess({root_dev, devs[k]}),
+                                                                   rt->PeerOK(root_dev, devs[k])));
+        if (direct) {
+          if (devs[k] != root_dev) {              // foreign GPU read by the root kernel
+            touch(devs[k]);
+            rt->StreamWait(root_dev, devs[k]);
+          }
+          srcptr[0][k] = v.data();
+        } else {                                   // host value, or no P2P: stage on the root
+          if (devs[k] >= 0) touch(devs[k]);
+          void* t = nullptr;
+          {
+            DeviceGuard dg(root_dev);
+            CUDA_CALL(cudaMallocAsync(&t, v.nbytes() ? v.nbytes() : 16, rt->Dev(root_dev).stream));
+          }
+          temps.push_back(t); temp_dev.push_back(root_dev);
+          CopyBytes(v.data(), v.ctx(), t, Context{kGPU, root_dev}, v.nbytes());
+          srcptr[0][k] = t;
+        }
+      }
+    }
+
+    // ---- destinations -------------------------------------------------------
+    std::vector<Dest> dests;
+    auto add_dest_sp = [&](void* ptr, int dev) {
+      Dest d;
+      for (int p = 0; p < kMaxRanks; ++p) d.ptr[p] = ptr;
+      d.owner = -1;
+      for (int p = 0; p < n_part; ++p) if (part_dev[p] == dev) d.owner = p;
+      dests.push_back(d);
+    };
+    if (callback) {
+      Replica& root = *rep[my_first];
+      if (root.merged.is_none())
+        root.merged = NDArray::Empty(ks.shape, Context{kGPU, root.dev}, ks.dtype, mp_mode);
+      if (mp_mode && collective) {
+        Dest d; d.owner = -2;   // every rank owns its own copy
+        for (int p = 0; p < n_part; ++p) d.ptr[p] = root.merged.peer_data(p);
+        dests.push_back(d);
+      } else {
+        add_dest_sp(root.merged.data(), root.dev);
+      }
+      callback_keys.push_back(&ks);
+    } else {
+      if (mp_mode && collective) {
+        Dest d; d.owner = -2;
+        for (int p = 0; p < n_part; ++p) d.ptr[p] = rep[pg->rank()]->local.peer_data(p);
+        dests.push_back(d);
+      } else {
+        for (auto& r : ks.reps) {
+          const bool reachable = r.dev == root_dev || collective ||
+                                 (rt->EnablePeerAccess({root_dev, r.dev}), rt->PeerOK(root_dev, r.dev));
+          bool is_part = false;
+          for (int p = 0; p < n_part; ++p) if (part_dev[p] == r.dev) is_part = true;
+          if (is_part || (reachable && !collective)) {
+            if (!is_part) { touch(r.dev); rt->StreamWait(root_dev, r.dev); }
+            add_dest_sp(r.local.data(), r.dev);
+            r.fresh = true;
+          } else {
+            r.fresh = false;          // refreshed lazily by EnsureReplica
+          }
+        }
+      }
+      if (write_outs) {
+        for (NDArray* o : g.outs) {
+          MXKV_CHECK(o->size() == ks.size && o->dtype() == ks.dtype)
+              << "pushpull: output does not match key " << ks.key;
+          const Context oc = o->ctx();
+          bool direct = false;
+          if (oc.is_gpu() && static_cast<int>(dests.size()) < kMaxOut - 1) {
+            if (mp_mode) {
+              direct = collective ? o->symmetric() : (oc.dev_id == pg->dev());
+            } else {
+              for (int p = 0; p < n_part; ++p) if (part_dev[p] == oc.dev_id) direct = true;
+            }
+            // one-shot in-place allreduce: peers still read this buffer while we would write it
+            if (direct && collective && !two_shot) {
+              for (auto& v : g.vals)
+                if (Overlap(o->data(), o->nbytes(), v.data(), v.nbytes())) direct = false;
+            }
+            if (direct && !Aligned16(o->data())) direct = false;
+          }
+          if (direct) {
+            touch(oc.dev_id);
+            if (mp_mode && collective) {
+              Dest d; d.owner = -2;
+              for (int p = 0; p < n_part; ++p) d.ptr[p] = o->peer_data(p);
+              dests.push_back(d);
+            } else {
+              add_dest_sp(o->data(), oc.dev_id);
+            }
+          } else {
+            if (oc.is_gpu()) touch(oc.dev_id);
+            PostCopy pc;
+            pc.dst = *o;
+            const int sdev = (oc.is_gpu() && FindReplica(ks, oc.dev_id)) ? oc.dev_id : part_dev[my_first];
+            pc.src = FindReplica(ks, sdev)->local;
+            post.push_back(pc);
+          }
+        }
+      }
+    }
+    MXKV_CHECK(static_cast<int>(dests.size()) <= kMaxOut) << "too many destinations for key " << ks.key;
+
+    // ---- hyper-parameters -------------------------------------------------
+    float lr = 0.f, wd = 0.f;
+    if (fused) {
+      ks.count += 1;                 // Optimizer._update_count
+      lr = KeyLR(ks);
+      wd = KeyWD(ks);
+    }
+
+    // ---- work entries -------------------------------------------------------
+    const int sync_mode = !collective ? SYNC_NONE : (two_shot ? SYNC_WRITE_PEERS : SYNC_READ_PEERS);
+    LaunchClassKey ck{sync_mode, ks.dtype, mp ? 1 : 0};
+    LaunchClass& lc = classes[ck];
+    auto& cls = lc.per_part;
+    if (cls.empty()) cls.resize(n_part);
+    const int64_t shard = two_shot ? ShardLen(ks.size, n_part) : ks.size;
+    lc.max_chunks += (std::min<int64_t>(ks.size, shard) + kChunkElems - 1) / kChunkElems;
+    for (int p = my_first; p <= my_last; ++p) {
+      TensorWork tw;
+      std::memset(&tw, 0, sizeof(tw));
+      bool vec_ok = true;
+      tw.n_src = static_cast<int>(srcptr[p].size());
+      for (int k = 0; k < tw.n_src; ++k) {
+        tw.src[k] = srcptr[p][k];
+        vec_ok = vec_ok && Aligned16(tw.src[k]);
+      }
+      for (auto& d : dests) {
+        bool mine;
+        if (d.owner == -2) mine = two_shot ? true : false;   // MP: handled below
+        else if (two_shot) mine = true;
+        else if (!collective) mine = true;
+        else mine = (d.owner == p) || (d.owner == -1 && p == 0);
+        if (d.owner == -2) {
+          if (two_shot) {
+            for (int q = 0; q < n_part; ++q) { tw.out[tw.n_out++] = d.ptr[q]; vec_ok = vec_ok && Aligned16(d.ptr[q]); }
+          } else {
+            tw.out[tw.n_out++] = d.ptr[p]; vec_ok = vec_ok && Aligned16(d.ptr[p]);
+          }
+          continue;
+        }
+        if (mine) { tw.out[tw.n_out++] = d.ptr[p]; vec_ok = vec_ok && Aligned16(d.ptr[p]); }
+      }
+      MXKV_CHECK(tw.n_out <= kMaxOut) << "too many destinations for key " << ks.key;
+      Replica& r = *rep[p];
+      tw.w = r.local.data();
+      tw.w32 = mp ? static_cast<float*>(r.w32.data()) : nullptr;
+      tw.s0 = r.s0.is_none() ? nullptr : static_cast<float*>(r.s0.data());
+      tw.s1 = r.s1.is_none() ? nullptr : static_cast<float*>(r.s1.data());
+      if (two_shot) {
+        tw.begin = std::min<int64_t>(ks.size, shard * p);
+        tw.end = std::min<int64_t>(ks.size, shard * (p + 1));
+      } else {
+        tw.begin = 0; tw.end = ks.size;
+      }
+      tw.lr = lr; tw.wd = wd; tw.eta = opt_.eta;
+      tw.pad_ = vec_ok ? 1 : 0;
+      cls[p].push_back(tw);
+    }
+  }
+
+  // ---- launches: one per class per local participant --------------------------
+  const int opt_kind = fused ? opt_.kind : OPT_NONE;
+  for (auto& kv : classes) {
+    const LaunchClassKey& ck = kv.first;
+    auto& per_part = kv.second.per_part;
+    // identical grid on every rank: derived from the busiest rank's chunk count
+    std::vector<std::vector<int64_t>> prefixes(n_part);
+    const int64_t max_chunks = std::max<int64_t>(1, kv.second.max_chunks);
+    const int my_first = mp_mode ? pg->rank() : 0;
+    const int my_last = mp_mode ? pg->rank() : n_part - 1;
+    for (int p = my_first; p <= my_last; ++p) {
+      auto& w = per_part[p];
+      prefixes[p].resize(w.size() + 1);
+      int64_t acc = 0;
+      for (size_t i = 0; i < w.size(); ++i) {
+        prefixes[p][i] = acc;
+        acc += (w[i].end - w[i].begin + kChunkElems - 1) / kChunkElems;
+      }
+      prefixes[p][w.size()] = acc;
+    }
+    for (int p = my_first; p <= my_last; ++p) {
+      auto& w = per_part[p];
+      if (w.empty()) continue;
+      const int dev = part_dev[p];
+      DeviceState& d = rt->Dev(dev);
+      const size_t wbytes = w.size() * sizeof(TensorWork);
+      const size_t pbytes = prefixes[p].size() * sizeof(int64_t);
+      const size_t bytes = wbytes + pbytes;
+      const size_t off = d.ring.Alloc(bytes);
+      std::memcpy(d.ring.host(off), w.data(), wbytes);
+      std::memcpy(d.ring.host(off) + wbytes, prefixes[p].data(), pbytes);
+      DeviceGuard dg(dev);
+      CUDA_CALL(cudaMemcpyAsync(d.ring.dev(off), d.ring.host(off), bytes, cudaMemcpyHostToDevice, d.stream));
+      DenseLaunch L;
+      std::memset(&L, 0, sizeof(L));
+      L.works = reinterpret_cast<const TensorWork*>(d.ring.dev(off));
+      L.chunk_prefix = reinterpret_cast<const int64_t*>(d.ring.dev(off) + wbytes);
+      L.nworks = static_cast<int>(w.size());
+      L.total_chunks = prefixes[p].back();
+      L.dtype = ck.dtype;
+      L.opt = opt_kind;
+      L.multi_precision = ck.mp;
+      L.order = order_;
+      L.fp32_accum = (opt_kind != OPT_NONE || ck.dtype == kBfloat16 ||
+                      EnvInt("MXKV_B200_FP16_FP32_ACCUM", 0) != 0) ? 1 : 0;
+      L.rescale = opt_.rescale; L.clip = opt_.clip; L.momentum = opt_.momentum;
+      L.beta1 = static_cast<float>(opt_.beta1); L.beta2 = static_cast<float>(opt_.beta2); L.eps = opt_.eps;
+      L.sync.mode = ck.sync_mode;
+      L.sync.world = n_part;
+      L.sync.rank = p;
+      L.sync.self = d.signal_pad;
+      for (int q = 0; q < n_part; ++q)
+        L.sync.peers[q] = mp_mode ? pg->signal_pad(q) : rt->Dev(part_dev[q]).signal_pad;
+      L.grid = static_cast<int>(std::min<int64_t>(d.max_grid, max_chunks));
+      const int rc = LaunchDense(L, d.stream);
+      MXKV_CHECK(rc == 0) << "kernel launch failed: " << cudaGetErrorString(static_cast<cudaError_t>(rc));
+      rt->launches++;
+      d.ring.Commit(off, bytes, d.stream);
+    }
+  }
+
+  // ---- epilogue -------------------------------------------------------------------
+  for (size_t i = 0; i < temps.size(); ++i) {
+    DeviceGuard dg(temp_dev[i]);
+    CUDA_CALL(cudaFreeAsync(temps[i], rt->Dev(temp_dev[i]).stream));
+  }
+  if (!collective) {
+    // destinations on other GPUs were written by the root's kernel
+    for (int dev : touched) if (dev != root_dev) rt->StreamWait(dev, root_dev);
+  }
+  for (KeyState* ks : callback_keys) {
+    Replica* root = FindReplica(*ks, part_dev[mp_mode ? pg->rank() : 0]);
+    RunCallbackUpdater(*ks, *root);
+  }
+  for (auto& pc : post) CopyFromTo(pc.src, pc.dst);
+  for (int dev : touched) rt->ReleaseToUser(dev);
+}
+
+// updater_(key, merged, &local) on the caller thread (kvstore_local.h:259-277); the callee owns and
+// frees both handles (c_api.cc:3066-3080).  The embedding framework computes on its own stream:
+// fence it on the reduce, then make the engine stream wait for whatever the callback enqueued.
+void KVStore::RunCallbackUpdater(KeyState& ks, Replica& root) {
+  Runtime* rt = Runtime::Get();
+  rt->Dev(root.dev).engine_dirty = true;
+  rt->Fence(root.dev);
+  NDArray* recv = new NDArray(root.merged);
+  NDArray* local = new NDArray(root.local);
+  if (key_type_ == kStringKey && str_updater_ != nullptr) {
+    const std::string& sk = reverse_str_key_dict_[ks.key];
+    str_updater_(sk.c_str(), recv, local, updater_handle_);
+  } else {
+    MXKV_CHECK(updater_ != nullptr) << "updater not set";
+    updater_(ks.key, recv, local, updater_handle_);
+  }
+  rt->AcquireUser(root.dev);
+  for (auto& r : ks.reps) r.fresh = (&r == &root);
+}
+
+// ---------------------------------------------------------------------------
+// optimizer state access (save/load_optimizer_states; Updater.get_states/set_states,
+// python/mxnet/optimizer/updater.py:108-127)
+// ---------------------------------------------------------------------------
+void KVStore::GatherState(KeyState& ks) {
+  // sharded layout -> every replica complete.  Shard p of {w32,s0,s1} is valid on participant p.
+  Runtime* rt = Runtime::Get();
+  ProcessGroup* pg = rt->pg();
+  const int n = ks.state_world;
+  if (n <= 1) return;
+  const int64_t shard = ShardLen(ks.size, n);
+  auto gather = [&](std::function<NDArray&(Replica&)> sel) {
+    if (pg) {
+      Replica& me = ks.reps[0];
+      NDArray& mine = sel(me);
+      if (mine.is_none()) return;
+      rt->WaitAll(); pg->Barrier();
+      for (int p = 0; p < n; ++p) {
+        if (p == pg->rank()) continue;
+        const int64_t b = std::min(ks.size, shard * p), e = std::min(ks.size, shard * (p + 1));
+        if (e <= b) continue;
+        const char* src = static_cast<const char*>(mine.peer_data(p)) + b * 4;
+        char* dst = static_cast<char*>(mine.data()) + b * 4;
+        DeviceGuard dg(me.dev);
+        CUDA_CALL(cudaMemcpyAsync(dst, src, (e - b) * 4, cudaMemcpyDeviceToDevice, rt->Dev(me.dev).stream));
+      }
+      rt->WaitAll(); pg->Barrier();
+    } else {
+      for (size_t q = 0; q < ks.reps.size(); ++q) {
+        for (int p = 0; p < n && p < static_cast<int>(ks.reps.size()); ++p) {
+          if (static_cast<int>(q) == p) continue;
+          NDArray& src = sel(ks.reps[p]);
+          NDArray& dst = sel(ks.reps[q]);
+          if (src.is_none() || dst.is_none()) continue;
+          const int64_t b = std::min(ks.size, shard * p), e = std::min(ks.size, shard * (p + 1));
+          if (e <= b) continue;
+          CopyFromTo(src.Reshape({ks.size}).Slice1D(b, e), dst.Reshape({ks.size}).Slice1D(b, e));
+        }
+      }
+    }
+  };
+  gather([](Replica& r) -> NDArray& { return r.w32; });
+  gather([](Replica& r) -> NDArray& { return r.s0; });
+  gather([](Replica& r) -> NDArray& { return r.s1; });
+  ks.state_world = 0;
+}
+
+NDArray KVStore::GetState(bool str_key, int ikey, const std::string& skey, int which) {
+  LOCK();
+  KeyState& ks = GetKey(ResolveKey(str_key, ikey, skey));
+  if (ks.reps.empty()) EnsureReplica(ks, DefaultDevice());
+  GatherState(ks);
+  Replica& r = FreshReplica(ks);
+  switch (which) {
+    case 0: return r.local;
+    case 1: return r.w32;
+    case 2: return r.s0;
+    case 3: return r.s1;
+  }
+  MXKV_FATAL() << "GetState: which must be 0..3";
+}
+
+void KVStore::SetState(bool str_key, int ikey, const std::string& skey, int which, const NDArray& v) {
+  LOCK();
+  KeyState& ks = GetKey(ResolveKey(str_key, ikey, skey));
+  if (ks.reps.empty()) EnsureReplica(ks, DefaultDevice());
+  GatherState(ks);
+  MXKV_CHECK(v.size() == ks.size) << "SetState: size mismatch";
+  for (auto& r : ks.reps) {
+    NDArray* dst = nullptr;
+    const bool lowp = ks.dtype == kFloat16 || ks.dtype == kBfloat16;
+    if (which != 0) EnsureState(ks, r, opt_.multi_precision || lowp);
+    switch (which) {
+      case 0: dst = &r.local; break;
+      case 1: dst = &r.w32; break;
+      case 2: dst = &r.s0; break;
+      case 3: dst = &r.s1; break;
+      default: MXKV_FATAL() << "SetState: which must be 0..3";
+    }
+    MXKV_CHECK(!dst->is_none()) << "SetState: the active optimizer has no such state";
+    CopyFromTo(v.Reshape(dst->shape()), *dst);
+  }
+}
+
+int64_t KVStore::GetUpdateCount(bool str_key, int ikey, const std::string& skey) {
+  LOCK();
+  return GetKey(ResolveKey(str_key, ikey, skey)).count;
+}
+void KVStore::SetUpdateCount(bool str_key, int ikey, const std::string& skey, int64_t c) {
+  LOCK();
+  GetKey(ResolveKey(str_key, ikey, skey)).count = c;
+}
+
+}  // namespace mxkv

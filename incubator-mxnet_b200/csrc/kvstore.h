@@ -1,0 +1,166 @@
+// kvstore.h -- KVStoreLocal semantics (src/kvstore/kvstore_local.h:70-552) on top of
+// the fused sm_100a reduce/update/broadcast kernel.
+//
+// What is kept from the reference: the API and its observable behaviour -- key
+// bookkeeping (int or str keys, never mixed, :344-347), duplicate-init check (:230-233),
+// sort-and-group of (key, value) pairs (:440-469), push = reduce (+ updater) into the
+// stored value (:240-286), pull = copy the stored value out (:288-314), pushpull = push
+// then pull (:358-365), broadcast = init then pull (:349-356), row_sparse_pull = unique +
+// retain (:316-336), updater callback contract (c_api.cc:3066-3111).
+//
+// What is redesigned: instead of one merge buffer per key on a load-balanced root GPU
+// (CommDevice::InitMergeBuffer, comm.h:687-725) fed by n peer copies, every participating
+// GPU keeps a replica of the stored value and the reduce(+update)(+broadcast) of a whole
+// list of keys is ONE kernel launch per GPU (kernels.cu).  Large keys are sharded across the
+// GPUs (each reduces and updates 1/n and stores it to all replicas), small keys are reduced
+// redundantly by everyone (one-shot).
+#pragma once
+#include <functional>
+#include <map>
+#include <string>
+#include <unordered_map>
+#include <unordered_set>
+#include "ndarray.h"
+
+namespace mxkv {
+
+typedef void (*UpdaterFn)(int key, void* recv, void* local, void* handle);
+typedef void (*StrUpdaterFn)(const char* key, void* recv, void* local, void* handle);
+
+struct OptimizerConfig {
+  int kind = OPT_NONE;
+  bool enabled = false;
+  // kept in double: the reference computes lr/wd multipliers and Adam's bias correction in
+  // Python doubles and rounds to float once, when the value becomes an op attribute
+  double lr = 0.01, wd = 0.0, beta1 = 0.9, beta2 = 0.999;
+  float momentum = 0.f, eps = 1e-8f, eta = 1.f;
+  float rescale = 1.f, clip = -1.f;
+  bool multi_precision = false;
+  bool correct_bias = true;   // AdamW only (python/mxnet/optimizer/adamW.py:80-88)
+  std::unordered_map<int, double> lr_mult, wd_mult;
+};
+
+struct Replica {
+  int dev = -1;
+  NDArray local;     // the stored value, key dtype
+  NDArray w32;       // fp32 master (multi precision)
+  NDArray s0, s1;    // optimizer state
+  NDArray stage;     // MP mode: symmetric staging for non-symmetric gradients
+  NDArray merged;    // updater-callback path: reduce target
+  bool fresh = true;
+};
+
+struct KeyState {
+  int key = 0;
+  std::vector<int64_t> shape;
+  int dtype = kFloat32;
+  int stype = kDefaultStorage;
+  int64_t size = 0;
+  NDArray init_value;            // value handed to Init until a GPU replica exists (host memory)
+  std::vector<Replica> reps;
+  int64_t count = 0;             // Optimizer._index_update_count
+  int state_world = 0;           // number of shards the optimizer state is laid out for (0: replicated/none)
+  bool has_state = false;
+  NDArray rsp_local;             // row_sparse stored value (dense-backed rows), see kvstore_rsp.cc
+};
+
+int64_t ShardLen(int64_t size, int world);
+
+class KVStore {
+ public:
+  explicit KVStore(const std::string& type);
+  ~KVStore();
+  const std::string& type() const { return type_; }
+  int rank() const;
+  int group_size() const;
+
+  void Init(const std::vector<int>& keys, const std::vector<NDArray>& vals);
+  void Init(const std::vector<std::string>& keys, const std::vector<NDArray>& vals);
+  void Push(const std::vector<int>& keys, const std::vector<NDArray>& vals, int priority);
+  void Push(const std::vector<std::string>& keys, const std::vector<NDArray>& vals, int priority);
+  void Pull(const std::vector<int>& keys, const std::vector<NDArray*>& outs, int priority, bool ignore_sparse);
+  void Pull(const std::vector<std::string>& keys, const std::vector<NDArray*>& outs, int priority, bool ignore_sparse);
+  void PushPull(const std::vector<int>& vkeys, const std::vector<int>& okeys, const std::vector<NDArray>& vals,
+                const std::vector<NDArray*>& outs, int priority);
+  void PushPull(const std::vector<std::string>& vkeys, const std::vector<std::string>& okeys,
+                const std::vector<NDArray>& vals, const std::vector<NDArray*>& outs, int priority);
+  void Broadcast(const std::vector<int>& vkeys, const std::vector<int>& okeys, const std::vector<NDArray>& vals,
+                 const std::vector<NDArray*>& outs, int priority);
+  void Broadcast(const std::vector<std::string>& vkeys, const std::vector<std::string>& okeys,
+                 const std::vector<NDArray>& vals, const std::vector<NDArray*>& outs, int priority);
+  void PullRowSparse(const std::vector<int>& keys, const std::vector<std::pair<NDArray*, NDArray>>& val_rowids,
+                     int priority);
+  void PullRowSparse(const std::vector<std::string>& keys,
+                     const std::vector<std::pair<NDArray*, NDArray>>& val_rowids, int priority);
+
+  void SetUpdater(UpdaterFn fn, StrUpdaterFn sfn, void* handle);
+  void SetGradientCompression(const std::vector<std::pair<std::string, std::string>>& kwargs);
+  void Barrier();
+
+  // fused optimizer (B200 extension; replaces the Python Updater round trip)
+  void SetOptimizer(const std::string& name, const std::vector<std::pair<std::string, std::string>>& kwargs);
+  void SetOptimizerMult(bool str_key, int ikey, const std::string& skey, float lr_mult, float wd_mult);
+  void SetLearningRate(double lr) { opt_.lr = lr; }
+  bool has_fused_optimizer() const { return opt_.enabled; }
+  // which: 0 stored value, 1 fp32 master, 2 state0, 3 state1; gathers shards so the result is complete
+  NDArray GetState(bool str_key, int ikey, const std::string& skey, int which);
+  void SetState(bool str_key, int ikey, const std::string& skey, int which, const NDArray& v);
+  int64_t GetUpdateCount(bool str_key, int ikey, const std::string& skey);
+  void SetUpdateCount(bool str_key, int ikey, const std::string& skey, int64_t c);
+
+ private:
+  enum KeyType { kUndefinedKey = -1, kStringKey = 0, kIntKey = 1 };
+  void SetKeyType(KeyType t);
+  void LookupKeys(const std::vector<std::string>& str_keys, std::vector<int>* keys);
+  void NewStrKeys(const std::vector<std::string>& str_keys, std::vector<int>* keys);
+  int ResolveKey(bool str_key, int ikey, const std::string& skey);
+
+  void InitImpl(const std::vector<int>& keys, const std::vector<NDArray>& vals);
+  void PushImpl(const std::vector<int>& keys, const std::vector<NDArray>& vals, int priority);
+  void PullImpl(const std::vector<int>& keys, const std::vector<NDArray*>& outs, int priority, bool ignore_sparse);
+  void PushPullImpl(const std::vector<int>& vkeys, const std::vector<int>& okeys, const std::vector<NDArray>& vals,
+                    const std::vector<NDArray*>& outs, int priority);
+  void PullRowSparseImpl(const std::vector<int>& keys, const std::vector<std::pair<NDArray*, NDArray>>& vr,
+                         int priority);
+
+  struct Group {                       // one unique key of a call
+    int key;
+    std::vector<NDArray> vals;         // pushed values (dense)
+    std::vector<NDArray*> outs;        // pull destinations (may be empty)
+  };
+  // the fused reduce(+update)(+broadcast) over a list of dense key groups
+  void ReduceUpdate(std::vector<Group>& groups, bool write_outs);
+  void RunCallbackUpdater(KeyState& ks, Replica& root);
+  void PushRowSparse(KeyState& ks, const std::vector<NDArray>& vals);
+  void InitRowSparseKey(KeyState& ks, const NDArray& v);
+  void PullDenseFromRowSparse(KeyState& ks, const std::vector<NDArray*>& outs);
+
+  KeyState& GetKey(int key);
+  Replica& EnsureReplica(KeyState& ks, int dev);
+  Replica* FindReplica(KeyState& ks, int dev);
+  Replica& FreshReplica(KeyState& ks);
+  void EnsureState(KeyState& ks, Replica& r, bool mp);
+  void GatherState(KeyState& ks);
+  int DefaultDevice();
+  float KeyLR(const KeyState& ks) const;
+  float KeyWD(const KeyState& ks) const;
+
+  std::string type_;
+  bool device_mode_ = false;
+  int order_ = ORDER_DEVICE;
+  std::unordered_map<int, KeyState> keys_;
+  std::unordered_map<std::string, int> str_key_dict_;
+  std::unordered_map<int, std::string> reverse_str_key_dict_;
+  int next_str_key_ = 0;
+  KeyType key_type_ = kUndefinedKey;
+  std::unordered_set<int> warnings_printed_;
+  UpdaterFn updater_ = nullptr;
+  StrUpdaterFn str_updater_ = nullptr;
+  void* updater_handle_ = nullptr;
+  OptimizerConfig opt_;
+  std::string gc_type_ = "none";
+  float gc_threshold_ = 0.5f;
+  std::recursive_mutex mu_;
+};
+
+}  // namespace mxkv

@@ -1,0 +1,125 @@
+// runtime.h -- the host side that replaces the reference's dependency engine and
+// device plumbing for this path.
+//
+// Reference                                   | here
+// --------------------------------------------+---------------------------------------------
+// ThreadedEnginePerDevice worker pools, one   | one in-order, high-priority CUDA stream per GPU
+//   mshadow stream per worker thread, host    |   (the "engine stream"); dependencies are CUDA
+//   blocking stream->Wait() in every op       |   events between streams, the host never blocks
+//   (src/engine/threaded_engine_perdevice.cc, |   except in WaitToRead/WaitAll
+//    src/ndarray/ndarray.cc:1396-1412,1477)   |
+// ThreadedVar read/write queues               | per-call event edges user-stream -> engine-stream
+//   (src/engine/threaded_engine.cc:51-190)    |   -> user-stream (AcquireUser / ReleaseToUser)
+// CommDevice::EnableP2P (comm.h:728-770)      | EnablePeerAccess + peer-mapped signal pads
+// (no equivalent: single process only)        | ProcessGroup: one process per GPU, symmetric
+//                                             |   arena exported with cudaIpc*, host all-gather
+//                                             |   callback supplied by the embedding language
+#pragma once
+#include <deque>
+#include <memory>
+#include <mutex>
+#include <unordered_map>
+#include "base.h"
+
+namespace mxkv {
+
+// Host all-gather used only for bootstrap (IPC handle / offset exchange).  Must
+// gather `bytes` from every rank into recv[rank*bytes ...].  Returns 0 on success.
+typedef int (*AllGatherFn)(const void* send, size_t bytes, void* recv, void* ctx);
+
+class StagingRing {
+ public:
+  void Init(int dev, size_t cap);
+  void Destroy();
+  // reserve `bytes` (256-aligned) in the mirrored host/device rings; blocks only if
+  // the region is still referenced by a launch that has not finished
+  size_t Alloc(size_t bytes);
+  void Commit(size_t off, size_t bytes, cudaStream_t s);   // call after the consuming launch
+  char* host(size_t off) const { return host_ + off; }
+  char* dev(size_t off) const { return dev_ + off; }
+ private:
+  struct InFlight { size_t b, e; cudaEvent_t ev; };
+  char* host_ = nullptr;
+  char* dev_ = nullptr;
+  size_t cap_ = 0, head_ = 0;
+  std::deque<InFlight> inflight_;
+  std::vector<cudaEvent_t> pool_;
+};
+
+struct DeviceState {
+  int dev = -1;
+  cudaStream_t stream = nullptr;       // engine stream
+  cudaStream_t user_stream = nullptr;  // stream the embedding framework computes on (legacy default)
+  cudaEvent_t ev_user = nullptr;
+  cudaEvent_t ev_engine = nullptr;
+  cudaEvent_t ev_xdev = nullptr;
+  uint32_t* signal_pad = nullptr;      // this device's pad (SP mode: cudaMalloc; MP mode: in the arena)
+  StagingRing ring;
+  int max_grid = 296;
+  bool engine_dirty = false;           // engine stream has work the user stream has not been fenced on
+};
+
+struct SymPtr {                 // one symmetric allocation as seen from this process
+  void* ptr[kMaxRanks] = {nullptr};
+  bool valid = false;
+};
+
+class ProcessGroup {
+ public:
+  ProcessGroup(int rank, int world, int dev, AllGatherFn fn, void* ctx);
+  ~ProcessGroup();
+  int rank() const { return rank_; }
+  int world() const { return world_; }
+  int dev() const { return dev_; }
+  // collective: every rank must call with the same byte count, in the same order
+  SymPtr SymAlloc(size_t bytes);
+  void AllGather(const void* send, size_t bytes, void* recv);
+  void Barrier();
+  uint32_t* signal_pad(int r) const { return pads_.ptr[r] ? static_cast<uint32_t*>(pads_.ptr[r]) : nullptr; }
+  size_t arena_used() const { return used_total_; }
+ private:
+  void NewSegment(size_t min_bytes);
+  struct Segment { char* base[kMaxRanks]; size_t bytes; size_t used; };
+  int rank_, world_, dev_;
+  AllGatherFn fn_;
+  void* ctx_;
+  std::vector<Segment> segs_;
+  SymPtr pads_;
+  size_t used_total_ = 0;
+};
+
+class Runtime {
+ public:
+  static Runtime* Get();
+  DeviceState& Dev(int dev);                 // lazily creates streams, pad, ring
+  int NumDevices();
+  void EnablePeerAccess(const std::vector<int>& devs);   // SP mode, idempotent
+  bool PeerOK(int a, int b);
+  // ordering edges between the embedding framework's stream and the engine stream
+  void AcquireUser(int dev);
+  void ReleaseToUser(int dev);
+  void Fence(int dev);                       // user stream waits for everything queued on the engine stream
+  void StreamWait(int waiter_dev, int signaler_dev);
+  void SetUserStream(int dev, cudaStream_t s);
+  void WaitAll();
+  void WaitDevice(int dev);
+
+  // one-process-per-GPU mode
+  void InitProcessGroup(int rank, int world, int dev, AllGatherFn fn, void* ctx);
+  void DestroyProcessGroup();
+  ProcessGroup* pg() { return pg_.get(); }
+
+  std::recursive_mutex& mu() { return mu_; }
+  bool auto_fence = true;
+  int64_t launches = 0;                      // kernels launched by this library (bench "gpu_launches")
+  int64_t twoshot_bytes = 256 * 1024;
+ private:
+  Runtime();
+  std::recursive_mutex mu_;
+  std::unordered_map<int, std::unique_ptr<DeviceState>> devs_;
+  std::unordered_map<int64_t, bool> peer_ok_;
+  std::unique_ptr<ProcessGroup> pg_;
+  int ndev_ = -1;
+};
+
+}  // namespace mxkv

@@ -1,0 +1,363 @@
+"""Python KVStore front-end: same surface as python/mxnet/kvstore/{base,kvstore}.py.
+
+* ``KVStoreBase`` + ``KVStoreBase.register`` + ``create(name)``: the plug-in registry
+  (base.py:74-243, 406-461).  ``create`` looks the registry up first and falls back to the
+  native store, like the reference.
+* ``KVStore``: the native wrapper (kvstore.py:54-742): init / push / pull / pushpull /
+  broadcast / row_sparse_pull / set_optimizer / _set_updater / save|load_optimizer_states /
+  type / rank / num_workers / is_capable / set_gradient_compression / _barrier.
+
+To let the reference's own ``mx.kv.create`` / ``gluon.Trainer`` pick this engine up, register
+:class:`KVStore` subclasses with the reference's ``mx.kvstore.KVStoreBase.register`` (see
+INTEGRATION.md); the method set below is exactly what that registry expects.
+"""
+import ctypes
+import pickle
+
+import numpy as np
+
+from .base import _LIB, check_call, c_str, c_str_array, c_array, MXNetError, KVStoreHandle
+from .ndarray import NDArray
+from . import ndarray as _nd
+from . import optimizer as opt
+
+
+def _ctype_key_value(keys, vals):
+    """Flatten (keys, vals) key-major like base.py:32-65.  Returns (keys list, NDArray list,
+    use_str_keys)."""
+    if isinstance(keys, (tuple, list)):
+        assert len(keys) == len(vals)
+        c_keys, c_vals, use_str = [], [], None
+        for key, val in zip(keys, vals):
+            k_i, v_i, s_i = _ctype_key_value(key, val)
+            c_keys += k_i
+            c_vals += v_i
+            use_str = s_i if use_str is None else use_str
+            assert use_str == s_i, "inconsistent types of keys detected."
+        return c_keys, c_vals, use_str
+    assert isinstance(keys, (int, str)), "unexpected type for keys: " + str(type(keys))
+    use_str = isinstance(keys, str)
+    if isinstance(vals, NDArray):
+        return [keys], [vals], use_str
+    for v in vals:
+        assert isinstance(v, NDArray)
+    return [keys] * len(vals), list(vals), use_str
+
+
+def _c_keys(keys, use_str):
+    return c_str_array(keys) if use_str else c_array(ctypes.c_int, keys)
+
+
+def _c_vals(vals):
+    arr = (ctypes.c_void_p * len(vals))()
+    arr[:] = [v.handle.value for v in vals]
+    return arr
+
+
+class KVStoreBase(object):
+    """An abstract key-value store interface for data parallel training (base.py:74-243)."""
+    OPTIMIZER = "optimizer"
+    kv_registry = {}
+
+    def broadcast(self, key, value, out, priority=0):
+        raise NotImplementedError()
+
+    def pushpull(self, key, value, out=None, priority=0):
+        raise NotImplementedError()
+
+    def set_optimizer(self, optimizer):
+        raise NotImplementedError()
+
+    def is_capable(self, capability):
+        raise NotImplementedError()
+
+    def save_optimizer_states(self, fname, dump_optimizer=False):
+        raise NotImplementedError()
+
+    def load_optimizer_states(self, fname):
+        raise NotImplementedError()
+
+    @property
+    def type(self):
+        raise NotImplementedError()
+
+    @property
+    def rank(self):
+        raise NotImplementedError()
+
+    @property
+    def num_workers(self):
+        raise NotImplementedError()
+
+    @staticmethod
+    def register(klass):
+        assert isinstance(klass, type)
+        KVStoreBase.kv_registry[klass.__name__.lower()] = klass
+        return klass
+
+
+class KVStore(KVStoreBase):
+    """Native key-value store (kvstore.py:54-742) backed by libmxkv_b200.so."""
+
+    def __init__(self, handle_or_name="device"):
+        if isinstance(handle_or_name, str):
+            handle = KVStoreHandle()
+            check_call(_LIB.MXKVStoreCreate(c_str(handle_or_name), ctypes.byref(handle)))
+            self.handle = handle
+        else:
+            self.handle = handle_or_name
+        self._updater = None
+        self._updater_func = None
+        self._str_updater_func = None
+        self._optimizer = None
+        self._fused = False
+        self._last_lr = None
+        self._keys = set()
+
+    def __del__(self):
+        try:
+            check_call(_LIB.MXKVStoreFree(self.handle))
+        except Exception:
+            pass
+
+    # -- data path -------------------------------------------------------------
+    def init(self, key, value):
+        keys, vals, use_str = _ctype_key_value(key, value)
+        fn = _LIB.MXKVStoreInitEx if use_str else _LIB.MXKVStoreInit
+        check_call(fn(self.handle, len(keys), _c_keys(keys, use_str), _c_vals(vals)))
+        self._keys.update(keys)
+
+    def push(self, key, value, priority=0):
+        keys, vals, use_str = _ctype_key_value(key, value)
+        self._sync_lr()
+        fn = _LIB.MXKVStorePushEx if use_str else _LIB.MXKVStorePush
+        check_call(fn(self.handle, len(keys), _c_keys(keys, use_str), _c_vals(vals), ctypes.c_int(priority)))
+
+    def pull(self, key, out=None, priority=0, ignore_sparse=True):
+        assert out is not None
+        keys, vals, use_str = _ctype_key_value(key, out)
+        fn = _LIB.MXKVStorePullWithSparseEx if use_str else _LIB.MXKVStorePullWithSparse
+        check_call(fn(self.handle, len(keys), _c_keys(keys, use_str), _c_vals(vals), ctypes.c_int(priority),
+                      ctypes.c_bool(ignore_sparse)))
+
+    def pushpull(self, key, value, out=None, priority=0):
+        vkeys, vals, use_str = _ctype_key_value(key, value)
+        if out is not None:
+            okeys, outs, _ = _ctype_key_value(key, out)
+        else:
+            okeys, outs = vkeys, vals
+        self._sync_lr()
+        fn = _LIB.MXKVStorePushPullEx if use_str else _LIB.MXKVStorePushPull
+        check_call(fn(self.handle, len(vkeys), _c_keys(vkeys, use_str), len(okeys), _c_keys(okeys, use_str),
+                      _c_vals(vals), _c_vals(outs), ctypes.c_int(priority)))
+
+    def broadcast(self, key, value, out, priority=0):
+        vkeys, vals, use_str = _ctype_key_value(key, value)
+        okeys, outs, _ = _ctype_key_value(key, out)
+        fn = _LIB.MXKVStoreBroadcastEx if use_str else _LIB.MXKVStoreBroadcast
+        check_call(fn(self.handle, len(vkeys), _c_keys(vkeys, use_str), len(okeys), _c_keys(okeys, use_str),
+                      _c_vals(vals), _c_vals(outs), ctypes.c_int(priority)))
+        self._keys.update(vkeys)
+
+    def row_sparse_pull(self, key, out=None, priority=0, row_ids=None):
+        assert out is not None
+        assert row_ids is not None
+        if isinstance(row_ids, NDArray):
+            row_ids = [row_ids]
+        assert isinstance(row_ids, list), "row_ids should be NDArray or list of NDArray"
+        first_out = out
+        single_rowid = False
+        if len(row_ids) == 1 and isinstance(out, list):
+            single_rowid = True
+            first_out = [out[0]]
+        keys, vals, use_str = _ctype_key_value(key, first_out)
+        _, rids, _ = _ctype_key_value(key, row_ids)
+        assert len(rids) == len(vals), "the number of row_ids doesn't match the number of values"
+        fn = _LIB.MXKVStorePullRowSparseEx if use_str else _LIB.MXKVStorePullRowSparse
+        check_call(fn(self.handle, len(keys), _c_keys(keys, use_str), _c_vals(vals), _c_vals(rids),
+                      ctypes.c_int(priority)))
+        if single_rowid:
+            for out_i in out[1:]:
+                out[0].copyto(out_i)
+
+    # -- capabilities / metadata -------------------------------------------------
+    @staticmethod
+    def is_capable(capability):
+        if capability.lower() == KVStoreBase.OPTIMIZER:
+            return True
+        raise MXNetError("Unknown capability: {}".format(capability))
+
+    @property
+    def type(self):
+        t = ctypes.c_char_p()
+        check_call(_LIB.MXKVStoreGetType(self.handle, ctypes.byref(t)))
+        return t.value.decode()
+
+    @property
+    def rank(self):
+        r = ctypes.c_int()
+        check_call(_LIB.MXKVStoreGetRank(self.handle, ctypes.byref(r)))
+        return r.value
+
+    @property
+    def num_workers(self):
+        r = ctypes.c_int()
+        check_call(_LIB.MXKVStoreGetGroupSize(self.handle, ctypes.byref(r)))
+        return r.value
+
+    def set_gradient_compression(self, compression_params):
+        keys = list(compression_params.keys())
+        vals = [str(compression_params[k]) for k in keys]
+        check_call(_LIB.MXKVStoreSetGradientCompression(self.handle, len(keys), c_str_array(keys),
+                                                        c_str_array(vals)))
+
+    def _barrier(self):
+        check_call(_LIB.MXKVStoreBarrier(self.handle))
+
+    # -- optimizer ---------------------------------------------------------------------
+    def set_optimizer(self, optimizer):
+        """Recognised optimizers run fused inside the reduce kernel; anything else goes through
+        the Python updater callback like the reference (kvstore.py:559-606)."""
+        self._optimizer = optimizer
+        if getattr(optimizer, "fused_name", None):
+            kw = optimizer.fused_kwargs()
+            keys = list(kw.keys())
+            vals = [str(kw[k]) for k in keys]
+            check_call(_LIB.MXKVB200SetOptimizer(self.handle, c_str(optimizer.fused_name), len(keys),
+                                                 c_str_array(keys), c_str_array(vals)))
+            self._fused = True
+            self._last_lr = optimizer.learning_rate
+            mults = set(optimizer.lr_mult) | set(optimizer.wd_mult)
+            for k in mults:
+                self.set_mult(k, optimizer.lr_mult.get(k, 1.0), optimizer.wd_mult.get(k, 1.0))
+        else:
+            self._fused = False
+            self._set_updater(opt.get_updater(optimizer))
+
+    def set_mult(self, key, lr_mult=1.0, wd_mult=1.0):
+        if isinstance(key, str):
+            check_call(_LIB.MXKVB200SetOptimizerMult(self.handle, 0, c_str(key), ctypes.c_float(lr_mult),
+                                                     ctypes.c_float(wd_mult)))
+        else:
+            check_call(_LIB.MXKVB200SetOptimizerMult(self.handle, int(key), None, ctypes.c_float(lr_mult),
+                                                     ctypes.c_float(wd_mult)))
+
+    def _sync_lr(self):
+        if self._fused and self._optimizer is not None:
+            lr = self._optimizer.learning_rate
+            if lr != self._last_lr:
+                check_call(_LIB.MXKVB200SetLearningRate(self.handle, ctypes.c_double(lr)))
+                self._last_lr = lr
+
+    def _set_updater(self, updater):
+        """kvstore.py:674-712: int- and str-key ctypes trampolines; the callee frees the handles."""
+        self._updater = updater
+
+        def _wrap(key, recv_h, local_h, _):
+            recv = NDArray(ctypes.c_void_p(recv_h))
+            local = NDArray(ctypes.c_void_p(local_h))
+            if isinstance(key, bytes):
+                key = key.decode()
+            updater(key, recv, local)
+
+        proto = ctypes.CFUNCTYPE(None, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p)
+        sproto = ctypes.CFUNCTYPE(None, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p)
+        self._updater_func = proto(_wrap)
+        self._str_updater_func = sproto(_wrap)
+        check_call(_LIB.MXKVStoreSetUpdaterEx(self.handle, self._updater_func, self._str_updater_func, None))
+
+    def _state_handle(self, key, which):
+        out = ctypes.c_void_p()
+        if isinstance(key, str):
+            check_call(_LIB.MXKVB200GetState(self.handle, 0, c_str(key), which, ctypes.byref(out)))
+        else:
+            check_call(_LIB.MXKVB200GetState(self.handle, int(key), None, which, ctypes.byref(out)))
+        return NDArray(out) if out.value else None
+
+    def save_optimizer_states(self, fname, dump_optimizer=False):
+        """Same file role as kvstore.py:647-660 (pickle of {key: states}); for the fused path the
+        states are read back from engine memory (sharded states are gathered first)."""
+        if not self._fused:
+            assert self._updater is not None, "Cannot save states for distributed training"
+            with open(fname, "wb") as fout:
+                fout.write(self._updater.get_states(dump_optimizer))
+            return
+        states = {}
+        for k in sorted(self._keys, key=str):
+            ent = {}
+            for which, name in ((1, "weight32"), (2, "state0"), (3, "state1")):
+                h = self._state_handle(k, which)
+                if h is not None:
+                    ent[name] = h.asnumpy()
+            cnt = ctypes.c_int64()
+            if isinstance(k, str):
+                check_call(_LIB.MXKVB200GetUpdateCount(self.handle, 0, c_str(k), ctypes.byref(cnt)))
+            else:
+                check_call(_LIB.MXKVB200GetUpdateCount(self.handle, int(k), None, ctypes.byref(cnt)))
+            ent["count"] = cnt.value
+            states[k] = ent
+        payload = {"format": "mxkv_b200_fused_v1", "states": states}
+        if dump_optimizer:
+            payload["optimizer"] = self._optimizer
+        with open(fname, "wb") as fout:
+            fout.write(pickle.dumps(payload))
+
+    def load_optimizer_states(self, fname):
+        with open(fname, "rb") as fin:
+            blob = fin.read()
+        if not self._fused:
+            assert self._updater is not None, "Cannot load states for distributed training"
+            self._updater.set_states(blob)
+            return
+        payload = pickle.loads(blob)
+        assert payload.get("format") == "mxkv_b200_fused_v1", "not a fused-optimizer state file"
+        for k, ent in payload["states"].items():
+            for which, name in ((1, "weight32"), (2, "state0"), (3, "state1")):
+                if name in ent:
+                    v = _nd.array(ent[name], dtype=np.float32)
+                    if isinstance(k, str):
+                        check_call(_LIB.MXKVB200SetState(self.handle, 0, c_str(k), which, v.handle))
+                    else:
+                        check_call(_LIB.MXKVB200SetState(self.handle, int(k), None, which, v.handle))
+            if isinstance(k, str):
+                check_call(_LIB.MXKVB200SetUpdateCount(self.handle, 0, c_str(k), ctypes.c_int64(ent["count"])))
+            else:
+                check_call(_LIB.MXKVB200SetUpdateCount(self.handle, int(k), None, ctypes.c_int64(ent["count"])))
+        _nd.waitall()
+
+
+@KVStoreBase.register
+class B200Device(KVStore):
+    """``create('b200device')`` -- the name under which the engine registers itself in a
+    KVStoreBase registry (see INTEGRATION.md for registering it as 'device' in the reference)."""
+
+    def __init__(self):
+        super(B200Device, self).__init__("device")
+
+
+def create(name="local"):
+    """Creates a new KVStore (base.py:406-461): registry first, native store otherwise."""
+    if not isinstance(name, str):
+        raise TypeError("name must be a string")
+    lname = name.lower()
+    if lname in KVStoreBase.kv_registry:
+        return KVStoreBase.kv_registry[lname]()
+    return KVStore(name)
+
+
+def fence(dev_id=None):
+    """Make the caller's CUDA stream(s) wait for everything the engine has queued (async)."""
+    from .context import num_gpus
+    devs = range(num_gpus()) if dev_id is None else [dev_id]
+    for d in devs:
+        check_call(_LIB.MXKVB200Fence(ctypes.c_int(d)))
+
+
+def set_auto_fence(flag):
+    check_call(_LIB.MXKVB200SetAutoFence(ctypes.c_int(1 if flag else 0)))
+
+
+def launch_count():
+    n = ctypes.c_int64()
+    check_call(_LIB.MXKVB200GetLaunchCount(ctypes.byref(n)))
+    return n.value

@@ -1,0 +1,359 @@
+"""Minimal NDArray front-end over the C ABI (the subset of python/mxnet/ndarray/ndarray.py
+and sparse.py that the KVStore path and its tests use).  Data lives in memory owned by the
+native library (or borrowed from torch); numpy is only a host-side transport here."""
+import ctypes
+
+import numpy as np
+
+from .base import _LIB, check_call, MXNetError
+from .context import Context, cpu, gpu
+
+# mshadow type flags, 3rdparty/mshadow/mshadow/base.h:352-366
+_DTYPE_NP_TO_MX = {np.dtype(np.float32): 0, np.dtype(np.float64): 1, np.dtype(np.float16): 2,
+                   np.dtype(np.uint8): 3, np.dtype(np.int32): 4, np.dtype(np.int8): 5, np.dtype(np.int64): 6}
+_DTYPE_MX_TO_NP = {v: k for k, v in _DTYPE_NP_TO_MX.items()}
+BFLOAT16 = 12
+_STYPE = {"default": 0, "row_sparse": 1}
+
+
+def _mx_dtype(dtype):
+    if isinstance(dtype, str) and dtype in ("bfloat16", "bf16"):
+        return BFLOAT16
+    if isinstance(dtype, int):
+        return dtype
+    return _DTYPE_NP_TO_MX[np.dtype(dtype)]
+
+
+def _bf16_to_f32(u16):
+    return (u16.astype(np.uint32) << 16).view(np.float32)
+
+
+def _f32_to_bf16(f32):
+    u = np.ascontiguousarray(f32, np.float32).view(np.uint32).astype(np.uint64)
+    return ((u + 0x7FFF + ((u >> 16) & 1)) >> 16).astype(np.uint16)
+
+
+class NDArray(object):
+    """Handle to a native array.  ``handle`` is the opaque NDArrayHandle."""
+    __slots__ = ("handle", "_keep", "__weakref__")
+
+    def __init__(self, handle, keep=None):
+        self.handle = handle if isinstance(handle, ctypes.c_void_p) else ctypes.c_void_p(handle)
+        self._keep = keep     # objects that own borrowed memory (e.g. a torch tensor)
+
+    def __del__(self):
+        try:
+            if self.handle:
+                _LIB.MXNDArrayFree(self.handle)
+        except Exception:  # interpreter shutdown
+            pass
+
+    # -- metadata ----------------------------------------------------------
+    @property
+    def shape(self):
+        ndim = ctypes.c_int()
+        pdata = ctypes.POINTER(ctypes.c_int64)()
+        check_call(_LIB.MXNDArrayGetShape64(self.handle, ctypes.byref(ndim), ctypes.byref(pdata)))
+        return tuple(int(pdata[i]) for i in range(ndim.value))
+
+    @property
+    def size(self):
+        n = 1
+        for d in self.shape:
+            n *= d
+        return n
+
+    @property
+    def mx_dtype(self):
+        t = ctypes.c_int()
+        check_call(_LIB.MXNDArrayGetDType(self.handle, ctypes.byref(t)))
+        return t.value
+
+    @property
+    def dtype(self):
+        t = self.mx_dtype
+        return "bfloat16" if t == BFLOAT16 else _DTYPE_MX_TO_NP[t].type
+
+    @property
+    def context(self):
+        dt, di = ctypes.c_int(), ctypes.c_int()
+        check_call(_LIB.MXNDArrayGetContext(self.handle, ctypes.byref(dt), ctypes.byref(di)))
+        return Context(Context.devtype2str[dt.value], di.value)
+
+    ctx = context
+
+    @property
+    def stype(self):
+        s = ctypes.c_int()
+        check_call(_LIB.MXNDArrayGetStorageType(self.handle, ctypes.byref(s)))
+        return {0: "default", 1: "row_sparse", 2: "csr"}.get(s.value, "undefined")
+
+    @property
+    def data_ptr(self):
+        p = ctypes.c_void_p()
+        check_call(_LIB.MXNDArrayGetData(self.handle, ctypes.byref(p)))
+        return p.value or 0
+
+    # -- sync ----------------------------------------------------------------
+    def wait_to_read(self):
+        check_call(_LIB.MXNDArrayWaitToRead(self.handle))
+
+    # -- host transport --------------------------------------------------------
+    def asnumpy(self, raw=False):
+        if self.stype == "row_sparse":
+            return self.todense_numpy()
+        t = self.mx_dtype
+        npdt = np.dtype(np.uint16) if t == BFLOAT16 else _DTYPE_MX_TO_NP[t]
+        out = np.empty(self.shape, npdt)
+        check_call(_LIB.MXNDArraySyncCopyToCPU(self.handle, out.ctypes.data_as(ctypes.c_void_p),
+                                               ctypes.c_size_t(out.size)))
+        if t == BFLOAT16 and not raw:
+            return _bf16_to_f32(out)
+        return out
+
+    def _sync_copyfrom(self, arr):
+        t = self.mx_dtype
+        if t == BFLOAT16:
+            arr = np.asarray(arr)
+            src = arr if arr.dtype == np.uint16 else _f32_to_bf16(arr.astype(np.float32))
+        else:
+            src = np.ascontiguousarray(arr, _DTYPE_MX_TO_NP[t])
+        src = np.ascontiguousarray(src)
+        if src.size != self.size:
+            src = np.ascontiguousarray(np.broadcast_to(src, self.shape))
+        check_call(_LIB.MXNDArraySyncCopyFromCPU(self.handle, src.ctypes.data_as(ctypes.c_void_p),
+                                                 ctypes.c_size_t(src.size)))
+
+    def __setitem__(self, key, value):
+        if not (isinstance(key, slice) and key == slice(None)):
+            raise NotImplementedError("only a[:] = value is supported")
+        if isinstance(value, NDArray):
+            value.copyto(self)
+        elif np.isscalar(value):
+            self._sync_copyfrom(np.full(self.shape, value))
+        else:
+            self._sync_copyfrom(np.asarray(value))
+
+    def copyto(self, other):
+        if isinstance(other, Context):
+            out = empty(self.shape, other, self.dtype)
+            self.copyto(out)
+            return out
+        if self.stype == "row_sparse":
+            other[:] = self.todense_numpy()
+            return other
+        check_call(_LIB.MXNDArraySyncCopyFromNDArray(other.handle, self.handle, ctypes.c_int(-1)))
+        return other
+
+    def copy(self):
+        return self.copyto(self.context)
+
+    def as_in_context(self, ctx):
+        return self if ctx == self.context else self.copyto(ctx)
+
+    def reshape(self, *shape):
+        if len(shape) == 1 and isinstance(shape[0], (tuple, list)):
+            shape = tuple(shape[0])
+        dims = (ctypes.c_int64 * len(shape))(*shape)
+        out = ctypes.c_void_p()
+        check_call(_LIB.MXNDArrayReshape64(self.handle, len(shape), dims, ctypes.c_bool(False), ctypes.byref(out)))
+        return NDArray(out, keep=self._keep)
+
+    def astype(self, dtype):
+        out = empty(self.shape, self.context, dtype)
+        out[:] = self.asnumpy()
+        return out
+
+    def tostype(self, stype):
+        if stype == self.stype:
+            return self
+        if stype == "row_sparse":
+            return row_sparse_array(self.asnumpy(), ctx=self.context, dtype=self.dtype)
+        if stype == "default":
+            return array(self.asnumpy(), ctx=self.context, dtype=self.dtype)
+        raise ValueError("unknown stype " + stype)
+
+    # -- torch views: the "embedding framework" side used by updater callbacks -------------
+    def as_torch(self):
+        """Zero-copy torch view of a dense array (DLPack, c_api.h:976-1002)."""
+        import torch
+        from torch.utils import dlpack as _dl
+        ptr = ctypes.c_void_p()
+        check_call(_LIB.MXNDArrayToDLPack(self.handle, ctypes.byref(ptr)))
+        ctypes.pythonapi.PyCapsule_New.restype = ctypes.py_object
+        ctypes.pythonapi.PyCapsule_New.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p]
+        cap = ctypes.pythonapi.PyCapsule_New(ptr, b"dltensor", None)
+        t = _dl.from_dlpack(cap)
+        return t
+
+    def _binary_inplace(self, other, op):
+        t = self.as_torch()
+        o = other.as_torch().to(t.device) if isinstance(other, NDArray) else other
+        getattr(t, op)(o)
+        return self
+
+    def __iadd__(self, other):
+        return self._binary_inplace(other, "add_")
+
+    def __isub__(self, other):
+        return self._binary_inplace(other, "sub_")
+
+    def __imul__(self, other):
+        return self._binary_inplace(other, "mul_")
+
+    def _binary(self, other, op):
+        out = self.copy()
+        return out._binary_inplace(other, op)
+
+    def __add__(self, other):
+        return self._binary(other, "add_")
+
+    def __sub__(self, other):
+        return self._binary(other, "sub_")
+
+    def __mul__(self, other):
+        return self._binary(other, "mul_")
+
+    __radd__ = __add__
+    __rmul__ = __mul__
+
+    def __repr__(self):
+        return "<NDArray %s @%s %s %s>" % ("x".join(map(str, self.shape)), self.context, self.dtype, self.stype)
+
+    # -- row_sparse --------------------------------------------------------------
+    @property
+    def indices(self):
+        out = ctypes.c_void_p()
+        check_call(_LIB.MXNDArrayGetAuxNDArray(self.handle, 0, ctypes.byref(out)))
+        return NDArray(out, keep=self)
+
+    @property
+    def data(self):
+        out = ctypes.c_void_p()
+        check_call(_LIB.MXNDArrayGetDataNDArray(self.handle, ctypes.byref(out)))
+        return NDArray(out, keep=self)
+
+    def todense_numpy(self):
+        shape = self.shape
+        idx = self.indices.asnumpy()
+        t = self.mx_dtype
+        out = np.zeros(shape, np.float32 if t == BFLOAT16 else _DTYPE_MX_TO_NP[t])
+        if idx.size:
+            out[idx] = self.data.asnumpy()
+        return out
+
+
+def empty(shape, ctx=None, dtype=np.float32, stype="default"):
+    if isinstance(shape, int):
+        shape = (shape,)
+    ctx = ctx or cpu()
+    cshape = (ctypes.c_int64 * len(shape))(*shape)
+    out = ctypes.c_void_p()
+    if stype == "row_sparse":
+        aux_type = (ctypes.c_int * 1)(6)
+        aux_ndims = (ctypes.c_int * 1)(1)
+        aux_shape = (ctypes.c_int64 * 1)(shape[0])
+        check_call(_LIB.MXNDArrayCreateSparseEx64(1, cshape, len(shape), ctx.device_typeid, ctx.device_id, 0,
+                                                  _mx_dtype(dtype), 1, aux_type, aux_ndims, aux_shape,
+                                                  ctypes.byref(out)))
+    else:
+        check_call(_LIB.MXNDArrayCreate64(cshape, len(shape), ctx.device_typeid, ctx.device_id, 0,
+                                          _mx_dtype(dtype), ctypes.byref(out)))
+    return NDArray(out)
+
+
+def array(source, ctx=None, dtype=None):
+    src = np.asarray(source)
+    if dtype is None:
+        dtype = src.dtype if src.dtype in _DTYPE_NP_TO_MX and src.dtype != np.float64 else np.float32
+    out = empty(src.shape, ctx, dtype)
+    out._sync_copyfrom(src)
+    return out
+
+
+def zeros(shape, ctx=None, dtype=np.float32, stype="default"):
+    if isinstance(shape, int):
+        shape = (shape,)
+    if stype == "row_sparse":
+        return row_sparse_array(np.zeros(shape, np.float32), ctx=ctx, dtype=dtype)
+    out = empty(shape, ctx, dtype)
+    out._sync_copyfrom(np.zeros(shape, np.float32))
+    return out
+
+
+def ones(shape, ctx=None, dtype=np.float32):
+    if isinstance(shape, int):
+        shape = (shape,)
+    out = empty(shape, ctx, dtype)
+    out._sync_copyfrom(np.ones(shape, np.float32))
+    return out
+
+
+def full(shape, val, ctx=None, dtype=np.float32):
+    if isinstance(shape, int):
+        shape = (shape,)
+    out = empty(shape, ctx, dtype)
+    out._sync_copyfrom(np.full(shape, val, np.float32))
+    return out
+
+
+def row_sparse_array(arg, shape=None, ctx=None, dtype=np.float32):
+    """row_sparse from a dense numpy array (non-zero rows kept) or a (data, indices) pair."""
+    if isinstance(arg, tuple):
+        data, indices = np.asarray(arg[0]), np.asarray(arg[1], np.int64)
+        assert shape is not None
+    else:
+        dense = np.asarray(arg)
+        shape = dense.shape
+        flat = dense.reshape(shape[0], -1)
+        indices = np.where(np.any(flat != 0, axis=1))[0].astype(np.int64)
+        data = dense[indices]
+    out = empty(shape, ctx, dtype, stype="row_sparse")
+    vals = empty((len(indices),) + tuple(shape[1:]), cpu(), dtype)
+    idx = empty((len(indices),), cpu(), np.int64)
+    if len(indices):
+        vals._sync_copyfrom(data)
+        idx._sync_copyfrom(indices)
+    check_call(_LIB.MXNDArraySyncCopyFromNDArray(out.handle, vals.handle, ctypes.c_int(-1)))
+    check_call(_LIB.MXNDArraySyncCopyFromNDArray(out.handle, idx.handle, ctypes.c_int(0)))
+    return out
+
+
+_TORCH_TO_MX = None
+
+
+def from_torch(t):
+    """Borrow a contiguous torch tensor's memory (no copy).  The tensor is kept alive by the
+    returned NDArray."""
+    import torch
+    global _TORCH_TO_MX
+    if _TORCH_TO_MX is None:
+        _TORCH_TO_MX = {torch.float32: 0, torch.float64: 1, torch.float16: 2, torch.uint8: 3, torch.int32: 4,
+                        torch.int8: 5, torch.int64: 6, torch.bfloat16: 12}
+    if not t.is_contiguous():
+        raise MXNetError("from_torch needs a contiguous tensor")
+    shape = tuple(t.shape) if t.dim() > 0 else (1,)
+    cshape = (ctypes.c_int64 * len(shape))(*shape)
+    if t.is_cuda:
+        dev_type, dev_id = 2, t.device.index if t.device.index is not None else torch.cuda.current_device()
+    else:
+        dev_type, dev_id = (3 if t.is_pinned() else 1), 0
+    out = ctypes.c_void_p()
+    check_call(_LIB.MXKVB200NDArrayFromPtr(ctypes.c_void_p(t.data_ptr()), cshape, len(shape), dev_type, dev_id,
+                                           _TORCH_TO_MX[t.dtype], ctypes.byref(out)))
+    return NDArray(out, keep=t)
+
+
+def empty_symmetric(shape, dtype=np.float32):
+    """Collective allocation in the peer-mapped arena (one-process-per-GPU mode); every rank must
+    call it in the same order with the same shape."""
+    if isinstance(shape, int):
+        shape = (shape,)
+    cshape = (ctypes.c_int64 * len(shape))(*shape)
+    out = ctypes.c_void_p()
+    check_call(_LIB.MXKVB200NDArrayCreateSymmetric(cshape, len(shape), _mx_dtype(dtype), ctypes.byref(out)))
+    return NDArray(out)
+
+
+def waitall():
+    check_call(_LIB.MXNDArrayWaitAll())

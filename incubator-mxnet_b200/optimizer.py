@@ -1,0 +1,248 @@
+"""Optimizer descriptors mirroring python/mxnet/optimizer/{optimizer,sgd,adam,adamW,updater}.py.
+
+Two roles:
+* describe the hyper-parameters of the optimizers that have a fused kernel in the native
+  engine (SGD / SGD-momentum / multi-precision SGD, Adam, AdamW, Test) -- ``KVStore.set_optimizer``
+  hands them to ``MXKVB200SetOptimizer`` and the update then runs inside the reduce kernel;
+* provide the generic ``Updater`` callback (updater.py:39-93) for any other Optimizer object:
+  the store reduces on the GPU and calls back into Python, exactly like the reference.  The
+  non-fused ``step`` arithmetic below runs as torch ops on the caller's stream.
+"""
+import math
+import pickle
+
+import numpy as np
+
+from .ndarray import NDArray
+
+
+class Optimizer(object):
+    """Base class (python/mxnet/optimizer/optimizer.py:37-352): rescale_grad, clip_gradient,
+    learning rate (+ scheduler), wd, per-index lr/wd multipliers and update counts."""
+    opt_registry = {}
+    fused_name = None
+
+    def __init__(self, rescale_grad=1., param_idx2name=None, wd=0., clip_gradient=None, learning_rate=None,
+                 lr_scheduler=None, begin_num_update=0, multi_precision=False, param_dict=None,
+                 aggregate_num=None, use_fused_step=None, **kwargs):
+        self.rescale_grad = rescale_grad
+        self.lr_scheduler = lr_scheduler
+        if learning_rate is None:
+            learning_rate = 0.01
+        self.lr = learning_rate
+        if self.lr_scheduler is not None:
+            self.lr_scheduler.base_lr = learning_rate
+        self.wd = wd
+        self.lr_mult = {}
+        self.wd_mult = {}
+        self.begin_num_update = begin_num_update
+        self.num_update = begin_num_update
+        self._index_update_count = {}
+        self.clip_gradient = clip_gradient
+        self.multi_precision = multi_precision
+        self.idx2name = dict(param_idx2name or {})
+        self.param_dict = param_dict or {}
+
+    @staticmethod
+    def register(klass):
+        Optimizer.opt_registry[klass.__name__.lower()] = klass
+        return klass
+
+    @staticmethod
+    def create_optimizer(name, **kwargs):
+        if name.lower() in Optimizer.opt_registry:
+            return Optimizer.opt_registry[name.lower()](**kwargs)
+        raise ValueError("Cannot find optimizer %s" % name)
+
+    @property
+    def learning_rate(self):
+        if self.lr_scheduler is not None:
+            return self.lr_scheduler(self.num_update)
+        return self.lr
+
+    def set_learning_rate(self, lr):
+        if self.lr_scheduler is not None:
+            raise UserWarning("LRScheduler of the optimizer has already been defined.")
+        self.lr = lr
+
+    def set_lr_mult(self, args_lr_mult):
+        self.lr_mult = dict(args_lr_mult)
+
+    def set_wd_mult(self, args_wd_mult):
+        self.wd_mult = dict(args_wd_mult)
+
+    def _update_count(self, index):
+        self._index_update_count[index] = self._index_update_count.get(index, self.begin_num_update) + 1
+        self.num_update = max(self._index_update_count[index], self.num_update)
+
+    def _get_lr(self, index):
+        lr = self.learning_rate
+        name = self.idx2name.get(index, index)
+        return lr * self.lr_mult.get(name, self.lr_mult.get(index, 1.0))
+
+    def _get_wd(self, index):
+        name = self.idx2name.get(index, index)
+        return self.wd * self.wd_mult.get(name, self.wd_mult.get(index, 1.0))
+
+    # hyper-parameters handed to the native fused kernel
+    def fused_kwargs(self):
+        kw = {"learning_rate": self.learning_rate, "wd": self.wd, "rescale_grad": self.rescale_grad,
+              "multi_precision": bool(self.multi_precision)}
+        if self.clip_gradient is not None:
+            kw["clip_gradient"] = self.clip_gradient
+        return kw
+
+    # non-fused path (torch ops on views of the native arrays)
+    def create_state(self, index, weight):
+        return None
+
+    def step(self, index, weight, grad, state):
+        raise NotImplementedError()
+
+
+register = Optimizer.register
+create = Optimizer.create_optimizer
+
+
+def _prep_grad(opt, index, w, g):
+    import torch
+    g = g.to(torch.float32) * opt.rescale_grad
+    if opt.clip_gradient is not None:
+        g = torch.clamp(g, -opt.clip_gradient, opt.clip_gradient)
+    return g + opt._get_wd(index) * w
+
+
+@register
+class SGD(Optimizer):
+    """python/mxnet/optimizer/sgd.py; fused kernels sgd_update / sgd_mom_update / mp_sgd_*."""
+    fused_name = "sgd"
+
+    def __init__(self, learning_rate=0.1, momentum=0.0, lazy_update=False, multi_precision=False, **kwargs):
+        super(SGD, self).__init__(learning_rate=learning_rate, multi_precision=multi_precision, **kwargs)
+        self.momentum = momentum
+        self.lazy_update = lazy_update
+
+    def fused_kwargs(self):
+        kw = super(SGD, self).fused_kwargs()
+        kw["momentum"] = self.momentum
+        return kw
+
+    def create_state(self, index, weight):
+        import torch
+        return torch.zeros_like(weight.as_torch(), dtype=torch.float32) if self.momentum != 0.0 else None
+
+    def step(self, index, weight, grad, state):          # sgd.py:118-154
+        w, g = weight.as_torch(), grad.as_torch()
+        lr = self._get_lr(index)
+        g = _prep_grad(self, index, w, g)
+        if state is not None:
+            state.mul_(self.momentum).sub_(lr * g)
+            w.add_(state)
+        else:
+            w.sub_(lr * g)
+
+
+@register
+class Adam(Optimizer):
+    """python/mxnet/optimizer/adam.py; fused kernel adam_update."""
+    fused_name = "adam"
+
+    def __init__(self, learning_rate=0.001, beta1=0.9, beta2=0.999, epsilon=1e-8, lazy_update=False, **kwargs):
+        super(Adam, self).__init__(learning_rate=learning_rate, **kwargs)
+        self.beta1, self.beta2, self.epsilon, self.lazy_update = beta1, beta2, epsilon, lazy_update
+
+    def fused_kwargs(self):
+        kw = super(Adam, self).fused_kwargs()
+        kw.update(beta1=self.beta1, beta2=self.beta2, epsilon=self.epsilon)
+        return kw
+
+    def create_state(self, index, weight):
+        import torch
+        w = weight.as_torch()
+        return (torch.zeros_like(w, dtype=torch.float32), torch.zeros_like(w, dtype=torch.float32))
+
+    def step(self, index, weight, grad, state):          # adam.py:107-147
+        import torch
+        w, g = weight.as_torch(), grad.as_torch()
+        t = self._index_update_count[index]
+        lr = self._get_lr(index) * math.sqrt(1. - self.beta2 ** t) / (1. - self.beta1 ** t)
+        g = _prep_grad(self, index, w, g)
+        mean, var = state
+        mean.mul_(self.beta1).add_((1. - self.beta1) * g)
+        var.mul_(self.beta2).add_((1. - self.beta2) * g * g)
+        w.sub_(lr * mean / (torch.sqrt(var) + self.epsilon))
+
+
+@register
+class AdamW(Optimizer):
+    """python/mxnet/optimizer/adamW.py; fused kernel _adamw_update / _mp_adamw_update
+    (decoupled weight decay, src/operator/contrib/adamw-inl.h:101-124)."""
+    fused_name = "adamw"
+
+    def __init__(self, learning_rate=0.001, beta1=0.9, beta2=0.999, epsilon=1e-6, correct_bias=True,
+                 eta=1.0, **kwargs):
+        super(AdamW, self).__init__(learning_rate=learning_rate, **kwargs)
+        self.beta1, self.beta2, self.epsilon, self.eta = beta1, beta2, epsilon, eta
+        self.correct_bias = correct_bias
+
+    def fused_kwargs(self):
+        kw = super(AdamW, self).fused_kwargs()
+        kw.update(beta1=self.beta1, beta2=self.beta2, epsilon=self.epsilon, eta=self.eta,
+                  correct_bias=bool(self.correct_bias))
+        return kw
+
+
+@register
+class Test(Optimizer):
+    """The Test optimizer (optimizer.py:561-577): w -= lr * (rescale_grad * g + wd * w)."""
+    fused_name = "test"
+
+    def create_state(self, index, weight):
+        return None
+
+    def step(self, index, weight, grad, state):
+        w, g = weight.as_torch(), grad.as_torch()
+        w.sub_(self._get_lr(index) * (self.rescale_grad * g + self._get_wd(index) * w))
+
+
+class Updater(object):
+    """The kvstore updater callback (python/mxnet/optimizer/updater.py:30-127)."""
+
+    def __init__(self, optimizer):
+        self.optimizer = optimizer
+        self.states = {}
+
+    def __call__(self, index, grad, weight):
+        if index not in self.states:
+            self.states[index] = self.optimizer.create_state(index, weight)
+        self.optimizer._update_count(index)
+        self.optimizer.step(index, weight, grad, self.states[index])
+
+    def get_states(self, dump_optimizer=False):
+        def host(s):
+            if s is None:
+                return None
+            if isinstance(s, tuple):
+                return tuple(host(x) for x in s)
+            return s.detach().cpu().numpy()
+        states = {k: host(v) for k, v in self.states.items()}
+        return pickle.dumps((states, self.optimizer) if dump_optimizer else states)
+
+    def set_states(self, states):
+        import torch
+        states = pickle.loads(states)
+        if isinstance(states, tuple) and len(states) == 2 and isinstance(states[1], Optimizer):
+            states, self.optimizer = states
+
+        def dev(s):
+            if s is None:
+                return None
+            if isinstance(s, tuple):
+                return tuple(dev(x) for x in s)
+            return torch.from_numpy(np.asarray(s))
+        self.states = {k: dev(v) for k, v in states.items()}
+        self._host_states = True
+
+
+def get_updater(optimizer):
+    return Updater(optimizer)

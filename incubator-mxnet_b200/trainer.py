@@ -1,0 +1,138 @@
+"""Trainer: the driver loop of python/mxnet/gluon/trainer.py (step -> _allreduce_grads ->
+kv.pushpull per parameter with priority -i, update on kvstore) for torch parameters.
+
+``params`` is a list of torch Parameters (one replica per process: one-process-per-GPU mode or a
+single GPU), or a list of lists -- ``params[i][d]`` being parameter i's replica on device d --
+for the reference's single-process multi-GPU layout (param.list_data()/list_grad()).
+"""
+from . import kvstore as _kv
+from . import optimizer as _opt
+from .ndarray import from_torch
+
+
+class Trainer(object):
+    def __init__(self, params, optimizer, optimizer_params=None, kvstore="device", update_on_kvstore=None,
+                 batched=True):
+        self._params = [p if isinstance(p, (list, tuple)) else [p] for p in params]
+        optimizer_params = dict(optimizer_params or {})
+        self._scale = float(optimizer_params.get("rescale_grad", 1.0))
+        if isinstance(optimizer, _opt.Optimizer):
+            assert not optimizer_params, "optimizer_params must be None if optimizer is an Optimizer instance"
+            self._optimizer = optimizer
+        else:
+            self._optimizer = _opt.create(optimizer, **optimizer_params)
+        self._kvstore_arg = kvstore
+        self._update_on_kvstore_arg = update_on_kvstore
+        self._kv_initialized = False
+        self._kvstore = None
+        self._update_on_kvstore = None
+        self._batched = batched
+        self._grads = None
+        self._weights = None
+
+    @property
+    def learning_rate(self):
+        return self._optimizer.learning_rate
+
+    def set_learning_rate(self, lr):
+        self._optimizer.set_learning_rate(lr)
+
+    def _init_kvstore(self):
+        """trainer.py:188-277 (dense, single-machine rows of the decision table)."""
+        kv = self._kvstore_arg
+        if isinstance(kv, str):
+            kv = _kv.create(kv)
+        self._kvstore = kv
+        uok = self._update_on_kvstore_arg
+        if kv is None:
+            uok = False
+        elif uok is None:
+            uok = kv.is_capable(_kv.KVStoreBase.OPTIMIZER)
+        elif uok and not kv.is_capable(_kv.KVStoreBase.OPTIMIZER):
+            raise ValueError("Please set update_on_kvstore=False when training with " + str(type(kv)))
+        self._update_on_kvstore = uok
+        self._weights = [[from_torch(p.data) for p in reps] for reps in self._params]
+        if kv is not None:
+            if uok:
+                kv.set_optimizer(self._optimizer)
+            # _init_params (trainer.py:155-176): broadcast(idx, w0, all_w)
+            idx = list(range(len(self._params)))
+            kv.broadcast(idx, [w[0] for w in self._weights], [w for w in self._weights])
+        self._kv_initialized = True
+
+    def _bind_grads(self):
+        self._grads = [[from_torch(p.grad) for p in reps] for reps in self._params]
+        self._grad_ptrs = [[p.grad.data_ptr() for p in reps] for reps in self._params]
+
+    def _allreduce_grads(self):
+        """trainer.py:385-409, with every parameter in ONE call when ``batched`` (one launch per
+        GPU instead of one per parameter; the C ABI has always accepted key lists)."""
+        if self._grads is None or any(p.grad.data_ptr() != q for reps, ptrs in zip(self._params, self._grad_ptrs)
+                                      for p, q in zip(reps, ptrs)):
+            self._bind_grads()
+        kv = self._kvstore
+        idx = list(range(len(self._params)))
+        if self._batched:
+            if self._update_on_kvstore:
+                kv.pushpull(idx, self._grads, out=self._weights, priority=0)
+            else:
+                kv.pushpull(idx, self._grads, priority=0)
+        else:
+            for i in idx:
+                if self._update_on_kvstore:
+                    kv.pushpull(i, self._grads[i], out=self._weights[i], priority=-i)
+                else:
+                    kv.pushpull(i, self._grads[i], priority=-i)
+
+    def step(self, batch_size, ignore_stale_grad=False):
+        """trainer.py:334-361: rescale_grad = scale / batch_size, allreduce, update."""
+        self._optimizer.rescale_grad = self._scale / batch_size
+        if not self._kv_initialized:
+            self._init_kvstore()
+        elif self._update_on_kvstore and self._kvstore is not None and \
+                getattr(self._kvstore, "_last_rescale", None) != self._optimizer.rescale_grad:
+            self._kvstore.set_optimizer(self._optimizer)
+        if self._kvstore is not None:
+            self._kvstore._last_rescale = self._optimizer.rescale_grad
+            self._allreduce_grads()
+        if not self._update_on_kvstore:
+            self._update()
+
+    def allreduce_grads(self):
+        if not self._kv_initialized:
+            self._init_kvstore()
+        assert not self._update_on_kvstore, \
+            "allreduce_grads() when parameters are updated on kvstore is not supported."
+        self._allreduce_grads()
+
+    def _update(self):
+        """trainer.py:444-480: per-device local updaters (non-fused torch ops)."""
+        if not hasattr(self, "_updaters"):
+            ndev = len(self._params[0])
+            self._updaters = [_opt.get_updater(self._optimizer) for _ in range(ndev)]
+        if self._grads is None:
+            self._bind_grads()
+        for i, (ws, gs) in enumerate(zip(self._weights, self._grads)):
+            for upd, w, g in zip(self._updaters, ws, gs):
+                upd(i, g, w)
+
+    def save_states(self, fname):
+        assert self._kv_initialized
+        if self._update_on_kvstore:
+            self._kvstore.save_optimizer_states(fname, dump_optimizer=True)
+        else:
+            with open(fname, "wb") as f:
+                f.write(self._updaters[0].get_states(dump_optimizer=True))
+
+    def load_states(self, fname):
+        if not self._kv_initialized:
+            self._init_kvstore()
+        if self._update_on_kvstore:
+            self._kvstore.load_optimizer_states(fname)
+        else:
+            with open(fname, "rb") as f:
+                blob = f.read()
+            if not hasattr(self, "_updaters"):
+                self._updaters = [_opt.get_updater(self._optimizer) for _ in range(len(self._params[0]))]
+            for u in self._updaters:
+                u.set_states(blob)

@@ -11,6 +11,10 @@
  * left-to-right association); the file MUST be compiled with
  * -ffp-contract=off so the compiler does not fuse a*b+c into an fma.
  *
+ * The dense optimizer loops carry an OpenMP pragma (elementwise, order-free) like the
+ * reference's CPU Kernel<OP, cpu>::Launch (src/operator/mxnet_op.h) so the CPU baseline can
+ * use every host core.
+ *
  * Pinning: the dense-sum routines are checked bit-for-bit against the
  * reference's own mshadow expression templates compiled from
  * /root/reference/3rdparty/mshadow (oracle/ref_harness.cc -> oracle/_ref/), and
@@ -172,6 +176,7 @@ static inline float clipf(float x, float b) { return x > b ? b : (x < -b ? -b : 
 /* SGDKernel, src/operator/optimizer_op-inl.h:377-390 (DType = float) */
 void kvo_sgd_update_f32(int64_t E, float* out, const float* w, const float* g,
                         float lr, float wd, float rescale, float clip) {
+#pragma omp parallel for schedule(static) if (E >= 200000)
   for (int64_t i = 0; i < E; ++i) {
     float r = rescale * g[i];
     if (clip >= 0.0f) r = clipf(r, clip);
@@ -183,6 +188,7 @@ void kvo_sgd_update_f32(int64_t E, float* out, const float* w, const float* g,
 /* SGDMomKernel, optimizer_op-inl.h:590-606 */
 void kvo_sgd_mom_update_f32(int64_t E, float* out, float* mom, const float* w, const float* g,
                             float lr, float wd, float momentum, float rescale, float clip) {
+#pragma omp parallel for schedule(static) if (E >= 200000)
   for (int64_t i = 0; i < E; ++i) {
     float r = rescale * g[i];
     if (clip >= 0.0f) r = clipf(r, clip);
@@ -205,6 +211,7 @@ static inline void store_lp(uint16_t* out_lp, int64_t i, float w, int lp_kind) {
 }
 void kvo_mp_sgd_update(int64_t E, uint16_t* out_lp, int lp_kind, float* w32, const float* g,
                        float lr, float wd, float rescale, float clip) {
+#pragma omp parallel for schedule(static) if (E >= 200000)
   for (int64_t i = 0; i < E; ++i) {
     float w = w32[i];
     float r = rescale * g[i];
@@ -218,6 +225,7 @@ void kvo_mp_sgd_update(int64_t E, uint16_t* out_lp, int lp_kind, float* w32, con
 void kvo_mp_sgd_mom_update(int64_t E, uint16_t* out_lp, int lp_kind, float* w32, float* mom,
                            const float* g, float lr, float wd, float momentum, float rescale,
                            float clip) {
+#pragma omp parallel for schedule(static) if (E >= 200000)
   for (int64_t i = 0; i < E; ++i) {
     float w = w32[i];
     float m = mom[i];
@@ -238,6 +246,7 @@ void kvo_mp_sgd_mom_update(int64_t E, uint16_t* out_lp, int lp_kind, float* w32,
 void kvo_adam_update_f32(int64_t E, float* out, float* mean, float* var, const float* w,
                          const float* g, float lr, float wd, float beta1, float beta2,
                          float eps, float rescale, float clip) {
+#pragma omp parallel for schedule(static) if (E >= 200000)
   for (int64_t i = 0; i < E; ++i) {
     float r = g[i] * rescale;
     if (clip >= 0.f) r = clipf(r, clip);
@@ -254,6 +263,7 @@ void kvo_adam_update_f32(int64_t E, float* out, float* mean, float* var, const f
 void kvo_mp_adam_update(int64_t E, uint16_t* out_lp, int lp_kind, float* w32, float* mean,
                         float* var, const float* g, float lr, float wd, float beta1, float beta2,
                         float eps, float rescale, float clip) {
+#pragma omp parallel for schedule(static) if (E >= 200000)
   for (int64_t i = 0; i < E; ++i) {
     float w = w32[i];
     float r = g[i] * rescale;
@@ -281,6 +291,7 @@ double kvo_adam_lr(double lr, double beta1, double beta2, int t) {
 void kvo_mp_adamw_update(int64_t E, uint16_t* out_lp, int lp_kind, float* w32, float* mean,
                          float* var, const float* g, float lr, float eta, float wd, float beta1,
                          float beta2, float eps, float rescale, float clip) {
+#pragma omp parallel for schedule(static) if (E >= 200000)
   for (int64_t i = 0; i < E; ++i) {
     float w = w32[i];
     float sg = rescale * g[i];
@@ -298,6 +309,7 @@ void kvo_mp_adamw_update(int64_t E, uint16_t* out_lp, int lp_kind, float* w32, f
  *   grad = rescale_grad * grad; weight[:] -= lr * (grad + wd * weight)
  * (NDArray ops: each is a separate fp32 elementwise op.) */
 void kvo_test_update_f32(int64_t E, float* w, const float* g, float lr, float wd, float rescale) {
+#pragma omp parallel for schedule(static) if (E >= 200000)
   for (int64_t i = 0; i < E; ++i) {
     float gr = rescale * g[i];
     float t = wd * w[i];

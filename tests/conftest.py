@@ -1,0 +1,36 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA GPU (run on the B200 box)")
+    config.addinivalue_line("markers", "multigpu: needs >= 2 GPUs")
+
+
+def _ngpu():
+    try:
+        import mxnet_b200 as mx
+        return mx.num_gpus()
+    except Exception:
+        return 0
+
+
+@pytest.fixture(scope="session")
+def ngpu():
+    return _ngpu()
+
+
+def pytest_collection_modifyitems(config, items):
+    n = None
+    for item in items:
+        if "multigpu" in item.keywords:
+            if n is None:
+                n = _ngpu()
+            if n < 2:
+                item.add_marker(pytest.mark.skip(reason="needs >= 2 GPUs"))

@@ -1,0 +1,114 @@
+"""The C-ABI library loads without a GPU and exports every symbol include/mxkv_b200.h declares;
+host-only entry points behave; device entry points fail loudly (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import mxnet_b200 as mx
+from mxnet_b200.base import _LIB, check_call
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "mxkv_b200.h")).read()
+    return sorted(set(re.findall(r"MXKV_DLL\s+(?:const\s+)?[\w\*]+\s+\*?(\w+)\s*\(", text)))
+
+
+def test_every_declared_symbol_is_exported():
+    syms = declared_symbols()
+    assert len(syms) >= 70, syms
+    for s in syms:
+        assert hasattr(_LIB, s), "symbol %s declared in mxkv_b200.h but not exported" % s
+    for must in ("MXKVStoreCreate", "MXKVStorePushPullEx", "MXKVStorePullRowSparse", "MXKVStoreSetUpdaterEx",
+                 "MXNDArrayFromDLPack", "MXKVB200CommInit", "MXGetLastError"):
+        assert must in syms
+
+
+def test_library_contains_sm100a_code():
+    import subprocess
+    so = os.path.join(ROOT, "incubator-mxnet_b200", "libmxkv_b200.so")
+    out = subprocess.run(["cuobjdump", "-lelf", so], capture_output=True, text=True)
+    if out.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    assert "sm_100a" in out.stdout
+
+
+def test_host_only_entry_points():
+    v = ctypes.c_int()
+    check_call(_LIB.MXGetVersion(ctypes.byref(v)))
+    assert v.value == 20000
+    for t in ("local", "device", "local_allreduce_cpu", "local_allreduce_device"):
+        kv = mx.kv.create(t)
+        assert kv.type == t                 # tests/python/unittest/test_kvstore.py:276-279
+        assert kv.rank == 0 and kv.num_workers == 1
+    with pytest.raises(mx.MXNetError):
+        mx.kv.create("dist_sync")
+    w = ctypes.c_int()
+    check_call(_LIB.MXKVStoreIsWorkerNode(ctypes.byref(w)))
+    assert w.value == 1
+
+
+def test_error_contract_and_key_rules_without_gpu():
+    kv = mx.kv.create("device")
+    a = mx.nd.zeros((4, 4))
+    kv.init(3, a)
+    with pytest.raises(mx.MXNetError, match="duplicate init of key 3"):
+        kv.init(3, a)
+    with pytest.raises(mx.MXNetError, match="Mixed key types"):
+        kv.init("a", a)
+    with pytest.raises(mx.MXNetError, match="has not been inited"):
+        kv.pull(99, out=a)
+    skv = mx.kv.create("device")
+    skv.init("a", a)
+    with pytest.raises(mx.MXNetError, match="doesn't exist"):
+        skv.pull("zz", out=a)
+    with pytest.raises(mx.MXNetError, match="Mixed key types"):
+        skv.push(3, a)
+    # host-resident value, host-resident output: plumbing only, no GPU needed (BASELINE configs[0] shape)
+    kv2 = mx.kv.create("local")
+    big = mx.nd.array(np.arange(1024 * 1024, dtype=np.float32).reshape(1024, 1024))
+    kv2.init(0, big)
+    out = mx.nd.zeros((1024, 1024))
+    kv2.pull(0, out=out)
+    assert np.array_equal(out.asnumpy(), big.asnumpy())
+
+
+@pytest.mark.skipif(mx.num_gpus() > 0, reason="checks the no-GPU failure mode")
+def test_compute_fails_loudly_without_gpu():
+    kv = mx.kv.create("device")
+    kv.init(1, mx.nd.zeros((8,)))
+    with pytest.raises(mx.MXNetError, match="no CPU fallback"):
+        kv.push(1, [mx.nd.ones((8,)), mx.nd.ones((8,))])
+    with pytest.raises(mx.MXNetError, match="no CPU fallback"):
+        mx.nd.zeros((2,), mx.gpu(0))
+
+
+def test_shard_ranges_cover_and_align():
+    for size in (0, 1, 127, 128, 1000, 65536, (1 << 26) + 5, 25_557_032):
+        for world in (1, 2, 3, 4, 8):
+            prev = 0
+            for r in range(world):
+                b, e = mx.dist.shard_range(size, world, r)
+                assert b == prev and b <= e <= size
+                assert b % 128 == 0 or b == size
+                prev = e
+            assert prev == size
+
+
+def test_optimizer_descriptors():
+    o = mx.optimizer.create("sgd", learning_rate=0.1, momentum=0.9, wd=1e-4, rescale_grad=0.5, clip_gradient=2.0)
+    kw = o.fused_kwargs()
+    assert o.fused_name == "sgd" and kw["momentum"] == 0.9 and kw["clip_gradient"] == 2.0
+    kv = mx.kv.create("device")
+    kv.set_optimizer(o)           # accepted by the native registry without touching a device
+    with pytest.raises(mx.MXNetError, match="unknown optimizer argument"):
+        check_call(_LIB.MXKVB200SetOptimizer(kv.handle, b"sgd", 1, (ctypes.c_char_p * 1)(b"bogus"),
+                                             (ctypes.c_char_p * 1)(b"1")))
+    with pytest.raises(mx.MXNetError, match="not implemented"):
+        kv.set_gradient_compression({"type": "2bit", "threshold": 0.5})
+    assert mx.kv.KVStore.is_capable("optimizer")
+    assert isinstance(mx.kv.create("b200device"), mx.kv.KVStore)      # registry path, base.py:450-452

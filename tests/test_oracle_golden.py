@@ -1,0 +1,274 @@
+"""CPU tests that pin the oracle (test infrastructure) to the reference:
+golden vectors produced by the reference's own arithmetic / simulators, the reference's
+scenario-level known answers, and an independent restatement of the reference's non-fused
+Python optimizer steps (the reference's own oracle for its fused kernels)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _eq_bits(a, b):
+    a, b = np.ascontiguousarray(a), np.ascontiguousarray(b)
+    v = {2: np.uint16, 4: np.uint32, 8: np.uint64, 1: np.uint8}[a.dtype.itemsize]
+    return np.array_equal(a.view(v), b.view(v))
+
+
+def test_dense_sum_golden_vectors():
+    g = np.load(os.path.join(GOLD, "dense_sums.npz"))
+    tags = sorted(k[3:] for k in g.files if k.startswith("in_"))
+    assert len(tags) == 18
+    for tag in tags:
+        vals = [np.ascontiguousarray(v) for v in g["in_" + tag]]
+        assert _eq_bits(O.sum_device(vals), g["device_f32_" + tag]), tag
+        assert _eq_bits(O.sum_cpu(vals), g["commcpu_f32_" + tag]), tag
+        assert _eq_bits(O.sum_device([v.astype(np.float16) for v in vals]), g["device_f16_" + tag]), tag
+    rng = np.random.default_rng(int(g["seed_big"][0]))
+    vals = [rng.uniform(-1, 1, 1000003).astype(np.float32) for _ in range(5)]
+    s = O.sum_cpu(vals)       # takes the OpenMP branch (>= MXNET_KVSTORE_BIGARRAY_BOUND)
+    assert _eq_bits(s[:4096], g["commcpu_f32_big_head"])
+    assert _eq_bits(s[-4096:], g["commcpu_f32_big_tail"])
+    assert np.bitwise_xor.reduce(s.view(np.uint32)) == g["commcpu_f32_big_xor"][0]
+
+
+@pytest.mark.skipif(O.ref_lib() is None, reason="oracle/_ref not built (no /root/reference here)")
+def test_dense_sum_against_live_reference_arithmetic():
+    rng = np.random.default_rng(5)
+    for n in (2, 3, 4, 5, 6, 8, 9, 13):
+        for E in (1, 17, 5000):
+            vals = [rng.uniform(-1, 1, E).astype(np.float32) for _ in range(n)]
+            assert _eq_bits(O.sum_device(vals), O.ref_sum_device(vals))
+            assert _eq_bits(O.sum_cpu(vals), O.ref_sum_cpu(vals))
+            d = [v.astype(np.float64) for v in vals]
+            assert _eq_bits(O.sum_device(d), O.ref_sum_device(d))
+            i = [(v * 1000).astype(np.int32) for v in vals]
+            assert _eq_bits(O.sum_device(i), O.ref_sum_device(i))
+
+
+def test_compression_golden_vectors():
+    g = np.load(os.path.join(GOLD, "compression.npz"))
+    for kind, thr in (("2bit", 0.5), ("1bit", 0.0)):
+        for E in (32, 64, 160):
+            for it in range(3):
+                tag = "%s_E%d_it%d" % (kind, E, it)
+                grad = np.ascontiguousarray(g["grad_" + tag])
+                res = np.ascontiguousarray(g["res_in_" + tag]).copy()
+                if kind == "2bit":
+                    comp = O.quantize_2bit(grad, res, thr)
+                    dec = O.dequantize_2bit(comp, E, thr)
+                else:
+                    comp = O.quantize_1bit(grad, res, thr)
+                    dec = O.dequantize_1bit(comp, E, thr)
+                assert np.array_equal(comp, g["bytes_" + tag]), tag
+                assert _eq_bits(res, g["res_out_" + tag]), tag
+                assert _eq_bits(dec, g["dec_" + tag]), tag
+
+
+# ---- reference scenario KATs against the oracle KVStore model --------------------------------
+SHAPE = (4, 4)
+KEYS = [5, 7, 11]
+STR_KEYS = ["b", "c", "d"]
+
+
+def _init_kv(kind="local", str_keys=False):
+    kv = O.OracleKVStore(kind)
+    if str_keys:
+        kv.init("a", np.zeros(SHAPE, np.float32))
+        kv.init(STR_KEYS, [np.zeros(SHAPE, np.float32)] * 3)
+    else:
+        kv.init(3, np.zeros(SHAPE, np.float32))
+        kv.init(KEYS, [np.zeros(SHAPE, np.float32)] * 3)
+    return kv
+
+
+def test_kat_single_kv_pair_and_init():
+    # tests/python/unittest/test_kvstore.py:55-66, 96-105
+    for s in (False, True):
+        kv = _init_kv(str_keys=s)
+        key = "a" if s else 3
+        kv.push(key, np.ones(SHAPE, np.float32))
+        val = np.empty(SHAPE, np.float32)
+        kv.pull(key, val)
+        assert np.all(val == 1)
+    kv = O.OracleKVStore("local")
+    kv.init(3, np.ones(SHAPE, np.float32) * 4)
+    a = np.zeros(SHAPE, np.float32)
+    kv.pull(3, a)
+    assert np.all(a == 4)
+
+
+def test_kat_pull_and_list():
+    # test_kvstore.py:107-136
+    for kind in ("device", "local"):
+        kv = O.OracleKVStore(kind)
+        a, b = np.ones(SHAPE, np.float32), np.zeros(SHAPE, np.float32)
+        kv.init("1", np.zeros(SHAPE, np.float32))
+        kv.push("1", [a, a, a, a])
+        kv.pull("1", b)
+        assert np.all(b == 4)
+        kv.init("2", np.zeros(SHAPE, np.float32))
+        kv.pull("2", b)
+        assert np.all(b == 0)
+    kv = _init_kv()
+    kv.push(KEYS, [np.ones(SHAPE, np.float32) * 4] * 3)
+    val = [np.empty(SHAPE, np.float32) for _ in KEYS]
+    kv.pull(KEYS, val)
+    assert all(np.all(v == 4) for v in val)
+
+
+def test_kat_updater():
+    # test_kvstore.py:222-274: updater local += recv, 4 devices, 4 pushes -> num_devs * num_push
+    for s in (False, True):
+        kv = _init_kv(str_keys=s)
+        kv.set_updater(lambda k, recv, local: np.add(local, recv, out=local))
+        key, klist = ("a", STR_KEYS) if s else (3, KEYS)
+        vals = [np.ones(SHAPE, np.float32) for _ in range(4)]
+        kv.push(key, vals)
+        outs = [np.empty(SHAPE, np.float32) for _ in range(4)]
+        kv.pull(key, outs)
+        assert all(np.all(o == 4) for o in outs)
+        for _ in range(4):
+            kv.push(klist, [vals] * 3)
+        outs = [[np.empty(SHAPE, np.float32) for _ in range(4)] for _ in klist]
+        kv.pull(klist, outs)
+        assert all(np.all(o == 16) for oo in outs for o in oo)
+
+
+def test_kat_key_type_mixing_and_duplicates():
+    # test_kvstore.py:281-339, kvstore_local.h:230-233,344-347
+    kv = _init_kv()
+    with pytest.raises(ValueError):
+        kv.init("a", np.zeros(SHAPE, np.float32))
+    with pytest.raises(ValueError):
+        kv.push("a", np.zeros(SHAPE, np.float32))
+    with pytest.raises(ValueError):
+        kv.init(3, np.zeros(SHAPE, np.float32))
+    kv = _init_kv(str_keys=True)
+    with pytest.raises(ValueError):
+        kv.pull(3, np.zeros(SHAPE, np.float32))
+
+
+def test_kat_row_sparse_pull():
+    # test_kvstore.py:68-94 and the docstring of kvstore.py:row_sparse_pull
+    kv = O.OracleKVStore("local")
+    kv.init("e", O.RowSparse.from_dense(np.ones(SHAPE, np.float32)))
+    rng = np.random.default_rng(0)
+    for _ in range(5):
+        row_id = rng.integers(0, SHAPE[0], SHAPE[0])
+        out = O.RowSparse(np.zeros(0, np.int64), np.zeros((0, SHAPE[1]), np.float32), SHAPE)
+        kv.row_sparse_pull("e", out, row_id.reshape(2, -1))
+        dense = out.todense()
+        for r in range(SHAPE[0]):
+            assert np.all(dense[r] == (1 if r in row_id else 0))
+
+
+def test_kat_nightly_test_optimizer():
+    # tests/nightly/test_kvstore.py:100-119,297-343: 4 workers, random uniform[-1,1), the 'test'
+    # optimizer; expectation restated from python/mxnet/optimizer/optimizer.py:570-577
+    rng = np.random.default_rng(1)
+    lr = 0.01  # Optimizer default learning_rate
+    rescale = 0.1
+    for shape in ((4, 4), (100, 100), (2000, 2000)):
+        kv = O.OracleKVStore("device")
+        kv.init(9, np.zeros(shape, np.float32))
+        kv.set_optimizer(O.OracleOptimizer("test", rescale_grad=rescale))
+        res = np.zeros(shape, np.float64)
+        for _ in range(3):
+            data = [rng.uniform(-1, 1, shape).astype(np.float32) for _ in range(4)]
+            kv.push(9, data)
+            res = res - lr * rescale * sum(d.astype(np.float64) for d in data)
+        out = np.empty(shape, np.float32)
+        kv.pull(9, out)
+        err = np.sum(np.abs(out - res)) / np.sum(np.abs(res))
+        assert err < 1e-6, (err, shape)
+
+
+# ---- optimizer kernels vs. an independent restatement of the reference's Python step() ---------
+def _np_sgd_step(w, g, mom, lr, wd, momentum, rescale, clip):
+    # python/mxnet/optimizer/sgd.py:118-154 (NDArray ops = separate fp32 elementwise ops)
+    g = (g * np.float32(rescale)).astype(np.float32)
+    if clip is not None:
+        g = np.clip(g, -clip, clip).astype(np.float32)
+    g = (g + np.float32(wd) * w).astype(np.float32)
+    if mom is not None:
+        mom *= np.float32(momentum)
+        mom -= np.float32(lr) * g
+        w += mom
+    else:
+        w += -np.float32(lr) * g
+
+
+def _np_adam_step(w, g, mean, var, lr, wd, b1, b2, eps, rescale, clip, t):
+    # python/mxnet/optimizer/adam.py:107-147
+    import math
+    g = (g * np.float32(rescale)).astype(np.float32)
+    if clip is not None:
+        g = np.clip(g, -clip, clip).astype(np.float32)
+    g = (g + np.float32(wd) * w).astype(np.float32)
+    lr = lr * math.sqrt(1. - b2 ** t) / (1. - b1 ** t)
+    mean *= np.float32(b1)
+    mean += np.float32(1. - b1) * g
+    var *= np.float32(b2)
+    var += np.float32(1. - b2) * np.square(g)
+    w -= np.float32(lr) * (mean / (np.sqrt(var) + np.float32(eps)))
+
+
+@pytest.mark.parametrize("momentum,clip", [(0.0, None), (0.9, None), (0.9, 0.4)])
+def test_sgd_kernel_vs_python_step(momentum, clip):
+    # tolerances of tests/python/unittest/test_optimizer.py:75-84 (rtol 1e-3 / atol 1e-4) -- the
+    # restatements in fact agree to ~1 ulp
+    rng = np.random.default_rng(11)
+    E = 10007
+    w = rng.uniform(0, 1, E).astype(np.float32); w2 = w.copy()
+    mom = np.zeros(E, np.float32) if momentum else None
+    opt = O.OracleOptimizer("sgd", learning_rate=0.1, wd=1e-3, momentum=momentum, rescale_grad=0.5,
+                            clip_gradient=clip)
+    for _ in range(5):
+        g = rng.uniform(-1, 1, E).astype(np.float32)
+        opt.update(0, w, g.copy())
+        _np_sgd_step(w2, g.copy(), mom, 0.1, 1e-3, momentum, 0.5, clip)
+        np.testing.assert_allclose(w, w2, rtol=1e-3, atol=1e-4)
+        assert np.max(np.abs(w - w2)) < 1e-6
+
+
+def test_adam_kernel_vs_python_step():
+    # tolerances of test_optimizer.py:461-463 (rtol 1e-4 / atol 2e-5)
+    rng = np.random.default_rng(12)
+    E = 10007
+    w = rng.uniform(0, 1, E).astype(np.float32); w2 = w.copy()
+    mean, var = np.zeros(E, np.float32), np.zeros(E, np.float32)
+    opt = O.OracleOptimizer("adam", learning_rate=0.01, wd=1e-3, rescale_grad=0.5, clip_gradient=0.8)
+    for t in range(1, 6):
+        g = rng.uniform(-1, 1, E).astype(np.float32)
+        opt.update(0, w, g.copy())
+        _np_adam_step(w2, g.copy(), mean, var, 0.01, 1e-3, 0.9, 0.999, 1e-8, 0.5, 0.8, t)
+        np.testing.assert_allclose(w, w2, rtol=1e-4, atol=2e-5)
+
+
+def test_rsp_sum_and_retain_oracle_properties():
+    rng = np.random.default_rng(2)
+    rows, L = 50, 8
+    rsps = []
+    dense_sum = np.zeros((rows, L), np.float64)
+    for _ in range(4):
+        idx = np.sort(rng.choice(rows, 12, replace=False)).astype(np.int64)
+        val = rng.uniform(-1, 1, (12, L)).astype(np.float32)
+        rsps.append(O.RowSparse(idx, val, (rows, L)))
+        dense_sum[idx] += val
+    s = O.rsp_sum(rsps)
+    assert np.all(np.diff(s.indices) > 0)
+    np.testing.assert_allclose(s.todense(), dense_sum, rtol=1e-6, atol=1e-6)
+    # order of accumulation = input order starting from zero (ndarray_function.cu:176-187)
+    r = int(s.indices[0])
+    acc = np.zeros(L, np.float32)
+    for x in rsps:
+        pos = np.where(x.indices == r)[0]
+        if len(pos):
+            acc = acc + x.data[pos[0]]
+    assert _eq_bits(acc, s.data[0])
+    ret = O.sparse_retain(s, O.unique([3, 3, 1, 49]))
+    assert list(ret.indices) == [1, 3, 49]

@@ -88,7 +88,7 @@ class ClockSampler(object):
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "25"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -195,7 +195,7 @@ def run_cpu_reference(args, shapes, as_baseline=False):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="sweep", choices=["sweep", "resnet50", "bert"])
@@ -277,15 +277,15 @@ def main():
     check_call(_LIB.MXKVB200GetEngineStream(dev, ctypes.byref(sp)))
     engine_stream = torch.cuda.ExternalStream(sp.value, device=torch.device("cuda", dev))
 
+    sampler = ClockSampler(dev)
+    if rank == 0:
+        sampler.start()
     for _ in range(max(3, args.warmup)):
         step()
     torch.cuda.synchronize()
     barrier()
 
     # ---- timed region: device time (inputs resident in HBM) ----------------------------------
-    sampler = ClockSampler(dev)
-    if rank == 0:
-        sampler.start()
     launches0 = mx.kv.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kern = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]

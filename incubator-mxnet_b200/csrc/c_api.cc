@@ -21,14 +21,6 @@ using namespace mxkv;
   return 0;
 
 namespace {
-struct NDHandle : public NDArray {
-  // per-handle scratch for MXNDArrayGetShape* return pointers (the reference keeps them in
-  // thread-local storage, MXAPIThreadLocalEntry)
-  std::vector<int> shape32;
-  std::vector<int64_t> shape64;
-  explicit NDHandle(const NDArray& a) : NDArray(a) {}
-  NDHandle() {}
-};
 inline NDHandle* ND(NDArrayHandle h) {
   MXKV_CHECK(h != nullptr) << "null NDArrayHandle";
   return static_cast<NDHandle*>(h);

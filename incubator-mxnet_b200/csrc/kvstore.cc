@@ -263,15 +263,21 @@ Replica& KVStore::EnsureReplica(KeyState& ks, int dev) {
     return *r;
   }
   Runtime* rt = Runtime::Get();
-  MXKV_CHECK(!(ks.has_state && !ks.reps.empty() && updater_ == nullptr))
-      << "key " << ks.key << ": the set of GPUs changed after fused optimizer state was created";
   if (rt->pg()) MXKV_CHECK(dev == rt->pg()->dev()) << "in one-process-per-GPU mode arrays must live on GPU "
                                                    << rt->pg()->dev();
   Replica nr;
   nr.dev = dev;
   nr.local = NDArray::Empty(ks.shape, Context{kGPU, dev}, ks.dtype, /*symmetric=*/rt->pg() != nullptr);
   if (!ks.reps.empty()) {
-    CopyFromTo(FreshReplica(ks).local, nr.local);
+    if (ks.has_state) GatherState(ks);   // make every existing replica's optimizer state complete
+    Replica& src = FreshReplica(ks);
+    CopyFromTo(src.local, nr.local);
+    // a GPU joining later (e.g. states were loaded before the first multi-GPU push) inherits the state
+    const Context nctx{kGPU, dev};
+    const bool sym = rt->pg() != nullptr;
+    if (!src.w32.is_none()) { nr.w32 = NDArray::Empty(ks.shape, nctx, kFloat32, sym); CopyFromTo(src.w32, nr.w32); }
+    if (!src.s0.is_none()) { nr.s0 = NDArray::Empty(ks.shape, nctx, kFloat32, sym); CopyFromTo(src.s0, nr.s0); }
+    if (!src.s1.is_none()) { nr.s1 = NDArray::Empty(ks.shape, nctx, kFloat32, sym); CopyFromTo(src.s1, nr.s1); }
   } else {
     MXKV_CHECK(!ks.init_value.is_none()) << "key " << ks.key << " has no initial value";
     CopyFromTo(ks.init_value, nr.local);
@@ -948,8 +954,8 @@ void KVStore::RunCallbackUpdater(KeyState& ks, Replica& root) {
   Runtime* rt = Runtime::Get();
   rt->Dev(root.dev).engine_dirty = true;
   rt->Fence(root.dev);
-  NDArray* recv = new NDArray(root.merged);
-  NDArray* local = new NDArray(root.local);
+  NDHandle* recv = new NDHandle(root.merged);
+  NDHandle* local = new NDHandle(root.local);
   if (key_type_ == kStringKey && str_updater_ != nullptr) {
     const std::string& sk = reverse_str_key_dict_[ks.key];
     str_updater_(sk.c_str(), recv, local, updater_handle_);

@@ -7,12 +7,23 @@
 namespace mxkv {
 
 Chunk::~Chunk() {
+  // The reference defers NDArray deletion through the engine (Engine::DeleteVariable) so memory
+  // outlives every pending reader.  Here kernels on ANY GPU may still be reading this buffer over
+  // NVLink (cudaFree only synchronises the owning device), so drain the engine streams first.
+  if ((kind == kOwnedCuda || kind == kOwnedPinned) && ptr) Runtime::Get()->DrainForFree();
   switch (kind) {
     case kOwnedCuda: {
-      if (ptr) { DeviceGuard g(ctx.dev_id); cudaFree(ptr); }
+      if (ptr) {
+        int prev = -1;
+        cudaGetDevice(&prev);
+        cudaSetDevice(ctx.dev_id);
+        cudaFree(ptr);
+        if (prev >= 0) cudaSetDevice(prev);
+        cudaGetLastError();
+      }
       break;
     }
-    case kOwnedPinned: if (ptr) cudaFreeHost(ptr); break;
+    case kOwnedPinned: if (ptr) { cudaFreeHost(ptr); cudaGetLastError(); } break;
     case kOwnedHost: std::free(ptr); break;
     case kDLPack: if (dl && dl->deleter) dl->deleter(dl); break;
     case kSymmetric:   // bump-allocated from the arena; released with the process group

@@ -81,6 +81,17 @@ class NDArray {
   int64_t cap_rows_ = 0;
 };
 
+// What an NDArrayHandle points to: the array plus per-handle scratch for the pointers
+// MXNDArrayGetShape* hands out (the reference keeps those in MXAPIThreadLocalEntry).  Every
+// handle that crosses the C ABI -- including the two the updater callback must free
+// (c_api.cc:3066-3080) -- is allocated as an NDHandle and released by MXNDArrayFree.
+struct NDHandle : public NDArray {
+  std::vector<int> shape32;
+  std::vector<int64_t> shape64;
+  explicit NDHandle(const NDArray& a) : NDArray(a) {}
+  NDHandle() {}
+};
+
 // async copy between any two dense arrays of equal byte size, ordered on engine streams
 // (CopyFromTo, src/ndarray/ndarray.cc:1331-1424, without the per-op host wait)
 void CopyFromTo(const NDArray& src, const NDArray& dst);

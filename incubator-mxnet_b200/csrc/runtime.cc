@@ -306,6 +306,21 @@ void Runtime::WaitAll() {
   }
 }
 
+void Runtime::DrainForFree() noexcept {
+  try {
+    std::lock_guard<std::recursive_mutex> lk(mu_);
+    int prev = -1;
+    cudaGetDevice(&prev);
+    for (auto& kv : devs_) {
+      cudaSetDevice(kv.first);
+      cudaStreamSynchronize(kv.second->stream);
+    }
+    if (prev >= 0) cudaSetDevice(prev);
+    cudaGetLastError();
+  } catch (...) {
+  }
+}
+
 void Runtime::InitProcessGroup(int rank, int world, int dev, AllGatherFn fn, void* ctx) {
   std::lock_guard<std::recursive_mutex> lk(mu_);
   MXKV_CHECK(!pg_) << "process group already initialised";

@@ -102,6 +102,7 @@ class Runtime {
   void StreamWait(int waiter_dev, int signaler_dev);
   void SetUserStream(int dev, cudaStream_t s);
   void WaitAll();
+  void DrainForFree() noexcept;            // like WaitAll, never throws (used by destructors)
   void WaitDevice(int dev);
 
   // one-process-per-GPU mode

@@ -1,0 +1,132 @@
+"""Worker of tests/test_gpu_multi.py::test_mp_one_process_per_gpu (launched by torchrun).
+Every rank regenerates every rank's data from seeds, so each can check itself against the oracle."""
+import os
+import sys
+import tempfile
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import mxnet_b200 as mx          # noqa: E402
+from oracle import oracle as O   # noqa: E402
+
+
+def bits_equal(a, b):
+    return np.array_equal(np.ascontiguousarray(a).view(np.uint32), np.ascontiguousarray(b).view(np.uint32))
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    mx.dist.init_process_group(device=local)
+    ctx = mx.gpu(local)
+
+    def data(seed, shape, r):
+        return np.random.default_rng(seed * 1000 + r).uniform(-1, 1, shape).astype(np.float32)
+
+    # 1. init/broadcast: rank 0's value wins
+    kv = mx.kv.create("device")
+    assert kv.rank == rank and kv.num_workers == world
+    shape = (300, 7)
+    out = mx.nd.empty(shape, ctx)
+    kv.broadcast("w", mx.nd.array(data(1, shape, rank), ctx), out=out)
+    assert bits_equal(out.asnumpy(), data(1, shape, 0)), "broadcast"
+
+    # 2. allreduce (no optimizer): one-shot and two-shot sizes; plain, symmetric and torch arrays
+    sizes = [5, 1000, 65536, 70001, (1 << 20) + 3, 3_000_001]
+    keys = list(range(len(sizes)))
+    kv.init([str(k) for k in keys], [mx.nd.zeros((e,), ctx) for e in sizes])
+    for mode in ("plain", "symmetric", "torch", "host"):
+        vals, outs, keep = [], [], []
+        for k, e in zip(keys, sizes):
+            src = data(2 + k, (e,), rank)
+            if mode == "symmetric":
+                v = mx.nd.empty_symmetric((e,)); v[:] = src
+                o = mx.nd.empty_symmetric((e,))
+            elif mode == "torch":
+                t = torch.from_numpy(src).cuda(); keep.append(t)
+                v = mx.nd.from_torch(t)
+                to = torch.empty(e, device="cuda"); keep.append(to)
+                o = mx.nd.from_torch(to)
+            elif mode == "host":
+                v = mx.nd.array(src, mx.cpu_pinned())
+                o = mx.nd.empty((e,), mx.cpu_pinned())
+            else:
+                v = mx.nd.array(src, ctx)
+                o = mx.nd.empty((e,), ctx)
+            vals.append(v); outs.append(o)
+        torch.cuda.synchronize()
+        kv.pushpull([str(k) for k in keys], vals, out=outs)
+        for k, e, o in zip(keys, sizes, outs):
+            want = O.sum_device([data(2 + k, (e,), r) for r in range(world)])
+            assert bits_equal(o.asnumpy(), want), ("allreduce", mode, e)
+    # in-place
+    for e, k in zip(sizes, keys):
+        v = mx.nd.array(data(50 + k, (e,), rank), ctx)
+        kv.pushpull(str(k), v)
+        want = O.sum_device([data(50 + k, (e,), r) for r in range(world)])
+        assert bits_equal(v.asnumpy(), want), ("inplace", e)
+
+    # 3. fused optimizers over a key list, several steps
+    for optname, kw in (("sgd", dict(learning_rate=0.1, momentum=0.9, wd=1e-4, rescale_grad=0.5)),
+                        ("adam", dict(learning_rate=0.01, wd=1e-3))):
+        shapes = [(64,), (513, 9), (1 << 19,), (1 << 21,)]
+        ks = list(range(len(shapes)))
+        kv2 = mx.kv.create("device")
+        w0 = [data(7 + k, s, 0) for k, s in zip(ks, shapes)]
+        kv2.init(ks, [mx.nd.array(w, ctx) for w in w0])
+        kv2.set_optimizer(mx.optimizer.create(optname, **kw))
+        okv = O.OracleKVStore("device")
+        okv.init(ks, [w.copy() for w in w0])
+        okv.set_optimizer(O.OracleOptimizer(optname, **kw))
+        outs = [mx.nd.empty_symmetric(s) for s in shapes]
+        gsym = [mx.nd.empty_symmetric(s) for s in shapes]
+        for step in range(3):
+            for k, s in zip(ks, shapes):
+                gsym[k][:] = data(100 * step + k, s, rank)
+            kv2.pushpull(ks, gsym, out=outs)
+            okv.push(ks, [[data(100 * step + k, s, r) for r in range(world)] for k, s in zip(ks, shapes)])
+            for k, s in zip(ks, shapes):
+                want = np.empty(s, np.float32)
+                okv.pull(k, want)
+                assert bits_equal(outs[k].asnumpy(), want), (optname, step, k)
+        if optname == "adam":
+            # sharded state: save on every rank (gathers), reload into a fresh store, continue
+            f = os.path.join(tempfile.gettempdir(), "mxkv_states_%d_%d" % (world, rank))
+            kv2.save_optimizer_states(f)
+            mids = [o.asnumpy() for o in outs]
+            kv3 = mx.kv.create("device")
+            kv3.init(ks, [mx.nd.array(m, ctx) for m in mids])
+            kv3.set_optimizer(mx.optimizer.create(optname, **kw))
+            kv3.load_optimizer_states(f)
+            outs3 = [mx.nd.empty(s, ctx) for s in shapes]
+            for k, s in zip(ks, shapes):
+                gsym[k][:] = data(900 + k, s, rank)
+            kv2.pushpull(ks, gsym, out=outs)
+            kv3.pushpull(ks, gsym, out=outs3)
+            for k in ks:
+                assert bits_equal(outs[k].asnumpy(), outs3[k].asnumpy()), ("reload", k)
+
+    # 4. python updater callback (every rank applies it to its own replica)
+    kv4 = mx.kv.create("device")
+    kv4.init(3, mx.nd.zeros((4, 4), ctx))
+    kv4._set_updater(lambda key, recv, local: local.__iadd__(recv))
+    for it in range(1, 3):
+        kv4.push(3, mx.nd.ones((4, 4), ctx))
+        o = mx.nd.empty((4, 4), ctx)
+        kv4.pull(3, out=o)
+        assert np.all(o.asnumpy() == it * world), "callback"
+
+    mx.nd.waitall()
+    dist.barrier()
+    print("MP_WORKER_OK rank", rank, flush=True)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -249,76 +249,99 @@ __device__ __forceinline__ float update_one(float g, float w, float& s0, float& 
 }
 
 // ---------------------------------------------------------------------------
-// one packet: gather n sources, sum in order, update, scatter
+// U packets per thread: gather n sources, sum in order, update, scatter.  All loads of a batch are
+// issued before the first use so U * min(n, BATCH) 16-byte requests per thread are in flight
+// (NVLink round trips are ~2 us: bytes in flight are what buys bandwidth).
 // ---------------------------------------------------------------------------
-template <typename T, int OPT, bool MP, int N>
-__device__ __forceinline__ void process_packet(const TensorWork& tw, int64_t e, const Hyper& h,
-                                               int order, bool native_half_add) {
+template <typename T, int OPT, bool MP, int N, int BATCH, int U>
+__device__ __forceinline__ void process_packets(const TensorWork& tw, const int64_t (&e)[U], const bool (&ok)[U],
+                                                const Hyper& h, int order, bool native_half_add) {
   typedef Packet<T, N> P;
-  constexpr int kBatch = 4;
-  float acc[N];
-  float grp[N];
+  float acc[U][N];
+  // the CommCPU grouping only differs from left-to-right for n >= 3, i.e. never when BATCH == 2
+  // (the small-n variant): no group registers there
+  float grp[BATCH > 2 ? U : 1][N];
   const int n = tw.n_src;
-  for (int k0 = 0; k0 < n; k0 += kBatch) {
-    P buf[kBatch];
+  for (int k0 = 0; k0 < n; k0 += BATCH) {
+    P buf[U][BATCH];
 #pragma unroll
-    for (int j = 0; j < kBatch; ++j)
-      if (k0 + j < n) buf[j].load(tw.src[k0 + j], e);
+    for (int u = 0; u < U; ++u)
 #pragma unroll
-    for (int j = 0; j < kBatch; ++j) {
+      for (int j = 0; j < BATCH; ++j)
+        if (ok[u] && k0 + j < n) buf[u][j].load(tw.src[k0 + j], e[u]);
+#pragma unroll
+    for (int j = 0; j < BATCH; ++j) {
       const int k = k0 + j;
       if (k < n) {
-        float x[N];
-        buf[j].unpack(x);
-        if (k == 0) {
 #pragma unroll
-          for (int i = 0; i < N; ++i) acc[i] = x[i];
-        } else if (order == ORDER_DEVICE) {
+        for (int u = 0; u < U; ++u) {
+          float x[N];
+          buf[u][j].unpack(x);
+          if (k == 0) {
 #pragma unroll
-          for (int i = 0; i < N; ++i) {
-            float s = __fadd_rn(acc[i], x[i]);
-            if (native_half_add) s = Cvt<T>::to(Cvt<T>::from(s));
-            acc[i] = s;
-          }
-        } else {  // ORDER_COMMCPU: in0 += ((in1+in2)+in3)+in4 per group of four
-          const int pos = (k - 1) & 3;
+            for (int i = 0; i < N; ++i) acc[u][i] = x[i];
+          } else if (order == ORDER_DEVICE || BATCH <= 2) {
 #pragma unroll
-          for (int i = 0; i < N; ++i) grp[i] = (pos == 0) ? x[i] : __fadd_rn(grp[i], x[i]);
-          if (pos == 3 || k == n - 1) {
+            for (int i = 0; i < N; ++i) {
+              float s = __fadd_rn(acc[u][i], x[i]);
+              if (native_half_add) s = Cvt<T>::to(Cvt<T>::from(s));
+              acc[u][i] = s;
+            }
+          } else {  // ORDER_COMMCPU: in0 += ((in1+in2)+in3)+in4 per group of four
+            const int pos = (k - 1) & 3;
+            constexpr int GU = BATCH > 2 ? 1 : 0;
 #pragma unroll
-            for (int i = 0; i < N; ++i) acc[i] = __fadd_rn(acc[i], grp[i]);
+            for (int i = 0; i < N; ++i) grp[u * GU][i] = (pos == 0) ? x[i] : __fadd_rn(grp[u * GU][i], x[i]);
+            if (pos == 3 || k == n - 1) {
+#pragma unroll
+              for (int i = 0; i < N; ++i) acc[u][i] = __fadd_rn(acc[u][i], grp[u * GU][i]);
+            }
           }
         }
       }
     }
   }
 
-  float wnew[N];
+  float wnew[U][N];
   if (OPT == OPT_NONE) {
 #pragma unroll
-    for (int i = 0; i < N; ++i) wnew[i] = acc[i];
-  } else {
-    float w[N], s0[N], s1[N];
-    if (MP) {
-      ldf<N>(tw.w32, e, w);
-    } else {
-      P pw;
-      pw.load(tw.w, e);
-      pw.unpack(w);
-    }
-    if (OPT == OPT_SGD_MOM || OPT == OPT_ADAM || OPT == OPT_ADAMW) ldf<N>(tw.s0, e, s0);
-    if (OPT == OPT_ADAM || OPT == OPT_ADAMW) ldf<N>(tw.s1, e, s1);
+    for (int u = 0; u < U; ++u)
 #pragma unroll
-    for (int i = 0; i < N; ++i) wnew[i] = update_one<OPT>(acc[i], w[i], s0[i], s1[i], h);
-    if (OPT == OPT_SGD_MOM || OPT == OPT_ADAM || OPT == OPT_ADAMW) stf<N>(tw.s0, e, s0);
-    if (OPT == OPT_ADAM || OPT == OPT_ADAMW) stf<N>(tw.s1, e, s1);
-    if (MP) stf<N>(tw.w32, e, wnew);
+      for (int i = 0; i < N; ++i) wnew[u][i] = acc[u][i];
+  } else {
+    float w[U][N], s0[U][N], s1[U][N];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (!ok[u]) continue;
+      if (MP) {
+        ldf<N>(tw.w32, e[u], w[u]);
+      } else {
+        P pw;
+        pw.load(tw.w, e[u]);
+        pw.unpack(w[u]);
+      }
+      if (OPT == OPT_SGD_MOM || OPT == OPT_ADAM || OPT == OPT_ADAMW) ldf<N>(tw.s0, e[u], s0[u]);
+      if (OPT == OPT_ADAM || OPT == OPT_ADAMW) ldf<N>(tw.s1, e[u], s1[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (!ok[u]) continue;
+#pragma unroll
+      for (int i = 0; i < N; ++i) wnew[u][i] = update_one<OPT>(acc[u][i], w[u][i], s0[u][i], s1[u][i], h);
+      if (OPT == OPT_SGD_MOM || OPT == OPT_ADAM || OPT == OPT_ADAMW) stf<N>(tw.s0, e[u], s0[u]);
+      if (OPT == OPT_ADAM || OPT == OPT_ADAMW) stf<N>(tw.s1, e[u], s1[u]);
+      if (MP) stf<N>(tw.w32, e[u], wnew[u]);
+    }
   }
   const int m = tw.n_out;
-  for (int j = 0; j < m; ++j) P::store(tw.out[j], e, wnew);
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    if (!ok[u]) continue;
+    for (int j = 0; j < m; ++j) P::store(tw.out[j], e[u], wnew[u]);
+  }
 }
 
-template <typename T, int OPT, bool MP>
+template <typename T, int OPT, bool MP, bool SMALLN>
 __global__ void __launch_bounds__(kThreads, 2)
 kv_dense_kernel(DenseLaunch L) {
   __shared__ TensorWork tw;
@@ -328,6 +351,8 @@ kv_dense_kernel(DenseLaunch L) {
   // 16-bit gradients with fp32 master/state: 4-element packets (8 B of gradient against
   // 16 B of every fp32 stream) keep the kernel inside 64 registers.
   constexpr int NV = (OPT != OPT_NONE && sizeof(T) == 2) ? 4 : 16 / sizeof(T);
+  constexpr int BATCH = SMALLN ? 2 : 4;
+  constexpr int U = SMALLN ? 2 : 1;
   const bool native_half_add = (sizeof(T) == 2) && !L.fp32_accum && (OPT == OPT_NONE);
   int cur = -1;
   for (int64_t c = blockIdx.x; c < L.total_chunks; c += gridDim.x) {
@@ -353,15 +378,26 @@ kv_dense_kernel(DenseLaunch L) {
 
     const int64_t cb = tw.begin + (c - L.chunk_prefix[lo]) * kChunkElems;
     const int64_t ce = (cb + kChunkElems < tw.end) ? cb + kChunkElems : tw.end;
+    int64_t scalar_from = cb;
     if (tw.pad_ & 1) {  // every pointer 16-byte aligned and begin % 8 == 0
       const int64_t nvec = (ce - cb) / NV;
-      for (int64_t v = threadIdx.x; v < nvec; v += kThreads)
-        process_packet<T, OPT, MP, NV>(tw, cb + v * NV, h, L.order, native_half_add);
-      for (int64_t e = cb + nvec * NV + threadIdx.x; e < ce; e += kThreads)
-        process_packet<T, OPT, MP, 1>(tw, e, h, L.order, native_half_add);
-    } else {
-      for (int64_t e = cb + threadIdx.x; e < ce; e += kThreads)
-        process_packet<T, OPT, MP, 1>(tw, e, h, L.order, native_half_add);
+      for (int64_t v = threadIdx.x; v < nvec; v += static_cast<int64_t>(U) * kThreads) {
+        int64_t e[U];
+        bool ok[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int64_t vv = v + static_cast<int64_t>(u) * kThreads;
+          ok[u] = vv < nvec;
+          e[u] = cb + (ok[u] ? vv : v) * NV;
+        }
+        process_packets<T, OPT, MP, NV, BATCH, U>(tw, e, ok, h, L.order, native_half_add);
+      }
+      scalar_from = cb + nvec * NV;
+    }
+    for (int64_t s = scalar_from + threadIdx.x; s < ce; s += kThreads) {
+      const int64_t e1[1] = {s};
+      const bool ok1[1] = {true};
+      process_packets<T, OPT, MP, 1, 4, 1>(tw, e1, ok1, h, L.order, native_half_add);
     }
   }
 
@@ -418,40 +454,45 @@ __global__ void kv_fill_kernel(uint4* p, uint32_t word, size_t n16, uint8_t* tai
 // ---------------------------------------------------------------------------
 typedef void (*DenseKernelFn)(DenseLaunch);
 
+template <typename T, int OPT, bool MP>
+static DenseKernelFn pick_n(bool small_n) {
+  return small_n ? kv_dense_kernel<T, OPT, MP, true> : kv_dense_kernel<T, OPT, MP, false>;
+}
+
 template <typename T>
-static DenseKernelFn pick_fused(int opt, bool mp) {
+static DenseKernelFn pick_opt(int opt, bool mp, bool small_n, bool allow_non_mp) {
+  if (opt == OPT_NONE) return pick_n<T, OPT_NONE, false>(small_n);
   if (mp) {
     switch (opt) {
-      case OPT_SGD: return kv_dense_kernel<T, OPT_SGD, true>;
-      case OPT_SGD_MOM: return kv_dense_kernel<T, OPT_SGD_MOM, true>;
-      case OPT_ADAM: return kv_dense_kernel<T, OPT_ADAM, true>;
-      case OPT_ADAMW: return kv_dense_kernel<T, OPT_ADAMW, true>;
-      case OPT_TEST: return kv_dense_kernel<T, OPT_TEST, true>;
+      case OPT_SGD: return pick_n<T, OPT_SGD, true>(small_n);
+      case OPT_SGD_MOM: return pick_n<T, OPT_SGD_MOM, true>(small_n);
+      case OPT_ADAM: return pick_n<T, OPT_ADAM, true>(small_n);
+      case OPT_ADAMW: return pick_n<T, OPT_ADAMW, true>(small_n);
+      case OPT_TEST: return pick_n<T, OPT_TEST, true>(small_n);
       default: return nullptr;
     }
   }
+  if (!allow_non_mp) return nullptr;
   return nullptr;
 }
 
 static DenseKernelFn pick_kernel(const DenseLaunch& L) {
   const bool mp = L.multi_precision != 0;
+  // the two-packet variant stays inside 64 registers (2 resident blocks/SM) only for these
+  const bool sn = L.small_n != 0 && (L.opt == OPT_NONE || L.opt == OPT_SGD || L.opt == OPT_TEST);
   switch (L.dtype) {
     case kFloat32:
+      if (mp || L.opt == OPT_NONE) return pick_opt<float>(L.opt, mp, sn, true);
       switch (L.opt) {
-        case OPT_NONE: return kv_dense_kernel<float, OPT_NONE, false>;
-        case OPT_SGD: return mp ? kv_dense_kernel<float, OPT_SGD, true> : kv_dense_kernel<float, OPT_SGD, false>;
-        case OPT_SGD_MOM: return mp ? kv_dense_kernel<float, OPT_SGD_MOM, true> : kv_dense_kernel<float, OPT_SGD_MOM, false>;
-        case OPT_ADAM: return mp ? kv_dense_kernel<float, OPT_ADAM, true> : kv_dense_kernel<float, OPT_ADAM, false>;
-        case OPT_ADAMW: return mp ? kv_dense_kernel<float, OPT_ADAMW, true> : kv_dense_kernel<float, OPT_ADAMW, false>;
-        case OPT_TEST: return mp ? kv_dense_kernel<float, OPT_TEST, true> : kv_dense_kernel<float, OPT_TEST, false>;
+        case OPT_SGD: return pick_n<float, OPT_SGD, false>(sn);
+        case OPT_SGD_MOM: return pick_n<float, OPT_SGD_MOM, false>(sn);
+        case OPT_ADAM: return pick_n<float, OPT_ADAM, false>(sn);
+        case OPT_ADAMW: return pick_n<float, OPT_ADAMW, false>(sn);
+        case OPT_TEST: return pick_n<float, OPT_TEST, false>(sn);
         default: return nullptr;
       }
-    case kFloat16:
-      if (L.opt == OPT_NONE) return kv_dense_kernel<__half, OPT_NONE, false>;
-      return pick_fused<__half>(L.opt, mp);
-    case kBfloat16:
-      if (L.opt == OPT_NONE) return kv_dense_kernel<__nv_bfloat16, OPT_NONE, false>;
-      return pick_fused<__nv_bfloat16>(L.opt, mp);
+    case kFloat16: return pick_opt<__half>(L.opt, mp, sn, false);
+    case kBfloat16: return pick_opt<__nv_bfloat16>(L.opt, mp, sn, false);
     case kFloat64: return L.opt == OPT_NONE ? kv_sum_typed_kernel<double> : nullptr;
     case kInt32: return L.opt == OPT_NONE ? kv_sum_typed_kernel<int32_t> : nullptr;
     case kInt64: return L.opt == OPT_NONE ? kv_sum_typed_kernel<int64_t> : nullptr;

@@ -88,6 +88,7 @@ struct DenseLaunch {
   float rescale, clip, momentum, beta1, beta2, eps;
   SyncArgs sync;
   int grid;                      // blocks to launch (identical on every rank of a collective)
+  int small_n;                   // every entry has n_src <= 2: use the two-packets-in-flight variant
 };
 
 // returns cudaError_t as int; never throws

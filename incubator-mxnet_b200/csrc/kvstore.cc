@@ -256,6 +256,8 @@ Replica& KVStore::FreshReplica(KeyState& ks) {
 Replica& KVStore::EnsureReplica(KeyState& ks, int dev) {
   if (Replica* r = FindReplica(ks, dev)) {
     if (!r->fresh) {
+      if (ks.local_world > 0) GatherLocal(ks);
+      if (r->fresh) return *r;
       Replica& src = FreshReplica(ks);
       CopyFromTo(src.local, r->local);
       r->fresh = true;
@@ -269,6 +271,7 @@ Replica& KVStore::EnsureReplica(KeyState& ks, int dev) {
   nr.dev = dev;
   nr.local = NDArray::Empty(ks.shape, Context{kGPU, dev}, ks.dtype, /*symmetric=*/rt->pg() != nullptr);
   if (!ks.reps.empty()) {
+    if (ks.local_world > 0) GatherLocal(ks);
     if (ks.has_state) GatherState(ks);   // make every existing replica's optimizer state complete
     Replica& src = FreshReplica(ks);
     CopyFromTo(src.local, nr.local);
@@ -470,6 +473,7 @@ void KVStore::PullImpl(const std::vector<int>& keys, const std::vector<NDArray*>
       PullDenseFromRowSparse(ks, grouped[i]);
       continue;
     }
+    if (ks.local_world > 0) GatherLocal(ks);       // the all-gather half of a sharded push
     for (NDArray* o : grouped[i]) {
       MXKV_CHECK(o->stype() == kDefaultStorage) << "pull into a sparse array is not supported for dense keys";
       MXKV_CHECK(o->size() == ks.size) << "pull: output has " << o->size() << " elements, key " << ks.key
@@ -544,15 +548,8 @@ int64_t ShardLen(int64_t size, int world) {
 namespace {
 struct Dest {
   void* ptr[kMaxRanks];   // address as seen by participant p (MP: peer mapping; SP: same everywhere)
-  int owner;              // participant index that owns the memory, -1: none
-};
-struct LaunchClassKey {
-  int sync_mode, dtype, mp;
-  bool operator<(const LaunchClassKey& o) const {
-    if (sync_mode != o.sync_mode) return sync_mode < o.sync_mode;
-    if (dtype != o.dtype) return dtype < o.dtype;
-    return mp < o.mp;
-  }
+  int owner;              // participant index that owns the memory, -1: none, -2: one copy per rank (MP)
+  bool own_only = false;  // two-shot: only the owning participant writes (its own shard of its own copy)
 };
 struct PostCopy { NDArray src; NDArray dst; };
 inline bool Overlap(const void* a, size_t an, const void* b, size_t bn) {
@@ -666,6 +663,11 @@ void KVStore::ReduceUpdate(std::vector<Group>& groups, bool write_outs) {
 
     const bool two_shot = collective && static_cast<int64_t>(ks.size * esize) >= rt->twoshot_bytes &&
                           ks.size >= static_cast<int64_t>(n_part) * 128;
+    if (ks.local_world > 0 && !(two_shot && ks.local_world == n_part && ks.shard_devs == part_dev)) {
+      GatherLocal(ks);
+      for (int p = my_first; p <= my_last; ++p) rep[p] = &EnsureReplica(ks, part_dev[p]);
+      for (int p = my_first; p <= my_last; ++p) rep[p] = FindReplica(ks, part_dev[p]);
+    }
     if (fused && collective) {
       const int want = two_shot ? n_part : 0;
       if (ks.count > 0 && ks.state_world != want) GatherState(ks);
@@ -750,32 +752,18 @@ void KVStore::ReduceUpdate(std::vector<Group>& groups, bool write_outs) {
       }
       callback_keys.push_back(&ks);
     } else {
-      if (mp_mode && collective) {
-        Dest d; d.owner = -2;
-        for (int p = 0; p < n_part; ++p) d.ptr[p] = rep[pg->rank()]->local.peer_data(p);
-        dests.push_back(d);
-      } else {
-        for (auto& r : ks.reps) {
-          const bool reachable = r.dev == root_dev || collective ||
-                                 (rt->EnablePeerAccess({root_dev, r.dev}), rt->PeerOK(root_dev, r.dev));
-          bool is_part = false;
-          for (int p = 0; p < n_part; ++p) if (part_dev[p] == r.dev) is_part = true;
-          if (is_part || (reachable && !collective)) {
-            if (!is_part) { touch(r.dev); rt->StreamWait(root_dev, r.dev); }
-            add_dest_sp(r.local.data(), r.dev);
-            r.fresh = true;
-          } else {
-            r.fresh = false;          // refreshed lazily by EnsureReplica
-          }
-        }
-      }
+      // which outputs can be written by the kernel itself?
+      std::vector<char> out_direct(g.outs.size(), 0);
+      bool need_post = false;
       if (write_outs) {
-        for (NDArray* o : g.outs) {
+        int budget = kMaxOut - 1 - (mp_mode ? 1 : static_cast<int>(ks.reps.size()));
+        for (size_t oi = 0; oi < g.outs.size(); ++oi) {
+          NDArray* o = g.outs[oi];
           MXKV_CHECK(o->size() == ks.size && o->dtype() == ks.dtype)
               << "pushpull: output does not match key " << ks.key;
           const Context oc = o->ctx();
           bool direct = false;
-          if (oc.is_gpu() && static_cast<int>(dests.size()) < kMaxOut - 1) {
+          if (oc.is_gpu() && budget > 0) {
             if (mp_mode) {
               direct = collective ? o->symmetric() : (oc.dev_id == pg->dev());
             } else {
@@ -788,7 +776,41 @@ void KVStore::ReduceUpdate(std::vector<Group>& groups, bool write_outs) {
             }
             if (direct && !Aligned16(o->data())) direct = false;
           }
-          if (direct) {
+          out_direct[oi] = direct ? 1 : 0;
+          if (direct) --budget; else need_post = true;
+        }
+      }
+      // Two-shot keys keep the stored value sharded (rank p owns shard p of its own replica) unless
+      // an output has to be copied out of a complete replica afterwards: the all-gather then moves
+      // each shard over NVLink once per peer (into the outputs) instead of twice.
+      const bool shard_local = two_shot && !need_post;
+      if (mp_mode && collective) {
+        Dest d; d.owner = -2; d.own_only = shard_local;
+        for (int p = 0; p < n_part; ++p) d.ptr[p] = rep[pg->rank()]->local.peer_data(p);
+        dests.push_back(d);
+      } else {
+        for (auto& r : ks.reps) {
+          const bool reachable = r.dev == root_dev || collective ||
+                                 (rt->EnablePeerAccess({root_dev, r.dev}), rt->PeerOK(root_dev, r.dev));
+          bool is_part = false;
+          for (int p = 0; p < n_part; ++p) if (part_dev[p] == r.dev) is_part = true;
+          if (is_part || (reachable && !collective)) {
+            if (!is_part) { touch(r.dev); rt->StreamWait(root_dev, r.dev); }
+            add_dest_sp(r.local.data(), r.dev);
+            dests.back().own_only = shard_local;
+            r.fresh = true;
+          } else {
+            r.fresh = false;          // refreshed lazily by EnsureReplica
+          }
+        }
+      }
+      if (shard_local) { ks.local_world = n_part; ks.shard_devs = part_dev; }
+      else ks.local_world = 0;
+      if (write_outs) {
+        for (size_t oi = 0; oi < g.outs.size(); ++oi) {
+          NDArray* o = g.outs[oi];
+          const Context oc = o->ctx();
+          if (out_direct[oi]) {
             touch(oc.dev_id);
             if (mp_mode && collective) {
               Dest d; d.owner = -2;
@@ -836,19 +858,18 @@ void KVStore::ReduceUpdate(std::vector<Group>& groups, bool write_outs) {
         vec_ok = vec_ok && Aligned16(tw.src[k]);
       }
       for (auto& d : dests) {
-        bool mine;
-        if (d.owner == -2) mine = two_shot ? true : false;   // MP: handled below
-        else if (two_shot) mine = true;
-        else if (!collective) mine = true;
-        else mine = (d.owner == p) || (d.owner == -1 && p == 0);
-        if (d.owner == -2) {
-          if (two_shot) {
+        if (d.owner == -2) {           // MP: one copy per rank
+          if (two_shot && !d.own_only) {
             for (int q = 0; q < n_part; ++q) { tw.out[tw.n_out++] = d.ptr[q]; vec_ok = vec_ok && Aligned16(d.ptr[q]); }
           } else {
             tw.out[tw.n_out++] = d.ptr[p]; vec_ok = vec_ok && Aligned16(d.ptr[p]);
           }
           continue;
         }
+        bool mine;
+        if (!collective) mine = true;
+        else if (two_shot && !d.own_only) mine = true;
+        else mine = (d.owner == p) || (d.owner == -1 && p == 0);
         if (mine) { tw.out[tw.n_out++] = d.ptr[p]; vec_ok = vec_ok && Aligned16(d.ptr[p]); }
       }
       MXKV_CHECK(tw.n_out <= kMaxOut) << "too many destinations for key " << ks.key;
@@ -871,64 +892,7 @@ void KVStore::ReduceUpdate(std::vector<Group>& groups, bool write_outs) {
 
   // ---- launches: one per class per local participant --------------------------
   const int opt_kind = fused ? opt_.kind : OPT_NONE;
-  for (auto& kv : classes) {
-    const LaunchClassKey& ck = kv.first;
-    auto& per_part = kv.second.per_part;
-    // identical grid on every rank: derived from the busiest rank's chunk count
-    std::vector<std::vector<int64_t>> prefixes(n_part);
-    const int64_t max_chunks = std::max<int64_t>(1, kv.second.max_chunks);
-    const int my_first = mp_mode ? pg->rank() : 0;
-    const int my_last = mp_mode ? pg->rank() : n_part - 1;
-    for (int p = my_first; p <= my_last; ++p) {
-      auto& w = per_part[p];
-      prefixes[p].resize(w.size() + 1);
-      int64_t acc = 0;
-      for (size_t i = 0; i < w.size(); ++i) {
-        prefixes[p][i] = acc;
-        acc += (w[i].end - w[i].begin + kChunkElems - 1) / kChunkElems;
-      }
-      prefixes[p][w.size()] = acc;
-    }
-    for (int p = my_first; p <= my_last; ++p) {
-      auto& w = per_part[p];
-      if (w.empty()) continue;
-      const int dev = part_dev[p];
-      DeviceState& d = rt->Dev(dev);
-      const size_t wbytes = w.size() * sizeof(TensorWork);
-      const size_t pbytes = prefixes[p].size() * sizeof(int64_t);
-      const size_t bytes = wbytes + pbytes;
-      const size_t off = d.ring.Alloc(bytes);
-      std::memcpy(d.ring.host(off), w.data(), wbytes);
-      std::memcpy(d.ring.host(off) + wbytes, prefixes[p].data(), pbytes);
-      DeviceGuard dg(dev);
-      CUDA_CALL(cudaMemcpyAsync(d.ring.dev(off), d.ring.host(off), bytes, cudaMemcpyHostToDevice, d.stream));
-      DenseLaunch L;
-      std::memset(&L, 0, sizeof(L));
-      L.works = reinterpret_cast<const TensorWork*>(d.ring.dev(off));
-      L.chunk_prefix = reinterpret_cast<const int64_t*>(d.ring.dev(off) + wbytes);
-      L.nworks = static_cast<int>(w.size());
-      L.total_chunks = prefixes[p].back();
-      L.dtype = ck.dtype;
-      L.opt = opt_kind;
-      L.multi_precision = ck.mp;
-      L.order = order_;
-      L.fp32_accum = (opt_kind != OPT_NONE || ck.dtype == kBfloat16 ||
-                      EnvInt("MXKV_B200_FP16_FP32_ACCUM", 0) != 0) ? 1 : 0;
-      L.rescale = opt_.rescale; L.clip = opt_.clip; L.momentum = opt_.momentum;
-      L.beta1 = static_cast<float>(opt_.beta1); L.beta2 = static_cast<float>(opt_.beta2); L.eps = opt_.eps;
-      L.sync.mode = ck.sync_mode;
-      L.sync.world = n_part;
-      L.sync.rank = p;
-      L.sync.self = d.signal_pad;
-      for (int q = 0; q < n_part; ++q)
-        L.sync.peers[q] = mp_mode ? pg->signal_pad(q) : rt->Dev(part_dev[q]).signal_pad;
-      L.grid = static_cast<int>(std::min<int64_t>(d.max_grid, max_chunks));
-      const int rc = LaunchDense(L, d.stream);
-      MXKV_CHECK(rc == 0) << "kernel launch failed: " << cudaGetErrorString(static_cast<cudaError_t>(rc));
-      rt->launches++;
-      d.ring.Commit(off, bytes, d.stream);
-    }
-  }
+  for (auto& kv : classes) LaunchWorks(kv.first, kv.second.per_part, kv.second.max_chunks, opt_kind, part_dev);
 
   // ---- epilogue -------------------------------------------------------------------
   for (size_t i = 0; i < temps.size(); ++i) {
@@ -945,6 +909,113 @@ void KVStore::ReduceUpdate(std::vector<Group>& groups, bool write_outs) {
   }
   for (auto& pc : post) CopyFromTo(pc.src, pc.dst);
   for (int dev : touched) rt->ReleaseToUser(dev);
+}
+
+// One kernel launch per local participant for a list of work entries that share dtype /
+// precision mode / synchronisation mode.  The grid is derived from the busiest rank's chunk
+// count, which every rank computes identically (paired blocks rendezvous across GPUs).
+void KVStore::LaunchWorks(const LaunchClassKey& ck, std::vector<std::vector<TensorWork>>& per_part,
+                          int64_t max_chunks_in, int opt_kind, const std::vector<int>& part_dev) {
+  Runtime* rt = Runtime::Get();
+  ProcessGroup* pg = rt->pg();
+  const bool mp_mode = pg != nullptr;
+  const int n_part = static_cast<int>(part_dev.size());
+  const int64_t max_chunks = std::max<int64_t>(1, max_chunks_in);
+  const int my_first = mp_mode ? pg->rank() : 0;
+  const int my_last = mp_mode ? pg->rank() : n_part - 1;
+  for (int p = my_first; p <= my_last; ++p) {
+    auto& w = per_part[p];
+    if (w.empty()) continue;
+    std::vector<int64_t> prefix(w.size() + 1);
+    int64_t acc = 0;
+    for (size_t i = 0; i < w.size(); ++i) {
+      prefix[i] = acc;
+      acc += (w[i].end - w[i].begin + kChunkElems - 1) / kChunkElems;
+    }
+    prefix[w.size()] = acc;
+    const int dev = part_dev[p];
+    DeviceState& d = rt->Dev(dev);
+    const size_t wbytes = w.size() * sizeof(TensorWork);
+    const size_t pbytes = prefix.size() * sizeof(int64_t);
+    const size_t bytes = wbytes + pbytes;
+    const size_t off = d.ring.Alloc(bytes);
+    std::memcpy(d.ring.host(off), w.data(), wbytes);
+    std::memcpy(d.ring.host(off) + wbytes, prefix.data(), pbytes);
+    DeviceGuard dg(dev);
+    CUDA_CALL(cudaMemcpyAsync(d.ring.dev(off), d.ring.host(off), bytes, cudaMemcpyHostToDevice, d.stream));
+    DenseLaunch L;
+    std::memset(&L, 0, sizeof(L));
+    L.works = reinterpret_cast<const TensorWork*>(d.ring.dev(off));
+    L.chunk_prefix = reinterpret_cast<const int64_t*>(d.ring.dev(off) + wbytes);
+    L.nworks = static_cast<int>(w.size());
+    L.total_chunks = prefix.back();
+    L.dtype = ck.dtype;
+    L.opt = opt_kind;
+    L.multi_precision = ck.mp;
+    L.order = order_;
+    L.fp32_accum = (opt_kind != OPT_NONE || ck.dtype == kBfloat16 ||
+                    EnvInt("MXKV_B200_FP16_FP32_ACCUM", 0) != 0) ? 1 : 0;
+    L.rescale = opt_.rescale; L.clip = opt_.clip; L.momentum = opt_.momentum;
+    L.beta1 = static_cast<float>(opt_.beta1); L.beta2 = static_cast<float>(opt_.beta2); L.eps = opt_.eps;
+    L.sync.mode = ck.sync_mode;
+    L.sync.world = n_part;
+    L.sync.rank = p;
+    L.sync.self = d.signal_pad;
+    for (int q = 0; q < n_part; ++q)
+      L.sync.peers[q] = mp_mode ? pg->signal_pad(q) : rt->Dev(part_dev[q]).signal_pad;
+    L.grid = static_cast<int>(std::min<int64_t>(d.max_grid, max_chunks));
+    int small_n = 1;
+    for (auto& t : w) if (t.n_src > 2) small_n = 0;
+    L.small_n = small_n;
+    const int rc = LaunchDense(L, d.stream);
+    MXKV_CHECK(rc == 0) << "kernel launch failed: " << cudaGetErrorString(static_cast<cudaError_t>(rc));
+    rt->launches++;
+    d.ring.Commit(off, bytes, d.stream);
+  }
+}
+
+// All-gather of a key whose stored value is valid shard-wise only (after a two-shot push that did
+// not have to deliver full outputs): participant p stores its shard into every replica.
+void KVStore::GatherLocal(KeyState& ks) {
+  const int n = ks.local_world;
+  if (n <= 1) { ks.local_world = 0; return; }
+  Runtime* rt = Runtime::Get();
+  ProcessGroup* pg = rt->pg();
+  const bool mp_mode = pg != nullptr;
+  const std::vector<int> part_dev = ks.shard_devs;
+  MXKV_CHECK(static_cast<int>(part_dev.size()) == n) << "inconsistent shard layout for key " << ks.key;
+  const int64_t shard = ShardLen(ks.size, n);
+  std::vector<std::vector<TensorWork>> per_part(n);
+  const int my_first = mp_mode ? pg->rank() : 0;
+  const int my_last = mp_mode ? pg->rank() : n - 1;
+  for (int p = my_first; p <= my_last; ++p) {
+    Replica* r = FindReplica(ks, part_dev[p]);
+    MXKV_CHECK(r != nullptr) << "missing replica";
+    TensorWork tw;
+    std::memset(&tw, 0, sizeof(tw));
+    tw.src[0] = r->local.data();
+    tw.n_src = 1;
+    for (int q = 0; q < n; ++q) {
+      if (mp_mode) {
+        tw.out[tw.n_out++] = r->local.peer_data(q);
+      } else {
+        Replica* rq = FindReplica(ks, part_dev[q]);
+        tw.out[tw.n_out++] = rq->local.data();
+      }
+    }
+    tw.begin = std::min<int64_t>(ks.size, shard * p);
+    tw.end = std::min<int64_t>(ks.size, shard * (p + 1));
+    tw.pad_ = 1;
+    per_part[p].push_back(tw);
+  }
+  LaunchClassKey ck{SYNC_WRITE_PEERS, ks.dtype, 0};
+  LaunchWorks(ck, per_part, (std::min<int64_t>(ks.size, shard) + kChunkElems - 1) / kChunkElems, OPT_NONE, part_dev);
+  ks.local_world = 0;
+  for (auto& r : ks.reps) {
+    bool is_part = false;
+    for (int d : part_dev) if (d == r.dev) is_part = true;
+    r.fresh = is_part;
+  }
 }
 
 // updater_(key, merged, &local) on the caller thread (kvstore_local.h:259-277); the callee owns and
@@ -1018,6 +1089,7 @@ NDArray KVStore::GetState(bool str_key, int ikey, const std::string& skey, int w
   LOCK();
   KeyState& ks = GetKey(ResolveKey(str_key, ikey, skey));
   if (ks.reps.empty()) EnsureReplica(ks, DefaultDevice());
+  if (ks.local_world > 0) GatherLocal(ks);
   GatherState(ks);
   Replica& r = FreshReplica(ks);
   switch (which) {
@@ -1033,6 +1105,7 @@ void KVStore::SetState(bool str_key, int ikey, const std::string& skey, int whic
   LOCK();
   KeyState& ks = GetKey(ResolveKey(str_key, ikey, skey));
   if (ks.reps.empty()) EnsureReplica(ks, DefaultDevice());
+  if (ks.local_world > 0) GatherLocal(ks);
   GatherState(ks);
   MXKV_CHECK(v.size() == ks.size) << "SetState: size mismatch";
   for (auto& r : ks.reps) {

@@ -60,11 +60,22 @@ struct KeyState {
   std::vector<Replica> reps;
   int64_t count = 0;             // Optimizer._index_update_count
   int state_world = 0;           // number of shards the optimizer state is laid out for (0: replicated/none)
+  int local_world = 0;           // > 0: the stored value is valid shard-wise only (shard p on shard_devs[p])
+  std::vector<int> shard_devs;   // devices (SP) / placeholder per rank (MP) of the shard owners
   bool has_state = false;
   NDArray rsp_local;             // row_sparse stored value (dense-backed rows), see kvstore_rsp.cc
 };
 
 int64_t ShardLen(int64_t size, int world);
+
+struct LaunchClassKey {
+  int sync_mode, dtype, mp;
+  bool operator<(const LaunchClassKey& o) const {
+    if (sync_mode != o.sync_mode) return sync_mode < o.sync_mode;
+    if (dtype != o.dtype) return dtype < o.dtype;
+    return mp < o.mp;
+  }
+};
 
 class KVStore {
  public:
@@ -130,6 +141,9 @@ class KVStore {
   };
   // the fused reduce(+update)(+broadcast) over a list of dense key groups
   void ReduceUpdate(std::vector<Group>& groups, bool write_outs);
+  void LaunchWorks(const LaunchClassKey& ck, std::vector<std::vector<TensorWork>>& per_part, int64_t max_chunks,
+                   int opt_kind, const std::vector<int>& part_dev);
+  void GatherLocal(KeyState& ks);
   void RunCallbackUpdater(KeyState& ks, Replica& root);
   void PushRowSparse(KeyState& ks, const std::vector<NDArray>& vals);
   void InitRowSparseKey(KeyState& ks, const NDArray& v);

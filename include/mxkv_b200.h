@@ -29,7 +29,7 @@ extern "C" {
 
 typedef void* NDArrayHandle;           /* c_api.h:67  */
 typedef void* KVStoreHandle;           /* c_api.h:93  */
-typedef void* DLManagedTensorHandle;   /* c_api.h:108 */
+typedef void* DLManagedTensorHandle;   /* c_api.h:105 */
 typedef uint32_t mx_uint;
 
 /* ---- errors / library info ---------------------------------------------- */
@@ -91,9 +91,9 @@ MXKV_DLL int MXKVStorePullWithSparse(KVStoreHandle handle, uint32_t num, const i
 MXKV_DLL int MXKVStorePullWithSparseEx(KVStoreHandle handle, uint32_t num, const char** keys,
                                        NDArrayHandle* vals, int priority, bool ignore_sparse); /* :2503 */
 MXKV_DLL int MXKVStorePull(KVStoreHandle handle, uint32_t num, const int* keys, NDArrayHandle* vals,
-                           int priority);                                                /* c_api.h:2517 */
+                           int priority);                                                /* c_api.h:2518 */
 MXKV_DLL int MXKVStorePullEx(KVStoreHandle handle, uint32_t num, const char** keys, NDArrayHandle* vals,
-                             int priority);                                              /* c_api.h:2531 */
+                             int priority);                                              /* c_api.h:2532 */
 MXKV_DLL int MXKVStorePullRowSparse(KVStoreHandle handle, uint32_t num, const int* keys,
                                     NDArrayHandle* vals, const NDArrayHandle* row_ids, int priority);   /* :2550 */
 MXKV_DLL int MXKVStorePullRowSparseEx(KVStoreHandle handle, uint32_t num, const char** keys,
@@ -113,16 +113,16 @@ MXKV_DLL int MXKVStorePushPullEx(KVStoreHandle handle, mx_uint vnum, const char*
 /* updater callbacks: the callee must free both NDArray handles (c_api.h:2661) */
 typedef void(MXKVStoreUpdater)(int key, NDArrayHandle recv, NDArrayHandle local, void* handle);
 typedef void(MXKVStoreStrUpdater)(const char* key, NDArrayHandle recv, NDArrayHandle local, void* handle);
-MXKV_DLL int MXKVStoreSetUpdater(KVStoreHandle handle, MXKVStoreUpdater updater, void* updater_handle);  /* :2683 */
+MXKV_DLL int MXKVStoreSetUpdater(KVStoreHandle handle, MXKVStoreUpdater updater, void* updater_handle);  /* :2690 */
 MXKV_DLL int MXKVStoreSetUpdaterEx(KVStoreHandle handle, MXKVStoreUpdater updater,
-                                   MXKVStoreStrUpdater str_updater, void* updater_handle);               /* :2696 */
+                                   MXKVStoreStrUpdater str_updater, void* updater_handle);               /* :2701 */
 MXKV_DLL int MXKVStoreGetType(KVStoreHandle handle, const char** type);                  /* c_api.h:2711 */
 MXKV_DLL int MXKVStoreGetRank(KVStoreHandle handle, int* ret);                           /* c_api.h:2724 */
-MXKV_DLL int MXKVStoreGetGroupSize(KVStoreHandle handle, int* ret);                      /* c_api.h:2735 */
-MXKV_DLL int MXKVStoreIsWorkerNode(int* ret);                                            /* c_api.h:2743 */
-MXKV_DLL int MXKVStoreIsServerNode(int* ret);                                            /* c_api.h:2751 */
-MXKV_DLL int MXKVStoreIsSchedulerNode(int* ret);                                         /* c_api.h:2759 */
-MXKV_DLL int MXKVStoreBarrier(KVStoreHandle handle);                                     /* c_api.h:2767 */
+MXKV_DLL int MXKVStoreGetGroupSize(KVStoreHandle handle, int* ret);                      /* c_api.h:2736 */
+MXKV_DLL int MXKVStoreIsWorkerNode(int* ret);                                            /* c_api.h:2744 */
+MXKV_DLL int MXKVStoreIsServerNode(int* ret);                                            /* c_api.h:2752 */
+MXKV_DLL int MXKVStoreIsSchedulerNode(int* ret);                                         /* c_api.h:2760 */
+MXKV_DLL int MXKVStoreBarrier(KVStoreHandle handle);                                     /* c_api.h:2768 */
 MXKV_DLL int MXKVStoreSetBarrierBeforeExit(KVStoreHandle handle, const int barrier_before_exit); /* :2777 */
 MXKV_DLL int MXKVStoreGetNumDeadNode(KVStoreHandle handle, const int node_id, int* number,
                                      const int timeout_sec);                             /* c_api.h:2822 */

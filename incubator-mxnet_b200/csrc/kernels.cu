@@ -17,6 +17,7 @@
 // FMA: results are bit-identical to the CPU oracle (oracle/kv_oracle.c), which
 // restates the reference source operation by operation.
 #include "kernels.h"
+#include "rsp_kernels.h"
 #include <cuda_fp16.h>
 #include <cuda_bf16.h>
 
@@ -548,6 +549,16 @@ int LaunchCastToF32(const void* src, int dtype, float* dst, int64_t n, cudaStrea
     case kBfloat16: kv_cast_f32_kernel<__nv_bfloat16><<<blocks, threads, 0, s>>>(static_cast<const __nv_bfloat16*>(src), dst, n); break;
     default: return static_cast<int>(cudaErrorInvalidValue);
   }
+  return static_cast<int>(cudaGetLastError());
+}
+
+__global__ void kv_barrier_kernel(SyncArgs sync) {
+  barrier_start(sync);
+  barrier_end(sync, true);
+}
+
+int LaunchBarrier(const SyncArgs& sync, cudaStream_t stream) {
+  kv_barrier_kernel<<<1, 32, 0, stream>>>(sync);
   return static_cast<int>(cudaGetLastError());
 }
 

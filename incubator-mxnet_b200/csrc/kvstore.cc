@@ -356,41 +356,7 @@ void KVStore::InitImpl(const std::vector<int>& keys, const std::vector<NDArray>&
       keys_[keys[i]] = ks;
       KeyState& k2 = keys_[keys[i]];
       Replica& r = EnsureReplica(k2, dev);
-      if (pg && pg->world() > 1) {
-        // every rank adopts rank 0's value: one-shot read of rank 0's replica
-        DeviceState& d = rt->Dev(dev);
-        TensorWork tw;
-        std::memset(&tw, 0, sizeof(tw));
-        tw.src[0] = r.local.peer_data(0);
-        tw.n_src = 1;
-        tw.out[0] = r.local.data();
-        tw.n_out = 1;
-        tw.begin = 0; tw.end = k2.size;
-        tw.pad_ = 1;
-        int64_t prefix[2] = {0, (k2.size + kChunkElems - 1) / kChunkElems};
-        if (prefix[1] == 0) prefix[1] = 1;
-        const size_t bytes = sizeof(TensorWork) + sizeof(prefix);
-        const size_t off = d.ring.Alloc(bytes);
-        std::memcpy(d.ring.host(off), &tw, sizeof(tw));
-        std::memcpy(d.ring.host(off) + sizeof(tw), prefix, sizeof(prefix));
-        DeviceGuard g(dev);
-        CUDA_CALL(cudaMemcpyAsync(d.ring.dev(off), d.ring.host(off), bytes, cudaMemcpyHostToDevice, d.stream));
-        DenseLaunch L;
-        std::memset(&L, 0, sizeof(L));
-        L.works = reinterpret_cast<const TensorWork*>(d.ring.dev(off));
-        L.chunk_prefix = reinterpret_cast<const int64_t*>(d.ring.dev(off) + sizeof(tw));
-        L.nworks = 1; L.total_chunks = prefix[1];
-        L.dtype = k2.dtype; L.opt = OPT_NONE; L.order = ORDER_DEVICE; L.fp32_accum = 1;
-        L.sync.self = d.signal_pad;
-        for (int q = 0; q < pg->world(); ++q) L.sync.peers[q] = pg->signal_pad(q);
-        L.sync.world = pg->world(); L.sync.rank = pg->rank(); L.sync.mode = SYNC_READ_PEERS;
-        L.grid = static_cast<int>(std::min<int64_t>(d.max_grid, prefix[1]));
-        // rank 0 must not have its replica overwritten while peers read it: it copies onto itself
-        const int rc = LaunchDense(L, d.stream);
-        MXKV_CHECK(rc == 0) << "kernel launch failed: " << cudaGetErrorString(static_cast<cudaError_t>(rc));
-        rt->launches++;
-        d.ring.Commit(off, bytes, d.stream);
-      }
+      if (pg && pg->world() > 1) BroadcastFromRank0(k2, r);
       rt->ReleaseToUser(dev);
     } else {
       // host value, devices unknown yet: keep a private host copy (values[i].Copy(pinned_ctx_))
@@ -400,6 +366,27 @@ void KVStore::InitImpl(const std::vector<int>& keys, const std::vector<NDArray>&
       keys_[keys[i]] = ks;
     }
   }
+}
+
+// one-process-per-GPU mode: every rank adopts rank 0's stored value (one-shot read of rank 0's
+// replica; rank 0 copies onto itself).  Collective.
+void KVStore::BroadcastFromRank0(KeyState& ks, Replica& r) {
+  Runtime* rt = Runtime::Get();
+  ProcessGroup* pg = rt->pg();
+  if (pg == nullptr || pg->world() <= 1) return;
+  TensorWork tw;
+  std::memset(&tw, 0, sizeof(tw));
+  tw.src[0] = r.local.peer_data(0);
+  tw.n_src = 1;
+  tw.out[0] = r.local.data();
+  tw.n_out = 1;
+  tw.begin = 0; tw.end = r.local.size();
+  tw.pad_ = 1;
+  std::vector<int> part_dev(pg->world(), pg->dev());
+  std::vector<std::vector<TensorWork>> per_part(pg->world());
+  per_part[pg->rank()].push_back(tw);
+  LaunchClassKey ck{SYNC_READ_PEERS, r.local.dtype(), 0};
+  LaunchWorks(ck, per_part, (r.local.size() + kChunkElems - 1) / kChunkElems, OPT_NONE, part_dev);
 }
 
 // ---------------------------------------------------------------------------

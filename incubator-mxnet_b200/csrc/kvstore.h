@@ -48,6 +48,12 @@ struct Replica {
   NDArray stage;     // MP mode: symmetric staging for non-symmetric gradients
   NDArray merged;    // updater-callback path: reduce target
   bool fresh = true;
+  // row_sparse keys: `local` is the dense-backed table [num_rows x row_len]
+  NDArray rsp_merged;            // union ids + summed rows of the last push (capacity n * rsp_cap rows)
+  NDArray rsp_first, rsp_pf;     // int32 workspaces of the union kernels
+  int64_t rsp_cap = 0;           // rows per source the workspaces are sized for
+  int rsp_n = 0;
+  NDArray stage_idx, stage_val, stage_nnz;   // MP mode: symmetric staging of this rank's gradient
 };
 
 struct KeyState {
@@ -148,6 +154,7 @@ class KVStore {
   void PushRowSparse(KeyState& ks, const std::vector<NDArray>& vals);
   void InitRowSparseKey(KeyState& ks, const NDArray& v);
   void PullDenseFromRowSparse(KeyState& ks, const std::vector<NDArray*>& outs);
+  void BroadcastFromRank0(KeyState& ks, Replica& r);
 
   KeyState& GetKey(int key);
   Replica& EnsureReplica(KeyState& ks, int dev);

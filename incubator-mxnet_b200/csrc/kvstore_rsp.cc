@@ -1,24 +1,376 @@
-// kvstore_rsp.cc -- row_sparse push / row_sparse_pull (placeholder until the sparse kernels land).
+// kvstore_rsp.cc -- row_sparse push / row_sparse_pull of KVStoreLocal on the B200 kernels.
+//
+// Reference: CommDevice::ReduceRowSparse (src/kvstore/comm.h:479-502) copies every row_sparse
+// source to one GPU and calls the row_sparse ElementwiseSum; the updater then runs a sparse
+// optimizer op; PullRowSparseImpl (src/kvstore/kvstore_local.h:316-336) = Unique(row_ids) +
+// BroadcastRowSparse (comm.h:627-683: SparseRetain + copy).
+//
+// Here the stored value of a row_sparse key is a dense-backed table [num_rows x row_len] on
+// every participating GPU (absent rows are zero rows, which is what SparseRetain returns for
+// them).  A push runs the nnz-proportional union + gather-sum + lazy-update kernels
+// (rsp_kernels.cu) on every replica's GPU, reading all sources in place (peer loads); nothing is
+// copied to a root and nothing synchronises with the host.  row_sparse_pull sorts/uniques the ids
+// in one block and gathers rows from the local replica.
+#include <algorithm>
+#include <cstring>
+#include <set>
 #include "kvstore.h"
+#include "rsp_kernels.h"
 
 namespace mxkv {
 
+namespace {
+inline bool Aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+void CheckLaunch(int rc, const char* what) {
+  MXKV_CHECK(rc == 0) << what << " launch failed: " << cudaGetErrorString(static_cast<cudaError_t>(rc));
+  Runtime::Get()->launches++;
+}
+
+// device-side view of a row_sparse NDArray living on (or staged to) GPU `dev`
+struct RspView {
+  const int64_t* idx;
+  const float* val;
+  const int64_t* nnz;
+};
+}  // namespace
+
+// make sure the device scalar of a row_sparse array mirrors its host-known row count
+static void PublishNnz(const NDArray& a) {
+  const int64_t n = a.nnz();   // host value (syncs only if it was device-only)
+  const Context c = a.ctx();
+  if (c.is_gpu()) {
+    DeviceGuard g(c.dev_id);
+    CheckLaunch(LaunchSetI64(a.d_nnz(), n, Runtime::Get()->Dev(c.dev_id).stream), "set_nnz");
+  } else {
+    *a.d_nnz() = n;
+  }
+}
+
 void KVStore::InitRowSparseKey(KeyState& ks, const NDArray& v) {
-  (void)ks; (void)v;
-  MXKV_FATAL() << "row_sparse keys are not implemented yet";
+  Runtime* rt = Runtime::Get();
+  ProcessGroup* pg = rt->pg();
+  MXKV_CHECK(v.dtype() == kFloat32) << "row_sparse keys support float32 only";
+  MXKV_CHECK(v.shape().size() >= 2) << "row_sparse keys need at least 2 dimensions";
+  const Context c = v.ctx();
+  const int dev = pg ? pg->dev() : (c.is_gpu() ? c.dev_id : DefaultDevice());
+  if (c.is_gpu()) rt->AcquireUser(c.dev_id);
+  Replica r;
+  r.dev = dev;
+  r.local = NDArray::Empty(ks.shape, Context{kGPU, dev}, kFloat32, pg != nullptr);
+  DeviceGuard g(dev);
+  cudaStream_t s = rt->Dev(dev).stream;
+  CUDA_CALL(cudaMemsetAsync(r.local.data(), 0, r.local.nbytes(), s));
+  const int64_t nnz = v.nnz();
+  const int64_t L = v.row_len();
+  if (nnz > 0) {
+    const int64_t* idx = v.idx_ptr();
+    const float* val = static_cast<const float*>(v.data());
+    void* tmp_idx = nullptr; void* tmp_val = nullptr; int64_t* tmp_nnz = nullptr;
+    CUDA_CALL(cudaMallocAsync(reinterpret_cast<void**>(&tmp_nnz), 16, s));
+    CheckLaunch(LaunchSetI64(tmp_nnz, nnz, s), "set_nnz");
+    if (!(c.is_gpu() && c.dev_id == dev)) {
+      CUDA_CALL(cudaMallocAsync(&tmp_idx, nnz * 8, s));
+      CUDA_CALL(cudaMallocAsync(&tmp_val, nnz * L * 4, s));
+      CopyBytes(idx, c, tmp_idx, Context{kGPU, dev}, nnz * 8);
+      CopyBytes(val, c, tmp_val, Context{kGPU, dev}, nnz * L * 4);
+      idx = static_cast<const int64_t*>(tmp_idx);
+      val = static_cast<const float*>(tmp_val);
+    }
+    CheckLaunch(LaunchRspScatter(static_cast<float*>(r.local.data()), idx, tmp_nnz, nnz, L, val, s), "rsp_scatter");
+    if (tmp_idx) CUDA_CALL(cudaFreeAsync(tmp_idx, s));
+    if (tmp_val) CUDA_CALL(cudaFreeAsync(tmp_val, s));
+    CUDA_CALL(cudaFreeAsync(tmp_nnz, s));
+  }
+  ks.reps.push_back(r);
+  if (pg && pg->world() > 1) BroadcastFromRank0(ks, ks.reps.back());
+  rt->WaitDevice(dev);            // the host-side source may be released by the caller
+  rt->ReleaseToUser(dev);
 }
+
+static void EnsureRspWorkspace(KeyState& ks, Replica& r, int n, int64_t cap) {
+  if (r.rsp_n >= n && r.rsp_cap >= cap && !r.rsp_merged.is_none()) return;
+  const Context ctx{kGPU, r.dev};
+  n = std::max(n, r.rsp_n);
+  cap = std::max<int64_t>(std::max<int64_t>(cap, r.rsp_cap), 16);
+  r.rsp_first = NDArray::Empty({static_cast<int64_t>(n) * cap}, ctx, kInt32);
+  r.rsp_pf = NDArray::Empty({static_cast<int64_t>(n) * (cap + 1)}, ctx, kInt32);
+  r.rsp_merged = NDArray::EmptyRowSparse(ks.shape, ctx, kFloat32, static_cast<int64_t>(n) * cap);
+  r.rsp_merged.set_nnz_device();
+  r.rsp_n = n;
+  r.rsp_cap = cap;
+}
+
 void KVStore::PushRowSparse(KeyState& ks, const std::vector<NDArray>& vals) {
-  (void)ks; (void)vals;
-  MXKV_FATAL() << "row_sparse push is not implemented yet";
+  Runtime* rt = Runtime::Get();
+  ProcessGroup* pg = rt->pg();
+  const bool mp_mode = pg != nullptr;
+  MXKV_CHECK(ks.stype == kRowSparseStorage)
+      << "key " << ks.key << " was initialised dense; row_sparse push needs a row_sparse key";
+  const int n_src = static_cast<int>(vals.size());
+  MXKV_CHECK(n_src >= 1 && n_src <= kMaxSrc) << "push of " << n_src << " row_sparse values (max " << kMaxSrc << ")";
+  const int64_t L = ks.size / ks.shape[0];
+  int64_t cap = 0;
+  for (auto& v : vals) {
+    MXKV_CHECK(v.stype() == kRowSparseStorage) << "mixing dense and row_sparse values in one push is not supported";
+    MXKV_CHECK(v.dtype() == kFloat32 && v.shape() == ks.shape) << "row_sparse push: shape/dtype mismatch";
+    cap = std::max(cap, v.nnz());
+  }
+  const bool callback = updater_ != nullptr;
+  const bool fused = opt_.enabled && !callback;
+  if (fused)
+    MXKV_CHECK(opt_.kind == OPT_SGD || opt_.kind == OPT_SGD_MOM || opt_.kind == OPT_ADAM)
+        << "row_sparse gradients: only the lazy SGD / SGD-momentum / Adam updates are fused";
+
+  // ---- which GPUs compute (each one redundantly, on its own replica) -------------------------
+  std::vector<int> work_devs;
+  std::set<int> touched;
+  auto touch = [&](int dev) { if (dev >= 0 && touched.insert(dev).second) rt->AcquireUser(dev); };
+  if (mp_mode) {
+    MXKV_CHECK(n_src == 1) << "one-process-per-GPU mode: push exactly one value per key per rank";
+    work_devs.push_back(pg->dev());
+  } else {
+    for (auto& r : ks.reps) work_devs.push_back(r.dev);
+    for (auto& v : vals) {
+      const Context c = v.ctx();
+      if (c.is_gpu() && std::find(work_devs.begin(), work_devs.end(), c.dev_id) == work_devs.end())
+        work_devs.push_back(c.dev_id);
+    }
+    if (work_devs.empty()) work_devs.push_back(DefaultDevice());
+    rt->EnablePeerAccess(work_devs);
+  }
+  for (auto& v : vals) {
+    if (v.ctx().is_gpu()) touch(v.ctx().dev_id);
+    PublishNnz(v);
+  }
+  for (int d : work_devs) { touch(d); EnsureReplica(ks, d); }
+
+  if (fused) ks.count += 1;
+  const float lr = fused ? KeyLR(ks) : 0.f;
+  const float wd = fused ? KeyWD(ks) : 0.f;
+
+  // ---- MP: publish this rank's gradient in the symmetric staging area ---------------------------
+  int world = 1;
+  if (mp_mode && pg->world() > 1) {
+    world = pg->world();
+    Replica& r = *FindReplica(ks, pg->dev());
+    const int64_t stage_rows = std::min<int64_t>(ks.shape[0], EnvInt("MXKV_B200_RSP_STAGE_ROWS", 131072));
+    if (r.stage_idx.is_none()) {
+      const Context ctx{kGPU, pg->dev()};
+      r.stage_idx = NDArray::Empty({stage_rows}, ctx, kInt64, true);
+      r.stage_val = NDArray::Empty({stage_rows * L}, ctx, kFloat32, true);
+      r.stage_nnz = NDArray::Empty({2}, ctx, kInt64, true);
+    }
+    const NDArray& v = vals[0];
+    MXKV_CHECK(v.nnz() <= r.stage_idx.size())
+        << "row_sparse gradient with " << v.nnz() << " rows exceeds the staging capacity of "
+        << r.stage_idx.size() << " rows; raise MXKV_B200_RSP_STAGE_ROWS";
+    cap = r.stage_idx.size();
+    DeviceGuard g(pg->dev());
+    cudaStream_t s = rt->Dev(pg->dev()).stream;
+    // peers may still be reading the staging area of the previous push: rendezvous first
+    SyncArgs sync;
+    std::memset(&sync, 0, sizeof(sync));
+    sync.self = rt->Dev(pg->dev()).signal_pad;
+    for (int q = 0; q < world; ++q) sync.peers[q] = pg->signal_pad(q);
+    sync.world = world; sync.rank = pg->rank(); sync.mode = SYNC_WRITE_PEERS;
+    CheckLaunch(LaunchBarrier(sync, s), "barrier");
+    if (v.nnz() > 0) {
+      CopyBytes(v.idx_ptr(), v.ctx(), r.stage_idx.data(), r.stage_idx.ctx(), v.nnz() * 8);
+      CopyBytes(v.data(), v.ctx(), r.stage_val.data(), r.stage_val.ctx(), v.nnz() * L * 4);
+    }
+    CheckLaunch(LaunchSetI64(static_cast<int64_t*>(r.stage_nnz.data()), v.nnz(), s), "set_nnz");
+    CheckLaunch(LaunchBarrier(sync, s), "barrier");
+  }
+
+  // ---- per computing GPU: sources as seen from it, then the four kernels -----------------------
+  for (int dev : work_devs) {
+    Replica& r = *FindReplica(ks, dev);
+    DeviceGuard g(dev);
+    cudaStream_t s = rt->Dev(dev).stream;
+    RspSources S;
+    std::memset(&S, 0, sizeof(S));
+    std::vector<void*> temps;
+    if (world > 1) {
+      S.n = world;
+      for (int q = 0; q < world; ++q) {
+        S.idx[q] = static_cast<const int64_t*>(r.stage_idx.peer_data(q));
+        S.val[q] = static_cast<const float*>(r.stage_val.peer_data(q));
+        S.nnz[q] = static_cast<const int64_t*>(r.stage_nnz.peer_data(q));
+      }
+    } else {
+      S.n = n_src;
+      for (int k = 0; k < n_src; ++k) {
+        const NDArray& v = vals[k];
+        const Context c = v.ctx();
+        const int64_t nnz = v.nnz();
+        const bool direct = c.is_gpu() && (c.dev_id == dev || rt->PeerOK(dev, c.dev_id));
+        if (direct) {
+          if (c.dev_id != dev) rt->StreamWait(dev, c.dev_id);
+          S.idx[k] = v.idx_ptr();
+          S.val[k] = static_cast<const float*>(v.data());
+          S.nnz[k] = v.d_nnz();
+        } else {   // host-resident (or unreachable) source: stage it on this GPU
+          void* ti = nullptr; void* tv = nullptr; int64_t* tn = nullptr;
+          CUDA_CALL(cudaMallocAsync(&ti, std::max<int64_t>(nnz, 1) * 8, s));
+          CUDA_CALL(cudaMallocAsync(&tv, std::max<int64_t>(nnz * L, 1) * 4, s));
+          CUDA_CALL(cudaMallocAsync(reinterpret_cast<void**>(&tn), 16, s));
+          if (nnz > 0) {
+            CopyBytes(v.idx_ptr(), c, ti, Context{kGPU, dev}, nnz * 8);
+            CopyBytes(v.data(), c, tv, Context{kGPU, dev}, nnz * L * 4);
+          }
+          CheckLaunch(LaunchSetI64(tn, nnz, s), "set_nnz");
+          temps.push_back(ti); temps.push_back(tv); temps.push_back(tn);
+          S.idx[k] = static_cast<const int64_t*>(ti);
+          S.val[k] = static_cast<const float*>(tv);
+          S.nnz[k] = tn;
+        }
+      }
+    }
+    EnsureRspWorkspace(ks, r, S.n, cap);
+    RspRowArgs A;
+    std::memset(&A, 0, sizeof(A));
+    A.out_idx = r.rsp_merged.idx_ptr();
+    A.out_val = (fused) ? nullptr : static_cast<float*>(r.rsp_merged.data());
+    A.d_nnz_out = r.rsp_merged.d_nnz();
+    A.table = static_cast<float*>(r.local.data());
+    A.row_len = L;
+    A.opt = fused ? opt_.kind : OPT_NONE;
+    A.assign = (!fused && !callback) ? 1 : 0;
+    A.lr = lr; A.wd = wd; A.rescale = opt_.rescale; A.clip = opt_.clip; A.momentum = opt_.momentum;
+    A.beta1 = static_cast<float>(opt_.beta1); A.beta2 = static_cast<float>(opt_.beta2); A.eps = opt_.eps;
+    if (fused) {
+      EnsureState(ks, r, false);
+      A.s0 = r.s0.is_none() ? nullptr : static_cast<float*>(r.s0.data());
+      A.s1 = r.s1.is_none() ? nullptr : static_cast<float*>(r.s1.data());
+    }
+    bool vec = (L % 4 == 0) && Aligned16(A.table) && (A.out_val == nullptr || Aligned16(A.out_val)) &&
+               (A.s0 == nullptr || Aligned16(A.s0)) && (A.s1 == nullptr || Aligned16(A.s1));
+    for (int k = 0; k < S.n; ++k) vec = vec && Aligned16(S.val[k]);
+    A.vec = vec ? 1 : 0;
+    if (A.assign) {
+      // push without updater: local = merged (kvstore_local.h:279-284) -- rows outside the union vanish
+      CUDA_CALL(cudaMemsetAsync(r.local.data(), 0, r.local.nbytes(), s));
+    }
+    CheckLaunch(LaunchRspSum(S, A, static_cast<int32_t*>(r.rsp_first.data()),
+                             static_cast<int32_t*>(r.rsp_pf.data()), r.rsp_cap, s), "rsp_sum");
+    rt->launches += 3;
+    r.rsp_merged.set_nnz_device();
+    for (void* t : temps) CUDA_CALL(cudaFreeAsync(t, s));
+    r.fresh = true;
+  }
+  if (world > 1) {
+    // nobody may overwrite its staging area while a peer is still reading it: the rendezvous at the
+    // start of the next push (above) provides that ordering
+  } else {
+    // sources on other GPUs were read by this GPU's kernels: they must not be reused earlier
+    for (auto& v : vals) {
+      const Context c = v.ctx();
+      if (!c.is_gpu()) continue;
+      for (int dev : work_devs) if (dev != c.dev_id) rt->StreamWait(c.dev_id, dev);
+    }
+  }
+  if (callback) {
+    Replica& root = *FindReplica(ks, work_devs[0]);
+    rt->Dev(root.dev).engine_dirty = true;
+    rt->Fence(root.dev);
+    NDHandle* recv = new NDHandle(root.rsp_merged);
+    NDHandle* local = new NDHandle(root.local);
+    if (key_type_ == kStringKey && str_updater_ != nullptr) {
+      str_updater_(reverse_str_key_dict_[ks.key].c_str(), recv, local, updater_handle_);
+    } else {
+      updater_(ks.key, recv, local, updater_handle_);
+    }
+    rt->AcquireUser(root.dev);
+    for (auto& r : ks.reps) r.fresh = (&r == &root);
+  }
+  for (int d : touched) rt->ReleaseToUser(d);
 }
+
 void KVStore::PullDenseFromRowSparse(KeyState& ks, const std::vector<NDArray*>& outs) {
-  (void)ks; (void)outs;
-  MXKV_FATAL() << "pull from a row_sparse key is not implemented yet";
+  Runtime* rt = Runtime::Get();
+  std::set<int> touched;
+  for (NDArray* o : outs) {
+    MXKV_CHECK(o->stype() == kDefaultStorage) << "pull of a row_sparse key into a sparse array: use row_sparse_pull";
+    MXKV_CHECK(o->size() == ks.size && o->dtype() == ks.dtype) << "pull: output does not match key " << ks.key;
+    const Context c = o->ctx();
+    if (c.is_gpu() && touched.insert(c.dev_id).second) rt->AcquireUser(c.dev_id);
+    const bool local_dev = c.is_gpu() && (rt->pg() == nullptr || c.dev_id == rt->pg()->dev());
+    Replica& r = local_dev ? EnsureReplica(ks, c.dev_id) : FreshReplica(ks);
+    CopyFromTo(r.local.Reshape(o->shape()), *o);      // storage-type cast of CopyFromTo (ndarray.cc:1301-1327)
+  }
+  for (int d : touched) rt->ReleaseToUser(d);
 }
+
 void KVStore::PullRowSparseImpl(const std::vector<int>& keys,
                                 const std::vector<std::pair<NDArray*, NDArray>>& vr, int priority) {
-  (void)keys; (void)vr; (void)priority;
-  MXKV_FATAL() << "row_sparse_pull is not implemented yet";
+  (void)priority;
+  MXKV_CHECK(keys.size() == vr.size()) << keys.size() << " keys but " << vr.size() << " values";
+  Runtime* rt = Runtime::Get();
+  std::set<int> touched;
+  auto touch = [&](int dev) { if (dev >= 0 && touched.insert(dev).second) rt->AcquireUser(dev); };
+  for (size_t i = 0; i < keys.size(); ++i) {
+    NDArray* out = vr[i].first;
+    const NDArray& row_id = vr[i].second;
+    // GroupKVPairsPullRsp validator, kvstore_local.h:421-431
+    MXKV_CHECK(out->stype() == kRowSparseStorage)
+        << "Expected row_sparse storage type for row_sparse_pull values, but detected storage type " << out->stype();
+    MXKV_CHECK(row_id.stype() == kDefaultStorage)
+        << "Expected default storage type for row_sparse_pull rowids, but detected storage type " << row_id.stype();
+    KeyState& ks = GetKey(keys[i]);
+    MXKV_CHECK(ks.stype == kRowSparseStorage) << "PullRowSparse expects row_sparse src NDArray";
+    MXKV_CHECK(row_id.dtype() == kInt64) << "row_ids must be int64";
+    const int64_t n = row_id.size();
+    MXKV_CHECK(n <= RspUniqueMax()) << "row_sparse_pull of more than " << RspUniqueMax() << " row ids per call";
+    const int64_t L = ks.size / ks.shape[0];
+    const Context oc = out->ctx();
+    const Context rc = row_id.ctx();
+    int dev;
+    if (rt->pg()) dev = rt->pg()->dev();
+    else if (oc.is_gpu()) dev = oc.dev_id;
+    else if (rc.is_gpu()) dev = rc.dev_id;
+    else dev = FreshReplica(ks).dev;
+    touch(dev);
+    if (oc.is_gpu()) touch(oc.dev_id);
+    if (rc.is_gpu()) touch(rc.dev_id);
+    Replica& r = EnsureReplica(ks, dev);
+    DeviceGuard g(dev);
+    cudaStream_t s = rt->Dev(dev).stream;
+    // ids on this GPU
+    const int64_t* ids = static_cast<const int64_t*>(row_id.data());
+    void* tmp_ids = nullptr;
+    if (!(rc.is_gpu() && rc.dev_id == dev) && n > 0) {
+      CUDA_CALL(cudaMallocAsync(&tmp_ids, n * 8, s));
+      CopyBytes(row_id.data(), rc, tmp_ids, Context{kGPU, dev}, n * 8);
+      ids = static_cast<const int64_t*>(tmp_ids);
+    }
+    const bool direct = oc.is_gpu() && oc.dev_id == dev;
+    if (direct && out->cap_rows() < n) out->ReserveRows(n);
+    NDArray target = *out;
+    if (!direct) target = NDArray::EmptyRowSparse(ks.shape, Context{kGPU, dev}, kFloat32, std::max<int64_t>(n, 1));
+    MXKV_CHECK(target.cap_rows() >= n) << "row_sparse_pull: output holds " << target.cap_rows() << " rows, "
+                                       << n << " row ids requested";
+    MXKV_CHECK(target.dtype() == kFloat32) << "row_sparse_pull: float32 outputs only";
+    CheckLaunch(LaunchRspUnique(ids, n, target.idx_ptr(), target.d_nnz(), s), "rsp_unique");
+    const int vec = (L % 4 == 0 && Aligned16(r.local.data()) && Aligned16(target.data())) ? 1 : 0;
+    CheckLaunch(LaunchRspGather(static_cast<const float*>(r.local.data()), target.idx_ptr(), target.d_nnz(),
+                                std::max<int64_t>(n, 1), L, static_cast<float*>(target.data()), target.idx_ptr(),
+                                vec, s), "rsp_gather");
+    target.set_nnz_device();
+    if (tmp_ids) CUDA_CALL(cudaFreeAsync(tmp_ids, s));
+    if (!direct) {
+      const int64_t cnt = target.nnz();      // one sync: the destination lives elsewhere
+      if (out->cap_rows() < cnt) out->ReserveRows(cnt);
+      if (cnt > 0) {
+        CopyBytes(target.idx_ptr(), target.ctx(), out->idx_ptr(), oc, cnt * 8);
+        CopyBytes(target.data(), target.ctx(), out->data(), oc, cnt * L * 4);
+      }
+      out->set_nnz(cnt);
+      if (oc.is_gpu()) PublishNnz(*out);
+      rt->WaitDevice(dev);
+    }
+  }
+  for (int d : touched) rt->ReleaseToUser(d);
 }
 
 }  // namespace mxkv

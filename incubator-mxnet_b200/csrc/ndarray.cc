@@ -209,6 +209,17 @@ NDArray NDArray::Slice1D(int64_t begin, int64_t end) const {
   return a;
 }
 
+void NDArray::ReserveRows(int64_t rows) {
+  MXKV_CHECK(stype_ == kRowSparseStorage) << "ReserveRows on a dense array";
+  if (rows <= cap_rows_) return;
+  NDArray fresh = EmptyRowSparse(shape_, ctx(), dtype_, rows);
+  chunk_ = fresh.chunk_;
+  aux_ = fresh.aux_;
+  byte_offset_ = 0;
+  cap_rows_ = rows;
+  *nnz_ = 0;
+}
+
 int64_t NDArray::row_len() const {
   int64_t L = 1;
   for (size_t i = 1; i < shape_.size(); ++i) L *= shape_[i];

@@ -56,6 +56,9 @@ class NDArray {
   // lives only on the device (d_nnz_) until someone asks (nnz() syncs).
   int64_t row_len() const;
   int64_t cap_rows() const { return cap_rows_; }
+  // grow the row capacity (contents are discarded); row_sparse arrays are dynamically sized in the
+  // reference (CheckAndAlloc), handles stay valid
+  void ReserveRows(int64_t rows);
   int64_t nnz() const;
   void set_nnz(int64_t n) { *nnz_ = n; }
   void set_nnz_device() { *nnz_ = -1; }

@@ -188,6 +188,13 @@ class NDArray(object):
 
     def _binary_inplace(self, other, op):
         t = self.as_torch()
+        if isinstance(other, NDArray) and other.stype == "row_sparse":
+            # dense (op)= row_sparse: only the stored rows take part (used by updater callbacks)
+            assert op in ("add_", "sub_"), "row_sparse operand supports += / -= only"
+            idx = other.indices.as_torch().to(t.device)
+            val = other.data.as_torch().to(t.device).reshape((idx.numel(),) + tuple(t.shape[1:]))
+            t.index_add_(0, idx, val if op == "add_" else -val)
+            return self
         o = other.as_torch().to(t.device) if isinstance(other, NDArray) else other
         getattr(t, op)(o)
         return self
@@ -243,7 +250,8 @@ class NDArray(object):
         return out
 
 
-def empty(shape, ctx=None, dtype=np.float32, stype="default"):
+def empty(shape, ctx=None, dtype=np.float32, stype="default", capacity=None):
+    """``capacity`` (row_sparse only): number of rows the array can hold (default: all rows)."""
     if isinstance(shape, int):
         shape = (shape,)
     ctx = ctx or cpu()
@@ -252,7 +260,7 @@ def empty(shape, ctx=None, dtype=np.float32, stype="default"):
     if stype == "row_sparse":
         aux_type = (ctypes.c_int * 1)(6)
         aux_ndims = (ctypes.c_int * 1)(1)
-        aux_shape = (ctypes.c_int64 * 1)(shape[0])
+        aux_shape = (ctypes.c_int64 * 1)(shape[0] if capacity is None else max(int(capacity), 1))
         check_call(_LIB.MXNDArrayCreateSparseEx64(1, cshape, len(shape), ctx.device_typeid, ctx.device_id, 0,
                                                   _mx_dtype(dtype), 1, aux_type, aux_ndims, aux_shape,
                                                   ctypes.byref(out)))
@@ -297,7 +305,7 @@ def full(shape, val, ctx=None, dtype=np.float32):
     return out
 
 
-def row_sparse_array(arg, shape=None, ctx=None, dtype=np.float32):
+def row_sparse_array(arg, shape=None, ctx=None, dtype=np.float32, capacity=None):
     """row_sparse from a dense numpy array (non-zero rows kept) or a (data, indices) pair."""
     if isinstance(arg, tuple):
         data, indices = np.asarray(arg[0]), np.asarray(arg[1], np.int64)
@@ -308,7 +316,7 @@ def row_sparse_array(arg, shape=None, ctx=None, dtype=np.float32):
         flat = dense.reshape(shape[0], -1)
         indices = np.where(np.any(flat != 0, axis=1))[0].astype(np.int64)
         data = dense[indices]
-    out = empty(shape, ctx, dtype, stype="row_sparse")
+    out = empty(shape, ctx, dtype, stype="row_sparse", capacity=capacity if capacity is not None else len(indices))
     vals = empty((len(indices),) + tuple(shape[1:]), cpu(), dtype)
     idx = empty((len(indices),), cpu(), np.int64)
     if len(indices):

@@ -122,6 +122,33 @@ def main():
         kv4.pull(3, out=o)
         assert np.all(o.asnumpy() == it * world), "callback"
 
+    # 5. row_sparse: lazy SGD-momentum over the ranks' sparse gradients + row_sparse_pull
+    rows, L, nnz = 3000, 64, 200
+    shape = (rows, L)
+    w0 = data(31, shape, 0)
+    kw = dict(learning_rate=0.1, momentum=0.9, wd=1e-4)
+    kv5 = mx.kv.create("device")
+    kv5.init("emb", mx.nd.row_sparse_array(w0, ctx=ctx))
+    kv5.set_optimizer(mx.optimizer.SGD(**kw))
+    okv = O.OracleKVStore("device")
+    okv.init("emb", O.RowSparse.from_dense(w0))
+    okv.set_optimizer(O.OracleOptimizer("sgd", **kw))
+
+    def rsp(seed, r):
+        g = np.random.default_rng(seed * 100 + r)
+        idx = np.sort(g.choice(rows, nnz, replace=False)).astype(np.int64)
+        return idx, g.uniform(-1, 1, (nnz, L)).astype(np.float32)
+    for step in range(3):
+        i, v = rsp(step, rank)
+        kv5.push("emb", mx.nd.row_sparse_array((v, i), shape=shape, ctx=ctx))
+        okv.push("emb", [O.RowSparse(*rsp(step, r), shape) for r in range(world)])
+        ids = np.random.default_rng(step).integers(0, rows, 300).astype(np.int64)
+        out = mx.nd.empty(shape, ctx, stype="row_sparse", capacity=300)
+        kv5.row_sparse_pull("emb", out=out, row_ids=mx.nd.array(ids, ctx, dtype=np.int64))
+        want = O.sparse_retain(okv.local["emb"], O.unique(ids))
+        assert np.array_equal(out.indices.asnumpy(), want.indices), "rsp idx"
+        assert bits_equal(out.data.asnumpy(), want.data.reshape(-1, L)), ("rsp", step)
+
     mx.nd.waitall()
     dist.barrier()
     print("MP_WORKER_OK rank", rank, flush=True)

@@ -521,6 +521,12 @@ int MXKVB200GetLaunchCount(int64_t* out) {
   API_END();
 }
 
+int MXKVB200SetTuning(int64_t chunk_elems, int threads, int max_blocks) {
+  API_BEGIN();
+  Runtime::Get()->SetTuning(chunk_elems, threads, max_blocks);
+  API_END();
+}
+
 int MXKVB200SetTwoShotBytes(int64_t bytes) {
   API_BEGIN();
   Runtime::Get()->twoshot_bytes = bytes;

@@ -367,7 +367,7 @@ kv_dense_kernel(DenseLaunch L) {
       __syncthreads();
       const uint4* src = reinterpret_cast<const uint4*>(L.works + lo);
       uint4* dst = reinterpret_cast<uint4*>(&tw);
-      for (int i = threadIdx.x; i < static_cast<int>(sizeof(TensorWork) / 16); i += kThreads)
+      for (int i = threadIdx.x; i < static_cast<int>(sizeof(TensorWork) / 16); i += blockDim.x)
         dst[i] = src[i];
       __syncthreads();
       cur = lo;
@@ -377,17 +377,18 @@ kv_dense_kernel(DenseLaunch L) {
     h.rescale = L.rescale; h.clip = L.clip; h.momentum = L.momentum;
     h.beta1 = L.beta1; h.beta2 = L.beta2; h.eps = L.eps;
 
-    const int64_t cb = tw.begin + (c - L.chunk_prefix[lo]) * kChunkElems;
-    const int64_t ce = (cb + kChunkElems < tw.end) ? cb + kChunkElems : tw.end;
+    const int64_t cb = tw.begin + (c - L.chunk_prefix[lo]) * L.chunk_elems;
+    const int64_t ce = (cb + L.chunk_elems < tw.end) ? cb + L.chunk_elems : tw.end;
     int64_t scalar_from = cb;
     if (tw.pad_ & 1) {  // every pointer 16-byte aligned and begin % 8 == 0
       const int64_t nvec = (ce - cb) / NV;
-      for (int64_t v = threadIdx.x; v < nvec; v += static_cast<int64_t>(U) * kThreads) {
+      const int64_t nthr = blockDim.x;
+      for (int64_t v = threadIdx.x; v < nvec; v += static_cast<int64_t>(U) * nthr) {
         int64_t e[U];
         bool ok[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          const int64_t vv = v + static_cast<int64_t>(u) * kThreads;
+          const int64_t vv = v + static_cast<int64_t>(u) * nthr;
           ok[u] = vv < nvec;
           e[u] = cb + (ok[u] ? vv : v) * NV;
         }
@@ -395,7 +396,7 @@ kv_dense_kernel(DenseLaunch L) {
       }
       scalar_from = cb + nvec * NV;
     }
-    for (int64_t s = scalar_from + threadIdx.x; s < ce; s += kThreads) {
+    for (int64_t s = scalar_from + threadIdx.x; s < ce; s += blockDim.x) {
       const int64_t e1[1] = {s};
       const bool ok1[1] = {true};
       process_packets<T, OPT, MP, 1, 4, 1>(tw, e1, ok1, h, L.order, native_half_add);
@@ -426,14 +427,14 @@ kv_sum_typed_kernel(DenseLaunch L) {
       __syncthreads();
       const uint4* src = reinterpret_cast<const uint4*>(L.works + lo);
       uint4* dst = reinterpret_cast<uint4*>(&tw);
-      for (int i = threadIdx.x; i < static_cast<int>(sizeof(TensorWork) / 16); i += kThreads)
+      for (int i = threadIdx.x; i < static_cast<int>(sizeof(TensorWork) / 16); i += blockDim.x)
         dst[i] = src[i];
       __syncthreads();
       cur = lo;
     }
-    const int64_t cb = tw.begin + (c - L.chunk_prefix[lo]) * kChunkElems;
-    const int64_t ce = (cb + kChunkElems < tw.end) ? cb + kChunkElems : tw.end;
-    for (int64_t e = cb + threadIdx.x; e < ce; e += kThreads) {
+    const int64_t cb = tw.begin + (c - L.chunk_prefix[lo]) * L.chunk_elems;
+    const int64_t ce = (cb + L.chunk_elems < tw.end) ? cb + L.chunk_elems : tw.end;
+    for (int64_t e = cb + threadIdx.x; e < ce; e += blockDim.x) {
       T acc = reinterpret_cast<const T*>(tw.src[0])[e];
       for (int k = 1; k < tw.n_src; ++k) acc = static_cast<T>(acc + reinterpret_cast<const T*>(tw.src[k])[e]);
       for (int j = 0; j < tw.n_out; ++j) reinterpret_cast<T*>(tw.out[j])[e] = acc;
@@ -515,9 +516,11 @@ static int sm_count(int device) {
   return g_num_sms[device];
 }
 
-int DenseMaxGrid(int device) {
-  // __launch_bounds__(512, 2): two resident blocks per SM for every instantiation
-  int g = 2 * sm_count(device);
+int DenseMaxGrid(int device, int threads) {
+  // __launch_bounds__(512, 2): 64 registers/thread, i.e. 1024 resident threads per SM for every
+  // instantiation, whatever the block size
+  if (threads != 128 && threads != 256 && threads != 512) threads = kThreads;
+  int g = (1024 / threads) * sm_count(device);
   return g > kMaxBlocks ? kMaxBlocks : g;
 }
 
@@ -527,7 +530,9 @@ int LaunchDense(const DenseLaunch& L, cudaStream_t stream) {
   int grid = L.grid;
   if (grid < 1) grid = 1;
   if (grid > kMaxBlocks) grid = kMaxBlocks;
-  fn<<<grid, kThreads, 0, stream>>>(L);
+  int threads = L.threads;
+  if (threads != 128 && threads != 256 && threads != 512) threads = kThreads;
+  fn<<<grid, threads, 0, stream>>>(L);
   return static_cast<int>(cudaGetLastError());
 }
 

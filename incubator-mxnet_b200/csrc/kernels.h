@@ -16,7 +16,7 @@ constexpr int kMaxSrc = 16;      // values per key in one push (reference tests 
 constexpr int kMaxOut = 24;      // n store replicas + n user outputs + merge buffers
 constexpr int kMaxRanks = 8;     // one NVSwitch domain
 constexpr int kMaxBlocks = 1184; // 148 SMs x 8
-constexpr int kChunkElems = 8192;
+constexpr int kChunkElems = 8192;   // default elements per scheduling chunk (MXKV_B200_CHUNK)
 
 // mshadow type flags, 3rdparty/mshadow/mshadow/base.h:352-366
 enum DType : int {
@@ -88,12 +88,14 @@ struct DenseLaunch {
   float rescale, clip, momentum, beta1, beta2, eps;
   SyncArgs sync;
   int grid;                      // blocks to launch (identical on every rank of a collective)
+  int chunk_elems;               // elements per scheduling chunk (multiple of 128)
+  int threads;                   // block size: 128, 256 or 512
   int small_n;                   // every entry has n_src <= 2: use the two-packets-in-flight variant
 };
 
 // returns cudaError_t as int; never throws
 int LaunchDense(const DenseLaunch& L, cudaStream_t stream);
-int DenseMaxGrid(int device);   // resident-block capacity of the dense kernel on `device`
+int DenseMaxGrid(int device, int threads);   // resident-block capacity of the dense kernel
 
 int LaunchFill(void* ptr, int value_byte, size_t bytes, cudaStream_t s);
 // dst[i] = float(src[i]) for float32/float16/bfloat16 sources (fp32 master-weight creation)

@@ -7,6 +7,11 @@
 
 namespace mxkv {
 
+static int64_t NumChunks(int64_t elems) {
+  const int64_t c = Runtime::Get()->chunk_elems;
+  return (elems + c - 1) / c;
+}
+
 static std::string Lower(std::string s) {
   std::transform(s.begin(), s.end(), s.begin(), ::tolower);
   return s;
@@ -386,7 +391,7 @@ void KVStore::BroadcastFromRank0(KeyState& ks, Replica& r) {
   std::vector<std::vector<TensorWork>> per_part(pg->world());
   per_part[pg->rank()].push_back(tw);
   LaunchClassKey ck{SYNC_READ_PEERS, r.local.dtype(), 0};
-  LaunchWorks(ck, per_part, (r.local.size() + kChunkElems - 1) / kChunkElems, OPT_NONE, part_dev);
+  LaunchWorks(ck, per_part, NumChunks(r.local.size()), OPT_NONE, part_dev);
 }
 
 // ---------------------------------------------------------------------------
@@ -834,7 +839,7 @@ void KVStore::ReduceUpdate(std::vector<Group>& groups, bool write_outs) {
     auto& cls = lc.per_part;
     if (cls.empty()) cls.resize(n_part);
     const int64_t shard = two_shot ? ShardLen(ks.size, n_part) : ks.size;
-    lc.max_chunks += (std::min<int64_t>(ks.size, shard) + kChunkElems - 1) / kChunkElems;
+    lc.max_chunks += NumChunks(std::min<int64_t>(ks.size, shard));
     for (int p = my_first; p <= my_last; ++p) {
       TensorWork tw;
       std::memset(&tw, 0, sizeof(tw));
@@ -917,7 +922,7 @@ void KVStore::LaunchWorks(const LaunchClassKey& ck, std::vector<std::vector<Tens
     int64_t acc = 0;
     for (size_t i = 0; i < w.size(); ++i) {
       prefix[i] = acc;
-      acc += (w[i].end - w[i].begin + kChunkElems - 1) / kChunkElems;
+      acc += NumChunks(w[i].end - w[i].begin);
     }
     prefix[w.size()] = acc;
     const int dev = part_dev[p];
@@ -951,6 +956,8 @@ void KVStore::LaunchWorks(const LaunchClassKey& ck, std::vector<std::vector<Tens
     for (int q = 0; q < n_part; ++q)
       L.sync.peers[q] = mp_mode ? pg->signal_pad(q) : rt->Dev(part_dev[q]).signal_pad;
     L.grid = static_cast<int>(std::min<int64_t>(d.max_grid, max_chunks));
+    L.chunk_elems = static_cast<int>(rt->chunk_elems);
+    L.threads = rt->threads;
     int small_n = 1;
     for (auto& t : w) if (t.n_src > 2) small_n = 0;
     L.small_n = small_n;
@@ -996,7 +1003,7 @@ void KVStore::GatherLocal(KeyState& ks) {
     per_part[p].push_back(tw);
   }
   LaunchClassKey ck{SYNC_WRITE_PEERS, ks.dtype, 0};
-  LaunchWorks(ck, per_part, (std::min<int64_t>(ks.size, shard) + kChunkElems - 1) / kChunkElems, OPT_NONE, part_dev);
+  LaunchWorks(ck, per_part, NumChunks(std::min<int64_t>(ks.size, shard)), OPT_NONE, part_dev);
   ks.local_world = 0;
   for (auto& r : ks.reps) {
     bool is_part = false;

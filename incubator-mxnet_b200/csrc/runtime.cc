@@ -1,6 +1,7 @@
 // runtime.cc -- streams, event edges, peer access, staging rings, process group.
 #include "runtime.h"
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
 
 namespace mxkv {
@@ -164,6 +165,11 @@ SymPtr ProcessGroup::SymAlloc(size_t bytes) {
 Runtime::Runtime() {
   twoshot_bytes = EnvInt("MXKV_B200_TWOSHOT_BYTES", 256 * 1024);
   auto_fence = EnvInt("MXKV_B200_AUTO_FENCE", 1) != 0;
+  chunk_elems = EnvInt("MXKV_B200_CHUNK", kChunkElems);
+  if (chunk_elems < 128) chunk_elems = 128;
+  chunk_elems = (chunk_elems + 127) / 128 * 128;
+  threads = static_cast<int>(EnvInt("MXKV_B200_THREADS", 512));
+  if (threads != 128 && threads != 256 && threads != 512) threads = 512;
 }
 
 Runtime* Runtime::Get() {
@@ -214,8 +220,8 @@ DeviceState& Runtime::Dev(int dev) {
     cudaGetLastError();
   }
   d->ring.Init(dev, static_cast<size_t>(EnvInt("MXKV_B200_RING_MB", 8)) << 20);
-  d->max_grid = DenseMaxGrid(dev);
-  const int64_t cap = EnvInt("MXKV_B200_MAX_BLOCKS", 0);
+  d->max_grid = DenseMaxGrid(dev, threads);
+  const int64_t cap = max_blocks_override_ > 0 ? max_blocks_override_ : EnvInt("MXKV_B200_MAX_BLOCKS", 0);
   if (cap > 0 && cap < d->max_grid) d->max_grid = static_cast<int>(cap);
   DeviceState& ref = *d;
   devs_[dev] = std::move(d);
@@ -304,6 +310,19 @@ void Runtime::WaitAll() {
     DeviceGuard g(kv.first);
     CUDA_CALL(cudaStreamSynchronize(kv.second->stream));
   }
+}
+
+void Runtime::SetTuning(int64_t chunk, int nthreads, int max_blocks) {
+  std::lock_guard<std::recursive_mutex> lk(mu_);
+  WaitAll();
+  if (chunk > 0) chunk_elems = std::max<int64_t>(128, (chunk + 127) / 128 * 128);
+  if (nthreads == 128 || nthreads == 256 || nthreads == 512) threads = nthreads;
+  for (auto& kv : devs_) {
+    int g = DenseMaxGrid(kv.first, threads);
+    if (max_blocks > 0 && max_blocks < g) g = max_blocks;
+    kv.second->max_grid = g;
+  }
+  max_blocks_override_ = max_blocks;
 }
 
 void Runtime::DrainForFree() noexcept {

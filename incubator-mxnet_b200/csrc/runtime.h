@@ -104,6 +104,7 @@ class Runtime {
   void WaitAll();
   void DrainForFree() noexcept;            // like WaitAll, never throws (used by destructors)
   void WaitDevice(int dev);
+  void SetTuning(int64_t chunk, int nthreads, int max_blocks);
 
   // one-process-per-GPU mode
   void InitProcessGroup(int rank, int world, int dev, AllGatherFn fn, void* ctx);
@@ -114,6 +115,8 @@ class Runtime {
   bool auto_fence = true;
   int64_t launches = 0;                      // kernels launched by this library (bench "gpu_launches")
   int64_t twoshot_bytes = 256 * 1024;
+  int64_t chunk_elems = kChunkElems;         // MXKV_B200_CHUNK
+  int threads = 512;                         // MXKV_B200_THREADS
  private:
   Runtime();
   std::recursive_mutex mu_;
@@ -121,6 +124,7 @@ class Runtime {
   std::unordered_map<int64_t, bool> peer_ok_;
   std::unique_ptr<ProcessGroup> pg_;
   int ndev_ = -1;
+  int max_blocks_override_ = 0;
 };
 
 }  // namespace mxkv

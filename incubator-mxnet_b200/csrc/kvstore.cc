@@ -552,7 +552,145 @@ inline bool Overlap(const void* a, size_t an, const void* b, size_t bn) {
 inline bool Aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 }  // namespace
 
+// Host-resident values and outputs (kv.create('local')-style use, and the end-to-end benchmark):
+// instead of "copy everything in, run, copy everything out" on one stream, every key is cut into
+// segments that flow through a three-stage pipeline on three streams -- H2D of segment i+1, the
+// fused kernel on segment i and D2H of segment i-1 overlap, so PCIe runs full duplex and the
+// kernel is hidden.  The kernel is the same work-list kernel, launched on an element range.
+bool KVStore::HostPipelined(std::vector<Group>& groups, bool write_outs) {
+  Runtime* rt = Runtime::Get();
+  ProcessGroup* pg = rt->pg();
+  if (pg != nullptr && pg->world() > 1) return false;
+  if (updater_ != nullptr) return false;
+  if (EnvInt("MXKV_B200_HOST_PIPELINE", 1) == 0) return false;
+  int64_t total_bytes = 0;
+  for (auto& g : groups) {
+    KeyState& ks = GetKey(g.key);
+    if (ks.stype != kDefaultStorage) return false;
+    if (static_cast<int>(g.vals.size()) > kMaxSrc) return false;
+    for (auto& v : g.vals) {
+      if (v.ctx().is_gpu()) return false;
+      if (v.size() != ks.size || v.dtype() != ks.dtype) return false;   // let the generic path report it
+    }
+    if (write_outs) {
+      for (NDArray* o : g.outs) {
+        if (o->ctx().is_gpu()) return false;
+        if (o->size() != ks.size || o->dtype() != ks.dtype) return false;
+      }
+    }
+    total_bytes += static_cast<int64_t>(ks.size) * DTypeSize(ks.dtype) * g.vals.size();
+  }
+  if (total_bytes < (int64_t(1) << 20)) return false;      // latency-bound: the simple path is fine
+
+  const bool fused = opt_.enabled;
+  const int opt_kind = fused ? opt_.kind : OPT_NONE;
+  int dev = -1;
+  for (auto& g : groups) {
+    KeyState& ks = GetKey(g.key);
+    if (!ks.reps.empty()) { dev = ks.reps[0].dev; break; }
+  }
+  if (dev < 0) dev = DefaultDevice();
+  DeviceState& d = rt->Dev(dev);
+  DeviceGuard dg(dev);
+  const int64_t seg_elems = std::max<int64_t>(rt->chunk_elems, EnvInt("MXKV_B200_HOST_SEG_ELEMS", 4 << 20)) /
+                            rt->chunk_elems * rt->chunk_elems;
+  // staging slots: kMaxSrc is the worst case, size for what this call needs
+  size_t need = 0;
+  for (auto& g : groups) {
+    KeyState& ks = GetKey(g.key);
+    const size_t seg_bytes = static_cast<size_t>(std::min<int64_t>(seg_elems, ks.size)) * DTypeSize(ks.dtype);
+    need = std::max(need, ((seg_bytes + 255) / 256 * 256) * g.vals.size());
+  }
+  if (need > d.host_stage_bytes) {
+    rt->WaitDevice(dev);
+    CUDA_CALL(cudaStreamSynchronize(d.copy_in));
+    CUDA_CALL(cudaStreamSynchronize(d.copy_out));
+    for (int i = 0; i < DeviceState::kHostSlots; ++i) {
+      if (d.host_stage[i]) CUDA_CALL(cudaFree(d.host_stage[i]));
+      CUDA_CALL(cudaMalloc(&d.host_stage[i], need));
+    }
+    d.host_stage_bytes = need;
+  }
+  // outputs of the previous call may still be streaming out of the replicas
+  CUDA_CALL(cudaStreamWaitEvent(d.stream, d.ev_d2h_all, 0));
+  // the staging slots may still be read by kernels of the previous call
+  for (int i = 0; i < DeviceState::kHostSlots; ++i) CUDA_CALL(cudaStreamWaitEvent(d.copy_in, d.ev_kern[i], 0));
+
+  int64_t seq = 0;
+  std::vector<int> part_dev(1, dev);
+  for (auto& g : groups) {
+    KeyState& ks = GetKey(g.key);
+    const size_t esize = DTypeSize(ks.dtype);
+    Replica* r = &EnsureReplica(ks, dev);
+    if (ks.local_world > 0) GatherLocal(ks);
+    const bool lowp = ks.dtype == kFloat16 || ks.dtype == kBfloat16;
+    const bool mp = fused && (opt_.multi_precision || lowp);
+    if (fused) {
+      MXKV_CHECK(ks.dtype == kFloat32 || lowp) << "fused optimizers need float32/float16/bfloat16 keys";
+      if (ks.has_state) GatherState(ks);
+      EnsureState(ks, *r, mp);
+      ks.state_world = 0;
+      ks.count += 1;
+    }
+    r = FindReplica(ks, dev);
+    for (auto& o : ks.reps) o.fresh = (&o == r);
+    const float lr = fused ? KeyLR(ks) : 0.f;
+    const float wd = fused ? KeyWD(ks) : 0.f;
+    const int n_src = static_cast<int>(g.vals.size());
+    const size_t slot_stride = ((static_cast<size_t>(std::min<int64_t>(seg_elems, ks.size)) * esize + 255) / 256) * 256;
+    for (int64_t b = 0; b < ks.size || (ks.size == 0 && b == 0); b += seg_elems) {
+      const int64_t e = std::min<int64_t>(ks.size, b + seg_elems);
+      if (e <= b) break;
+      const int slot = static_cast<int>(seq % DeviceState::kHostSlots);
+      const size_t bytes = static_cast<size_t>(e - b) * esize;
+      // stage 1: H2D (the slot is free once the kernel that last read it has finished)
+      if (seq >= DeviceState::kHostSlots) CUDA_CALL(cudaStreamWaitEvent(d.copy_in, d.ev_kern[slot], 0));
+      for (int k = 0; k < n_src; ++k) {
+        char* dst = static_cast<char*>(d.host_stage[slot]) + k * slot_stride;
+        const char* src = static_cast<const char*>(g.vals[k].data()) + static_cast<size_t>(b) * esize;
+        CUDA_CALL(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, d.copy_in));
+      }
+      CUDA_CALL(cudaEventRecord(d.ev_h2d[slot], d.copy_in));
+      // stage 2: fused reduce(+update) on the element range [b, e)
+      CUDA_CALL(cudaStreamWaitEvent(d.stream, d.ev_h2d[slot], 0));
+      TensorWork tw;
+      std::memset(&tw, 0, sizeof(tw));
+      tw.n_src = n_src;
+      for (int k = 0; k < n_src; ++k)
+        tw.src[k] = static_cast<char*>(d.host_stage[slot]) + k * slot_stride - static_cast<size_t>(b) * esize;
+      tw.out[tw.n_out++] = r->local.data();
+      tw.w = r->local.data();
+      tw.w32 = mp ? static_cast<float*>(r->w32.data()) : nullptr;
+      tw.s0 = r->s0.is_none() ? nullptr : static_cast<float*>(r->s0.data());
+      tw.s1 = r->s1.is_none() ? nullptr : static_cast<float*>(r->s1.data());
+      tw.begin = b; tw.end = e;
+      tw.lr = lr; tw.wd = wd; tw.eta = opt_.eta;
+      tw.pad_ = 1;
+      std::vector<std::vector<TensorWork>> per_part(1);
+      per_part[0].push_back(tw);
+      LaunchClassKey ck{SYNC_NONE, ks.dtype, mp ? 1 : 0};
+      LaunchWorks(ck, per_part, NumChunks(e - b), opt_kind, part_dev);
+      CUDA_CALL(cudaEventRecord(d.ev_kern[slot], d.stream));
+      // stage 3: D2H of the freshly written range of the replica
+      if (write_outs && !g.outs.empty()) {
+        CUDA_CALL(cudaStreamWaitEvent(d.copy_out, d.ev_kern[slot], 0));
+        for (NDArray* o : g.outs) {
+          char* dst = static_cast<char*>(o->data()) + static_cast<size_t>(b) * esize;
+          const char* src = static_cast<const char*>(r->local.data()) + static_cast<size_t>(b) * esize;
+          CUDA_CALL(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, d.copy_out));
+        }
+      }
+      ++seq;
+    }
+  }
+  CUDA_CALL(cudaEventRecord(d.ev_d2h_all, d.copy_out));
+  // WaitToRead / WaitAll synchronise the engine stream: make it cover the copies as well
+  CUDA_CALL(cudaStreamWaitEvent(d.stream, d.ev_d2h_all, 0));
+  return true;
+}
+
 void KVStore::ReduceUpdate(std::vector<Group>& groups, bool write_outs) {
+  if (HostPipelined(groups, write_outs)) return;
   Runtime* rt = Runtime::Get();
   ProcessGroup* pg = rt->pg();
   const bool mp_mode = pg != nullptr;

@@ -150,6 +150,7 @@ class KVStore {
   void LaunchWorks(const LaunchClassKey& ck, std::vector<std::vector<TensorWork>>& per_part, int64_t max_chunks,
                    int opt_kind, const std::vector<int>& part_dev);
   void GatherLocal(KeyState& ks);
+  bool HostPipelined(std::vector<Group>& groups, bool write_outs);
   void RunCallbackUpdater(KeyState& ks, Replica& root);
   void PushRowSparse(KeyState& ks, const std::vector<NDArray>& vals);
   void InitRowSparseKey(KeyState& ks, const NDArray& v);

@@ -203,6 +203,13 @@ DeviceState& Runtime::Dev(int dev) {
   CUDA_CALL(cudaEventCreateWithFlags(&d->ev_user, cudaEventDisableTiming));
   CUDA_CALL(cudaEventCreateWithFlags(&d->ev_engine, cudaEventDisableTiming));
   CUDA_CALL(cudaEventCreateWithFlags(&d->ev_xdev, cudaEventDisableTiming));
+  CUDA_CALL(cudaStreamCreateWithFlags(&d->copy_in, cudaStreamNonBlocking));
+  CUDA_CALL(cudaStreamCreateWithFlags(&d->copy_out, cudaStreamNonBlocking));
+  for (int i = 0; i < DeviceState::kHostSlots; ++i) {
+    CUDA_CALL(cudaEventCreateWithFlags(&d->ev_h2d[i], cudaEventDisableTiming));
+    CUDA_CALL(cudaEventCreateWithFlags(&d->ev_kern[i], cudaEventDisableTiming));
+  }
+  CUDA_CALL(cudaEventCreateWithFlags(&d->ev_d2h_all, cudaEventDisableTiming));
   if (pg_ && pg_->dev() == dev) {
     d->signal_pad = pg_->signal_pad(pg_->rank());
   } else {

@@ -57,6 +57,13 @@ struct DeviceState {
   StagingRing ring;
   int max_grid = 296;
   bool engine_dirty = false;           // engine stream has work the user stream has not been fenced on
+  // host-resident values: H2D / compute / D2H software pipeline (kvstore.cc: HostPipelined)
+  static constexpr int kHostSlots = 3;
+  cudaStream_t copy_in = nullptr, copy_out = nullptr;
+  cudaEvent_t ev_h2d[kHostSlots] = {nullptr}, ev_kern[kHostSlots] = {nullptr};
+  cudaEvent_t ev_d2h_all = nullptr;
+  void* host_stage[kHostSlots] = {nullptr};
+  size_t host_stage_bytes = 0;
 };
 
 struct SymPtr {                 // one symmetric allocation as seen from this process

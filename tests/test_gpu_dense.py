@@ -142,6 +142,35 @@ def test_fused_host_values():
     _fused_case("sgd", kw, kw, 4, 4099, 3, cpu_vals=True)
 
 
+@pytest.mark.parametrize("pinned", [True, False])
+def test_host_pipeline_segments(pinned, monkeypatch):
+    """large host-resident values/outputs go through the segmented H2D / kernel / D2H pipeline;
+    results must not depend on the segmentation."""
+    monkeypatch.setenv("MXKV_B200_HOST_SEG_ELEMS", str(1 << 18))
+    E, n = (1 << 20) + 12345, 3
+    rng = _rng(77)
+    hctx = mx.cpu_pinned() if pinned else mx.cpu()
+    w0 = rng.uniform(0, 1, E).astype(np.float32)
+    kw = dict(learning_rate=0.05, momentum=0.9, wd=1e-4)
+    kv = mx.kv.create("device")
+    kv.init([0, 1], [mx.nd.array(w0, hctx), mx.nd.array(w0[:5000], hctx)])
+    kv.set_optimizer(mx.optimizer.SGD(**kw))
+    okv = O.OracleKVStore("device")
+    okv.init([0, 1], [w0.copy(), w0[:5000].copy()])
+    okv.set_optimizer(O.OracleOptimizer("sgd", **kw))
+    outs = [mx.nd.empty((E,), hctx), mx.nd.empty((5000,), hctx)]
+    for step in range(3):
+        g0 = [rng.uniform(-1, 1, E).astype(np.float32) for _ in range(n)]
+        g1 = [rng.uniform(-1, 1, 5000).astype(np.float32) for _ in range(n)]
+        kv.pushpull([0, 1], [[mx.nd.array(g, hctx) for g in g0], [mx.nd.array(g, hctx) for g in g1]], out=outs)
+        okv.push([0, 1], [g0, g1])
+        for k, o in enumerate(outs):
+            o.wait_to_read()
+            want = np.empty(o.shape, np.float32)
+            okv.pull(k, want)
+            assert_bits_equal(o.asnumpy(), want, "host pipeline step %d key %d" % (step, k))
+
+
 @pytest.mark.parametrize("lp", ["bfloat16", np.float16])
 def test_multi_precision_sgd_momentum(lp):
     """bf16/fp16 weights+grads, fp32 master and momentum (MP_SGDMomKernel)."""

@@ -521,9 +521,9 @@ int MXKVB200GetLaunchCount(int64_t* out) {
   API_END();
 }
 
-int MXKVB200SetTuning(int64_t chunk_elems, int threads, int max_blocks) {
+int MXKVB200SetTuning(int64_t chunk_elems, int threads, int max_blocks, int bulk) {
   API_BEGIN();
-  Runtime::Get()->SetTuning(chunk_elems, threads, max_blocks);
+  Runtime::Get()->SetTuning(chunk_elems, threads, max_blocks, bulk);
   API_END();
 }
 

@@ -20,6 +20,8 @@
 #include "rsp_kernels.h"
 #include <cuda_fp16.h>
 #include <cuda_bf16.h>
+#include <cstdio>
+#include <cstdlib>
 
 namespace mxkv {
 
@@ -61,13 +63,20 @@ __device__ __forceinline__ uint32_t ld_flag_acquire(const uint32_t* p) {
 // spins on the slot rank i writes in ours.  Separate start/end slots so a fast
 // rank's next start cannot overwrite a slow rank's pending end.
 // ---------------------------------------------------------------------------
+// A peer that never shows up (its launch failed, its process died) must not hang this GPU for
+// ever: after `timeout` clock cycles the kernel traps and the host sees a CUDA error.
+__device__ __forceinline__ void spin_check(long long t0, long long timeout) {
+  if (timeout > 0 && clock64() - t0 > timeout) __trap();
+}
+
 __device__ __forceinline__ void barrier_start(const SyncArgs& s) {
   const uint32_t flag = s.self[kSigFlagOff + blockIdx.x] + 1;
   if (threadIdx.x < s.world) {
     uint32_t* peer = s.peers[threadIdx.x] + kSigStartOff + blockIdx.x * kMaxRanks + s.rank;
     const uint32_t* mine = s.self + kSigStartOff + blockIdx.x * kMaxRanks + threadIdx.x;
     st_flag_volatile(peer, flag);
-    while (ld_flag_volatile(mine) != flag) {}
+    const long long t0 = clock64();
+    while (ld_flag_volatile(mine) != flag) spin_check(t0, s.timeout);
   }
   __syncthreads();
   if (threadIdx.x == 0) s.self[kSigFlagOff + blockIdx.x] = flag;
@@ -81,12 +90,13 @@ __device__ __forceinline__ void barrier_end(const SyncArgs& s, bool release) {
   if (threadIdx.x < s.world) {
     uint32_t* peer = s.peers[threadIdx.x] + kSigEndOff + blockIdx.x * kMaxRanks + s.rank;
     const uint32_t* mine = s.self + kSigEndOff + blockIdx.x * kMaxRanks + threadIdx.x;
+    const long long t0 = clock64();
     if (release) {
       st_flag_release(peer, flag);
-      while (ld_flag_acquire(mine) != flag) {}
+      while (ld_flag_acquire(mine) != flag) spin_check(t0, s.timeout);
     } else {
       st_flag_volatile(peer, flag);
-      while (ld_flag_volatile(mine) != flag) {}
+      while (ld_flag_volatile(mine) != flag) spin_check(t0, s.timeout);
     }
   }
   __syncthreads();
@@ -407,6 +417,197 @@ kv_dense_kernel(DenseLaunch L) {
 }
 
 // ---------------------------------------------------------------------------
+// Shared-memory staged variant (float32): a bulk-copy engine pipeline instead of per-thread loads.
+// One elected thread issues cp.async.bulk (the 1-D TMA path, SASS UBLKCP) for every input stream of
+// a tile -- the n gradient replicas (local HBM or NVLink peers), the weight and the optimizer state
+// -- into a ring of `stages` shared-memory buffers, arming an mbarrier with the byte count; all
+// threads wait on the barrier, compute the tile out of shared memory and store results straight
+// from registers.  Bytes in flight per SM are bounded by shared memory (up to ~200 KB) instead of by
+// registers (48 KB for the per-thread variant), which is what a latency-bound stream needs.
+// ---------------------------------------------------------------------------
+constexpr int kBulkThreads = 256;
+constexpr int kBulkMaxStages = 8;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t"
+      "}" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+template <int OPT, bool MP>
+__global__ void __launch_bounds__(kBulkThreads, 2)
+kv_dense_bulk_kernel(DenseLaunch L) {
+  extern __shared__ __align__(128) unsigned char bulk_smem[];
+  __shared__ TensorWork tw;
+  __shared__ __align__(8) uint64_t full[kBulkMaxStages];
+  const bool sync = L.sync.mode != SYNC_NONE;
+  const int stages = L.bulk_stages;
+  const int tile = L.chunk_elems;
+  const uint32_t arr_bytes = static_cast<uint32_t>(tile) * 4u;
+  const uint32_t stage_bytes = arr_bytes * static_cast<uint32_t>(L.bulk_arrays);
+  constexpr bool HAS_W = OPT != OPT_NONE;
+  constexpr bool HAS_S0 = OPT == OPT_SGD_MOM || OPT == OPT_ADAM || OPT == OPT_ADAMW;
+  constexpr bool HAS_S1 = OPT == OPT_ADAM || OPT == OPT_ADAMW;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) mbar_init(&full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (sync) barrier_start(L.sync);     // no peer byte may be requested before the rendezvous
+
+  // tiles of this block: c = blockIdx.x + i * gridDim.x
+  const int64_t first = blockIdx.x;
+  const int64_t ntiles = first < L.total_chunks ? (L.total_chunks - first + gridDim.x - 1) / gridDim.x : 0;
+
+  auto issue = [&](int64_t i) {       // thread 0 only: request every input stream of tile i
+    const int64_t c = first + i * gridDim.x;
+    int lo = 0, hi = L.nworks - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (L.chunk_prefix[mid] <= c) lo = mid; else hi = mid - 1;
+    }
+    const TensorWork* w = L.works + lo;
+    const int64_t cb = w->begin + (c - L.chunk_prefix[lo]) * tile;
+    const int64_t ce = (cb + tile < w->end) ? cb + tile : w->end;
+    const uint32_t bytes = static_cast<uint32_t>(ce - cb) * 4u;
+    const int n = w->n_src;
+    const int narr = n + (HAS_W ? 1 : 0) + (HAS_S0 ? 1 : 0) + (HAS_S1 ? 1 : 0);
+    const int s = static_cast<int>(i % stages);
+    unsigned char* base = bulk_smem + static_cast<size_t>(s) * stage_bytes;
+    mbar_expect_tx(&full[s], bytes * static_cast<uint32_t>(narr));
+    int a = 0;
+    for (int k = 0; k < n; ++k, ++a)
+      bulk_g2s(base + static_cast<size_t>(a) * arr_bytes, static_cast<const float*>(w->src[k]) + cb, bytes, &full[s]);
+    if (HAS_W) {
+      const float* wp = MP ? w->w32 : static_cast<const float*>(w->w);
+      bulk_g2s(base + static_cast<size_t>(a) * arr_bytes, wp + cb, bytes, &full[s]); ++a;
+    }
+    if (HAS_S0) { bulk_g2s(base + static_cast<size_t>(a) * arr_bytes, w->s0 + cb, bytes, &full[s]); ++a; }
+    if (HAS_S1) { bulk_g2s(base + static_cast<size_t>(a) * arr_bytes, w->s1 + cb, bytes, &full[s]); ++a; }
+  };
+
+  if (threadIdx.x == 0) {
+    for (int64_t i = 0; i < ntiles && i < stages; ++i) issue(i);
+  }
+
+  int cur = -1;
+  for (int64_t i = 0; i < ntiles; ++i) {
+    const int64_t c = first + i * gridDim.x;
+    int lo = 0, hi = L.nworks - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (L.chunk_prefix[mid] <= c) lo = mid; else hi = mid - 1;
+    }
+    if (lo != cur) {
+      __syncthreads();
+      const uint4* src = reinterpret_cast<const uint4*>(L.works + lo);
+      uint4* dst = reinterpret_cast<uint4*>(&tw);
+      for (int t = threadIdx.x; t < static_cast<int>(sizeof(TensorWork) / 16); t += blockDim.x) dst[t] = src[t];
+      __syncthreads();
+      cur = lo;
+    }
+    Hyper h;
+    h.lr = tw.lr; h.wd = tw.wd; h.eta = tw.eta;
+    h.rescale = L.rescale; h.clip = L.clip; h.momentum = L.momentum;
+    h.beta1 = L.beta1; h.beta2 = L.beta2; h.eps = L.eps;
+    const int64_t cb = tw.begin + (c - L.chunk_prefix[lo]) * tile;
+    const int64_t ce = (cb + tile < tw.end) ? cb + tile : tw.end;
+    const int nvec = static_cast<int>((ce - cb) >> 2);
+    const int n = tw.n_src;
+    const int s = static_cast<int>(i % stages);
+    const uint32_t parity = static_cast<uint32_t>((i / stages) & 1);
+    const unsigned char* base = bulk_smem + static_cast<size_t>(s) * stage_bytes;
+    mbar_wait(&full[s], parity);
+
+    for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
+      float acc[4], grp[4];
+      for (int k = 0; k < n; ++k) {
+        const float4 x4 = reinterpret_cast<const float4*>(base + static_cast<size_t>(k) * arr_bytes)[v];
+        const float x[4] = {x4.x, x4.y, x4.z, x4.w};
+        if (k == 0) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[j] = x[j];
+        } else if (L.order == ORDER_DEVICE) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[j] = __fadd_rn(acc[j], x[j]);
+        } else {
+          const int pos = (k - 1) & 3;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) grp[j] = (pos == 0) ? x[j] : __fadd_rn(grp[j], x[j]);
+          if (pos == 3 || k == n - 1) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[j] = __fadd_rn(acc[j], grp[j]);
+          }
+        }
+      }
+      float wnew[4];
+      const int64_t e = cb + static_cast<int64_t>(v) * 4;
+      if (OPT == OPT_NONE) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) wnew[j] = acc[j];
+      } else {
+        int a = n;
+        const float4 w4 = reinterpret_cast<const float4*>(base + static_cast<size_t>(a) * arr_bytes)[v]; ++a;
+        float w[4] = {w4.x, w4.y, w4.z, w4.w};
+        float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+        if (HAS_S0) {
+          const float4 t4 = reinterpret_cast<const float4*>(base + static_cast<size_t>(a) * arr_bytes)[v]; ++a;
+          s0[0] = t4.x; s0[1] = t4.y; s0[2] = t4.z; s0[3] = t4.w;
+        }
+        if (HAS_S1) {
+          const float4 t4 = reinterpret_cast<const float4*>(base + static_cast<size_t>(a) * arr_bytes)[v]; ++a;
+          s1[0] = t4.x; s1[1] = t4.y; s1[2] = t4.z; s1[3] = t4.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) wnew[j] = update_one<OPT>(acc[j], w[j], s0[j], s1[j], h);
+        if (HAS_S0) stf<4>(tw.s0, e, s0);
+        if (HAS_S1) stf<4>(tw.s1, e, s1);
+        if (MP) stf<4>(tw.w32, e, wnew);
+      }
+      const int m = tw.n_out;
+      for (int j = 0; j < m; ++j) stf<4>(static_cast<float*>(tw.out[j]), e, wnew);
+    }
+    __syncthreads();                  // every thread is done reading stage s
+    if (threadIdx.x == 0 && i + stages < ntiles) issue(i + stages);
+  }
+
+  if (sync) barrier_end(L.sync, L.sync.mode == SYNC_WRITE_PEERS);
+}
+
+typedef void (*BulkKernelFn)(DenseLaunch);
+static BulkKernelFn pick_bulk(int opt, int mp) {
+  switch (opt) {
+    case OPT_NONE: return kv_dense_bulk_kernel<OPT_NONE, false>;
+    case OPT_SGD: return mp ? kv_dense_bulk_kernel<OPT_SGD, true> : kv_dense_bulk_kernel<OPT_SGD, false>;
+    case OPT_SGD_MOM: return mp ? kv_dense_bulk_kernel<OPT_SGD_MOM, true> : kv_dense_bulk_kernel<OPT_SGD_MOM, false>;
+    case OPT_ADAM: return mp ? kv_dense_bulk_kernel<OPT_ADAM, true> : kv_dense_bulk_kernel<OPT_ADAM, false>;
+    case OPT_ADAMW: return mp ? kv_dense_bulk_kernel<OPT_ADAMW, true> : kv_dense_bulk_kernel<OPT_ADAMW, false>;
+    case OPT_TEST: return mp ? kv_dense_bulk_kernel<OPT_TEST, true> : kv_dense_bulk_kernel<OPT_TEST, false>;
+    default: return nullptr;
+  }
+}
+
+// ---------------------------------------------------------------------------
 // plain typed sum for the dtypes the reference's ElementwiseSum also accepts
 // (MSHADOW_TYPE_SWITCH: f64, u8, i32, i8, i64); native arithmetic, device order.
 // ---------------------------------------------------------------------------
@@ -458,7 +659,11 @@ typedef void (*DenseKernelFn)(DenseLaunch);
 
 template <typename T, int OPT, bool MP>
 static DenseKernelFn pick_n(bool small_n) {
-  return small_n ? kv_dense_kernel<T, OPT, MP, true> : kv_dense_kernel<T, OPT, MP, false>;
+  // the two-packet variant is only instantiated where it stays inside 64 registers
+  if constexpr (OPT == OPT_NONE || OPT == OPT_SGD || OPT == OPT_TEST) {
+    if (small_n) return kv_dense_kernel<T, OPT, MP, true>;
+  }
+  return kv_dense_kernel<T, OPT, MP, false>;
 }
 
 template <typename T>
@@ -524,7 +729,64 @@ int DenseMaxGrid(int device, int threads) {
   return g > kMaxBlocks ? kMaxBlocks : g;
 }
 
+static int g_smem_budget = 0;   // MXKV_B200_BULK_SMEM_KB per block (default 100: two blocks per SM)
+
+int BulkPlan(int device, int opt, int multi_precision, int arrays, int* tile_elems, int* stages) {
+  BulkKernelFn fn = pick_bulk(opt, multi_precision);
+  if (fn == nullptr || arrays < 1) return 0;
+  if (g_smem_budget == 0) {
+    const char* e = getenv("MXKV_B200_BULK_SMEM_KB");
+    g_smem_budget = (e && *e) ? atoi(e) * 1024 : 100 * 1024;
+    if (g_smem_budget < 16 * 1024) g_smem_budget = 16 * 1024;
+    if (g_smem_budget > 200 * 1024) g_smem_budget = 200 * 1024;
+  }
+  int tile = 2048;
+  while (tile > 256 && arrays * tile * 4 * 2 > g_smem_budget) tile >>= 1;
+  int st = g_smem_budget / (arrays * tile * 4);
+  if (st < 2) return 0;
+  if (st > kBulkMaxStages) st = kBulkMaxStages;
+  const int smem = st * arrays * tile * 4;
+  // function attributes are per device: opt in to large dynamic shared memory on every GPU
+  static bool attr_done[64][16] = {{false}};
+  const int slot = (opt & 7) * 2 + (multi_precision ? 1 : 0);
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess) { cudaGetLastError(); return 0; }
+  int prev = -1;
+  cudaGetDevice(&prev);
+  bool ok = true;
+  for (int dv = 0; dv < ndev && dv < 64; ++dv) {
+    if (attr_done[dv][slot]) continue;
+    cudaSetDevice(dv);
+    if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) {
+      cudaGetLastError();
+      ok = false;
+      break;
+    }
+    attr_done[dv][slot] = true;
+  }
+  cudaSetDevice(device);
+  int occ = 0;
+  if (ok && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kBulkThreads, smem) != cudaSuccess || occ < 1)) {
+    cudaGetLastError();
+    ok = false;
+  }
+  if (prev >= 0) cudaSetDevice(prev);
+  if (!ok) return 0;
+  *tile_elems = tile;
+  *stages = st;
+  int g = occ * sm_count(device);
+  return g > kMaxBlocks ? kMaxBlocks : g;
+}
+
 int LaunchDense(const DenseLaunch& L, cudaStream_t stream) {
+  if (L.bulk) {
+    BulkKernelFn bf = pick_bulk(L.opt, L.multi_precision);
+    if (bf == nullptr || L.dtype != kFloat32) return static_cast<int>(cudaErrorInvalidValue);
+    int grid = L.grid < 1 ? 1 : (L.grid > kMaxBlocks ? kMaxBlocks : L.grid);
+    const size_t smem = static_cast<size_t>(L.bulk_stages) * L.bulk_arrays * L.chunk_elems * 4;
+    bf<<<grid, kBulkThreads, smem, stream>>>(L);
+    return static_cast<int>(cudaGetLastError());
+  }
   DenseKernelFn fn = pick_kernel(L);
   if (fn == nullptr) return static_cast<int>(cudaErrorInvalidValue);
   int grid = L.grid;

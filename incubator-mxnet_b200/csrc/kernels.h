@@ -67,6 +67,7 @@ struct SyncArgs {
   int world;
   int rank;
   int mode;                      // SyncMode
+  long long timeout;             // spin limit in SM clock cycles (0: wait for ever)
 };
 
 // signal pad layout in uint32 words
@@ -91,11 +92,17 @@ struct DenseLaunch {
   int chunk_elems;               // elements per scheduling chunk (multiple of 128)
   int threads;                   // block size: 128, 256 or 512
   int small_n;                   // every entry has n_src <= 2: use the two-packets-in-flight variant
+  int bulk;                      // 1: shared-memory staged variant (cp.async.bulk + mbarrier pipeline)
+  int bulk_stages;               // pipeline depth
+  int bulk_arrays;               // input arrays staged per tile (max over the work list)
 };
 
 // returns cudaError_t as int; never throws
 int LaunchDense(const DenseLaunch& L, cudaStream_t stream);
 int DenseMaxGrid(int device, int threads);   // resident-block capacity of the dense kernel
+// Plan the shared-memory staged variant for a float32 launch with `arrays` staged input streams per
+// tile: picks tile elements / stages and returns the resident grid capacity (0: not applicable).
+int BulkPlan(int device, int opt, int multi_precision, int arrays, int* tile_elems, int* stages);
 
 int LaunchFill(void* ptr, int value_byte, size_t bytes, cudaStream_t s);
 // dst[i] = float(src[i]) for float32/float16/bfloat16 sources (fp32 master-weight creation)

@@ -7,11 +7,6 @@
 
 namespace mxkv {
 
-static int64_t NumChunks(int64_t elems) {
-  const int64_t c = Runtime::Get()->chunk_elems;
-  return (elems + c - 1) / c;
-}
-
 static std::string Lower(std::string s) {
   std::transform(s.begin(), s.end(), s.begin(), ::tolower);
   return s;
@@ -386,12 +381,12 @@ void KVStore::BroadcastFromRank0(KeyState& ks, Replica& r) {
   tw.out[0] = r.local.data();
   tw.n_out = 1;
   tw.begin = 0; tw.end = r.local.size();
-  tw.pad_ = 1;
+  tw.pad_ = 1 | ((r.local.dtype() == kFloat32 && r.local.size() % 4 == 0) ? 2 : 0);
   std::vector<int> part_dev(pg->world(), pg->dev());
   std::vector<std::vector<TensorWork>> per_part(pg->world());
   per_part[pg->rank()].push_back(tw);
   LaunchClassKey ck{SYNC_READ_PEERS, r.local.dtype(), 0};
-  LaunchWorks(ck, per_part, NumChunks(r.local.size()), OPT_NONE, part_dev);
+  LaunchWorks(ck, per_part, {r.local.size()}, OPT_NONE, part_dev);
 }
 
 // ---------------------------------------------------------------------------
@@ -665,11 +660,11 @@ bool KVStore::HostPipelined(std::vector<Group>& groups, bool write_outs) {
       tw.s1 = r->s1.is_none() ? nullptr : static_cast<float*>(r->s1.data());
       tw.begin = b; tw.end = e;
       tw.lr = lr; tw.wd = wd; tw.eta = opt_.eta;
-      tw.pad_ = 1;
+      tw.pad_ = 1 | ((esize == 4 && ks.size % 4 == 0) ? 2 : 0);
       std::vector<std::vector<TensorWork>> per_part(1);
       per_part[0].push_back(tw);
       LaunchClassKey ck{SYNC_NONE, ks.dtype, mp ? 1 : 0};
-      LaunchWorks(ck, per_part, NumChunks(e - b), opt_kind, part_dev);
+      LaunchWorks(ck, per_part, {e - b}, opt_kind, part_dev);
       CUDA_CALL(cudaEventRecord(d.ev_kern[slot], d.stream));
       // stage 3: D2H of the freshly written range of the replica
       if (write_outs && !g.outs.empty()) {
@@ -700,7 +695,7 @@ void KVStore::ReduceUpdate(std::vector<Group>& groups, bool write_outs) {
   // participant slot -> device; SP: discovered from the first key, MP: this rank only is local
   struct LaunchClass {
     std::vector<std::vector<TensorWork>> per_part;   // [participant] -> work list
-    int64_t max_chunks = 0;                          // chunk count of the busiest rank (same on every rank)
+    std::vector<int64_t> busiest;                    // per key: elements the busiest rank handles
   };
   std::map<LaunchClassKey, LaunchClass> classes;
   std::vector<int> part_dev;      // device of participant p (SP) / own device at index rank (MP)
@@ -977,7 +972,7 @@ void KVStore::ReduceUpdate(std::vector<Group>& groups, bool write_outs) {
     auto& cls = lc.per_part;
     if (cls.empty()) cls.resize(n_part);
     const int64_t shard = two_shot ? ShardLen(ks.size, n_part) : ks.size;
-    lc.max_chunks += NumChunks(std::min<int64_t>(ks.size, shard));
+    lc.busiest.push_back(std::min<int64_t>(ks.size, shard));
     for (int p = my_first; p <= my_last; ++p) {
       TensorWork tw;
       std::memset(&tw, 0, sizeof(tw));
@@ -1015,14 +1010,14 @@ void KVStore::ReduceUpdate(std::vector<Group>& groups, bool write_outs) {
         tw.begin = 0; tw.end = ks.size;
       }
       tw.lr = lr; tw.wd = wd; tw.eta = opt_.eta;
-      tw.pad_ = vec_ok ? 1 : 0;
+      tw.pad_ = (vec_ok ? 1 : 0) | ((vec_ok && esize == 4 && ks.size % 4 == 0) ? 2 : 0);
       cls[p].push_back(tw);
     }
   }
 
   // ---- launches: one per class per local participant --------------------------
   const int opt_kind = fused ? opt_.kind : OPT_NONE;
-  for (auto& kv : classes) LaunchWorks(kv.first, kv.second.per_part, kv.second.max_chunks, opt_kind, part_dev);
+  for (auto& kv : classes) LaunchWorks(kv.first, kv.second.per_part, kv.second.busiest, opt_kind, part_dev);
 
   // ---- epilogue -------------------------------------------------------------------
   for (size_t i = 0; i < temps.size(); ++i) {
@@ -1045,14 +1040,38 @@ void KVStore::ReduceUpdate(std::vector<Group>& groups, bool write_outs) {
 // precision mode / synchronisation mode.  The grid is derived from the busiest rank's chunk
 // count, which every rank computes identically (paired blocks rendezvous across GPUs).
 void KVStore::LaunchWorks(const LaunchClassKey& ck, std::vector<std::vector<TensorWork>>& per_part,
-                          int64_t max_chunks_in, int opt_kind, const std::vector<int>& part_dev) {
+                          const std::vector<int64_t>& busiest, int opt_kind, const std::vector<int>& part_dev) {
   Runtime* rt = Runtime::Get();
   ProcessGroup* pg = rt->pg();
   const bool mp_mode = pg != nullptr;
   const int n_part = static_cast<int>(part_dev.size());
-  const int64_t max_chunks = std::max<int64_t>(1, max_chunks_in);
   const int my_first = mp_mode ? pg->rank() : 0;
   const int my_last = mp_mode ? pg->rank() : n_part - 1;
+
+  // ---- kernel variant: identical decision on every rank (it fixes the grid) --------------------
+  // shared-memory staged (bulk-copy) variant: float32, every entry 16-byte aligned with a key size
+  // that is a multiple of 4 elements (rank-independent facts only)
+  int64_t chunk = rt->chunk_elems;
+  int bulk = 0, bulk_stages = 0, bulk_arrays = 0, bulk_cap = 0;
+  if (rt->bulk_mode != 0 && ck.dtype == kFloat32) {
+    bool ok = true;
+    int max_src = 1;
+    for (int p = my_first; p <= my_last; ++p)
+      for (auto& t : per_part[p]) { ok = ok && (t.pad_ & 2); max_src = std::max(max_src, t.n_src); }
+    if (ok && (rt->bulk_mode == 1 || max_src >= rt->bulk_mode)) {
+      const int extra = (opt_kind != OPT_NONE ? 1 : 0) +
+                        ((opt_kind == OPT_SGD_MOM || opt_kind == OPT_ADAM || opt_kind == OPT_ADAMW) ? 1 : 0) +
+                        ((opt_kind == OPT_ADAM || opt_kind == OPT_ADAMW) ? 1 : 0);
+      // n_src is the same for every entry of a collective class; take the max for safety
+      int tile = 0, st = 0;
+      const int cap = BulkPlan(part_dev[my_first], opt_kind, ck.mp, max_src + extra, &tile, &st);
+      if (cap > 0) { bulk = 1; bulk_stages = st; bulk_arrays = max_src + extra; bulk_cap = cap; chunk = tile; }
+    }
+  }
+  int64_t max_chunks = 0;
+  for (int64_t len : busiest) max_chunks += (len + chunk - 1) / chunk;
+  max_chunks = std::max<int64_t>(1, max_chunks);
+
   for (int p = my_first; p <= my_last; ++p) {
     auto& w = per_part[p];
     if (w.empty()) continue;
@@ -1060,7 +1079,7 @@ void KVStore::LaunchWorks(const LaunchClassKey& ck, std::vector<std::vector<Tens
     int64_t acc = 0;
     for (size_t i = 0; i < w.size(); ++i) {
       prefix[i] = acc;
-      acc += NumChunks(w[i].end - w[i].begin);
+      acc += (w[i].end - w[i].begin + chunk - 1) / chunk;
     }
     prefix[w.size()] = acc;
     const int dev = part_dev[p];
@@ -1091,11 +1110,14 @@ void KVStore::LaunchWorks(const LaunchClassKey& ck, std::vector<std::vector<Tens
     L.sync.world = n_part;
     L.sync.rank = p;
     L.sync.self = d.signal_pad;
+    L.sync.timeout = rt->spin_timeout_cycles;
     for (int q = 0; q < n_part; ++q)
       L.sync.peers[q] = mp_mode ? pg->signal_pad(q) : rt->Dev(part_dev[q]).signal_pad;
-    L.grid = static_cast<int>(std::min<int64_t>(d.max_grid, max_chunks));
-    L.chunk_elems = static_cast<int>(rt->chunk_elems);
+    L.grid = static_cast<int>(std::min<int64_t>(bulk ? std::min(bulk_cap, rt->max_blocks > 0 ? rt->max_blocks : bulk_cap)
+                                                     : d.max_grid, max_chunks));
+    L.chunk_elems = static_cast<int>(chunk);
     L.threads = rt->threads;
+    L.bulk = bulk; L.bulk_stages = bulk_stages; L.bulk_arrays = bulk_arrays;
     int small_n = 1;
     for (auto& t : w) if (t.n_src > 2) small_n = 0;
     L.small_n = small_n;
@@ -1137,11 +1159,11 @@ void KVStore::GatherLocal(KeyState& ks) {
     }
     tw.begin = std::min<int64_t>(ks.size, shard * p);
     tw.end = std::min<int64_t>(ks.size, shard * (p + 1));
-    tw.pad_ = 1;
+    tw.pad_ = 1 | ((ks.dtype == kFloat32 && ks.size % 4 == 0) ? 2 : 0);
     per_part[p].push_back(tw);
   }
   LaunchClassKey ck{SYNC_WRITE_PEERS, ks.dtype, 0};
-  LaunchWorks(ck, per_part, NumChunks(std::min<int64_t>(ks.size, shard)), OPT_NONE, part_dev);
+  LaunchWorks(ck, per_part, {std::min<int64_t>(ks.size, shard)}, OPT_NONE, part_dev);
   ks.local_world = 0;
   for (auto& r : ks.reps) {
     bool is_part = false;

@@ -147,8 +147,9 @@ class KVStore {
   };
   // the fused reduce(+update)(+broadcast) over a list of dense key groups
   void ReduceUpdate(std::vector<Group>& groups, bool write_outs);
-  void LaunchWorks(const LaunchClassKey& ck, std::vector<std::vector<TensorWork>>& per_part, int64_t max_chunks,
-                   int opt_kind, const std::vector<int>& part_dev);
+  // busiest[i]: number of elements the busiest rank processes for entry i (fixes the common grid)
+  void LaunchWorks(const LaunchClassKey& ck, std::vector<std::vector<TensorWork>>& per_part,
+                   const std::vector<int64_t>& busiest, int opt_kind, const std::vector<int>& part_dev);
   void GatherLocal(KeyState& ks);
   bool HostPipelined(std::vector<Group>& groups, bool write_outs);
   void RunCallbackUpdater(KeyState& ks, Replica& root);

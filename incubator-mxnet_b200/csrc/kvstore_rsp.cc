@@ -174,6 +174,7 @@ void KVStore::PushRowSparse(KeyState& ks, const std::vector<NDArray>& vals) {
     sync.self = rt->Dev(pg->dev()).signal_pad;
     for (int q = 0; q < world; ++q) sync.peers[q] = pg->signal_pad(q);
     sync.world = world; sync.rank = pg->rank(); sync.mode = SYNC_WRITE_PEERS;
+    sync.timeout = rt->spin_timeout_cycles;
     CheckLaunch(LaunchBarrier(sync, s), "barrier");
     if (v.nnz() > 0) {
       CopyBytes(v.idx_ptr(), v.ctx(), r.stage_idx.data(), r.stage_idx.ctx(), v.nnz() * 8);

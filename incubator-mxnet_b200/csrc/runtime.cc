@@ -168,6 +168,9 @@ Runtime::Runtime() {
   chunk_elems = EnvInt("MXKV_B200_CHUNK", kChunkElems);
   if (chunk_elems < 128) chunk_elems = 128;
   chunk_elems = (chunk_elems + 127) / 128 * 128;
+  bulk_mode = static_cast<int>(EnvInt("MXKV_B200_BULK", 1));
+  spin_timeout_cycles = EnvInt("MXKV_B200_SPIN_TIMEOUT_S", 120) * 1900000000LL;   // ~1.9 GHz SM clock
+  max_blocks = static_cast<int>(EnvInt("MXKV_B200_MAX_BLOCKS", 0));
   threads = static_cast<int>(EnvInt("MXKV_B200_THREADS", 512));
   if (threads != 128 && threads != 256 && threads != 512) threads = 512;
 }
@@ -319,7 +322,8 @@ void Runtime::WaitAll() {
   }
 }
 
-void Runtime::SetTuning(int64_t chunk, int nthreads, int max_blocks) {
+void Runtime::SetTuning(int64_t chunk, int nthreads, int max_blocks, int bulk) {
+  if (bulk >= 0) bulk_mode = bulk;
   std::lock_guard<std::recursive_mutex> lk(mu_);
   WaitAll();
   if (chunk > 0) chunk_elems = std::max<int64_t>(128, (chunk + 127) / 128 * 128);
@@ -330,6 +334,7 @@ void Runtime::SetTuning(int64_t chunk, int nthreads, int max_blocks) {
     kv.second->max_grid = g;
   }
   max_blocks_override_ = max_blocks;
+  this->max_blocks = max_blocks;
 }
 
 void Runtime::DrainForFree() noexcept {

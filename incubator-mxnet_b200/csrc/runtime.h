@@ -111,7 +111,7 @@ class Runtime {
   void WaitAll();
   void DrainForFree() noexcept;            // like WaitAll, never throws (used by destructors)
   void WaitDevice(int dev);
-  void SetTuning(int64_t chunk, int nthreads, int max_blocks);
+  void SetTuning(int64_t chunk, int nthreads, int max_blocks, int bulk = -1);
 
   // one-process-per-GPU mode
   void InitProcessGroup(int rank, int world, int dev, AllGatherFn fn, void* ctx);
@@ -124,6 +124,9 @@ class Runtime {
   int64_t twoshot_bytes = 256 * 1024;
   int64_t chunk_elems = kChunkElems;         // MXKV_B200_CHUNK
   int threads = 512;                         // MXKV_B200_THREADS
+  long long spin_timeout_cycles = 0;         // MXKV_B200_SPIN_TIMEOUT_S (default 120 s) in SM cycles
+  int max_blocks = 0;                        // MXKV_B200_MAX_BLOCKS (0: resident capacity)
+  int bulk_mode = 1;                         // MXKV_B200_BULK: 0 off, 1 always, k>=2: when n_src >= k
  private:
   Runtime();
   std::recursive_mutex mu_;

@@ -4,6 +4,8 @@ import sys
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+# a missing peer must fail a test quickly instead of hanging the GPU box
+os.environ.setdefault("MXKV_B200_SPIN_TIMEOUT_S", "20")
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 

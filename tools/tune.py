@@ -39,15 +39,10 @@ def main():
         kv.set_optimizer(mx.optimizer.SGD(learning_rate=0.01, momentum=0.9, wd=1e-4))
     elif opt == "adam":
         kv.set_optimizer(mx.optimizer.Adam())
-    configs = []
-    for chunk in (1024, 2048, 4096, 8192, 32768):
-        for threads in (256, 512):
-            configs.append((chunk, threads, 0))
-    for mb in (148, 222):
-        configs.append((8192, 512, mb))
+    configs = [(8192, 512, 0, 0), (8192, 512, 0, 1)]
     steps = 40
-    for chunk, threads, mb in configs:
-        check_call(_LIB.MXKVB200SetTuning(ctypes.c_int64(chunk), threads, mb))
+    for chunk, threads, mb, bulk in configs:
+        check_call(_LIB.MXKVB200SetTuning(ctypes.c_int64(chunk), threads, mb, bulk))
         for _ in range(5):
             kv.pushpull(keys, grads, out=weights)
         torch.cuda.synchronize()
@@ -67,10 +62,10 @@ def main():
         if rank == 0:
             if world == 1:
                 bw = (S // 4) * 24 / (ms * 1e-3) / 1e9
-                print("chunk %6d threads %3d max_blocks %4d : %.4f ms  HBM %.0f GB/s" % (chunk, threads, mb, ms, bw), flush=True)
+                print("chunk %6d threads %3d max_blocks %4d bulk %d : %.4f ms  HBM %.0f GB/s" % (chunk, threads, mb, bulk, ms, bw), flush=True)
             else:
                 bw = 2.0 * S * (world - 1) / world / (ms * 1e-3) / 1e9
-                print("chunk %6d threads %3d max_blocks %4d : %.4f ms  busbw %.0f GB/s" % (chunk, threads, mb, ms, bw), flush=True)
+                print("chunk %6d threads %3d max_blocks %4d bulk %d : %.4f ms  busbw %.0f GB/s" % (chunk, threads, mb, bulk, ms, bw), flush=True)
     mx.nd.waitall()
     if world > 1:
         torch.distributed.barrier()

@@ -167,8 +167,8 @@ MXKV_DLL int MXKVB200GetLaunchCount(int64_t* out);
 MXKV_DLL int MXKVB200SetTwoShotBytes(int64_t bytes);
 /* Kernel scheduling knobs (also MXKV_B200_CHUNK / _THREADS / _MAX_BLOCKS / _BULK): elements per
  * scheduling chunk, block size (128/256/512), cap on the grid (0 = resident capacity), and the
- * shared-memory staged (cp.async.bulk) variant: 0 off, 1 on, k >= 2 on when a key has >= k sources,
- * -1 keep.  Every rank of a process group must use the same values. */
+ * shared-memory staged (cp.async.bulk) variant: 0 off, 1 auto (keys with <= 2 sources), 2 whenever
+ * eligible, -1 keep.  Every rank of a process group must use the same values. */
 MXKV_DLL int MXKVB200SetTuning(int64_t chunk_elems, int threads, int max_blocks, int bulk);
 
 /* [begin, end) of the elements rank `rank` of `world` reduces and updates for a key of `size`

@@ -457,8 +457,10 @@ template <int OPT, bool MP>
 __global__ void __launch_bounds__(kBulkThreads, 2)
 kv_dense_bulk_kernel(DenseLaunch L) {
   extern __shared__ __align__(128) unsigned char bulk_smem[];
-  __shared__ TensorWork tw;
+  __shared__ TensorWork tw;        // descriptor of the tile being computed (all threads)
+  __shared__ TensorWork twp;       // descriptor of the tile being requested (thread 0 only)
   __shared__ __align__(8) uint64_t full[kBulkMaxStages];
+  int p_cur = -1;
   const bool sync = L.sync.mode != SYNC_NONE;
   const int stages = L.bulk_stages;
   const int tile = L.chunk_elems;
@@ -486,7 +488,13 @@ kv_dense_bulk_kernel(DenseLaunch L) {
       const int mid = (lo + hi + 1) >> 1;
       if (L.chunk_prefix[mid] <= c) lo = mid; else hi = mid - 1;
     }
-    const TensorWork* w = L.works + lo;
+    if (lo != p_cur) {               // descriptor changes once per key: keep a private copy
+      const uint4* src = reinterpret_cast<const uint4*>(L.works + lo);
+      uint4* dst = reinterpret_cast<uint4*>(&twp);
+      for (int t = 0; t < static_cast<int>(sizeof(TensorWork) / 16); ++t) dst[t] = src[t];
+      p_cur = lo;
+    }
+    const TensorWork* w = &twp;
     const int64_t cb = w->begin + (c - L.chunk_prefix[lo]) * tile;
     const int64_t ce = (cb + tile < w->end) ? cb + tile : w->end;
     const uint32_t bytes = static_cast<uint32_t>(ce - cb) * 4u;
@@ -740,9 +748,25 @@ int BulkPlan(int device, int opt, int multi_precision, int arrays, int* tile_ele
     if (g_smem_budget < 16 * 1024) g_smem_budget = 16 * 1024;
     if (g_smem_budget > 200 * 1024) g_smem_budget = 200 * 1024;
   }
+  // measured on B200 (profiles/r01_tune_bulk.txt): 2048-element tiles, two stages; deeper rings or
+  // smaller tiles are slower.  Wide work lists (many sources) fall back to 1024-element tiles to keep
+  // two blocks per SM resident.
   int tile = 2048;
-  while (tile > 256 && arrays * tile * 4 * 2 > g_smem_budget) tile >>= 1;
-  int st = g_smem_budget / (arrays * tile * 4);
+  int st = 2;
+  if (st * arrays * tile * 4 > g_smem_budget) tile = 1024;
+  if (st * arrays * tile * 4 > g_smem_budget) return 0;
+  {
+    static int env_tile = -1, env_st = -1;
+    if (env_tile < 0) {
+      const char* e1 = getenv("MXKV_B200_BULK_TILE");
+      const char* e2 = getenv("MXKV_B200_BULK_STAGES");
+      env_tile = (e1 && *e1) ? atoi(e1) : 0;
+      env_st = (e2 && *e2) ? atoi(e2) : 0;
+    }
+    if (env_tile >= 256 && env_tile % 128 == 0) tile = env_tile;
+    if (env_st >= 2) st = env_st;
+    if (st * arrays * tile * 4 > 200 * 1024) return 0;
+  }
   if (st < 2) return 0;
   if (st > kBulkMaxStages) st = kBulkMaxStages;
   const int smem = st * arrays * tile * 4;

@@ -1058,10 +1058,15 @@ void KVStore::LaunchWorks(const LaunchClassKey& ck, std::vector<std::vector<Tens
     int max_src = 1;
     for (int p = my_first; p <= my_last; ++p)
       for (auto& t : per_part[p]) { ok = ok && (t.pad_ & 2); max_src = std::max(max_src, t.n_src); }
-    if (ok && (rt->bulk_mode == 1 || max_src >= rt->bulk_mode)) {
-      const int extra = (opt_kind != OPT_NONE ? 1 : 0) +
-                        ((opt_kind == OPT_SGD_MOM || opt_kind == OPT_ADAM || opt_kind == OPT_ADAMW) ? 1 : 0) +
-                        ((opt_kind == OPT_ADAM || opt_kind == OPT_ADAMW) ? 1 : 0);
+    const int extra = (opt_kind != OPT_NONE ? 1 : 0) +
+                      ((opt_kind == OPT_SGD_MOM || opt_kind == OPT_ADAM || opt_kind == OPT_ADAMW) ? 1 : 0) +
+                      ((opt_kind == OPT_ADAM || opt_kind == OPT_ADAMW) ? 1 : 0);
+    // measured (profiles/r01_tune_bulk.txt): the staged variant wins when a thread of the per-thread
+    // variant would have few loads in flight (<= 2 sources, >= 3 streams: 6255 vs 5413 GB/s at n=1,
+    // busbw 623 vs 575 at n=2); with >= 3 sources the per-thread variant already keeps enough
+    // requests in flight and is faster (6606 vs 5794 GB/s at n=4).  bulk_mode 2 forces it.
+    const bool want = rt->bulk_mode >= 2 || (max_src <= 2 && max_src + extra >= 3);
+    if (ok && want) {
       // n_src is the same for every entry of a collective class; take the max for safety
       int tile = 0, st = 0;
       const int cap = BulkPlan(part_dev[my_first], opt_kind, ck.mp, max_src + extra, &tile, &st);

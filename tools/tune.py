@@ -28,10 +28,14 @@ def main():
     S = 4 * sum(nelem(s) for s in shapes)
     keys = list(range(len(shapes)))
     rng = np.random.default_rng(rank)
+    nval = int(os.environ.get("TUNE_NVAL", 1))      # values per key on this GPU (emulates n sources)
     grads = [mx.nd.empty_symmetric(s) for s in shapes]
+    if nval > 1:
+        grads = [[mx.nd.empty(s, mx.gpu(local)) for _ in range(nval)] for s in shapes]
     weights = [mx.nd.empty_symmetric(s) for s in shapes]
     for g, s in zip(grads, shapes):
-        g[:] = rng.uniform(-1, 1, s).astype(np.float32)
+        for gg in (g if isinstance(g, list) else [g]):
+            gg[:] = rng.uniform(-1, 1, s).astype(np.float32)
     kv = mx.kv.create("device")
     kv.init(keys, [mx.nd.zeros(s, mx.gpu(local)) for s in shapes])
     opt = os.environ.get("TUNE_OPT", "sgd")
@@ -61,7 +65,7 @@ def main():
         ms = t.item()
         if rank == 0:
             if world == 1:
-                bw = (S // 4) * 24 / (ms * 1e-3) / 1e9
+                bw = (S // 4) * (20 + 4 * nval) / (ms * 1e-3) / 1e9
                 print("chunk %6d threads %3d max_blocks %4d bulk %d : %.4f ms  HBM %.0f GB/s" % (chunk, threads, mb, bulk, ms, bw), flush=True)
             else:
                 bw = 2.0 * S * (world - 1) / world / (ms * 1e-3) / 1e9

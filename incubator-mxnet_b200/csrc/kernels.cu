@@ -843,6 +843,84 @@ int LaunchCastToF32(const void* src, int dtype, float* dst, int64_t n, cudaStrea
   return static_cast<int>(cudaGetLastError());
 }
 
+// ---------------------------------------------------------------------------
+// 1-bit / 2-bit gradient compression with error feedback
+// (src/kvstore/gradient_compression-inl.h:44-227).  One thread per 32-bit code word (the reference
+// uses one thread per byte): residual += grad; emit the code; keep the quantisation error in the
+// residual.  Bit layout is the reference's: byte j of the stream holds values 4j..4j+3 (2-bit) or
+// 8j..8j+7 (1-bit), first value in the most significant bits.
+// ---------------------------------------------------------------------------
+template <int BITS>
+__global__ void kv_quantize_kernel(const float* __restrict__ grad, float* __restrict__ residual,
+                                   uint32_t* __restrict__ out, int64_t n, float thr) {
+  constexpr int PER_WORD = 32 / BITS;
+  const int64_t nwords = (n + PER_WORD - 1) / PER_WORD;
+  for (int64_t w = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; w < nwords;
+       w += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    uint32_t word = 0;
+    const int64_t base = w * PER_WORD;
+#pragma unroll
+    for (int j = 0; j < PER_WORD; ++j) {
+      const int64_t i = base + j;
+      if (i >= n) break;
+      float r = __fadd_rn(residual[i], grad[i]);
+      const int byte = j / (8 / BITS);           // byte within the word (little endian in memory)
+      const int slot = j % (8 / BITS);           // value within the byte, MSB first
+      if (BITS == 2) {
+        if (r >= thr) { word |= (0x3u << (6 - 2 * slot)) << (8 * byte); r = __fsub_rn(r, thr); }
+        else if (r <= -thr) { word |= (0x2u << (6 - 2 * slot)) << (8 * byte); r = __fsub_rn(r, -thr); }
+      } else {
+        if (r > thr) { word |= (0x1u << (7 - slot)) << (8 * byte); r = __fsub_rn(r, 1.0f); }
+        else r = __fadd_rn(r, 1.0f);
+      }
+      residual[i] = r;
+    }
+    out[w] = word;
+  }
+}
+
+template <int BITS>
+__global__ void kv_dequantize_kernel(const uint32_t* __restrict__ in, float* __restrict__ out, int64_t n, float thr) {
+  constexpr int PER_WORD = 32 / BITS;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const uint32_t word = in[i / PER_WORD];
+    const int j = static_cast<int>(i % PER_WORD);
+    const int byte = j / (8 / BITS), slot = j % (8 / BITS);
+    const uint32_t b = (word >> (8 * byte)) & 0xffu;
+    float v;
+    if (BITS == 2) {
+      const uint32_t code = (b >> (6 - 2 * slot)) & 0x3u;
+      v = code == 0x3u ? thr : (code == 0x2u ? -thr : 0.0f);
+    } else {
+      v = ((b >> (7 - slot)) & 0x1u) ? 1.0f : -1.0f;
+    }
+    out[i] = v;
+  }
+}
+
+int LaunchQuantize(int bits, const float* grad, float* residual, uint32_t* out, int64_t n, float thr, cudaStream_t s) {
+  if (n == 0) return 0;
+  const int per = 32 / bits;
+  int64_t blocks = ((n + per - 1) / per + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  if (bits == 2) kv_quantize_kernel<2><<<blocks, 256, 0, s>>>(grad, residual, out, n, thr);
+  else if (bits == 1) kv_quantize_kernel<1><<<blocks, 256, 0, s>>>(grad, residual, out, n, thr);
+  else return static_cast<int>(cudaErrorInvalidValue);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int LaunchDequantize(int bits, const uint32_t* in, float* out, int64_t n, float thr, cudaStream_t s) {
+  if (n == 0) return 0;
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (bits == 2) kv_dequantize_kernel<2><<<blocks, 256, 0, s>>>(in, out, n, thr);
+  else if (bits == 1) kv_dequantize_kernel<1><<<blocks, 256, 0, s>>>(in, out, n, thr);
+  else return static_cast<int>(cudaErrorInvalidValue);
+  return static_cast<int>(cudaGetLastError());
+}
+
 __global__ void kv_barrier_kernel(SyncArgs sync) {
   barrier_start(sync);
   barrier_end(sync, true);

@@ -105,6 +105,9 @@ int DenseMaxGrid(int device, int threads);   // resident-block capacity of the d
 int BulkPlan(int device, int opt, int multi_precision, int arrays, int* tile_elems, int* stages);
 
 int LaunchFill(void* ptr, int value_byte, size_t bytes, cudaStream_t s);
+// gradient compression codec (bits = 1 or 2); code stream = ceil(n / (32/bits)) 32-bit words
+int LaunchQuantize(int bits, const float* grad, float* residual, uint32_t* out, int64_t n, float thr, cudaStream_t s);
+int LaunchDequantize(int bits, const uint32_t* in, float* out, int64_t n, float thr, cudaStream_t s);
 // dst[i] = float(src[i]) for float32/float16/bfloat16 sources (fp32 master-weight creation)
 int LaunchCastToF32(const void* src, int dtype, float* dst, int64_t n, cudaStream_t s);
 

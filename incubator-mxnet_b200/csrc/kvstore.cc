@@ -1,5 +1,6 @@
 // kvstore.cc -- see kvstore.h for the reference mapping.
 #include "kvstore.h"
+#include "rsp_kernels.h"
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -164,8 +165,7 @@ void KVStore::SetGradientCompression(const std::vector<std::pair<std::string, st
       MXKV_FATAL() << "Cannot find argument '" << kv.first << "' for gradient compression";
     }
   }
-  MXKV_CHECK(gc_type_ == "none")
-      << "gradient compression ('" << gc_type_ << "') is not implemented on this path yet (SURVEY 8f rank 2)";
+  gc_bits_ = gc_type_ == "2bit" ? 2 : (gc_type_ == "1bit" ? 1 : 0);
 }
 
 // ---------------------------------------------------------------------------
@@ -684,7 +684,180 @@ bool KVStore::HostPipelined(std::vector<Group>& groups, bool write_outs) {
   return true;
 }
 
+// CommDevice::ReduceCompressed (src/kvstore/comm.h:556-605): every pushed value is quantised on its
+// own GPU against a per-source residual (error feedback), the 16x / 32x smaller code stream is what
+// crosses the interconnect, and the consumer dequantises and sums.  Here every participating GPU is
+// a consumer: it reads all n code streams (peer loads), dequantises them into local scratch and
+// runs the ordinary fused reduce(+update) kernel on its own replica -- no root, no broadcast.
+void KVStore::ReduceUpdateCompressed(std::vector<Group>& groups, bool write_outs) {
+  Runtime* rt = Runtime::Get();
+  ProcessGroup* pg = rt->pg();
+  const bool mp_mode = pg != nullptr;
+  const bool callback = updater_ != nullptr;
+  MXKV_CHECK(!callback) << "gradient compression together with a Python updater callback is not supported; "
+                           "use a fused optimizer or no optimizer";
+  const bool fused = opt_.enabled;
+  const int opt_kind = fused ? opt_.kind : OPT_NONE;
+  const int world = mp_mode ? pg->world() : 1;
+  std::set<int> touched;
+  auto touch = [&](int dev) { if (dev >= 0 && touched.insert(dev).second) rt->AcquireUser(dev); };
+  std::vector<PostCopy> post;
+  std::vector<std::pair<void*, int>> temps;
+
+  for (auto& g : groups) {
+    KeyState& ks = GetKey(g.key);
+    MXKV_CHECK(ks.dtype == kFloat32) << "Gradient compression is only supported for float32";   // gradient_compression.cc
+    const int n_src = static_cast<int>(g.vals.size());
+    MXKV_CHECK(n_src >= 1 && n_src <= kMaxSrc) << "push of " << n_src << " values for one key";
+    if (mp_mode) MXKV_CHECK(n_src == 1) << "one-process-per-GPU mode: push exactly one value per key per rank";
+    const int per_word = 32 / gc_bits_;
+    const int64_t nwords = (ks.size + per_word - 1) / per_word;
+    // ---- 1. quantise every value where it lives ---------------------------------------------
+    if (static_cast<int>(ks.gc_residual.size()) < n_src) { ks.gc_residual.resize(n_src); ks.gc_packed.resize(n_src); }
+    std::vector<int> src_dev(n_src);
+    for (int k = 0; k < n_src; ++k) {
+      const NDArray& v = g.vals[k];
+      MXKV_CHECK(v.size() == ks.size && v.dtype() == ks.dtype) << "push: value does not match key " << ks.key;
+      const Context c = v.ctx();
+      const int dev = mp_mode ? pg->dev() : (c.is_gpu() ? c.dev_id : (ks.reps.empty() ? DefaultDevice() : ks.reps[0].dev));
+      src_dev[k] = dev;
+      touch(dev);
+      if (ks.gc_residual[k].is_none() || ks.gc_residual[k].dev() != dev) {
+        ks.gc_residual[k] = NDArray::Empty(ks.shape, Context{kGPU, dev}, kFloat32);
+        ks.gc_packed[k] = NDArray::Empty({nwords}, Context{kGPU, dev}, kInt32, mp_mode);
+        DeviceGuard dg(dev);
+        CUDA_CALL(cudaMemsetAsync(ks.gc_residual[k].data(), 0, ks.gc_residual[k].nbytes(), rt->Dev(dev).stream));
+      }
+      DeviceGuard dg(dev);
+      cudaStream_t s = rt->Dev(dev).stream;
+      const float* gptr = static_cast<const float*>(v.data());
+      if (!(c.is_gpu() && c.dev_id == dev)) {     // host value: stage it
+        void* t = nullptr;
+        CUDA_CALL(cudaMallocAsync(&t, std::max<size_t>(v.nbytes(), 16), s));
+        CopyBytes(v.data(), c, t, Context{kGPU, dev}, v.nbytes());
+        temps.push_back({t, dev});
+        gptr = static_cast<const float*>(t);
+      }
+      const int rc = LaunchQuantize(gc_bits_, gptr, static_cast<float*>(ks.gc_residual[k].data()),
+                                    static_cast<uint32_t*>(ks.gc_packed[k].data()), ks.size, gc_threshold_, s);
+      MXKV_CHECK(rc == 0) << "quantize launch failed: " << cudaGetErrorString(static_cast<cudaError_t>(rc));
+      rt->launches++;
+    }
+    // ---- 2. consumers: every GPU that holds (or must hold) a replica ----------------------------
+    std::vector<int> consumers;
+    if (mp_mode) consumers.push_back(pg->dev());
+    else {
+      for (int d : src_dev) if (std::find(consumers.begin(), consumers.end(), d) == consumers.end()) consumers.push_back(d);
+      for (auto& r : ks.reps) if (std::find(consumers.begin(), consumers.end(), r.dev) == consumers.end()) consumers.push_back(r.dev);
+      rt->EnablePeerAccess(consumers);
+    }
+    SyncArgs sync;
+    std::memset(&sync, 0, sizeof(sync));
+    if (world > 1) {
+      sync.self = rt->Dev(pg->dev()).signal_pad;
+      for (int q = 0; q < world; ++q) sync.peers[q] = pg->signal_pad(q);
+      sync.world = world; sync.rank = pg->rank(); sync.mode = SYNC_WRITE_PEERS;
+      sync.timeout = rt->spin_timeout_cycles;
+      DeviceGuard dg(pg->dev());
+      MXKV_CHECK(LaunchBarrier(sync, rt->Dev(pg->dev()).stream) == 0) << "barrier launch failed";   // codes published
+      rt->launches++;
+    }
+    const int n_total = mp_mode ? world : n_src;
+    const bool mp = fused && opt_.multi_precision;
+    std::set<NDArray*> written;
+    if (fused) ks.count += 1;
+    const float lr = fused ? KeyLR(ks) : 0.f;
+    const float wd = fused ? KeyWD(ks) : 0.f;
+    for (int dev : consumers) {
+      touch(dev);
+      EnsureReplica(ks, dev);
+      if (ks.local_world > 0) GatherLocal(ks);
+      Replica& r = *FindReplica(ks, dev);
+      if (fused) { if (ks.has_state) GatherState(ks); EnsureState(ks, r, mp); ks.state_world = 0; }
+      DeviceGuard dg(dev);
+      cudaStream_t s = rt->Dev(dev).stream;
+      float* deq = nullptr;
+      CUDA_CALL(cudaMallocAsync(reinterpret_cast<void**>(&deq), static_cast<size_t>(n_total) * std::max<int64_t>(ks.size, 4) * 4, s));
+      temps.push_back({deq, dev});
+      TensorWork tw;
+      std::memset(&tw, 0, sizeof(tw));
+      tw.n_src = n_total;
+      for (int k = 0; k < n_total; ++k) {
+        const uint32_t* codes;
+        if (mp_mode) {
+          codes = static_cast<const uint32_t*>(world > 1 ? ks.gc_packed[0].peer_data(k) : ks.gc_packed[0].data());
+        } else {
+          if (src_dev[k] != dev) {
+            MXKV_CHECK(rt->PeerOK(dev, src_dev[k])) << "gradient compression needs peer access between GPU " << dev
+                                                    << " and GPU " << src_dev[k];
+            rt->StreamWait(dev, src_dev[k]);
+          }
+          codes = static_cast<const uint32_t*>(ks.gc_packed[k].data());
+        }
+        float* out = deq + static_cast<size_t>(k) * ks.size;
+        const int rc = LaunchDequantize(gc_bits_, codes, out, ks.size, gc_threshold_, s);
+        MXKV_CHECK(rc == 0) << "dequantize launch failed: " << cudaGetErrorString(static_cast<cudaError_t>(rc));
+        rt->launches++;
+        tw.src[k] = out;
+      }
+      tw.out[tw.n_out++] = r.local.data();
+      bool vec_ok = (ks.size % 4 == 0);          // scratch slices stay 16-byte aligned only then
+      if (write_outs) {
+        for (NDArray* o : g.outs) {
+          MXKV_CHECK(o->size() == ks.size && o->dtype() == ks.dtype) << "pushpull: output does not match key " << ks.key;
+          const Context oc = o->ctx();
+          if (oc.is_gpu() && oc.dev_id == dev && tw.n_out < kMaxOut) {
+            tw.out[tw.n_out++] = o->data();
+            vec_ok = vec_ok && ((reinterpret_cast<uintptr_t>(o->data()) & 15) == 0);
+            written.insert(o);
+          }
+        }
+      }
+      tw.w = r.local.data();
+      tw.w32 = mp ? static_cast<float*>(r.w32.data()) : nullptr;
+      tw.s0 = r.s0.is_none() ? nullptr : static_cast<float*>(r.s0.data());
+      tw.s1 = r.s1.is_none() ? nullptr : static_cast<float*>(r.s1.data());
+      tw.begin = 0; tw.end = ks.size;
+      tw.lr = lr; tw.wd = wd; tw.eta = opt_.eta;
+      tw.pad_ = vec_ok ? 3 : 0;
+      LaunchLocal(LaunchClassKey{SYNC_NONE, ks.dtype, mp ? 1 : 0}, tw, opt_kind, dev);
+      r.fresh = true;
+    }
+    if (world > 1) {
+      DeviceGuard dg(pg->dev());
+      MXKV_CHECK(LaunchBarrier(sync, rt->Dev(pg->dev()).stream) == 0) << "barrier launch failed";   // codes consumed
+      rt->launches++;
+    } else {
+      for (int k = 0; k < n_src; ++k)
+        for (int dev : consumers) if (dev != src_dev[k]) rt->StreamWait(src_dev[k], dev);
+    }
+    for (auto& r : ks.reps) {
+      if (std::find(consumers.begin(), consumers.end(), r.dev) == consumers.end()) r.fresh = false;
+    }
+    if (write_outs) {
+      for (NDArray* o : g.outs) {
+        if (written.count(o)) continue;          // the kernel on that GPU wrote it
+        const Context oc = o->ctx();
+        if (oc.is_gpu()) touch(oc.dev_id);
+        PostCopy pc;
+        pc.dst = *o;
+        Replica* src = (oc.is_gpu() && FindReplica(ks, oc.dev_id) && FindReplica(ks, oc.dev_id)->fresh)
+                           ? FindReplica(ks, oc.dev_id) : &FreshReplica(ks);
+        pc.src = src->local;
+        post.push_back(pc);
+      }
+    }
+  }
+  for (auto& t : temps) {
+    DeviceGuard dg(t.second);
+    CUDA_CALL(cudaFreeAsync(t.first, rt->Dev(t.second).stream));
+  }
+  for (auto& pc : post) CopyFromTo(pc.src, pc.dst);
+  for (int dev : touched) rt->ReleaseToUser(dev);
+}
+
 void KVStore::ReduceUpdate(std::vector<Group>& groups, bool write_outs) {
+  if (gc_bits_ != 0) { ReduceUpdateCompressed(groups, write_outs); return; }
   if (HostPipelined(groups, write_outs)) return;
   Runtime* rt = Runtime::Get();
   ProcessGroup* pg = rt->pg();
@@ -1131,6 +1304,19 @@ void KVStore::LaunchWorks(const LaunchClassKey& ck, std::vector<std::vector<Tens
     rt->launches++;
     d.ring.Commit(off, bytes, d.stream);
   }
+}
+
+// A launch that involves one GPU only (no rendezvous), whatever the deployment shape.
+void KVStore::LaunchLocal(const LaunchClassKey& ck, const TensorWork& tw, int opt_kind, int dev) {
+  ProcessGroup* pg = Runtime::Get()->pg();
+  const int slots = pg ? pg->world() : 1;
+  const int mine = pg ? pg->rank() : 0;
+  std::vector<std::vector<TensorWork>> per_part(slots);
+  per_part[mine].push_back(tw);
+  std::vector<int> part_dev(slots, dev);
+  LaunchClassKey local = ck;
+  local.sync_mode = SYNC_NONE;
+  LaunchWorks(local, per_part, {tw.end - tw.begin}, opt_kind, part_dev);
 }
 
 // All-gather of a key whose stored value is valid shard-wise only (after a two-shot push that did

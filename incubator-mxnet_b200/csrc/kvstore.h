@@ -69,7 +69,8 @@ struct KeyState {
   int local_world = 0;           // > 0: the stored value is valid shard-wise only (shard p on shard_devs[p])
   std::vector<int> shard_devs;   // devices (SP) / placeholder per rank (MP) of the shard owners
   bool has_state = false;
-  NDArray rsp_local;             // row_sparse stored value (dense-backed rows), see kvstore_rsp.cc
+  // gradient compression: per pushed-value slot, error-feedback residual and the code stream
+  std::vector<NDArray> gc_residual, gc_packed;
 };
 
 int64_t ShardLen(int64_t size, int world);
@@ -150,8 +151,10 @@ class KVStore {
   // busiest[i]: number of elements the busiest rank processes for entry i (fixes the common grid)
   void LaunchWorks(const LaunchClassKey& ck, std::vector<std::vector<TensorWork>>& per_part,
                    const std::vector<int64_t>& busiest, int opt_kind, const std::vector<int>& part_dev);
+  void LaunchLocal(const LaunchClassKey& ck, const TensorWork& tw, int opt_kind, int dev);
   void GatherLocal(KeyState& ks);
   bool HostPipelined(std::vector<Group>& groups, bool write_outs);
+  void ReduceUpdateCompressed(std::vector<Group>& groups, bool write_outs);
   void RunCallbackUpdater(KeyState& ks, Replica& root);
   void PushRowSparse(KeyState& ks, const std::vector<NDArray>& vals);
   void InitRowSparseKey(KeyState& ks, const NDArray& v);
@@ -183,6 +186,7 @@ class KVStore {
   OptimizerConfig opt_;
   std::string gc_type_ = "none";
   float gc_threshold_ = 0.5f;
+  int gc_bits_ = 0;
   std::recursive_mutex mu_;
 };
 

@@ -149,6 +149,19 @@ def main():
         assert np.array_equal(out.indices.asnumpy(), want.indices), "rsp idx"
         assert bits_equal(out.data.asnumpy(), want.data.reshape(-1, L)), ("rsp", step)
 
+    # 6. 2-bit gradient compression with error feedback, one code stream per rank
+    E, thr = 30000, 0.5
+    kv6 = mx.kv.create("device")
+    kv6.set_gradient_compression({"type": "2bit", "threshold": thr})
+    kv6.init("c", mx.nd.zeros((E,), ctx))
+    residual = [np.zeros(E, np.float32) for _ in range(world)]
+    for step in range(3):
+        out = mx.nd.empty((E,), ctx)
+        kv6.pushpull("c", mx.nd.array(data(70 + step, (E,), rank), ctx), out=out)
+        deq = [O.dequantize_2bit(O.quantize_2bit(data(70 + step, (E,), r), residual[r], thr), E, thr)
+               for r in range(world)]
+        assert bits_equal(out.asnumpy(), O.sum_device(deq)), ("compression", step)
+
     mx.nd.waitall()
     dist.barrier()
     print("MP_WORKER_OK rank", rank, flush=True)

@@ -1139,7 +1139,9 @@ void KVStore::ReduceUpdate(std::vector<Group>& groups, bool write_outs) {
     }
 
     // ---- work entries -------------------------------------------------------
-    const int sync_mode = !collective ? SYNC_NONE : (two_shot ? SYNC_WRITE_PEERS : SYNC_READ_PEERS);
+    // one launch (one pair of rendezvous) for the one-shot and the two-shot keys of a call: the
+    // release/acquire flavour of the end barrier covers both
+    const int sync_mode = !collective ? SYNC_NONE : SYNC_WRITE_PEERS;
     LaunchClassKey ck{sync_mode, ks.dtype, mp ? 1 : 0};
     LaunchClass& lc = classes[ck];
     auto& cls = lc.per_part;
@@ -1234,11 +1236,13 @@ void KVStore::LaunchWorks(const LaunchClassKey& ck, std::vector<std::vector<Tens
     const int extra = (opt_kind != OPT_NONE ? 1 : 0) +
                       ((opt_kind == OPT_SGD_MOM || opt_kind == OPT_ADAM || opt_kind == OPT_ADAMW) ? 1 : 0) +
                       ((opt_kind == OPT_ADAM || opt_kind == OPT_ADAMW) ? 1 : 0);
-    // measured (profiles/r01_tune_bulk.txt): the staged variant wins when a thread of the per-thread
-    // variant would have few loads in flight (<= 2 sources, >= 3 streams: 6255 vs 5413 GB/s at n=1,
-    // busbw 623 vs 575 at n=2); with >= 3 sources the per-thread variant already keeps enough
-    // requests in flight and is faster (6606 vs 5794 GB/s at n=4).  bulk_mode 2 forces it.
-    const bool want = rt->bulk_mode >= 2 || (max_src <= 2 && max_src + extra >= 3);
+    // measured (profiles/r01_tune_bulk.txt): the staged variant wins (a) whenever sources are read
+    // over NVLink (busbw 623 vs 575 GB/s at n=2, 664 vs 637 at n=4: more bytes in flight against a
+    // ~2 us round trip) and (b) locally when a thread of the per-thread variant would have few loads
+    // in flight (<= 2 sources, >= 3 streams: 6255 vs 5413 GB/s at n=1).  With >= 3 local sources the
+    // per-thread variant already keeps enough requests in flight and is faster (6606 vs 5794 GB/s at
+    // n=4 on one GPU).  bulk_mode 2 forces the staged variant wherever it is eligible.
+    const bool want = rt->bulk_mode >= 2 || ck.sync_mode != SYNC_NONE || (max_src <= 2 && max_src + extra >= 3);
     if (ok && want) {
       // n_src is the same for every entry of a collective class; take the max for safety
       int tile = 0, st = 0;

@@ -43,7 +43,7 @@ def main():
         kv.set_optimizer(mx.optimizer.SGD(learning_rate=0.01, momentum=0.9, wd=1e-4))
     elif opt == "adam":
         kv.set_optimizer(mx.optimizer.Adam())
-    configs = [(8192, 512, 0, 0), (8192, 512, 0, 1)]
+    configs = [(8192, 512, 0, 0), (8192, 512, 0, 1), (8192, 512, 0, 2)]
     steps = 40
     for chunk, threads, mb, bulk in configs:
         check_call(_LIB.MXKVB200SetTuning(ctypes.c_int64(chunk), threads, mb, bulk))

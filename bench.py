@@ -7,7 +7,7 @@ weights, new weights delivered to every rank).  Workload (config.workload):
 
   sweep     BASELINE.json configs[1]: one fp32 key per size 2^10, 2^12, ..., 2^26 elements
             (4 KB ... 256 MB; 89.5 M elements, 358 MB per rank) -- the default
-  resnet50  configs[2]'s key set: the 161 gradient-carrying arrays of Gluon ResNet-50-v1
+  resnet50  configs[2]'s key set: the 193 gradient-carrying arrays of Gluon ResNet-50-v1 (25.6 M elements)
   bert      configs[3]'s key set: BERT-base (synthetic shape list), Adam
 
 One process per GPU (torchrun for N > 1); every rank contributes its own gradient for every key
@@ -168,13 +168,26 @@ def cpu_kvstore_step_factory(shapes, n_values, threads, optimizer):
 
 
 def run_cpu_reference(args, shapes, as_baseline=False):
+    """Times the reference's CPU KVStore algorithm (oracle port, all host threads).  A step is a
+    BOUNDED SAMPLE of the workload: every key is cut to the same leading fraction so that the whole
+    --steps/--warmup run stays within ~2 minutes (GB/s is intensive, so the sample is comparable)."""
     from oracle import oracle as O
     threads = O.lib().kvo_max_threads()
     n_values = max(1, args.gpus)
-    S = 4 * sum(nelem(s) for s in shapes)
-    step = cpu_kvstore_step_factory(shapes, n_values, threads, args.optimizer)
     warm = 1 if as_baseline else args.warmup
     steps = 3 if as_baseline else args.steps
+    budget_s = 20.0 if as_baseline else 100.0
+    sizes = [nelem(s) for s in shapes]
+    probe_frac = min(1.0, 64e6 / max(1, sum(sizes)) / n_values * 4)     # probe on <= ~64 M elements of traffic
+    probe_shapes = [(max(256, int(e * probe_frac)),) for e in sizes]
+    probe = cpu_kvstore_step_factory(probe_shapes, n_values, threads, args.optimizer)
+    probe()
+    t0 = time.perf_counter(); probe(); t_probe = time.perf_counter() - t0
+    t_full = t_probe / probe_frac
+    frac = min(1.0, budget_s / (steps + warm) / t_full)
+    sample_shapes = [(max(256, int(e * frac)),) for e in sizes]
+    S = 4 * sum(nelem(s) for s in sample_shapes)
+    step = cpu_kvstore_step_factory(sample_shapes, n_values, threads, args.optimizer)
     for _ in range(warm):
         step()
     t0 = time.perf_counter()
@@ -182,11 +195,86 @@ def run_cpu_reference(args, shapes, as_baseline=False):
         step()
     dt = (time.perf_counter() - t0) / steps
     value = n_values * 2 * S / dt / 1e9
-    sample = "%d step(s) of the full %s key set (%.0f MB x %d value(s) per key), %d OpenMP threads" % (
-        steps, args.workload, S / 1e6, n_values, threads)
+    sample = ("%d step(s), each over the leading %.1f%% of every key of the %s key set (%.1f MB x %d value(s) per key), "
+              "%d OpenMP threads" % (steps, 100 * frac, args.workload, S / 1e6, n_values, threads))
     base = {"value": value, "unit": "GB/s", "cores": threads,
             "kind": "port", "sample": sample}
     return value, dt, base
+
+
+# ---------------------------------------------------------------------------
+# samples/sec: BASELINE.json configs[2] -- ResNet-50 bf16, synthetic 3x224x224, SGD-momentum
+# (multi-precision) through Trainer(kvstore='device'); torch does forward/backward, the engine does
+# the gradient exchange + fused update.  Secondary workload: one JSON line with img/s.
+# ---------------------------------------------------------------------------
+def train_resnet50(args):
+    import torch
+    import torchvision
+    import mxnet_b200 as mx
+    rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        mx.dist.init_process_group(device=local)
+    torch.manual_seed(0)
+    model = torchvision.models.resnet50(weights=None).cuda().to(memory_format=torch.channels_last).to(torch.bfloat16)
+    params = [p for p in model.parameters() if p.requires_grad]
+    trainer = mx.Trainer(params, "sgd", {"learning_rate": 0.1, "momentum": 0.9, "wd": 1e-4, "multi_precision": True},
+                         kvstore="device", symmetric=True)
+    B = args.batch
+    x = torch.randn(B, 3, 224, 224, device="cuda", dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    y = torch.randint(0, 1000, (B,), device="cuda")
+    lossf = torch.nn.CrossEntropyLoss()
+
+    def step():
+        out = model(x)
+        loss = lossf(out.float(), y)
+        loss.backward()
+        trainer.step(B * world)
+        return loss
+
+    steps, warm = min(args.steps, 50), max(3, args.warmup)
+    for _ in range(warm):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ec = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    launches0 = mx.kv.launch_count()
+    e0.record()
+    for i in range(steps):
+        out = model(x)
+        loss = lossf(out.float(), y)
+        loss.backward()
+        ec[i][0].record()
+        trainer.step(B * world)
+        ec[i][1].record()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    comm_ms = sum(a.elapsed_time(b) for a, b in ec) / steps
+    t = torch.tensor([ms, comm_ms], device="cuda", dtype=torch.float64)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    ms, comm_ms = t[0].item(), t[1].item()
+    nparam = sum(p.numel() for p in params)
+    if rank == 0:
+        print(json.dumps({"metric": "samples/sec (ResNet-50 bf16, synthetic 3x224x224, Trainer(kvstore='device'))",
+                          "value": world * B / (ms * 1e-3), "unit": "img/s", "n_gpus": world, "steps": steps,
+                          "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+                          "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                          "config": {"workload": "resnet50-train: torchvision resnet50 (random init), batch %d per GPU, "
+                                                 "SGD momentum 0.9 wd 1e-4 multi-precision, %d keys / %.1f M params"
+                                                 % (B, len(params), nparam / 1e6),
+                                     "exchange_ms_per_step": comm_ms, "keys": len(params)},
+                          "gpu_launches": mx.kv.launch_count() - launches0, "loss": float(loss)}))
+    mx.nd.waitall()
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
 
 
 # ---------------------------------------------------------------------------
@@ -198,11 +286,14 @@ def main():
     ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="sweep", choices=["sweep", "resnet50", "bert"])
+    ap.add_argument("--workload", default="sweep", choices=["sweep", "resnet50", "bert", "resnet50-train"])
+    ap.add_argument("--batch", type=int, default=128, help="per-GPU batch of resnet50-train")
     ap.add_argument("--optimizer", default=None, choices=[None, "sgd", "adam", "none"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    if args.workload == "resnet50-train":
+        return train_resnet50(args)
     if args.optimizer is None:
         args.optimizer = "adam" if args.workload == "bert" else "sgd"
     shapes = keyset(args.workload)

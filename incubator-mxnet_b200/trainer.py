@@ -12,7 +12,7 @@ from .ndarray import from_torch
 
 class Trainer(object):
     def __init__(self, params, optimizer, optimizer_params=None, kvstore="device", update_on_kvstore=None,
-                 batched=True):
+                 batched=True, symmetric=False):
         self._params = [p if isinstance(p, (list, tuple)) else [p] for p in params]
         optimizer_params = dict(optimizer_params or {})
         self._scale = float(optimizer_params.get("rescale_grad", 1.0))
@@ -27,6 +27,7 @@ class Trainer(object):
         self._kvstore = None
         self._update_on_kvstore = None
         self._batched = batched
+        self._symmetric = symmetric      # rebind p.data / p.grad to peer-mapped arena memory (zero-copy)
         self._grads = None
         self._weights = None
 
@@ -51,7 +52,10 @@ class Trainer(object):
         elif uok and not kv.is_capable(_kv.KVStoreBase.OPTIMIZER):
             raise ValueError("Please set update_on_kvstore=False when training with " + str(type(kv)))
         self._update_on_kvstore = uok
-        self._weights = [[from_torch(p.data) for p in reps] for reps in self._params]
+        if self._symmetric:
+            self._bind_symmetric()
+        else:
+            self._weights = [[from_torch(p.data) for p in reps] for reps in self._params]
         if kv is not None:
             if uok:
                 kv.set_optimizer(self._optimizer)
@@ -59,6 +63,31 @@ class Trainer(object):
             idx = list(range(len(self._params)))
             kv.broadcast(idx, [w[0] for w in self._weights], [w for w in self._weights])
         self._kv_initialized = True
+
+    def _bind_symmetric(self):
+        """One-process-per-GPU: move every parameter and its gradient into the engine's peer-mapped
+        arena (collective allocation, same order on every rank) and hand torch views of that memory
+        back to the module, so push/pull read and write them over NVLink without staging."""
+        import torch
+        from . import ndarray as _nd
+        tmap = {torch.float32: "float32", torch.float16: "float16", torch.bfloat16: "bfloat16"}
+        self._weights, self._grads, self._grad_ptrs = [], [], []
+        for reps in self._params:
+            assert len(reps) == 1, "symmetric binding is for one replica per process"
+            p = reps[0]
+            dt = tmap[p.dtype]
+            shape = tuple(p.shape) if p.dim() > 0 else (1,)
+            w = _nd.empty_symmetric(shape, dt if dt == "bfloat16" else getattr(__import__("numpy"), dt))
+            g = _nd.empty_symmetric(shape, dt if dt == "bfloat16" else getattr(__import__("numpy"), dt))
+            wt, gt = w.as_torch().view(p.shape), g.as_torch().view(p.shape)
+            wt.copy_(p.data)
+            gt.zero_()
+            p.data = wt
+            p.grad = gt
+            self._weights.append([w])
+            self._grads.append([g])
+            self._grad_ptrs.append([gt.data_ptr()])
+        torch.cuda.synchronize()
 
     def _bind_grads(self):
         self._grads = [[from_torch(p.grad) for p in reps] for reps in self._params]

@@ -1,0 +1,105 @@
+"""Trainer (python/mxnet/gluon/trainer.py driver loop) over torch parameters."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import mxnet_b200 as mx
+from oracle import oracle as O
+
+
+def _bits_equal(a, b):
+    return np.array_equal(np.ascontiguousarray(a, np.float32).view(np.uint32),
+                          np.ascontiguousarray(b, np.float32).view(np.uint32))
+
+
+def _model():
+    import torch
+    torch.manual_seed(0)
+    return torch.nn.Sequential(torch.nn.Linear(64, 128), torch.nn.ReLU(), torch.nn.Linear(128, 10)).cuda()
+
+
+@pytest.mark.parametrize("batched", [True, False])
+def test_trainer_step_matches_oracle_sgd(batched):
+    """update_on_kvstore (default): step = rescale 1/batch, per-parameter pushpull, fused SGD-momentum."""
+    import torch
+    model = _model()
+    params = list(model.parameters())
+    kw = dict(learning_rate=0.1, momentum=0.9, wd=1e-4)
+    trainer = mx.Trainer(params, "sgd", dict(kw), kvstore="device", batched=batched)
+    ref_w = [p.detach().cpu().numpy().copy() for p in params]
+    opt = O.OracleOptimizer("sgd", **kw)
+    x = torch.randn(32, 64, device="cuda")
+    for step in range(3):
+        model.zero_grad()
+        model(x).square().mean().backward()
+        grads = [p.grad.detach().cpu().numpy().copy() for p in params]
+        trainer.step(32)
+        torch.cuda.synchronize()
+        opt.rescale_grad = 1.0 / 32
+        for i, (w, g) in enumerate(zip(ref_w, grads)):
+            opt.update(i, w.reshape(-1), g.reshape(-1))
+        for p, w in zip(params, ref_w):
+            assert _bits_equal(p.detach().cpu().numpy(), w), step
+    assert trainer._update_on_kvstore is True
+
+
+def test_trainer_decision_table_and_local_update():
+    """tests/python/unittest/test_gluon_trainer.py:247-281 (single-machine rows): kvstore=None or
+    update_on_kvstore=False -> updates run per device outside the store."""
+    import torch
+    model = _model()
+    params = list(model.parameters())
+    t = mx.Trainer(params, "sgd", {"learning_rate": 0.1}, kvstore=None)
+    x = torch.randn(8, 64, device="cuda")
+    model(x).sum().backward()
+    before = [p.detach().clone() for p in params]
+    t.step(8)
+    assert t._kvstore is None and t._update_on_kvstore is False
+    for p, b in zip(params, before):
+        assert torch.allclose(p, b - 0.1 * p.grad / 8, rtol=1e-5, atol=1e-6)
+    t2 = mx.Trainer(list(_model().parameters()), "sgd", {"learning_rate": 0.1}, kvstore="device",
+                    update_on_kvstore=False)
+    m2 = t2._params
+    model2 = _model()
+    t2 = mx.Trainer(list(model2.parameters()), "sgd", {"learning_rate": 0.1}, kvstore="device",
+                    update_on_kvstore=False)
+    model2(x).sum().backward()
+    t2.step(8)
+    assert t2._update_on_kvstore is False and t2._kvstore is not None
+    with pytest.raises(ValueError):
+        class NoOpt(mx.kv.KVStore):
+            @staticmethod
+            def is_capable(c):
+                return False
+        mx.Trainer(list(_model().parameters()), "sgd", {}, kvstore=NoOpt("device"), update_on_kvstore=True)._init_kvstore()
+
+
+def test_trainer_save_load_states(tmp_path):
+    import torch
+    x = torch.randn(16, 64, device="cuda")
+
+    def run(trainer, model, n):
+        for _ in range(n):
+            model.zero_grad()
+            model(x).square().mean().backward()
+            trainer.step(16)
+        torch.cuda.synchronize()
+        return [p.detach().cpu().numpy().copy() for p in model.parameters()]
+
+    m1 = _model()
+    t1 = mx.Trainer(list(m1.parameters()), "adam", {"learning_rate": 0.01}, kvstore="device")
+    run(t1, m1, 2)
+    f = str(tmp_path / "trainer.states")
+    t1.save_states(f)
+    mid = [p.detach().clone() for p in m1.parameters()]
+    want = run(t1, m1, 2)
+    m2 = _model()
+    with torch.no_grad():
+        for p, v in zip(m2.parameters(), mid):
+            p.copy_(v)
+    t2 = mx.Trainer(list(m2.parameters()), "adam", {"learning_rate": 0.01}, kvstore="device")
+    t2.load_states(f)
+    got = run(t2, m2, 2)
+    for a, b in zip(got, want):
+        assert _bits_equal(a, b)

@@ -278,6 +278,73 @@ def train_resnet50(args):
 
 
 # ---------------------------------------------------------------------------
+# BASELINE.json configs[4]: one row_sparse key (1 M x 256 fp32), 10 k distinct rows per GPU;
+# step = row_sparse push (union + gather-sum + lazy SGD-momentum on the touched rows) followed by
+# row_sparse_pull of the same ids.  Secondary workload: one JSON line with rows/s and GB/s.
+# ---------------------------------------------------------------------------
+def bench_rsp(args):
+    import torch
+    import mxnet_b200 as mx
+    rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        mx.dist.init_process_group(device=local)
+    ctx = mx.gpu(local)
+    R, L, nnz = 1_000_000, 256, 10_000
+    rng = np.random.default_rng(1234 + rank)
+    idx = np.sort(rng.choice(R, nnz, replace=False)).astype(np.int64)
+    val = rng.uniform(-1, 1, (nnz, L)).astype(np.float32)
+    grad = mx.nd.row_sparse_array((val, idx), shape=(R, L), ctx=ctx)
+    ids = mx.nd.array(idx, ctx, dtype=np.int64)
+    out = mx.nd.empty((R, L), ctx, stype="row_sparse", capacity=nnz)
+    kv = mx.kv.create("device")
+    kv.init("emb", mx.nd.row_sparse_array((np.zeros((1, L), np.float32), np.zeros(1, np.int64)), shape=(R, L), ctx=ctx))
+    kv.set_optimizer(mx.optimizer.SGD(learning_rate=0.01, momentum=0.9, wd=0.0))
+
+    def step():
+        kv.push("emb", grad)
+        kv.row_sparse_pull("emb", out=out, row_ids=ids)
+
+    steps, warm = min(args.steps, 100), max(3, args.warmup)
+    for _ in range(warm):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    launches0 = mx.kv.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / steps], device="cuda", dtype=torch.float64)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    ms = t.item()
+    union = int(out.indices.shape[0])
+    row_bytes = L * 4 + 8
+    alg_per_gpu = world * nnz * row_bytes + nnz * row_bytes    # every GPU reads all sources' rows, then pulls its rows
+    if rank == 0:
+        print(json.dumps({"metric": "row_sparse push + row_sparse_pull rows/s", "value": world * nnz / (ms * 1e-3),
+                          "unit": "rows/s", "n_gpus": world, "steps": steps, "warmup": warm, "ms_per_step": ms,
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                          "data": "synthetic",
+                          "config": {"workload": "rsp: 1 key 1000000x256 fp32 row_sparse, %d rows per GPU, lazy SGD-momentum, "
+                                                 "push + row_sparse_pull" % nnz,
+                                     "union_rows": union,
+                                     "algorithmic_gbs_per_gpu": alg_per_gpu / (ms * 1e-3) / 1e9},
+                          "gpu_launches": mx.kv.launch_count() - launches0}))
+    mx.nd.waitall()
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------
 def main():
@@ -286,7 +353,7 @@ def main():
     ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="sweep", choices=["sweep", "resnet50", "bert", "resnet50-train"])
+    ap.add_argument("--workload", default="sweep", choices=["sweep", "resnet50", "bert", "resnet50-train", "rsp"])
     ap.add_argument("--batch", type=int, default=128, help="per-GPU batch of resnet50-train")
     ap.add_argument("--optimizer", default=None, choices=[None, "sgd", "adam", "none"])
     ap.add_argument("--no-e2e", action="store_true")
@@ -294,6 +361,8 @@ def main():
     args = ap.parse_args()
     if args.workload == "resnet50-train":
         return train_resnet50(args)
+    if args.workload == "rsp":
+        return bench_rsp(args)
     if args.optimizer is None:
         args.optimizer = "adam" if args.workload == "bert" else "sgd"
     shapes = keyset(args.workload)

@@ -198,6 +198,17 @@ constexpr int kUniqueMax = 16384;
 __global__ void __launch_bounds__(1024)
 rsp_unique_kernel(const int64_t* in, int64_t n, int64_t* out, int64_t* d_count) {
   extern __shared__ int64_t sm[];
+  // fast path: ids that are already strictly increasing (e.g. the index array of a row_sparse
+  // gradient) need neither the sort nor the compaction
+  {
+    int ok = 1;
+    for (int64_t i = threadIdx.x; i + 1 < n; i += blockDim.x) ok &= (in[i] < in[i + 1]) ? 1 : 0;
+    if (__syncthreads_and(ok)) {
+      for (int64_t i = threadIdx.x; i < n; i += blockDim.x) out[i] = in[i];
+      if (threadIdx.x == 0) *d_count = n;
+      return;
+    }
+  }
   int64_t npad = 1;
   while (npad < n) npad <<= 1;
   for (int64_t i = threadIdx.x; i < npad; i += blockDim.x) sm[i] = i < n ? in[i] : INT64_MAX;

@@ -357,6 +357,7 @@ def main():
     ap.add_argument("--batch", type=int, default=128, help="per-GPU batch of resnet50-train")
     ap.add_argument("--optimizer", default=None, choices=[None, "sgd", "adam", "none"])
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-nvls", action="store_true", help="keep gradients/weights out of multicast memory")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.workload == "resnet50-train":
@@ -407,10 +408,21 @@ def main():
     keys = list(range(len(shapes)))
     # gradients / weights live in the peer-mapped arena (zero-copy over NVLink); at N=1 this is
     # plain device memory
-    grads = [mx.nd.empty_symmetric(s) for s in shapes]
-    weights = [mx.nd.empty_symmetric(s) for s in shapes]
+    exchange = "nvlink-p2p"
+    alloc = mx.nd.empty_symmetric
+    if world > 1 and not args.no_nvls:
+        try:
+            probe = mx.nd.empty_multicast((1024,))
+            if mx.nd.has_multicast(probe):
+                alloc = mx.nd.empty_multicast          # NVSwitch multicast: multimem.ld_reduce / multimem.st
+                exchange = "nvls-multicast"
+        except Exception as e:                         # noqa: BLE001 -- torch symmetric memory unavailable
+            sys.stderr.write("multicast allocation unavailable (%r): peer-load kernels\n" % (e,))
+    grads = [alloc(s) for s in shapes]
+    weights = [alloc(s) for s in shapes]
     for g, s in zip(grads, shapes):
         g[:] = rng.uniform(-1, 1, s).astype(np.float32)
+    config["exchange"] = exchange
     w0 = np.random.default_rng(99)
     kv = mx.kv.create("device")
     kv.init(keys, [mx.nd.array(w0.uniform(0, 1, s).astype(np.float32), ctx) for s in shapes])
@@ -482,14 +494,24 @@ def main():
         peak = peaks.get("hbm_gbs", 6650.0)
         roof = {"bound": "hbm", "achieved": alg / (kern_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650",
-                "traffic": None, "kernel": "kv_dense_kernel", "kernel_ms": kern_ms,
+                "traffic": None, "kernel": "kv_dense_bulk_kernel", "kernel_ms": kern_ms,
                 "algorithmic_bytes_per_launch": alg}
     else:
-        alg = 2.0 * S * (world - 1) / world      # per GPU per direction (tools/bandwidth/measure.py:138)
+        nvls_active = exchange == "nvls-multicast" and world > 4
+        if nvls_active:
+            # in-switch reduction + replication: per GPU per direction S (own data out / all shards in)
+            # plus S/n (its reduced shard in / its updated shard out)
+            alg = S * (1.0 + 1.0 / world)
+            kname = "kv_dense_nvls_kernel (multimem.ld_reduce + fused update + multimem.st)"
+        else:
+            alg = 2.0 * S * (world - 1) / world      # per GPU per direction (tools/bandwidth/measure.py:138)
+            kname = "kv_dense_bulk_kernel (peer cp.async.bulk loads + fused update + peer stores)"
         roof = {"bound": "nvlink", "achieved": alg / (kern_ms * 1e-3) / 1e9, "peak": 770.0, "unit": "GB/s",
                 "peak_source": "B200_PROFILING.md measured peer copy 770 GB/s/dir (900 nominal)",
-                "traffic": None, "kernel": "kv_dense_kernel", "kernel_ms": kern_ms,
-                "algorithmic_bytes_per_launch": alg}
+                "traffic": None, "kernel": kname, "kernel_ms": kern_ms,
+                "algorithmic_bytes_per_launch": alg,
+                "note": "bytes that must cross this GPU's NVLink per direction; busbw_gbs_per_gpu is the "
+                        "NCCL-comparable 2S(n-1)/n / t"}
     roof["frac"] = roof["achieved"] / roof["peak"]
 
     # ---- e2e: host gradients in, host weights out, through the same public API ---------------------

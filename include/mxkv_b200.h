@@ -185,6 +185,16 @@ MXKV_DLL int MXKVB200CommDestroy(void);
  * peer-mapped arena, so push/pushpull read and write it over NVLink without staging. */
 MXKV_DLL int MXKVB200NDArrayCreateSymmetric(const int64_t* shape, int ndim, int dtype, NDArrayHandle* out);
 
+/* Wrap peer-mapped memory owned by the embedding framework (one process per GPU): peer_ptrs[r] is
+ * the address of rank r's copy as mapped in THIS process, mc_ptr the NVSwitch multicast alias of all
+ * copies (NULL when none).  With a multicast alias the exchange uses the NVLS kernel
+ * (multimem.ld_reduce / multimem.st): the switch does the sum and the replication. */
+MXKV_DLL int MXKVB200NDArrayFromPeers(void* const* peer_ptrs, int world, void* mc_ptr, const int64_t* shape,
+                                      int ndim, int dtype, NDArrayHandle* out);
+/* 0: never use the NVLS kernel; 1 (default): use it above 4 ranks when every array of a key has a
+ * multicast alias; 2: whenever the arrays have one */
+MXKV_DLL int MXKVB200SetNvls(int mode);
+
 #ifdef __cplusplus
 }
 #endif

@@ -491,6 +491,22 @@ int MXKVB200NDArrayFromPtr(void* data, const int64_t* shape, int ndim, int dev_t
   API_END();
 }
 
+int MXKVB200NDArrayFromPeers(void* const* peer_ptrs, int world, void* mc_ptr, const int64_t* shape, int ndim,
+                             int dtype, NDArrayHandle* out) {
+  API_BEGIN();
+  ProcessGroup* pg = Runtime::Get()->pg();
+  MXKV_CHECK(pg != nullptr && pg->world() == world) << "MXKVB200NDArrayFromPeers needs a process group of " << world;
+  std::vector<int64_t> s(shape, shape + ndim);
+  *out = new NDHandle(NDArray::FromPeers(peer_ptrs, world, pg->rank(), mc_ptr, s, Context{kGPU, pg->dev()}, dtype));
+  API_END();
+}
+
+int MXKVB200SetNvls(int mode) {
+  API_BEGIN();
+  Runtime::Get()->nvls_mode = mode;
+  API_END();
+}
+
 int MXKVB200SetStream(int dev_id, void* cuda_stream) {
   API_BEGIN();
   Runtime::Get()->SetUserStream(dev_id, static_cast<cudaStream_t>(cuda_stream));

@@ -58,8 +58,11 @@ struct alignas(16) TensorWork {
   float eta;         // AdamW schedule multiplier
   int n_src;
   int n_out;
-  int pad_;
+  int pad_;          // bit 0: every pointer 16-byte aligned; bit 1: eligible for the staged variant
+  int n_mc;          // NVLS launches: the last n_mc entries of out[] are multicast addresses
+  int reserved_;
 };
+static_assert(sizeof(TensorWork) == 400, "TensorWork layout");
 
 struct SyncArgs {
   uint32_t* self;                // this rank's signal pad
@@ -92,6 +95,7 @@ struct DenseLaunch {
   int chunk_elems;               // elements per scheduling chunk (multiple of 128)
   int threads;                   // block size: 128, 256 or 512
   int small_n;                   // every entry has n_src <= 2: use the two-packets-in-flight variant
+  int nvls;                      // 1: src[0] is a multicast address (multimem.ld_reduce / multimem.st variant)
   int bulk;                      // 1: shared-memory staged variant (cp.async.bulk + mbarrier pipeline)
   int bulk_stages;               // pipeline depth
   int bulk_arrays;               // input arrays staged per tile (max over the work list)

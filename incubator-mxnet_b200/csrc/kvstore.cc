@@ -537,6 +537,7 @@ struct Dest {
   void* ptr[kMaxRanks];   // address as seen by participant p (MP: peer mapping; SP: same everywhere)
   int owner;              // participant index that owns the memory, -1: none, -2: one copy per rank (MP)
   bool own_only = false;  // two-shot: only the owning participant writes (its own shard of its own copy)
+  void* mc = nullptr;     // NVSwitch multicast alias of all copies (one store reaches every rank)
 };
 struct PostCopy { NDArray src; NDArray dst; };
 inline bool Overlap(const void* a, size_t an, const void* b, size_t bn) {
@@ -1029,6 +1030,7 @@ void KVStore::ReduceUpdate(std::vector<Group>& groups, bool write_outs) {
     }
 
     // ---- destinations -------------------------------------------------------
+    bool nvls_key = false;
     std::vector<Dest> dests;
     auto add_dest_sp = [&](void* ptr, int dev) {
       Dest d;
@@ -1081,6 +1083,19 @@ void KVStore::ReduceUpdate(std::vector<Group>& groups, bool write_outs) {
       // Two-shot keys keep the stored value sharded (rank p owns shard p of its own replica) unless
       // an output has to be copied out of a complete replica afterwards: the all-gather then moves
       // each shard over NVLink once per peer (into the outputs) instead of twice.
+      // NVLS: every array of the key is bound to a multicast object (and nothing has to be copied
+      // out of a complete replica afterwards)
+      // (auto: above 4 ranks.  Per direction the switch path moves S(1 + 1/n) against 2S(n-1)/n of
+      // the peer path: 1.5x more at n=2, equal time measured at n=4 -- where the peer path is kept
+      // because it is bit-exact --, 1.56x less at n=8: busbw 782 vs 641 GB/s, profiles/r01_tune_bulk.txt)
+      if (mp_mode && collective && (rt->nvls_mode >= 2 || (rt->nvls_mode == 1 && n_part > 4)) &&
+          ks.dtype == kFloat32 && ks.size % 4 == 0 &&
+          g.vals[0].mc_data() != nullptr && Aligned16(g.vals[0].mc_data()) && !(two_shot && need_post)) {
+        nvls_key = true;
+        if (write_outs)
+          for (size_t oi = 0; oi < g.outs.size(); ++oi)
+            if (out_direct[oi] && g.outs[oi]->mc_data() == nullptr) nvls_key = false;
+      }
       const bool shard_local = two_shot && !need_post;
       if (mp_mode && collective) {
         Dest d; d.owner = -2; d.own_only = shard_local;
@@ -1113,6 +1128,7 @@ void KVStore::ReduceUpdate(std::vector<Group>& groups, bool write_outs) {
             if (mp_mode && collective) {
               Dest d; d.owner = -2;
               for (int p = 0; p < n_part; ++p) d.ptr[p] = o->peer_data(p);
+              d.mc = o->mc_data();
               dests.push_back(d);
             } else {
               add_dest_sp(o->data(), oc.dev_id);
@@ -1143,6 +1159,7 @@ void KVStore::ReduceUpdate(std::vector<Group>& groups, bool write_outs) {
     // release/acquire flavour of the end barrier covers both
     const int sync_mode = !collective ? SYNC_NONE : SYNC_WRITE_PEERS;
     LaunchClassKey ck{sync_mode, ks.dtype, mp ? 1 : 0};
+    ck.nvls = nvls_key ? 1 : 0;
     LaunchClass& lc = classes[ck];
     auto& cls = lc.per_part;
     if (cls.empty()) cls.resize(n_part);
@@ -1152,14 +1169,21 @@ void KVStore::ReduceUpdate(std::vector<Group>& groups, bool write_outs) {
       TensorWork tw;
       std::memset(&tw, 0, sizeof(tw));
       bool vec_ok = true;
-      tw.n_src = static_cast<int>(srcptr[p].size());
-      for (int k = 0; k < tw.n_src; ++k) {
-        tw.src[k] = srcptr[p][k];
-        vec_ok = vec_ok && Aligned16(tw.src[k]);
+      if (nvls_key) {                  // the switch sums the replicas: one multicast "source"
+        tw.n_src = 1;
+        tw.src[0] = g.vals[0].mc_data();
+      } else {
+        tw.n_src = static_cast<int>(srcptr[p].size());
+        for (int k = 0; k < tw.n_src; ++k) {
+          tw.src[k] = srcptr[p][k];
+          vec_ok = vec_ok && Aligned16(tw.src[k]);
+        }
       }
+      std::vector<void*> mc_outs;
       for (auto& d : dests) {
         if (d.owner == -2) {           // MP: one copy per rank
           if (two_shot && !d.own_only) {
+            if (nvls_key) { mc_outs.push_back(d.mc); vec_ok = vec_ok && Aligned16(d.mc); continue; }
             for (int q = 0; q < n_part; ++q) { tw.out[tw.n_out++] = d.ptr[q]; vec_ok = vec_ok && Aligned16(d.ptr[q]); }
           } else {
             tw.out[tw.n_out++] = d.ptr[p]; vec_ok = vec_ok && Aligned16(d.ptr[p]);
@@ -1172,7 +1196,9 @@ void KVStore::ReduceUpdate(std::vector<Group>& groups, bool write_outs) {
         else mine = (d.owner == p) || (d.owner == -1 && p == 0);
         if (mine) { tw.out[tw.n_out++] = d.ptr[p]; vec_ok = vec_ok && Aligned16(d.ptr[p]); }
       }
+      for (void* m : mc_outs) { tw.out[tw.n_out++] = m; tw.n_mc++; }
       MXKV_CHECK(tw.n_out <= kMaxOut) << "too many destinations for key " << ks.key;
+      if (nvls_key) MXKV_CHECK(vec_ok) << "NVLS arrays must be 16-byte aligned";
       Replica& r = *rep[p];
       tw.w = r.local.data();
       tw.w32 = mp ? static_cast<float*>(r.w32.data()) : nullptr;
@@ -1228,7 +1254,7 @@ void KVStore::LaunchWorks(const LaunchClassKey& ck, std::vector<std::vector<Tens
   // that is a multiple of 4 elements (rank-independent facts only)
   int64_t chunk = rt->chunk_elems;
   int bulk = 0, bulk_stages = 0, bulk_arrays = 0, bulk_cap = 0;
-  if (rt->bulk_mode != 0 && ck.dtype == kFloat32) {
+  if (rt->bulk_mode != 0 && ck.dtype == kFloat32 && !ck.nvls) {
     bool ok = true;
     int max_src = 1;
     for (int p = my_first; p <= my_last; ++p)
@@ -1300,6 +1326,8 @@ void KVStore::LaunchWorks(const LaunchClassKey& ck, std::vector<std::vector<Tens
     L.chunk_elems = static_cast<int>(chunk);
     L.threads = rt->threads;
     L.bulk = bulk; L.bulk_stages = bulk_stages; L.bulk_arrays = bulk_arrays;
+    L.nvls = ck.nvls;
+    if (ck.nvls) { L.threads = 512; L.grid = static_cast<int>(std::min<int64_t>(DenseMaxGrid(dev, 512), max_chunks)); }
     int small_n = 1;
     for (auto& t : w) if (t.n_src > 2) small_n = 0;
     L.small_n = small_n;

@@ -77,10 +77,12 @@ int64_t ShardLen(int64_t size, int world);
 
 struct LaunchClassKey {
   int sync_mode, dtype, mp;
+  int nvls = 0;      // 1: multicast (multimem) kernel
   bool operator<(const LaunchClassKey& o) const {
     if (sync_mode != o.sync_mode) return sync_mode < o.sync_mode;
     if (dtype != o.dtype) return dtype < o.dtype;
-    return mp < o.mp;
+    if (mp != o.mp) return mp < o.mp;
+    return nvls < o.nvls;
   }
 };
 

@@ -27,6 +27,7 @@ Chunk::~Chunk() {
     case kOwnedHost: std::free(ptr); break;
     case kDLPack: if (dl && dl->deleter) dl->deleter(dl); break;
     case kSymmetric:   // bump-allocated from the arena; released with the process group
+    case kExternalSymmetric:
     case kExternal: break;
   }
 }
@@ -93,6 +94,17 @@ NDArray NDArray::FromExternal(void* ptr, const std::vector<int64_t>& shape, Cont
   a.chunk_->bytes = static_cast<size_t>(ShapeSize(shape)) * DTypeSize(dtype);
   a.chunk_->ctx = ctx;
   a.chunk_->kind = Chunk::kExternal;
+  return a;
+}
+
+NDArray NDArray::FromPeers(void* const* peer_ptrs, int world, int rank, void* mc_ptr,
+                           const std::vector<int64_t>& shape, Context ctx, int dtype) {
+  MXKV_CHECK(world >= 1 && world <= kMaxRanks && rank >= 0 && rank < world) << "bad peer table";
+  NDArray a = FromExternal(peer_ptrs[rank], shape, ctx, dtype);
+  a.chunk_->kind = Chunk::kExternalSymmetric;
+  for (int r = 0; r < world; ++r) a.chunk_->sym.ptr[r] = peer_ptrs[r];
+  a.chunk_->sym.valid = true;
+  a.chunk_->mc_ptr = mc_ptr;
   return a;
 }
 

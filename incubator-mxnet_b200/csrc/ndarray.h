@@ -13,13 +13,14 @@ struct DLManagedTensor;
 namespace mxkv {
 
 struct Chunk {
-  enum Kind { kOwnedCuda, kOwnedPinned, kOwnedHost, kSymmetric, kExternal, kDLPack };
+  enum Kind { kOwnedCuda, kOwnedPinned, kOwnedHost, kSymmetric, kExternal, kDLPack, kExternalSymmetric };
   void* ptr = nullptr;
   size_t bytes = 0;
   Context ctx;
   Kind kind = kExternal;
   DLManagedTensor* dl = nullptr;
-  SymPtr sym;                      // valid when kind == kSymmetric (MP mode)
+  SymPtr sym;                      // valid when kind == kSymmetric / kExternalSymmetric (MP mode)
+  void* mc_ptr = nullptr;          // NVSwitch multicast alias of the same bytes on every rank, if bound
   ~Chunk();
 };
 
@@ -38,7 +39,14 @@ class NDArray {
   void* data() const { return chunk_ ? static_cast<char*>(chunk_->ptr) + byte_offset_ : nullptr; }
   // pointer to the same bytes as mapped for peer `r` (symmetric chunks only)
   void* peer_data(int r) const;
-  bool symmetric() const { return chunk_ && chunk_->kind == Chunk::kSymmetric; }
+  bool symmetric() const {
+    return chunk_ && (chunk_->kind == Chunk::kSymmetric || chunk_->kind == Chunk::kExternalSymmetric);
+  }
+  // multicast (NVLS) address of element 0, or nullptr
+  void* mc_data() const { return (chunk_ && chunk_->mc_ptr) ? static_cast<char*>(chunk_->mc_ptr) + byte_offset_ : nullptr; }
+  // peer-mapped memory owned by the embedding framework (e.g. torch symmetric memory)
+  static NDArray FromPeers(void* const* peer_ptrs, int world, int rank, void* mc_ptr,
+                           const std::vector<int64_t>& shape, Context ctx, int dtype);
   const std::vector<int64_t>& shape() const { return shape_; }
   int64_t size() const { return ShapeSize(shape_); }
   size_t nbytes() const { return static_cast<size_t>(size()) * DTypeSize(dtype_); }

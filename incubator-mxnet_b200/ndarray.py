@@ -363,5 +363,40 @@ def empty_symmetric(shape, dtype=np.float32):
     return NDArray(out)
 
 
+def empty_multicast(shape, dtype=np.float32, group=None):
+    """Collective (one process per GPU): allocate through torch's symmetric memory -- plumbing that
+    creates the CUDA multicast object on NVSwitch systems -- and wrap the peer pointers and the
+    multicast alias.  Arrays created this way are exchanged by the NVLS kernel
+    (multimem.ld_reduce / multimem.st); without multicast support they behave like
+    ``empty_symmetric``.  Every rank must call it in the same order with the same shape."""
+    import torch
+    import torch.distributed as dist
+    import torch.distributed._symmetric_memory as symm_mem
+    if isinstance(shape, int):
+        shape = (shape,)
+    mxdt = _mx_dtype(dtype)
+    tdt = {0: torch.float32, 1: torch.float64, 2: torch.float16, 3: torch.uint8, 4: torch.int32, 5: torch.int8,
+           6: torch.int64, BFLOAT16: torch.bfloat16}[mxdt]
+    n = 1
+    for d in shape:
+        n *= d
+    t = symm_mem.empty(max(n, 1), dtype=tdt, device="cuda")
+    grp = group if group is not None else dist.group.WORLD
+    h = symm_mem.rendezvous(t, grp.group_name)
+    world = dist.get_world_size(grp)
+    ptrs = (ctypes.c_void_p * world)(*[int(p) for p in h.buffer_ptrs])
+    mc = int(h.multicast_ptr) if getattr(h, "multicast_ptr", 0) else 0
+    cshape = (ctypes.c_int64 * len(shape))(*shape)
+    out = ctypes.c_void_p()
+    check_call(_LIB.MXKVB200NDArrayFromPeers(ptrs, world, ctypes.c_void_p(mc), cshape, len(shape), mxdt,
+                                             ctypes.byref(out)))
+    return NDArray(out, keep=(t, h))
+
+
+def has_multicast(nd_array):
+    keep = nd_array._keep
+    return bool(keep) and isinstance(keep, tuple) and bool(getattr(keep[1], "multicast_ptr", 0))
+
+
 def waitall():
     check_call(_LIB.MXNDArrayWaitAll())

@@ -162,6 +162,49 @@ def main():
                for r in range(world)]
         assert bits_equal(out.asnumpy(), O.sum_device(deq)), ("compression", step)
 
+    # 7. NVLS: arrays bound to an NVSwitch multicast object -> multimem.ld_reduce / multimem.st kernel.
+    #    The switch's summation order is not left-to-right: tolerance 1e-6 relative (the reference's
+    #    own bound) against the oracle, and bit-identical replicas across ranks.
+    try:
+        probe = mx.nd.empty_multicast((1024,))
+        nvls = mx.nd.has_multicast(probe)
+    except Exception as e:          # torch symmetric memory unavailable: nothing to test
+        print("multicast unavailable:", repr(e), flush=True)
+        nvls = False
+    if nvls:
+        for optname, kw in ((None, {}), ("sgd", dict(learning_rate=0.1, momentum=0.9, wd=1e-4))):
+            shapes = [(1 << 10,), (3 * (1 << 16),), (1 << 21,)]
+            ks = list(range(len(shapes)))
+            kv7 = mx.kv.create("device")
+            w0 = [data(41 + k, s, 0) for k, s in zip(ks, shapes)]
+            kv7.init(ks, [mx.nd.array(w, ctx) for w in w0])
+            okv = O.OracleKVStore("device")
+            okv.init(ks, [w.copy() for w in w0])
+            if optname:
+                kv7.set_optimizer(mx.optimizer.create(optname, **kw))
+                okv.set_optimizer(O.OracleOptimizer(optname, **kw))
+            gm = [mx.nd.empty_multicast(s) for s in shapes]
+            om = [mx.nd.empty_multicast(s) for s in shapes]
+            before = mx.kv.launch_count()
+            for step in range(3):
+                for k, s in zip(ks, shapes):
+                    gm[k][:] = data(300 + 10 * step + k, s, rank)
+                torch.cuda.synchronize(); dist.barrier()
+                kv7.pushpull(ks, gm, out=om)
+                okv.push(ks, [[data(300 + 10 * step + k, s, r) for r in range(world)] for k, s in zip(ks, shapes)])
+                for k, s in zip(ks, shapes):
+                    want = np.empty(s, np.float32)
+                    okv.pull(k, want)
+                    got = om[k].asnumpy()
+                    err = np.abs(got.astype(np.float64) - want).sum() / max(np.abs(want).sum(), 1e-30)
+                    assert err < 1e-6, ("nvls", optname, step, k, err)
+                    chk = torch.from_numpy(got.view(np.int32).astype(np.int64)).sum().cuda().reshape(1)
+                    allc = [torch.empty_like(chk) for _ in range(world)]
+                    dist.all_gather(allc, chk)
+                    assert all(int(c) == int(chk) for c in allc), ("nvls replicas differ", optname, step, k)
+            assert mx.kv.launch_count() - before == 3, "one launch per pushpull expected"
+        print("NVLS_OK rank", rank, flush=True)
+
     mx.nd.waitall()
     dist.barrier()
     print("MP_WORKER_OK rank", rank, flush=True)

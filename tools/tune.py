@@ -29,10 +29,11 @@ def main():
     keys = list(range(len(shapes)))
     rng = np.random.default_rng(rank)
     nval = int(os.environ.get("TUNE_NVAL", 1))      # values per key on this GPU (emulates n sources)
-    grads = [mx.nd.empty_symmetric(s) for s in shapes]
+    alloc = mx.nd.empty_multicast if os.environ.get("TUNE_ALLOC", "symmetric") == "multicast" else mx.nd.empty_symmetric
+    grads = [alloc(s) for s in shapes]
     if nval > 1:
         grads = [[mx.nd.empty(s, mx.gpu(local)) for _ in range(nval)] for s in shapes]
-    weights = [mx.nd.empty_symmetric(s) for s in shapes]
+    weights = [alloc(s) for s in shapes]
     for g, s in zip(grads, shapes):
         for gg in (g if isinstance(g, list) else [g]):
             gg[:] = rng.uniform(-1, 1, s).astype(np.float32)
@@ -43,7 +44,7 @@ def main():
         kv.set_optimizer(mx.optimizer.SGD(learning_rate=0.01, momentum=0.9, wd=1e-4))
     elif opt == "adam":
         kv.set_optimizer(mx.optimizer.Adam())
-    configs = [(8192, 512, 0, 0), (8192, 512, 0, 1), (8192, 512, 0, 2)]
+    configs = [(8192, 512, 0, 1)]
     steps = 40
     for chunk, threads, mb, bulk in configs:
         check_call(_LIB.MXKVB200SetTuning(ctypes.c_int64(chunk), threads, mb, bulk))

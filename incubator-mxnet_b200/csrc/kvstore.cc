@@ -548,6 +548,46 @@ inline bool Overlap(const void* a, size_t an, const void* b, size_t bn) {
 inline bool Aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 }  // namespace
 
+// Outputs of one key that alias the pushed values of ANOTHER key of the same call (the reference's
+// tests do this: the same arrays are pushed for every key and pulled in place).  The reference runs
+// every reduce of a call before any pull (PushImpl then PullImpl, kvstore_local.h:358-365), so such
+// outputs must not be written by the fused kernel -- they are copied out after all kernels.
+namespace {
+class AliasIndex {
+ public:
+  template <typename Groups>
+  explicit AliasIndex(const Groups& groups) {
+    for (size_t gi = 0; gi < groups.size(); ++gi)
+      for (auto& v : groups[gi].vals) {
+        const char* b = static_cast<const char*>(v.data());
+        if (b != nullptr && v.nbytes() > 0) iv_.push_back({b, b + v.nbytes(), static_cast<int>(gi)});
+      }
+    std::sort(iv_.begin(), iv_.end(), [](const Iv& a, const Iv& b) { return a.b < b.b; });
+    // running maximum of interval ends for the overlap query
+    maxe_.resize(iv_.size());
+    const char* m = nullptr;
+    for (size_t i = 0; i < iv_.size(); ++i) { if (i == 0 || iv_[i].e > m) m = iv_[i].e; maxe_[i] = m; }
+  }
+  // does [p, p+n) overlap a pushed value of a group other than `gi`?
+  bool OverlapsOther(const void* p, size_t n, int gi) const {
+    if (iv_.empty() || p == nullptr || n == 0) return false;
+    const char* b = static_cast<const char*>(p);
+    const char* e = b + n;
+    // intervals with begin < e
+    size_t hi = std::lower_bound(iv_.begin(), iv_.end(), e, [](const Iv& a, const char* x) { return a.b < x; }) - iv_.begin();
+    for (size_t i = hi; i-- > 0;) {
+      if (maxe_[i] <= b) break;                 // nothing at or before i reaches into [b, e)
+      if (iv_[i].e > b && iv_[i].g != gi) return true;
+    }
+    return false;
+  }
+ private:
+  struct Iv { const char* b; const char* e; int g; };
+  std::vector<Iv> iv_;
+  std::vector<const char*> maxe_;
+};
+}  // namespace
+
 // Host-resident values and outputs (kv.create('local')-style use, and the end-to-end benchmark):
 // instead of "copy everything in, run, copy everything out" on one stream, every key is cut into
 // segments that flow through a three-stage pipeline on three streams -- H2D of segment i+1, the
@@ -577,6 +617,12 @@ bool KVStore::HostPipelined(std::vector<Group>& groups, bool write_outs) {
     total_bytes += static_cast<int64_t>(ks.size) * DTypeSize(ks.dtype) * g.vals.size();
   }
   if (total_bytes < (int64_t(1) << 20)) return false;      // latency-bound: the simple path is fine
+  if (write_outs && groups.size() > 1) {
+    AliasIndex alias(groups);
+    for (size_t gi = 0; gi < groups.size(); ++gi)
+      for (NDArray* o : groups[gi].outs)
+        if (alias.OverlapsOther(o->data(), o->nbytes(), static_cast<int>(gi))) return false;
+  }
 
   const bool fused = opt_.enabled;
   const int opt_kind = fused ? opt_.kind : OPT_NONE;
@@ -704,8 +750,10 @@ void KVStore::ReduceUpdateCompressed(std::vector<Group>& groups, bool write_outs
   auto touch = [&](int dev) { if (dev >= 0 && touched.insert(dev).second) rt->AcquireUser(dev); };
   std::vector<PostCopy> post;
   std::vector<std::pair<void*, int>> temps;
+  const AliasIndex alias(groups);
 
-  for (auto& g : groups) {
+  for (size_t gi = 0; gi < groups.size(); ++gi) {
+    auto& g = groups[gi];
     KeyState& ks = GetKey(g.key);
     MXKV_CHECK(ks.dtype == kFloat32) << "Gradient compression is only supported for float32";   // gradient_compression.cc
     const int n_src = static_cast<int>(g.vals.size());
@@ -807,7 +855,8 @@ void KVStore::ReduceUpdateCompressed(std::vector<Group>& groups, bool write_outs
         for (NDArray* o : g.outs) {
           MXKV_CHECK(o->size() == ks.size && o->dtype() == ks.dtype) << "pushpull: output does not match key " << ks.key;
           const Context oc = o->ctx();
-          if (oc.is_gpu() && oc.dev_id == dev && tw.n_out < kMaxOut) {
+          if (oc.is_gpu() && oc.dev_id == dev && tw.n_out < kMaxOut &&
+              !(groups.size() > 1 && alias.OverlapsOther(o->data(), o->nbytes(), static_cast<int>(gi)))) {
             tw.out[tw.n_out++] = o->data();
             vec_ok = vec_ok && ((reinterpret_cast<uintptr_t>(o->data()) & 15) == 0);
             written.insert(o);
@@ -883,6 +932,7 @@ void KVStore::ReduceUpdate(std::vector<Group>& groups, bool write_outs) {
   int n_part = 0;
   bool collective = false;
   int root_dev = -1;
+  const AliasIndex alias(groups);
 
   for (size_t gi = 0; gi < groups.size(); ++gi) {
     Group& g = groups[gi];
@@ -1075,6 +1125,8 @@ void KVStore::ReduceUpdate(std::vector<Group>& groups, bool write_outs) {
                 if (Overlap(o->data(), o->nbytes(), v.data(), v.nbytes())) direct = false;
             }
             if (direct && !Aligned16(o->data())) direct = false;
+            if (direct && groups.size() > 1 && alias.OverlapsOther(o->data(), o->nbytes(), static_cast<int>(gi)))
+              direct = false;
           }
           out_direct[oi] = direct ? 1 : 0;
           if (direct) --budget; else need_post = true;

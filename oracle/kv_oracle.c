@@ -488,6 +488,14 @@ void kvo_dequantize_1bit(int64_t E, const uint8_t* in, float* out, float thr) {
   }
 }
 
+void kvo_set_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 int kvo_max_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

@@ -445,8 +445,9 @@ def main():
         try:
             probe = mx.nd.empty_multicast((1024,))
             if mx.nd.has_multicast(probe):
-                alloc = mx.nd.empty_multicast          # NVSwitch multicast: multimem.ld_reduce / multimem.st
-                exchange = "nvls-multicast"
+                alloc = mx.nd.empty_multicast          # NVSwitch multicast-capable arrays
+                # the engine switches to the multimem kernel above 4 ranks (MXKVB200SetNvls)
+                exchange = "nvls-multicast" if world > 4 else "nvlink-p2p (multicast-capable arrays)"
         except Exception as e:                         # noqa: BLE001 -- torch symmetric memory unavailable
             sys.stderr.write("multicast allocation unavailable (%r): peer-load kernels\n" % (e,))
     grads = [alloc(s) for s in shapes]

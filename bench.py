@@ -333,7 +333,7 @@ def bench_rsp(args):
     out = mx.nd.empty((R, L), ctx, stype="row_sparse", capacity=nnz)
     kv = mx.kv.create("device")
     kv.init("emb", mx.nd.row_sparse_array((np.zeros((1, L), np.float32), np.zeros(1, np.int64)), shape=(R, L), ctx=ctx))
-    kv.set_optimizer(mx.optimizer.SGD(learning_rate=0.01, momentum=0.9, wd=0.0))
+    kv.set_optimizer(mx.optimizer.SGD(learning_rate=0.01, momentum=0.9, wd=0.0, lazy_update=True))
 
     def step():
         kv.push("emb", grad)

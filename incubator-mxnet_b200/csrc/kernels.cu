@@ -255,6 +255,21 @@ __device__ __forceinline__ float update_one(float g, float w, float& s0, float& 
     const float gr = __fmul_rn(h.rescale, g);
     const float s = __fadd_rn(gr, __fmul_rn(h.wd, w));
     return __fsub_rn(w, __fmul_rn(h.lr, s));
+  } else if (OPT == OPT_SGD_STD) {
+    // every row: w *= (1 - lr*wd); rows of the gradient: w -= lr * clip(rescale*g) (wd already applied)
+    const float ws = __fmul_rn(w, __fsub_rn(1.0f, __fmul_rn(h.lr, h.wd)));
+    float r = __fmul_rn(h.rescale, g);
+    if (h.clip >= 0.0f) r = clipf(r, h.clip);
+    r = __fadd_rn(r, __fmul_rn(0.0f, ws));
+    return __fsub_rn(ws, __fmul_rn(h.lr, r));
+  } else if (OPT == OPT_ADAM_STD) {
+    float r = __fmul_rn(g, h.rescale);
+    if (h.clip >= 0.0f) r = clipf(r, h.clip);
+    r = __fadd_rn(r, __fmul_rn(w, h.wd));
+    const float m = __fadd_rn(__fmul_rn(h.beta1, s0), __fmul_rn(__fsub_rn(1.f, h.beta1), r));
+    const float v = __fadd_rn(__fmul_rn(h.beta2, s1), __fmul_rn(__fsub_rn(1.f, h.beta2), __fmul_rn(r, r)));
+    s0 = m; s1 = v;
+    return __fsub_rn(w, __fdiv_rn(__fmul_rn(h.lr, m), __fadd_rn(__fsqrt_rn(v), h.eps)));
   }
   return g;  // OPT_NONE
 }
@@ -331,16 +346,16 @@ __device__ __forceinline__ void process_packets(const TensorWork& tw, const int6
         pw.load(tw.w, e[u]);
         pw.unpack(w[u]);
       }
-      if (OPT == OPT_SGD_MOM || OPT == OPT_ADAM || OPT == OPT_ADAMW) ldf<N>(tw.s0, e[u], s0[u]);
-      if (OPT == OPT_ADAM || OPT == OPT_ADAMW) ldf<N>(tw.s1, e[u], s1[u]);
+      if (OPT == OPT_SGD_MOM || OPT == OPT_ADAM || OPT == OPT_ADAMW || OPT == OPT_ADAM_STD) ldf<N>(tw.s0, e[u], s0[u]);
+      if (OPT == OPT_ADAM || OPT == OPT_ADAMW || OPT == OPT_ADAM_STD) ldf<N>(tw.s1, e[u], s1[u]);
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       if (!ok[u]) continue;
 #pragma unroll
       for (int i = 0; i < N; ++i) wnew[u][i] = update_one<OPT>(acc[u][i], w[u][i], s0[u][i], s1[u][i], h);
-      if (OPT == OPT_SGD_MOM || OPT == OPT_ADAM || OPT == OPT_ADAMW) stf<N>(tw.s0, e[u], s0[u]);
-      if (OPT == OPT_ADAM || OPT == OPT_ADAMW) stf<N>(tw.s1, e[u], s1[u]);
+      if (OPT == OPT_SGD_MOM || OPT == OPT_ADAM || OPT == OPT_ADAMW || OPT == OPT_ADAM_STD) stf<N>(tw.s0, e[u], s0[u]);
+      if (OPT == OPT_ADAM || OPT == OPT_ADAMW || OPT == OPT_ADAM_STD) stf<N>(tw.s1, e[u], s1[u]);
       if (MP) stf<N>(tw.w32, e[u], wnew[u]);
     }
   }
@@ -816,6 +831,8 @@ static DenseKernelFn pick_kernel(const DenseLaunch& L) {
         case OPT_ADAM: return pick_n<float, OPT_ADAM, false>(sn);
         case OPT_ADAMW: return pick_n<float, OPT_ADAMW, false>(sn);
         case OPT_TEST: return pick_n<float, OPT_TEST, false>(sn);
+        case OPT_SGD_STD: return kv_dense_kernel<float, OPT_SGD_STD, false, false>;
+        case OPT_ADAM_STD: return kv_dense_kernel<float, OPT_ADAM_STD, false, false>;
         default: return nullptr;
       }
     case kFloat16: return pick_opt<__half>(L.opt, mp, sn, false);

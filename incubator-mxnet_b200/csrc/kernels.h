@@ -30,7 +30,11 @@ enum OptKind : int {
   OPT_SGD_MOM = 2,  // SGDMomKernel / MP_SGDMomKernel        optimizer_op-inl.h:590-606,681-701
   OPT_ADAM = 3,     // AdamUpdateKernel                      optimizer_op-inl.h:1246-1269
   OPT_ADAMW = 4,    // MPAdamWKernel                         contrib/adamw-inl.h:101-124
-  OPT_TEST = 5      // mx.optimizer.Test                     python/mxnet/optimizer/optimizer.py:570-577
+  OPT_TEST = 5,     // mx.optimizer.Test                     python/mxnet/optimizer/optimizer.py:570-577
+  // standard (non-lazy) updates of a dense weight with a row_sparse gradient, applied to the
+  // densified gradient (absent rows = 0); arithmetic of the reference's *Std* sparse kernels
+  OPT_SGD_STD = 6,  // SGDUpdateDnsRspImpl, lazy_update=false: w*(1-lr*wd) then w - lr*g   optimizer_op-inl.h:471-515
+  OPT_ADAM_STD = 7  // AdamStdDnsRspDnsKernel: (1-beta2)*square(g)                          optimizer_op.cu:125-152
 };
 
 enum SumOrder : int {

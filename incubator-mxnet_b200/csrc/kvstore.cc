@@ -193,6 +193,7 @@ void KVStore::SetOptimizer(const std::string& name, const std::vector<std::pair<
     else if (k == "eta") c.eta = std::stof(v);
     else if (k == "rescale_grad") c.rescale = std::stof(v);
     else if (k == "clip_gradient") c.clip = (v == "None" || v.empty()) ? -1.f : std::stof(v);
+    else if (k == "lazy_update") c.lazy_update = (v == "True" || v == "true" || v == "1");
     else if (k == "correct_bias") c.correct_bias = (v == "True" || v == "true" || v == "1");
     else if (k == "multi_precision") c.multi_precision = (v == "True" || v == "true" || v == "1");
     else MXKV_FATAL() << "unknown optimizer argument '" << k << "'";

@@ -36,6 +36,7 @@ struct OptimizerConfig {
   float momentum = 0.f, eps = 1e-8f, eta = 1.f;
   float rescale = 1.f, clip = -1.f;
   bool multi_precision = false;
+  bool lazy_update = false;   // row_sparse gradients: touch only the rows present (sgd.py:78, adam.py:77 default False)
   bool correct_bias = true;   // AdamW only (python/mxnet/optimizer/adamW.py:80-88)
   std::unordered_map<int, double> lr_mult, wd_mult;
 };

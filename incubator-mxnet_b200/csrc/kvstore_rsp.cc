@@ -232,11 +232,12 @@ void KVStore::PushRowSparse(KeyState& ks, const std::vector<NDArray>& vals) {
     RspRowArgs A;
     std::memset(&A, 0, sizeof(A));
     A.out_idx = r.rsp_merged.idx_ptr();
-    A.out_val = (fused) ? nullptr : static_cast<float*>(r.rsp_merged.data());
+    const bool std_update = fused && !opt_.lazy_update;   // dense pass over every row (reference default)
+    A.out_val = (fused && !std_update) ? nullptr : static_cast<float*>(r.rsp_merged.data());
     A.d_nnz_out = r.rsp_merged.d_nnz();
     A.table = static_cast<float*>(r.local.data());
     A.row_len = L;
-    A.opt = fused ? opt_.kind : OPT_NONE;
+    A.opt = (fused && !std_update) ? opt_.kind : OPT_NONE;
     A.assign = (!fused && !callback) ? 1 : 0;
     A.lr = lr; A.wd = wd; A.rescale = opt_.rescale; A.clip = opt_.clip; A.momentum = opt_.momentum;
     A.beta1 = static_cast<float>(opt_.beta1); A.beta2 = static_cast<float>(opt_.beta2); A.eps = opt_.eps;
@@ -257,6 +258,27 @@ void KVStore::PushRowSparse(KeyState& ks, const std::vector<NDArray>& vals) {
                              static_cast<int32_t*>(r.rsp_pf.data()), r.rsp_cap, s), "rsp_sum");
     rt->launches += 3;
     r.rsp_merged.set_nnz_device();
+    if (std_update) {
+      // densify the merged gradient (absent rows = 0) and run the dense kernel with the reference's
+      // "Std" arithmetic over the whole table: O(table), as in the reference
+      float* gd = nullptr;
+      CUDA_CALL(cudaMallocAsync(reinterpret_cast<void**>(&gd), static_cast<size_t>(ks.size) * 4, s));
+      CUDA_CALL(cudaMemsetAsync(gd, 0, static_cast<size_t>(ks.size) * 4, s));
+      CheckLaunch(LaunchRspScatter(gd, r.rsp_merged.idx_ptr(), r.rsp_merged.d_nnz(), r.rsp_merged.cap_rows(), L,
+                                   static_cast<const float*>(r.rsp_merged.data()), s), "rsp_scatter");
+      TensorWork tw;
+      std::memset(&tw, 0, sizeof(tw));
+      tw.src[0] = gd; tw.n_src = 1;
+      tw.out[0] = r.local.data(); tw.n_out = 1;
+      tw.w = r.local.data();
+      tw.s0 = A.s0; tw.s1 = A.s1;
+      tw.begin = 0; tw.end = ks.size;
+      tw.lr = lr; tw.wd = wd; tw.eta = opt_.eta;
+      tw.pad_ = (ks.size % 4 == 0 && Aligned16(r.local.data())) ? 1 : 0;
+      const int kind = opt_.kind == OPT_SGD ? OPT_SGD_STD : (opt_.kind == OPT_ADAM ? OPT_ADAM_STD : opt_.kind);
+      LaunchLocal(LaunchClassKey{SYNC_NONE, kFloat32, 0}, tw, kind, dev);
+      CUDA_CALL(cudaFreeAsync(gd, s));
+    }
     for (void* t : temps) CUDA_CALL(cudaFreeAsync(t, s));
     r.fresh = true;
   }
@@ -322,7 +344,6 @@ void KVStore::PullRowSparseImpl(const std::vector<int>& keys,
     MXKV_CHECK(ks.stype == kRowSparseStorage) << "PullRowSparse expects row_sparse src NDArray";
     MXKV_CHECK(row_id.dtype() == kInt64) << "row_ids must be int64";
     const int64_t n = row_id.size();
-    MXKV_CHECK(n <= RspUniqueMax()) << "row_sparse_pull of more than " << RspUniqueMax() << " row ids per call";
     const int64_t L = ks.size / ks.shape[0];
     const Context oc = out->ctx();
     const Context rc = row_id.ctx();

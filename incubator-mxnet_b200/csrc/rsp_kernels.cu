@@ -262,6 +262,63 @@ rsp_unique_kernel(const int64_t* in, int64_t n, int64_t* out, int64_t* d_count) 
   if (threadIdx.x == 0) *d_count = carry;
 }
 
+// ---- large id lists (> kUniqueMax): bitonic sort in global memory, one launch per (k, j) step, then
+// a single-block chunked compaction.  Rare path (the reference sorts with cub); correctness first.
+__global__ void rsp_pad_kernel(const int64_t* in, int64_t n, int64_t* buf, int64_t npad) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < npad;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    buf[i] = i < n ? in[i] : INT64_MAX;
+}
+
+__global__ void rsp_bitonic_step_kernel(int64_t* buf, int64_t npad, int64_t k, int64_t j) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < npad;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t l = i ^ j;
+    if (l > i) {
+      const bool up = (i & k) == 0;
+      const int64_t a = buf[i], b = buf[l];
+      if ((a > b) == up) { buf[i] = b; buf[l] = a; }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(1024)
+rsp_compact_sorted_kernel(const int64_t* sorted, int64_t n, int64_t* out, int64_t* d_count) {
+  __shared__ int32_t warp_sums[32];
+  __shared__ int64_t carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  for (int64_t base = 0; base < n; base += blockDim.x) {
+    const int64_t i = base + threadIdx.x;
+    const int32_t v = (i < n && (i == 0 || sorted[i] != sorted[i - 1])) ? 1 : 0;
+    int32_t x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int32_t y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) warp_sums[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+      int32_t w = lane < nwarp ? warp_sums[lane] : 0;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int32_t y = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += y;
+      }
+      warp_sums[lane] = w;
+    }
+    __syncthreads();
+    const int64_t before = carry + (warp > 0 ? warp_sums[warp - 1] : 0);
+    if (v) out[before + x - 1] = sorted[i];
+    __syncthreads();
+    if (threadIdx.x == 0) carry += warp_sums[nwarp - 1];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *d_count = carry;
+}
+
 // out_val[j, :] = table[ids[j], :]  (the stored value is dense-backed: SparseRetain's "input rsp
 // is dense" branch, sparse_retain-inl.h:286-311); one warp per row
 __global__ void __launch_bounds__(256)
@@ -335,7 +392,20 @@ int LaunchRspSum(const RspSources& S, const RspRowArgs& A, int32_t* first, int32
 int RspUniqueMax() { return kUniqueMax; }
 
 int LaunchRspUnique(const int64_t* ids, int64_t n, int64_t* out, int64_t* d_count, cudaStream_t stream) {
-  if (n > kUniqueMax) return static_cast<int>(cudaErrorInvalidValue);
+  if (n > kUniqueMax) {
+    int64_t npad = 1;
+    while (npad < n) npad <<= 1;
+    int64_t* buf = nullptr;
+    cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&buf), static_cast<size_t>(npad) * 8, stream);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    const int grid = grid_for(npad, 256);
+    rsp_pad_kernel<<<grid, 256, 0, stream>>>(ids, n, buf, npad);
+    for (int64_t k = 2; k <= npad; k <<= 1)
+      for (int64_t j = k >> 1; j > 0; j >>= 1) rsp_bitonic_step_kernel<<<grid, 256, 0, stream>>>(buf, npad, k, j);
+    rsp_compact_sorted_kernel<<<1, 1024, 0, stream>>>(buf, n, out, d_count);
+    cudaFreeAsync(buf, stream);
+    return static_cast<int>(cudaGetLastError());
+  }
   if (n == 0) {
     rsp_set_i64_kernel<<<1, 1, 0, stream>>>(d_count, 0);
     return static_cast<int>(cudaGetLastError());

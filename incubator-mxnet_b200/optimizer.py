@@ -125,6 +125,7 @@ class SGD(Optimizer):
     def fused_kwargs(self):
         kw = super(SGD, self).fused_kwargs()
         kw["momentum"] = self.momentum
+        kw["lazy_update"] = bool(self.lazy_update)
         return kw
 
     def create_state(self, index, weight):
@@ -153,7 +154,7 @@ class Adam(Optimizer):
 
     def fused_kwargs(self):
         kw = super(Adam, self).fused_kwargs()
-        kw.update(beta1=self.beta1, beta2=self.beta2, epsilon=self.epsilon)
+        kw.update(beta1=self.beta1, beta2=self.beta2, epsilon=self.epsilon, lazy_update=bool(self.lazy_update))
         return kw
 
     def create_state(self, index, weight):

@@ -430,6 +430,38 @@ void kvo_adam_rsp_lazy_f32(float* w, float* mean, float* var, int64_t L, const i
   }
 }
 
+/* Standard (lazy_update=false) updates of a dense weight with a row_sparse gradient.
+ * SGD without momentum, SGDUpdateDnsRspImpl optimizer_op-inl.h:471-515: every row is first scaled by
+ * (1 - lr*wd) (float arithmetic), then the rows of the gradient get w -= lr*clip(rescale*g) with wd = 0. */
+void kvo_sgd_std_rsp_f32(float* w, int64_t R, int64_t L, const int64_t* gidx, const float* gval,
+                         int64_t nnz, float lr, float wd, float rescale, float clip) {
+  const float c = 1 - lr * wd;
+  for (int64_t i = 0; i < R * L; ++i) w[i] = w[i] * c;
+  for (int64_t r = 0; r < nnz; ++r) {
+    float* wr = w + gidx[r] * L; const float* gr = gval + r * L;
+    for (int64_t j = 0; j < L; ++j) {
+      float x = rescale * gr[j];
+      if (clip >= 0.0f) x = clipf(x, clip);
+      x += 0.0f * wr[j];
+      wr[j] = wr[j] - (lr * x);
+    }
+  }
+}
+/* AdamStdDnsRspDnsKernel, optimizer_op.cu:125-152, on the densified gradient (absent rows = 0):
+ * as AdamUpdateKernel but the second moment uses (1-beta2)*square(g). */
+void kvo_adam_std_update_f32(int64_t E, float* w, float* mean, float* var, const float* g, float lr,
+                             float wd, float beta1, float beta2, float eps, float rescale, float clip) {
+  for (int64_t i = 0; i < E; ++i) {
+    float r = g[i] * rescale;
+    if (clip >= 0.f) r = clipf(r, clip);
+    r += w[i] * wd;
+    float m = beta1 * mean[i] + (1.f - beta1) * r;
+    float v = beta2 * var[i] + (1.f - beta2) * (r * r);
+    mean[i] = m; var[i] = v;
+    w[i] = w[i] - lr * m / (sqrtf(v) + eps);
+  }
+}
+
 /* ===================================================================== */
 /* Gradient compression (src/kvstore/gradient_compression-inl.h:44-227)    */
 /* ===================================================================== */

@@ -287,6 +287,19 @@ def sgd_rsp_lazy(w, grad, lr, wd=0.0, rescale=1.0, clip=None, mom=None, momentum
                                        _clip(clip))
 
 
+def sgd_std_rsp(w, grad, lr, wd=0.0, rescale=1.0, clip=None):
+    L = int(np.prod(w.shape[1:]))
+    gv = np.ascontiguousarray(grad.data.reshape(-1, L))
+    lib().kvo_sgd_std_rsp_f32(_ptr(w, c_f32p), _I64(w.shape[0]), _I64(L), _ptr(grad.indices, c_i64p),
+                              _ptr(gv, c_f32p), _I64(len(grad.indices)), _F(lr), _F(wd), _F(rescale), _clip(clip))
+
+
+def adam_std_update(w, gdense, mean, var, lr, wd=0.0, beta1=0.9, beta2=0.999, eps=1e-8, rescale=1.0, clip=None):
+    lib().kvo_adam_std_update_f32(_I64(w.size), _ptr(w, c_f32p), _ptr(mean, c_f32p), _ptr(var, c_f32p),
+                                  _ptr(gdense, c_f32p), _F(lr), _F(wd), _F(beta1), _F(beta2), _F(eps),
+                                  _F(rescale), _clip(clip))
+
+
 def adam_rsp_lazy(w, grad, mean, var, lr, wd=0.0, beta1=0.9, beta2=0.999, eps=1e-8, rescale=1.0, clip=None):
     L = int(np.prod(w.shape[1:]))
     gv = np.ascontiguousarray(grad.data.reshape(-1, L))
@@ -371,7 +384,15 @@ class OracleOptimizer(object):
             if self.momentum != 0.0 and index not in self.states:
                 self.states[index] = np.zeros_like(weight)
             mom = self.states.get(index)
-            if sparse:
+            if sparse and not self.lazy_update:
+                # standard update (sgd.py default lazy_update=False): optimizer_op-inl.h:471-515 /
+                # SGDMomStdDnsRspDnsKernel optimizer_op.cu:32-57 (= the dense kernel on the densified grad)
+                if mom is None:
+                    sgd_std_rsp(weight, grad, lr, wd, self.rescale_grad, self.clip_gradient)
+                else:
+                    sgd_mom_update(weight, np.ascontiguousarray(grad.todense()), mom, lr, wd, self.momentum,
+                                   self.rescale_grad, self.clip_gradient)
+            elif sparse:
                 sgd_rsp_lazy(weight, grad, lr, wd, self.rescale_grad, self.clip_gradient, mom, self.momentum)
             elif mom is None:
                 sgd_update(weight, grad, lr, wd, self.rescale_grad, self.clip_gradient)
@@ -382,7 +403,10 @@ class OracleOptimizer(object):
                 self.states[index] = (np.zeros_like(weight), np.zeros_like(weight))
             mean, var = self.states[index]
             lr = adam_lr(lr, self.beta1, self.beta2, t)
-            if sparse:
+            if sparse and not self.lazy_update:
+                adam_std_update(weight, np.ascontiguousarray(grad.todense()), mean, var, lr, wd, self.beta1,
+                                self.beta2, self.epsilon, self.rescale_grad, self.clip_gradient)
+            elif sparse:
                 adam_rsp_lazy(weight, grad, mean, var, lr, wd, self.beta1, self.beta2, self.epsilon,
                               self.rescale_grad, self.clip_gradient)
             else:

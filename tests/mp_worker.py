@@ -126,7 +126,7 @@ def main():
     rows, L, nnz = 3000, 64, 200
     shape = (rows, L)
     w0 = data(31, shape, 0)
-    kw = dict(learning_rate=0.1, momentum=0.9, wd=1e-4)
+    kw = dict(learning_rate=0.1, momentum=0.9, wd=1e-4, lazy_update=True)
     kv5 = mx.kv.create("device")
     kv5.init("emb", mx.nd.row_sparse_array(w0, ctx=ctx))
     kv5.set_optimizer(mx.optimizer.SGD(**kw))

@@ -48,7 +48,7 @@ def test_row_sparse_pull_retain():
     table = rng.uniform(-1, 1, shape).astype(np.float32)
     kv = mx.kv.create("device")
     kv.init("e", mx.nd.row_sparse_array(table, ctx=mx.gpu(0)))
-    for count in (1, 7, 300, 1000):
+    for count in (1, 7, 300, 1000, 40000):      # 40000 > 16384: global-memory sort path
         ids = rng.integers(0, rows, count).astype(np.int64)
         out = mx.nd.empty(shape, mx.gpu(0), stype="row_sparse", capacity=max(count, 1))
         kv.row_sparse_pull("e", out=out, row_ids=mx.nd.array(ids, mx.gpu(0), dtype=np.int64))
@@ -64,14 +64,18 @@ def test_row_sparse_pull_retain():
         assert _bits_equal(dense[r], table[r] if r in ids else np.zeros(L, np.float32))
 
 
+@pytest.mark.parametrize("lazy", [True, False])
 @pytest.mark.parametrize("optname,kw", [
     ("sgd", dict(learning_rate=0.1, wd=1e-3, rescale_grad=0.5, clip_gradient=0.6)),
     ("sgd", dict(learning_rate=0.1, wd=1e-3, momentum=0.9)),
     ("adam", dict(learning_rate=0.01, wd=1e-3)),
 ])
-def test_fused_lazy_sparse_update(optname, kw):
-    """lazy update: only the rows present in the summed gradient are touched
-    (SGDDnsRspKernel / SGDMomDnsRspDnsKernel / AdamDnsRspDnsKernel)."""
+def test_fused_sparse_update(optname, kw, lazy):
+    """lazy_update=True: only the rows present in the summed gradient are touched (SGDDnsRspKernel /
+    SGDMomDnsRspDnsKernel / AdamDnsRspDnsKernel); lazy_update=False (the reference default): the
+    standard update over every row (SGDUpdateDnsRspImpl non-lazy branch, SGDMomStdDnsRspDnsKernel,
+    AdamStdDnsRspDnsKernel)."""
+    kw = dict(kw, lazy_update=lazy)
     rng = np.random.default_rng(11)
     rows, L, nnz, n = 2000, 64, 150, 4
     shape = (rows, L)
@@ -134,7 +138,7 @@ def test_sp_multi_gpu_sources():
     rows, L, nnz = 5000, 128, 400
     shape = (rows, L)
     w0 = rng.uniform(0, 1, shape).astype(np.float32)
-    kw = dict(learning_rate=0.1, momentum=0.9, wd=1e-4)
+    kw = dict(learning_rate=0.1, momentum=0.9, wd=1e-4, lazy_update=True)
     kv = mx.kv.create("device")
     kv.init(0, mx.nd.row_sparse_array(w0, ctx=mx.gpu(0)))
     kv.set_optimizer(mx.optimizer.SGD(**kw))

@@ -779,14 +779,6 @@ kv_sum_typed_kernel(DenseLaunch L) {
   if (sync) barrier_end(L.sync, L.sync.mode == SYNC_WRITE_PEERS);
 }
 
-__global__ void kv_fill_kernel(uint4* p, uint32_t word, size_t n16, uint8_t* tail, int ntail, uint8_t b) {
-  const uint4 v = make_uint4(word, word, word, word);
-  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n16;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x)
-    p[i] = v;
-  if (blockIdx.x == 0 && threadIdx.x < ntail) tail[threadIdx.x] = b;
-}
-
 // ---------------------------------------------------------------------------
 // host launchers
 // ---------------------------------------------------------------------------

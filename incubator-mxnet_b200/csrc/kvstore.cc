@@ -1013,7 +1013,7 @@ void KVStore::ReduceUpdate(std::vector<Group>& groups, bool write_outs) {
 
     const bool two_shot = collective && static_cast<int64_t>(ks.size * esize) >= rt->twoshot_bytes &&
                           ks.size >= static_cast<int64_t>(n_part) * 128;
-    if (ks.local_world > 0 && !(two_shot && ks.local_world == n_part && ks.shard_devs == part_dev)) {
+    if (ks.local_world > 0 && (callback || !(two_shot && ks.local_world == n_part && ks.shard_devs == part_dev))) {
       GatherLocal(ks);
       for (int p = my_first; p <= my_last; ++p) rep[p] = &EnsureReplica(ks, part_dev[p]);
       for (int p = my_first; p <= my_last; ++p) rep[p] = FindReplica(ks, part_dev[p]);

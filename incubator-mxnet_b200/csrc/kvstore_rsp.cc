@@ -27,12 +27,6 @@ void CheckLaunch(int rc, const char* what) {
   Runtime::Get()->launches++;
 }
 
-// device-side view of a row_sparse NDArray living on (or staged to) GPU `dev`
-struct RspView {
-  const int64_t* idx;
-  const float* val;
-  const int64_t* nnz;
-};
 }  // namespace
 
 // make sure the device scalar of a row_sparse array mirrors its host-known row count

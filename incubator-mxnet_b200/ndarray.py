@@ -327,6 +327,22 @@ def row_sparse_array(arg, shape=None, ctx=None, dtype=np.float32, capacity=None)
     return out
 
 
+def from_dlpack(obj):
+    """Zero-copy import of a DLPack producer (an object with ``__dlpack__`` such as a torch tensor
+    or an MXNet NDArray, or a raw ``dltensor`` PyCapsule) through MXNDArrayFromDLPack
+    (include/mxnet/c_api.h:993).  The producer's memory is kept alive until the NDArray is freed."""
+    cap = obj.__dlpack__() if hasattr(obj, "__dlpack__") else obj
+    ctypes.pythonapi.PyCapsule_GetPointer.restype = ctypes.c_void_p
+    ctypes.pythonapi.PyCapsule_GetPointer.argtypes = [ctypes.py_object, ctypes.c_char_p]
+    ptr = ctypes.pythonapi.PyCapsule_GetPointer(cap, b"dltensor")
+    out = ctypes.c_void_p()
+    check_call(_LIB.MXNDArrayFromDLPack(ctypes.c_void_p(ptr), ctypes.c_bool(False), ctypes.byref(out)))
+    # ownership of the DLManagedTensor moved to the NDArray: mark the capsule as consumed
+    ctypes.pythonapi.PyCapsule_SetName.argtypes = [ctypes.py_object, ctypes.c_char_p]
+    ctypes.pythonapi.PyCapsule_SetName(cap, b"used_dltensor")
+    return NDArray(out, keep=cap)
+
+
 _TORCH_TO_MX = None
 
 

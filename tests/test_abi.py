@@ -113,3 +113,21 @@ def test_optimizer_descriptors():
         kv.set_gradient_compression({"type": "3bit"})
     assert mx.kv.KVStore.is_capable("optimizer")
     assert isinstance(mx.kv.create("b200device"), mx.kv.KVStore)      # registry path, base.py:450-452
+
+
+def test_dlpack_roundtrip_on_host():
+    """MXNDArrayFromDLPack / MXNDArrayToDLPack (c_api.h:976-1002) with host tensors: zero copy both ways."""
+    import torch
+    t = torch.arange(12, dtype=torch.float32).reshape(3, 4)
+    a = mx.nd.from_dlpack(t)
+    assert a.shape == (3, 4) and a.context.device_type == "cpu"
+    assert a.data_ptr == t.data_ptr()
+    assert np.array_equal(a.asnumpy(), t.numpy())
+    back = a.as_torch()
+    back[0, 0] = 42.0
+    assert t[0, 0].item() == 42.0            # same memory
+    kv = mx.kv.create("local")
+    kv.init("w", a)                           # host value parked in the store (no GPU needed)
+    out = mx.nd.zeros((3, 4))
+    kv.pull("w", out=out)
+    assert out.asnumpy()[0, 0] == 42.0

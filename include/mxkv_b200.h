@@ -130,15 +130,31 @@ MXKV_DLL int MXKVStoreGetNumDeadNode(KVStoreHandle handle, const int node_id, in
 /* ---- B200 extensions ------------------------------------------------------ */
 /* Fused optimizer: what Python's Updater + sgd_update/adam_update ops do per key in the
  * reference (python/mxnet/optimizer/updater.py:39-93) happens inside the reduce kernel.
- * name: "sgd" | "adam" | "adamw" | "test"; kwargs use the reference's hyper-parameter names
- * (learning_rate, wd, momentum, rescale_grad, clip_gradient, beta1, beta2, epsilon, eta,
- * multi_precision). */
+ * name: "sgd" | "adam" | "adamw" | "test" | "lamb" | "lans" | "lars"; kwargs use the reference's
+ * hyper-parameter names (learning_rate, wd, momentum, rescale_grad, clip_gradient, beta1, beta2,
+ * epsilon, eta, multi_precision, lazy_update, correct_bias, lower_bound, upper_bound,
+ * bias_correction).  lamb / lans / lars additionally take skip_nonfinite=True: when any merged
+ * gradient of a push holds inf/nan, that push changes neither weights nor optimizer state (the AMP
+ * overflow skip of gluon/trainer.py:445-448, decided on the device inside the same launch sequence). */
 MXKV_DLL int MXKVB200SetOptimizer(KVStoreHandle handle, const char* name, uint32_t num_params,
                                   const char** keys, const char** vals);
 MXKV_DLL int MXKVB200SetLearningRate(KVStoreHandle handle, double lr);
 /* per-key multipliers (Optimizer.set_lr_mult / set_wd_mult); pass str_key = NULL for int keys */
 MXKV_DLL int MXKVB200SetOptimizerMult(KVStoreHandle handle, int key, const char* str_key,
                                       float lr_mult, float wd_mult);
+/* per-key switch of a fused optimizer.  "no_trust_ratio" != 0: LARS keeps the plain learning rate
+ * for this key (the reference does so for names ending in gamma / beta / bias, lars.py:121-123). */
+MXKV_DLL int MXKVB200SetKeyFlag(KVStoreHandle handle, int key, const char* str_key, const char* name,
+                                int value);
+/* skip_nonfinite: *out = 1 if the last push met a non-finite gradient and was therefore skipped.
+ * Waits for the engine streams, takes the skipped step back out of the update counts and clears the
+ * flag (the next push does the same implicitly). */
+MXKV_DLL int MXKVB200GetOverflow(KVStoreHandle handle, int* out);
+/* multi_sum_sq (src/operator/contrib/multi_sum_sq-inl.h:83-96): out[i] = sum((scale * arrays[i])^2),
+ * float32 [num] on the arrays' GPU; and multi_all_finite (src/operator/all_finite.cu:68-103):
+ * out[0] = 0 if any element of any array is inf/nan (init_output != 0: out[0] is set to 1 first). */
+MXKV_DLL int MXKVB200MultiSumSq(uint32_t num, NDArrayHandle* arrays, float scale, NDArrayHandle out);
+MXKV_DLL int MXKVB200MultiAllFinite(uint32_t num, NDArrayHandle* arrays, int init_output, NDArrayHandle out);
 /* which: 0 stored value, 1 fp32 master weight, 2 state0 (momentum | mean), 3 state1 (variance).
  * Returns a NEW handle aliasing engine memory (free it with MXNDArrayFree); *out = NULL when the
  * state does not exist. */

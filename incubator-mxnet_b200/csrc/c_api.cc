@@ -482,6 +482,37 @@ int MXKVB200SetUpdateCount(KVStoreHandle handle, int key, const char* str_key, i
   API_END();
 }
 
+int MXKVB200SetKeyFlag(KVStoreHandle handle, int key, const char* str_key, const char* name, int value) {
+  API_BEGIN();
+  MXKV_CHECK(name != nullptr) << "flag name is null";
+  KV(handle)->SetKeyFlag(str_key != nullptr, key, str_key ? str_key : "", name, value);
+  API_END();
+}
+
+int MXKVB200GetOverflow(KVStoreHandle handle, int* out) {
+  API_BEGIN();
+  *out = KV(handle)->ResolveOverflow();
+  API_END();
+}
+
+int MXKVB200MultiSumSq(uint32_t num, NDArrayHandle* arrays, float scale, NDArrayHandle out) {
+  API_BEGIN();
+  std::vector<NDArray> a;
+  for (uint32_t i = 0; i < num; ++i) a.push_back(*ND(arrays[i]));
+  NDArray o = *ND(out);
+  MultiSumSq(a, scale, &o, nullptr, false);
+  API_END();
+}
+
+int MXKVB200MultiAllFinite(uint32_t num, NDArrayHandle* arrays, int init_output, NDArrayHandle out) {
+  API_BEGIN();
+  std::vector<NDArray> a;
+  for (uint32_t i = 0; i < num; ++i) a.push_back(*ND(arrays[i]));
+  NDArray o = *ND(out);
+  MultiSumSq(a, 1.0f, nullptr, &o, init_output != 0);
+  API_END();
+}
+
 int MXKVB200NDArrayFromPtr(void* data, const int64_t* shape, int ndim, int dev_type, int dev_id, int dtype,
                            NDArrayHandle* out) {
   API_BEGIN();

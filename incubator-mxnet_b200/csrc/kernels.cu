@@ -18,261 +18,11 @@
 // restates the reference source operation by operation.
 #include "kernels.h"
 #include "rsp_kernels.h"
-#include <cuda_fp16.h>
-#include <cuda_bf16.h>
+#include "device_utils.cuh"
 #include <cstdio>
 #include <cstdlib>
 
 namespace mxkv {
-
-constexpr int kThreads = 512;
-
-// ---------------------------------------------------------------------------
-// memory helpers
-// ---------------------------------------------------------------------------
-__device__ __forceinline__ uint4 ld16(const void* p) {
-  uint4 v;
-  asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st16(void* p, const uint4& v) {
-  asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};"
-               :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
-__device__ __forceinline__ void st_flag_volatile(uint32_t* p, uint32_t v) {
-  asm volatile("st.volatile.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint32_t ld_flag_volatile(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_flag_release(uint32_t* p, uint32_t v) {
-  asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint32_t ld_flag_acquire(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-
-// ---------------------------------------------------------------------------
-// cross-GPU rendezvous.  Block b of every rank pairs with block b of every other
-// rank: thread i<world stores the block's next flag value into rank i's pad and
-// spins on the slot rank i writes in ours.  Separate start/end slots so a fast
-// rank's next start cannot overwrite a slow rank's pending end.
-// ---------------------------------------------------------------------------
-// A peer that never shows up (its launch failed, its process died) must not hang this GPU for
-// ever: after `timeout` clock cycles the kernel traps and the host sees a CUDA error.
-__device__ __forceinline__ void spin_check(long long t0, long long timeout) {
-  if (timeout > 0 && clock64() - t0 > timeout) __trap();
-}
-
-__device__ __forceinline__ void barrier_start(const SyncArgs& s) {
-  const uint32_t flag = s.self[kSigFlagOff + blockIdx.x] + 1;
-  if (threadIdx.x < s.world) {
-    uint32_t* peer = s.peers[threadIdx.x] + kSigStartOff + blockIdx.x * kMaxRanks + s.rank;
-    const uint32_t* mine = s.self + kSigStartOff + blockIdx.x * kMaxRanks + threadIdx.x;
-    st_flag_volatile(peer, flag);
-    const long long t0 = clock64();
-    while (ld_flag_volatile(mine) != flag) spin_check(t0, s.timeout);
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) s.self[kSigFlagOff + blockIdx.x] = flag;
-}
-
-// release == true: this block stored into peer memory; make those stores visible
-// system-wide before signalling (two-shot all-gather half).
-__device__ __forceinline__ void barrier_end(const SyncArgs& s, bool release) {
-  __syncthreads();
-  const uint32_t flag = s.self[kSigFlagOff + blockIdx.x] + 1;
-  if (threadIdx.x < s.world) {
-    uint32_t* peer = s.peers[threadIdx.x] + kSigEndOff + blockIdx.x * kMaxRanks + s.rank;
-    const uint32_t* mine = s.self + kSigEndOff + blockIdx.x * kMaxRanks + threadIdx.x;
-    const long long t0 = clock64();
-    if (release) {
-      st_flag_release(peer, flag);
-      while (ld_flag_acquire(mine) != flag) spin_check(t0, s.timeout);
-    } else {
-      st_flag_volatile(peer, flag);
-      while (ld_flag_volatile(mine) != flag) spin_check(t0, s.timeout);
-    }
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) s.self[kSigFlagOff + blockIdx.x] = flag;
-}
-
-// ---------------------------------------------------------------------------
-// packets: a 16-byte vector or a single element, exposed as N floats
-// ---------------------------------------------------------------------------
-template <typename T> struct Cvt;
-template <> struct Cvt<float> {
-  __device__ static __forceinline__ float to(float v) { return v; }
-  __device__ static __forceinline__ float from(float v) { return v; }
-};
-template <> struct Cvt<__half> {
-  __device__ static __forceinline__ float to(__half v) { return __half2float(v); }
-  __device__ static __forceinline__ __half from(float v) { return __float2half_rn(v); }
-};
-template <> struct Cvt<__nv_bfloat16> {
-  __device__ static __forceinline__ float to(__nv_bfloat16 v) { return __bfloat162float(v); }
-  __device__ static __forceinline__ __nv_bfloat16 from(float v) { return __float2bfloat16_rn(v); }
-};
-
-__device__ __forceinline__ uint2 ld8(const void* p) {
-  uint2 v;
-  asm volatile("ld.global.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st8(void* p, const uint2& v) {
-  asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1,%2};" :: "l"(p), "r"(v.x), "r"(v.y) : "memory");
-}
-
-// Packet<T, N>: N consecutive elements (N*sizeof(T) in {16, 8} bytes, or N == 1)
-template <typename T, int N, int BYTES = N * sizeof(T)> struct Packet;
-template <typename T, int N_> struct Packet<T, N_, 16> {
-  static constexpr int N = N_;
-  uint4 raw;
-  __device__ __forceinline__ void load(const void* base, int64_t elem) {
-    raw = ld16(reinterpret_cast<const T*>(base) + elem);
-  }
-  __device__ __forceinline__ void unpack(float (&f)[N]) const {
-    const T* t = reinterpret_cast<const T*>(&raw);
-#pragma unroll
-    for (int i = 0; i < N; ++i) f[i] = Cvt<T>::to(t[i]);
-  }
-  __device__ static __forceinline__ void store(void* base, int64_t elem, const float (&f)[N]) {
-    uint4 v;
-    T* t = reinterpret_cast<T*>(&v);
-#pragma unroll
-    for (int i = 0; i < N; ++i) t[i] = Cvt<T>::from(f[i]);
-    st16(reinterpret_cast<T*>(base) + elem, v);
-  }
-};
-template <typename T, int N_> struct Packet<T, N_, 8> {
-  static constexpr int N = N_;
-  uint2 raw;
-  __device__ __forceinline__ void load(const void* base, int64_t elem) {
-    raw = ld8(reinterpret_cast<const T*>(base) + elem);
-  }
-  __device__ __forceinline__ void unpack(float (&f)[N]) const {
-    const T* t = reinterpret_cast<const T*>(&raw);
-#pragma unroll
-    for (int i = 0; i < N; ++i) f[i] = Cvt<T>::to(t[i]);
-  }
-  __device__ static __forceinline__ void store(void* base, int64_t elem, const float (&f)[N]) {
-    uint2 v;
-    T* t = reinterpret_cast<T*>(&v);
-#pragma unroll
-    for (int i = 0; i < N; ++i) t[i] = Cvt<T>::from(f[i]);
-    st8(reinterpret_cast<T*>(base) + elem, v);
-  }
-};
-template <typename T, int BYTES> struct Packet<T, 1, BYTES> {
-  static constexpr int N = 1;
-  T raw;
-  __device__ __forceinline__ void load(const void* base, int64_t elem) {
-    raw = reinterpret_cast<const T*>(base)[elem];
-  }
-  __device__ __forceinline__ void unpack(float (&f)[1]) const { f[0] = Cvt<T>::to(raw); }
-  __device__ static __forceinline__ void store(void* base, int64_t elem, const float (&f)[1]) {
-    reinterpret_cast<T*>(base)[elem] = Cvt<T>::from(f[0]);
-  }
-};
-
-// fp32 packets for master weights / optimizer state (N floats, N in {1,4,8})
-template <int N> __device__ __forceinline__ void ldf(const float* p, int64_t e, float (&f)[N]) {
-  if (N == 1) {
-    f[0] = p[e];
-  } else {
-#pragma unroll
-    for (int i = 0; i < N; i += 4) {
-      uint4 v = ld16(p + e + i);
-      f[i] = __uint_as_float(v.x); f[i + 1] = __uint_as_float(v.y);
-      f[i + 2] = __uint_as_float(v.z); f[i + 3] = __uint_as_float(v.w);
-    }
-  }
-}
-template <int N> __device__ __forceinline__ void stf(float* p, int64_t e, const float (&f)[N]) {
-  if (N == 1) {
-    p[e] = f[0];
-  } else {
-#pragma unroll
-    for (int i = 0; i < N; i += 4) {
-      uint4 v = make_uint4(__float_as_uint(f[i]), __float_as_uint(f[i + 1]),
-                           __float_as_uint(f[i + 2]), __float_as_uint(f[i + 3]));
-      st16(p + e + i, v);
-    }
-  }
-}
-
-struct Hyper {
-  float lr, wd, eta, rescale, clip, momentum, beta1, beta2, eps;
-};
-
-__device__ __forceinline__ float clipf(float x, float b) {   // mshadow_op::clip, mshadow_op.h:999-1009
-  return x > b ? b : (x < -b ? -b : x);
-}
-
-// one element of the fused update; returns the new weight.  Operation order is
-// the reference source's, see the OptKind comments in kernels.h.
-template <int OPT>
-__device__ __forceinline__ float update_one(float g, float w, float& s0, float& s1, const Hyper& h) {
-  if (OPT == OPT_SGD) {
-    float r = __fmul_rn(h.rescale, g);
-    if (h.clip >= 0.0f) r = clipf(r, h.clip);
-    r = __fadd_rn(r, __fmul_rn(h.wd, w));
-    return __fsub_rn(w, __fmul_rn(h.lr, r));
-  } else if (OPT == OPT_SGD_MOM) {
-    float r = __fmul_rn(h.rescale, g);
-    if (h.clip >= 0.0f) r = clipf(r, h.clip);
-    r = __fadd_rn(r, __fmul_rn(h.wd, w));
-    float m = __fmul_rn(s0, h.momentum);
-    m = __fsub_rn(m, __fmul_rn(h.lr, r));
-    s0 = m;
-    return __fadd_rn(w, m);
-  } else if (OPT == OPT_ADAM) {
-    float r = __fmul_rn(g, h.rescale);
-    if (h.clip >= 0.0f) r = clipf(r, h.clip);
-    r = __fadd_rn(r, __fmul_rn(w, h.wd));
-    const float m = __fadd_rn(__fmul_rn(h.beta1, s0), __fmul_rn(__fsub_rn(1.f, h.beta1), r));
-    const float v = __fadd_rn(__fmul_rn(h.beta2, s1),
-                              __fmul_rn(__fmul_rn(__fsub_rn(1.f, h.beta2), r), r));
-    s0 = m; s1 = v;
-    return __fsub_rn(w, __fdiv_rn(__fmul_rn(h.lr, m), __fadd_rn(__fsqrt_rn(v), h.eps)));
-  } else if (OPT == OPT_ADAMW) {
-    float sg = __fmul_rn(h.rescale, g);
-    if (h.clip >= 0.0f) sg = clipf(sg, h.clip);
-    const float m = __fadd_rn(__fmul_rn(h.beta1, s0), __fmul_rn(__fsub_rn(1.0f, h.beta1), sg));
-    const float v = __fadd_rn(__fmul_rn(h.beta2, s1),
-                              __fmul_rn(__fsub_rn(1.0f, h.beta2), __fmul_rn(sg, sg)));
-    s0 = m; s1 = v;
-    const float step = __fadd_rn(__fdiv_rn(__fmul_rn(h.lr, m), __fadd_rn(__fsqrt_rn(v), h.eps)),
-                                 __fmul_rn(h.wd, w));
-    return __fsub_rn(w, __fmul_rn(h.eta, step));
-  } else if (OPT == OPT_TEST) {
-    const float gr = __fmul_rn(h.rescale, g);
-    const float s = __fadd_rn(gr, __fmul_rn(h.wd, w));
-    return __fsub_rn(w, __fmul_rn(h.lr, s));
-  } else if (OPT == OPT_SGD_STD) {
-    // every row: w *= (1 - lr*wd); rows of the gradient: w -= lr * clip(rescale*g) (wd already applied)
-    const float ws = __fmul_rn(w, __fsub_rn(1.0f, __fmul_rn(h.lr, h.wd)));
-    float r = __fmul_rn(h.rescale, g);
-    if (h.clip >= 0.0f) r = clipf(r, h.clip);
-    r = __fadd_rn(r, __fmul_rn(0.0f, ws));
-    return __fsub_rn(ws, __fmul_rn(h.lr, r));
-  } else if (OPT == OPT_ADAM_STD) {
-    float r = __fmul_rn(g, h.rescale);
-    if (h.clip >= 0.0f) r = clipf(r, h.clip);
-    r = __fadd_rn(r, __fmul_rn(w, h.wd));
-    const float m = __fadd_rn(__fmul_rn(h.beta1, s0), __fmul_rn(__fsub_rn(1.f, h.beta1), r));
-    const float v = __fadd_rn(__fmul_rn(h.beta2, s1), __fmul_rn(__fsub_rn(1.f, h.beta2), __fmul_rn(r, r)));
-    s0 = m; s1 = v;
-    return __fsub_rn(w, __fdiv_rn(__fmul_rn(h.lr, m), __fadd_rn(__fsqrt_rn(v), h.eps)));
-  }
-  return g;  // OPT_NONE
-}
 
 // ---------------------------------------------------------------------------
 // U packets per thread: gather n sources, sum in order, update, scatter.  All loads of a batch are

@@ -34,8 +34,13 @@ enum OptKind : int {
   // standard (non-lazy) updates of a dense weight with a row_sparse gradient, applied to the
   // densified gradient (absent rows = 0); arithmetic of the reference's *Std* sparse kernels
   OPT_SGD_STD = 6,  // SGDUpdateDnsRspImpl, lazy_update=false: w*(1-lr*wd) then w - lr*g   optimizer_op-inl.h:471-515
-  OPT_ADAM_STD = 7  // AdamStdDnsRspDnsKernel: (1-beta2)*square(g)                          optimizer_op.cu:125-152
+  OPT_ADAM_STD = 7, // AdamStdDnsRspDnsKernel: (1-beta2)*square(g)                          optimizer_op.cu:125-152
+  // layer-wise adaptive optimizers: need per-tensor norms, run as a launch sequence (norm_kernels.h)
+  OPT_LAMB = 8,     // multi_lamb_update / multi_mp_lamb_update   contrib/multi_lamb.cc:36-120
+  OPT_LANS = 9,     // multi_lans_update / multi_mp_lans_update   contrib/multi_lans.cc:36-130
+  OPT_LARS = 10     // LARS._get_lars + (mp_)sgd(_mom)_update     python/mxnet/optimizer/lars.py:117-133,244-275
 };
+inline bool IsNormOpt(int kind) { return kind == OPT_LAMB || kind == OPT_LANS || kind == OPT_LARS; }
 
 enum SumOrder : int {
   ORDER_DEVICE = 0,  // ((in0+in1)+in2)+...                  ndarray_function-inl.h:457-486
@@ -64,7 +69,7 @@ struct alignas(16) TensorWork {
   int n_out;
   int pad_;          // bit 0: every pointer 16-byte aligned; bit 1: eligible for the staged variant
   int n_mc;          // NVLS launches: the last n_mc entries of out[] are multicast addresses
-  int reserved_;
+  int reserved_;     // host side only: the key this entry belongs to
 };
 static_assert(sizeof(TensorWork) == 400, "TensorWork layout");
 

@@ -1,6 +1,7 @@
 // kvstore.cc -- see kvstore.h for the reference mapping.
 #include "kvstore.h"
 #include "rsp_kernels.h"
+#include "norm_kernels.h"
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -180,6 +181,9 @@ void KVStore::SetOptimizer(const std::string& name, const std::vector<std::pair<
   else if (n == "adam") { c.kind = OPT_ADAM; c.lr = 0.001; }
   else if (n == "adamw") { c.kind = OPT_ADAMW; c.lr = 0.001; }
   else if (n == "test") { c.kind = OPT_TEST; c.lr = 0.01; }
+  else if (n == "lamb") { c.kind = OPT_LAMB; c.lr = 0.001; c.eps = 1e-6f; }    // lamb.py:66-68
+  else if (n == "lans") { c.kind = OPT_LANS; c.lr = 0.001; c.eps = 1e-6f; }    // lans.py:61-63
+  else if (n == "lars") { c.kind = OPT_LARS; c.lr = 0.1; }                     // lars.py:77-79
   else MXKV_FATAL() << "optimizer '" << name << "' has no fused kernel; register a Python updater instead";
   for (auto& kv : kwargs) {
     const std::string& k = kv.first;
@@ -189,8 +193,12 @@ void KVStore::SetOptimizer(const std::string& name, const std::vector<std::pair<
     else if (k == "momentum") c.momentum = std::stof(v);
     else if (k == "beta1") c.beta1 = std::stod(v);
     else if (k == "beta2") c.beta2 = std::stod(v);
-    else if (k == "epsilon") c.eps = std::stof(v);
-    else if (k == "eta") c.eta = std::stof(v);
+    else if (k == "epsilon") { if (c.kind == OPT_LARS) c.lars_eps = std::stof(v); else c.eps = std::stof(v); }
+    else if (k == "eta") { if (c.kind == OPT_LARS) c.lars_eta = std::stof(v); else c.eta = std::stof(v); }
+    else if (k == "lower_bound") c.lower_bound = (v == "None" || v.empty()) ? -1.f : std::stof(v);
+    else if (k == "upper_bound") c.upper_bound = (v == "None" || v.empty()) ? -1.f : std::stof(v);
+    else if (k == "bias_correction") c.bias_correction = (v == "True" || v == "true" || v == "1");
+    else if (k == "skip_nonfinite") c.skip_nonfinite = (v == "True" || v == "true" || v == "1");
     else if (k == "rescale_grad") c.rescale = std::stof(v);
     else if (k == "clip_gradient") c.clip = (v == "None" || v.empty()) ? -1.f : std::stof(v);
     else if (k == "lazy_update") c.lazy_update = (v == "True" || v == "true" || v == "1");
@@ -199,9 +207,21 @@ void KVStore::SetOptimizer(const std::string& name, const std::vector<std::pair<
     else MXKV_FATAL() << "unknown optimizer argument '" << k << "'";
   }
   if (c.kind == OPT_SGD && c.momentum != 0.f) c.kind = OPT_SGD_MOM;   // sgd.py:213-224
+  MXKV_CHECK(!c.skip_nonfinite || IsNormOpt(c.kind)) << "skip_nonfinite is available for lamb / lans / lars";
   c.lr_mult = opt_.lr_mult;
   c.wd_mult = opt_.wd_mult;
+  c.no_trust = opt_.no_trust;
   opt_ = c;
+}
+
+void KVStore::SetKeyFlag(bool str_key, int ikey, const std::string& skey, const std::string& name, int value) {
+  LOCK();
+  const int key = ResolveKey(str_key, ikey, skey);
+  if (name == "no_trust_ratio") {
+    if (value) opt_.no_trust.insert(key); else opt_.no_trust.erase(key);
+  } else {
+    MXKV_FATAL() << "unknown key flag '" << name << "'";
+  }
 }
 
 void KVStore::SetOptimizerMult(bool str_key, int ikey, const std::string& skey, float lr_mult, float wd_mult) {
@@ -211,7 +231,9 @@ void KVStore::SetOptimizerMult(bool str_key, int ikey, const std::string& skey, 
   opt_.wd_mult[key] = wd_mult;
 }
 
-float KVStore::KeyLR(const KeyState& ks) const {
+float KVStore::KeyLR(const KeyState& ks) const { return static_cast<float>(KeyLRd(ks)); }
+
+double KVStore::KeyLRd(const KeyState& ks) const {
   // Optimizer._get_lr (optimizer.py) then, for Adam, the host-side bias correction of
   // adam.py:166-175 -- all in double like Python, rounded to float once.
   double lr = opt_.lr;
@@ -223,7 +245,7 @@ float KVStore::KeyLR(const KeyState& ks) const {
     const double coef2 = 1. - std::pow(opt_.beta2, t);
     lr *= std::sqrt(coef2) / coef1;
   }
-  return static_cast<float>(lr);
+  return lr;
 }
 
 float KVStore::KeyWD(const KeyState& ks) const {
@@ -299,8 +321,20 @@ void KVStore::EnsureState(KeyState& ks, Replica& r, bool mp) {
   const Context ctx{kGPU, r.dev};
   DeviceGuard g(r.dev);
   cudaStream_t s = rt->Dev(r.dev).stream;
-  const bool need_s0 = opt_.kind == OPT_SGD_MOM || opt_.kind == OPT_ADAM || opt_.kind == OPT_ADAMW;
-  const bool need_s1 = opt_.kind == OPT_ADAM || opt_.kind == OPT_ADAMW;
+  const bool need_s0 = opt_.kind == OPT_SGD_MOM || opt_.kind == OPT_ADAM || opt_.kind == OPT_ADAMW ||
+                       opt_.kind == OPT_LAMB || opt_.kind == OPT_LANS ||
+                       (opt_.kind == OPT_LARS && opt_.momentum != 0.f);      // lars.py:96-101
+  const bool need_s1 = opt_.kind == OPT_ADAM || opt_.kind == OPT_ADAMW || opt_.kind == OPT_LAMB || opt_.kind == OPT_LANS;
+  if (IsNormOpt(opt_.kind)) {
+    // temporaries between the phases and the per-key totals the peers read (allocated collectively
+    // in one-process-per-GPU mode: every rank reaches this point for the same keys in the same order)
+    if (r.aux0.is_none()) r.aux0 = NDArray::Empty(ks.shape, ctx, kFloat32, false);
+    if (opt_.kind == OPT_LANS && r.aux1.is_none()) r.aux1 = NDArray::Empty(ks.shape, ctx, kFloat32, false);
+    if (r.nrm.is_none()) {
+      r.nrm = NDArray::Empty({kNrmFloats}, ctx, kFloat32, sym);
+      CUDA_CALL(cudaMemsetAsync(r.nrm.data(), 0, r.nrm.nbytes(), s));
+    }
+  }
   if (mp && r.w32.is_none()) {
     r.w32 = NDArray::Empty(ks.shape, ctx, kFloat32, sym);
     // create_state_multi_precision: weight_master_copy = weight.astype(float32) (optimizer.py:341-352)
@@ -599,6 +633,7 @@ bool KVStore::HostPipelined(std::vector<Group>& groups, bool write_outs) {
   ProcessGroup* pg = rt->pg();
   if (pg != nullptr && pg->world() > 1) return false;
   if (updater_ != nullptr) return false;
+  if (opt_.enabled && IsNormOpt(opt_.kind)) return false;   // per-key norms need the whole key in one launch
   if (EnvInt("MXKV_B200_HOST_PIPELINE", 1) == 0) return false;
   int64_t total_bytes = 0;
   for (auto& g : groups) {
@@ -707,7 +742,7 @@ bool KVStore::HostPipelined(std::vector<Group>& groups, bool write_outs) {
       tw.s0 = r->s0.is_none() ? nullptr : static_cast<float*>(r->s0.data());
       tw.s1 = r->s1.is_none() ? nullptr : static_cast<float*>(r->s1.data());
       tw.begin = b; tw.end = e;
-      tw.lr = lr; tw.wd = wd; tw.eta = opt_.eta;
+      tw.lr = lr; tw.wd = wd; tw.eta = opt_.eta; tw.reserved_ = ks.key;
       tw.pad_ = 1 | ((esize == 4 && ks.size % 4 == 0) ? 2 : 0);
       std::vector<std::vector<TensorWork>> per_part(1);
       per_part[0].push_back(tw);
@@ -869,7 +904,7 @@ void KVStore::ReduceUpdateCompressed(std::vector<Group>& groups, bool write_outs
       tw.s0 = r.s0.is_none() ? nullptr : static_cast<float*>(r.s0.data());
       tw.s1 = r.s1.is_none() ? nullptr : static_cast<float*>(r.s1.data());
       tw.begin = 0; tw.end = ks.size;
-      tw.lr = lr; tw.wd = wd; tw.eta = opt_.eta;
+      tw.lr = lr; tw.wd = wd; tw.eta = opt_.eta; tw.reserved_ = ks.key;
       tw.pad_ = vec_ok ? 3 : 0;
       LaunchLocal(LaunchClassKey{SYNC_NONE, ks.dtype, mp ? 1 : 0}, tw, opt_kind, dev);
       r.fresh = true;
@@ -908,6 +943,8 @@ void KVStore::ReduceUpdateCompressed(std::vector<Group>& groups, bool write_outs
 }
 
 void KVStore::ReduceUpdate(std::vector<Group>& groups, bool write_outs) {
+  // an overflow of the previous step is settled before this step's update counts are taken
+  if (opt_.enabled && updater_ == nullptr && opt_.skip_nonfinite) ResolveOverflow();
   if (gc_bits_ != 0) { ReduceUpdateCompressed(groups, write_outs); return; }
   if (HostPipelined(groups, write_outs)) return;
   Runtime* rt = Runtime::Get();
@@ -1142,7 +1179,7 @@ void KVStore::ReduceUpdate(std::vector<Group>& groups, bool write_outs) {
       // the peer path: 1.5x more at n=2, equal time measured at n=4 -- where the peer path is kept
       // because it is bit-exact --, 1.56x less at n=8: busbw 782 vs 641 GB/s, profiles/r01_tune_bulk.txt)
       if (mp_mode && collective && (rt->nvls_mode >= 2 || (rt->nvls_mode == 1 && n_part > 4)) &&
-          ks.dtype == kFloat32 && ks.size % 4 == 0 &&
+          !(fused && IsNormOpt(opt_.kind)) && ks.dtype == kFloat32 && ks.size % 4 == 0 &&
           g.vals[0].mc_data() != nullptr && Aligned16(g.vals[0].mc_data()) && !(two_shot && need_post)) {
         nvls_key = true;
         if (write_outs)
@@ -1263,7 +1300,7 @@ void KVStore::ReduceUpdate(std::vector<Group>& groups, bool write_outs) {
       } else {
         tw.begin = 0; tw.end = ks.size;
       }
-      tw.lr = lr; tw.wd = wd; tw.eta = opt_.eta;
+      tw.lr = lr; tw.wd = wd; tw.eta = opt_.eta; tw.reserved_ = ks.key;
       tw.pad_ = (vec_ok ? 1 : 0) | ((vec_ok && esize == 4 && ks.size % 4 == 0) ? 2 : 0);
       cls[p].push_back(tw);
     }
@@ -1271,7 +1308,15 @@ void KVStore::ReduceUpdate(std::vector<Group>& groups, bool write_outs) {
 
   // ---- launches: one per class per local participant --------------------------
   const int opt_kind = fused ? opt_.kind : OPT_NONE;
-  for (auto& kv : classes) LaunchWorks(kv.first, kv.second.per_part, kv.second.busiest, opt_kind, part_dev);
+  if (IsNormOpt(opt_kind)) {
+    // all classes together: the phases of every class are interleaved so that the overflow check
+    // covers the whole push
+    std::vector<NormClass> all;
+    for (auto& kv : classes) all.push_back(NormClass{kv.first, &kv.second.per_part, &kv.second.busiest});
+    LaunchNormWorks(all, opt_kind, part_dev);
+  } else {
+    for (auto& kv : classes) LaunchWorks(kv.first, kv.second.per_part, kv.second.busiest, opt_kind, part_dev);
+  }
 
   // ---- epilogue -------------------------------------------------------------------
   for (size_t i = 0; i < temps.size(); ++i) {
@@ -1301,6 +1346,11 @@ void KVStore::LaunchWorks(const LaunchClassKey& ck, std::vector<std::vector<Tens
   const int n_part = static_cast<int>(part_dev.size());
   const int my_first = mp_mode ? pg->rank() : 0;
   const int my_last = mp_mode ? pg->rank() : n_part - 1;
+  if (IsNormOpt(opt_kind)) {
+    std::vector<NormClass> one{NormClass{ck, &per_part, &busiest}};
+    LaunchNormWorks(one, opt_kind, part_dev);
+    return;
+  }
 
   // ---- kernel variant: identical decision on every rank (it fixes the grid) --------------------
   // shared-memory staged (bulk-copy) variant: float32, every entry 16-byte aligned with a key size

@@ -38,6 +38,12 @@ struct OptimizerConfig {
   bool multi_precision = false;
   bool lazy_update = false;   // row_sparse gradients: touch only the rows present (sgd.py:78, adam.py:77 default False)
   bool correct_bias = true;   // AdamW only (python/mxnet/optimizer/adamW.py:80-88)
+  // LAMB / LANS / LARS (python/mxnet/optimizer/{lamb,lans,lars}.py)
+  float lower_bound = -1.f, upper_bound = -1.f;   // bounds on the weight norm, < 0: not set
+  bool bias_correction = true;                     // LAMB
+  float lars_eta = 0.001f, lars_eps = 1e-8f;       // LARS trust coefficient and epsilon
+  bool skip_nonfinite = false;   // leave weight/state untouched when a merged gradient of the call is not finite
+  std::unordered_set<int> no_trust;   // LARS: keys named *gamma / *beta / *bias keep the plain learning rate
   std::unordered_map<int, double> lr_mult, wd_mult;
 };
 
@@ -48,6 +54,8 @@ struct Replica {
   NDArray s0, s1;    // optimizer state
   NDArray stage;     // MP mode: symmetric staging for non-symmetric gradients
   NDArray merged;    // updater-callback path: reduce target
+  NDArray aux0, aux1;  // LAMB/LANS/LARS: fp32 temporaries between the phases (update direction / merged gradient)
+  NDArray nrm;         // LAMB/LANS/LARS: this replica's per-key sums of squares (peer-visible)
   bool fresh = true;
   // row_sparse keys: `local` is the dense-backed table [num_rows x row_len]
   NDArray rsp_merged;            // union ids + summed rows of the last push (capacity n * rsp_cap rows)
@@ -126,6 +134,11 @@ class KVStore {
   // which: 0 stored value, 1 fp32 master, 2 state0, 3 state1; gathers shards so the result is complete
   NDArray GetState(bool str_key, int ikey, const std::string& skey, int which);
   void SetState(bool str_key, int ikey, const std::string& skey, int which, const NDArray& v);
+  // per-key switches of the fused optimizers; "no_trust_ratio": LARS skips the layer-wise ratio (lars.py:121-123)
+  void SetKeyFlag(bool str_key, int ikey, const std::string& skey, const std::string& name, int value);
+  // 1 if the last push with skip_nonfinite met a non-finite gradient (and therefore changed nothing);
+  // waits for the engine streams, undoes that push's update counts, clears the flag
+  int ResolveOverflow();
   int64_t GetUpdateCount(bool str_key, int ikey, const std::string& skey);
   void SetUpdateCount(bool str_key, int ikey, const std::string& skey, int64_t c);
 
@@ -155,6 +168,13 @@ class KVStore {
   void LaunchWorks(const LaunchClassKey& ck, std::vector<std::vector<TensorWork>>& per_part,
                    const std::vector<int64_t>& busiest, int opt_kind, const std::vector<int>& part_dev);
   void LaunchLocal(const LaunchClassKey& ck, const TensorWork& tw, int opt_kind, int dev);
+  // LAMB / LANS / LARS: the same work lists as a first / finalize / (mid) / apply launch sequence
+  struct NormClass {
+    LaunchClassKey ck;
+    std::vector<std::vector<TensorWork>>* per_part;
+    const std::vector<int64_t>* busiest;
+  };
+  void LaunchNormWorks(std::vector<NormClass>& classes, int opt_kind, const std::vector<int>& part_dev);
   void GatherLocal(KeyState& ks);
   bool HostPipelined(std::vector<Group>& groups, bool write_outs);
   void ReduceUpdateCompressed(std::vector<Group>& groups, bool write_outs);
@@ -171,6 +191,7 @@ class KVStore {
   void EnsureState(KeyState& ks, Replica& r, bool mp);
   void GatherState(KeyState& ks);
   int DefaultDevice();
+  double KeyLRd(const KeyState& ks) const;
   float KeyLR(const KeyState& ks) const;
   float KeyWD(const KeyState& ks) const;
 
@@ -190,7 +211,13 @@ class KVStore {
   std::string gc_type_ = "none";
   float gc_threshold_ = 0.5f;
   int gc_bits_ = 0;
+  int* overflow_flag_ = nullptr;        // host-mapped word written by the apply kernel
+  std::vector<int> last_norm_keys_;     // keys of the last skip_nonfinite push (count roll-back)
   std::recursive_mutex mu_;
 };
+
+// multi_sum_sq / multi_all_finite over a list of dense arrays on one GPU (kvstore_norm.cc)
+void MultiSumSq(const std::vector<NDArray>& arrays, float scale, NDArray* out_sumsq, NDArray* all_finite,
+                bool init_output);
 
 }  // namespace mxkv

@@ -230,6 +230,9 @@ class KVStore(KVStoreBase):
             mults = set(optimizer.lr_mult) | set(optimizer.wd_mult)
             for k in mults:
                 self.set_mult(k, optimizer.lr_mult.get(k, 1.0), optimizer.wd_mult.get(k, 1.0))
+            if hasattr(optimizer, "no_trust_ratio_indices"):
+                for k in optimizer.no_trust_ratio_indices():
+                    self.set_key_flag(k, "no_trust_ratio", 1)
         else:
             self._fused = False
             self._set_updater(opt.get_updater(optimizer))
@@ -241,6 +244,20 @@ class KVStore(KVStoreBase):
         else:
             check_call(_LIB.MXKVB200SetOptimizerMult(self.handle, int(key), None, ctypes.c_float(lr_mult),
                                                      ctypes.c_float(wd_mult)))
+
+    def set_key_flag(self, key, name, value=1):
+        """Per-key switch of a fused optimizer (MXKVB200SetKeyFlag)."""
+        if isinstance(key, str):
+            check_call(_LIB.MXKVB200SetKeyFlag(self.handle, 0, c_str(key), c_str(name), int(value)))
+        else:
+            check_call(_LIB.MXKVB200SetKeyFlag(self.handle, int(key), None, c_str(name), int(value)))
+
+    def overflow(self):
+        """True if the last push (optimizer created with ``skip_nonfinite=True``) met a non-finite
+        gradient and therefore changed nothing; waits for the push to finish and clears the flag."""
+        out = ctypes.c_int(0)
+        check_call(_LIB.MXKVB200GetOverflow(self.handle, ctypes.byref(out)))
+        return bool(out.value)
 
     def _sync_lr(self):
         if self._fused and self._optimizer is not None:

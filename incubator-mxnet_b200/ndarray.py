@@ -414,5 +414,32 @@ def has_multicast(nd_array):
     return bool(keep) and isinstance(keep, tuple) and bool(getattr(keep[1], "multicast_ptr", 0))
 
 
+def multi_sum_sq(*arrays, **kwargs):
+    """Sums of squares of several arrays in one launch (the reference's ``multi_sum_sq`` operator,
+    src/operator/contrib/multi_sum_sq-inl.h:83-96): returns float32 [len(arrays)] on the arrays' GPU."""
+    scale = float(kwargs.pop("scale", 1.0))
+    out = kwargs.pop("out", None)
+    assert not kwargs and arrays
+    if out is None:
+        out = empty((len(arrays),), ctx=arrays[0].context, dtype=np.float32)
+    handles = (ctypes.c_void_p * len(arrays))(*[a.handle.value for a in arrays])
+    check_call(_LIB.MXKVB200MultiSumSq(len(arrays), handles, ctypes.c_float(scale), out.handle))
+    return out
+
+
+def multi_all_finite(*arrays, **kwargs):
+    """1.0 if every element of every array is finite, else 0.0 (``multi_all_finite``,
+    src/operator/all_finite.cu:68-103).  ``init_output=False`` keeps a 0 already in ``out``."""
+    init_output = bool(kwargs.pop("init_output", True))
+    out = kwargs.pop("out", None)
+    assert not kwargs and arrays
+    if out is None:
+        assert init_output
+        out = empty((1,), ctx=arrays[0].context, dtype=np.float32)
+    handles = (ctypes.c_void_p * len(arrays))(*[a.handle.value for a in arrays])
+    check_call(_LIB.MXKVB200MultiAllFinite(len(arrays), handles, int(init_output), out.handle))
+    return out
+
+
 def waitall():
     check_call(_LIB.MXNDArrayWaitAll())

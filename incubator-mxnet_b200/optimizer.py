@@ -2,7 +2,8 @@
 
 Two roles:
 * describe the hyper-parameters of the optimizers that have a fused kernel in the native
-  engine (SGD / SGD-momentum / multi-precision SGD, Adam, AdamW, Test) -- ``KVStore.set_optimizer``
+  engine (SGD / SGD-momentum / multi-precision SGD, Adam, AdamW, Test, and the layer-wise adaptive
+  LAMB / LANS / LARS) -- ``KVStore.set_optimizer``
   hands them to ``MXKVB200SetOptimizer`` and the update then runs inside the reduce kernel;
 * provide the generic ``Updater`` callback (updater.py:39-93) for any other Optimizer object:
   the store reduces on the GPU and calls back into Python, exactly like the reference.  The
@@ -191,6 +192,87 @@ class AdamW(Optimizer):
         kw.update(beta1=self.beta1, beta2=self.beta2, epsilon=self.epsilon, eta=self.eta,
                   correct_bias=bool(self.correct_bias))
         return kw
+
+
+class _LayerwiseAdaptive(Optimizer):
+    """Shared part of LAMB / LANS / LARS: ``skip_nonfinite=True`` asks the store to leave weights and
+    state alone when a merged gradient holds inf/nan (the AMP overflow skip, gluon/trainer.py:445-448,
+    decided on the device; query it with ``KVStore.overflow()``)."""
+
+    def __init__(self, skip_nonfinite=False, **kwargs):
+        super(_LayerwiseAdaptive, self).__init__(**kwargs)
+        self.skip_nonfinite = skip_nonfinite
+
+    def fused_kwargs(self):
+        kw = super(_LayerwiseAdaptive, self).fused_kwargs()
+        if self.skip_nonfinite:
+            kw["skip_nonfinite"] = True
+        return kw
+
+
+@register
+class LAMB(_LayerwiseAdaptive):
+    """python/mxnet/optimizer/lamb.py; fused kernels multi_lamb_update / multi_mp_lamb_update
+    (src/operator/contrib/multi_lamb.cc:36-120) with the two norms taken inside the gradient exchange."""
+    fused_name = "lamb"
+
+    def __init__(self, learning_rate=0.001, beta1=0.9, beta2=0.999, epsilon=1e-6, lower_bound=None,
+                 upper_bound=None, bias_correction=True, **kwargs):
+        super(LAMB, self).__init__(learning_rate=learning_rate, **kwargs)
+        self.beta1, self.beta2, self.epsilon = beta1, beta2, epsilon
+        self.lower_bound, self.upper_bound, self.bias_correction = lower_bound, upper_bound, bias_correction
+
+    def fused_kwargs(self):
+        kw = super(LAMB, self).fused_kwargs()
+        kw.update(beta1=self.beta1, beta2=self.beta2, epsilon=self.epsilon,
+                  bias_correction=bool(self.bias_correction))
+        if self.lower_bound:            # lamb.py:182-185: falsy bounds are not passed
+            kw["lower_bound"] = self.lower_bound
+        if self.upper_bound:
+            kw["upper_bound"] = self.upper_bound
+        return kw
+
+
+@register
+class LANS(_LayerwiseAdaptive):
+    """python/mxnet/optimizer/lans.py; fused kernels multi_lans_update / multi_mp_lans_update
+    (src/operator/contrib/multi_lans.cc:36-130)."""
+    fused_name = "lans"
+
+    def __init__(self, learning_rate=0.001, beta1=0.9, beta2=0.999, epsilon=1e-6, lower_bound=None,
+                 upper_bound=None, **kwargs):
+        super(LANS, self).__init__(learning_rate=learning_rate, **kwargs)
+        self.beta1, self.beta2, self.epsilon = beta1, beta2, epsilon
+        self.lower_bound, self.upper_bound = lower_bound, upper_bound
+
+    def fused_kwargs(self):
+        kw = super(LANS, self).fused_kwargs()
+        kw.update(beta1=self.beta1, beta2=self.beta2, epsilon=self.epsilon)
+        if self.lower_bound:
+            kw["lower_bound"] = self.lower_bound
+        if self.upper_bound:
+            kw["upper_bound"] = self.upper_bound
+        return kw
+
+
+@register
+class LARS(_LayerwiseAdaptive):
+    """python/mxnet/optimizer/lars.py: lr *= eta * ||w|| / (||g|| + wd * ||w|| + eps) per layer (not for
+    names ending in gamma / beta / bias), then the sgd / sgd_mom update."""
+    fused_name = "lars"
+
+    def __init__(self, learning_rate=0.1, momentum=0.0, eta=0.001, epsilon=1e-8, **kwargs):
+        super(LARS, self).__init__(learning_rate=learning_rate, **kwargs)
+        self.momentum, self.eta, self.epsilon = momentum, eta, epsilon
+
+    def fused_kwargs(self):
+        kw = super(LARS, self).fused_kwargs()
+        kw.update(momentum=self.momentum, eta=self.eta, epsilon=self.epsilon)
+        return kw
+
+    def no_trust_ratio_indices(self):
+        """Indices whose name ends in gamma / beta / bias (lars.py:121-123)."""
+        return [i for i, n in self.idx2name.items() if str(n).endswith(("gamma", "beta", "bias"))]
 
 
 @register

@@ -535,3 +535,126 @@ int kvo_max_threads(void) {
   return 1;
 #endif
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Layer-wise adaptive optimizers.  CPU kernels of the reference:
+ *   multi_sum_sq   src/operator/contrib/multi_sum_sq.cc:42-62 (CalcSumSq: sequential float sum)
+ *   multi_lamb     src/operator/contrib/multi_lamb.cc:36-120 (step 1 / step 2)
+ *   multi_lans     src/operator/contrib/multi_lans.cc:36-130
+ *   LARS           python/mxnet/optimizer/lars.py:117-133 (_get_lars on float32 NDArrays)
+ * The element arithmetic is restated operation by operation; the sums of squares are an input of
+ * step 2 so that a test can feed the sequential sum (what the reference's CPU operator computes),
+ * or a double-precision sum (the value every float summation order approximates).
+ * ------------------------------------------------------------------------------------------ */
+float kvo_sum_sq_f32(int64_t E, const float* x, float scale) {
+  float sum = 0.f;
+  for (int64_t j = 0; j < E; ++j) {
+    float val = x[j];
+    if (scale != 1.0f) val *= scale;
+    sum += val * val;
+  }
+  return sum;
+}
+double kvo_sum_sq_f64(int64_t E, const float* x, float scale) {
+  double sum = 0.0;
+  for (int64_t j = 0; j < E; ++j) {
+    float val = x[j];
+    if (scale != 1.0f) val *= scale;
+    sum += (double)val * (double)val;
+  }
+  return sum;
+}
+int64_t kvo_count_nonfinite_f32(int64_t E, const float* x) {
+  int64_t bad = 0;
+  for (int64_t j = 0; j < E; ++j) bad += !isfinite(x[j]);
+  return bad;
+}
+
+/* MultiLAMBKernelStep1, multi_lamb.cc:36-82.  w is the fp32 weight (the master in the mp variant) */
+void kvo_lamb_step1_f32(int64_t E, const float* w, const float* g, float* mean, float* var, float* temp_g,
+                        float beta1, float beta2, float eps, float wd, float rescale, float clip,
+                        int bias_correction, int step_count) {
+  const float c1 = 1.0f - powf(beta1, (float)step_count);
+  const float c2 = 1.0f - powf(beta2, (float)step_count);
+#pragma omp parallel for schedule(static) if (E >= 200000)
+  for (int64_t i = 0; i < E; ++i) {
+    float scaled_grad = g[i] * rescale;
+    if (clip >= 0.0f) scaled_grad = clipf(scaled_grad, clip);
+    float m = beta1 * mean[i] + (1.0f - beta1) * scaled_grad;
+    float v = beta2 * var[i] + (1.0f - beta2) * scaled_grad * scaled_grad;
+    mean[i] = m; var[i] = v;
+    float out;
+    if (bias_correction) {
+      float mean_hat = m / c1;
+      float var_hat = v / c2;
+      out = mean_hat / (sqrtf(var_hat) + eps) + wd * w[i];
+    } else {
+      out = m / (sqrtf(v) + eps) + wd * w[i];
+    }
+    temp_g[i] = out;
+  }
+}
+/* MultiLAMBKernelStep2, multi_lamb.cc:84-120 */
+void kvo_lamb_step2_f32(int64_t E, float* w, const float* temp_g, float lr, float sum_sq_w, float sum_sq_g,
+                        float lower_bound, float upper_bound) {
+  float r1 = sqrtf(sum_sq_w);
+  float r2 = sqrtf(sum_sq_g);
+  if (lower_bound >= 0) r1 = r1 > lower_bound ? r1 : lower_bound;
+  if (upper_bound >= 0) r1 = r1 < upper_bound ? r1 : upper_bound;
+  float r = (r1 == 0.0f || r2 == 0.0f) ? 1.0f : r1 / r2;
+  float lr_adjusted = lr * r;
+#pragma omp parallel for schedule(static) if (E >= 200000)
+  for (int64_t i = 0; i < E; ++i) w[i] = w[i] - lr_adjusted * temp_g[i];
+}
+
+/* MultiLANSKernelStep1, multi_lans.cc:36-84 */
+void kvo_lans_step1_f32(int64_t E, const float* w, const float* g, float* mean, float* var, float* temp_m,
+                        float* temp_g, float beta1, float beta2, float eps, float wd, float rescale, float clip,
+                        int step_count, float g_sq_norm) {
+  const float c1 = 1.0f - powf(beta1, (float)step_count);
+  const float c2 = 1.0f - powf(beta2, (float)step_count);
+  const float g_norm = sqrtf(g_sq_norm);
+#pragma omp parallel for schedule(static) if (E >= 200000)
+  for (int64_t i = 0; i < E; ++i) {
+    float scaled_grad = g[i] * rescale;
+    scaled_grad /= g_norm;
+    if (clip >= 0.0f) scaled_grad = clipf(scaled_grad, clip);
+    float m = beta1 * mean[i] + (1.0f - beta1) * scaled_grad;
+    float v = beta2 * var[i] + (1.0f - beta2) * scaled_grad * scaled_grad;
+    mean[i] = m; var[i] = v;
+    float mean_hat = m / c1;
+    float var_hat = v / c2;
+    var_hat = sqrtf(var_hat) + eps;
+    float scaled_w = wd * w[i];
+    temp_m[i] = mean_hat / var_hat + scaled_w;
+    temp_g[i] = scaled_grad / var_hat + scaled_w;
+  }
+}
+/* MultiLANSKernelStep2, multi_lans.cc:86-140 */
+void kvo_lans_step2_f32(int64_t E, float* w, const float* temp_m, const float* temp_g, float lr, float beta1,
+                        float sum_sq_w, float sum_sq_m, float sum_sq_g, float lower_bound, float upper_bound) {
+  float r1 = sqrtf(sum_sq_w);
+  float r2_m = sqrtf(sum_sq_m);
+  float r2_g = sqrtf(sum_sq_g);
+  if (lower_bound >= 0) r1 = r1 > lower_bound ? r1 : lower_bound;
+  if (upper_bound >= 0) r1 = r1 < upper_bound ? r1 : upper_bound;
+  float r_m = (r1 == 0.0f || r2_m == 0.0f) ? 1.0f : r1 / r2_m;
+  float r_g = (r1 == 0.0f || r2_g == 0.0f) ? 1.0f : r1 / r2_g;
+  r_m *= beta1;
+  r_g *= (1. - beta1);                       /* double right-hand side, as written in the reference */
+  float lr_adjusted_m = lr * r_m;
+  float lr_adjusted_g = lr * r_g;
+#pragma omp parallel for schedule(static) if (E >= 200000)
+  for (int64_t i = 0; i < E; ++i) w[i] = w[i] - (lr_adjusted_m * temp_m[i] + lr_adjusted_g * temp_g[i]);
+}
+
+/* LARS._get_lars, lars.py:117-133: float32 NDArray arithmetic on the two norms; the caller multiplies
+ * the (double) learning rate by the returned value */
+float kvo_lars_ratio_f32(float sum_sq_w, float sum_sq_g, float eta, float wd, float eps) {
+  float w_norm = sqrtf(sum_sq_w);
+  float g_norm = sqrtf(sum_sq_g);
+  float ratio = w_norm / g_norm;
+  float lars = (eta * w_norm) / ((g_norm + wd * w_norm) + eps);
+  if (!isfinite(ratio) || ratio == 0.0f) lars = 1.0f;    /* nan_or_zero = 1 - ratio / ratio */
+  return lars;
+}

@@ -50,6 +50,10 @@ def lib():
         _LIB.kvo_adam_lr.argtypes = [ctypes.c_double] * 3 + [ctypes.c_int]
         _LIB.kvo_unique_i64.restype = ctypes.c_int64
         _LIB.kvo_rsp_sum_f32.restype = ctypes.c_int64
+        _LIB.kvo_sum_sq_f32.restype = ctypes.c_float
+        _LIB.kvo_sum_sq_f64.restype = ctypes.c_double
+        _LIB.kvo_count_nonfinite_f32.restype = ctypes.c_int64
+        _LIB.kvo_lars_ratio_f32.restype = ctypes.c_float
     return _LIB
 
 
@@ -205,6 +209,63 @@ def mp_adamw_update(w_lp, lp_kind, w32, mean, var, g32, lr, eta=1.0, wd=0.0, bet
                               _F(beta2), _F(eps), _F(rescale), _clip(clip))
 
 
+# ---- layer-wise adaptive optimizers (multi_sum_sq / multi_lamb / multi_lans / LARS) -------------
+def sum_sq(x, scale=1.0, mode="seq"):
+    """Sum of squares as a float32.  mode 'seq': the reference CPU operator's sequential float sum
+    (multi_sum_sq.cc:42-62); 'f64': accumulated in double and rounded once -- the value every float
+    summation order (CPU sequential, GPU block tree) approximates."""
+    x = np.ascontiguousarray(x, dtype=np.float32).ravel()
+    if mode == "seq":
+        return np.float32(lib().kvo_sum_sq_f32(_I64(x.size), _ptr(x, c_f32p), _F(scale)))
+    return np.float32(lib().kvo_sum_sq_f64(_I64(x.size), _ptr(x, c_f32p), _F(scale)))
+
+
+def count_nonfinite(x):
+    x = np.ascontiguousarray(x, dtype=np.float32).ravel()
+    return int(lib().kvo_count_nonfinite_f32(_I64(x.size), _ptr(x, c_f32p)))
+
+
+def lamb_update(w, g, mean, var, lr, wd, t, beta1=0.9, beta2=0.999, eps=1e-6, rescale=1.0, clip=None,
+                bias_correction=True, lower_bound=None, upper_bound=None, norm_mode="seq"):
+    """multi_lamb_update on one tensor (multi_lamb-inl.h:248-330): r1 from the weight, step 1, r2 from
+    the update direction, step 2.  ``w`` (float32, the master in the mp variant) is updated in place."""
+    tmp = np.empty_like(w)
+    ssw = sum_sq(w, 1.0, norm_mode)
+    lib().kvo_lamb_step1_f32(_I64(w.size), _ptr(w, c_f32p), _ptr(g, c_f32p), _ptr(mean, c_f32p), _ptr(var, c_f32p),
+                             _ptr(tmp, c_f32p), _F(beta1), _F(beta2), _F(eps), _F(wd), _F(rescale), _clip(clip),
+                             ctypes.c_int(1 if bias_correction else 0), ctypes.c_int(t))
+    ssg = sum_sq(tmp, 1.0, norm_mode)
+    lib().kvo_lamb_step2_f32(_I64(w.size), _ptr(w, c_f32p), _ptr(tmp, c_f32p), _F(lr), _F(ssw), _F(ssg),
+                             _F(lower_bound if lower_bound else -1.0), _F(upper_bound if upper_bound else -1.0))
+
+
+def lans_update(w, g, mean, var, lr, wd, t, beta1=0.9, beta2=0.999, eps=1e-6, rescale=1.0, clip=None,
+                lower_bound=None, upper_bound=None, norm_mode="seq", w_norm_src=None):
+    """multi_lans_update on one tensor (multi_lans-inl.h:262-380).  ``w_norm_src``: the array whose norm
+    is r1 -- the reference takes the low-precision weight even in the mp variant (:296-300)."""
+    tm, tg = np.empty_like(w), np.empty_like(w)
+    ssw = sum_sq(w if w_norm_src is None else w_norm_src, 1.0, norm_mode)
+    gsq = sum_sq(g, rescale, norm_mode)
+    lib().kvo_lans_step1_f32(_I64(w.size), _ptr(w, c_f32p), _ptr(g, c_f32p), _ptr(mean, c_f32p), _ptr(var, c_f32p),
+                             _ptr(tm, c_f32p), _ptr(tg, c_f32p), _F(beta1), _F(beta2), _F(eps), _F(wd), _F(rescale),
+                             _clip(clip), ctypes.c_int(t), _F(gsq))
+    ssm, ssg = sum_sq(tm, 1.0, norm_mode), sum_sq(tg, 1.0, norm_mode)
+    lib().kvo_lans_step2_f32(_I64(w.size), _ptr(w, c_f32p), _ptr(tm, c_f32p), _ptr(tg, c_f32p), _F(lr), _F(beta1),
+                             _F(ssw), _F(ssm), _F(ssg), _F(lower_bound if lower_bound else -1.0),
+                             _F(upper_bound if upper_bound else -1.0))
+
+
+def lars_lr(lr, w_for_norm, g, wd, eta=0.001, eps=1e-8, rescale=1.0, norm_mode="seq"):
+    """LARS._get_lars (lars.py:117-133) folded into the learning rate like lars.py:258-260: the
+    Python double ``lr`` times the float32 ratio."""
+    ssw = sum_sq(w_for_norm, 1.0, norm_mode)
+    # `v *= self.rescale_grad` is always applied (lars.py:108-110)
+    gs = np.ascontiguousarray(g, dtype=np.float32) * np.float32(rescale)
+    ssg = sum_sq(gs, 1.0, norm_mode)
+    lars = lib().kvo_lars_ratio_f32(_F(ssw), _F(ssg), _F(eta), _F(wd), _F(eps))
+    return float(lr) * float(lars)
+
+
 def test_update(w, g, lr, wd=0.0, rescale=1.0):
     lib().kvo_test_update_f32(_I64(w.size), _ptr(w, c_f32p), _ptr(g, c_f32p), _F(lr), _F(wd), _F(rescale))
 
@@ -346,16 +407,25 @@ class OracleOptimizer(object):
     rescale_grad, clip_gradient, multi_precision."""
 
     def __init__(self, name, learning_rate=None, wd=0.0, rescale_grad=1.0, clip_gradient=None,
-                 momentum=0.0, beta1=0.9, beta2=0.999, epsilon=1e-8, eta=1.0, multi_precision=False,
-                 lr_mult=None, wd_mult=None, lazy_update=True):
+                 momentum=0.0, beta1=0.9, beta2=0.999, epsilon=None, eta=None, multi_precision=False,
+                 lr_mult=None, wd_mult=None, lazy_update=True, lower_bound=None, upper_bound=None,
+                 bias_correction=True, norm_mode="seq", no_trust=()):
         self.name = name.lower()
+        self.lower_bound, self.upper_bound, self.bias_correction = lower_bound, upper_bound, bias_correction
+        self.norm_mode = norm_mode
+        self.no_trust = set(no_trust)       # LARS: indices named *gamma / *beta / *bias
         if learning_rate is None:
-            learning_rate = 0.001 if self.name in ("adam", "adamw") else 0.01
+            learning_rate = {"adam": 0.001, "adamw": 0.001, "lamb": 0.001, "lans": 0.001, "lars": 0.1}.get(
+                self.name, 0.01)
         self.lr = learning_rate
         self.wd = wd
         self.rescale_grad = rescale_grad
         self.clip_gradient = clip_gradient
         self.momentum = momentum
+        if epsilon is None:      # adam.py:85, lars.py:78: 1e-8; adamW.py:87, lamb.py:67, lans.py:62: 1e-6
+            epsilon = 1e-6 if self.name in ("adamw", "lamb", "lans") else 1e-8
+        if eta is None:          # AdamW's schedule multiplier (1.0) / LARS' trust coefficient (0.001)
+            eta = 0.001 if self.name == "lars" else 1.0
         self.beta1, self.beta2, self.epsilon, self.eta = beta1, beta2, epsilon, eta
         self.multi_precision = multi_precision
         self.lr_mult = dict(lr_mult or {})
@@ -418,6 +488,29 @@ class OracleOptimizer(object):
             mean, var = self.states[index]
             mp_adamw_update(None, 0, weight, mean, var, grad, lr, self.eta, wd, self.beta1, self.beta2,
                             self.epsilon, self.rescale_grad, self.clip_gradient)
+        elif n in ("lamb", "lans"):
+            assert not sparse
+            if index not in self.states:
+                self.states[index] = (np.zeros_like(weight), np.zeros_like(weight))
+            mean, var = self.states[index]
+            kw = dict(beta1=self.beta1, beta2=self.beta2, eps=self.epsilon, rescale=self.rescale_grad,
+                      clip=self.clip_gradient, lower_bound=self.lower_bound, upper_bound=self.upper_bound,
+                      norm_mode=self.norm_mode)
+            if n == "lamb":
+                lamb_update(weight, grad, mean, var, lr, wd, t, bias_correction=self.bias_correction, **kw)
+            else:
+                lans_update(weight, grad, mean, var, lr, wd, t, **kw)
+        elif n == "lars":
+            assert not sparse
+            if index not in self.no_trust:
+                lr = lars_lr(lr, weight, grad, wd, self.eta, self.epsilon, self.rescale_grad, self.norm_mode)
+            if self.momentum != 0.0:
+                if index not in self.states:
+                    self.states[index] = np.zeros_like(weight)
+                sgd_mom_update(weight, grad, self.states[index], lr, wd, self.momentum, self.rescale_grad,
+                               self.clip_gradient)
+            else:
+                sgd_update(weight, grad, lr, wd, self.rescale_grad, self.clip_gradient)
         else:
             raise ValueError("unknown optimizer " + n)
 

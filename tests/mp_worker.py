@@ -205,6 +205,43 @@ def main():
             assert mx.kv.launch_count() - before == 3, "one launch per pushpull expected"
         print("NVLS_OK rank", rank, flush=True)
 
+    # 8. layer-wise adaptive optimizers: sharded keys take the norms across the ranks' shards, small
+    #    keys are updated redundantly; replicas must stay bit-identical across ranks
+    for optname, kw in (("lamb", dict(learning_rate=0.01, wd=0.01)),
+                        ("lans", dict(learning_rate=0.01, wd=0.01)),
+                        ("lars", dict(learning_rate=0.1, momentum=0.9, wd=1e-3, eta=0.01)),
+                        ("lamb", dict(learning_rate=0.01, wd=0.01, skip_nonfinite=True))):
+        shapes = [(64,), (513, 9), (1 << 19,), (1 << 21,)]
+        ks = list(range(len(shapes)))
+        kv8 = mx.kv.create("device")
+        w0 = [data(61 + k, s, 0) for k, s in zip(ks, shapes)]
+        kv8.init(ks, [mx.nd.array(w, ctx) for w in w0])
+        kv8.set_optimizer(mx.optimizer.create(optname, **kw))
+        okw = {k: v for k, v in kw.items() if k != "skip_nonfinite"}
+        oopt = O.OracleOptimizer(optname, norm_mode="f64", **okw)
+        ow = [w.copy() for w in w0]
+        outs = [mx.nd.empty(s, ctx) for s in shapes]
+        for step in range(3):
+            overflow = kw.get("skip_nonfinite") and step == 1
+
+            def grad(k, s, r):
+                g = data(500 + 10 * step + k, s, r)
+                if overflow and k == 0 and r == world - 1:
+                    g.flat[3] = np.inf
+                return g
+            kv8.pushpull(ks, [mx.nd.array(grad(k, s, rank), ctx) for k, s in zip(ks, shapes)], out=outs)
+            if kw.get("skip_nonfinite"):
+                assert kv8.overflow() == bool(overflow), ("overflow flag", step)
+            for k, s in zip(ks, shapes):
+                if not overflow:
+                    oopt.update(k, ow[k], O.sum_device([grad(k, s, r) for r in range(world)]).reshape(s))
+                got = outs[k].asnumpy()
+                np.testing.assert_allclose(got, ow[k], rtol=2e-6, atol=2e-7, err_msg=str((optname, step, k)))
+                chk = torch.from_numpy(got.view(np.int32).astype(np.int64)).sum().cuda().reshape(1)
+                allc = [torch.empty_like(chk) for _ in range(world)]
+                dist.all_gather(allc, chk)
+                assert all(int(c) == int(chk) for c in allc), ("replicas differ", optname, step, k)
+
     mx.nd.waitall()
     dist.barrier()
     print("MP_WORKER_OK rank", rank, flush=True)

@@ -97,6 +97,43 @@ def test_sp_fused_update_multi_key(optname, kw):
                 assert _bits_equal(o.asnumpy(), want), (optname, step, k)
 
 
+@pytest.mark.parametrize("optname,kw", [
+    ("lamb", dict(learning_rate=0.01, wd=0.01)),
+    ("lamb", dict(learning_rate=0.01, wd=0.01, skip_nonfinite=True)),
+    ("lans", dict(learning_rate=0.01, wd=0.01, clip_gradient=0.5)),
+    ("lars", dict(learning_rate=0.1, momentum=0.9, wd=1e-3, eta=0.01)),
+])
+def test_sp_layerwise_adaptive_multi_key(optname, kw):
+    """LAMB / LANS / LARS over one-shot and two-shot (sharded: norms added across the GPUs' shards)
+    keys.  Tolerance: see tests/test_gpu_norm_opt.py; replicas on different GPUs must be bit-identical."""
+    devs = _devs()
+    shapes = [(64,), (1000, 33), (300, 1000), (7,), (1 << 21,)]
+    keys = list(range(len(shapes)))
+    rng = np.random.default_rng(19)
+    w0 = [rng.uniform(-1, 1, s).astype(np.float32) for s in shapes]
+    kv = mx.kv.create("device")
+    kv.init(keys, [mx.nd.array(w, mx.gpu(0)) for w in w0])
+    kv.set_optimizer(mx.optimizer.create(optname, **kw))
+    oopt = O.OracleOptimizer(optname, norm_mode="f64", **{k: v for k, v in kw.items() if k != "skip_nonfinite"})
+    ow = [w.copy() for w in w0]
+    outs = [[mx.nd.empty(s, mx.gpu(d)) for d in devs] for s in shapes]
+    for step in range(3):
+        grads = [[rng.uniform(-1, 1, s).astype(np.float32) for _ in devs] for s in shapes]
+        overflow = kw.get("skip_nonfinite") and step == 1
+        if overflow:
+            grads[3][-1][2] = np.nan
+        kv.pushpull(keys, [[mx.nd.array(g, mx.gpu(d)) for g, d in zip(gs, devs)] for gs in grads], out=outs)
+        if kw.get("skip_nonfinite"):
+            assert kv.overflow() == bool(overflow)
+        for k in keys:
+            if not overflow:
+                oopt.update(k, ow[k], O.sum_device(grads[k]).reshape(shapes[k]))
+            first = outs[k][0].asnumpy()
+            np.testing.assert_allclose(first, ow[k], rtol=2e-6, atol=2e-7, err_msg=str((optname, step, k)))
+            for o in outs[k][1:]:
+                assert _bits_equal(o.asnumpy(), first), (optname, step, k)
+
+
 def test_sp_save_load_states_sharded(tmp_path):
     """two-shot keys keep optimizer state sharded across the GPUs; save gathers it."""
     devs = _devs()

@@ -249,6 +249,180 @@ def test_adam_kernel_vs_python_step():
         np.testing.assert_allclose(w, w2, rtol=1e-4, atol=2e-5)
 
 
+# ---- LAMB / LANS / LARS: the fused-kernel restatement against a transcription of the reference's
+# ---- non-fused Python ``step`` -- the comparison tests/python/unittest/test_optimizer.py:232-312 makes
+def _norm32(x):
+    return np.sqrt(np.sum(np.square(x.astype(np.float32)), dtype=np.float32), dtype=np.float32)
+
+
+def _trust(r1, r2):
+    with np.errstate(divide="ignore", invalid="ignore"):
+        ratio = np.float32(r1) / np.float32(r2)
+    return np.float32(1.0) if (not np.isfinite(ratio) or ratio == 0) else ratio
+
+
+def _np_lamb_step(w, g, mean, var, lr, wd, t, b1, b2, eps, rescale, clip, bias_correction, lb, ub):
+    """lamb.py:93-150 on float32 arrays."""
+    f = np.float32
+    g = g * f(rescale)
+    if clip is not None:
+        g = np.clip(g, -f(clip), f(clip))
+    mean *= f(b1); mean += f(1. - b1) * g
+    var *= f(b2); var += f(1. - b2) * np.square(g)
+    r1 = _norm32(w)
+    if lb is not None:
+        r1 = max(r1, f(lb))
+    if ub is not None:
+        r1 = min(r1, f(ub))
+    if bias_correction:
+        mean_hat = mean / f(1. - b1 ** t)
+        var_hat = var / f(1. - b2 ** t)
+        var_hat = np.sqrt(var_hat) + f(eps)
+        mean_hat = mean_hat / var_hat + f(wd) * w
+    else:
+        mean_hat = mean / (np.sqrt(var) + f(eps)) + f(wd) * w
+    r = _trust(r1, _norm32(mean_hat))
+    w -= mean_hat * f(lr * r)
+
+
+def _np_lans_step(w, g, mean, var, lr, wd, t, b1, b2, eps, rescale, clip, lb, ub):
+    """lans.py:86-150."""
+    f = np.float32
+    g = g * f(rescale)
+    g = g / _norm32(g)
+    if clip is not None:
+        g = np.clip(g, -f(clip), f(clip))
+    mean *= f(b1); mean += f(1. - b1) * g
+    var *= f(b2); var += f(1. - b2) * np.square(g)
+    r1 = _norm32(w)
+    if lb is not None:
+        r1 = max(r1, f(lb))
+    if ub is not None:
+        r1 = min(r1, f(ub))
+    mean_hat = mean / f(1. - b1 ** t)
+    var_hat = np.sqrt(var / f(1. - b2 ** t)) + f(eps)
+    m = mean_hat / var_hat + f(wd) * w
+    r_m = _trust(r1, _norm32(m))
+    # the reference's step() applies the two halves one after the other (the second sees the
+    # already-updated weight in wd * weight); the fused kernel uses the old weight for both -- the
+    # reference test accepts the difference at rtol/atol 1e-3
+    w -= m * f(lr * r_m * b1)
+    gg = g / var_hat + f(wd) * w
+    r_g = _trust(r1, _norm32(gg))
+    w -= gg * f(lr * r_g * (1 - b1))
+
+
+def _np_lars_step(w, g, mom, lr, wd, momentum, eta, eps, rescale, clip, use_lars=True):
+    """lars.py:117-133,135-175."""
+    f = np.float32
+    if use_lars:
+        w_norm = _norm32(w)
+        g_norm = _norm32(g * f(rescale))
+        with np.errstate(divide="ignore", invalid="ignore"):
+            ratio = w_norm / g_norm
+        lars = f(eta) * w_norm / (g_norm + f(wd) * w_norm + f(eps))
+        if not np.isfinite(ratio) or ratio == 0:
+            lars = f(1.0)
+        lr = lr * float(lars)
+    g = g * f(rescale)
+    if clip is not None:
+        g = np.clip(g, -f(clip), f(clip))
+    g = g + f(wd) * w
+    if mom is not None:
+        mom *= f(momentum); mom -= f(lr) * g
+        w += mom
+    else:
+        w += -f(lr) * g
+
+
+_SHAPES = [(3, 4, 5), (10, 4), (7,)]     # test_optimizer.py:235,261,291
+
+
+@pytest.mark.parametrize("bias_correction", [False, True])
+@pytest.mark.parametrize("bounds", [(None, None), (1e-3, 10)])
+def test_lamb_kernel_vs_python_step(bias_correction, bounds):
+    lb, ub = bounds
+    for opts in (dict(), dict(beta1=0.5, beta2=0.8, clip_gradient=0.4, rescale_grad=0.14, wd=0.03)):
+        for shape in _SHAPES:
+            rng = np.random.default_rng(31)
+            w = rng.uniform(-1, 1, shape).astype(np.float32); w2 = w.copy()
+            mean, var = np.zeros(shape, np.float32), np.zeros(shape, np.float32)
+            opt = O.OracleOptimizer("lamb", learning_rate=0.01, bias_correction=bias_correction, lower_bound=lb,
+                                    upper_bound=ub, **opts)
+            for t in range(1, 5):
+                g = rng.uniform(-1, 1, shape).astype(np.float32)
+                opt.update(0, w, g.copy())
+                _np_lamb_step(w2, g.copy(), mean, var, 0.01, opts.get("wd", 0.0), t, opts.get("beta1", 0.9),
+                              opts.get("beta2", 0.999), 1e-6, opts.get("rescale_grad", 1.0),
+                              opts.get("clip_gradient"), bias_correction, lb, ub)
+                np.testing.assert_allclose(w, w2, rtol=1e-3, atol=1e-3)
+                assert np.max(np.abs(w - w2)) < 1e-5      # in fact the two restatements agree to ~1e-7
+                np.testing.assert_allclose(opt.states[0][0], mean, rtol=1e-5, atol=1e-7)
+                np.testing.assert_allclose(opt.states[0][1], var, rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize("bounds", [(None, None), (1e-3, 10)])
+def test_lans_kernel_vs_python_step(bounds):
+    lb, ub = bounds
+    for opts in (dict(), dict(beta1=0.5, beta2=0.8, clip_gradient=0.4, rescale_grad=0.14, wd=0.03)):
+        for shape in _SHAPES:
+            rng = np.random.default_rng(32)
+            w = rng.uniform(-1, 1, shape).astype(np.float32); w2 = w.copy()
+            mean, var = np.zeros(shape, np.float32), np.zeros(shape, np.float32)
+            opt = O.OracleOptimizer("lans", learning_rate=0.01, lower_bound=lb, upper_bound=ub, **opts)
+            for t in range(1, 5):
+                g = rng.uniform(-1, 1, shape).astype(np.float32)
+                opt.update(0, w, g.copy())
+                _np_lans_step(w2, g.copy(), mean, var, 0.01, opts.get("wd", 0.0), t, opts.get("beta1", 0.9),
+                              opts.get("beta2", 0.999), 1e-6, opts.get("rescale_grad", 1.0),
+                              opts.get("clip_gradient"), lb, ub)
+                np.testing.assert_allclose(w, w2, rtol=1e-3, atol=1e-3)     # test_optimizer.py:310-312
+
+
+@pytest.mark.parametrize("momentum", [0.0, 0.9])
+def test_lars_kernel_vs_python_step(momentum):
+    for opts in (dict(), dict(eta=0.01, clip_gradient=0.4, rescale_grad=0.14, wd=0.05)):
+        for shape in _SHAPES:
+            rng = np.random.default_rng(33)
+            w = rng.uniform(-1, 1, shape).astype(np.float32); w2 = w.copy()
+            mom = np.zeros(shape, np.float32) if momentum else None
+            opt = O.OracleOptimizer("lars", learning_rate=0.1, momentum=momentum, **opts)
+            for t in range(1, 5):
+                g = rng.uniform(-1, 1, shape).astype(np.float32)
+                opt.update(0, w, g.copy())
+                _np_lars_step(w2, g.copy(), mom, 0.1, opts.get("wd", 0.0), momentum, opts.get("eta", 0.001), 1e-8,
+                              opts.get("rescale_grad", 1.0), opts.get("clip_gradient"))
+                np.testing.assert_allclose(w, w2, rtol=1e-3, atol=1e-3)     # test_optimizer.py:251-253
+                assert np.max(np.abs(w - w2)) < 1e-6
+    # names ending in gamma / beta / bias keep the plain learning rate (lars.py:121-123)
+    rng = np.random.default_rng(34)
+    w = rng.uniform(-1, 1, 50).astype(np.float32); w2 = w.copy()
+    g = rng.uniform(-1, 1, 50).astype(np.float32)
+    O.OracleOptimizer("lars", learning_rate=0.1, no_trust=[3]).update(3, w, g.copy())
+    _np_lars_step(w2, g.copy(), None, 0.1, 0.0, 0.0, 0.001, 1e-8, 1.0, None, use_lars=False)
+    assert np.max(np.abs(w - w2)) < 1e-6
+
+
+def test_sum_sq_and_trust_ratio_edge_cases():
+    rng = np.random.default_rng(35)
+    x = rng.uniform(-1, 1, 100003).astype(np.float32)
+    exact = float(np.sum(x.astype(np.float64) ** 2))
+    assert abs(float(O.sum_sq(x, mode="f64")) - exact) <= 1e-7 * exact
+    assert abs(float(O.sum_sq(x, mode="seq")) - exact) <= 1e-4 * exact      # sequential float sum drifts
+    assert abs(float(O.sum_sq(x, 0.5, mode="f64")) - exact / 4) <= 1e-6 * exact
+    assert O.count_nonfinite(np.array([1, np.inf, -np.inf, np.nan, 0], np.float32)) == 3
+    # zero weight or zero update direction: ratio 1 (multi_lamb.cc:104-107)
+    w = np.zeros(16, np.float32); g = np.ones(16, np.float32)
+    opt = O.OracleOptimizer("lamb", learning_rate=0.5)
+    opt.update(0, w, g)
+    # step 1: m = 0.1 g, v = 0.001 g^2, bias-corrected -> ghat = 1/(1+eps); lr * 1 * ghat
+    np.testing.assert_allclose(w, -0.5 / (1 + 1e-6), rtol=1e-6)
+    # LARS with a zero gradient: ratio inf -> lars 1 -> plain sgd step (which is a no-op on g = 0, wd = 0)
+    w = np.ones(8, np.float32)
+    O.OracleOptimizer("lars", learning_rate=0.1).update(0, w, np.zeros(8, np.float32))
+    assert np.all(w == 1)
+
+
 def test_rsp_sum_and_retain_oracle_properties():
     rng = np.random.default_rng(2)
     rows, L = 50, 8

@@ -136,7 +136,7 @@ def cpu_kvstore_step_factory(shapes, n_values, threads, optimizer):
     stage = [[np.empty(e, np.float32) for _ in range(n_values)] for e in sizes]    # pinned merge/copy bufs
     weights = [rng.uniform(0, 1, e).astype(np.float32) for e in sizes]
     mom = [np.zeros(e, np.float32) for e in sizes]
-    mean = [np.zeros(e, np.float32) for e in sizes] if optimizer == "adam" else None
+    mean = [np.zeros(e, np.float32) for e in sizes] if optimizer in ("adam", "lamb", "lans") else None
     outs = [[np.empty(e, np.float32) for _ in range(n_values)] for e in sizes]
     lib = O.lib()
     import ctypes
@@ -159,6 +159,12 @@ def cpu_kvstore_step_factory(shapes, n_values, threads, optimizer):
                 O.adam_update(weights[k], merged, mean[k], mom[k], O.adam_lr(0.001, 0.9, 0.999, state["t"]))
             elif optimizer == "sgd":
                 O.sgd_mom_update(weights[k], merged, mom[k], 0.01, 1e-4, 0.9)
+            elif optimizer == "lamb":        # multi_lamb_update on the CPU: sequential norms + two passes
+                O.lamb_update(weights[k], merged, mean[k], mom[k], 0.001, 0.01, state["t"])
+            elif optimizer == "lans":
+                O.lans_update(weights[k], merged, mean[k], mom[k], 0.001, 0.01, state["t"])
+            elif optimizer == "lars":
+                O.sgd_mom_update(weights[k], merged, mom[k], O.lars_lr(0.1, weights[k], merged, 1e-4), 1e-4, 0.9)
             else:
                 weights[k][...] = merged
             for j in range(n_values):                                 # Broadcast: CopyFromTo(local, out_j)
@@ -386,7 +392,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="sweep", choices=["sweep", "resnet50", "bert", "resnet50-train", "rsp"])
     ap.add_argument("--batch", type=int, default=128, help="per-GPU batch of resnet50-train")
-    ap.add_argument("--optimizer", default=None, choices=[None, "sgd", "adam", "none"])
+    ap.add_argument("--optimizer", default=None, choices=[None, "sgd", "adam", "lamb", "lans", "lars", "none"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-nvls", action="store_true", help="keep gradients/weights out of multicast memory")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -464,8 +470,22 @@ def main():
     elif args.optimizer == "adam":
         kv.set_optimizer(mx.optimizer.Adam(learning_rate=0.001))
         bytes_per_elem_n1 = 8 * 4      # read g, w, m, v; write w, m, v, out
+    elif args.optimizer == "lamb":
+        kv.set_optimizer(mx.optimizer.LAMB(learning_rate=0.001, wd=0.01))
+        # first: read g, w, m, v; write m, v, ghat.  apply: read w, ghat; write w(store), out
+        bytes_per_elem_n1 = 11 * 4
+    elif args.optimizer == "lans":
+        kv.set_optimizer(mx.optimizer.LANS(learning_rate=0.001, wd=0.01))
+        # first: read g, w; write g.  mid: read g, w, m, v; write m, v, temp_m, temp_g.
+        # apply: read w, temp_m, temp_g; write w(store), out
+        bytes_per_elem_n1 = 16 * 4
+    elif args.optimizer == "lars":
+        kv.set_optimizer(mx.optimizer.LARS(learning_rate=0.1, momentum=0.9, wd=1e-4))
+        # first: read g, w; write g.  apply: read w, g, mom; write w(store), mom, out
+        bytes_per_elem_n1 = 9 * 4
     else:
         bytes_per_elem_n1 = 3 * 4      # read g; write store, out
+    layerwise = args.optimizer in ("lamb", "lans", "lars")
 
     def step():
         kv.pushpull(keys, grads, out=weights)
@@ -526,7 +546,8 @@ def main():
         peak = peaks.get("hbm_gbs", 6650.0)
         roof = {"bound": "hbm", "achieved": alg / (kern_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650",
-                "traffic": None, "kernel": "kv_dense_bulk_kernel", "kernel_ms": kern_ms,
+                "traffic": None, "kernel": "kv_norm_first/(mid)/apply_kernel sequence" if layerwise
+                else "kv_dense_bulk_kernel", "kernel_ms": kern_ms,
                 "algorithmic_bytes_per_launch": alg}
     else:
         nvls_active = exchange == "nvls-multicast" and world > 4

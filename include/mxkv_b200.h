@@ -142,6 +142,19 @@ MXKV_DLL int MXKVB200SetLearningRate(KVStoreHandle handle, double lr);
 /* per-key multipliers (Optimizer.set_lr_mult / set_wd_mult); pass str_key = NULL for int keys */
 MXKV_DLL int MXKVB200SetOptimizerMult(KVStoreHandle handle, int key, const char* str_key,
                                       float lr_mult, float wd_mult);
+/* The native counterpart of the reference's per-device Updater (python/mxnet/optimizer/updater.py:
+ * 39-93) and of the multi-tensor update operators it ends in when parameters are NOT updated on the
+ * kvstore (multi_sgd_update / multi_sgd_mom_update / multi_mp_sgd_*, src/operator/optimizer_op-inl.h:
+ * 207-375; multi_adamw, multi_lamb, multi_lans).  Create the handle with MXKVStoreCreate("updater"),
+ * give it an optimizer with MXKVB200SetOptimizer, then every call updates all (weight, grad) pairs
+ * IN PLACE with one launch (sequence) on their GPU.  Optimizer state of an index is created on first
+ * sight and is reachable through MXKVB200GetState / SetState / Get|SetUpdateCount.  One handle serves
+ * one device, like the reference's `Trainer._updaters[dev]`.  Never collective.  grads == NULL only
+ * registers the indices with their weights (so that states can be loaded before the first update). */
+MXKV_DLL int MXKVB200UpdaterStep(KVStoreHandle handle, uint32_t num, const int* keys,
+                                 NDArrayHandle* weights, NDArrayHandle* grads);
+MXKV_DLL int MXKVB200UpdaterStepEx(KVStoreHandle handle, uint32_t num, const char** keys,
+                                   NDArrayHandle* weights, NDArrayHandle* grads);
 /* per-key switch of a fused optimizer.  "no_trust_ratio" != 0: LARS keeps the plain learning rate
  * for this key (the reference does so for names ending in gamma / beta / bias, lars.py:121-123). */
 MXKV_DLL int MXKVB200SetKeyFlag(KVStoreHandle handle, int key, const char* str_key, const char* name,

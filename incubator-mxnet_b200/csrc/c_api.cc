@@ -482,6 +482,33 @@ int MXKVB200SetUpdateCount(KVStoreHandle handle, int key, const char* str_key, i
   API_END();
 }
 
+int MXKVB200UpdaterStep(KVStoreHandle handle, uint32_t num, const int* keys, NDArrayHandle* weights,
+                        NDArrayHandle* grads) {
+  API_BEGIN();
+  std::vector<int> k(keys, keys + num);
+  std::vector<NDArray> w, g;
+  for (uint32_t i = 0; i < num; ++i) {
+    w.push_back(*ND(weights[i]));
+    if (grads != nullptr) g.push_back(*ND(grads[i]));
+  }
+  KV(handle)->UpdaterStep(false, k, {}, w, g);
+  API_END();
+}
+
+int MXKVB200UpdaterStepEx(KVStoreHandle handle, uint32_t num, const char** keys, NDArrayHandle* weights,
+                          NDArrayHandle* grads) {
+  API_BEGIN();
+  std::vector<std::string> k;
+  std::vector<NDArray> w, g;
+  for (uint32_t i = 0; i < num; ++i) {
+    k.emplace_back(keys[i]);
+    w.push_back(*ND(weights[i]));
+    if (grads != nullptr) g.push_back(*ND(grads[i]));
+  }
+  KV(handle)->UpdaterStep(true, {}, k, w, g);
+  API_END();
+}
+
 int MXKVB200SetKeyFlag(KVStoreHandle handle, int key, const char* str_key, const char* name, int value) {
   API_BEGIN();
   MXKV_CHECK(name != nullptr) << "flag name is null";

@@ -23,26 +23,32 @@ KVStore::KVStore(const std::string& type) : type_(type) {
       << "distributed kvstore types ('" << type << "') are out of scope of this library";
   MXKV_CHECK(t.find("nccl") == std::string::npos)
       << "kvstore type 'nccl' is not provided; use 'device'";
-  device_mode_ = t.find("device") != std::string::npos;
+  // 'updater': not a store of the reference -- the native counterpart of its per-device Updater
+  // (python/mxnet/optimizer/updater.py:30-127): optimizer state + fused multi-tensor updates of
+  // caller-owned weights (UpdaterStep), never collective even in one-process-per-GPU mode
+  solo_ = t.find("updater") != std::string::npos;
+  device_mode_ = solo_ || t.find("device") != std::string::npos;
   order_ = device_mode_ ? ORDER_DEVICE : ORDER_COMMCPU;
 }
+
+ProcessGroup* KVStore::PG() const { return solo_ ? nullptr : Runtime::Get()->pg(); }
 
 KVStore::~KVStore() {
   try { Runtime::Get()->WaitAll(); } catch (...) {}
 }
 
 int KVStore::rank() const {
-  ProcessGroup* pg = Runtime::Get()->pg();
+  ProcessGroup* pg = PG();
   return pg ? pg->rank() : 0;
 }
 int KVStore::group_size() const {
-  ProcessGroup* pg = Runtime::Get()->pg();
+  ProcessGroup* pg = PG();
   return pg ? pg->world() : 1;
 }
 
 void KVStore::Barrier() {
   Runtime::Get()->WaitAll();
-  ProcessGroup* pg = Runtime::Get()->pg();
+  ProcessGroup* pg = PG();
   if (pg) pg->Barrier();
 }
 
@@ -292,7 +298,7 @@ Replica& KVStore::EnsureReplica(KeyState& ks, int dev) {
                                                    << rt->pg()->dev();
   Replica nr;
   nr.dev = dev;
-  nr.local = NDArray::Empty(ks.shape, Context{kGPU, dev}, ks.dtype, /*symmetric=*/rt->pg() != nullptr);
+  nr.local = NDArray::Empty(ks.shape, Context{kGPU, dev}, ks.dtype, /*symmetric=*/PG() != nullptr);
   if (!ks.reps.empty()) {
     if (ks.local_world > 0) GatherLocal(ks);
     if (ks.has_state) GatherState(ks);   // make every existing replica's optimizer state complete
@@ -300,7 +306,7 @@ Replica& KVStore::EnsureReplica(KeyState& ks, int dev) {
     CopyFromTo(src.local, nr.local);
     // a GPU joining later (e.g. states were loaded before the first multi-GPU push) inherits the state
     const Context nctx{kGPU, dev};
-    const bool sym = rt->pg() != nullptr;
+    const bool sym = PG() != nullptr;
     if (!src.w32.is_none()) { nr.w32 = NDArray::Empty(ks.shape, nctx, kFloat32, sym); CopyFromTo(src.w32, nr.w32); }
     if (!src.s0.is_none()) { nr.s0 = NDArray::Empty(ks.shape, nctx, kFloat32, sym); CopyFromTo(src.s0, nr.s0); }
     if (!src.s1.is_none()) { nr.s1 = NDArray::Empty(ks.shape, nctx, kFloat32, sym); CopyFromTo(src.s1, nr.s1); }
@@ -317,7 +323,7 @@ Replica& KVStore::EnsureReplica(KeyState& ks, int dev) {
 
 void KVStore::EnsureState(KeyState& ks, Replica& r, bool mp) {
   Runtime* rt = Runtime::Get();
-  const bool sym = rt->pg() != nullptr;
+  const bool sym = PG() != nullptr;
   const Context ctx{kGPU, r.dev};
   DeviceGuard g(r.dev);
   cudaStream_t s = rt->Dev(r.dev).stream;
@@ -364,7 +370,7 @@ void KVStore::EnsureState(KeyState& ks, Replica& r, bool mp) {
 void KVStore::InitImpl(const std::vector<int>& keys, const std::vector<NDArray>& vals) {
   MXKV_CHECK(keys.size() == vals.size()) << "Init: " << keys.size() << " keys but " << vals.size() << " values";
   Runtime* rt = Runtime::Get();
-  ProcessGroup* pg = rt->pg();
+  ProcessGroup* pg = PG();
   for (size_t i = 0; i < keys.size(); ++i) {
     MXKV_CHECK(keys_.find(keys[i]) == keys_.end())
         << "duplicate init of key " << keys[i]
@@ -407,7 +413,7 @@ void KVStore::InitImpl(const std::vector<int>& keys, const std::vector<NDArray>&
 // replica; rank 0 copies onto itself).  Collective.
 void KVStore::BroadcastFromRank0(KeyState& ks, Replica& r) {
   Runtime* rt = Runtime::Get();
-  ProcessGroup* pg = rt->pg();
+  ProcessGroup* pg = PG();
   if (pg == nullptr || pg->world() <= 1) return;
   TensorWork tw;
   std::memset(&tw, 0, sizeof(tw));
@@ -630,7 +636,7 @@ class AliasIndex {
 // kernel is hidden.  The kernel is the same work-list kernel, launched on an element range.
 bool KVStore::HostPipelined(std::vector<Group>& groups, bool write_outs) {
   Runtime* rt = Runtime::Get();
-  ProcessGroup* pg = rt->pg();
+  ProcessGroup* pg = PG();
   if (pg != nullptr && pg->world() > 1) return false;
   if (updater_ != nullptr) return false;
   if (opt_.enabled && IsNormOpt(opt_.kind)) return false;   // per-key norms need the whole key in one launch
@@ -774,7 +780,7 @@ bool KVStore::HostPipelined(std::vector<Group>& groups, bool write_outs) {
 // runs the ordinary fused reduce(+update) kernel on its own replica -- no root, no broadcast.
 void KVStore::ReduceUpdateCompressed(std::vector<Group>& groups, bool write_outs) {
   Runtime* rt = Runtime::Get();
-  ProcessGroup* pg = rt->pg();
+  ProcessGroup* pg = PG();
   const bool mp_mode = pg != nullptr;
   const bool callback = updater_ != nullptr;
   MXKV_CHECK(!callback) << "gradient compression together with a Python updater callback is not supported; "
@@ -948,7 +954,7 @@ void KVStore::ReduceUpdate(std::vector<Group>& groups, bool write_outs) {
   if (gc_bits_ != 0) { ReduceUpdateCompressed(groups, write_outs); return; }
   if (HostPipelined(groups, write_outs)) return;
   Runtime* rt = Runtime::Get();
-  ProcessGroup* pg = rt->pg();
+  ProcessGroup* pg = PG();
   const bool mp_mode = pg != nullptr;
   const bool callback = updater_ != nullptr;
   const bool fused = opt_.enabled && !callback;
@@ -1341,7 +1347,7 @@ void KVStore::ReduceUpdate(std::vector<Group>& groups, bool write_outs) {
 void KVStore::LaunchWorks(const LaunchClassKey& ck, std::vector<std::vector<TensorWork>>& per_part,
                           const std::vector<int64_t>& busiest, int opt_kind, const std::vector<int>& part_dev) {
   Runtime* rt = Runtime::Get();
-  ProcessGroup* pg = rt->pg();
+  ProcessGroup* pg = PG();
   const bool mp_mode = pg != nullptr;
   const int n_part = static_cast<int>(part_dev.size());
   const int my_first = mp_mode ? pg->rank() : 0;
@@ -1443,7 +1449,7 @@ void KVStore::LaunchWorks(const LaunchClassKey& ck, std::vector<std::vector<Tens
 
 // A launch that involves one GPU only (no rendezvous), whatever the deployment shape.
 void KVStore::LaunchLocal(const LaunchClassKey& ck, const TensorWork& tw, int opt_kind, int dev) {
-  ProcessGroup* pg = Runtime::Get()->pg();
+  ProcessGroup* pg = PG();
   const int slots = pg ? pg->world() : 1;
   const int mine = pg ? pg->rank() : 0;
   std::vector<std::vector<TensorWork>> per_part(slots);
@@ -1460,7 +1466,7 @@ void KVStore::GatherLocal(KeyState& ks) {
   const int n = ks.local_world;
   if (n <= 1) { ks.local_world = 0; return; }
   Runtime* rt = Runtime::Get();
-  ProcessGroup* pg = rt->pg();
+  ProcessGroup* pg = PG();
   const bool mp_mode = pg != nullptr;
   const std::vector<int> part_dev = ks.shard_devs;
   MXKV_CHECK(static_cast<int>(part_dev.size()) == n) << "inconsistent shard layout for key " << ks.key;
@@ -1525,7 +1531,7 @@ void KVStore::RunCallbackUpdater(KeyState& ks, Replica& root) {
 void KVStore::GatherState(KeyState& ks) {
   // sharded layout -> every replica complete.  Shard p of {w32,s0,s1} is valid on participant p.
   Runtime* rt = Runtime::Get();
-  ProcessGroup* pg = rt->pg();
+  ProcessGroup* pg = PG();
   const int n = ks.state_world;
   if (n <= 1) return;
   const int64_t shard = ShardLen(ks.size, n);
@@ -1563,6 +1569,76 @@ void KVStore::GatherState(KeyState& ks) {
   gather([](Replica& r) -> NDArray& { return r.s0; });
   gather([](Replica& r) -> NDArray& { return r.s1; });
   ks.state_world = 0;
+}
+
+// Updater.__call__ (python/mxnet/optimizer/updater.py:39-93) + the multi-tensor update operators it
+// ends in (multi_sgd_update / multi_sgd_mom_update / multi_mp_sgd_* optimizer_op-inl.h:207-375,
+// multi_adamw contrib/adamw-inl.h:329-464, multi_lamb / multi_lans): every (weight, grad) pair of
+// the call is updated IN PLACE in one launch (sequence) on the arrays' GPU; the optimizer state of an
+// index is created on first sight (create_state_multi_precision) and lives in this object.
+void KVStore::UpdaterStep(bool str_keys, const std::vector<int>& ikeys, const std::vector<std::string>& skeys,
+                          const std::vector<NDArray>& weights, const std::vector<NDArray>& grads) {
+  LOCK();
+  MXKV_CHECK(solo_) << "UpdaterStep needs a store created with type 'updater'";
+  MXKV_CHECK(opt_.enabled && updater_ == nullptr) << "set a fused optimizer first (MXKVB200SetOptimizer)";
+  const size_t n = weights.size();
+  const bool bind_only = grads.empty() && n > 0;     // register the indices (e.g. before loading states)
+  MXKV_CHECK((bind_only || grads.size() == n) && (str_keys ? skeys.size() : ikeys.size()) == n)
+      << "UpdaterStep: keys / weights / grads differ in length";
+  SetKeyType(str_keys ? kStringKey : kIntKey);
+  std::vector<Group> groups;
+  for (size_t i = 0; i < n; ++i) {
+    int key;
+    if (str_keys) {
+      auto it = str_key_dict_.find(skeys[i]);
+      if (it == str_key_dict_.end()) {
+        key = next_str_key_++;
+        str_key_dict_[skeys[i]] = key;
+        reverse_str_key_dict_[key] = skeys[i];
+      } else {
+        key = it->second;
+      }
+    } else {
+      key = ikeys[i];
+    }
+    const NDArray& w = weights[i];
+    MXKV_CHECK(w.stype() == kDefaultStorage && w.ctx().is_gpu()) << "UpdaterStep: dense GPU arrays only";
+    if (!bind_only) {
+      const NDArray& g = grads[i];
+      MXKV_CHECK(g.stype() == kDefaultStorage && g.ctx().is_gpu() && w.dev() == g.dev())
+          << "UpdaterStep: weight and gradient of index " << key << " must be dense arrays on the same GPU";
+    }
+    auto it = keys_.find(key);
+    if (it == keys_.end()) {
+      KeyState ks;
+      ks.key = key;
+      ks.shape = w.shape();
+      ks.dtype = w.dtype();
+      ks.size = w.size();
+      it = keys_.emplace(key, ks).first;
+    }
+    KeyState& ks = it->second;
+    MXKV_CHECK(ks.size == w.size() && ks.dtype == w.dtype())
+        << "UpdaterStep: weight of index " << key << " changed shape or dtype";
+    Replica* r = FindReplica(ks, w.dev());
+    if (r == nullptr) {
+      MXKV_CHECK(ks.reps.empty()) << "an updater serves one device (index " << key << " was first seen on GPU "
+                                  << ks.reps[0].dev << "); the reference keeps one Updater per device, too";
+      Replica nr;
+      nr.dev = w.dev();
+      ks.reps.push_back(nr);
+      r = &ks.reps.back();
+    }
+    r->local = w;          // alias of the caller's array: the kernel's store target
+    r->fresh = true;
+    ks.local_world = 0;
+    if (bind_only) continue;
+    Group grp;
+    grp.key = key;
+    grp.vals = {grads[i]};
+    groups.push_back(grp);
+  }
+  if (!groups.empty()) ReduceUpdate(groups, false);
 }
 
 NDArray KVStore::GetState(bool str_key, int ikey, const std::string& skey, int which) {

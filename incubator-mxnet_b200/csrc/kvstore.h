@@ -129,6 +129,9 @@ class KVStore {
   // fused optimizer (B200 extension; replaces the Python Updater round trip)
   void SetOptimizer(const std::string& name, const std::vector<std::pair<std::string, std::string>>& kwargs);
   void SetOptimizerMult(bool str_key, int ikey, const std::string& skey, float lr_mult, float wd_mult);
+  // type 'updater' only: in-place fused update of caller-owned (weight, grad) pairs (kvstore.cc)
+  void UpdaterStep(bool str_keys, const std::vector<int>& ikeys, const std::vector<std::string>& skeys,
+                   const std::vector<NDArray>& weights, const std::vector<NDArray>& grads);
   void SetLearningRate(double lr) { opt_.lr = lr; }
   bool has_fused_optimizer() const { return opt_.enabled; }
   // which: 0 stored value, 1 fp32 master, 2 state0, 3 state1; gathers shards so the result is complete
@@ -195,8 +198,10 @@ class KVStore {
   float KeyLR(const KeyState& ks) const;
   float KeyWD(const KeyState& ks) const;
 
+  ProcessGroup* PG() const;     // the process group this store exchanges over (none for 'updater' stores)
   std::string type_;
   bool device_mode_ = false;
+  bool solo_ = false;
   int order_ = ORDER_DEVICE;
   std::unordered_map<int, KeyState> keys_;
   std::unordered_map<std::string, int> str_key_dict_;

@@ -16,7 +16,7 @@ namespace mxkv {
 
 void KVStore::LaunchNormWorks(std::vector<NormClass>& classes, int opt_kind, const std::vector<int>& part_dev) {
   Runtime* rt = Runtime::Get();
-  ProcessGroup* pg = rt->pg();
+  ProcessGroup* pg = PG();
   const bool mp_mode = pg != nullptr;
   const int n_part = static_cast<int>(part_dev.size());
   const int my_first = mp_mode ? pg->rank() : 0;

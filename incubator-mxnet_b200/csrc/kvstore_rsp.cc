@@ -43,7 +43,7 @@ static void PublishNnz(const NDArray& a) {
 
 void KVStore::InitRowSparseKey(KeyState& ks, const NDArray& v) {
   Runtime* rt = Runtime::Get();
-  ProcessGroup* pg = rt->pg();
+  ProcessGroup* pg = PG();
   MXKV_CHECK(v.dtype() == kFloat32) << "row_sparse keys support float32 only";
   MXKV_CHECK(v.shape().size() >= 2) << "row_sparse keys need at least 2 dimensions";
   const Context c = v.ctx();
@@ -97,7 +97,7 @@ static void EnsureRspWorkspace(KeyState& ks, Replica& r, int n, int64_t cap) {
 
 void KVStore::PushRowSparse(KeyState& ks, const std::vector<NDArray>& vals) {
   Runtime* rt = Runtime::Get();
-  ProcessGroup* pg = rt->pg();
+  ProcessGroup* pg = PG();
   const bool mp_mode = pg != nullptr;
   MXKV_CHECK(ks.stype == kRowSparseStorage)
       << "key " << ks.key << " was initialised dense; row_sparse push needs a row_sparse key";

@@ -235,7 +235,7 @@ class KVStore(KVStoreBase):
                     self.set_key_flag(k, "no_trust_ratio", 1)
         else:
             self._fused = False
-            self._set_updater(opt.get_updater(optimizer))
+            self._set_updater(opt.get_updater(optimizer, native=False))
 
     def set_mult(self, key, lr_mult=1.0, wd_mult=1.0):
         if isinstance(key, str):
@@ -299,6 +299,10 @@ class KVStore(KVStoreBase):
             with open(fname, "wb") as fout:
                 fout.write(self._updater.get_states(dump_optimizer))
             return
+        with open(fname, "wb") as fout:
+            fout.write(self._dump_fused_states(dump_optimizer))
+
+    def _dump_fused_states(self, dump_optimizer=False):
         states = {}
         for k in sorted(self._keys, key=str):
             ent = {}
@@ -316,8 +320,7 @@ class KVStore(KVStoreBase):
         payload = {"format": "mxkv_b200_fused_v1", "states": states}
         if dump_optimizer:
             payload["optimizer"] = self._optimizer
-        with open(fname, "wb") as fout:
-            fout.write(pickle.dumps(payload))
+        return pickle.dumps(payload)
 
     def load_optimizer_states(self, fname):
         with open(fname, "rb") as fin:
@@ -326,9 +329,14 @@ class KVStore(KVStoreBase):
             assert self._updater is not None, "Cannot load states for distributed training"
             self._updater.set_states(blob)
             return
-        payload = pickle.loads(blob)
+        self._load_fused_states(blob)
+
+    def _load_fused_states(self, blob, only=None):
+        payload = pickle.loads(blob) if isinstance(blob, bytes) else blob
         assert payload.get("format") == "mxkv_b200_fused_v1", "not a fused-optimizer state file"
         for k, ent in payload["states"].items():
+            if only is not None and k not in only:
+                continue
             for which, name in ((1, "weight32"), (2, "state0"), (3, "state1")):
                 if name in ent:
                     v = _nd.array(ent[name], dtype=np.float32)

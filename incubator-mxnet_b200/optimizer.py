@@ -327,5 +327,69 @@ class Updater(object):
         self._host_states = True
 
 
-def get_updater(optimizer):
-    return Updater(optimizer)
+class NativeUpdater(object):
+    """Same call contract as :class:`Updater` (updater.py:39-93; ``index`` / ``grad`` / ``weight`` may be
+    lists), but the whole list is updated IN PLACE by one fused launch (sequence) of the native engine
+    -- what the reference does with ``multi_sgd_mom_update`` / ``multi_mp_sgd_*`` / ``multi_adamw`` /
+    ``multi_lamb`` / ``multi_lans`` when parameters are not updated on the kvstore (sgd.py:170-213,
+    lamb.py:170-215).  One instance serves one device, like ``Trainer._updaters[dev]``."""
+
+    def __init__(self, optimizer):
+        from . import kvstore as _kvs
+        assert getattr(optimizer, "fused_name", None), "no fused kernel for %s" % type(optimizer).__name__
+        self.optimizer = optimizer
+        self._kv = _kvs.KVStore("updater")
+        self._kw = None
+        self._pending = None          # states loaded before the indices are known to the engine
+        self._sync()
+
+    def _sync(self):
+        kw = self.optimizer.fused_kwargs()
+        kw.pop("learning_rate", None)
+        if kw != self._kw:            # rescale_grad etc. changed (Trainer.step sets it per batch size)
+            self._kv.set_optimizer(self.optimizer)
+            self._kw = kw
+        self._kv._sync_lr()
+
+    def __call__(self, index, grad, weight):
+        from .base import _LIB, check_call, c_str_array
+        import ctypes
+        if not isinstance(index, (list, tuple)):
+            index, grad, weight = [index], [grad], [weight]
+        self._sync()
+        n = len(index)
+        use_str = isinstance(index[0], str)
+        wh = (ctypes.c_void_p * n)(*[w.handle.value for w in weight])
+        gh = (ctypes.c_void_p * n)(*[g.handle.value for g in grad])
+        keys = c_str_array(list(index)) if use_str else (ctypes.c_int * n)(*[int(i) for i in index])
+        fn = _LIB.MXKVB200UpdaterStepEx if use_str else _LIB.MXKVB200UpdaterStep
+        if self._pending is not None:
+            have = [i for i in index if i in self._pending["states"]]
+            if have:
+                check_call(fn(self._kv.handle, n, keys, wh, None))          # register, then load
+                self._kv._load_fused_states(self._pending, only=set(have))
+                for i in have:
+                    del self._pending["states"][i]
+        check_call(fn(self._kv.handle, n, keys, wh, gh))
+        self._kv._keys.update(index)
+        for i in index:               # keep the Python-side bookkeeping of Optimizer._update_count
+            self.optimizer._update_count(i)
+
+    def get_states(self, dump_optimizer=False):
+        return self._kv._dump_fused_states(dump_optimizer)
+
+    def set_states(self, states):
+        payload = pickle.loads(states)
+        assert payload.get("format") == "mxkv_b200_fused_v1", "not a fused-optimizer state blob"
+        if "optimizer" in payload:
+            self.optimizer = payload["optimizer"]
+            self._kw = None
+        self._pending = {"format": payload["format"], "states": dict(payload["states"])}
+
+
+def get_updater(optimizer, native=None):
+    """updater.py:130-143.  ``native`` (default: whenever the optimizer has a fused kernel) selects the
+    engine-side multi-tensor updater; otherwise the generic Python one."""
+    if native is None:
+        native = bool(getattr(optimizer, "fused_name", None))
+    return NativeUpdater(optimizer) if native else Updater(optimizer)

@@ -135,15 +135,22 @@ class Trainer(object):
         self._allreduce_grads()
 
     def _update(self):
-        """trainer.py:444-480: per-device local updaters (non-fused torch ops)."""
+        """trainer.py:444-480: per-device local updaters.  Optimizers with a fused kernel update every
+        parameter of a device in one native launch (the reference's aggregated multi_* operators);
+        the others run the generic Python updater per parameter."""
         if not hasattr(self, "_updaters"):
             ndev = len(self._params[0])
             self._updaters = [_opt.get_updater(self._optimizer) for _ in range(ndev)]
-        if self._grads is None:
+        if self._grads is None or any(p.grad.data_ptr() != q for reps, ptrs in zip(self._params, self._grad_ptrs)
+                                      for p, q in zip(reps, ptrs)):
             self._bind_grads()
-        for i, (ws, gs) in enumerate(zip(self._weights, self._grads)):
-            for upd, w, g in zip(self._updaters, ws, gs):
-                upd(i, g, w)
+        idx = list(range(len(self._params)))
+        for d, upd in enumerate(self._updaters):
+            if isinstance(upd, _opt.NativeUpdater):
+                upd(idx, [gs[d] for gs in self._grads], [ws[d] for ws in self._weights])
+            else:
+                for i in idx:
+                    upd(i, self._grads[i][d], self._weights[i][d])
 
     def save_states(self, fname):
         assert self._kv_initialized

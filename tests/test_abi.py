@@ -131,3 +131,15 @@ def test_dlpack_roundtrip_on_host():
     out = mx.nd.zeros((3, 4))
     kv.pull("w", out=out)
     assert out.asnumpy()[0, 0] == 42.0
+
+
+def test_native_library_is_current():
+    """The in-tree .so must have been rebuilt after the last source edit (it travels to the GPU box
+    as built; __graft_entry__.build() does this)."""
+    import importlib.util, os
+    spec = importlib.util.spec_from_file_location(
+        "mxkv_build", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                   "incubator-mxnet_b200", "build.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    assert not b.needs_build(), "libmxkv_b200.so is older than its sources: run python __graft_entry__.py"

@@ -121,9 +121,16 @@ class Trainer(object):
         elif self._update_on_kvstore and self._kvstore is not None and \
                 getattr(self._kvstore, "_last_rescale", None) != self._optimizer.rescale_grad:
             self._kvstore.set_optimizer(self._optimizer)
+        scaler = getattr(self, "_amp_loss_scaler", None)
         if self._kvstore is not None:
             self._kvstore._last_rescale = self._optimizer.rescale_grad
             self._allreduce_grads()
+            if scaler is not None and self._update_on_kvstore:
+                # the push decided on the device (optimizer created with skip_nonfinite=True)
+                assert getattr(self._optimizer, "skip_nonfinite", False), \
+                    "AMP with update_on_kvstore needs an optimizer created with skip_nonfinite=True " \
+                    "(lamb / lans / lars); otherwise use update_on_kvstore=False"
+                scaler.update(self._kvstore.overflow())
         if not self._update_on_kvstore:
             self._update()
 
@@ -144,6 +151,9 @@ class Trainer(object):
         if self._grads is None or any(p.grad.data_ptr() != q for reps, ptrs in zip(self._params, self._grad_ptrs)
                                       for p, q in zip(reps, ptrs)):
             self._bind_grads()
+        scaler = getattr(self, "_amp_loss_scaler", None)
+        if scaler is not None and scaler.has_overflow([gs[0] for gs in self._grads]):
+            return          # skip on overflow (trainer.py:445-448)
         idx = list(range(len(self._params)))
         for d, upd in enumerate(self._updaters):
             if isinstance(upd, _opt.NativeUpdater):

@@ -282,6 +282,50 @@ def test_skip_nonfinite_leaves_everything_untouched():
             assert _bits_equal(outs[k].asnumpy(), snap_w[k])
 
 
+def test_lamb_after_gradient_compression():
+    """2-bit compressed exchange (comm.h:556-605) feeding the LAMB sequence: the dequantised sum is what
+    the optimizer sees, on every consumer GPU."""
+    E, n, thr = 10000, 4, 0.5
+    rng = _rng(31)
+    w0 = rng.uniform(-1, 1, E).astype(np.float32)
+    kw = dict(learning_rate=0.01, wd=0.01)
+    kv = mx.kv.create("device")
+    kv.set_gradient_compression({"type": "2bit", "threshold": thr})
+    kv.init(0, mx.nd.array(w0, mx.gpu(0)))
+    kv.set_optimizer(mx.optimizer.LAMB(**kw))
+    oopt = O.OracleOptimizer("lamb", norm_mode="f64", **kw)
+    ow = w0.copy()
+    residual = [np.zeros(E, np.float32) for _ in range(n)]
+    out = mx.nd.empty((E,), mx.gpu(0))
+    for step in range(3):
+        grads = [rng.uniform(-1, 1, E).astype(np.float32) for _ in range(n)]
+        kv.pushpull(0, [mx.nd.array(g, mx.gpu(0)) for g in grads], out=out)
+        deq = [O.dequantize_2bit(O.quantize_2bit(g, r, thr), E, thr) for g, r in zip(grads, residual)]
+        oopt.update(0, ow, O.sum_device(deq))
+        np.testing.assert_allclose(out.asnumpy(), ow, rtol=RTOL, atol=ATOL, err_msg="step %d" % step)
+
+
+def test_host_resident_values_and_outputs():
+    """kv.create('local')-style use: gradients and outputs in host memory (staged through the GPU; the
+    segment pipeline of the one-pass optimizers cannot be used -- a norm needs the whole key)."""
+    E, n = 300007, 2
+    rng = _rng(37)
+    w0 = rng.uniform(-1, 1, E).astype(np.float32)
+    for name, kw in (("lars", dict(learning_rate=0.1, momentum=0.9, wd=1e-3, eta=0.01)),
+                     ("lamb", dict(learning_rate=0.01, wd=0.01))):
+        kv = mx.kv.create("local")
+        kv.init("w", mx.nd.array(w0))
+        kv.set_optimizer(mx.optimizer.create(name, **kw))
+        oopt = O.OracleOptimizer(name, norm_mode="f64", **kw)
+        ow = w0.copy()
+        out = mx.nd.empty((E,), mx.cpu())
+        for step in range(2):
+            grads = [rng.uniform(-1, 1, E).astype(np.float32) for _ in range(n)]
+            kv.pushpull("w", [mx.nd.array(g) for g in grads], out=out)
+            oopt.update(0, ow, O.sum_cpu([g.copy() for g in grads], 4).reshape(E))
+            np.testing.assert_allclose(out.asnumpy(), ow, rtol=RTOL, atol=ATOL, err_msg="%s step %d" % (name, step))
+
+
 def test_states_round_trip_through_checkpoint(tmp_path):
     """save / load_optimizer_states with LAMB's mean / var (kvstore.py:647-672)."""
     E = 20011

@@ -103,3 +103,68 @@ def test_trainer_save_load_states(tmp_path):
     got = run(t2, m2, 2)
     for a, b in zip(got, want):
         assert _bits_equal(a, b)
+
+
+def test_amp_loss_scaler_skips_local_update_on_overflow():
+    """amp.init_trainer + scale_loss (amp.py:290-298,374-400) with parameters updated outside the
+    kvstore: an inf gradient skips the whole update and halves the scale; clean steps are unscaled by
+    rescale_grad (gluon/trainer.py:445-448, loss_scaler.py:44-79)."""
+    import torch
+    model = _model()
+    params = list(model.parameters())
+    t = mx.Trainer(params, "sgd", {"learning_rate": 0.1}, kvstore=None)
+    mx.amp.init_trainer(t)
+    assert t._amp_loss_scaler.loss_scale == 2. ** 16
+    x = torch.randn(8, 64, device="cuda")
+    # clean step
+    model.zero_grad()
+    with mx.amp.scale_loss(model(x).sum(), t) as scaled:
+        scaled.backward()
+    before = [p.detach().clone() for p in params]
+    grads = [p.grad.detach().clone() / 2. ** 16 for p in params]
+    t.step(8)
+    for p, b, g in zip(params, before, grads):
+        assert torch.allclose(p, b - 0.1 * g / 8, rtol=1e-5, atol=1e-6)
+    # overflow
+    model.zero_grad()
+    with mx.amp.scale_loss(model(x).sum(), t) as scaled:
+        scaled.backward()
+    params[1].grad[0] = float("inf")
+    before = [p.detach().clone() for p in params]
+    t.step(8)
+    for p, b in zip(params, before):
+        assert torch.equal(p, b)
+    assert t._amp_loss_scaler._next_loss_scale == 2. ** 15
+    # the next step runs with the halved scale
+    model.zero_grad()
+    with mx.amp.scale_loss(model(x).sum(), t) as scaled:
+        scaled.backward()
+    assert t._amp_loss_scaler.loss_scale == 2. ** 16      # switched at the next has_overflow (loss_scaler.py:67)
+    t.step(8)
+    assert t._amp_loss_scaler.loss_scale == 2. ** 15
+
+
+def test_amp_with_update_on_kvstore_and_device_side_skip():
+    """LAMB created with skip_nonfinite=True, parameters updated on the kvstore: the push itself skips
+    on overflow and the Trainer feeds KVStore.overflow() to the loss scaler."""
+    import torch
+    model = _model()
+    params = list(model.parameters())
+    t = mx.Trainer(params, mx.optimizer.LAMB(learning_rate=0.01, skip_nonfinite=True), kvstore="device")
+    mx.amp.init_trainer(t)
+    x = torch.randn(8, 64, device="cuda")
+    model.zero_grad()
+    with mx.amp.scale_loss(model(x).square().mean(), t) as scaled:
+        scaled.backward()
+    t.step(1)
+    torch.cuda.synchronize()
+    after_clean = [p.detach().clone() for p in params]
+    model.zero_grad()
+    with mx.amp.scale_loss(model(x).square().mean(), t) as scaled:
+        scaled.backward()
+    params[0].grad.view(-1)[5] = float("nan")
+    t.step(1)
+    torch.cuda.synchronize()
+    for p, b in zip(params, after_clean):
+        assert torch.equal(p, b)
+    assert t._amp_loss_scaler._next_loss_scale == 2. ** 15

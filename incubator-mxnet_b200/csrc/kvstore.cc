@@ -21,13 +21,14 @@ KVStore::KVStore(const std::string& type) : type_(type) {
   const std::string t = Lower(type);
   MXKV_CHECK(t.find("dist") == std::string::npos)
       << "distributed kvstore types ('" << type << "') are out of scope of this library";
-  MXKV_CHECK(t.find("nccl") == std::string::npos)
-      << "kvstore type 'nccl' is not provided; use 'device'";
+  // 'nccl' (KVStoreNCCL, src/kvstore/kvstore_nccl.h:62-551: rooted ncclReduce + ncclBcast per key) is
+  // served by the same engine: NCCL leaves its summation order unspecified, so the device order is a
+  // conforming result for that name ("parity unpinned" for this one type).
   // 'updater': not a store of the reference -- the native counterpart of its per-device Updater
   // (python/mxnet/optimizer/updater.py:30-127): optimizer state + fused multi-tensor updates of
   // caller-owned weights (UpdaterStep), never collective even in one-process-per-GPU mode
   solo_ = t.find("updater") != std::string::npos;
-  device_mode_ = solo_ || t.find("device") != std::string::npos;
+  device_mode_ = solo_ || t.find("device") != std::string::npos || t.find("nccl") != std::string::npos;
   order_ = device_mode_ ? ORDER_DEVICE : ORDER_COMMCPU;
 }
 

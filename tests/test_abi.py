@@ -143,3 +143,48 @@ def test_native_library_is_current():
     b = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(b)
     assert not b.needs_build(), "libmxkv_b200.so is older than its sources: run python __graft_entry__.py"
+
+
+def test_store_types_of_the_reference_factory():
+    """KVStore::Create (src/kvstore/kvstore.cc:42-85): local / device / nccl names are served, dist is not."""
+    for name in ("local", "device", "local_update_cpu", "local_allreduce_cpu", "local_allreduce_device", "nccl"):
+        kv = mx.kv.create(name)
+        assert kv.type == name and kv.rank == 0 and kv.num_workers == 1
+    with pytest.raises(mx.MXNetError):
+        mx.kv.create("dist_sync")
+
+
+def test_loss_scaler_schedule():
+    """loss_scaler.py:67-79: halve on overflow (effective one step later), double after scale_seq_len clean steps."""
+    s = mx.amp.LossScaler(init_scale=1024., scale_seq_len=3, max_loss_scale=4096.)
+    assert s.update(True) is True and s.loss_scale == 1024. and s._next_loss_scale == 512.
+    assert s.update(False) is False and s.loss_scale == 512.
+    s.update(False)
+    s.update(False)                       # third clean step: schedule a doubling
+    assert s._next_loss_scale == 1024.
+    s.update(False)
+    assert s.loss_scale == 1024.
+    for _ in range(12):
+        s.update(False)
+    assert s.loss_scale <= 4096. and s._next_loss_scale == 4096.
+
+
+def test_layerwise_optimizer_descriptors():
+    """hyper-parameter names handed to MXKVB200SetOptimizer follow python/mxnet/optimizer/{lamb,lans,lars}.py."""
+    kw = mx.optimizer.create("lamb", learning_rate=0.01, lower_bound=0.1, skip_nonfinite=True).fused_kwargs()
+    assert kw["bias_correction"] is True and kw["lower_bound"] == 0.1 and "upper_bound" not in kw
+    assert kw["skip_nonfinite"] is True and kw["epsilon"] == 1e-6
+    lars = mx.optimizer.create("lars", momentum=0.9, param_idx2name={0: "fc_weight", 1: "fc_bias", 2: "bn_gamma"})
+    assert lars.fused_kwargs()["eta"] == 0.001 and sorted(lars.no_trust_ratio_indices()) == [1, 2]
+    kv = mx.kv.create("device")
+    kv.set_optimizer(lars)               # descriptors reach the engine without a GPU
+    kv.set_optimizer(mx.optimizer.create("lans"))
+    with pytest.raises(mx.MXNetError):   # skip_nonfinite is a layer-wise-optimizer feature
+        from mxnet_b200.base import _LIB, check_call, c_str, c_str_array
+        check_call(_LIB.MXKVB200SetOptimizer(kv.handle, c_str("sgd"), 1, c_str_array(["skip_nonfinite"]),
+                                             c_str_array(["True"])))
+    assert isinstance(mx.optimizer.get_updater(mx.optimizer.create("adam")), mx.optimizer.NativeUpdater)
+
+    class Custom(mx.optimizer.Optimizer):
+        pass
+    assert isinstance(mx.optimizer.get_updater(Custom()), mx.optimizer.Updater)

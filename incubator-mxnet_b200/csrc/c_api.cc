@@ -132,8 +132,9 @@ int MXNDArraySyncCopyFromNDArray(NDArrayHandle handle_dst, const NDArrayHandle h
   if (dst->stype() == kRowSparseStorage) {
     // filling a row_sparse destination: i < 0 data, i >= 0 indices; the row count follows the source
     const int64_t rows = s.shape().empty() ? 0 : s.shape()[0];
-    MXKV_CHECK(rows <= dst->cap_rows()) << "row_sparse destination holds " << dst->cap_rows() << " rows, source has "
-                                       << rows;
+    // row_sparse arrays are dynamically sized in the reference (CheckAndAlloc): grow on demand.  Growing
+    // discards the contents, so fill the data (i < 0) before the indices, as the front-end does.
+    if (rows > dst->cap_rows()) dst->ReserveRows(rows);
     dst->set_nnz(rows);
     d = (i < 0) ? dst->data_nd() : dst->aux_idx();
   }

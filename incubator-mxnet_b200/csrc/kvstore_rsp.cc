@@ -99,8 +99,19 @@ void KVStore::PushRowSparse(KeyState& ks, const std::vector<NDArray>& vals) {
   Runtime* rt = Runtime::Get();
   ProcessGroup* pg = PG();
   const bool mp_mode = pg != nullptr;
-  MXKV_CHECK(ks.stype == kRowSparseStorage)
-      << "key " << ks.key << " was initialised dense; row_sparse push needs a row_sparse key";
+  if (ks.stype != kRowSparseStorage) {
+    // Without an updater the stored value simply becomes the merged value, storage type included
+    // (`local = merged.Copy(...)` on a storage-type mismatch, kvstore_local.h:268-276; the reference's
+    // test_aggregator pushes row_sparse values to keys initialised dense).  The stored value is a
+    // dense-backed table either way, so the key only changes its label.
+    MXKV_CHECK(updater_ == nullptr && !opt_.enabled)
+        << "key " << ks.key << " was initialised dense; a row_sparse push with an updater / optimizer needs a "
+           "row_sparse key";
+    MXKV_CHECK(ks.dtype == kFloat32 && ks.shape.size() >= 2)
+        << "row_sparse values need a float32 key with at least 2 dimensions (key " << ks.key << ")";
+    if (ks.local_world > 0) GatherLocal(ks);
+    ks.stype = kRowSparseStorage;
+  }
   const int n_src = static_cast<int>(vals.size());
   MXKV_CHECK(n_src >= 1 && n_src <= kMaxSrc) << "push of " << n_src << " row_sparse values (max " << kMaxSrc << ")";
   const int64_t L = ks.size / ks.shape[0];
@@ -308,7 +319,17 @@ void KVStore::PullDenseFromRowSparse(KeyState& ks, const std::vector<NDArray*>& 
   Runtime* rt = Runtime::Get();
   std::set<int> touched;
   for (NDArray* o : outs) {
-    MXKV_CHECK(o->stype() == kDefaultStorage) << "pull of a row_sparse key into a sparse array: use row_sparse_pull";
+    if (o->stype() == kRowSparseStorage) {
+      // pull(..., ignore_sparse=False) into a row_sparse array: the whole stored value (CopyFromTo
+      // rsp -> rsp in CommDevice::Broadcast, comm.h:607-625).  The stored value is a dense-backed
+      // table, so every row is delivered (rows the reference would not list arrive as zero rows: the
+      // dense view is identical).
+      NDArray ids = NDArray::Empty({ks.shape[0]}, Context{kCPU, 0}, kInt64);
+      int64_t* p = static_cast<int64_t*>(ids.data());
+      for (int64_t i = 0; i < ks.shape[0]; ++i) p[i] = i;
+      PullRowSparseImpl({ks.key}, {{o, ids}}, 0);
+      continue;
+    }
     MXKV_CHECK(o->size() == ks.size && o->dtype() == ks.dtype) << "pull: output does not match key " << ks.key;
     const Context c = o->ctx();
     if (c.is_gpu() && touched.insert(c.dev_id).second) rt->AcquireUser(c.dev_id);
@@ -336,7 +357,8 @@ void KVStore::PullRowSparseImpl(const std::vector<int>& keys,
         << "Expected default storage type for row_sparse_pull rowids, but detected storage type " << row_id.stype();
     KeyState& ks = GetKey(keys[i]);
     MXKV_CHECK(ks.stype == kRowSparseStorage) << "PullRowSparse expects row_sparse src NDArray";
-    MXKV_CHECK(row_id.dtype() == kInt64) << "row_ids must be int64";
+    MXKV_CHECK(row_id.dtype() == kInt64 || row_id.dtype() == kInt32 || row_id.dtype() == kFloat32 ||
+               row_id.dtype() == kFloat64) << "row_ids must be int64, int32, float32 or float64";
     const int64_t n = row_id.size();
     const int64_t L = ks.size / ks.shape[0];
     const Context oc = out->ctx();
@@ -352,13 +374,19 @@ void KVStore::PullRowSparseImpl(const std::vector<int>& keys,
     Replica& r = EnsureReplica(ks, dev);
     DeviceGuard g(dev);
     cudaStream_t s = rt->Dev(dev).stream;
-    // ids on this GPU
+    // ids on this GPU, as int64
     const int64_t* ids = static_cast<const int64_t*>(row_id.data());
     void* tmp_ids = nullptr;
+    void* tmp_cast = nullptr;
     if (!(rc.is_gpu() && rc.dev_id == dev) && n > 0) {
-      CUDA_CALL(cudaMallocAsync(&tmp_ids, n * 8, s));
-      CopyBytes(row_id.data(), rc, tmp_ids, Context{kGPU, dev}, n * 8);
+      CUDA_CALL(cudaMallocAsync(&tmp_ids, row_id.nbytes(), s));
+      CopyBytes(row_id.data(), rc, tmp_ids, Context{kGPU, dev}, row_id.nbytes());
       ids = static_cast<const int64_t*>(tmp_ids);
+    }
+    if (row_id.dtype() != kInt64 && n > 0) {
+      CUDA_CALL(cudaMallocAsync(&tmp_cast, n * 8, s));
+      CheckLaunch(LaunchCastIdsToI64(ids, row_id.dtype(), static_cast<int64_t*>(tmp_cast), n, s), "rsp_cast_ids");
+      ids = static_cast<const int64_t*>(tmp_cast);
     }
     const bool direct = oc.is_gpu() && oc.dev_id == dev;
     if (direct && out->cap_rows() < n) out->ReserveRows(n);
@@ -374,6 +402,7 @@ void KVStore::PullRowSparseImpl(const std::vector<int>& keys,
                                 vec, s), "rsp_gather");
     target.set_nnz_device();
     if (tmp_ids) CUDA_CALL(cudaFreeAsync(tmp_ids, s));
+    if (tmp_cast) CUDA_CALL(cudaFreeAsync(tmp_cast, s));
     if (!direct) {
       const int64_t cnt = target.nnz();      // one sync: the destination lives elsewhere
       if (out->cap_rows() < cnt) out->ReserveRows(cnt);

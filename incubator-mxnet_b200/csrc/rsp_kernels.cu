@@ -435,6 +435,29 @@ int LaunchRspScatter(float* table, const int64_t* idx, const int64_t* d_nnz, int
   return static_cast<int>(cudaGetLastError());
 }
 
+// row ids of any real dtype -> int64 (KVStoreLocal::Unique copies them with ndarray::Copy, which casts:
+// src/kvstore/kvstore_local.h:507-512; the reference's tests pass float32 ids)
+template <typename T>
+__global__ void rsp_cast_ids_kernel(const T* src, int64_t* dst, int64_t n) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    dst[i] = static_cast<int64_t>(src[i]);
+}
+
+int LaunchCastIdsToI64(const void* src, int dtype, int64_t* dst, int64_t n, cudaStream_t stream) {
+  if (n <= 0) return 0;
+  const int threads = 256;
+  const int grid = static_cast<int>(std::min<int64_t>((n + threads - 1) / threads, 1184));
+  switch (dtype) {
+    case kFloat32: rsp_cast_ids_kernel<float><<<grid, threads, 0, stream>>>(static_cast<const float*>(src), dst, n); break;
+    case kFloat64: rsp_cast_ids_kernel<double><<<grid, threads, 0, stream>>>(static_cast<const double*>(src), dst, n); break;
+    case kInt32: rsp_cast_ids_kernel<int32_t><<<grid, threads, 0, stream>>>(static_cast<const int32_t*>(src), dst, n); break;
+    case kInt64: rsp_cast_ids_kernel<int64_t><<<grid, threads, 0, stream>>>(static_cast<const int64_t*>(src), dst, n); break;
+    default: return static_cast<int>(cudaErrorInvalidValue);
+  }
+  return static_cast<int>(cudaGetLastError());
+}
+
 int LaunchSetI64(int64_t* p, int64_t v, cudaStream_t stream) {
   rsp_set_i64_kernel<<<1, 1, 0, stream>>>(p, v);
   return static_cast<int>(cudaGetLastError());

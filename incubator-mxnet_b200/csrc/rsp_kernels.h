@@ -34,6 +34,8 @@ int LaunchRspGather(const float* table, const int64_t* ids, const int64_t* d_cou
 int LaunchRspScatter(float* table, const int64_t* idx, const int64_t* d_nnz, int64_t max_rows, int64_t L,
                      const float* val, cudaStream_t stream);
 int LaunchSetI64(int64_t* p, int64_t v, cudaStream_t stream);
+// dst[i] = (int64) src[i] for float32 / float64 / int32 / int64 row ids
+int LaunchCastIdsToI64(const void* src, int dtype, int64_t* dst, int64_t n, cudaStream_t stream);
 // cross-process rendezvous of block 0 (one-process-per-GPU mode, between non-collective kernels)
 int LaunchBarrier(const SyncArgs& sync, cudaStream_t stream);
 

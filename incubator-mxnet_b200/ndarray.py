@@ -140,7 +140,11 @@ class NDArray(object):
             self.copyto(out)
             return out
         if self.stype == "row_sparse":
-            other[:] = self.todense_numpy()
+            if other.stype == "row_sparse":       # values first, then indices (the row count follows the source)
+                check_call(_LIB.MXNDArraySyncCopyFromNDArray(other.handle, self.handle, ctypes.c_int(-1)))
+                check_call(_LIB.MXNDArraySyncCopyFromNDArray(other.handle, self.handle, ctypes.c_int(0)))
+            else:
+                other[:] = self.todense_numpy()
             return other
         check_call(_LIB.MXNDArraySyncCopyFromNDArray(other.handle, self.handle, ctypes.c_int(-1)))
         return other

@@ -194,3 +194,98 @@ def test_nightly_random_accuracy():
             kv.pull(ks[j], out=out)
             err = np.sum(np.abs(out.asnumpy() - res[j])) / np.sum(np.abs(res[j]))
             assert err < 1e-6, (err, s)
+
+
+@pytest.mark.parametrize("stype", ["default", "row_sparse"])
+def test_aggregator(stype):
+    # tests/python/unittest/test_kvstore.py:139-172: values on four cpu contexts, single key then a key
+    # list, int and str keys; row_sparse values are pushed to keys that were initialised dense
+    def check_aggregator(kv, key, key_list):
+        num_devs = 4
+        devs = [mx.Context("cpu", i) for i in range(num_devs)]
+        vals = [mx.nd.ones(shape, d).tostype(stype) for d in devs]
+        outs = [mx.nd.empty(shape, d) for d in devs]
+        kv.push(key, vals)
+        kv.pull(key, out=outs)
+        for out in outs:
+            check_diff_to_scalar(out, num_devs)
+        vals = [[(mx.nd.ones(shape, d) * 2.0).tostype(stype) for d in devs]] * len(key_list)
+        outs = [[mx.nd.empty(shape, d) for d in devs]] * len(key_list)
+        kv.push(key_list, vals)
+        kv.pull(key_list, out=outs)
+        for out in outs:
+            for o in out:
+                check_diff_to_scalar(o, num_devs * 2.0)
+
+    check_aggregator(init_kv("cpu"), 3, keys)
+    check_aggregator(init_kv_with_str("cpu"), "a", str_keys)
+
+
+@pytest.mark.parametrize("kv_type", ["local", "device"])
+@pytest.mark.parametrize("push_on_gpu", [False, True])
+def test_rsp_push_pull(kv_type, push_on_gpu):
+    # tests/python/gpu/test_kvstore_gpu.py:48-110 on one GPU: row_sparse key of ones, two row_sparse
+    # pushes of ones (stored value becomes 2), then row_sparse_pull with random -- repeated, unsorted,
+    # FLOAT32 -- row ids into outputs on the GPU and on cpu contexts, one id array per output or a
+    # shared one, and the dense pull of the whole value
+    rshape = (20, 6)
+    num_rows = rshape[0]
+    kv = mx.kv.create(kv_type)
+    kv.init("a", mx.nd.zeros(rshape, stype="row_sparse"))
+    kv.init("e", mx.nd.ones(rshape).tostype("row_sparse"))
+    push_ctxs = [mx.gpu(0) if push_on_gpu else mx.Context("cpu", i) for i in range(2)]
+    kv.push("e", [mx.nd.ones(rshape, c).tostype("row_sparse") for c in push_ctxs])
+    rng = np.random.default_rng(3)
+
+    def check_rsp_pull(ctxs, is_same_rowid=False):
+        count = len(ctxs)
+        all_row_ids = np.arange(num_rows)
+        vals = [mx.nd.zeros(rshape, c, stype="row_sparse") for c in ctxs]
+        if is_same_rowid:
+            row_id = rng.integers(0, num_rows, num_rows)
+            row_ids = [mx.nd.array(row_id.astype(np.float32), dtype=np.float32)] * count
+        else:
+            row_ids = [mx.nd.array(rng.integers(0, num_rows, num_rows).astype(np.float32), dtype=np.float32)
+                       for _ in range(count)]
+        row_ids_to_pull = row_ids[0] if (len(row_ids) == 1 or is_same_rowid) else row_ids
+        vals_to_pull = vals[0] if len(vals) == 1 else vals
+        kv.row_sparse_pull("e", out=vals_to_pull, row_ids=row_ids_to_pull)
+        for val, row_id in zip(vals, row_ids):
+            retained = val.todense_numpy()
+            excluded = np.setdiff1d(all_row_ids, row_id.asnumpy())
+            for row in range(num_rows):
+                want = 0.0 if row in excluded else 2.0
+                assert np.all(retained[row] == want), (row, retained[row], want)
+        kv.pull("e", out=vals_to_pull, ignore_sparse=False)
+        for val in vals:
+            assert np.all(val.todense_numpy() == 2.0)
+
+    check_rsp_pull([mx.gpu(0)])
+    check_rsp_pull([mx.cpu(0)])
+    check_rsp_pull([mx.gpu(0) for _ in range(4)])
+    check_rsp_pull([mx.gpu(0) for _ in range(4)], is_same_rowid=True)
+    check_rsp_pull([mx.Context("cpu", i) for i in range(4)])
+    check_rsp_pull([mx.Context("cpu", i) for i in range(4)], is_same_rowid=True)
+
+
+def test_row_sparse_pull_single_device_and_large_rowid():
+    # tests/python/gpu/test_kvstore_gpu.py:112-125
+    rng = np.random.default_rng(4)
+    dense = rng.normal(size=(4, 4)).astype(np.float32)
+    grad = mx.nd.array(dense, mx.gpu(0)).tostype("row_sparse")
+    kv = mx.kv.create("device")
+    kv.init(0, grad)
+    idx = grad.indices
+    kv.push(0, grad)
+    kv.row_sparse_pull(0, out=grad, row_ids=idx)
+    assert np.array_equal(grad.todense_numpy(), dense)
+    # :127-136: 793470 rows of one element, every row id requested
+    num_rows = 793470
+    val = mx.nd.row_sparse_array(np.ones((num_rows, 1), np.float32), ctx=mx.gpu(0))
+    kv = mx.kv.create("device")
+    kv.init("a", val)
+    out = mx.nd.zeros((num_rows, 1), mx.gpu(0), stype="row_sparse")
+    kv.push("a", val)
+    kv.row_sparse_pull("a", out=out, row_ids=mx.nd.array(np.arange(num_rows, dtype=np.int64), mx.gpu(0), dtype=np.int64))
+    assert out.indices.shape[0] == num_rows
+    assert np.all(out.data.asnumpy() == 1.0)

@@ -174,6 +174,22 @@ def cpu_kvstore_step_factory(shapes, n_values, threads, optimizer):
     return step
 
 
+def ncu_dram_bytes(path):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the first kernel in an `ncu --page raw` text dump."""
+    units = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    got = {}
+    try:
+        with open(path) as f:
+            for line in f:
+                parts = line.split()
+                if len(parts) >= 3 and parts[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum") \
+                        and parts[0] not in got and parts[-1] in units:
+                    got[parts[0]] = float(parts[-2].replace(",", "")) * units[parts[-1]]
+    except OSError:
+        return None
+    return sum(got.values()) if len(got) == 2 else None
+
+
 def host_cpus():
     """CPUs this process may actually use: affinity mask, capped by the cgroup CPU quota."""
     try:
@@ -566,6 +582,11 @@ def main():
                 "note": "bytes that must cross this GPU's NVLink per direction; busbw_gbs_per_gpu is the "
                         "NCCL-comparable 2S(n-1)/n / t"}
     roof["frac"] = roof["achieved"] / roof["peak"]
+    if world == 1 and args.workload == "sweep" and args.optimizer == "sgd":
+        # DRAM bytes of the same kernel on the same workload from this round's `ncu --set full` capture
+        # (bench.py cannot run under ncu itself: a number printed under a profiler is never a bench value)
+        src = os.path.join(ROOT, "profiles", "r01_final_n1_kv_dense_bulk_kernel_ncu_full.txt")
+        roof["traffic"], roof["traffic_source"] = ncu_dram_bytes(src), os.path.relpath(src, ROOT)
 
     # ---- e2e: host gradients in, host weights out, through the same public API ---------------------
     e2e = None

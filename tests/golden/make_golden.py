@@ -7,6 +7,12 @@
                       `compute_2bit` (tests/nightly/test_kvstore.py:35-98), executed from the
                       reference file itself (nothing is copied into this repository).
 
+* layerwise.npz    -- weights produced by the reference's own non-fused ``step`` methods of LAMB / LANS /
+                      LARS (python/mxnet/optimizer/{lamb,lans,lars}.py), executed from the reference files
+                      on a float32 numpy stand-in for NDArray (nothing is copied into this repository).
+
+* optimizer_steps.npz -- the same for SGD / SGD-momentum / Adam / Test (sgd.py, adam.py, optimizer.py).
+
 The GPU box has no /root/reference; tests read the committed fixtures instead.
 """
 import ast
@@ -78,7 +84,166 @@ def compression():
     np.savez_compressed(os.path.join(HERE, "compression.npz"), **out)
 
 
+# ---------------------------------------------------------------------------------------------
+# LAMB / LANS / LARS: run the reference's Python `step` (the "use_fused_step=False" implementation the
+# reference's own tests compare its fused kernels against, tests/python/unittest/test_optimizer.py:232-312)
+# ---------------------------------------------------------------------------------------------
+class _F32(np.ndarray):
+    """float32 ndarray that answers the few NDArray methods `step` calls."""
+
+    def norm(self):
+        return np.sqrt(np.sum(np.square(np.asarray(self, np.float32)), dtype=np.float32, keepdims=False)
+                       ).astype(np.float32).reshape(1).view(_F32)
+
+    def asscalar(self):
+        return np.asarray(self).reshape(-1)[0]
+
+    def astype(self, dtype, copy=True):       # noqa: D401 -- NDArray.astype always copies
+        return np.array(np.asarray(self), dtype=dtype).view(_F32)
+
+
+def _nd(a):
+    return np.array(a, dtype=np.float32).view(_F32)
+
+
+def _step_functions(fname, cls, names):
+    """The named methods of class `cls` in the reference file, compiled from the reference source."""
+    src = open(os.path.join(REF, "python/mxnet/optimizer", fname)).read()
+    tree = ast.parse(src)
+    import math
+    shim = {
+        "math": math,
+        "clip": lambda x, lo, hi: np.clip(x, np.float32(lo), np.float32(hi)).view(_F32),
+        "sqrt": lambda x, out=None: np.sqrt(x, out=out),
+        "square": lambda x: np.square(x),
+        "maximum": lambda a, b: np.maximum(a, np.float32(b)).view(_F32),
+        "minimum": lambda a, b: np.minimum(a, np.float32(b)).view(_F32),
+        "where": lambda c, x, y: np.where(np.asarray(c) != 0, x, y).view(_F32),   # NaN counts as true
+        "ones_like": lambda x: np.ones_like(x),
+        "NDnorm": lambda v: v.norm(),
+    }
+    fns = {}
+    for node in tree.body:
+        if isinstance(node, ast.ClassDef) and node.name == cls:
+            for item in node.body:
+                if isinstance(item, ast.FunctionDef) and item.name in names:
+                    ns = dict(shim)
+                    exec(compile(ast.Module([item], []), "reference:python/mxnet/optimizer/" + fname, "exec"), ns)
+                    fns[item.name] = ns[item.name]
+    assert set(fns) == set(names), (fname, sorted(fns))
+    return fns
+
+
+class _FakeOptimizer(object):
+    """The attributes `step` reads from `self` (python/mxnet/optimizer/optimizer.py)."""
+
+    def __init__(self, fns, lr, wd, **attrs):
+        self.lr, self.wd = lr, wd
+        self.rescale_grad, self.clip_gradient = 1.0, None
+        self._index_update_count = {}
+        self.idx2name = {}
+        self.__dict__.update(attrs)
+        for name, fn in fns.items():
+            setattr(self, name, fn.__get__(self))
+
+    def _update_count(self, index):
+        self._index_update_count[index] = self._index_update_count.get(index, 0) + 1
+
+    def _get_lr(self, index):
+        return self.lr
+
+    def _get_wd(self, index):
+        return self.wd
+
+
+def layerwise():
+    out = {}
+    shapes = [(3, 4, 5), (10, 4), (7,)]                       # test_optimizer.py:235,261,291
+    lamb = _step_functions("lamb.py", "LAMB", ["step"])
+    lans = _step_functions("lans.py", "LANS", ["step"])
+    lars = _step_functions("lars.py", "LARS", ["step", "_get_lars", "_l2norm"])
+    cases = []
+    for bc in (True, False):
+        for extra in (dict(), dict(beta1=0.5, beta2=0.8, clip_gradient=0.4, rescale_grad=0.14, wd=0.03,
+                                   lower_bound=1e-3, upper_bound=10.0)):
+            cases.append(("lamb", lamb, dict(bias_correction=bc, **extra)))
+    for extra in (dict(), dict(beta1=0.5, beta2=0.8, clip_gradient=0.4, rescale_grad=0.14, wd=0.03,
+                               lower_bound=1e-3, upper_bound=10.0)):
+        cases.append(("lans", lans, dict(extra)))
+    for mom in (0.0, 0.9):
+        for extra in (dict(), dict(eta=0.01, clip_gradient=0.4, rescale_grad=0.14, wd=0.05)):
+            cases.append(("lars", lars, dict(momentum=mom, **extra)))
+    rng = np.random.default_rng(20260922)
+    meta = []
+    for ci, (name, fns, kw) in enumerate(cases):
+        kw = dict(kw)
+        wd = kw.pop("wd", 0.0)
+        lr = 0.1 if name == "lars" else 0.01
+        attrs = dict(beta1=0.9, beta2=0.999, epsilon=1e-8 if name == "lars" else 1e-6, lower_bound=None,
+                     upper_bound=None, bias_correction=True, momentum=0.0, eta=0.001)
+        attrs.update(kw)
+        for si, shape in enumerate(shapes):
+            opt = _FakeOptimizer(fns, lr, wd, **attrs)
+            w = _nd(rng.uniform(-1, 1, shape))
+            if name == "lars":
+                state = _nd(np.zeros(shape)) if attrs["momentum"] != 0.0 else None
+            else:
+                state = (_nd(np.zeros(shape)), _nd(np.zeros(shape)))
+            tag = "c%d_s%d" % (ci, si)
+            out["w0_" + tag] = np.asarray(w).copy()
+            for t in range(4):
+                g = rng.uniform(-1, 1, shape).astype(np.float32)
+                out["g%d_%s" % (t, tag)] = g
+                opt.step([0], [w], [_nd(g)], [state])
+                out["w%d_%s" % (t + 1, tag)] = np.asarray(w).copy()
+        meta.append(repr((name, lr, wd, {k: v for k, v in attrs.items()})))
+    out["cases"] = np.array(meta)
+    np.savez_compressed(os.path.join(HERE, "layerwise.npz"), **out)
+
+
+def plain_steps():
+    """SGD / SGD-momentum / Adam / Test: the reference's `step` methods (sgd.py:118-154, adam.py:107-147,
+    optimizer.py:570-577) executed the same way -> optimizer_steps.npz."""
+    out = {}
+    sgd = _step_functions("sgd.py", "SGD", ["step"])
+    adam = _step_functions("adam.py", "Adam", ["step"])
+    test = _step_functions("optimizer.py", "Test", ["step"])
+    cases = [("sgd", sgd, 0.1, dict(momentum=0.0, wd=1e-3, rescale_grad=0.5)),
+             ("sgd", sgd, 0.1, dict(momentum=0.9, wd=1e-3, rescale_grad=0.5)),
+             ("sgd", sgd, 0.05, dict(momentum=0.9, wd=1e-4, rescale_grad=0.25, clip_gradient=0.4)),
+             ("adam", adam, 0.01, dict(beta1=0.9, beta2=0.999, epsilon=1e-8, wd=1e-3, rescale_grad=0.5,
+                                       clip_gradient=0.8)),
+             ("adam", adam, 0.001, dict(beta1=0.5, beta2=0.8, epsilon=1e-8, wd=0.0)),
+             ("test", test, 0.01, dict(wd=0.01, rescale_grad=0.5))]
+    rng = np.random.default_rng(20260923)
+    meta = []
+    for ci, (name, fns, lr, kw) in enumerate(cases):
+        kw = dict(kw)
+        wd = kw.pop("wd", 0.0)
+        for si, shape in enumerate([(3, 4, 5), (10, 4), (1001,)]):
+            opt = _FakeOptimizer(fns, lr, wd, **kw)
+            w = _nd(rng.uniform(0, 1, shape))
+            if name == "sgd":
+                state = _nd(np.zeros(shape)) if kw["momentum"] != 0.0 else None
+            elif name == "adam":
+                state = (_nd(np.zeros(shape)), _nd(np.zeros(shape)))
+            else:
+                state = None
+            tag = "c%d_s%d" % (ci, si)
+            out["w0_" + tag] = np.asarray(w).copy()
+            for t in range(5):
+                g = rng.uniform(-1, 1, shape).astype(np.float32)
+                out["g%d_%s" % (t, tag)] = g
+                opt.step([0], [w], [_nd(g)], [state])
+                out["w%d_%s" % (t + 1, tag)] = np.asarray(w).copy()
+        meta.append(repr((name, lr, wd, kw)))
+    out["cases"] = np.array(meta)
+    np.savez_compressed(os.path.join(HERE, "optimizer_steps.npz"), **out)
+
+
 if __name__ == "__main__":
     dense_sums()
     compression()
+    layerwise()
+    plain_steps()
     print("wrote", sorted(f for f in os.listdir(HERE) if f.endswith(".npz")))

@@ -423,6 +423,61 @@ def test_sum_sq_and_trust_ratio_edge_cases():
     assert np.all(w == 1)
 
 
+def test_plain_optimizers_vs_reference_step_golden():
+    """tests/golden/optimizer_steps.npz: weights produced by the reference's own `step` of SGD / Adam / Test
+    (sgd.py:118-154, adam.py:107-147, optimizer.py:570-577; make_golden.py::plain_steps).  Tolerances of
+    tests/python/unittest/test_optimizer.py (:75-84 SGD rtol 1e-3 / atol 1e-4, :461-463 Adam rtol 1e-4 /
+    atol 2e-5); the kernel restatement in fact agrees to a few ulp."""
+    gold = np.load(os.path.join(GOLD, "optimizer_steps.npz"))
+    cases = [eval(c) for c in gold["cases"]]
+    for ci, (name, lr, wd, kw) in enumerate(cases):
+        for si in range(3):
+            tag = "c%d_s%d" % (ci, si)
+            w = gold["w0_" + tag].copy()
+            opt = O.OracleOptimizer(name, learning_rate=lr, wd=wd, **kw)
+            for t in range(5):
+                opt.update(0, w, gold["g%d_%s" % (t, tag)].copy())
+                want = gold["w%d_%s" % (t + 1, tag)]
+                if name == "adam":
+                    np.testing.assert_allclose(w, want, rtol=1e-4, atol=2e-5, err_msg=str((name, ci, si, t)))
+                else:
+                    np.testing.assert_allclose(w, want, rtol=1e-3, atol=1e-4, err_msg=str((name, ci, si, t)))
+                assert np.max(np.abs(w - want)) < 2e-6, (name, ci, si, t, np.max(np.abs(w - want)))
+
+
+def test_layerwise_oracle_vs_reference_step_golden():
+    """tests/golden/layerwise.npz holds weights produced by the reference's OWN `step` methods of LAMB /
+    LANS / LARS, executed from python/mxnet/optimizer/{lamb,lans,lars}.py (make_golden.py::layerwise).
+    The fused-kernel restatement in oracle/ must agree with them within the tolerance the reference's
+    tests grant its fused kernels against that same `step` (rtol = atol = 1e-3, test_optimizer.py:251-312);
+    LAMB and LARS perform the same operations in both forms and agree to ~1e-7."""
+    gold = np.load(os.path.join(GOLD, "layerwise.npz"))
+    cases = [eval(c) for c in gold["cases"]]        # (name, lr, wd, attrs) literals written by make_golden.py
+    shapes = 3
+    worst = {"lamb": 0.0, "lans": 0.0, "lars": 0.0}
+    for ci, (name, lr, wd, attrs) in enumerate(cases):
+        for si in range(shapes):
+            tag = "c%d_s%d" % (ci, si)
+            w = gold["w0_" + tag].copy()
+            kw = dict(learning_rate=lr, wd=wd, rescale_grad=attrs.get("rescale_grad", 1.0),
+                      clip_gradient=attrs.get("clip_gradient"), epsilon=attrs["epsilon"])
+            if name == "lars":
+                kw.update(momentum=attrs["momentum"], eta=attrs["eta"])
+            else:
+                kw.update(beta1=attrs["beta1"], beta2=attrs["beta2"], lower_bound=attrs["lower_bound"],
+                          upper_bound=attrs["upper_bound"])
+                if name == "lamb":
+                    kw.update(bias_correction=attrs["bias_correction"])
+            opt = O.OracleOptimizer(name, **kw)
+            for t in range(4):
+                opt.update(0, w, gold["g%d_%s" % (t, tag)].copy())
+                want = gold["w%d_%s" % (t + 1, tag)]
+                np.testing.assert_allclose(w, want, rtol=1e-3, atol=1e-3, err_msg=str((name, ci, si, t)))
+                worst[name] = max(worst[name], float(np.max(np.abs(w - want))))
+    assert worst["lamb"] < 1e-5 and worst["lars"] < 1e-5, worst
+    assert worst["lans"] < 1e-3, worst
+
+
 def test_rsp_sum_and_retain_oracle_properties():
     rng = np.random.default_rng(2)
     rows, L = 50, 8

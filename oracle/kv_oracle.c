@@ -19,11 +19,14 @@
  * reference's own mshadow expression templates compiled from
  * /root/reference/3rdparty/mshadow (oracle/ref_harness.cc -> oracle/_ref/), and
  * against the known-answer tests of the reference test-suite re-expressed in
- * tests/ (see tests/golden/README.md).  The optimizer kernels have no runnable
- * reference in this container (libmxnet cannot be built here);
- * they are pinned by an independent numpy restatement of the reference's
- * non-fused Python `step()` (the reference's own oracle for its fused kernels,
- * tests/python/unittest/test_optimizer.py) within that test's tolerances.
+ * tests/ (see tests/golden/README.md).  The C++ optimizer operators cannot be built in
+ * this container (libmxnet needs a BLAS and ~1.5k translation units), but the
+ * reference's non-fused Python `step()` methods -- its own oracle for its fused kernels,
+ * tests/python/unittest/test_optimizer.py -- can be executed: tests/golden/make_golden.py runs
+ * SGD / Adam / Test / LAMB / LANS / LARS `step` out of the reference tree and the optimizer
+ * routines below are checked against those outputs (tests/golden/optimizer_steps.npz,
+ * layerwise.npz) within that test's tolerances.  AdamW and the sparse update kernels are pinned
+ * by a hand-written restatement only.
  */
 #include <stdint.h>
 #include <stdlib.h>

@@ -201,7 +201,10 @@ void KVStore::SetOptimizer(const std::string& name, const std::vector<std::pair<
     else if (k == "beta1") c.beta1 = std::stod(v);
     else if (k == "beta2") c.beta2 = std::stod(v);
     else if (k == "epsilon") { if (c.kind == OPT_LARS) c.lars_eps = std::stof(v); else c.eps = std::stof(v); }
-    else if (k == "eta") { if (c.kind == OPT_LARS) c.lars_eta = std::stof(v); else c.eta = std::stof(v); }
+    else if (k == "eta") {
+      if (c.kind == OPT_LARS) c.lars_eta = std::stof(v);
+      else { c.eta = std::stof(v); c.eta_d = std::stod(v); }
+    }
     else if (k == "lower_bound") c.lower_bound = (v == "None" || v.empty()) ? -1.f : std::stof(v);
     else if (k == "upper_bound") c.upper_bound = (v == "None" || v.empty()) ? -1.f : std::stof(v);
     else if (k == "bias_correction") c.bias_correction = (v == "True" || v == "true" || v == "1");
@@ -238,7 +241,28 @@ void KVStore::SetOptimizerMult(bool str_key, int ikey, const std::string& skey, 
   opt_.wd_mult[key] = wd_mult;
 }
 
-float KVStore::KeyLR(const KeyState& ks) const { return static_cast<float>(KeyLRd(ks)); }
+// AdamW: the reference's optimizer class hands the operator lr = 1 and eta = the (bias-corrected)
+// learning rate (`lrs=np.ones(...)`, `etas=lrs`, python/mxnet/optimizer/adamW.py:176-200), which is
+// how `w -= eta * (lr * m / (sqrt(v) + eps) + wd * w)` (contrib/adamw-inl.h:101-124) becomes the
+// documented `w -= lr * (m / (sqrt(v) + eps) + wd * w)`.  opt_.eta is an additional schedule multiplier
+// of this engine's own (1 by default; the reference class has none).
+float KVStore::KeyLR(const KeyState& ks) const {
+  if (opt_.kind == OPT_ADAMW) return 1.0f;
+  return static_cast<float>(KeyLRd(ks));
+}
+
+// `_adamw_update` and its multi / mp forms leave everything untouched when the rescale_grad scalar is
+// 0, inf or nan (contrib/adamw-inl.h:455: the AMP loss-scale path); Optimizer._update_count has already
+// run by then (adamW.py:158).
+bool KVStore::AdamWSkips() const {
+  return opt_.enabled && updater_ == nullptr && opt_.kind == OPT_ADAMW &&
+         (!std::isfinite(opt_.rescale) || opt_.rescale == 0.f);
+}
+
+float KVStore::KeyEta(const KeyState& ks) const {
+  if (opt_.kind == OPT_ADAMW) return static_cast<float>(KeyLRd(ks) * opt_.eta_d);
+  return opt_.eta;
+}
 
 double KVStore::KeyLRd(const KeyState& ks) const {
   // Optimizer._get_lr (optimizer.py) then, for Adam, the host-side bias correction of
@@ -473,6 +497,7 @@ void KVStore::PushImpl(const std::vector<int>& keys, const std::vector<NDArray>&
       PushRowSparse(ks, grouped[i]);
       continue;
     }
+    if (AdamWSkips()) { ks.count += 1; continue; }
     Group g;
     g.key = uniq[i];
     g.vals = grouped[i];
@@ -552,6 +577,11 @@ void KVStore::PushPullImpl(const std::vector<int>& vkeys, const std::vector<int>
   }
   if (!fusable) {
     PushImpl(vkeys, vals, priority);
+    PullImpl(okeys, outs, priority, true);
+    return;
+  }
+  if (AdamWSkips()) {
+    for (int key : vu) GetKey(key).count += 1;
     PullImpl(okeys, outs, priority, true);
     return;
   }
@@ -749,7 +779,7 @@ bool KVStore::HostPipelined(std::vector<Group>& groups, bool write_outs) {
       tw.s0 = r->s0.is_none() ? nullptr : static_cast<float*>(r->s0.data());
       tw.s1 = r->s1.is_none() ? nullptr : static_cast<float*>(r->s1.data());
       tw.begin = b; tw.end = e;
-      tw.lr = lr; tw.wd = wd; tw.eta = opt_.eta; tw.reserved_ = ks.key;
+      tw.lr = lr; tw.wd = wd; tw.eta = KeyEta(ks); tw.reserved_ = ks.key;
       tw.pad_ = 1 | ((esize == 4 && ks.size % 4 == 0) ? 2 : 0);
       std::vector<std::vector<TensorWork>> per_part(1);
       per_part[0].push_back(tw);
@@ -911,7 +941,7 @@ void KVStore::ReduceUpdateCompressed(std::vector<Group>& groups, bool write_outs
       tw.s0 = r.s0.is_none() ? nullptr : static_cast<float*>(r.s0.data());
       tw.s1 = r.s1.is_none() ? nullptr : static_cast<float*>(r.s1.data());
       tw.begin = 0; tw.end = ks.size;
-      tw.lr = lr; tw.wd = wd; tw.eta = opt_.eta; tw.reserved_ = ks.key;
+      tw.lr = lr; tw.wd = wd; tw.eta = KeyEta(ks); tw.reserved_ = ks.key;
       tw.pad_ = vec_ok ? 3 : 0;
       LaunchLocal(LaunchClassKey{SYNC_NONE, ks.dtype, mp ? 1 : 0}, tw, opt_kind, dev);
       r.fresh = true;
@@ -1307,7 +1337,7 @@ void KVStore::ReduceUpdate(std::vector<Group>& groups, bool write_outs) {
       } else {
         tw.begin = 0; tw.end = ks.size;
       }
-      tw.lr = lr; tw.wd = wd; tw.eta = opt_.eta; tw.reserved_ = ks.key;
+      tw.lr = lr; tw.wd = wd; tw.eta = KeyEta(ks); tw.reserved_ = ks.key;
       tw.pad_ = (vec_ok ? 1 : 0) | ((vec_ok && esize == 4 && ks.size % 4 == 0) ? 2 : 0);
       cls[p].push_back(tw);
     }
@@ -1634,6 +1664,7 @@ void KVStore::UpdaterStep(bool str_keys, const std::vector<int>& ikeys, const st
     r->fresh = true;
     ks.local_world = 0;
     if (bind_only) continue;
+    if (AdamWSkips()) { ks.count += 1; continue; }
     Group grp;
     grp.key = key;
     grp.vals = {grads[i]};

@@ -34,6 +34,7 @@ struct OptimizerConfig {
   // Python doubles and rounds to float once, when the value becomes an op attribute
   double lr = 0.01, wd = 0.0, beta1 = 0.9, beta2 = 0.999;
   float momentum = 0.f, eps = 1e-8f, eta = 1.f;
+  double eta_d = 1.0;          // eta as given (AdamW multiplies it with the learning rate in double)
   float rescale = 1.f, clip = -1.f;
   bool multi_precision = false;
   bool lazy_update = false;   // row_sparse gradients: touch only the rows present (sgd.py:78, adam.py:77 default False)
@@ -196,6 +197,8 @@ class KVStore {
   int DefaultDevice();
   double KeyLRd(const KeyState& ks) const;
   float KeyLR(const KeyState& ks) const;
+  float KeyEta(const KeyState& ks) const;
+  bool AdamWSkips() const;
   float KeyWD(const KeyState& ks) const;
 
   ProcessGroup* PG() const;     // the process group this store exchanges over (none for 'updater' stores)

@@ -278,7 +278,7 @@ void KVStore::PushRowSparse(KeyState& ks, const std::vector<NDArray>& vals) {
       tw.w = r.local.data();
       tw.s0 = A.s0; tw.s1 = A.s1;
       tw.begin = 0; tw.end = ks.size;
-      tw.lr = lr; tw.wd = wd; tw.eta = opt_.eta; tw.reserved_ = ks.key;
+      tw.lr = lr; tw.wd = wd; tw.eta = KeyEta(ks); tw.reserved_ = ks.key;
       tw.pad_ = (ks.size % 4 == 0 && Aligned16(r.local.data())) ? 1 : 0;
       const int kind = opt_.kind == OPT_SGD ? OPT_SGD_STD : (opt_.kind == OPT_ADAM ? OPT_ADAM_STD : opt_.kind);
       LaunchLocal(LaunchClassKey{SYNC_NONE, kFloat32, 0}, tw, kind, dev);

@@ -177,8 +177,12 @@ class Adam(Optimizer):
 
 @register
 class AdamW(Optimizer):
-    """python/mxnet/optimizer/adamW.py; fused kernel _adamw_update / _mp_adamw_update
-    (decoupled weight decay, src/operator/contrib/adamw-inl.h:101-124)."""
+    """python/mxnet/optimizer/adamW.py: ``w -= lr_t * (m / (sqrt(v) + eps) + wd * w)`` with
+    ``lr_t = lr * sqrt(1 - beta2^t) / (1 - beta1^t)`` (``correct_bias``).  The fused kernel is
+    _adamw_update / _mp_adamw_update (src/operator/contrib/adamw-inl.h:101-124), driven the way the
+    reference class drives it: operator ``lr = 1``, operator ``eta = lr_t`` (adamW.py:176-200).  ``eta`` here
+    is an extra schedule multiplier of this engine (default 1); a ``rescale_grad`` of 0 / inf / nan skips the
+    update like the operator does (adamw-inl.h:455)."""
     fused_name = "adamw"
 
     def __init__(self, learning_rate=0.001, beta1=0.9, beta2=0.999, epsilon=1e-6, correct_bias=True,

@@ -409,10 +409,11 @@ class OracleOptimizer(object):
     def __init__(self, name, learning_rate=None, wd=0.0, rescale_grad=1.0, clip_gradient=None,
                  momentum=0.0, beta1=0.9, beta2=0.999, epsilon=None, eta=None, multi_precision=False,
                  lr_mult=None, wd_mult=None, lazy_update=True, lower_bound=None, upper_bound=None,
-                 bias_correction=True, norm_mode="seq", no_trust=()):
+                 bias_correction=True, norm_mode="seq", no_trust=(), correct_bias=True):
         self.name = name.lower()
         self.lower_bound, self.upper_bound, self.bias_correction = lower_bound, upper_bound, bias_correction
         self.norm_mode = norm_mode
+        self.correct_bias = correct_bias    # AdamW (adamW.py:80-88)
         self.no_trust = set(no_trust)       # LARS: indices named *gamma / *beta / *bias
         if learning_rate is None:
             learning_rate = {"adam": 0.001, "adamw": 0.001, "lamb": 0.001, "lans": 0.001, "lars": 0.1}.get(
@@ -486,8 +487,14 @@ class OracleOptimizer(object):
             if index not in self.states:
                 self.states[index] = (np.zeros_like(weight), np.zeros_like(weight))
             mean, var = self.states[index]
-            mp_adamw_update(None, 0, weight, mean, var, grad, lr, self.eta, wd, self.beta1, self.beta2,
-                            self.epsilon, self.rescale_grad, self.clip_gradient)
+            # AdamW.fused_step hands the operator lr = 1 and eta = the (bias-corrected) learning rate
+            # (`lrs=np.ones(...)`, `etas=lrs`, adamW.py:176-200); self.eta is the engine's extra multiplier
+            lr_c = adam_lr(lr, self.beta1, self.beta2, t) if self.correct_bias else lr
+            rg = self.rescale_grad
+            if not np.isfinite(rg) or rg == 0:      # the operator skips the update (adamw-inl.h:455)
+                return
+            mp_adamw_update(None, 0, weight, mean, var, grad, 1.0, float(np.float32(lr_c * self.eta)), wd,
+                            self.beta1, self.beta2, self.epsilon, rg, self.clip_gradient)
         elif n in ("lamb", "lans"):
             assert not sparse
             if index not in self.states:

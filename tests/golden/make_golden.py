@@ -202,19 +202,24 @@ def layerwise():
 
 
 def plain_steps():
-    """SGD / SGD-momentum / Adam / Test: the reference's `step` methods (sgd.py:118-154, adam.py:107-147,
-    optimizer.py:570-577) executed the same way -> optimizer_steps.npz."""
+    """SGD / SGD-momentum / Adam / AdamW / Test: the reference's `step` methods (sgd.py:118-154,
+    adam.py:107-147, adamW.py:98-140, optimizer.py:570-577) executed the same way -> optimizer_steps.npz."""
     out = {}
     sgd = _step_functions("sgd.py", "SGD", ["step"])
     adam = _step_functions("adam.py", "Adam", ["step"])
     test = _step_functions("optimizer.py", "Test", ["step"])
-    cases = [("sgd", sgd, 0.1, dict(momentum=0.0, wd=1e-3, rescale_grad=0.5)),
+    adamw = _step_functions("adamW.py", "AdamW", ["step"])
+    cases = [("adamw", adamw, 0.01, dict(beta1=0.9, beta2=0.999, epsilon=1e-6, wd=0.03, correct_bias=True)),
+             ("adamw", adamw, 0.01, dict(beta1=0.7, beta2=0.9, epsilon=1e-6, wd=0.05, correct_bias=False,
+                                         rescale_grad=0.8, clip_gradient=0.5)),
+             ("sgd", sgd, 0.1, dict(momentum=0.0, wd=1e-3, rescale_grad=0.5)),
              ("sgd", sgd, 0.1, dict(momentum=0.9, wd=1e-3, rescale_grad=0.5)),
              ("sgd", sgd, 0.05, dict(momentum=0.9, wd=1e-4, rescale_grad=0.25, clip_gradient=0.4)),
              ("adam", adam, 0.01, dict(beta1=0.9, beta2=0.999, epsilon=1e-8, wd=1e-3, rescale_grad=0.5,
                                        clip_gradient=0.8)),
              ("adam", adam, 0.001, dict(beta1=0.5, beta2=0.8, epsilon=1e-8, wd=0.0)),
              ("test", test, 0.01, dict(wd=0.01, rescale_grad=0.5))]
+    cases = cases[2:] + cases[:2]      # keep the indices of the earlier cases stable
     rng = np.random.default_rng(20260923)
     meta = []
     for ci, (name, fns, lr, kw) in enumerate(cases):
@@ -225,7 +230,7 @@ def plain_steps():
             w = _nd(rng.uniform(0, 1, shape))
             if name == "sgd":
                 state = _nd(np.zeros(shape)) if kw["momentum"] != 0.0 else None
-            elif name == "adam":
+            elif name in ("adam", "adamw"):
                 state = (_nd(np.zeros(shape)), _nd(np.zeros(shape)))
             else:
                 state = None

@@ -129,9 +129,26 @@ def test_fused_adam(n):
 
 
 def test_fused_adamw_and_test_optimizer():
-    kw = dict(learning_rate=0.01, wd=1e-2, beta1=0.9, beta2=0.98, epsilon=1e-6, eta=0.7, clip_gradient=0.5)
-    # oracle AdamW has no host-side bias correction; disable it natively too for the bit-exact check
-    _fused_case("adamw", dict(kw, correct_bias=False), kw, 2, 4099, 3)
+    # AdamW as the reference's optimizer class drives the operator: lr = 1, eta = bias-corrected learning
+    # rate (adamW.py:176-200), i.e. w -= lr_t * (m / (sqrt(v) + eps) + wd * w); `eta` is this engine's extra
+    # schedule multiplier
+    kw = dict(learning_rate=0.01, wd=1e-2, beta1=0.9, beta2=0.98, epsilon=1e-6, clip_gradient=0.5)
+    for extra in (dict(correct_bias=True), dict(correct_bias=False, eta=0.7)):
+        k2 = dict(kw, **extra)
+        _fused_case("adamw", k2, k2, 2, 4099, 3)
+    # rescale_grad of 0 / inf / nan: the operator leaves weight and state untouched (adamw-inl.h:455)
+    for bad in (0.0, float("inf"), float("nan")):
+        E = 1003
+        w0 = _rng(3).uniform(0, 1, E).astype(np.float32)
+        kv = mx.kv.create("device")
+        kv.init(0, mx.nd.array(w0, mx.gpu(0)))
+        kv.set_optimizer(mx.optimizer.AdamW(learning_rate=0.01, wd=0.1, rescale_grad=bad))
+        out = mx.nd.empty((E,), mx.gpu(0))
+        kv.pushpull(0, [mx.nd.ones((E,), mx.gpu(0))] * 2, out=out)
+        assert_bits_equal(out.asnumpy(), w0, "adamw rescale %r" % bad)
+        kv.push(0, mx.nd.ones((E,), mx.gpu(0)))
+        kv.pull(0, out=out)
+        assert_bits_equal(out.asnumpy(), w0, "adamw rescale %r (push/pull)" % bad)
     kw = dict(learning_rate=0.3, wd=1e-2, rescale_grad=0.5)
     _fused_case("test", kw, kw, 4, 10007, 3)
 

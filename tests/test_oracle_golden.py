@@ -424,8 +424,8 @@ def test_sum_sq_and_trust_ratio_edge_cases():
 
 
 def test_plain_optimizers_vs_reference_step_golden():
-    """tests/golden/optimizer_steps.npz: weights produced by the reference's own `step` of SGD / Adam / Test
-    (sgd.py:118-154, adam.py:107-147, optimizer.py:570-577; make_golden.py::plain_steps).  Tolerances of
+    """tests/golden/optimizer_steps.npz: weights produced by the reference's own `step` of SGD / Adam / AdamW /
+    Test (sgd.py:118-154, adam.py:107-147, adamW.py:98-140, optimizer.py:570-577; make_golden.py::plain_steps).  Tolerances of
     tests/python/unittest/test_optimizer.py (:75-84 SGD rtol 1e-3 / atol 1e-4, :461-463 Adam rtol 1e-4 /
     atol 2e-5); the kernel restatement in fact agrees to a few ulp."""
     gold = np.load(os.path.join(GOLD, "optimizer_steps.npz"))
@@ -438,6 +438,13 @@ def test_plain_optimizers_vs_reference_step_golden():
             for t in range(5):
                 opt.update(0, w, gold["g%d_%s" % (t, tag)].copy())
                 want = gold["w%d_%s" % (t + 1, tag)]
+                if name == "adamw":
+                    # AdamW.step applies `w -= lr*d` and then `w -= lr*wd*w` to the already-updated weight
+                    # (adamW.py:135-140); the operator uses the old weight for the decay term
+                    # (adamw-inl.h:118-120): they differ by lr^2 * wd * d.  The reference's own comparison of
+                    # the two grants rtol/atol 1e-4 (test_contrib_optimizer.py:163-168)
+                    np.testing.assert_allclose(w, want, rtol=1e-4, atol=1e-4, err_msg=str((name, ci, si, t)))
+                    continue
                 if name == "adam":
                     np.testing.assert_allclose(w, want, rtol=1e-4, atol=2e-5, err_msg=str((name, ci, si, t)))
                 else:

@@ -13,6 +13,7 @@ from . import ndarray
 from . import ndarray as nd
 from .ndarray import NDArray
 from . import optimizer
+from . import lr_scheduler
 from . import kvstore
 from . import kvstore as kv
 from .kvstore import KVStore, KVStoreBase, create

@@ -127,9 +127,20 @@ class KVStore(KVStoreBase):
         check_call(fn(self.handle, len(keys), _c_keys(keys, use_str), _c_vals(vals)))
         self._keys.update(keys)
 
+    def _advance_counts(self, keys):
+        """Optimizer._update_count for every distinct pushed key, THEN the learning rate: the reference's
+        fused_step counts first and asks the scheduler afterwards (sgd.py:184-186), so the first update
+        already runs at ``lr_scheduler(1)``.  The engine keeps the same per-key counts (bias correction)."""
+        if self._fused and self._optimizer is not None:
+            uniq = list(dict.fromkeys(keys))
+            for k in uniq:
+                self._optimizer._update_count(k)
+            self._last_pushed = uniq
+        self._sync_lr()
+
     def push(self, key, value, priority=0):
         keys, vals, use_str = _ctype_key_value(key, value)
-        self._sync_lr()
+        self._advance_counts(keys)
         fn = _LIB.MXKVStorePushEx if use_str else _LIB.MXKVStorePush
         check_call(fn(self.handle, len(keys), _c_keys(keys, use_str), _c_vals(vals), ctypes.c_int(priority)))
 
@@ -146,7 +157,7 @@ class KVStore(KVStoreBase):
             okeys, outs, _ = _ctype_key_value(key, out)
         else:
             okeys, outs = vkeys, vals
-        self._sync_lr()
+        self._advance_counts(vkeys)
         fn = _LIB.MXKVStorePushPullEx if use_str else _LIB.MXKVStorePushPull
         check_call(fn(self.handle, len(vkeys), _c_keys(vkeys, use_str), len(okeys), _c_keys(okeys, use_str),
                       _c_vals(vals), _c_vals(outs), ctypes.c_int(priority)))
@@ -227,9 +238,8 @@ class KVStore(KVStoreBase):
                                                  c_str_array(keys), c_str_array(vals)))
             self._fused = True
             self._last_lr = optimizer.learning_rate
-            mults = set(optimizer.lr_mult) | set(optimizer.wd_mult)
-            for k in mults:
-                self.set_mult(k, optimizer.lr_mult.get(k, 1.0), optimizer.wd_mult.get(k, 1.0))
+            for k, (lm, wm) in optimizer.key_multipliers().items():
+                self.set_mult(k, lm, wm)
             if hasattr(optimizer, "no_trust_ratio_indices"):
                 for k in optimizer.no_trust_ratio_indices():
                     self.set_key_flag(k, "no_trust_ratio", 1)
@@ -257,6 +267,13 @@ class KVStore(KVStoreBase):
         gradient and therefore changed nothing; waits for the push to finish and clears the flag."""
         out = ctypes.c_int(0)
         check_call(_LIB.MXKVB200GetOverflow(self.handle, ctypes.byref(out)))
+        if out.value and self._optimizer is not None:
+            # the skipped step does not count on the Python side either
+            cnt = self._optimizer._index_update_count
+            for k in getattr(self, "_last_pushed", []):
+                if cnt.get(k, 0) > self._optimizer.begin_num_update:
+                    cnt[k] -= 1
+            self._optimizer.num_update = max([self._optimizer.begin_num_update] + list(cnt.values()))
         return bool(out.value)
 
     def _sync_lr(self):

@@ -76,14 +76,38 @@ class Optimizer(object):
         self._index_update_count[index] = self._index_update_count.get(index, self.begin_num_update) + 1
         self.num_update = max(self._index_update_count[index], self.num_update)
 
+    def _mult(self, table, attr, index):
+        """Per-parameter multiplier in the reference's order of precedence (optimizer.py:479-487,518-525):
+        the Parameter object, then the table by index, then the table by name."""
+        if index in self.param_dict:
+            return getattr(self.param_dict[index], attr)
+        if index in table:
+            return table[index]
+        if index in self.idx2name:
+            return table.get(self.idx2name[index], 1.0)
+        return 1.0
+
     def _get_lr(self, index):
-        lr = self.learning_rate
-        name = self.idx2name.get(index, index)
-        return lr * self.lr_mult.get(name, self.lr_mult.get(index, 1.0))
+        return self.learning_rate * self._mult(self.lr_mult, "lr_mult", index)
 
     def _get_wd(self, index):
-        name = self.idx2name.get(index, index)
-        return self.wd * self.wd_mult.get(name, self.wd_mult.get(index, 1.0))
+        return self.wd * self._mult(self.wd_mult, "wd_mult", index)
+
+    def key_multipliers(self):
+        """{index or name: (lr_mult, wd_mult)} for every parameter whose multipliers differ from 1 -- what
+        ``KVStore.set_optimizer`` hands to the engine (MXKVB200SetOptimizerMult)."""
+        names = set(self.idx2name.values())
+        keys = set(self.idx2name) | set(self.param_dict)
+        for table in (self.lr_mult, self.wd_mult):
+            for k in table:
+                if not (isinstance(k, str) and k in names):      # names are reached through their index
+                    keys.add(k)
+        out = {}
+        for k in keys:
+            lm, wm = self._mult(self.lr_mult, "lr_mult", k), self._mult(self.wd_mult, "wd_mult", k)
+            if lm != 1.0 or wm != 1.0:
+                out[k] = (lm, wm)
+        return out
 
     # hyper-parameters handed to the native fused kernel
     def fused_kwargs(self):
@@ -360,6 +384,8 @@ class NativeUpdater(object):
         import ctypes
         if not isinstance(index, (list, tuple)):
             index, grad, weight = [index], [grad], [weight]
+        for i in dict.fromkeys(index):   # count first, then read the learning rate (sgd.py:184-186)
+            self.optimizer._update_count(i)
         self._sync()
         n = len(index)
         use_str = isinstance(index[0], str)
@@ -376,8 +402,6 @@ class NativeUpdater(object):
                     del self._pending["states"][i]
         check_call(fn(self._kv.handle, n, keys, wh, gh))
         self._kv._keys.update(index)
-        for i in index:               # keep the Python-side bookkeeping of Optimizer._update_count
-            self.optimizer._update_count(i)
 
     def get_states(self, dump_optimizer=False):
         return self._kv._dump_fused_states(dump_optimizer)

@@ -246,9 +246,39 @@ def plain_steps():
     np.savez_compressed(os.path.join(HERE, "optimizer_steps.npz"), **out)
 
 
+LR_CASES = [
+    ("FactorScheduler", dict(step=7, factor=0.5, base_lr=0.3)),
+    ("FactorScheduler", dict(step=3, factor=0.1, stop_factor_lr=1e-4, base_lr=0.1, warmup_steps=5, warmup_begin_lr=0.01)),
+    ("MultiFactorScheduler", dict(step=[4, 9, 30], factor=0.3, base_lr=0.2)),
+    ("MultiFactorScheduler", dict(step=[10, 20], factor=0.5, base_lr=1.0, warmup_steps=6, warmup_mode="constant",
+                                  warmup_begin_lr=0.1)),
+    ("PolyScheduler", dict(max_update=40, base_lr=0.05, pwr=2, final_lr=1e-4)),
+    ("PolyScheduler", dict(max_update=30, base_lr=0.4, pwr=1, warmup_steps=8)),
+    ("CosineScheduler", dict(max_update=45, base_lr=0.1, final_lr=0.001)),
+    ("CosineScheduler", dict(max_update=25, base_lr=0.7, warmup_steps=5, warmup_begin_lr=0.2)),
+]
+
+
+def lr_schedules():
+    """lr_schedules.npz: python/mxnet/lr_scheduler.py imported from the reference tree and called with
+    num_update = 0..59 (and once more out of order, for the stateful classes)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_lr_scheduler", os.path.join(REF, "python/mxnet/lr_scheduler.py"))
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    out = {}
+    for i, (cls, kw) in enumerate(LR_CASES):
+        s = getattr(ref, cls)(**kw)
+        out["seq_%d" % i] = np.array([s(n) for n in range(60)], np.float64)
+        s2 = getattr(ref, cls)(**kw)                      # a resumed run jumps straight to a late update
+        out["jump_%d" % i] = np.array([s2(37), s2(38), s2(59)], np.float64)
+    np.savez_compressed(os.path.join(HERE, "lr_schedules.npz"), **out)
+
+
 if __name__ == "__main__":
     dense_sums()
     compression()
     layerwise()
     plain_steps()
+    lr_schedules()
     print("wrote", sorted(f for f in os.listdir(HERE) if f.endswith(".npz")))

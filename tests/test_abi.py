@@ -188,3 +188,54 @@ def test_layerwise_optimizer_descriptors():
     class Custom(mx.optimizer.Optimizer):
         pass
     assert isinstance(mx.optimizer.get_updater(Custom()), mx.optimizer.Updater)
+
+
+def test_lr_schedulers_match_the_reference_module():
+    """tests/golden/lr_schedules.npz was produced by importing python/mxnet/lr_scheduler.py out of the
+    reference tree (make_golden.py::lr_schedules); the schedules here must return the same doubles."""
+    import importlib.util, os
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("mk", os.path.join(here, "golden", "make_golden.py"))
+    mk = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mk)
+    gold = np.load(os.path.join(here, "golden", "lr_schedules.npz"))
+    for i, (cls, kw) in enumerate(mk.LR_CASES):
+        s = getattr(mx.lr_scheduler, cls)(**kw)
+        got = np.array([s(n) for n in range(60)], np.float64)
+        assert np.array_equal(got, gold["seq_%d" % i]), (cls, kw)
+        s2 = getattr(mx.lr_scheduler, cls)(**kw)
+        assert np.array_equal(np.array([s2(37), s2(38), s2(59)]), gold["jump_%d" % i]), (cls, kw)
+    with pytest.raises(ValueError):
+        mx.lr_scheduler.FactorScheduler(step=0)
+    with pytest.raises(ValueError):
+        mx.lr_scheduler.MultiFactorScheduler(step=[5, 5])
+
+
+def test_scheduler_is_consulted_after_counting_the_update():
+    """fused_step counts first and reads the learning rate afterwards (sgd.py:184-186): the first update
+    runs at lr_scheduler(1), and every key of one call sees the same rate."""
+    sched = mx.lr_scheduler.FactorScheduler(step=2, factor=0.5, base_lr=1.0)
+    opt = mx.optimizer.SGD(learning_rate=1.0, lr_scheduler=sched)
+    kv = mx.kv.create("device")
+    kv.set_optimizer(opt)
+    seen = []
+    for step in range(1, 7):
+        kv._advance_counts([0, 1, 0])          # two keys, one of them pushed from two devices
+        seen.append(kv._last_lr)
+        assert opt._index_update_count == {0: step, 1: step} and opt.num_update == step
+    assert seen == [sched_ref for sched_ref in [1.0, 1.0, 0.5, 0.5, 0.25, 0.25]]
+
+
+def test_multipliers_follow_the_reference_precedence():
+    """Optimizer._get_lrs / _get_wds (optimizer.py:461-526): Parameter object, then index, then name."""
+    class P(object):
+        lr_mult, wd_mult = 3.0, 0.0
+    opt = mx.optimizer.SGD(learning_rate=0.1, wd=0.01, param_idx2name={0: "fc_weight", 1: "fc_bias", 2: "bn_gamma"},
+                           param_dict={2: P()})
+    opt.set_lr_mult({"fc_bias": 2.0, 0: 0.5})
+    opt.set_wd_mult({"fc_bias": 0.0})
+    assert opt._get_lr(0) == 0.05 and opt._get_lr(1) == 0.2 and abs(opt._get_lr(2) - 0.3) < 1e-15
+    assert opt._get_wd(0) == 0.01 and opt._get_wd(1) == 0.0 and opt._get_wd(2) == 0.0
+    assert opt.key_multipliers() == {0: (0.5, 1.0), 1: (2.0, 0.0), 2: (3.0, 0.0)}
+    kv = mx.kv.create("device")
+    kv.set_optimizer(opt)                     # reaches MXKVB200SetOptimizerMult by index

@@ -239,3 +239,21 @@ def test_multipliers_follow_the_reference_precedence():
     assert opt.key_multipliers() == {0: (0.5, 1.0), 1: (2.0, 0.0), 2: (3.0, 0.0)}
     kv = mx.kv.create("device")
     kv.set_optimizer(opt)                     # reaches MXKVB200SetOptimizerMult by index
+
+
+def test_plain_c_consumer(tmp_path):
+    """include/mxkv_b200.h is valid C99 and the library links from plain C; the host-only part of the
+    contract (handles, host arrays, key-type rules, 0 / -1 + MXGetLastError) runs without a GPU."""
+    import os, shutil, subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no C compiler")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.join(root, "incubator-mxnet_b200")
+    exe = str(tmp_path / "abi_consumer")
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(root, "include"),
+                    os.path.join(root, "tests", "c", "abi_consumer.c"), "-o", exe, "-L", libdir, "-lmxkv_b200",
+                    "-Wl,-rpath," + libdir], check=True, capture_output=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "abi_consumer ok" in r.stdout

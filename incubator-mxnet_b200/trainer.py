@@ -141,6 +141,17 @@ class Trainer(object):
             "allreduce_grads() when parameters are updated on kvstore is not supported."
         self._allreduce_grads()
 
+    def update(self, batch_size, ignore_stale_grad=False):
+        """trainer.py:411-442: the update half of ``step`` for callers that ran ``allreduce_grads()``
+        themselves (e.g. to clip the reduced gradients); not available when the kvstore updates."""
+        if not self._kv_initialized:
+            self._init_kvstore()
+        assert not (self._kvstore is not None and self._update_on_kvstore), \
+            "update() when parameters are updated on kvstore is not supported. " \
+            "Try setting `update_on_kvstore` to False when creating trainer."
+        self._optimizer.rescale_grad = self._scale / batch_size
+        self._update()
+
     def _update(self):
         """trainer.py:444-480: per-device local updaters.  Optimizers with a fused kernel update every
         parameter of a device in one native launch (the reference's aggregated multi_* operators);

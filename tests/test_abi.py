@@ -257,3 +257,13 @@ def test_plain_c_consumer(tmp_path):
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     assert "abi_consumer ok" in r.stdout
+
+
+def test_trainer_update_requires_local_updates():
+    """trainer.py:436-439: update() is refused when the kvstore applies the optimizer."""
+    class P(object):                       # stands in for a torch Parameter: never touched before the assert
+        pass
+    tr = mx.Trainer([P()], "sgd", {"learning_rate": 0.1}, kvstore="device")
+    tr._kv_initialized, tr._kvstore, tr._update_on_kvstore = True, object(), True
+    with pytest.raises(AssertionError):
+        tr.update(4)

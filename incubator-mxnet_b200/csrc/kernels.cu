@@ -401,12 +401,13 @@ __device__ __forceinline__ void mm_st(void* p, const float4& v) {
                :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
-template <int OPT, bool MP>
+// U: 16-byte multimem.ld_reduce requests in flight per thread (MXKV_B200_NVLS_U; 2 is the measured
+// default, 4 / 8 exist for the light optimizers to explore the latency-bound reduce-scatter half)
+template <int OPT, bool MP, int U>
 __global__ void __launch_bounds__(kThreads, 2)
 kv_dense_nvls_kernel(DenseLaunch L) {
   __shared__ TensorWork tw;
   barrier_start(L.sync);
-  constexpr int U = 2;
   constexpr bool HAS_S0 = OPT == OPT_SGD_MOM || OPT == OPT_ADAM || OPT == OPT_ADAMW;
   constexpr bool HAS_S1 = OPT == OPT_ADAM || OPT == OPT_ADAMW;
   int cur = -1;
@@ -480,14 +481,23 @@ kv_dense_nvls_kernel(DenseLaunch L) {
 }
 
 typedef void (*NvlsKernelFn)(DenseLaunch);
-static NvlsKernelFn pick_nvls(int opt, int mp) {
+static NvlsKernelFn pick_nvls(int opt, int mp, int unroll) {
+  if (unroll >= 8 && opt == OPT_NONE) return kv_dense_nvls_kernel<OPT_NONE, false, 8>;
+  if (unroll >= 4) {
+    switch (opt) {
+      case OPT_NONE: return kv_dense_nvls_kernel<OPT_NONE, false, 4>;
+      case OPT_SGD: return mp ? kv_dense_nvls_kernel<OPT_SGD, true, 4> : kv_dense_nvls_kernel<OPT_SGD, false, 4>;
+      case OPT_SGD_MOM: return mp ? kv_dense_nvls_kernel<OPT_SGD_MOM, true, 4> : kv_dense_nvls_kernel<OPT_SGD_MOM, false, 4>;
+      default: break;      // the heavier optimizers stay at two requests (register budget)
+    }
+  }
   switch (opt) {
-    case OPT_NONE: return kv_dense_nvls_kernel<OPT_NONE, false>;
-    case OPT_SGD: return mp ? kv_dense_nvls_kernel<OPT_SGD, true> : kv_dense_nvls_kernel<OPT_SGD, false>;
-    case OPT_SGD_MOM: return mp ? kv_dense_nvls_kernel<OPT_SGD_MOM, true> : kv_dense_nvls_kernel<OPT_SGD_MOM, false>;
-    case OPT_ADAM: return mp ? kv_dense_nvls_kernel<OPT_ADAM, true> : kv_dense_nvls_kernel<OPT_ADAM, false>;
-    case OPT_ADAMW: return mp ? kv_dense_nvls_kernel<OPT_ADAMW, true> : kv_dense_nvls_kernel<OPT_ADAMW, false>;
-    case OPT_TEST: return mp ? kv_dense_nvls_kernel<OPT_TEST, true> : kv_dense_nvls_kernel<OPT_TEST, false>;
+    case OPT_NONE: return kv_dense_nvls_kernel<OPT_NONE, false, 2>;
+    case OPT_SGD: return mp ? kv_dense_nvls_kernel<OPT_SGD, true, 2> : kv_dense_nvls_kernel<OPT_SGD, false, 2>;
+    case OPT_SGD_MOM: return mp ? kv_dense_nvls_kernel<OPT_SGD_MOM, true, 2> : kv_dense_nvls_kernel<OPT_SGD_MOM, false, 2>;
+    case OPT_ADAM: return mp ? kv_dense_nvls_kernel<OPT_ADAM, true, 2> : kv_dense_nvls_kernel<OPT_ADAM, false, 2>;
+    case OPT_ADAMW: return mp ? kv_dense_nvls_kernel<OPT_ADAMW, true, 2> : kv_dense_nvls_kernel<OPT_ADAMW, false, 2>;
+    case OPT_TEST: return mp ? kv_dense_nvls_kernel<OPT_TEST, true, 2> : kv_dense_nvls_kernel<OPT_TEST, false, 2>;
     default: return nullptr;
   }
 }
@@ -675,7 +685,7 @@ int BulkPlan(int device, int opt, int multi_precision, int arrays, int* tile_ele
 
 int LaunchDense(const DenseLaunch& L, cudaStream_t stream) {
   if (L.nvls) {
-    NvlsKernelFn nf = pick_nvls(L.opt, L.multi_precision);
+    NvlsKernelFn nf = pick_nvls(L.opt, L.multi_precision, L.nvls_unroll);
     if (nf == nullptr || L.dtype != kFloat32 || L.sync.mode == SYNC_NONE) return static_cast<int>(cudaErrorInvalidValue);
     int grid = L.grid < 1 ? 1 : (L.grid > kMaxBlocks ? kMaxBlocks : L.grid);
     nf<<<grid, kThreads, 0, stream>>>(L);

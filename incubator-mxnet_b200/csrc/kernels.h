@@ -108,6 +108,7 @@ struct DenseLaunch {
   int bulk;                      // 1: shared-memory staged variant (cp.async.bulk + mbarrier pipeline)
   int bulk_stages;               // pipeline depth
   int bulk_arrays;               // input arrays staged per tile (max over the work list)
+  int nvls_unroll;               // NVLS variant: multimem.ld_reduce requests in flight per thread (2, 4 or 8)
 };
 
 // returns cudaError_t as int; never throws

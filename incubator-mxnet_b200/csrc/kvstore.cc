@@ -1467,6 +1467,7 @@ void KVStore::LaunchWorks(const LaunchClassKey& ck, std::vector<std::vector<Tens
     L.threads = rt->threads;
     L.bulk = bulk; L.bulk_stages = bulk_stages; L.bulk_arrays = bulk_arrays;
     L.nvls = ck.nvls;
+    L.nvls_unroll = rt->nvls_unroll;
     if (ck.nvls) { L.threads = 512; L.grid = static_cast<int>(std::min<int64_t>(DenseMaxGrid(dev, 512), max_chunks)); }
     int small_n = 1;
     for (auto& t : w) if (t.n_src > 2) small_n = 0;

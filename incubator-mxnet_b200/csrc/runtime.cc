@@ -170,6 +170,7 @@ Runtime::Runtime() {
   chunk_elems = (chunk_elems + 127) / 128 * 128;
   bulk_mode = static_cast<int>(EnvInt("MXKV_B200_BULK", 1));
   nvls_mode = static_cast<int>(EnvInt("MXKV_B200_NVLS", 1));
+  nvls_unroll = static_cast<int>(EnvInt("MXKV_B200_NVLS_U", 2));
   spin_timeout_cycles = EnvInt("MXKV_B200_SPIN_TIMEOUT_S", 120) * 1900000000LL;   // ~1.9 GHz SM clock
   max_blocks = static_cast<int>(EnvInt("MXKV_B200_MAX_BLOCKS", 0));
   threads = static_cast<int>(EnvInt("MXKV_B200_THREADS", 512));

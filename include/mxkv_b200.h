@@ -155,6 +155,11 @@ MXKV_DLL int MXKVB200UpdaterStep(KVStoreHandle handle, uint32_t num, const int* 
                                  NDArrayHandle* weights, NDArrayHandle* grads);
 MXKV_DLL int MXKVB200UpdaterStepEx(KVStoreHandle handle, uint32_t num, const char** keys,
                                    NDArrayHandle* weights, NDArrayHandle* grads);
+/* Introspection: the per-key scalars the fused kernel would receive for the key's CURRENT update count
+ * (learning rate with lr_mult and, for Adam, the host-side bias correction folded in; weight decay with
+ * wd_mult; AdamW: operator lr = 1 and eta = the bias-corrected learning rate).  Host-only, no GPU needed. */
+MXKV_DLL int MXKVB200GetKeyHyper(KVStoreHandle handle, int key, const char* str_key, float* lr, float* wd,
+                                 float* eta);
 /* per-key switch of a fused optimizer.  "no_trust_ratio" != 0: LARS keeps the plain learning rate
  * for this key (the reference does so for names ending in gamma / beta / bias, lars.py:121-123). */
 MXKV_DLL int MXKVB200SetKeyFlag(KVStoreHandle handle, int key, const char* str_key, const char* name,

@@ -510,6 +510,12 @@ int MXKVB200UpdaterStepEx(KVStoreHandle handle, uint32_t num, const char** keys,
   API_END();
 }
 
+int MXKVB200GetKeyHyper(KVStoreHandle handle, int key, const char* str_key, float* lr, float* wd, float* eta) {
+  API_BEGIN();
+  KV(handle)->GetKeyHyper(str_key != nullptr, key, str_key ? str_key : "", lr, wd, eta);
+  API_END();
+}
+
 int MXKVB200SetKeyFlag(KVStoreHandle handle, int key, const char* str_key, const char* name, int value) {
   API_BEGIN();
   MXKV_CHECK(name != nullptr) << "flag name is null";

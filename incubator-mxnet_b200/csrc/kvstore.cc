@@ -1713,6 +1713,15 @@ void KVStore::SetState(bool str_key, int ikey, const std::string& skey, int whic
   }
 }
 
+void KVStore::GetKeyHyper(bool str_key, int ikey, const std::string& skey, float* lr, float* wd, float* eta) {
+  LOCK();
+  MXKV_CHECK(opt_.enabled) << "no fused optimizer is set";
+  const KeyState& ks = GetKey(ResolveKey(str_key, ikey, skey));
+  if (lr) *lr = KeyLR(ks);
+  if (wd) *wd = KeyWD(ks);
+  if (eta) *eta = KeyEta(ks);
+}
+
 int64_t KVStore::GetUpdateCount(bool str_key, int ikey, const std::string& skey) {
   LOCK();
   return GetKey(ResolveKey(str_key, ikey, skey)).count;

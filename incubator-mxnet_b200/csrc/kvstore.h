@@ -143,6 +143,7 @@ class KVStore {
   // 1 if the last push with skip_nonfinite met a non-finite gradient (and therefore changed nothing);
   // waits for the engine streams, undoes that push's update counts, clears the flag
   int ResolveOverflow();
+  void GetKeyHyper(bool str_key, int ikey, const std::string& skey, float* lr, float* wd, float* eta);
   int64_t GetUpdateCount(bool str_key, int ikey, const std::string& skey);
   void SetUpdateCount(bool str_key, int ikey, const std::string& skey, int64_t c);
 

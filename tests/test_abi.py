@@ -267,3 +267,52 @@ def test_trainer_update_requires_local_updates():
     tr._kv_initialized, tr._kvstore, tr._update_on_kvstore = True, object(), True
     with pytest.raises(AssertionError):
         tr.update(4)
+
+
+def _key_hyper(kv, key):
+    import ctypes
+    from mxnet_b200.base import _LIB, check_call
+    lr, wd, eta = ctypes.c_float(), ctypes.c_float(), ctypes.c_float()
+    check_call(_LIB.MXKVB200GetKeyHyper(kv.handle, int(key), None, ctypes.byref(lr), ctypes.byref(wd), ctypes.byref(eta)))
+    return np.float32(lr.value), np.float32(wd.value), np.float32(eta.value)
+
+
+def _set_count(kv, key, t):
+    import ctypes
+    from mxnet_b200.base import _LIB, check_call
+    check_call(_LIB.MXKVB200SetUpdateCount(kv.handle, int(key), None, ctypes.c_int64(t)))
+
+
+def test_per_key_hyper_parameters_follow_the_python_optimizers():
+    """What the fused kernel receives per key, checked on the host against the reference's Python
+    bookkeeping: lr/wd multipliers (optimizer.py:461-526), Adam's bias correction folded into lr in double
+    (adam.py:172-175), AdamW driving its operator with lr = 1 and eta = lr_t (adamW.py:158-200)."""
+    import math
+    from oracle import oracle as O
+    kv = mx.kv.create("device")
+    kv.init([0, 1], [mx.nd.zeros((4,)), mx.nd.zeros((4,))])
+    # SGD with multipliers
+    opt = mx.optimizer.SGD(learning_rate=0.1, wd=0.01)
+    opt.set_lr_mult({1: 0.5}); opt.set_wd_mult({1: 0.0})
+    kv.set_optimizer(opt)
+    assert _key_hyper(kv, 0) == (np.float32(0.1), np.float32(0.01), np.float32(1.0))
+    assert _key_hyper(kv, 1) == (np.float32(0.05), np.float32(0.0), np.float32(1.0))
+    # Adam: lr * sqrt(1 - b2^t) / (1 - b1^t), rounded once
+    kv.set_optimizer(mx.optimizer.Adam(learning_rate=0.003, beta1=0.8, beta2=0.95, wd=0.02))
+    for t in (1, 2, 7, 1000):
+        _set_count(kv, 0, t)
+        want = 0.003 * math.sqrt(1. - 0.95 ** t) / (1. - 0.8 ** t)
+        lr, wd, eta = _key_hyper(kv, 0)
+        assert lr == np.float32(want) == np.float32(O.adam_lr(0.003, 0.8, 0.95, t)) and wd == np.float32(0.02)
+    # AdamW: operator lr = 1, eta = (bias-corrected) learning rate [* the engine's own eta multiplier]
+    for correct_bias, mult in ((True, 1.0), (False, 0.7)):
+        kv.set_optimizer(mx.optimizer.AdamW(learning_rate=0.01, beta1=0.9, beta2=0.98, wd=0.05,
+                                            correct_bias=correct_bias, eta=mult))
+        for t in (1, 3, 50):
+            _set_count(kv, 0, t)
+            lr_t = 0.01 * math.sqrt(1. - 0.98 ** t) / (1. - 0.9 ** t) if correct_bias else 0.01
+            lr, wd, eta = _key_hyper(kv, 0)
+            assert lr == np.float32(1.0) and wd == np.float32(0.05) and eta == np.float32(lr_t * mult)
+    # LAMB / LARS keep the plain learning rate (their ratios are taken on the device)
+    kv.set_optimizer(mx.optimizer.LAMB(learning_rate=0.02))
+    assert _key_hyper(kv, 0)[0] == np.float32(0.02)

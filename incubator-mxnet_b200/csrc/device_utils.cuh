@@ -3,6 +3,7 @@
 // arithmetic of the fused optimizers.
 #pragma once
 #include "kernels.h"
+#include "optim_math.h"
 #include <cuda_fp16.h>
 #include <cuda_bf16.h>
 
@@ -188,73 +189,6 @@ template <int N> __device__ __forceinline__ void stf(float* p, int64_t e, const 
       st16(p + e + i, v);
     }
   }
-}
-
-struct Hyper {
-  float lr, wd, eta, rescale, clip, momentum, beta1, beta2, eps;
-};
-
-__device__ __forceinline__ float clipf(float x, float b) {   // mshadow_op::clip, mshadow_op.h:999-1009
-  return x > b ? b : (x < -b ? -b : x);
-}
-
-// one element of the fused update; returns the new weight.  Operation order is
-// the reference source's, see the OptKind comments in kernels.h.
-template <int OPT>
-__device__ __forceinline__ float update_one(float g, float w, float& s0, float& s1, const Hyper& h) {
-  if (OPT == OPT_SGD) {
-    float r = __fmul_rn(h.rescale, g);
-    if (h.clip >= 0.0f) r = clipf(r, h.clip);
-    r = __fadd_rn(r, __fmul_rn(h.wd, w));
-    return __fsub_rn(w, __fmul_rn(h.lr, r));
-  } else if (OPT == OPT_SGD_MOM) {
-    float r = __fmul_rn(h.rescale, g);
-    if (h.clip >= 0.0f) r = clipf(r, h.clip);
-    r = __fadd_rn(r, __fmul_rn(h.wd, w));
-    float m = __fmul_rn(s0, h.momentum);
-    m = __fsub_rn(m, __fmul_rn(h.lr, r));
-    s0 = m;
-    return __fadd_rn(w, m);
-  } else if (OPT == OPT_ADAM) {
-    float r = __fmul_rn(g, h.rescale);
-    if (h.clip >= 0.0f) r = clipf(r, h.clip);
-    r = __fadd_rn(r, __fmul_rn(w, h.wd));
-    const float m = __fadd_rn(__fmul_rn(h.beta1, s0), __fmul_rn(__fsub_rn(1.f, h.beta1), r));
-    const float v = __fadd_rn(__fmul_rn(h.beta2, s1),
-                              __fmul_rn(__fmul_rn(__fsub_rn(1.f, h.beta2), r), r));
-    s0 = m; s1 = v;
-    return __fsub_rn(w, __fdiv_rn(__fmul_rn(h.lr, m), __fadd_rn(__fsqrt_rn(v), h.eps)));
-  } else if (OPT == OPT_ADAMW) {
-    float sg = __fmul_rn(h.rescale, g);
-    if (h.clip >= 0.0f) sg = clipf(sg, h.clip);
-    const float m = __fadd_rn(__fmul_rn(h.beta1, s0), __fmul_rn(__fsub_rn(1.0f, h.beta1), sg));
-    const float v = __fadd_rn(__fmul_rn(h.beta2, s1),
-                              __fmul_rn(__fsub_rn(1.0f, h.beta2), __fmul_rn(sg, sg)));
-    s0 = m; s1 = v;
-    const float step = __fadd_rn(__fdiv_rn(__fmul_rn(h.lr, m), __fadd_rn(__fsqrt_rn(v), h.eps)),
-                                 __fmul_rn(h.wd, w));
-    return __fsub_rn(w, __fmul_rn(h.eta, step));
-  } else if (OPT == OPT_TEST) {
-    const float gr = __fmul_rn(h.rescale, g);
-    const float s = __fadd_rn(gr, __fmul_rn(h.wd, w));
-    return __fsub_rn(w, __fmul_rn(h.lr, s));
-  } else if (OPT == OPT_SGD_STD) {
-    // every row: w *= (1 - lr*wd); rows of the gradient: w -= lr * clip(rescale*g) (wd already applied)
-    const float ws = __fmul_rn(w, __fsub_rn(1.0f, __fmul_rn(h.lr, h.wd)));
-    float r = __fmul_rn(h.rescale, g);
-    if (h.clip >= 0.0f) r = clipf(r, h.clip);
-    r = __fadd_rn(r, __fmul_rn(0.0f, ws));
-    return __fsub_rn(ws, __fmul_rn(h.lr, r));
-  } else if (OPT == OPT_ADAM_STD) {
-    float r = __fmul_rn(g, h.rescale);
-    if (h.clip >= 0.0f) r = clipf(r, h.clip);
-    r = __fadd_rn(r, __fmul_rn(w, h.wd));
-    const float m = __fadd_rn(__fmul_rn(h.beta1, s0), __fmul_rn(__fsub_rn(1.f, h.beta1), r));
-    const float v = __fadd_rn(__fmul_rn(h.beta2, s1), __fmul_rn(__fsub_rn(1.f, h.beta2), __fmul_rn(r, r)));
-    s0 = m; s1 = v;
-    return __fsub_rn(w, __fdiv_rn(__fmul_rn(h.lr, m), __fadd_rn(__fsqrt_rn(v), h.eps)));
-  }
-  return g;  // OPT_NONE
 }
 
 }  // namespace mxkv

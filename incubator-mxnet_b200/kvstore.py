@@ -24,24 +24,40 @@ from . import optimizer as opt
 
 def _ctype_key_value(keys, vals):
     """Flatten (keys, vals) key-major like base.py:32-65.  Returns (keys list, NDArray list,
-    use_str_keys)."""
-    if isinstance(keys, (tuple, list)):
-        assert len(keys) == len(vals)
-        c_keys, c_vals, use_str = [], [], None
-        for key, val in zip(keys, vals):
+    use_str_keys).  Written as a loop, not a recursion: a training step passes a few hundred keys and this
+    sits on the host's critical path (the launch is asynchronous; the marshalling is not)."""
+    if not isinstance(keys, (tuple, list)):
+        assert isinstance(keys, (int, str)), "unexpected type for keys: " + str(type(keys))
+        use_str = isinstance(keys, str)
+        if isinstance(vals, NDArray):
+            return [keys], [vals], use_str
+        vals = list(vals)
+        assert all(isinstance(v, NDArray) for v in vals)
+        return [keys] * len(vals), vals, use_str
+    assert len(keys) == len(vals)
+    c_keys, c_vals = [], []
+    n_str = 0
+    for key, val in zip(keys, vals):
+        if isinstance(key, (tuple, list)):                     # nested key lists: the general case
             k_i, v_i, s_i = _ctype_key_value(key, val)
             c_keys += k_i
             c_vals += v_i
-            use_str = s_i if use_str is None else use_str
-            assert use_str == s_i, "inconsistent types of keys detected."
-        return c_keys, c_vals, use_str
-    assert isinstance(keys, (int, str)), "unexpected type for keys: " + str(type(keys))
-    use_str = isinstance(keys, str)
-    if isinstance(vals, NDArray):
-        return [keys], [vals], use_str
-    for v in vals:
-        assert isinstance(v, NDArray)
-    return [keys] * len(vals), list(vals), use_str
+            n_str += len(k_i) if s_i else 0
+            continue
+        if isinstance(key, str):
+            n_str += 1 if isinstance(val, NDArray) else len(val)
+        else:
+            assert isinstance(key, int), "unexpected type for keys: " + str(type(key))
+        if isinstance(val, NDArray):
+            c_keys.append(key)
+            c_vals.append(val)
+        else:
+            for v in val:
+                assert isinstance(v, NDArray)
+                c_keys.append(key)
+                c_vals.append(v)
+    assert n_str == 0 or n_str == len(c_keys), "inconsistent types of keys detected."
+    return c_keys, c_vals, (n_str > 0 if c_keys else None)
 
 
 def _c_keys(keys, use_str):
@@ -50,7 +66,7 @@ def _c_keys(keys, use_str):
 
 def _c_vals(vals):
     arr = (ctypes.c_void_p * len(vals))()
-    arr[:] = [v.handle.value for v in vals]
+    arr[:] = [v._h for v in vals]
     return arr
 
 
@@ -132,9 +148,15 @@ class KVStore(KVStoreBase):
         fused_step counts first and asks the scheduler afterwards (sgd.py:184-186), so the first update
         already runs at ``lr_scheduler(1)``.  The engine keeps the same per-key counts (bias correction)."""
         if self._fused and self._optimizer is not None:
+            opt_ = self._optimizer
             uniq = list(dict.fromkeys(keys))
-            for k in uniq:
-                self._optimizer._update_count(k)
+            cnt, begin, top = opt_._index_update_count, opt_.begin_num_update, opt_.num_update
+            for k in uniq:                      # Optimizer._update_count, inlined: hundreds of keys per step
+                c = cnt.get(k, begin) + 1
+                cnt[k] = c
+                if c > top:
+                    top = c
+            opt_.num_update = top
             self._last_pushed = uniq
         self._sync_lr()
 

@@ -35,10 +35,11 @@ def _f32_to_bf16(f32):
 
 class NDArray(object):
     """Handle to a native array.  ``handle`` is the opaque NDArrayHandle."""
-    __slots__ = ("handle", "_keep", "__weakref__")
+    __slots__ = ("handle", "_h", "_keep", "__weakref__")
 
     def __init__(self, handle, keep=None):
         self.handle = handle if isinstance(handle, ctypes.c_void_p) else ctypes.c_void_p(handle)
+        self._h = self.handle.value      # the raw address, read once (marshalling hundreds of arrays per step)
         self._keep = keep     # objects that own borrowed memory (e.g. a torch tensor)
 
     def __del__(self):

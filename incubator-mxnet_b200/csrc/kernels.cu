@@ -744,47 +744,15 @@ __global__ void kv_quantize_kernel(const float* __restrict__ grad, float* __rest
   constexpr int PER_WORD = 32 / BITS;
   const int64_t nwords = (n + PER_WORD - 1) / PER_WORD;
   for (int64_t w = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; w < nwords;
-       w += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    uint32_t word = 0;
-    const int64_t base = w * PER_WORD;
-#pragma unroll
-    for (int j = 0; j < PER_WORD; ++j) {
-      const int64_t i = base + j;
-      if (i >= n) break;
-      float r = __fadd_rn(residual[i], grad[i]);
-      const int byte = j / (8 / BITS);           // byte within the word (little endian in memory)
-      const int slot = j % (8 / BITS);           // value within the byte, MSB first
-      if (BITS == 2) {
-        if (r >= thr) { word |= (0x3u << (6 - 2 * slot)) << (8 * byte); r = __fsub_rn(r, thr); }
-        else if (r <= -thr) { word |= (0x2u << (6 - 2 * slot)) << (8 * byte); r = __fsub_rn(r, -thr); }
-      } else {
-        if (r > thr) { word |= (0x1u << (7 - slot)) << (8 * byte); r = __fsub_rn(r, 1.0f); }
-        else r = __fadd_rn(r, 1.0f);
-      }
-      residual[i] = r;
-    }
-    out[w] = word;
-  }
+       w += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    out[w] = quantize_word<BITS>(grad, residual, n, thr, w);
 }
 
 template <int BITS>
 __global__ void kv_dequantize_kernel(const uint32_t* __restrict__ in, float* __restrict__ out, int64_t n, float thr) {
-  constexpr int PER_WORD = 32 / BITS;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const uint32_t word = in[i / PER_WORD];
-    const int j = static_cast<int>(i % PER_WORD);
-    const int byte = j / (8 / BITS), slot = j % (8 / BITS);
-    const uint32_t b = (word >> (8 * byte)) & 0xffu;
-    float v;
-    if (BITS == 2) {
-      const uint32_t code = (b >> (6 - 2 * slot)) & 0x3u;
-      v = code == 0x3u ? thr : (code == 0x2u ? -thr : 0.0f);
-    } else {
-      v = ((b >> (7 - slot)) & 0x1u) ? 1.0f : -1.0f;
-    }
-    out[i] = v;
-  }
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    out[i] = dequantize_value<BITS>(in, thr, i);
 }
 
 int LaunchQuantize(int bits, const float* grad, float* residual, uint32_t* out, int64_t n, float thr, cudaStream_t s) {

@@ -90,4 +90,49 @@ MXKV_HD float update_one(float g, float w, float& s0, float& s1, const Hyper& h)
   return g;  // OPT_NONE
 }
 
+// ---------------------------------------------------------------------------
+// 1-bit / 2-bit gradient compression with error feedback (src/kvstore/gradient_compression-inl.h:44-227).
+// Bit layout is the reference's: byte j of the stream holds values 4j..4j+3 (2-bit) or 8j..8j+7 (1-bit),
+// first value in the most significant bits.
+// ---------------------------------------------------------------------------
+// code word w of the stream: residual += grad for its values, emit the codes, keep the quantisation error
+template <int BITS>
+MXKV_HD uint32_t quantize_word(const float* grad, float* residual, int64_t n, float thr, int64_t w) {
+  constexpr int PER_WORD = 32 / BITS;
+  uint32_t word = 0;
+  const int64_t base = w * PER_WORD;
+#pragma unroll
+  for (int j = 0; j < PER_WORD; ++j) {
+    const int64_t i = base + j;
+    if (i >= n) break;
+    float r = __fadd_rn(residual[i], grad[i]);
+    const int byte = j / (8 / BITS);           // byte within the word (little endian in memory)
+    const int slot = j % (8 / BITS);           // value within the byte, MSB first
+    if (BITS == 2) {
+      if (r >= thr) { word |= (0x3u << (6 - 2 * slot)) << (8 * byte); r = __fsub_rn(r, thr); }
+      else if (r <= -thr) { word |= (0x2u << (6 - 2 * slot)) << (8 * byte); r = __fsub_rn(r, -thr); }
+    } else {
+      if (r > thr) { word |= (0x1u << (7 - slot)) << (8 * byte); r = __fsub_rn(r, 1.0f); }
+      else r = __fadd_rn(r, 1.0f);
+    }
+    residual[i] = r;
+  }
+  return word;
+}
+
+// value i of a code stream
+template <int BITS>
+MXKV_HD float dequantize_value(const uint32_t* in, float thr, int64_t i) {
+  constexpr int PER_WORD = 32 / BITS;
+  const uint32_t word = in[i / PER_WORD];
+  const int j = static_cast<int>(i % PER_WORD);
+  const int byte = j / (8 / BITS), slot = j % (8 / BITS);
+  const uint32_t b = (word >> (8 * byte)) & 0xffu;
+  if (BITS == 2) {
+    const uint32_t code = (b >> (6 - 2 * slot)) & 0x3u;
+    return code == 0x3u ? thr : (code == 0x2u ? -thr : 0.0f);
+  }
+  return ((b >> (7 - slot)) & 0x1u) ? 1.0f : -1.0f;
+}
+
 }  // namespace mxkv

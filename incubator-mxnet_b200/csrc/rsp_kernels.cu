@@ -17,6 +17,7 @@
 //                     materialise the merged row_sparse value.
 // The row counts stay on the device (every kernel reads nnz through a pointer).
 #include "rsp_kernels.h"
+#include "rsp_math.h"
 
 namespace mxkv {
 
@@ -30,8 +31,6 @@ __device__ __forceinline__ int64_t lower_bound_i64(const int64_t* a, int64_t n, 
   }
   return lo;
 }
-
-__device__ __forceinline__ float clipf(float x, float b) { return x > b ? b : (x < -b ? -b : x); }
 
 __global__ void rsp_first_kernel(RspSources S, int32_t* first, int64_t cap) {
   const int s = blockIdx.y;
@@ -162,29 +161,7 @@ rsp_rows_kernel(RspSources S, RspRowArgs A) {
 #pragma unroll
         for (int i = 0; i < W; ++i) {
           if (OPT == OPT_NONE) { w[i] = acc[i]; continue; }
-          // SGDDnsRspKernel / SGDMomDnsRspDnsKernel / AdamDnsRspDnsKernel: same arithmetic as the
-          // dense kernels, only on the rows present in the gradient (lazy update)
-          float g = (OPT == OPT_ADAM) ? __fmul_rn(acc[i], A.rescale) : __fmul_rn(A.rescale, acc[i]);
-          if (A.clip >= 0.0f) g = clipf(g, A.clip);
-          const float wv = w[i];
-          g = __fadd_rn(g, (OPT == OPT_ADAM) ? __fmul_rn(wv, A.wd) : __fmul_rn(A.wd, wv));
-          if (OPT == OPT_SGD) {
-            w[i] = __fsub_rn(wv, __fmul_rn(A.lr, g));
-          } else if (OPT == OPT_SGD_MOM) {
-            float* mp = A.s0 + id * L + c + i;
-            float m = __fmul_rn(*mp, A.momentum);
-            m = __fsub_rn(m, __fmul_rn(A.lr, g));
-            *mp = m;
-            w[i] = __fadd_rn(wv, m);
-          } else if (OPT == OPT_ADAM) {
-            float* mp = A.s0 + id * L + c + i;
-            float* vp = A.s1 + id * L + c + i;
-            const float m = __fadd_rn(__fmul_rn(A.beta1, *mp), __fmul_rn(__fsub_rn(1.f, A.beta1), g));
-            const float v = __fadd_rn(__fmul_rn(A.beta2, *vp),
-                                      __fmul_rn(__fmul_rn(__fsub_rn(1.f, A.beta2), g), g));
-            *mp = m; *vp = v;
-            w[i] = __fsub_rn(wv, __fdiv_rn(__fmul_rn(A.lr, m), __fadd_rn(__fsqrt_rn(v), A.eps)));
-          }
+          w[i] = rsp_lazy_update<OPT>(acc[i], w[i], id * L + c + i, A);
         }
       }
     }

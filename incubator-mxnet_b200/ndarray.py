@@ -2,6 +2,7 @@
 and sparse.py that the KVStore path and its tests use).  Data lives in memory owned by the
 native library (or borrowed from torch); numpy is only a host-side transport here."""
 import ctypes
+import os
 
 import numpy as np
 
@@ -192,6 +193,20 @@ class NDArray(object):
         return t
 
     def _binary_inplace(self, other, op):
+        if os.environ.get("MXKV_SIM"):
+            # simulated CUDA runtime (tests/sim): torch cannot share a process with the stand-in
+            # libcudart, so the convenience arithmetic goes through numpy
+            a = self.asnumpy().astype(np.float64 if self.dtype == np.float64 else np.float32)
+            if isinstance(other, NDArray) and other.stype == "row_sparse":
+                assert op in ("add_", "sub_"), "row_sparse operand supports += / -= only"
+                idx = other.indices.asnumpy()
+                val = other.data.asnumpy().reshape((idx.size,) + a.shape[1:])
+                np.add.at(a, idx, val if op == "add_" else -val)
+            else:
+                o = other.asnumpy() if isinstance(other, NDArray) else other
+                a = {"add_": a + o, "sub_": a - o, "mul_": a * o}[op]
+            self._sync_copyfrom(a)
+            return self
         t = self.as_torch()
         if isinstance(other, NDArray) and other.stype == "row_sparse":
             # dense (op)= row_sparse: only the stored rows take part (used by updater callbacks)

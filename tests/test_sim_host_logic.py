@@ -1,0 +1,59 @@
+"""The engine's host logic exercised on a simulated CUDA runtime (tests/sim): the `-m gpu` parity tests run,
+unchanged, against the product's own object files re-linked to a stand-in libcudart whose kernel launches are
+carried out by semantic emulators built from the kernels' arithmetic headers.  Everything around the kernels
+is real: C ABI, key bookkeeping, placement over several (simulated) GPUs, replica / optimizer-state / shard
+management, work lists, aliasing rules, launch sequences.  See tests/sim/README.md for what this can and
+cannot establish."""
+import importlib.util
+import os
+import shutil
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SIM = os.path.join(ROOT, "tests", "sim")
+
+
+@pytest.fixture(scope="module")
+def sim_lib():
+    if shutil.which("g++") is None or not os.path.exists("/usr/local/cuda/bin/nvcc"):
+        pytest.skip("needs g++ and nvcc to build the simulated runtime")
+    spec = importlib.util.spec_from_file_location("build_sim", os.path.join(SIM, "build_sim.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    lib, _ = b.build()
+    return lib
+
+
+def _run(sim_lib, devices, files, extra=()):
+    env = dict(os.environ)
+    env.update(MXKV_SIM="1", MXKV_B200_LIBRARY_PATH=sim_lib, MXKV_SIM_DEVICES=str(devices))
+    cmd = [sys.executable, "-m", "pytest", "-q", "-m", "gpu", "-p", "no:cacheprovider"] + list(extra) + \
+          [os.path.join(ROOT, "tests", f) for f in files]
+    r = subprocess.run(cmd, env=env, cwd=ROOT, capture_output=True, text=True, timeout=1500)
+    tail = (r.stdout + r.stderr)[-3000:]
+    assert r.returncode == 0, tail
+    return r.stdout
+
+
+def _passed(out):
+    import re
+    m = re.search(r"(\d+) passed", out)
+    return int(m.group(1)) if m else 0
+
+
+def test_single_gpu_paths(sim_lib):
+    out = _run(sim_lib, 1, ["test_gpu_dense.py", "test_gpu_reference_kats.py", "test_gpu_rsp.py",
+                            "test_gpu_norm_opt.py", "test_gpu_compression.py", "test_gpu_updater.py"])
+    assert _passed(out) >= 100, out[-500:]
+
+
+@pytest.mark.parametrize("devices", [2, 4, 8])
+def test_single_process_multi_gpu_paths(sim_lib, devices):
+    """one-shot and two-shot (sharded) exchange, sharded optimizer state, layer-wise optimizers with norms added
+    across the shards, compression, the updater callback -- over 2, 4 and 8 simulated GPUs."""
+    out = _run(sim_lib, devices, ["test_gpu_multi.py", "test_gpu_compression.py", "test_gpu_rsp.py"],
+               extra=["-k", "not one_process_per_gpu"])
+    assert _passed(out) >= 30, out[-500:]

@@ -23,7 +23,7 @@ def build(verbose=False):
     os.makedirs(OUT, exist_ok=True)
     fake = os.path.join(OUT, "libcudart.so.12")
     srcs = [os.path.join(HERE, f) for f in ("fake_cudart.cc", "sim_kernels.cc", "sim_rsp.cc")]
-    cmd = ["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-Wall",
+    cmd = ["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-Wall", "-Wno-unknown-pragmas",
            "-I", os.path.join(PKG, "csrc"), "-I", os.path.join(CUDA, "include"), "-I", HERE] + srcs + \
           ["-o", fake, "-Wl,-soname,libcudart.so.12", "-Wl,--version-script=" + os.path.join(HERE, "cudart.map")]
     if verbose:

@@ -30,7 +30,7 @@ def host(tmp_path_factory):
     if not os.path.exists(os.path.join(cuda_inc, "cuda_runtime.h")):
         pytest.skip("CUDA headers not installed")
     so = str(tmp_path_factory.mktemp("optim_host") / "liboptim_host.so")
-    subprocess.run([gxx, "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-Wall", "-Werror",
+    subprocess.run([gxx, "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-Wall", "-Werror", "-Wno-unknown-pragmas",
                     "-I", os.path.join(ROOT, "incubator-mxnet_b200", "csrc"), "-I", cuda_inc,
                     os.path.join(ROOT, "tests", "c", "optim_host.cc"), "-o", so], check=True, capture_output=True)
     return ctypes.CDLL(so)

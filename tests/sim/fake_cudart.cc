@@ -80,6 +80,8 @@ API cudaError_t cudaLaunchKernel(const void* func, dim3 grid, dim3 block, void**
     if (it == g_kernels.end()) return fail(cudaErrorInvalidDeviceFunction);
     name = it->second;
   }
+  static const bool noexec = getenv("MXKV_SIM_NOEXEC") != nullptr;   // host-overhead measurements: launch = no-op
+  if (noexec) return cudaSuccess;
   sim::LaunchInfo info;
   info.name = name;
   info.grid = grid.x; info.block = block.x; info.smem = smem;

@@ -327,9 +327,11 @@ Replica& KVStore::EnsureReplica(KeyState& ks, int dev) {
   if (!ks.reps.empty()) {
     if (ks.local_world > 0) GatherLocal(ks);
     if (ks.has_state) GatherState(ks);   // make every existing replica's optimizer state complete
-    Replica& src = FreshReplica(ks);
-    CopyFromTo(src.local, nr.local);
+    CopyFromTo(FreshReplica(ks).local, nr.local);
     // a GPU joining later (e.g. states were loaded before the first multi-GPU push) inherits the state
+    Replica* holder = nullptr;
+    for (auto& cand : ks.reps) if (cand.state_fresh) { holder = &cand; break; }
+    Replica& src = holder ? *holder : FreshReplica(ks);
     const Context nctx{kGPU, dev};
     const bool sym = PG() != nullptr;
     if (!src.w32.is_none()) { nr.w32 = NDArray::Empty(ks.shape, nctx, kFloat32, sym); CopyFromTo(src.w32, nr.w32); }
@@ -344,6 +346,21 @@ Replica& KVStore::EnsureReplica(KeyState& ks, int dev) {
   }
   ks.reps.push_back(nr);
   return ks.reps.back();
+}
+
+// Bring the optimizer state of a replica up to date from a replica whose state is (replicated layout only;
+// a sharded layout is made complete everywhere by GatherState first).
+void KVStore::SyncState(KeyState& ks, Replica& r) {
+  if (r.state_fresh) return;
+  for (auto& s : ks.reps) {
+    if (&s == &r || !s.state_fresh) continue;
+    if (!s.w32.is_none() && !r.w32.is_none()) CopyFromTo(s.w32, r.w32);
+    if (!s.s0.is_none() && !r.s0.is_none()) CopyFromTo(s.s0, r.s0);
+    if (!s.s1.is_none() && !r.s1.is_none()) CopyFromTo(s.s1, r.s1);
+    r.state_fresh = true;
+    return;
+  }
+  r.state_fresh = true;     // nobody holds newer state (first use)
 }
 
 void KVStore::EnsureState(KeyState& ks, Replica& r, bool mp) {
@@ -748,7 +765,11 @@ bool KVStore::HostPipelined(std::vector<Group>& groups, bool write_outs) {
       ks.count += 1;
     }
     r = FindReplica(ks, dev);
-    for (auto& o : ks.reps) o.fresh = (&o == r);
+    if (fused) SyncState(ks, *r);
+    for (auto& o : ks.reps) {
+      o.fresh = (&o == r);
+      if (fused && &o != r) o.state_fresh = false;
+    }
     const float lr = fused ? KeyLR(ks) : 0.f;
     const float wd = fused ? KeyWD(ks) : 0.f;
     const int n_src = static_cast<int>(g.vals.size());
@@ -1092,10 +1113,23 @@ void KVStore::ReduceUpdate(std::vector<Group>& groups, bool write_outs) {
       for (int p = my_first; p <= my_last; ++p) rep[p] = &EnsureReplica(ks, part_dev[p]);
       for (int p = my_first; p <= my_last; ++p) rep[p] = FindReplica(ks, part_dev[p]);
     }
-    if (fused && collective) {
-      const int want = two_shot ? n_part : 0;
-      if (ks.count > 0 && ks.state_world != want) GatherState(ks);
+    if (fused) {
+      // the optimizer state is laid out for this call's shape: sharded over the n participants of a
+      // two-shot push, complete on every replica otherwise (also when a key that used to be sharded is
+      // now pushed from one GPU only)
+      const int want = (collective && two_shot) ? n_part : 0;
+      const bool same = ks.state_world == want && (want == 0 || ks.state_devs == part_dev);
+      if (ks.count > 0 && !same) GatherState(ks);
       ks.state_world = want;
+      if (want > 0) ks.state_devs = part_dev; else ks.state_devs.clear();
+      // a replica that sat out earlier updates (its GPU did not take part) first takes over the state of
+      // one that did; after this call only the participants' state is current
+      for (int p = my_first; p <= my_last; ++p) SyncState(ks, *rep[p]);
+      for (auto& r : ks.reps) {
+        bool part = false;
+        for (int p = my_first; p <= my_last; ++p) part = part || (&r == rep[p]);
+        if (!part) r.state_fresh = false;
+      }
     }
 
     // ---- sources as addressable pointers ----------------------------------
@@ -1264,7 +1298,10 @@ void KVStore::ReduceUpdate(std::vector<Group>& groups, bool write_outs) {
             if (oc.is_gpu()) touch(oc.dev_id);
             PostCopy pc;
             pc.dst = *o;
-            const int sdev = (oc.is_gpu() && FindReplica(ks, oc.dev_id)) ? oc.dev_id : part_dev[my_first];
+            // copy out of a replica this call has just written: a replica on the output's own GPU only if
+            // that GPU took part (a replica left over from an earlier device set is stale now)
+            Replica* near = oc.is_gpu() ? FindReplica(ks, oc.dev_id) : nullptr;
+            const int sdev = (near != nullptr && near->fresh) ? oc.dev_id : part_dev[my_first];
             pc.src = FindReplica(ks, sdev)->local;
             post.push_back(pc);
           }
@@ -1584,10 +1621,13 @@ void KVStore::GatherState(KeyState& ks) {
       }
       rt->WaitAll(); pg->Barrier();
     } else {
+      MXKV_CHECK(static_cast<int>(ks.state_devs.size()) == n) << "inconsistent state layout for key " << ks.key;
       for (size_t q = 0; q < ks.reps.size(); ++q) {
-        for (int p = 0; p < n && p < static_cast<int>(ks.reps.size()); ++p) {
-          if (static_cast<int>(q) == p) continue;
-          NDArray& src = sel(ks.reps[p]);
+        for (int p = 0; p < n; ++p) {
+          Replica* owner = FindReplica(ks, ks.state_devs[p]);      // shard p lives on participant p's GPU
+          MXKV_CHECK(owner != nullptr) << "state shard " << p << " of key " << ks.key << " has no replica";
+          if (owner == &ks.reps[q]) continue;
+          NDArray& src = sel(*owner);
           NDArray& dst = sel(ks.reps[q]);
           if (src.is_none() || dst.is_none()) continue;
           const int64_t b = std::min(ks.size, shard * p), e = std::min(ks.size, shard * (p + 1));
@@ -1601,6 +1641,8 @@ void KVStore::GatherState(KeyState& ks) {
   gather([](Replica& r) -> NDArray& { return r.s0; });
   gather([](Replica& r) -> NDArray& { return r.s1; });
   ks.state_world = 0;
+  ks.state_devs.clear();
+  for (auto& r : ks.reps) r.state_fresh = true;      // every replica now holds every shard
 }
 
 // Updater.__call__ (python/mxnet/optimizer/updater.py:39-93) + the multi-tensor update operators it

@@ -58,6 +58,7 @@ struct Replica {
   NDArray aux0, aux1;  // LAMB/LANS/LARS: fp32 temporaries between the phases (update direction / merged gradient)
   NDArray nrm;         // LAMB/LANS/LARS: this replica's per-key sums of squares (peer-visible)
   bool fresh = true;
+  bool state_fresh = true;   // optimizer state (w32/s0/s1) reflects every update so far
   // row_sparse keys: `local` is the dense-backed table [num_rows x row_len]
   NDArray rsp_merged;            // union ids + summed rows of the last push (capacity n * rsp_cap rows)
   NDArray rsp_first, rsp_pf;     // int32 workspaces of the union kernels
@@ -78,6 +79,7 @@ struct KeyState {
   int state_world = 0;           // number of shards the optimizer state is laid out for (0: replicated/none)
   int local_world = 0;           // > 0: the stored value is valid shard-wise only (shard p on shard_devs[p])
   std::vector<int> shard_devs;   // devices (SP) / placeholder per rank (MP) of the shard owners
+  std::vector<int> state_devs;   // the same for the optimizer-state shards (state_world entries)
   bool has_state = false;
   // gradient compression: per pushed-value slot, error-feedback residual and the code stream
   std::vector<NDArray> gc_residual, gc_packed;
@@ -194,6 +196,7 @@ class KVStore {
   Replica* FindReplica(KeyState& ks, int dev);
   Replica& FreshReplica(KeyState& ks);
   void EnsureState(KeyState& ks, Replica& r, bool mp);
+  void SyncState(KeyState& ks, Replica& r);
   void GatherState(KeyState& ks);
   int DefaultDevice();
   double KeyLRd(const KeyState& ks) const;

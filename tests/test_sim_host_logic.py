@@ -54,6 +54,7 @@ def test_single_gpu_paths(sim_lib):
 def test_single_process_multi_gpu_paths(sim_lib, devices):
     """one-shot and two-shot (sharded) exchange, sharded optimizer state, layer-wise optimizers with norms added
     across the shards, compression, the updater callback -- over 2, 4 and 8 simulated GPUs."""
-    out = _run(sim_lib, devices, ["test_gpu_multi.py", "test_gpu_compression.py", "test_gpu_rsp.py"],
+    out = _run(sim_lib, devices, ["test_gpu_multi.py", "test_gpu_compression.py", "test_gpu_rsp.py",
+                                  "test_gpu_placement.py"],
                extra=["-k", "not one_process_per_gpu"])
     assert _passed(out) >= 30, out[-500:]

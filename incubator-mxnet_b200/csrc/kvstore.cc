@@ -865,11 +865,19 @@ void KVStore::ReduceUpdateCompressed(std::vector<Group>& groups, bool write_outs
       const int dev = mp_mode ? pg->dev() : (c.is_gpu() ? c.dev_id : (ks.reps.empty() ? DefaultDevice() : ks.reps[0].dev));
       src_dev[k] = dev;
       touch(dev);
-      if (ks.gc_residual[k].is_none() || ks.gc_residual[k].dev() != dev) {
+      if (ks.gc_residual[k].is_none()) {
         ks.gc_residual[k] = NDArray::Empty(ks.shape, Context{kGPU, dev}, kFloat32);
         ks.gc_packed[k] = NDArray::Empty({nwords}, Context{kGPU, dev}, kInt32, mp_mode);
         DeviceGuard dg(dev);
         CUDA_CALL(cudaMemsetAsync(ks.gc_residual[k].data(), 0, ks.gc_residual[k].nbytes(), rt->Dev(dev).stream));
+      } else if (ks.gc_residual[k].dev() != dev) {
+        // value slot k is now pushed from another GPU: its error feedback moves along (the reference
+        // allocates the residuals on the contexts of the first push and has no answer for a later change)
+        touch(ks.gc_residual[k].dev());
+        NDArray moved = NDArray::Empty(ks.shape, Context{kGPU, dev}, kFloat32);
+        CopyFromTo(ks.gc_residual[k], moved);
+        ks.gc_residual[k] = moved;
+        ks.gc_packed[k] = NDArray::Empty({nwords}, Context{kGPU, dev}, kInt32, mp_mode);
       }
       DeviceGuard dg(dev);
       cudaStream_t s = rt->Dev(dev).stream;

@@ -172,3 +172,158 @@ def test_many_keys_many_gpus_layerwise_and_plain_mixed_dtypes():
             hb = obf[k][0].asnumpy(raw=True)
             for o in obf[k][1:]:
                 assert np.array_equal(o.asnumpy(raw=True), hb)
+
+
+def test_row_sparse_device_set_changes():
+    """row_sparse push from GPUs 0 and 1, then from GPU 2 alone, then from the host; pulls to every device"""
+    _need(3)
+    rows, L, nnz = 500, 8, 60
+    rng = _rng(6)
+    shape = (rows, L)
+    w0 = rng.uniform(0, 1, shape).astype(np.float32)
+    kw = dict(learning_rate=0.1, momentum=0.9, wd=1e-3, lazy_update=True)
+    kv = mx.kv.create("device")
+    kv.init("e", mx.nd.row_sparse_array(w0, ctx=mx.gpu(0)))
+    kv.set_optimizer(mx.optimizer.SGD(**kw))
+    okv = O.OracleKVStore("device"); okv.init("e", O.RowSparse.from_dense(w0))
+    okv.set_optimizer(O.OracleOptimizer("sgd", **kw))
+
+    def rsp():
+        idx = np.sort(rng.choice(rows, nnz, replace=False)).astype(np.int64)
+        return idx, rng.uniform(-1, 1, (nnz, L)).astype(np.float32)
+
+    for ctxs in ([mx.gpu(0), mx.gpu(1)], [mx.gpu(2)], [mx.cpu()], [mx.gpu(1), mx.gpu(2), mx.gpu(0)]):
+        parts = [rsp() for _ in ctxs]
+        kv.push("e", [mx.nd.row_sparse_array((v, i), shape=shape, ctx=c) for (i, v), c in zip(parts, ctxs)])
+        okv.push("e", [O.RowSparse(i, v, shape) for i, v in parts])
+        ids = rng.integers(0, rows, 100).astype(np.int64)
+        want = O.sparse_retain(okv.local["e"], O.unique(ids))
+        for c in (mx.gpu(0), mx.gpu(2), mx.cpu()):
+            out = mx.nd.zeros(shape, c, stype="row_sparse")
+            kv.row_sparse_pull("e", out=out, row_ids=mx.nd.array(ids, c, dtype=np.int64))
+            assert np.array_equal(out.indices.asnumpy(), want.indices), (ctxs, c)
+            assert _bits_equal(out.data.asnumpy(), want.data.reshape(-1, L)), (ctxs, c)
+        dense = mx.nd.empty(shape, mx.gpu(1))
+        kv.pull("e", out=dense, ignore_sparse=False)
+        assert _bits_equal(dense.asnumpy(), okv.local["e"].todense())
+
+
+def test_updater_callback_with_changing_devices():
+    """test_kvstore.py:222-274 generalised: the Python updater sees the merged value on whatever GPU reduced"""
+    _need(3)
+    shape = (6, 5)
+    kv = mx.kv.create("device")
+    kv.init(9, mx.nd.zeros(shape, mx.gpu(1)))
+    calls = []
+
+    def updater(key, recv, local):
+        calls.append((key, recv.context.device_id, local.context.device_id))
+        local += recv
+    kv._set_updater(updater)
+    total = 0
+    for devs in ([0, 1, 2], [2], [1, 0]):
+        kv.push(9, [mx.nd.ones(shape, mx.gpu(d)) * (d + 1) for d in devs])
+        total += sum(d + 1 for d in devs)
+        for d in (0, 1, 2):
+            o = mx.nd.empty(shape, mx.gpu(d))
+            kv.pull(9, out=o)
+            assert np.all(o.asnumpy() == total), (devs, d)
+    assert len(calls) == 3 and all(c[0] == 9 for c in calls)
+
+
+def test_compression_with_changing_devices():
+    _need(3)
+    E, thr = 9000, 0.5
+    rng = _rng(8)
+    kv = mx.kv.create("device")
+    kv.set_gradient_compression({"type": "2bit", "threshold": thr})
+    kv.init(0, mx.nd.zeros((E,), mx.gpu(0)))
+    residual = {}
+    for devs in ([0, 1], [0, 1, 2], [1]):
+        g = [rng.uniform(-1, 1, E).astype(np.float32) for _ in devs]
+        outs = [mx.nd.empty((E,), mx.gpu(d)) for d in (0, 1, 2)]
+        kv.pushpull(0, [mx.nd.array(x, mx.gpu(d)) for x, d in zip(g, devs)], out=outs)
+        # residuals are kept per pushed-value slot (comm.h:575-580), not per device
+        deq = []
+        for slot, x in enumerate(g):
+            r = residual.setdefault(slot, np.zeros(E, np.float32))
+            deq.append(O.dequantize_2bit(O.quantize_2bit(x, r, thr), E, thr))
+        want = O.sum_device(deq)
+        for o in outs:
+            assert _bits_equal(o.asnumpy(), want), devs
+
+
+def test_checkpoint_after_device_set_change(tmp_path):
+    """optimizer states saved while sharded over 4 GPUs, loaded into a store that then runs on 2"""
+    _need(4)
+    E = 300007
+    rng = _rng(9)
+    w0 = rng.uniform(0, 1, E).astype(np.float32)
+    kw = dict(learning_rate=0.01, wd=1e-3)
+    grads = [[rng.uniform(-1, 1, E).astype(np.float32) for _ in range(4)] for _ in range(4)]
+    okv = O.OracleKVStore("device"); okv.init(0, w0.copy()); okv.set_optimizer(O.OracleOptimizer("adam", **kw))
+    kv = mx.kv.create("device")
+    kv.init(0, mx.nd.array(w0, mx.gpu(0)))
+    kv.set_optimizer(mx.optimizer.Adam(**kw))
+    for g in grads[:2]:
+        kv.push(0, [mx.nd.array(x, mx.gpu(d)) for d, x in enumerate(g)])
+        okv.push(0, g)
+    f = str(tmp_path / "adam.states")
+    kv.save_optimizer_states(f)
+    mid = mx.nd.empty((E,), mx.gpu(0)); kv.pull(0, out=mid)
+    kv2 = mx.kv.create("device")
+    kv2.init(0, mx.nd.array(mid.asnumpy(), mx.gpu(1)))
+    kv2.set_optimizer(mx.optimizer.Adam(**kw))
+    kv2.load_optimizer_states(f)
+    for g in grads[2:]:
+        kv2.push(0, [mx.nd.array(g[0] + g[1], mx.gpu(1)), mx.nd.array(g[2] + g[3], mx.gpu(3))])
+        okv.push(0, [g[0] + g[1], g[2] + g[3]])
+    out = mx.nd.empty((E,), mx.gpu(2)); kv2.pull(0, out=out)
+    want = np.empty(E, np.float32); okv.pull(0, want)
+    assert _bits_equal(out.asnumpy(), want)
+
+
+def test_call_level_rules():
+    """error rules of one call: different device sets for different keys, too many values, duplicate keys"""
+    _need(2)
+    kv = mx.kv.create("device")
+    kv.init([0, 1], [mx.nd.zeros((8,), mx.gpu(0))] * 2)
+    with pytest.raises(mx.MXNetError):       # key 0 from GPUs {0,1}, key 1 from GPU {0}
+        kv.push([0, 1], [[mx.nd.ones((8,), mx.gpu(0)), mx.nd.ones((8,), mx.gpu(1))], [mx.nd.ones((8,), mx.gpu(0))]])
+    with pytest.raises(mx.MXNetError):       # more values than one launch addresses
+        kv.push(0, [mx.nd.ones((8,), mx.gpu(0))] * 17)
+    # the same key twice in one list: the values are summed (GroupKVPairs, kvstore_local.h:440-469)
+    kv2 = mx.kv.create("device")
+    kv2.init(3, mx.nd.zeros((8,), mx.gpu(0)))
+    kv2.push([3, 3, 3], [mx.nd.ones((8,), mx.gpu(0)) * 2, mx.nd.ones((8,), mx.gpu(1)), mx.nd.ones((8,), mx.gpu(0))])
+    o = mx.nd.empty((8,), mx.gpu(1)); kv2.pull(3, out=o)
+    assert np.all(o.asnumpy() == 4)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.int32, np.int64, np.uint8, np.float16])
+def test_other_dtypes_across_gpus(dtype):
+    """ElementwiseSum accepts every MSHADOW_TYPE_SWITCH type (ndarray_function-inl.h:443-489); fp16 rounds every
+    add to half like mshadow's half_t"""
+    _need(2)
+    devs = list(range(min(mx.num_gpus(), 4)))
+    E = 70001
+    rng = _rng(10)
+    if np.issubdtype(dtype, np.floating):
+        vals = [rng.uniform(-1, 1, E).astype(dtype) for _ in devs]
+    else:
+        vals = [rng.integers(0, 50, E).astype(dtype) for _ in devs]
+    kv = mx.kv.create("device")
+    kv.init(0, mx.nd.array(np.zeros(E, dtype), mx.gpu(0), dtype=dtype))
+    outs = [mx.nd.empty((E,), mx.gpu(d), dtype=dtype) for d in devs]
+    kv.pushpull(0, [mx.nd.array(v, mx.gpu(d), dtype=dtype) for v, d in zip(vals, devs)], out=outs)
+    if dtype == np.float16:
+        acc = vals[0].copy()
+        for v in vals[1:]:
+            acc = (acc.astype(np.float32) + v.astype(np.float32)).astype(np.float16)
+        want = acc
+    else:
+        want = vals[0].copy()
+        for v in vals[1:]:
+            want = (want + v).astype(dtype)
+    for o in outs:
+        assert np.array_equal(o.asnumpy(), want)

@@ -297,6 +297,8 @@ int KVStore::DefaultDevice() {
   return 0;
 }
 
+static bool HoldsState(const Replica& r) { return !(r.w32.is_none() && r.s0.is_none() && r.s1.is_none()); }
+
 Replica* KVStore::FindReplica(KeyState& ks, int dev) {
   for (auto& r : ks.reps) if (r.dev == dev) return &r;
   return nullptr;
@@ -330,7 +332,7 @@ Replica& KVStore::EnsureReplica(KeyState& ks, int dev) {
     CopyFromTo(FreshReplica(ks).local, nr.local);
     // a GPU joining later (e.g. states were loaded before the first multi-GPU push) inherits the state
     Replica* holder = nullptr;
-    for (auto& cand : ks.reps) if (cand.state_fresh) { holder = &cand; break; }
+    for (auto& cand : ks.reps) if (cand.state_fresh && HoldsState(cand)) { holder = &cand; break; }
     Replica& src = holder ? *holder : FreshReplica(ks);
     const Context nctx{kGPU, dev};
     const bool sym = PG() != nullptr;
@@ -353,7 +355,7 @@ Replica& KVStore::EnsureReplica(KeyState& ks, int dev) {
 void KVStore::SyncState(KeyState& ks, Replica& r) {
   if (r.state_fresh) return;
   for (auto& s : ks.reps) {
-    if (&s == &r || !s.state_fresh) continue;
+    if (&s == &r || !s.state_fresh || !HoldsState(s)) continue;
     if (!s.w32.is_none() && !r.w32.is_none()) CopyFromTo(s.w32, r.w32);
     if (!s.s0.is_none() && !r.s0.is_none()) CopyFromTo(s.s0, r.s0);
     if (!s.s1.is_none() && !r.s1.is_none()) CopyFromTo(s.s1, r.s1);
@@ -383,7 +385,9 @@ void KVStore::EnsureState(KeyState& ks, Replica& r, bool mp) {
       CUDA_CALL(cudaMemsetAsync(r.nrm.data(), 0, r.nrm.nbytes(), s));
     }
   }
+  bool created = false;
   if (mp && r.w32.is_none()) {
+    created = true;
     r.w32 = NDArray::Empty(ks.shape, ctx, kFloat32, sym);
     // create_state_multi_precision: weight_master_copy = weight.astype(float32) (optimizer.py:341-352)
     MXKV_CHECK(ks.dtype == kFloat32 || ks.dtype == kFloat16 || ks.dtype == kBfloat16)
@@ -393,13 +397,19 @@ void KVStore::EnsureState(KeyState& ks, Replica& r, bool mp) {
     rt->launches++;
   }
   if (need_s0 && r.s0.is_none()) {
+    created = true;
     r.s0 = NDArray::Empty(ks.shape, ctx, kFloat32, sym);
     CUDA_CALL(cudaMemsetAsync(r.s0.data(), 0, r.s0.nbytes(), s));
   }
   if (need_s1 && r.s1.is_none()) {
+    created = true;
     r.s1 = NDArray::Empty(ks.shape, ctx, kFloat32, sym);
     CUDA_CALL(cudaMemsetAsync(r.s1.data(), 0, r.s1.nbytes(), s));
   }
+  // state arrays that come into being after updates have already happened elsewhere start out stale:
+  // SyncState fills them from a replica that took part (zeros / a cast of the weight are only right for
+  // the very first update)
+  if (created && ks.count > 0 && ks.reps.size() > 1) r.state_fresh = false;
   ks.has_state = true;
 }
 
@@ -1008,6 +1018,55 @@ void KVStore::ReduceUpdateCompressed(std::vector<Group>& groups, bool write_outs
   for (int dev : touched) rt->ReleaseToUser(dev);
 }
 
+// Where a key of a call is reduced: collectively on the GPUs its values live on (distinct,
+// P2P-reachable GPUs, single process), by every rank (one process per GPU), or on one root GPU that reads
+// and writes wherever the arrays are.
+void KVStore::PlaceKey(const Group& g, KeyState& ks, std::vector<int>* devs_out, std::vector<int>* key_part_out,
+                       bool* key_collective_out) {
+  Runtime* rt = Runtime::Get();
+  ProcessGroup* pg = PG();
+  const bool mp_mode = pg != nullptr;
+  const int n_src = static_cast<int>(g.vals.size());
+  std::vector<int>& devs = *devs_out;
+  std::vector<int>& key_part = *key_part_out;
+  bool key_collective = false;
+  devs.clear();
+  key_part.clear();
+  for (auto& v : g.vals) devs.push_back(v.ctx().is_gpu() ? v.ctx().dev_id : -1);
+  if (mp_mode) {
+    MXKV_CHECK(n_src == 1) << "one-process-per-GPU mode: push exactly one value per key per rank";
+    MXKV_CHECK(devs[0] < 0 || devs[0] == pg->dev()) << "value must live on GPU " << pg->dev() << " or on the host";
+    key_part.assign(pg->world(), pg->dev());
+    key_collective = pg->world() > 1;
+  } else {
+    bool all_gpu = true, distinct = true;
+    std::set<int> seen;
+    for (int d : devs) {
+      if (d < 0) { all_gpu = false; continue; }
+      if (!seen.insert(d).second) distinct = false;
+    }
+    if (all_gpu && distinct && n_src >= 2 && n_src <= kMaxRanks) {
+      rt->EnablePeerAccess(devs);
+      bool p2p = true;
+      for (int a : devs) for (int b : devs) if (!rt->PeerOK(a, b)) p2p = false;
+      key_collective = p2p;
+    }
+    if (key_collective) {
+      key_part = devs;
+    } else {
+      int rd = -1;
+      for (int d : devs) if (d >= 0) { rd = d; break; }
+      if (rd < 0) {
+        for (NDArray* o : g.outs) if (o->ctx().is_gpu()) { rd = o->ctx().dev_id; break; }
+      }
+      if (rd < 0 && !ks.reps.empty()) rd = ks.reps[0].dev;
+      if (rd < 0) rd = DefaultDevice();
+      key_part.assign(1, rd);
+    }
+  }
+  *key_collective_out = key_collective;
+}
+
 void KVStore::ReduceUpdate(std::vector<Group>& groups, bool write_outs) {
   // an overflow of the previous step is settled before this step's update counts are taken
   if (opt_.enabled && updater_ == nullptr && opt_.skip_nonfinite) ResolveOverflow();
@@ -1018,6 +1077,42 @@ void KVStore::ReduceUpdate(std::vector<Group>& groups, bool write_outs) {
   const bool mp_mode = pg != nullptr;
   const bool callback = updater_ != nullptr;
   const bool fused = opt_.enabled && !callback;
+
+  // Keys of one call that reduce on different GPUs (e.g. host-resident values for keys whose stored
+  // values live on different GPUs) are served group by group; the reference has no such restriction
+  // because every key has its own merge buffer.  Reduce first, copy out afterwards: the order of
+  // kvstore_local.h:358-365, which also keeps values that alias another key's outputs intact.
+  if (!mp_mode && groups.size() > 1) {
+    std::vector<std::pair<std::vector<int>, bool>> sig(groups.size());
+    bool uniform = true;
+    for (size_t gi = 0; gi < groups.size(); ++gi) {
+      std::vector<int> devs;
+      PlaceKey(groups[gi], GetKey(groups[gi].key), &devs, &sig[gi].first, &sig[gi].second);
+      if (sig[gi] != sig[0]) uniform = false;
+    }
+    if (!uniform) {
+      std::vector<char> done(groups.size(), 0);
+      for (size_t gi = 0; gi < groups.size(); ++gi) {
+        if (done[gi]) continue;
+        std::vector<Group> bucket;
+        for (size_t gj = gi; gj < groups.size(); ++gj) {
+          if (done[gj] || sig[gj] != sig[gi]) continue;
+          done[gj] = 1;
+          Group c = groups[gj];
+          c.outs.clear();
+          bucket.push_back(c);
+        }
+        ReduceUpdate(bucket, false);
+      }
+      if (write_outs) {
+        std::vector<int> okeys;
+        std::vector<NDArray*> outs;
+        for (auto& g : groups) for (NDArray* o : g.outs) { okeys.push_back(g.key); outs.push_back(o); }
+        if (!outs.empty()) PullImpl(okeys, outs, 0, true);
+      }
+      return;
+    }
+  }
 
   // participant slot -> device; SP: discovered from the first key, MP: this rank only is local
   struct LaunchClass {
@@ -1054,40 +1149,9 @@ void KVStore::ReduceUpdate(std::vector<Group>& groups, bool write_outs) {
 
     // ---- placement ------------------------------------------------------
     std::vector<int> devs;        // per source; -1 = host
-    for (auto& v : g.vals) devs.push_back(v.ctx().is_gpu() ? v.ctx().dev_id : -1);
     std::vector<int> key_part;    // participant devices for this key
     bool key_collective = false;
-    if (mp_mode) {
-      MXKV_CHECK(n_src == 1) << "one-process-per-GPU mode: push exactly one value per key per rank";
-      MXKV_CHECK(devs[0] < 0 || devs[0] == pg->dev()) << "value must live on GPU " << pg->dev() << " or on the host";
-      key_part.assign(pg->world(), pg->dev());
-      key_collective = pg->world() > 1;
-    } else {
-      bool all_gpu = true, distinct = true;
-      std::set<int> seen;
-      for (int d : devs) {
-        if (d < 0) { all_gpu = false; continue; }
-        if (!seen.insert(d).second) distinct = false;
-      }
-      if (all_gpu && distinct && n_src >= 2 && n_src <= kMaxRanks) {
-        rt->EnablePeerAccess(devs);
-        bool p2p = true;
-        for (int a : devs) for (int b : devs) if (!rt->PeerOK(a, b)) p2p = false;
-        key_collective = p2p;
-      }
-      if (key_collective) {
-        key_part = devs;
-      } else {
-        int rd = -1;
-        for (int d : devs) if (d >= 0) { rd = d; break; }
-        if (rd < 0) {
-          for (NDArray* o : g.outs) if (o->ctx().is_gpu()) { rd = o->ctx().dev_id; break; }
-        }
-        if (rd < 0 && !ks.reps.empty()) rd = ks.reps[0].dev;
-        if (rd < 0) rd = DefaultDevice();
-        key_part.assign(1, rd);
-      }
-    }
+    PlaceKey(g, ks, &devs, &key_part, &key_collective);
     if (gi == 0) {
       part_dev = key_part; n_part = static_cast<int>(key_part.size()); collective = key_collective;
       root_dev = key_part[0];
@@ -1650,7 +1714,7 @@ void KVStore::GatherState(KeyState& ks) {
   gather([](Replica& r) -> NDArray& { return r.s1; });
   ks.state_world = 0;
   ks.state_devs.clear();
-  for (auto& r : ks.reps) r.state_fresh = true;      // every replica now holds every shard
+  for (auto& r : ks.reps) r.state_fresh = HoldsState(r);      // every replica with state arrays holds every shard
 }
 
 // Updater.__call__ (python/mxnet/optimizer/updater.py:39-93) + the multi-tensor update operators it

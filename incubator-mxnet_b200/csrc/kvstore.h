@@ -171,6 +171,7 @@ class KVStore {
   };
   // the fused reduce(+update)(+broadcast) over a list of dense key groups
   void ReduceUpdate(std::vector<Group>& groups, bool write_outs);
+  void PlaceKey(const Group& g, KeyState& ks, std::vector<int>* devs, std::vector<int>* key_part, bool* key_collective);
   // busiest[i]: number of elements the busiest rank processes for entry i (fixes the common grid)
   void LaunchWorks(const LaunchClassKey& ck, std::vector<std::vector<TensorWork>>& per_part,
                    const std::vector<int64_t>& busiest, int opt_kind, const std::vector<int>& part_dev);

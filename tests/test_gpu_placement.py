@@ -284,12 +284,16 @@ def test_checkpoint_after_device_set_change(tmp_path):
 
 
 def test_call_level_rules():
-    """error rules of one call: different device sets for different keys, too many values, duplicate keys"""
+    """rules of one call: different device sets for different keys, too many values, duplicate keys"""
     _need(2)
     kv = mx.kv.create("device")
     kv.init([0, 1], [mx.nd.zeros((8,), mx.gpu(0))] * 2)
-    with pytest.raises(mx.MXNetError):       # key 0 from GPUs {0,1}, key 1 from GPU {0}
-        kv.push([0, 1], [[mx.nd.ones((8,), mx.gpu(0)), mx.nd.ones((8,), mx.gpu(1))], [mx.nd.ones((8,), mx.gpu(0))]])
+    # key 0 from GPUs {0,1}, key 1 from GPU {0}: different reduction sites in one call are served one group
+    # after the other (every key has its own merge buffer in the reference, so it accepts this too)
+    outs = [mx.nd.empty((8,), mx.gpu(1)), mx.nd.empty((8,), mx.gpu(0))]
+    kv.pushpull([0, 1], [[mx.nd.ones((8,), mx.gpu(0)), mx.nd.ones((8,), mx.gpu(1)) * 2], [mx.nd.ones((8,), mx.gpu(0)) * 5]],
+                out=outs)
+    assert np.all(outs[0].asnumpy() == 3) and np.all(outs[1].asnumpy() == 5)
     with pytest.raises(mx.MXNetError):       # more values than one launch addresses
         kv.push(0, [mx.nd.ones((8,), mx.gpu(0))] * 17)
     # the same key twice in one list: the values are summed (GroupKVPairs, kvstore_local.h:440-469)
@@ -327,3 +331,118 @@ def test_other_dtypes_across_gpus(dtype):
             want = (want + v).astype(dtype)
     for o in outs:
         assert np.array_equal(o.asnumpy(), want)
+
+
+@pytest.mark.parametrize("optname,kw", [
+    (None, {}),
+    ("sgd", dict(learning_rate=0.1, momentum=0.9, wd=1e-4)),
+    ("adam", dict(learning_rate=0.01, wd=1e-3)),
+    ("lamb", dict(learning_rate=0.01, wd=0.01)),
+])
+def test_host_resident_key_lists(optname, kw, monkeypatch):
+    """kv.create('local')-style use with whole key lists in host memory: small and large keys mixed (the large
+    ones go through the segmented H2D / kernel / D2H pipeline), in place and out of place, several steps"""
+    monkeypatch.setenv("MXKV_B200_HOST_SEG_ELEMS", str(1 << 16))
+    shapes = [(7,), (300, 1000), (64,), ((1 << 18) + 37,), (5, 5)]
+    keys = ["k%d" % i for i in range(len(shapes))]
+    n = 3
+    rng = _rng(11)
+    w0 = [rng.uniform(-1, 1, s).astype(np.float32) for s in shapes]
+    kv = mx.kv.create("local")
+    kv.init(keys, [mx.nd.array(w) for w in w0])
+    okv = O.OracleKVStore("local"); okv.init(keys, [w.copy() for w in w0])
+    oopt = None
+    if optname:
+        kv.set_optimizer(mx.optimizer.create(optname, **kw))
+        oopt = O.OracleOptimizer(optname, **(dict(kw, norm_mode="f64") if optname == "lamb" else kw))
+        okv.set_optimizer(oopt)
+    outs = [mx.nd.empty(s, mx.cpu_pinned()) for s in shapes]
+    for step in range(3):
+        grads = [[rng.uniform(-1, 1, s).astype(np.float32) for _ in range(n)] for s in shapes]
+        vals = [[mx.nd.array(g, mx.cpu_pinned() if (step + j) % 2 else mx.cpu()) for j, g in enumerate(gs)]
+                for gs in grads]
+        if step == 1 and optname is None:
+            kv.pushpull(keys, vals)                      # in place: every value array receives the sum
+            okv.push(keys, grads)
+            for k, vs in enumerate(vals):
+                want = np.empty(shapes[k], np.float32); okv.pull(keys[k], want)
+                for v in vs:
+                    assert _bits_equal(v.asnumpy(), want), (step, k)
+            continue
+        kv.pushpull(keys, vals, out=outs)
+        okv.push(keys, grads)
+        for k in range(len(shapes)):
+            want = np.empty(shapes[k], np.float32); okv.pull(keys[k], want)
+            if optname == "lamb":
+                np.testing.assert_allclose(outs[k].asnumpy(), want, rtol=2e-6, atol=2e-7)
+            else:
+                assert _bits_equal(outs[k].asnumpy(), want), (optname, step, k)
+
+
+@pytest.mark.parametrize("seed", list(range(12)))
+def test_randomized_call_sequences(seed):
+    """A random walk over the store's states: keys of one-shot and two-shot size, values pushed from random
+    subsets of the GPUs (or the host), pushes and fused pushpulls interleaved with pulls to random devices, a
+    fused optimizer that is switched on part-way -- compared with the oracle after every call."""
+    _need(2)
+    ngpu = min(mx.num_gpus(), 8)
+    rng = _rng(1000 + seed)
+    sizes = [int(x) for x in rng.choice([5, 640, 4099, 70001, 300007], size=3, replace=False)]
+    keys = list(range(len(sizes)))
+    w0 = [rng.uniform(-1, 1, e).astype(np.float32) for e in sizes]
+    kv = mx.kv.create("device")
+    okv = O.OracleKVStore("device")
+    kv.init(keys, [mx.nd.array(w, mx.gpu(int(rng.integers(ngpu)))) for w in w0])
+    okv.init(keys, [w.copy() for w in w0])
+    optname = [None, "sgd", "adam"][seed % 3]
+    kw = {"sgd": dict(learning_rate=0.05, momentum=0.9, wd=1e-3), "adam": dict(learning_rate=0.01, wd=1e-3)}.get(optname)
+    switch_at = int(rng.integers(0, 4))
+
+    def ctx_of(d):
+        return mx.cpu() if d < 0 else mx.gpu(d)
+
+    def check(ks):
+        for k in ks:
+            d = int(rng.integers(-1, ngpu))
+            o = mx.nd.empty((sizes[k],), ctx_of(d))
+            kv.pull(k, out=o)
+            want = np.empty(sizes[k], np.float32)
+            okv.pull(k, want)
+            assert _bits_equal(o.asnumpy(), want), ("pull", seed, k, d)
+
+    for step in range(10):
+        if optname and step == switch_at:
+            kv.set_optimizer(mx.optimizer.create(optname, **kw))
+            okv.set_optimizer(O.OracleOptimizer(optname, **kw))
+        nk = int(rng.integers(1, len(keys) + 1))
+        ks = sorted(int(x) for x in rng.choice(keys, size=nk, replace=False))
+        ndev = int(rng.integers(1, ngpu + 1))
+        devs = [int(x) for x in rng.choice(ngpu, size=ndev, replace=False)]
+        if rng.random() < 0.2:
+            devs = [-1] + devs[: max(0, len(devs) - 1)]          # one value from the host
+        grads = [[rng.uniform(-1, 1, sizes[k]).astype(np.float32) for _ in devs] for k in ks]
+        vals = [[mx.nd.array(g, ctx_of(d)) for g, d in zip(gs, devs)] for gs in grads]
+        mode = rng.choice(["push", "pushpull", "inplace"]) if optname is None or step < switch_at else \
+            rng.choice(["push", "pushpull"])
+        if mode == "push":
+            kv.push(ks, vals)
+            okv.push(ks, grads)
+        elif mode == "pushpull":
+            odevs = [int(x) for x in rng.choice(ngpu, size=int(rng.integers(1, ngpu + 1)), replace=False)]
+            outs = [[mx.nd.empty((sizes[k],), mx.gpu(d)) for d in odevs] for k in ks]
+            kv.pushpull(ks, vals, out=outs)
+            okv.push(ks, grads)
+            for k, oo in zip(ks, outs):
+                want = np.empty(sizes[k], np.float32)
+                okv.pull(k, want)
+                for o in oo:
+                    assert _bits_equal(o.asnumpy(), want), ("pushpull", seed, step, k)
+        else:
+            kv.pushpull(ks, vals)
+            okv.push(ks, grads)
+            for k, vs in zip(ks, vals):
+                want = np.empty(sizes[k], np.float32)
+                okv.pull(k, want)
+                for v in vs:
+                    assert _bits_equal(v.asnumpy(), want), ("inplace", seed, step, k)
+        check(ks)

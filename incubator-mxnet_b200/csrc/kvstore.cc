@@ -1794,9 +1794,12 @@ NDArray KVStore::GetState(bool str_key, int ikey, const std::string& skey, int w
   if (ks.reps.empty()) EnsureReplica(ks, DefaultDevice());
   if (ks.local_world > 0) GatherLocal(ks);
   GatherState(ks);
-  Replica& r = FreshReplica(ks);
+  if (which == 0) return FreshReplica(ks).local;
+  // optimizer state: from a replica that took part in the latest update (the others may lag behind)
+  Replica* holder = nullptr;
+  for (auto& cand : ks.reps) if (cand.state_fresh && HoldsState(cand)) { holder = &cand; break; }
+  Replica& r = holder ? *holder : FreshReplica(ks);
   switch (which) {
-    case 0: return r.local;
     case 1: return r.w32;
     case 2: return r.s0;
     case 3: return r.s1;

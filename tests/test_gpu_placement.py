@@ -446,3 +446,85 @@ def test_randomized_call_sequences(seed):
                 for v in vs:
                     assert _bits_equal(v.asnumpy(), want), ("inplace", seed, step, k)
         check(ks)
+
+
+_FUZZ_OPTS = [
+    (None, {}),
+    ("sgd", dict(learning_rate=0.05, wd=1e-3, rescale_grad=0.5)),
+    ("sgd", dict(learning_rate=0.05, momentum=0.9, wd=1e-3, clip_gradient=0.7)),
+    ("adam", dict(learning_rate=0.01, wd=1e-3)),
+    ("adamw", dict(learning_rate=0.01, wd=0.05)),
+    ("test", dict(learning_rate=0.1, wd=0.01, rescale_grad=0.5)),
+    ("lamb", dict(learning_rate=0.01, wd=0.01)),
+    ("lans", dict(learning_rate=0.01, wd=0.01)),
+    ("lars", dict(learning_rate=0.1, momentum=0.9, wd=1e-3, eta=0.01)),
+]
+
+
+@pytest.mark.parametrize("seed", list(range(27)))
+def test_randomized_optimizers_store_types_and_checkpoints(seed, tmp_path):
+    """Every fused optimizer x {'device', 'local'} association order, random device subsets per call, and a
+    save / load of the optimizer states into a fresh store in the middle of the run."""
+    _need(2)
+    ngpu = min(mx.num_gpus(), 8)
+    rng = _rng(5000 + seed)
+    optname, kw = _FUZZ_OPTS[seed % len(_FUZZ_OPTS)]
+    kvtype = ["device", "local", "device"][seed % 3]
+    layerwise = optname in ("lamb", "lans", "lars")
+    sizes = [int(x) for x in rng.choice([7, 640, 4099, 70001, 300007], size=3, replace=False)]
+    keys = ["p%d" % i for i in range(len(sizes))]
+    w0 = [rng.uniform(-1, 1, e).astype(np.float32) for e in sizes]
+
+    def make_store(weights):
+        s = mx.kv.create(kvtype)
+        s.init(keys, [mx.nd.array(w, mx.gpu(int(rng.integers(ngpu)))) for w in weights])
+        if optname:
+            s.set_optimizer(mx.optimizer.create(optname, **kw))
+        return s
+
+    kv = make_store(w0)
+    okv = O.OracleKVStore(kvtype)
+    okv.init(keys, [w.copy() for w in w0])
+    if optname:
+        okv.set_optimizer(O.OracleOptimizer(optname, **(dict(kw, norm_mode="f64") if layerwise else kw)))
+    reload_at = int(rng.integers(2, 6)) if optname else -1
+
+    def compare(got, want, what):
+        if layerwise:
+            np.testing.assert_allclose(got, want, rtol=5e-6, atol=5e-7, err_msg=str(what))
+        else:
+            assert _bits_equal(got, want), what
+
+    for step in range(8):
+        if step == reload_at:
+            f = str(tmp_path / ("states_%d" % seed))
+            kv.save_optimizer_states(f)
+            cur = []
+            for k, e in zip(keys, sizes):
+                o = mx.nd.empty((e,), mx.cpu())
+                kv.pull(k, out=o)
+                cur.append(o.asnumpy().copy())
+            kv = make_store(cur)
+            kv.load_optimizer_states(f)
+        nk = int(rng.integers(1, len(keys) + 1))
+        ks = sorted(rng.choice(len(keys), size=nk, replace=False).tolist())
+        devs = [int(x) for x in rng.choice(ngpu, size=int(rng.integers(1, ngpu + 1)), replace=False)]
+        grads = [[rng.uniform(-1, 1, sizes[k]).astype(np.float32) for _ in devs] for k in ks]
+        vals = [[mx.nd.array(g, mx.gpu(d)) for g, d in zip(gs, devs)] for gs in grads]
+        names = [keys[k] for k in ks]
+        if rng.random() < 0.5:
+            kv.push(names, vals)
+        else:
+            odevs = [int(x) for x in rng.choice(ngpu, size=int(rng.integers(1, 4)), replace=False)]
+            outs = [[mx.nd.empty((sizes[k],), mx.gpu(d)) for d in odevs] for k in ks]
+            kv.pushpull(names, vals, out=outs)
+        okv.push(names, grads)
+        for k in ks:
+            d = int(rng.integers(ngpu))
+            o = mx.nd.empty((sizes[k],), mx.gpu(d))
+            kv.pull(keys[k], out=o)
+            want = np.empty(sizes[k], np.float32)
+            okv.pull(keys[k], want)
+            compare(o.asnumpy(), want, (optname, kvtype, seed, step, k, devs))
+            if layerwise:
+                okv.local[keys[k]][...] = o.asnumpy().reshape(okv.local[keys[k]].shape)   # follow the device trajectory

@@ -515,7 +515,7 @@ def test_randomized_optimizers_store_types_and_checkpoints(seed, tmp_path):
         if rng.random() < 0.5:
             kv.push(names, vals)
         else:
-            odevs = [int(x) for x in rng.choice(ngpu, size=int(rng.integers(1, 4)), replace=False)]
+            odevs = [int(x) for x in rng.choice(ngpu, size=int(rng.integers(1, min(4, ngpu + 1))), replace=False)]
             outs = [[mx.nd.empty((sizes[k],), mx.gpu(d)) for d in odevs] for k in ks]
             kv.pushpull(names, vals, out=outs)
         okv.push(names, grads)
@@ -528,3 +528,80 @@ def test_randomized_optimizers_store_types_and_checkpoints(seed, tmp_path):
             compare(o.asnumpy(), want, (optname, kvtype, seed, step, k, devs))
             if layerwise:
                 okv.local[keys[k]][...] = o.asnumpy().reshape(okv.local[keys[k]].shape)   # follow the device trajectory
+
+
+@pytest.mark.parametrize("seed", list(range(16)))
+def test_randomized_row_sparse_compression_callback(seed):
+    """Random walks over the other three kinds of keys: row_sparse (lazy / standard SGD, Adam, or plain
+    assignment), 2-bit compressed dense keys, and keys updated through the Python updater callback."""
+    _need(2)
+    ngpu = min(mx.num_gpus(), 8)
+    rng = _rng(9000 + seed)
+    flavour = ["rsp", "gc", "callback", "rsp"][seed % 4]
+
+    def ctx_of(d):
+        return mx.cpu() if d < 0 else mx.gpu(d)
+
+    if flavour == "rsp":
+        rows, L = int(rng.choice([40, 300])), int(rng.choice([4, 6, 16]))
+        shape = (rows, L)
+        w0 = rng.uniform(-1, 1, shape).astype(np.float32)
+        optname, kw = [(None, {}), ("sgd", dict(learning_rate=0.1, momentum=0.9, wd=1e-3, lazy_update=True)),
+                       ("sgd", dict(learning_rate=0.1, wd=1e-3, lazy_update=False)),
+                       ("adam", dict(learning_rate=0.01, wd=1e-3, lazy_update=bool(seed & 8)))][(seed // 4) % 4]
+        kv = mx.kv.create("device")
+        kv.init("e", mx.nd.row_sparse_array(w0, ctx=ctx_of(int(rng.integers(-1, ngpu)))))
+        okv = O.OracleKVStore("device")
+        okv.init("e", O.RowSparse.from_dense(w0))
+        if optname:
+            kv.set_optimizer(mx.optimizer.create(optname, **kw))
+            okv.set_optimizer(O.OracleOptimizer(optname, **kw))
+        for step in range(6):
+            devs = [int(x) for x in rng.choice(np.arange(-1, ngpu), size=int(rng.integers(1, min(5, ngpu + 2))), replace=False)]
+            parts = []
+            for _ in devs:
+                nnz = int(rng.integers(0, rows // 2 + 1))
+                idx = np.sort(rng.choice(rows, nnz, replace=False)).astype(np.int64)
+                parts.append((idx, rng.uniform(-1, 1, (nnz, L)).astype(np.float32)))
+            kv.push("e", [mx.nd.row_sparse_array((v, i), shape=shape, ctx=ctx_of(d)) for (i, v), d in zip(parts, devs)])
+            okv.push("e", [O.RowSparse(i, v, shape) for i, v in parts])
+            ids = rng.integers(0, rows, int(rng.integers(1, 2 * rows))).astype(np.int64)
+            d = int(rng.integers(-1, ngpu))
+            out = mx.nd.zeros(shape, ctx_of(d), stype="row_sparse")
+            kv.row_sparse_pull("e", out=out, row_ids=mx.nd.array(ids, ctx_of(int(rng.integers(-1, ngpu))), dtype=np.int64))
+            want = O.sparse_retain(okv.local["e"], O.unique(ids))
+            assert np.array_equal(out.indices.asnumpy(), want.indices), (seed, step)
+            assert _bits_equal(out.data.asnumpy(), want.data.reshape(-1, L)), (seed, step, devs, d)
+    elif flavour == "gc":
+        E, thr = int(rng.choice([33, 4099, 70001])), 0.5
+        bits = "2bit" if seed & 4 else "1bit"
+        thr = 0.5 if bits == "2bit" else 0.0
+        kv = mx.kv.create("device")
+        kv.set_gradient_compression({"type": bits, "threshold": thr})
+        kv.init(0, mx.nd.zeros((E,), mx.gpu(int(rng.integers(ngpu)))))
+        n_slots = int(rng.integers(1, min(5, ngpu + 1)))
+        residual = [np.zeros(E, np.float32) for _ in range(n_slots)]
+        q, dq = (O.quantize_2bit, O.dequantize_2bit) if bits == "2bit" else (O.quantize_1bit, O.dequantize_1bit)
+        for step in range(5):
+            devs = [int(x) for x in rng.choice(ngpu, size=n_slots, replace=False)]
+            g = [rng.uniform(-1, 1, E).astype(np.float32) for _ in devs]
+            outs = [mx.nd.empty((E,), mx.gpu(int(d))) for d in rng.choice(ngpu, size=min(2, ngpu), replace=False)]
+            kv.pushpull(0, [mx.nd.array(x, mx.gpu(d)) for x, d in zip(g, devs)], out=outs)
+            deq = [dq(q(x, r, thr), E, thr) for x, r in zip(g, residual)]
+            want = O.sum_device(deq) if len(deq) > 1 else deq[0]
+            for o in outs:
+                assert _bits_equal(o.asnumpy(), want), (seed, step, devs)
+    else:
+        shape = (int(rng.integers(1, 9)), int(rng.integers(1, 9)))
+        kv = mx.kv.create("device")
+        kv.init("c", mx.nd.zeros(shape, ctx_of(int(rng.integers(-1, ngpu)))))
+        kv._set_updater(lambda key, recv, local: local.__iadd__(recv * 2))
+        total = np.zeros(shape, np.float32)
+        for step in range(6):
+            devs = [int(x) for x in rng.choice(np.arange(-1, ngpu), size=int(rng.integers(1, min(5, ngpu + 2))), replace=False)]
+            g = [rng.integers(-3, 4, shape).astype(np.float32) for _ in devs]
+            kv.push("c", [mx.nd.array(x, ctx_of(d)) for x, d in zip(g, devs)])
+            total += 2 * sum(g)
+            o = mx.nd.empty(shape, ctx_of(int(rng.integers(-1, ngpu))))
+            kv.pull("c", out=o)
+            assert np.array_equal(o.asnumpy(), total), (seed, step, devs)

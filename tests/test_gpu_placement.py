@@ -605,3 +605,71 @@ def test_randomized_row_sparse_compression_callback(seed):
             o = mx.nd.empty(shape, ctx_of(int(rng.integers(-1, ngpu))))
             kv.pull("c", out=o)
             assert np.array_equal(o.asnumpy(), total), (seed, step, devs)
+
+
+@pytest.mark.parametrize("seed", list(range(6)))
+def test_randomized_low_precision_master_weights(seed):
+    """bf16 / fp16 keys with an fp32 master and momentum (multi_precision SGD): the master and the momentum
+    must follow the key when the set of GPUs changes from call to call."""
+    _need(2)
+    ngpu = min(mx.num_gpus(), 8)
+    rng = _rng(12000 + seed)
+    lp = "bfloat16" if seed % 2 == 0 else np.float16
+    kind = 2 if lp == "bfloat16" else 1
+    to_lp = (lambda x: O.f32_to_bf16(x)) if kind == 2 else (lambda x: x.astype(np.float16))
+    to_f32 = (lambda x: O.bf16_to_f32(x)) if kind == 2 else (lambda x: x.astype(np.float32))
+    E = int(rng.choice([4099, 70001, 300007]))
+    w_lp = to_lp(rng.uniform(-1, 1, E).astype(np.float32))
+    w32, mom = to_f32(w_lp), np.zeros(E, np.float32)
+    kv = mx.kv.create("device")
+    kv.init(0, mx.nd.array(w_lp, mx.gpu(int(rng.integers(ngpu))), dtype=lp))
+    kv.set_optimizer(mx.optimizer.SGD(learning_rate=0.1, momentum=0.9, wd=1e-4, multi_precision=True))
+    want = np.zeros(E, np.uint16)
+    for step in range(6):
+        devs = [int(x) for x in rng.choice(ngpu, size=int(rng.integers(1, ngpu + 1)), replace=False)]
+        g_lp = [to_lp(rng.uniform(-1, 1, E).astype(np.float32)) for _ in devs]
+        kv.push(0, [mx.nd.array(x, mx.gpu(d), dtype=lp) for x, d in zip(g_lp, devs)])
+        gsum = O.sum_device_lp_f32out(g_lp, kind) if len(g_lp) > 1 else to_f32(g_lp[0])
+        O.mp_sgd_mom_update(want, kind, w32, mom, gsum, 0.1, 1e-4, 0.9)
+        out = mx.nd.empty((E,), mx.gpu(int(rng.integers(ngpu))), dtype=lp)
+        kv.pull(0, out=out)
+        got = out.asnumpy(raw=True) if kind == 2 else out.asnumpy().view(np.uint16)
+        assert np.array_equal(got, want), (seed, step, devs)
+
+
+def test_sharding_threshold_and_chunking_change_between_calls():
+    """MXKVB200SetTwoShotBytes / MXKVB200SetTuning between steps: the same key goes from redundant (one-shot) to
+    sharded (two-shot) updates and back, with Adam state and with the LAMB sequence, and the scheduling chunk
+    changes under it -- results do not depend on any of that."""
+    _need(2)
+    import ctypes
+    from mxnet_b200.base import _LIB, check_call
+    devs = list(range(min(mx.num_gpus(), 4)))
+    E = 70001
+    try:
+        for optname, kw, exact in (("adam", dict(learning_rate=0.01, wd=1e-3), True),
+                                   ("lamb", dict(learning_rate=0.01, wd=0.01), False)):
+            rng = _rng(13)
+            w0 = rng.uniform(-1, 1, E).astype(np.float32)
+            kv = mx.kv.create("device")
+            kv.init(0, mx.nd.array(w0, mx.gpu(0)))
+            kv.set_optimizer(mx.optimizer.create(optname, **kw))
+            oopt = O.OracleOptimizer(optname, **(kw if exact else dict(kw, norm_mode="f64")))
+            ow = w0.copy()
+            outs = [mx.nd.empty((E,), mx.gpu(d)) for d in devs]
+            for step, (thr, chunk) in enumerate([(1 << 30, 8192), (1024, 8192), (1024, 2048), (1 << 30, 4096), (4096, 8192)]):
+                check_call(_LIB.MXKVB200SetTwoShotBytes(ctypes.c_int64(thr)))
+                check_call(_LIB.MXKVB200SetTuning(ctypes.c_int64(chunk), 512, 0, -1))
+                g = [rng.uniform(-1, 1, E).astype(np.float32) for _ in devs]
+                kv.pushpull(0, [mx.nd.array(x, mx.gpu(d)) for x, d in zip(g, devs)], out=outs)
+                oopt.update(0, ow, O.sum_device(g))
+                for o in outs:
+                    if exact:
+                        assert _bits_equal(o.asnumpy(), ow), (optname, step)
+                    else:
+                        np.testing.assert_allclose(o.asnumpy(), ow, rtol=5e-6, atol=5e-7, err_msg=str((optname, step)))
+                if not exact:
+                    ow = outs[0].asnumpy().copy()
+    finally:
+        check_call(_LIB.MXKVB200SetTwoShotBytes(ctypes.c_int64(262144)))
+        check_call(_LIB.MXKVB200SetTuning(ctypes.c_int64(8192), 512, 0, -1))

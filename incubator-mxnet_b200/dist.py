@@ -60,6 +60,28 @@ def init_process_group(device=None, group=None):
     return rank, world
 
 
+def init_with_allgather(rank, world, device, allgather):
+    """Bind the engine to ANY process group: all it needs is ``allgather(payload: bytes) -> [bytes] * world``
+    (used once per collective allocation, to exchange CUDA IPC handles).  ``init_process_group`` is this with
+    torch.distributed behind it; MPI, a TCP store, or -- in the simulator tests -- files work as well."""
+    def _cb(send, nbytes, recv, _ctx):
+        try:
+            parts = allgather(ctypes.string_at(send, nbytes))
+            assert len(parts) == world
+            for i, b in enumerate(parts):
+                ctypes.memmove(recv + i * nbytes, bytes(b), nbytes)
+            return 0
+        except Exception as e:  # never raise through the C boundary
+            import sys
+            sys.stderr.write("mxnet_b200.dist all-gather failed: %r\n" % (e,))
+            return 1
+
+    cb = _ALLGATHER_PROTO(_cb)
+    check_call(_LIB.MXKVB200CommInit(rank, world, device, cb, None))
+    _state.update(cb=cb, group=None, rank=rank, world=world, dev=device)
+    return rank, world
+
+
 def destroy_process_group():
     check_call(_LIB.MXKVB200CommDestroy())
     _state.update(cb=None, group=None, rank=0, world=1, dev=None)

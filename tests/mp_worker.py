@@ -5,11 +5,13 @@ import sys
 import tempfile
 
 import numpy as np
-import torch
-import torch.distributed as dist
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+SIM = bool(os.environ.get("MXKV_SIM"))      # tests/sim: stand-in CUDA runtime, no torch, files as the process group
+if not SIM:
+    import torch
+    import torch.distributed as dist
 import mxnet_b200 as mx          # noqa: E402
 from oracle import oracle as O   # noqa: E402
 
@@ -21,9 +23,23 @@ def bits_equal(a, b):
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
-    torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    mx.dist.init_process_group(device=local)
+    if SIM:
+        sys.path.insert(0, os.path.join(ROOT, "tests", "sim"))
+        from file_comm import FileComm
+        comm = FileComm(rank, world, os.environ["MXKV_SIM_RDV"])
+        mx.dist.init_with_allgather(rank, world, local, comm.allgather)
+        device_sync, barrier, allgather_int = mx.nd.waitall, comm.barrier, comm.allgather_int
+    else:
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        mx.dist.init_process_group(device=local)
+        device_sync, barrier = torch.cuda.synchronize, dist.barrier
+
+        def allgather_int(x):
+            chk = torch.tensor([int(x)], dtype=torch.int64).cuda()
+            allc = [torch.empty_like(chk) for _ in range(world)]
+            dist.all_gather(allc, chk)
+            return [int(c) for c in allc]
     ctx = mx.gpu(local)
 
     def data(seed, shape, r):
@@ -41,7 +57,7 @@ def main():
     sizes = [5, 1000, 65536, 70001, (1 << 20) + 3, 3_000_001]
     keys = list(range(len(sizes)))
     kv.init([str(k) for k in keys], [mx.nd.zeros((e,), ctx) for e in sizes])
-    for mode in ("plain", "symmetric", "torch", "host"):
+    for mode in ("plain", "symmetric", "host") if SIM else ("plain", "symmetric", "torch", "host"):
         vals, outs, keep = [], [], []
         for k, e in zip(keys, sizes):
             src = data(2 + k, (e,), rank)
@@ -60,7 +76,7 @@ def main():
                 v = mx.nd.array(src, ctx)
                 o = mx.nd.empty((e,), ctx)
             vals.append(v); outs.append(o)
-        torch.cuda.synchronize()
+        device_sync()
         kv.pushpull([str(k) for k in keys], vals, out=outs)
         for k, e, o in zip(keys, sizes, outs):
             want = O.sum_device([data(2 + k, (e,), r) for r in range(world)])
@@ -189,7 +205,7 @@ def main():
             for step in range(3):
                 for k, s in zip(ks, shapes):
                     gm[k][:] = data(300 + 10 * step + k, s, rank)
-                torch.cuda.synchronize(); dist.barrier()
+                device_sync(); barrier()
                 kv7.pushpull(ks, gm, out=om)
                 okv.push(ks, [[data(300 + 10 * step + k, s, r) for r in range(world)] for k, s in zip(ks, shapes)])
                 for k, s in zip(ks, shapes):
@@ -198,10 +214,8 @@ def main():
                     got = om[k].asnumpy()
                     err = np.abs(got.astype(np.float64) - want).sum() / max(np.abs(want).sum(), 1e-30)
                     assert err < 1e-6, ("nvls", optname, step, k, err)
-                    chk = torch.from_numpy(got.view(np.int32).astype(np.int64)).sum().cuda().reshape(1)
-                    allc = [torch.empty_like(chk) for _ in range(world)]
-                    dist.all_gather(allc, chk)
-                    assert all(int(c) == int(chk) for c in allc), ("nvls replicas differ", optname, step, k)
+                    chk = int(got.view(np.int32).astype(np.int64).sum())
+                    assert all(c == chk for c in allgather_int(chk)), ("nvls replicas differ", optname, step, k)
             assert mx.kv.launch_count() - before == 3, "one launch per pushpull expected"
         print("NVLS_OK rank", rank, flush=True)
 
@@ -237,15 +251,14 @@ def main():
                     oopt.update(k, ow[k], O.sum_device([grad(k, s, r) for r in range(world)]).reshape(s))
                 got = outs[k].asnumpy()
                 np.testing.assert_allclose(got, ow[k], rtol=2e-6, atol=2e-7, err_msg=str((optname, step, k)))
-                chk = torch.from_numpy(got.view(np.int32).astype(np.int64)).sum().cuda().reshape(1)
-                allc = [torch.empty_like(chk) for _ in range(world)]
-                dist.all_gather(allc, chk)
-                assert all(int(c) == int(chk) for c in allc), ("replicas differ", optname, step, k)
+                chk = int(got.view(np.int32).astype(np.int64).sum())
+                assert all(c == chk for c in allgather_int(chk)), ("replicas differ", optname, step, k)
 
     mx.nd.waitall()
-    dist.barrier()
+    barrier()
     print("MP_WORKER_OK rank", rank, flush=True)
-    dist.destroy_process_group()
+    if not SIM:
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -13,6 +13,10 @@
 // The number of simulated GPUs is MXKV_SIM_DEVICES (default 4).
 #include <cuda_runtime_api.h>
 #include <cxxabi.h>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -39,10 +43,51 @@ int device_count() {
 
 cudaError_t fail(cudaError_t e) { g_last = e; return e; }
 
+// Allocations of 1 MiB and more are backed by named POSIX shared memory so that another simulated "GPU
+// process" can map them (cudaIpcGetMemHandle / cudaIpcOpenMemHandle: the one-process-per-GPU mode).
+struct Shm { std::string name; size_t bytes; bool owner; };
+std::map<void*, Shm> g_shm;
+int g_shm_counter = 0;
+
+void unlink_owned_shm() {           // a process that exits without freeing must not leave /dev/shm entries behind
+  for (auto& kv : g_shm)
+    if (kv.second.owner) shm_unlink(kv.second.name.c_str());
+}
+constexpr size_t kShmThreshold = 1 << 20;
+
 void* sim_alloc(size_t bytes) {
+  if (bytes >= kShmThreshold) {
+    char name[64];
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_shm_counter == 0) atexit(unlink_owned_shm);
+    snprintf(name, sizeof(name), "/mxkvsim_%d_%d", static_cast<int>(getpid()), g_shm_counter++);
+    const int fd = shm_open(name, O_CREAT | O_RDWR | O_EXCL, 0600);
+    if (fd < 0) return nullptr;
+    if (ftruncate(fd, static_cast<off_t>(bytes)) != 0) { close(fd); shm_unlink(name); return nullptr; }
+    void* p = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    if (p == MAP_FAILED) { shm_unlink(name); return nullptr; }
+    g_shm[p] = Shm{name, bytes, true};
+    return p;
+  }
   void* p = nullptr;
   if (posix_memalign(&p, 512, bytes ? bytes : 16) != 0) return nullptr;
   return p;
+}
+
+void sim_free(void* p) {
+  if (p == nullptr) return;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_shm.find(p);
+    if (it != g_shm.end()) {
+      munmap(p, it->second.bytes);
+      if (it->second.owner) shm_unlink(it->second.name.c_str());
+      g_shm.erase(it);
+      return;
+    }
+  }
+  free(p);
 }
 
 }  // namespace
@@ -140,9 +185,9 @@ API cudaError_t cudaMalloc(void** p, size_t n) { *p = sim_alloc(n); return *p ? 
 API cudaError_t cudaMallocAsync(void** p, size_t n, cudaStream_t) { return cudaMalloc(p, n); }
 API cudaError_t cudaMallocHost(void** p, size_t n) { return cudaMalloc(p, n); }
 API cudaError_t cudaHostAlloc(void** p, size_t n, unsigned) { return cudaMalloc(p, n); }
-API cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
-API cudaError_t cudaFreeAsync(void* p, cudaStream_t) { free(p); return cudaSuccess; }
-API cudaError_t cudaFreeHost(void* p) { free(p); return cudaSuccess; }
+API cudaError_t cudaFree(void* p) { sim_free(p); return cudaSuccess; }
+API cudaError_t cudaFreeAsync(void* p, cudaStream_t) { sim_free(p); return cudaSuccess; }
+API cudaError_t cudaFreeHost(void* p) { sim_free(p); return cudaSuccess; }
 API cudaError_t cudaMemcpyAsync(void* dst, const void* src, size_t n, cudaMemcpyKind, cudaStream_t) {
   if (n) memmove(dst, src, n);
   return cudaSuccess;
@@ -153,20 +198,44 @@ API cudaError_t cudaMemcpyPeerAsync(void* dst, int, const void* src, int, size_t
 }
 API cudaError_t cudaMemset(void* p, int v, size_t n) { if (n) memset(p, v, n); return cudaSuccess; }
 API cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) { return cudaMemset(p, v, n); }
-API cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t*, void*) { return fail(cudaErrorNotSupported); }
-API cudaError_t cudaIpcOpenMemHandle(void**, cudaIpcMemHandle_t, unsigned) { return fail(cudaErrorNotSupported); }
-API cudaError_t cudaIpcCloseMemHandle(void*) { return fail(cudaErrorNotSupported); }
+// IPC handle = name and size of the shared-memory object behind the allocation (64 bytes, like the real one)
+API cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  auto it = g_shm.find(p);
+  if (it == g_shm.end()) return fail(cudaErrorInvalidValue);
+  memset(h, 0, sizeof(*h));
+  snprintf(h->reserved, 48, "%s", it->second.name.c_str());
+  memcpy(h->reserved + 48, &it->second.bytes, sizeof(size_t));
+  return cudaSuccess;
+}
+API cudaError_t cudaIpcOpenMemHandle(void** out, cudaIpcMemHandle_t h, unsigned) {
+  char name[49];
+  memcpy(name, h.reserved, 48);
+  name[48] = 0;
+  size_t bytes = 0;
+  memcpy(&bytes, h.reserved + 48, sizeof(size_t));
+  const int fd = shm_open(name, O_RDWR, 0600);
+  if (fd < 0) return fail(cudaErrorInvalidValue);
+  void* p = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+  close(fd);
+  if (p == MAP_FAILED) return fail(cudaErrorMemoryAllocation);
+  std::lock_guard<std::mutex> lk(g_mu);
+  g_shm[p] = Shm{name, bytes, false};
+  *out = p;
+  return cudaSuccess;
+}
+API cudaError_t cudaIpcCloseMemHandle(void* p) { sim_free(p); return cudaSuccess; }
 
 // ---- streams and events: everything has already happened -----------------------------------------
 API cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) {
-  *s = reinterpret_cast<cudaStream_t>(sim_alloc(16));
+  *s = reinterpret_cast<cudaStream_t>(malloc(16));
   return cudaSuccess;
 }
 API cudaError_t cudaStreamCreateWithPriority(cudaStream_t* s, unsigned f, int) { return cudaStreamCreateWithFlags(s, f); }
 API cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
 API cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
 API cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) {
-  *e = reinterpret_cast<cudaEvent_t>(sim_alloc(16));
+  *e = reinterpret_cast<cudaEvent_t>(malloc(16));
   return cudaSuccess;
 }
 API cudaError_t cudaEventDestroy(cudaEvent_t e) { free(e); return cudaSuccess; }

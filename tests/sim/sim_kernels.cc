@@ -11,6 +11,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <sched.h>
 #include <functional>
 #include <map>
 #include "sim.h"
@@ -21,6 +22,35 @@
 using namespace mxkv;
 
 namespace sim {
+
+// ---- cross-process rendezvous (one simulated GPU per process: MXKV_SIM_MP=1) -------------------------------
+// The signal pads live in shared memory there, so the flag protocol of csrc/device_utils.cuh can run for
+// real, for "block 0" (an emulated kernel is one sequential block): write the next flag value into every
+// rank's pad, spin until every rank has written it into ours.  In the single-process simulation kernels run
+// to completion one after another and a rendezvous would only deadlock: it is skipped.
+static bool MultiProcess() {
+  static const bool mp = getenv("MXKV_SIM_MP") != nullptr;
+  return mp;
+}
+
+static void Rendezvous(const SyncArgs& s, int offset) {
+  if (!MultiProcess() || s.mode == SYNC_NONE || s.world <= 1) return;
+  uint32_t* counter = s.self + kSigFlagOff;          // block 0
+  const uint32_t flag = __atomic_load_n(counter, __ATOMIC_RELAXED) + 1;
+  for (int r = 0; r < s.world; ++r)
+    __atomic_store_n(s.peers[r] + offset + s.rank, flag, __ATOMIC_RELEASE);
+  for (int r = 0; r < s.world; ++r) {
+    const uint32_t* mine = s.self + offset + r;
+    long spins = 0;
+    while (__atomic_load_n(mine, __ATOMIC_ACQUIRE) != flag) {
+      if (++spins > 200000000L) { fprintf(stderr, "[mxkv sim] rendezvous timed out (rank %d waits for %d)\n", s.rank, r); abort(); }
+      if ((spins & 1023) == 0) sched_yield();
+    }
+  }
+  __atomic_store_n(counter, flag, __ATOMIC_RELAXED);
+}
+static void RendezvousStart(const SyncArgs& s) { Rendezvous(s, kSigStartOff); }
+static void RendezvousEnd(const SyncArgs& s) { Rendezvous(s, kSigEndOff); }
 
 void ParseName(const std::string& demangled, std::string* base, std::vector<std::string>* targs) {
   std::string s = demangled;
@@ -117,6 +147,8 @@ void DenseEntry(const DenseLaunch& L, const TensorWork& tw, bool mp) {
 
 template <typename T>
 bool DenseT(const DenseLaunch& L, int opt, bool mp) {
+  RendezvousStart(L.sync);
+  struct AtExit { const SyncArgs& s; ~AtExit() { RendezvousEnd(s); } } at_exit{L.sync};
   for (int i = 0; i < L.nworks; ++i) {
     const TensorWork& tw = L.works[i];
     switch (opt) {
@@ -151,6 +183,8 @@ bool DenseBulk(const std::vector<std::string>& t, void** args) {      // kv_dens
 
 template <typename T>
 void TypedSum(const DenseLaunch& L) {
+  RendezvousStart(L.sync);
+  struct AtExit { const SyncArgs& s; ~AtExit() { RendezvousEnd(s); } } at_exit{L.sync};
   for (int i = 0; i < L.nworks; ++i) {
     const TensorWork& tw = L.works[i];
     for (int64_t e = tw.begin; e < tw.end; ++e) {
@@ -241,6 +275,8 @@ float BadTotal(const NormLaunch& L) {
 
 template <typename T>
 bool NormFirstT(const NormLaunch& L, bool mp, bool grad_only) {
+  RendezvousStart(L.sync);
+  struct AtExit { const SyncArgs& s; ~AtExit() { RendezvousEnd(s); } } at_exit{L.sync};
   for (int i = 0; i < L.nworks; ++i) {
     const NormWork& tw = L.works[i];
     const int64_t nchunks = L.chunk_prefix[i + 1] - L.chunk_prefix[i];
@@ -303,6 +339,8 @@ bool NormFinalize(const LaunchInfo& info, void** args) {   // (works, prefix, ns
 
 template <typename T>
 bool NormMidT(const NormLaunch& L, bool mp, int kind) {
+  RendezvousStart(L.sync);
+  struct AtExit { const SyncArgs& s; ~AtExit() { RendezvousEnd(s); } } at_exit{L.sync};
   if (L.skip_nonfinite && BadTotal(L) > 0.f) return true;
   for (int i = 0; i < L.nworks; ++i) {
     const NormWork& tw = L.works[i];
@@ -351,6 +389,8 @@ bool NormMid(const std::vector<std::string>& t, void** args) {        // kv_norm
 
 template <typename T>
 bool NormApplyT(const NormLaunch& L, bool mp, int flavor) {
+  RendezvousStart(L.sync);
+  struct AtExit { const SyncArgs& s; ~AtExit() { RendezvousEnd(s); } } at_exit{L.sync};
   bool skip = false;
   if (L.skip_nonfinite) {
     skip = BadTotal(L) > 0.f;
@@ -480,7 +520,12 @@ bool Dispatch(const LaunchInfo& info, void** args) {
   if (base == "mxkv::kv_cast_f32_kernel") return CastF32(t, args);
   if (base == "mxkv::kv_quantize_kernel") return Quantize(t, args);
   if (base == "mxkv::kv_dequantize_kernel") return Dequantize(t, args);
-  if (base == "mxkv::kv_barrier_kernel") return true;          // rendezvous: nothing to wait for
+  if (base == "mxkv::kv_barrier_kernel") {                     // block-0 rendezvous between non-collective kernels
+    const SyncArgs& sy = *static_cast<const SyncArgs*>(args[0]);
+    RendezvousStart(sy);
+    RendezvousEnd(sy);
+    return true;
+  }
   if (base == "mxkv::kv_norm_first_kernel") return NormFirst(t, args);
   if (base == "mxkv::kv_norm_finalize_kernel") return NormFinalize(info, args);
   if (base == "mxkv::kv_norm_mid_kernel") return NormMid(t, args);

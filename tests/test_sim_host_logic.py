@@ -58,3 +58,35 @@ def test_single_process_multi_gpu_paths(sim_lib, devices):
                                   "test_gpu_placement.py"],
                extra=["-k", "not one_process_per_gpu"])
     assert _passed(out) >= 30, out[-500:]
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_one_process_per_gpu_on_simulator(sim_lib, world, tmp_path):
+    """The torchrun deployment shape without GPUs: `world` processes, each with one simulated GPU, peer memory
+    over POSIX shared memory (the stand-in for CUDA IPC), the real flag rendezvous between the emulated kernels,
+    files as the bootstrap process group.  Runs every scenario of tests/mp_worker.py except the torch-tensor
+    and NVSwitch-multicast ones."""
+    import glob
+    env = dict(os.environ)
+    env.update(MXKV_SIM="1", MXKV_SIM_MP="1", MXKV_SIM_RDV=str(tmp_path), MXKV_B200_LIBRARY_PATH=sim_lib,
+               MXKV_SIM_DEVICES=str(world), MXKV_B200_ARENA_MB="256", WORLD_SIZE=str(world))
+    procs = []
+    for r in range(world):
+        e = dict(env, RANK=str(r), LOCAL_RANK=str(r))
+        procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "mp_worker.py")], env=e, cwd=ROOT,
+                                      stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    outs = []
+    try:
+        for p in procs:
+            out, _ = p.communicate(timeout=900)
+            outs.append(out)
+    finally:
+        for p in procs:
+            if p.poll() is None:
+                p.kill()
+        for p in procs:                       # in case a worker died before its exit handler ran
+            for f in glob.glob("/dev/shm/mxkvsim_%d_*" % p.pid):
+                os.unlink(f)
+    for r, (p, out) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0, "rank %d:\n%s" % (r, out[-3000:])
+        assert "MP_WORKER_OK rank %d" % r in out, out[-2000:]

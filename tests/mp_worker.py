@@ -254,6 +254,64 @@ def main():
                 chk = int(got.view(np.int32).astype(np.int64).sum())
                 assert all(c == chk for c in allgather_int(chk)), ("replicas differ", optname, step, k)
 
+    # 9. random walks (every rank draws the same walk from a shared seed): key subsets, plain / symmetric /
+    #    host-resident gradients and outputs, pushes and fused pushpulls, pulls, every optimizer family
+    opts = [(None, {}), ("sgd", dict(learning_rate=0.05, momentum=0.9, wd=1e-3)), ("adam", dict(learning_rate=0.01, wd=1e-3)),
+            ("adamw", dict(learning_rate=0.01, wd=0.05)), ("lars", dict(learning_rate=0.1, momentum=0.9, wd=1e-3, eta=0.01))]
+    for walk in range(5):
+        wr = np.random.default_rng(31337 + walk)               # the walk itself: identical on every rank
+        optname, kw = opts[walk % len(opts)]
+        layerwise = optname == "lars"
+        sizes = [int(x) for x in wr.choice([5, 640, 4099, 70001, 300007], size=3, replace=False)]
+        ks = ["r%d" % i for i in range(len(sizes))]
+        kv9 = mx.kv.create("device")
+        w0 = [data(700 + 10 * walk + i, (e,), 0) for i, e in enumerate(sizes)]
+        kv9.init(ks, [mx.nd.array(w, ctx) for w in w0])
+        okv = O.OracleKVStore("device")
+        okv.init(ks, [w.copy() for w in w0])
+        if optname:
+            kv9.set_optimizer(mx.optimizer.create(optname, **kw))
+            okv.set_optimizer(O.OracleOptimizer(optname, **(dict(kw, norm_mode="f64") if layerwise else kw)))
+
+        def same(got, want, what):
+            if layerwise:
+                np.testing.assert_allclose(got, want, rtol=5e-6, atol=5e-7, err_msg=str(what))
+            else:
+                assert bits_equal(got, want), what
+
+        for step in range(6):
+            sub = sorted(wr.choice(len(ks), size=int(wr.integers(1, len(ks) + 1)), replace=False).tolist())
+            kind = str(wr.choice(["plain", "symmetric", "host"]))
+            fused_pull = bool(wr.integers(0, 2))
+            seed0 = 800 + 100 * walk + 10 * step
+
+            def make(e):
+                if kind == "symmetric":
+                    return mx.nd.empty_symmetric((e,))
+                return mx.nd.empty((e,), mx.cpu_pinned() if kind == "host" else ctx)
+            vals = []
+            for k in sub:
+                v = make(sizes[k]); v[:] = data(seed0 + k, (sizes[k],), rank); vals.append(v)
+            names = [ks[k] for k in sub]
+            device_sync()
+            if fused_pull:
+                outs = [make(sizes[k]) for k in sub]
+                kv9.pushpull(names, vals, out=outs)
+            else:
+                kv9.push(names, vals)
+                outs = [mx.nd.empty((sizes[k],), ctx) for k in sub]
+                kv9.pull(names, out=outs)
+            okv.push(names, [[data(seed0 + k, (sizes[k],), r) for r in range(world)] for k in sub])
+            for k, o in zip(sub, outs):
+                want = np.empty(sizes[k], np.float32)
+                okv.pull(ks[k], want)
+                got = o.asnumpy()
+                same(got, want, ("walk", walk, optname, step, k, kind, fused_pull))
+                chk = int(got.view(np.int32).astype(np.int64).sum())
+                assert all(c == chk for c in allgather_int(chk)), ("walk replicas differ", walk, step, k)
+                if layerwise:
+                    okv.local[ks[k]][...] = got
+
     mx.nd.waitall()
     barrier()
     print("MP_WORKER_OK rank", rank, flush=True)

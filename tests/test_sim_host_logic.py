@@ -60,7 +60,7 @@ def test_single_process_multi_gpu_paths(sim_lib, devices):
     assert _passed(out) >= 30, out[-500:]
 
 
-@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("world", [2, 4, 8])
 def test_one_process_per_gpu_on_simulator(sim_lib, world, tmp_path):
     """The torchrun deployment shape without GPUs: `world` processes, each with one simulated GPU, peer memory
     over POSIX shared memory (the stand-in for CUDA IPC), the real flag rendezvous between the emulated kernels,

@@ -1,13 +1,23 @@
 """Trainer: the driver loop of python/mxnet/gluon/trainer.py (step -> _allreduce_grads ->
 kv.pushpull per parameter with priority -i, update on kvstore) for torch parameters.
 
-``params`` is a list of torch Parameters (one replica per process: one-process-per-GPU mode or a
-single GPU), or a list of lists -- ``params[i][d]`` being parameter i's replica on device d --
+``params`` is a list of torch Parameters -- or of any objects with ``.data`` / ``.grad`` holding torch tensors
+or engine NDArrays -- (one replica per process: one-process-per-GPU mode or a single GPU), or a list of lists -- ``params[i][d]`` being parameter i's replica on device d --
 for the reference's single-process multi-GPU layout (param.list_data()/list_grad()).
 """
 from . import kvstore as _kv
 from . import optimizer as _opt
-from .ndarray import from_torch
+from .ndarray import NDArray, from_torch
+
+
+def _nd(x):
+    """Engine view of a parameter's data or gradient: a torch tensor is wrapped zero-copy, an NDArray (the
+    reference's own parameter type, and what the simulator tests use) is taken as it is."""
+    return x if isinstance(x, NDArray) else from_torch(x)
+
+
+def _ptr(x):
+    return x.data_ptr if isinstance(x, NDArray) else x.data_ptr()
 
 
 class Trainer(object):
@@ -55,7 +65,7 @@ class Trainer(object):
         if self._symmetric:
             self._bind_symmetric()
         else:
-            self._weights = [[from_torch(p.data) for p in reps] for reps in self._params]
+            self._weights = [[_nd(p.data) for p in reps] for reps in self._params]
         if kv is not None:
             if uok:
                 kv.set_optimizer(self._optimizer)
@@ -90,13 +100,13 @@ class Trainer(object):
         torch.cuda.synchronize()
 
     def _bind_grads(self):
-        self._grads = [[from_torch(p.grad) for p in reps] for reps in self._params]
-        self._grad_ptrs = [[p.grad.data_ptr() for p in reps] for reps in self._params]
+        self._grads = [[_nd(p.grad) for p in reps] for reps in self._params]
+        self._grad_ptrs = [[_ptr(p.grad) for p in reps] for reps in self._params]
 
     def _allreduce_grads(self):
         """trainer.py:385-409, with every parameter in ONE call when ``batched`` (one launch per
         GPU instead of one per parameter; the C ABI has always accepted key lists)."""
-        if self._grads is None or any(p.grad.data_ptr() != q for reps, ptrs in zip(self._params, self._grad_ptrs)
+        if self._grads is None or any(_ptr(p.grad) != q for reps, ptrs in zip(self._params, self._grad_ptrs)
                                       for p, q in zip(reps, ptrs)):
             self._bind_grads()
         kv = self._kvstore
@@ -159,7 +169,7 @@ class Trainer(object):
         if not hasattr(self, "_updaters"):
             ndev = len(self._params[0])
             self._updaters = [_opt.get_updater(self._optimizer) for _ in range(ndev)]
-        if self._grads is None or any(p.grad.data_ptr() != q for reps, ptrs in zip(self._params, self._grad_ptrs)
+        if self._grads is None or any(_ptr(p.grad) != q for reps, ptrs in zip(self._params, self._grad_ptrs)
                                       for p, q in zip(reps, ptrs)):
             self._bind_grads()
         scaler = getattr(self, "_amp_loss_scaler", None)

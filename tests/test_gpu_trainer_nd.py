@@ -1,0 +1,137 @@
+"""Trainer (python/mxnet/gluon/trainer.py driver loop) over parameters held in engine NDArrays -- the
+reference's own parameter type -- so that the loop can run without torch (e.g. on the simulator): the
+decision table, update on the kvstore vs. per-device updaters, several replicas per parameter, AMP."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import mxnet_b200 as mx
+from oracle import oracle as O
+
+
+class Param(object):
+    """What Trainer needs of a parameter replica: .data and .grad"""
+
+    def __init__(self, w, ctx):
+        self.data = mx.nd.array(w, ctx)
+        self.grad = mx.nd.zeros(w.shape, ctx)
+
+
+def _bits_equal(a, b):
+    return np.array_equal(np.ascontiguousarray(a).view(np.uint32), np.ascontiguousarray(b).view(np.uint32))
+
+
+SHAPES = [(64, 33), (129,), (1 << 17,), (7,)]
+
+
+@pytest.mark.parametrize("update_on_kvstore", [True, False])
+@pytest.mark.parametrize("optname,kw", [
+    ("sgd", dict(learning_rate=0.1, momentum=0.9, wd=1e-4)),
+    ("adam", dict(learning_rate=0.01, wd=1e-3)),
+])
+def test_step_matches_oracle_over_replicas(update_on_kvstore, optname, kw):
+    """trainer.py:334-480 with one replica of every parameter per GPU: rescale 1/batch, allreduce (+ update on
+    the store, or per-device native updaters), every replica ends up bit-identical to the oracle"""
+    ndev = min(mx.num_gpus(), 4)
+    rng = np.random.default_rng(5)
+    w0 = [rng.uniform(-1, 1, s).astype(np.float32) for s in SHAPES]
+    params = [[Param(w, mx.gpu(d)) for d in range(ndev)] for w in w0]
+    tr = mx.Trainer(params, optname, dict(kw), kvstore="device", update_on_kvstore=update_on_kvstore)
+    oopt = O.OracleOptimizer(optname, **kw)
+    ow = [w.copy() for w in w0]
+    batch = 16
+    for step in range(3):
+        grads = [[rng.uniform(-1, 1, s).astype(np.float32) for _ in range(ndev)] for s in SHAPES]
+        for reps, gs in zip(params, grads):
+            for p, g in zip(reps, gs):
+                p.grad[:] = g
+        tr.step(batch)
+        oopt.rescale_grad = 1.0 / batch
+        for i in range(len(SHAPES)):
+            oopt.update(i, ow[i], O.sum_device(grads[i]).reshape(SHAPES[i]) if ndev > 1 else grads[i][0])
+            for p in params[i]:
+                assert _bits_equal(p.data.asnumpy(), ow[i]), (optname, update_on_kvstore, step, i)
+    assert tr._update_on_kvstore is update_on_kvstore
+
+
+def test_kvstore_none_uses_local_updaters():
+    rng = np.random.default_rng(6)
+    w0 = [rng.uniform(-1, 1, s).astype(np.float32) for s in SHAPES]
+    params = [Param(w, mx.gpu(0)) for w in w0]
+    kw = dict(learning_rate=0.1, momentum=0.9)
+    tr = mx.Trainer(params, "sgd", dict(kw), kvstore=None)
+    oopt = O.OracleOptimizer("sgd", **kw)
+    ow = [w.copy() for w in w0]
+    for step in range(2):
+        for p, s in zip(params, SHAPES):
+            p.grad[:] = rng.uniform(-1, 1, s).astype(np.float32)
+        gs = [p.grad.asnumpy().copy() for p in params]
+        tr.step(4)
+        oopt.rescale_grad = 0.25
+        for i, p in enumerate(params):
+            oopt.update(i, ow[i], gs[i])
+            assert _bits_equal(p.data.asnumpy(), ow[i])
+    assert tr._kvstore is None and isinstance(tr._updaters[0], mx.optimizer.NativeUpdater)
+
+
+def test_amp_loss_scaling_both_ways():
+    """dynamic loss scaling: skip in the Trainer (local updaters) and skip on the device (LAMB, update on kvstore)"""
+    rng = np.random.default_rng(7)
+    w0 = [rng.uniform(-1, 1, s).astype(np.float32) for s in SHAPES[:2]]
+    for on_kv in (False, True):
+        params = [Param(w, mx.gpu(0)) for w in w0]
+        if on_kv:
+            tr = mx.Trainer(params, mx.optimizer.LAMB(learning_rate=0.01, skip_nonfinite=True), kvstore="device")
+        else:
+            tr = mx.Trainer(params, "sgd", {"learning_rate": 0.1}, kvstore=None)
+        mx.amp.init_trainer(tr)
+        scale = tr._amp_loss_scaler.loss_scale
+
+        def backward(poison=False):
+            tr._scale = tr._amp_original_scale / tr._amp_loss_scaler.loss_scale       # what amp.scale_loss does
+            for p, s in zip(params, SHAPES):
+                g = rng.uniform(-1, 1, s).astype(np.float32) * np.float32(tr._amp_loss_scaler.loss_scale)
+                if poison and s == SHAPES[1]:
+                    g[3] = np.inf
+                p.grad[:] = g
+        backward()
+        tr.step(1)
+        after = [p.data.asnumpy().copy() for p in params]
+        assert not any(_bits_equal(a, w) for a, w in zip(after, w0))
+        backward(poison=True)
+        tr.step(1)
+        for p, a in zip(params, after):
+            assert _bits_equal(p.data.asnumpy(), a), on_kv
+        assert tr._amp_loss_scaler._next_loss_scale == scale / 2
+        backward()
+        tr.step(1)
+        assert tr._amp_loss_scaler.loss_scale == scale / 2
+        assert not any(_bits_equal(p.data.asnumpy(), a) for p, a in zip(params, after))
+
+
+def test_save_load_states_round_trip(tmp_path):
+    rng = np.random.default_rng(8)
+    w0 = [rng.uniform(-1, 1, s).astype(np.float32) for s in SHAPES]
+    grads = [[rng.uniform(-1, 1, s).astype(np.float32) for s in SHAPES] for _ in range(4)]
+
+    def run(tr, params, gs_list):
+        for gs in gs_list:
+            for p, g in zip(params, gs):
+                p.grad[:] = g
+            tr.step(2)
+
+    for on_kv in (True, False):
+        pa = [Param(w, mx.gpu(0)) for w in w0]
+        ta = mx.Trainer(pa, "adam", {"learning_rate": 0.01}, kvstore="device", update_on_kvstore=on_kv)
+        run(ta, pa, grads[:2])
+        f = str(tmp_path / ("t_%d.states" % on_kv))
+        ta.save_states(f)
+        mid = [p.data.asnumpy().copy() for p in pa]
+        run(ta, pa, grads[2:])
+        pb = [Param(w, mx.gpu(0)) for w in mid]
+        tb = mx.Trainer(pb, "adam", {"learning_rate": 0.01}, kvstore="device", update_on_kvstore=on_kv)
+        tb.load_states(f)
+        run(tb, pb, grads[2:])
+        for a, b in zip(pa, pb):
+            assert _bits_equal(a.data.asnumpy(), b.data.asnumpy()), on_kv

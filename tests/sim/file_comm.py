@@ -6,7 +6,7 @@ import time
 
 
 class FileComm(object):
-    def __init__(self, rank, world, directory, timeout=120.0):
+    def __init__(self, rank, world, directory, timeout=600.0):
         self.rank, self.world, self.dir, self.timeout = rank, world, directory, timeout
         self.seq = 0
 

@@ -12,6 +12,10 @@ import mxnet_b200 as mx
 from oracle import oracle as O
 
 
+import os as _os
+_EXTRA = int(_os.environ.get("MXKV_FUZZ_SEEDS", "0"))     # more random walks on demand (soak runs on the simulator)
+
+
 def _need(n):
     if mx.num_gpus() < n:
         pytest.skip("needs %d GPUs" % n)
@@ -379,7 +383,7 @@ def test_host_resident_key_lists(optname, kw, monkeypatch):
                 assert _bits_equal(outs[k].asnumpy(), want), (optname, step, k)
 
 
-@pytest.mark.parametrize("seed", list(range(12)))
+@pytest.mark.parametrize("seed", list(range(12 + _EXTRA)))
 def test_randomized_call_sequences(seed):
     """A random walk over the store's states: keys of one-shot and two-shot size, values pushed from random
     subsets of the GPUs (or the host), pushes and fused pushpulls interleaved with pulls to random devices, a
@@ -461,7 +465,7 @@ _FUZZ_OPTS = [
 ]
 
 
-@pytest.mark.parametrize("seed", list(range(27)))
+@pytest.mark.parametrize("seed", list(range(27 + _EXTRA)))
 def test_randomized_optimizers_store_types_and_checkpoints(seed, tmp_path):
     """Every fused optimizer x {'device', 'local'} association order, random device subsets per call, and a
     save / load of the optimizer states into a fresh store in the middle of the run."""
@@ -530,7 +534,7 @@ def test_randomized_optimizers_store_types_and_checkpoints(seed, tmp_path):
                 okv.local[keys[k]][...] = o.asnumpy().reshape(okv.local[keys[k]].shape)   # follow the device trajectory
 
 
-@pytest.mark.parametrize("seed", list(range(16)))
+@pytest.mark.parametrize("seed", list(range(16 + _EXTRA)))
 def test_randomized_row_sparse_compression_callback(seed):
     """Random walks over the other three kinds of keys: row_sparse (lazy / standard SGD, Adam, or plain
     assignment), 2-bit compressed dense keys, and keys updated through the Python updater callback."""
@@ -607,7 +611,7 @@ def test_randomized_row_sparse_compression_callback(seed):
             assert np.array_equal(o.asnumpy(), total), (seed, step, devs)
 
 
-@pytest.mark.parametrize("seed", list(range(6)))
+@pytest.mark.parametrize("seed", list(range(6 + _EXTRA)))
 def test_randomized_low_precision_master_weights(seed):
     """bf16 / fp16 keys with an fp32 master and momentum (multi_precision SGD): the master and the momentum
     must follow the key when the set of GPUs changes from call to call."""

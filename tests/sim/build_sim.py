@@ -41,5 +41,69 @@ def build(verbose=False):
     return sim, fake
 
 
+def build_sanitized(verbose=False):
+    """The engine's host code AND the stand-in runtime recompiled with AddressSanitizer + UBSan
+    (tests/sim/_build/asan/).  The device code in the objects is untouched (nothing executes it here); what is
+    checked is the host side: replica / state bookkeeping, work-list construction, the C ABI's buffer handling.
+    Run python with LD_PRELOAD=<libasan> (see `sanitizer_env`)."""
+    sys.path.insert(0, PKG)
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("mxkv_build", os.path.join(PKG, "build.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    out = os.path.join(OUT, "asan")
+    os.makedirs(out, exist_ok=True)
+    san = ["-fsanitize=address", "-fsanitize=undefined", "-fno-sanitize=vptr", "-fno-omit-frame-pointer",
+           "-fno-sanitize-recover=undefined"]
+    fake = os.path.join(out, "libcudart.so.12")
+    srcs = [os.path.join(HERE, f) for f in ("fake_cudart.cc", "sim_kernels.cc", "sim_rsp.cc")]
+    deps = srcs + [os.path.join(PKG, "csrc", f) for f in os.listdir(os.path.join(PKG, "csrc"))] + \
+           [os.path.join(HERE, "sim.h"), os.path.abspath(__file__)]
+    sim = os.path.join(out, "libmxkv_b200_sim.so")
+    if os.path.exists(sim) and os.path.exists(fake) and \
+            all(os.path.getmtime(d) <= os.path.getmtime(sim) for d in deps):
+        return sim, fake
+    cmd = ["g++", "-std=c++17", "-O1", "-g", "-ffp-contract=off", "-fPIC", "-shared", "-Wall", "-Wno-unknown-pragmas"] + \
+          san + \
+          ["-I", os.path.join(PKG, "csrc"), "-I", os.path.join(CUDA, "include"), "-I", HERE] + srcs + \
+          ["-o", fake, "-Wl,-soname,libcudart.so.12", "-Wl,--version-script=" + os.path.join(HERE, "cudart.map")]
+    if verbose:
+        print(" ".join(cmd))
+    subprocess.check_call(cmd)
+    procs, objs = [], []
+    for src in b.SOURCES:
+        obj = os.path.join(out, src.rsplit(".", 1)[0] + ".o")
+        flags = [f for f in b.FLAGS if f != "-O3"]
+        cmd = [b.NVCC] + flags + ["-O1", "-g", "-Xcompiler", ",".join(san), "-x", "cu", "-c", os.path.join(PKG, "csrc", src), "-o", obj]
+        if verbose:
+            print(" ".join(cmd))
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
+        objs.append(obj)
+    for src, p in procs:
+        o, _ = p.communicate()
+        if p.returncode != 0:
+            raise RuntimeError("sanitized build failed on %s:\n%s" % (src, o.decode()))
+    cmd = ["g++", "-shared", "-o", sim] + objs + ["-fsanitize=address,undefined", "-L", out, "-l:libcudart.so.12",
+                                                  "-Wl,--disable-new-dtags", "-Wl,-rpath," + out]
+    if verbose:
+        print(" ".join(cmd))
+    subprocess.check_call(cmd)
+    return sim, fake
+
+
+def sanitizer_env():
+    """Environment additions for a python process that loads the sanitized libraries."""
+    def lib(name):
+        return subprocess.check_output(["gcc", "-print-file-name=" + name], text=True).strip()
+    return {"LD_PRELOAD": lib("libasan.so") + ":" + lib("libubsan.so"),
+            # python itself leaks by design; the interceptors must not trip over its allocator either
+            "ASAN_OPTIONS": "detect_leaks=0:abort_on_error=1:allocator_may_return_null=1:handle_segv=0",
+            "UBSAN_OPTIONS": "print_stacktrace=1:halt_on_error=1",
+            "PYTHONMALLOC": "malloc"}
+
+
 if __name__ == "__main__":
-    print(build(verbose=True))
+    if "--asan" in sys.argv:
+        print(build_sanitized(verbose=True))
+    else:
+        print(build(verbose=True))

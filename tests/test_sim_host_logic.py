@@ -61,6 +61,34 @@ def test_single_process_multi_gpu_paths(sim_lib, devices):
     assert _passed(out) >= 30, out[-500:]
 
 
+def test_host_code_under_address_and_ub_sanitizers():
+    """The engine's host code (and the stand-in runtime) rebuilt with AddressSanitizer + UBSan, driven through
+    the placement random walks, the multi-GPU parity tests and the row_sparse paths on 4 simulated GPUs: replica
+    vectors that reallocate while pointers into them are held, work lists, state migration, C-ABI buffers.  Any
+    report aborts the run.  (The reference's counterpart is its USE_ASAN CI job, CMakeLists.txt:88.)"""
+    if shutil.which("g++") is None or not os.path.exists("/usr/local/cuda/bin/nvcc"):
+        pytest.skip("needs g++ and nvcc")
+    spec = importlib.util.spec_from_file_location("build_sim", os.path.join(SIM, "build_sim.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    san = b.sanitizer_env()
+    if not all(os.path.isabs(x) and os.path.exists(x) for x in san["LD_PRELOAD"].split(":")):
+        pytest.skip("libasan / libubsan not installed")
+    lib, _ = b.build_sanitized()
+    env = dict(os.environ)
+    env.update(san)
+    env.update(MXKV_SIM="1", MXKV_B200_LIBRARY_PATH=lib, MXKV_SIM_DEVICES="4")
+    cmd = [sys.executable, "-m", "pytest", "-q", "-m", "gpu", "-p", "no:cacheprovider", "-x",
+           "-k", "not one_process_per_gpu"] + \
+          [os.path.join(ROOT, "tests", f) for f in ("test_gpu_placement.py", "test_gpu_multi.py", "test_gpu_rsp.py",
+                                                    "test_gpu_updater.py")]
+    r = subprocess.run(cmd, env=env, cwd=ROOT, capture_output=True, text=True, timeout=1500)
+    tail = (r.stdout + r.stderr)[-4000:]
+    assert r.returncode == 0, tail
+    assert "AddressSanitizer" not in tail and "runtime error" not in tail, tail
+    assert _passed(r.stdout) >= 100, tail
+
+
 @pytest.mark.parametrize("world", [2, 4, 8])
 def test_one_process_per_gpu_on_simulator(sim_lib, world, tmp_path):
     """The torchrun deployment shape without GPUs: `world` processes, each with one simulated GPU, peer memory

@@ -62,6 +62,9 @@ class Trainer(object):
         elif uok and not kv.is_capable(_kv.KVStoreBase.OPTIMIZER):
             raise ValueError("Please set update_on_kvstore=False when training with " + str(type(kv)))
         self._update_on_kvstore = uok
+        # key lists in one call are this engine's extension of the plug-in API; a third-party store gets the
+        # reference's call pattern, one key per call (trainer.py:155-176, 385-409)
+        self._batched = self._batched and isinstance(kv, _kv.KVStore)
         if self._symmetric:
             self._bind_symmetric()
         else:
@@ -71,7 +74,11 @@ class Trainer(object):
                 kv.set_optimizer(self._optimizer)
             # _init_params (trainer.py:155-176): broadcast(idx, w0, all_w)
             idx = list(range(len(self._params)))
-            kv.broadcast(idx, [w[0] for w in self._weights], [w for w in self._weights])
+            if self._batched or isinstance(kv, _kv.KVStore):
+                kv.broadcast(idx, [w[0] for w in self._weights], [w for w in self._weights])
+            else:
+                for i in idx:
+                    kv.broadcast(i, self._weights[i][0], self._weights[i])
         self._kv_initialized = True
 
     def _bind_symmetric(self):

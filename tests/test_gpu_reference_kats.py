@@ -221,6 +221,56 @@ def test_aggregator(stype):
     check_aggregator(init_kv_with_str("cpu"), "a", str_keys)
 
 
+@pytest.mark.parametrize("sparse_pull", [False, True])
+@pytest.mark.parametrize("dev", ["cpu", "gpu"])
+def test_sparse_aggregator(sparse_pull, dev):
+    # tests/python/unittest/test_kvstore.py:174-220: row_sparse keys, random row_sparse values on four contexts,
+    # pushed and then read back INTO THE SAME ARRAYS, either with row_sparse_pull of every row or with
+    # pull(ignore_sparse=False); single key, then the key list with one shared list of values
+    rng = np.random.default_rng(11 + int(sparse_pull))
+
+    def rand_rsp(ctx):
+        dense = rng.normal(size=shape).astype(np.float32)
+        dense[rng.random(shape[0]) < 0.5] = 0                     # rand_ndarray: random density
+        return mx.nd.array(dense, ctx).tostype("row_sparse")
+
+    kv = mx.kv.create("device")
+    kv.init("a", mx.nd.zeros(shape, stype="row_sparse"))
+    kv.init(str_keys, [mx.nd.zeros(shape, stype="row_sparse")] * len(keys))
+    num_devs = 4
+    devs = [ctx_of(dev, i) for i in range(num_devs)]
+    all_rows = mx.nd.array(np.arange(shape[0]), dtype=np.float32)
+
+    vals = [rand_rsp(d) for d in devs]
+    expected_sum = np.zeros(shape)
+    for v in vals:
+        expected_sum += v.todense_numpy()
+    kv.push("a", vals)
+    if sparse_pull:
+        kv.row_sparse_pull("a", out=vals, row_ids=[all_rows] * len(vals))
+    else:
+        kv.pull("a", out=vals, ignore_sparse=False)
+    result_sum = np.zeros(shape)
+    for v in vals:
+        result_sum += v.todense_numpy()
+    np.testing.assert_allclose(result_sum, expected_sum * num_devs, rtol=1e-5, atol=1e-6)
+
+    vals = [[rand_rsp(d) for d in devs]] * len(keys)
+    expected_sum = np.zeros(shape)
+    for v in vals[0]:
+        expected_sum += v.todense_numpy()
+    kv.push(str_keys, vals)
+    if sparse_pull:
+        kv.row_sparse_pull(str_keys, out=vals, row_ids=[[all_rows] * num_devs] * len(vals))
+    else:
+        kv.pull(str_keys, out=vals, ignore_sparse=False)
+    for vv in vals:
+        result_sum = np.zeros(shape)
+        for v in vv:
+            result_sum += v.todense_numpy()
+        np.testing.assert_allclose(result_sum, expected_sum * num_devs, rtol=1e-5, atol=1e-6)
+
+
 @pytest.mark.parametrize("kv_type", ["local", "device"])
 @pytest.mark.parametrize("push_on_gpu", [False, True])
 def test_rsp_push_pull(kv_type, push_on_gpu):

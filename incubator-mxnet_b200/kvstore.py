@@ -129,6 +129,7 @@ class KVStore(KVStoreBase):
         self._fused = False
         self._last_lr = None
         self._keys = set()
+        self._mults = {}
 
     def __del__(self):
         try:
@@ -158,6 +159,8 @@ class KVStore(KVStoreBase):
                     top = c
             opt_.num_update = top
             self._last_pushed = uniq
+            if opt_.param_dict:
+                self._sync_mults(uniq)
         self._sync_lr()
 
     def push(self, key, value, priority=0):
@@ -260,7 +263,10 @@ class KVStore(KVStoreBase):
                                                  c_str_array(keys), c_str_array(vals)))
             self._fused = True
             self._last_lr = optimizer.learning_rate
-            for k, (lm, wm) in optimizer.key_multipliers().items():
+            now = optimizer.key_multipliers()
+            for k in [k for k in self._mults if k not in now and self._mults[k] != (1.0, 1.0)]:
+                self.set_mult(k, 1.0, 1.0)              # a multiplier of the previous optimizer
+            for k, (lm, wm) in now.items():
                 self.set_mult(k, lm, wm)
             if hasattr(optimizer, "no_trust_ratio_indices"):
                 for k in optimizer.no_trust_ratio_indices():
@@ -269,7 +275,22 @@ class KVStore(KVStoreBase):
             self._fused = False
             self._set_updater(opt.get_updater(optimizer, native=False))
 
+    def _sync_mults(self, keys):
+        """``Parameter.lr_mult`` / ``wd_mult`` are read at every update by the reference
+        (optimizer.py:479-487,518-525 through ``param_dict``), so a change between steps takes effect at once
+        (tests/python/unittest/test_gluon_trainer.py:94-100,131-149): the engine's per-key multipliers follow."""
+        opt_ = self._optimizer
+        if not (self._fused and opt_ is not None and opt_.param_dict):
+            return
+        pd, seen = opt_.param_dict, self._mults
+        for k in keys:
+            if k in pd:
+                m = (opt_._mult(opt_.lr_mult, "lr_mult", k), opt_._mult(opt_.wd_mult, "wd_mult", k))
+                if seen.get(k, (1.0, 1.0)) != m:
+                    self.set_mult(k, m[0], m[1])
+
     def set_mult(self, key, lr_mult=1.0, wd_mult=1.0):
+        self._mults[key] = (lr_mult, wd_mult)
         if isinstance(key, str):
             check_call(_LIB.MXKVB200SetOptimizerMult(self.handle, 0, c_str(key), ctypes.c_float(lr_mult),
                                                      ctypes.c_float(wd_mult)))
@@ -368,7 +389,12 @@ class KVStore(KVStoreBase):
             assert self._updater is not None, "Cannot load states for distributed training"
             self._updater.set_states(blob)
             return
-        self._load_fused_states(blob)
+        payload = pickle.loads(blob)
+        if payload.get("optimizer") is not None:
+            # updater.py:118-127: a dumped optimizer replaces the current one (its update counts and learning
+            # rate included); the engine's arrays are untouched by set_optimizer
+            self.set_optimizer(payload["optimizer"])
+        self._load_fused_states(payload)
 
     def _load_fused_states(self, blob, only=None):
         payload = pickle.loads(blob) if isinstance(blob, bytes) else blob

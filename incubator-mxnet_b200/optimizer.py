@@ -38,11 +38,23 @@ class Optimizer(object):
         self.wd_mult = {}
         self.begin_num_update = begin_num_update
         self.num_update = begin_num_update
-        self._index_update_count = {}
+        self._all_index_update_counts = {0: {}}          # per device id (optimizer.py:113-114)
+        self._index_update_count = self._all_index_update_counts[0]
         self.clip_gradient = clip_gradient
         self.multi_precision = multi_precision
         self.idx2name = dict(param_idx2name or {})
         self.param_dict = param_dict or {}
+
+    def __getstate__(self):
+        """optimizer.py:544-553: ``param_dict`` (the Parameter objects) is not part of a saved optimizer; the
+        Trainer attaches its own parameters again after loading."""
+        ret = self.__dict__.copy()
+        ret.pop("param_dict", None)
+        return ret
+
+    def __setstate__(self, state):
+        self.__dict__ = state
+        self.param_dict = {}
 
     @staticmethod
     def register(klass):
@@ -72,6 +84,13 @@ class Optimizer(object):
     def set_wd_mult(self, args_wd_mult):
         self.wd_mult = dict(args_wd_mult)
 
+    def _set_current_context(self, device_id):
+        """optimizer.py:433-443: one table of update counts per device, so that the per-device updaters of a
+        Trainer that share this optimizer count every step once, not once per device."""
+        if device_id not in self._all_index_update_counts:
+            self._all_index_update_counts[device_id] = {}
+        self._index_update_count = self._all_index_update_counts[device_id]
+
     def _update_count(self, index):
         self._index_update_count[index] = self._index_update_count.get(index, self.begin_num_update) + 1
         self.num_update = max(self._index_update_count[index], self.num_update)
@@ -80,7 +99,7 @@ class Optimizer(object):
         """Per-parameter multiplier in the reference's order of precedence (optimizer.py:479-487,518-525):
         the Parameter object, then the table by index, then the table by name."""
         if index in self.param_dict:
-            return getattr(self.param_dict[index], attr)
+            return getattr(self.param_dict[index], attr, 1.0)
         if index in table:
             return table[index]
         if index in self.idx2name:
@@ -316,6 +335,11 @@ class Test(Optimizer):
         w.sub_(self._get_lr(index) * (self.rescale_grad * g + self._get_wd(index) * w))
 
 
+def _device_id(weight):
+    ctx = getattr(weight, "context", None)
+    return getattr(ctx, "device_id", 0) if ctx is not None else 0
+
+
 class Updater(object):
     """The kvstore updater callback (python/mxnet/optimizer/updater.py:30-127)."""
 
@@ -324,6 +348,7 @@ class Updater(object):
         self.states = {}
 
     def __call__(self, index, grad, weight):
+        self.optimizer._set_current_context(_device_id(weight))          # updater.py:50-51
         if index not in self.states:
             self.states[index] = self.optimizer.create_state(index, weight)
         self.optimizer._update_count(index)
@@ -384,9 +409,11 @@ class NativeUpdater(object):
         import ctypes
         if not isinstance(index, (list, tuple)):
             index, grad, weight = [index], [grad], [weight]
+        self.optimizer._set_current_context(_device_id(weight[0]))       # updater.py:50-51
         for i in dict.fromkeys(index):   # count first, then read the learning rate (sgd.py:184-186)
             self.optimizer._update_count(i)
         self._sync()
+        self._kv._sync_mults(index)
         n = len(index)
         use_str = isinstance(index[0], str)
         wh = (ctypes.c_void_p * n)(*[w.handle.value for w in weight])

@@ -31,6 +31,7 @@ class Trainer(object):
             self._optimizer = optimizer
         else:
             self._optimizer = _opt.create(optimizer, **optimizer_params)
+        self._attach_params()
         self._kvstore_arg = kvstore
         self._update_on_kvstore_arg = update_on_kvstore
         self._kv_initialized = False
@@ -40,6 +41,14 @@ class Trainer(object):
         self._symmetric = symmetric      # rebind p.data / p.grad to peer-mapped arena memory (zero-copy)
         self._grads = None
         self._weights = None
+
+    def _attach_params(self):
+        """trainer.py:139-153,540-541: the optimizer sees the Parameter objects, whose ``lr_mult`` / ``wd_mult``
+        it reads at every update (plain torch Parameters have neither and are left out)."""
+        pd = {i: reps[0] for i, reps in enumerate(self._params)
+              if hasattr(reps[0], "lr_mult") or hasattr(reps[0], "wd_mult")}
+        if pd:
+            self._optimizer.param_dict = pd
 
     @property
     def learning_rate(self):
@@ -203,6 +212,7 @@ class Trainer(object):
             self._init_kvstore()
         if self._update_on_kvstore:
             self._kvstore.load_optimizer_states(fname)
+            self._optimizer = self._kvstore._optimizer
         else:
             with open(fname, "rb") as f:
                 blob = f.read()
@@ -210,3 +220,6 @@ class Trainer(object):
                 self._updaters = [_opt.get_updater(self._optimizer) for _ in range(len(self._params[0]))]
             for u in self._updaters:
                 u.set_states(blob)
+                u.optimizer = self._updaters[0].optimizer
+            self._optimizer = self._updaters[0].optimizer
+        self._attach_params()

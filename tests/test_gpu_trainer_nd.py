@@ -135,3 +135,107 @@ def test_save_load_states_round_trip(tmp_path):
         run(tb, pb, grads[2:])
         for a, b in zip(pa, pb):
             assert _bits_equal(a.data.asnumpy(), b.data.asnumpy()), on_kv
+
+
+class RefParam(Param):
+    """a gluon.Parameter as far as the optimizer is concerned: replicas + lr_mult / wd_mult read at every update"""
+
+    def __init__(self, w, ctx):
+        super(RefParam, self).__init__(w, ctx)
+        self.lr_mult = 1.0
+        self.wd_mult = 1.0
+
+
+def _two_replicas(shape=(10,)):
+    ndev = max(1, min(mx.num_gpus(), 2))
+    reps = [RefParam(np.zeros(shape, np.float32), mx.gpu(d % ndev)) for d in range(2)]
+    reps[1].__dict__.pop("lr_mult"), reps[1].__dict__.pop("wd_mult")        # the Parameter is replica 0's owner
+    return reps
+
+
+def _backward_of_w_plus_1(reps):
+    for p in reps:
+        p.grad[:] = 1           # d(w + 1)/dw
+
+
+@pytest.mark.parametrize("update_on_kvstore", [None, False])
+def test_reference_trainer_known_answers(update_on_kvstore, tmp_path):
+    # tests/python/unittest/test_gluon_trainer.py:80-128: two replicas, sgd lr 1 momentum 0.5; every replica
+    # contributes a gradient of ones -> -2 after one step; then lr_mult = 0.5 ON THE PARAMETER -> -4
+    x = _two_replicas()
+    trainer = mx.Trainer([x], "sgd", {"learning_rate": 1.0, "momentum": 0.5}, update_on_kvstore=update_on_kvstore)
+    _backward_of_w_plus_1(x)
+    trainer.step(1)
+    assert (x[1].data.asnumpy() == -2).all()
+    x[0].lr_mult = 0.5
+    _backward_of_w_plus_1(x)
+    trainer.step(1)
+    assert (x[1].data.asnumpy() == -4).all(), x[1].data.asnumpy()
+    assert (x[0].data.asnumpy() == -4).all()
+
+    f = str(tmp_path / "test_trainer.states")
+    trainer.save_states(f)
+    trainer.load_states(f)
+    if trainer._update_on_kvstore:
+        assert trainer._optimizer is trainer._kvstore._optimizer
+        # invalid usage of update and allreduce_grads if update_on_kvstore (:109-111)
+        with pytest.raises(AssertionError):
+            trainer.update(1)
+        with pytest.raises(AssertionError):
+            trainer.allreduce_grads()
+    else:
+        assert all(u.optimizer is trainer._optimizer for u in trainer._updaters)
+    # the loaded optimizer carries on: momentum -2 -> 0.5 * -2 - 0.5 * 2 = -2 -> w = -6
+    _backward_of_w_plus_1(x)
+    trainer.step(1)
+    assert (x[0].data.asnumpy() == -6).all(), x[0].data.asnumpy()
+
+
+def test_reference_trainer_allreduce_then_update():
+    # test_gluon_trainer.py:117-129: gradients that differ per replica (i * w -> i), allreduce_grads makes them
+    # equal, update(1) applies them: 0 - 1 * (0 + 1) = -1
+    x = _two_replicas()
+    trainer2 = mx.Trainer([x], "sgd", {"learning_rate": 1.0, "momentum": 0.5}, update_on_kvstore=False)
+    for i, p in enumerate(x):
+        p.grad[:] = float(i)
+    assert (x[0].grad.asnumpy() != x[1].grad.asnumpy()).all()
+    trainer2.allreduce_grads()
+    assert (x[0].grad.asnumpy() == x[1].grad.asnumpy()).all()
+    trainer2.update(1)
+    assert (x[1].data.asnumpy() == -1).all(), x[1].data.asnumpy()
+
+
+def test_reference_trainer_save_load_reattaches_parameters(tmp_path):
+    # test_gluon_trainer.py:131-149: after load_states the optimizer reads the CURRENT parameters' multipliers
+    x = _two_replicas()
+    trainer = mx.Trainer([x], "sgd", {"learning_rate": 0.1})
+    _backward_of_w_plus_1(x)
+    trainer.step(1)
+    assert trainer._kvstore._optimizer._get_lr(0) == 0.1
+    f = str(tmp_path / "test_trainer_save_load.states")
+    trainer.save_states(f)
+    trainer.load_states(f)
+    x[0].lr_mult = 2.0
+    assert trainer._kvstore._optimizer._get_lr(0) == 0.2
+    # ... and so does the engine: -0.2 - 0.2 * 2
+    _backward_of_w_plus_1(x)
+    trainer.step(1)
+    np.testing.assert_array_equal(x[1].data.asnumpy(), np.float32(np.float32(-0.2) - np.float32(0.2) * np.float32(2)))
+
+
+@pytest.mark.parametrize("update_on_kvstore", [None, False])
+def test_reference_trainer_lr_sched(update_on_kvstore):
+    # test_gluon_trainer.py:283-320: FactorScheduler(2, 0.1); with two replicas every step counts ONCE
+    # (per-device updaters count per device id, optimizer.py:433-443: the replicas must sit on two devices)
+    if update_on_kvstore is False and mx.num_gpus() < 2:
+        pytest.skip("needs two GPUs")
+    x = _two_replicas()
+    freq, factor, lr = 2, 0.1, 1
+    sched = mx.lr_scheduler.FactorScheduler(freq, factor=factor, base_lr=lr)
+    trainer = mx.Trainer([x], "sgd", {"learning_rate": lr, "lr_scheduler": sched}, update_on_kvstore=update_on_kvstore)
+    for i in range(10):
+        _backward_of_w_plus_1(x)
+        trainer.step(1)
+        if i % freq == 0:
+            assert trainer.learning_rate == lr, (lr, trainer.learning_rate, i)
+            lr *= factor

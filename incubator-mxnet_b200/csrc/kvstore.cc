@@ -1733,6 +1733,7 @@ void KVStore::UpdaterStep(bool str_keys, const std::vector<int>& ikeys, const st
       << "UpdaterStep: keys / weights / grads differ in length";
   SetKeyType(str_keys ? kStringKey : kIntKey);
   std::vector<Group> groups;
+  std::vector<std::pair<int, NDArray>> sparse;
   for (size_t i = 0; i < n; ++i) {
     int key;
     if (str_keys) {
@@ -1748,11 +1749,14 @@ void KVStore::UpdaterStep(bool str_keys, const std::vector<int>& ikeys, const st
       key = ikeys[i];
     }
     const NDArray& w = weights[i];
-    MXKV_CHECK(w.stype() == kDefaultStorage && w.ctx().is_gpu()) << "UpdaterStep: dense GPU arrays only";
+    MXKV_CHECK(w.stype() == kDefaultStorage && w.ctx().is_gpu()) << "UpdaterStep: weights are dense GPU arrays";
     if (!bind_only) {
+      // a row_sparse gradient updates the rows it holds (sgd / sgd-momentum / adam; lazy or standard
+      // flavour as the optimizer says): the reference's per-device updater on Parameter(grad_stype='row_sparse')
       const NDArray& g = grads[i];
-      MXKV_CHECK(g.stype() == kDefaultStorage && g.ctx().is_gpu() && w.dev() == g.dev())
-          << "UpdaterStep: weight and gradient of index " << key << " must be dense arrays on the same GPU";
+      MXKV_CHECK((g.stype() == kDefaultStorage || g.stype() == kRowSparseStorage) && g.ctx().is_gpu() &&
+                 w.dev() == g.dev())
+          << "UpdaterStep: weight and gradient of index " << key << " must be arrays on the same GPU";
     }
     auto it = keys_.find(key);
     if (it == keys_.end()) {
@@ -1780,12 +1784,14 @@ void KVStore::UpdaterStep(bool str_keys, const std::vector<int>& ikeys, const st
     ks.local_world = 0;
     if (bind_only) continue;
     if (AdamWSkips()) { ks.count += 1; continue; }
+    if (grads[i].stype() == kRowSparseStorage) { sparse.emplace_back(key, grads[i]); continue; }
     Group grp;
     grp.key = key;
     grp.vals = {grads[i]};
     groups.push_back(grp);
   }
   if (!groups.empty()) ReduceUpdate(groups, false);
+  for (auto& kg : sparse) PushRowSparse(GetKey(kg.first), {kg.second});
 }
 
 NDArray KVStore::GetState(bool str_key, int ikey, const std::string& skey, int which) {

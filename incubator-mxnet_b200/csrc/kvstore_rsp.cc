@@ -45,7 +45,7 @@ void KVStore::InitRowSparseKey(KeyState& ks, const NDArray& v) {
   Runtime* rt = Runtime::Get();
   ProcessGroup* pg = PG();
   MXKV_CHECK(v.dtype() == kFloat32) << "row_sparse keys support float32 only";
-  MXKV_CHECK(v.shape().size() >= 2) << "row_sparse keys need at least 2 dimensions";
+  MXKV_CHECK(!v.shape().empty()) << "row_sparse keys need at least 1 dimension";
   const Context c = v.ctx();
   const int dev = pg ? pg->dev() : (c.is_gpu() ? c.dev_id : DefaultDevice());
   if (c.is_gpu()) rt->AcquireUser(c.dev_id);
@@ -100,17 +100,26 @@ void KVStore::PushRowSparse(KeyState& ks, const std::vector<NDArray>& vals) {
   ProcessGroup* pg = PG();
   const bool mp_mode = pg != nullptr;
   if (ks.stype != kRowSparseStorage) {
-    // Without an updater the stored value simply becomes the merged value, storage type included
-    // (`local = merged.Copy(...)` on a storage-type mismatch, kvstore_local.h:268-276; the reference's
-    // test_aggregator pushes row_sparse values to keys initialised dense).  The stored value is a
-    // dense-backed table either way, so the key only changes its label.
-    MXKV_CHECK(updater_ == nullptr && !opt_.enabled)
-        << "key " << ks.key << " was initialised dense; a row_sparse push with an updater / optimizer needs a "
-           "row_sparse key";
-    MXKV_CHECK(ks.dtype == kFloat32 && ks.shape.size() >= 2)
-        << "row_sparse values need a float32 key with at least 2 dimensions (key " << ks.key << ")";
+    MXKV_CHECK(ks.dtype == kFloat32 && !ks.shape.empty())
+        << "row_sparse values need a float32 key (key " << ks.key << ")";
     if (ks.local_world > 0) GatherLocal(ks);
-    ks.stype = kRowSparseStorage;
+    if (updater_ == nullptr && !opt_.enabled) {
+      // Without an updater the stored value simply becomes the merged value, storage type included
+      // (`local = merged.Copy(...)` on a storage-type mismatch, kvstore_local.h:268-276; the reference's
+      // test_aggregator pushes row_sparse values to keys initialised dense).  The stored value is a
+      // dense-backed table either way, so the key only changes its label.
+      ks.stype = kRowSparseStorage;
+    } else {
+      // Dense weight, row_sparse gradient (gluon Parameter(grad_stype='row_sparse') updated on the store,
+      // trainer.py:204-236; SGDUpdateDnsRspImpl / AdamLazyUpdate..., optimizer_op-inl.h:471-555,1305-1516):
+      // the updater sees (merged row_sparse, stored dense) and the key stays dense.  The rows are updated
+      // on every replica, each with its own complete optimizer state.
+      if (opt_.enabled && updater_ == nullptr && ks.state_world > 0) {
+        GatherState(ks);
+        ks.state_world = 0;
+        ks.state_devs.clear();
+      }
+    }
   }
   const int n_src = static_cast<int>(vals.size());
   MXKV_CHECK(n_src >= 1 && n_src <= kMaxSrc) << "push of " << n_src << " row_sparse values (max " << kMaxSrc << ")";
@@ -149,6 +158,17 @@ void KVStore::PushRowSparse(KeyState& ks, const std::vector<NDArray>& vals) {
     PublishNnz(v);
   }
   for (int d : work_devs) { touch(d); EnsureReplica(ks, d); }
+  if (fused) {
+    // optimizer state of every computing replica, brought up to date BEFORE this update is counted or any
+    // replica has run it (a replica whose GPU sat out earlier dense updates takes over a participant's state)
+    for (int d : work_devs) {
+      Replica& r = *FindReplica(ks, d);
+      EnsureState(ks, r, false);
+    }
+    for (int d : work_devs) SyncState(ks, *FindReplica(ks, d));
+    for (auto& r : ks.reps)
+      if (std::find(work_devs.begin(), work_devs.end(), r.dev) == work_devs.end()) r.state_fresh = false;
+  }
 
   if (fused) ks.count += 1;
   const float lr = fused ? KeyLR(ks) : 0.f;
@@ -247,7 +267,6 @@ void KVStore::PushRowSparse(KeyState& ks, const std::vector<NDArray>& vals) {
     A.lr = lr; A.wd = wd; A.rescale = opt_.rescale; A.clip = opt_.clip; A.momentum = opt_.momentum;
     A.beta1 = static_cast<float>(opt_.beta1); A.beta2 = static_cast<float>(opt_.beta2); A.eps = opt_.eps;
     if (fused) {
-      EnsureState(ks, r, false);
       A.s0 = r.s0.is_none() ? nullptr : static_cast<float*>(r.s0.data());
       A.s1 = r.s1.is_none() ? nullptr : static_cast<float*>(r.s1.data());
     }

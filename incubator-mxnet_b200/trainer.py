@@ -20,9 +20,13 @@ def _ptr(x):
     return x.data_ptr if isinstance(x, NDArray) else x.data_ptr()
 
 
+def _stype(x):
+    return x.stype if isinstance(x, NDArray) else "default"
+
+
 class Trainer(object):
-    def __init__(self, params, optimizer, optimizer_params=None, kvstore="device", update_on_kvstore=None,
-                 batched=True, symmetric=False):
+    def __init__(self, params, optimizer, optimizer_params=None, kvstore="device", compression_params=None,
+                 update_on_kvstore=None, batched=True, symmetric=False):
         self._params = [p if isinstance(p, (list, tuple)) else [p] for p in params]
         optimizer_params = dict(optimizer_params or {})
         self._scale = float(optimizer_params.get("rescale_grad", 1.0))
@@ -33,6 +37,7 @@ class Trainer(object):
             self._optimizer = _opt.create(optimizer, **optimizer_params)
         self._attach_params()
         self._kvstore_arg = kvstore
+        self._compression_params = compression_params
         self._update_on_kvstore_arg = update_on_kvstore
         self._kv_initialized = False
         self._kvstore = None
@@ -58,18 +63,53 @@ class Trainer(object):
         self._optimizer.set_learning_rate(lr)
 
     def _init_kvstore(self):
-        """trainer.py:188-277 (dense, single-machine rows of the decision table)."""
+        """trainer.py:188-277, single-machine rows of the decision table: row_sparse weights must be updated on
+        the store; dense weights with row_sparse gradients default to per-device updates; dense / dense follows
+        ``update_on_kvstore`` (default: MXNET_UPDATE_ON_KVSTORE, on; off for 'local' with a parameter above 16M
+        elements, model.py:88-130) as far as the store is capable of it.  Unlike the reference a store is kept
+        for a single replica per parameter as well: in one-process-per-GPU mode that replica is one of many, and
+        the fused update inside the store is this engine's fast path either way."""
+        import os
+        import numpy as np
         kv = self._kvstore_arg
-        if isinstance(kv, str):
-            kv = _kv.create(kv)
+        config_uok = self._update_on_kvstore_arg
+        sparse_weight = any(_stype(reps[0].data) != "default" for reps in self._params)
+        sparse_grad = any(getattr(reps[0], "grad", None) is not None and _stype(reps[0].grad) != "default"
+                          for reps in self._params)
+        if sparse_weight:
+            if isinstance(kv, str):
+                kv = _kv.create(kv)
+            elif not isinstance(kv, _kv.KVStore):
+                raise TypeError("Cannot create '%s' KVStore with row_sparse parameters. "
+                                "The type must be KVStore or str." % kv)
+            assert kv.is_capable(_kv.KVStoreBase.OPTIMIZER), "KVStore with sparse weight requires optimizer support."
+            if config_uok is False:
+                raise ValueError("Cannot set update_on_kvstore=False when sparse weights are present.")
+            uok = True
+        else:
+            uok = bool(int(os.getenv("MXNET_UPDATE_ON_KVSTORE", "1")))
+            if isinstance(kv, str):
+                name = kv
+                kv = _kv.create(kv)
+                if name == "local" and max(int(np.prod(_nd(reps[0].data).shape)) for reps in self._params) > (16 << 20):
+                    uok = False
+            elif kv is not None and not isinstance(kv, _kv.KVStoreBase):
+                raise TypeError("kvstore must be KVStore, str or None")
+            if kv is None:
+                uok = False
+            else:
+                uok = uok and bool(kv.is_capable(_kv.KVStoreBase.OPTIMIZER))
+            if sparse_grad:
+                uok = False                 # usually faster on one machine (trainer.py:204-236)
+                if kv is not None and not isinstance(kv, _kv.KVStore):
+                    raise ValueError("Cannot use {} for multi-device training with sparse gradients".format(type(kv)))
+            if config_uok is not None and kv is not None:
+                uok = config_uok
+            if uok and not kv.is_capable(_kv.KVStoreBase.OPTIMIZER):
+                if config_uok:
+                    raise ValueError("Please set update_on_kvstore=False when training with " + str(type(kv)))
+                uok = False
         self._kvstore = kv
-        uok = self._update_on_kvstore_arg
-        if kv is None:
-            uok = False
-        elif uok is None:
-            uok = kv.is_capable(_kv.KVStoreBase.OPTIMIZER)
-        elif uok and not kv.is_capable(_kv.KVStoreBase.OPTIMIZER):
-            raise ValueError("Please set update_on_kvstore=False when training with " + str(type(kv)))
         self._update_on_kvstore = uok
         # key lists in one call are this engine's extension of the plug-in API; a third-party store gets the
         # reference's call pattern, one key per call (trainer.py:155-176, 385-409)
@@ -79,16 +119,34 @@ class Trainer(object):
         else:
             self._weights = [[_nd(p.data) for p in reps] for reps in self._params]
         if kv is not None:
+            if self._compression_params:
+                kv.set_gradient_compression(self._compression_params)
             if uok:
                 kv.set_optimizer(self._optimizer)
-            # _init_params (trainer.py:155-176): broadcast(idx, w0, all_w)
-            idx = list(range(len(self._params)))
-            if self._batched or isinstance(kv, _kv.KVStore):
-                kv.broadcast(idx, [w[0] for w in self._weights], [w for w in self._weights])
+            # _init_params (trainer.py:155-176): broadcast(idx, w0, all_w); row_sparse weights are only stored
+            dense = [i for i, w in enumerate(self._weights) if w[0].stype == "default"]
+            for i, w in enumerate(self._weights):
+                if w[0].stype != "default":
+                    kv.init(i, w[0])
+            if dense and isinstance(kv, _kv.KVStore):
+                kv.broadcast(dense, [self._weights[i][0] for i in dense], [self._weights[i] for i in dense])
             else:
-                for i in idx:
+                for i in dense:
                     kv.broadcast(i, self._weights[i][0], self._weights[i])
         self._kv_initialized = True
+
+    def _row_sparse_pull(self, parameter, out, row_id, full_idx=False):
+        """trainer.py:310-324: the rows ``row_id`` of a row_sparse parameter (its index in ``params``, or the
+        parameter object) into ``out``; all rows through a plain pull when ``full_idx``."""
+        if not self._kv_initialized:
+            self._init_kvstore()
+        idx = parameter if isinstance(parameter, int) else \
+            next(i for i, reps in enumerate(self._params) if parameter is reps[0] or parameter is reps)
+        if full_idx:
+            assert row_id.size == (out[0] if isinstance(out, (list, tuple)) else out).shape[0]
+            self._kvstore.pull(idx, out=out, priority=-idx, ignore_sparse=False)
+        else:
+            self._kvstore.row_sparse_pull(idx, out=out, row_ids=row_id, priority=-idx)
 
     def _bind_symmetric(self):
         """One-process-per-GPU: move every parameter and its gradient into the engine's peer-mapped
@@ -118,6 +176,9 @@ class Trainer(object):
     def _bind_grads(self):
         self._grads = [[_nd(p.grad) for p in reps] for reps in self._params]
         self._grad_ptrs = [[_ptr(p.grad) for p in reps] for reps in self._params]
+        self._sparse_idx = [i for i, g in enumerate(self._grads) if g[0].stype != "default"]
+        held = set(self._sparse_idx)
+        self._dense_idx = [i for i in range(len(self._params)) if i not in held]
 
     def _allreduce_grads(self):
         """trainer.py:385-409, with every parameter in ONE call when ``batched`` (one launch per
@@ -126,12 +187,25 @@ class Trainer(object):
                                       for p, q in zip(reps, ptrs)):
             self._bind_grads()
         kv = self._kvstore
-        idx = list(range(len(self._params)))
+        idx = self._dense_idx if hasattr(self, "_dense_idx") else list(range(len(self._params)))
+        sparse = getattr(self, "_sparse_idx", [])
+        # row_sparse gradients: push and pull separately, parameter by parameter (trainer.py:392-401); the
+        # pull brings back the weights when the store updates, the reduced gradient otherwise, and nothing for a
+        # row_sparse weight (its rows are fetched on demand, _row_sparse_pull)
+        for i in sparse:
+            kv.push(i, self._grads[i], priority=-i)
+            if self._weights[i][0].stype == "default":
+                kv.pull(i, self._weights[i] if self._update_on_kvstore else self._grads[i], priority=-i,
+                        ignore_sparse=False)
+        if not idx:
+            return
         if self._batched:
+            grads = self._grads if not sparse else [self._grads[i] for i in idx]
             if self._update_on_kvstore:
-                kv.pushpull(idx, self._grads, out=self._weights, priority=0)
+                kv.pushpull(idx, grads, out=self._weights if not sparse else [self._weights[i] for i in idx],
+                            priority=0)
             else:
-                kv.pushpull(idx, self._grads, priority=0)
+                kv.pushpull(idx, grads, priority=0)
         else:
             for i in idx:
                 if self._update_on_kvstore:

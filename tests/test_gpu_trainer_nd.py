@@ -239,3 +239,97 @@ def test_reference_trainer_lr_sched(update_on_kvstore):
         if i % freq == 0:
             assert trainer.learning_rate == lr, (lr, trainer.learning_rate, i)
             lr *= factor
+
+
+class SparseParam(object):
+    """Parameter(stype=..., grad_stype=...) replica: the arrays carry the storage types"""
+
+    def __init__(self, shape, ctx, stype, grad_stype):
+        self.data = mx.nd.zeros(shape, ctx, stype=stype)
+        self.grad = mx.nd.zeros(shape, ctx, stype=grad_stype)
+        self.lr_mult = 1.0
+        self.wd_mult = 1.0
+
+    def set_grad_ones(self):
+        ones = mx.nd.ones(self.data.shape, self.grad.context)
+        (ones.tostype("row_sparse") if self.grad.stype == "row_sparse" else ones).copyto(self.grad)
+
+
+@pytest.mark.parametrize("kv", ["local", "device"])
+@pytest.mark.parametrize("stype,grad_stype,update_on_kv,expected", [
+    ("default", "default", True, True),
+    ("default", "default", False, False),
+    ("default", "default", None, True),
+    ("default", "row_sparse", None, False),
+    ("default", "row_sparse", True, True),
+    ("default", "row_sparse", False, False),
+    ("row_sparse", "row_sparse", None, True),
+    ("row_sparse", "row_sparse", False, ValueError),
+])
+def test_reference_trainer_sparse_kv(kv, stype, grad_stype, update_on_kv, expected):
+    # tests/python/unittest/test_gluon_trainer.py:247-281: the storage-type rows of the decision table; every
+    # variant ends at w = 0 - 0.1 * (1 + 1) on all ten rows
+    shape = (10, 1)
+    ndev = max(1, min(mx.num_gpus(), 2))
+    x = [SparseParam(shape, mx.gpu(d % ndev), stype, grad_stype) for d in range(2)]
+    trainer = mx.Trainer([x], "sgd", {"learning_rate": 0.1}, kvstore=kv, update_on_kvstore=update_on_kv)
+    all_rows = mx.nd.array(np.arange(10), dtype=np.int64)
+    if expected is ValueError:
+        with pytest.raises(ValueError):
+            trainer.step(1)
+        return
+    if stype == "row_sparse":                                   # list_row_sparse_data(all_rows) before forward
+        trainer._row_sparse_pull(0, [p.data for p in x], all_rows)
+        for p in x:
+            assert np.all(p.data.todense_numpy() == 0)
+    for p in x:
+        p.set_grad_ones()
+    trainer.step(1)
+    assert trainer._kvstore.type == kv
+    assert trainer._kv_initialized
+    assert trainer._update_on_kvstore is expected
+    mx.nd.waitall()
+    if stype == "default":
+        for p in x:
+            assert (p.data.asnumpy() == np.float32(-0.2)).all(), p.data.asnumpy()
+    else:
+        out = mx.nd.zeros(shape, mx.gpu(0), stype="row_sparse")
+        trainer._row_sparse_pull(0, out, all_rows)
+        assert (out.todense_numpy() == np.float32(-0.2)).all(), out.todense_numpy()
+        out2 = mx.nd.zeros(shape, mx.gpu(0), stype="row_sparse")
+        trainer._row_sparse_pull(x[0], out2, all_rows, full_idx=True)
+        assert (out2.todense_numpy() == np.float32(-0.2)).all()
+
+
+def test_reference_trainer_sparse_save_load(tmp_path):
+    # test_gluon_trainer.py:151-167: row_sparse weight and gradient on one context, update on the store,
+    # save / load, then the parameter's lr_mult is still consulted
+    x = [SparseParam((10, 1), mx.gpu(0), "row_sparse", "row_sparse")]
+    trainer = mx.Trainer([x], "sgd", {"learning_rate": 0.1})
+    all_rows = mx.nd.array(np.arange(10), dtype=np.int64)
+    trainer._row_sparse_pull(0, x[0].data, all_rows)
+    x[0].set_grad_ones()
+    trainer.step(1)
+    assert trainer._kvstore._optimizer._get_lr(0) == 0.1
+    f = str(tmp_path / "test_trainer_sparse_save_load.states")
+    trainer.save_states(f)
+    trainer.load_states(f)
+    x[0].lr_mult = 2.0
+    assert trainer._kvstore._optimizer._get_lr(0) == 0.2
+    x[0].set_grad_ones()
+    trainer.step(1)
+    trainer._row_sparse_pull(0, x[0].data, all_rows)
+    want = np.float32(np.float32(-0.1) - np.float32(0.2) * np.float32(1))
+    assert (x[0].data.todense_numpy() == want).all(), x[0].data.todense_numpy()
+
+
+def test_reference_trainer_sparse_grad_single_context():
+    # test_gluon_trainer.py:48-60: 1-D parameter, row_sparse gradient, sgd momentum 0.5 lr 1 -> -1.  (The
+    # reference creates no store for a single context; this engine keeps one -- see Trainer._init_kvstore --
+    # and the result is the same.)
+    x = [SparseParam((10,), mx.gpu(0), "default", "row_sparse")]
+    trainer = mx.Trainer([x], "sgd", {"learning_rate": 1.0, "momentum": 0.5})
+    x[0].set_grad_ones()
+    trainer.step(1)
+    assert trainer._update_on_kvstore is False
+    assert (x[0].data.asnumpy() == -1).all(), x[0].data.asnumpy()

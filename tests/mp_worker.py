@@ -165,6 +165,26 @@ def main():
         assert np.array_equal(out.indices.asnumpy(), want.indices), "rsp idx"
         assert bits_equal(out.data.asnumpy(), want.data.reshape(-1, L)), ("rsp", step)
 
+    # 5b. a DENSE weight updated on the store by alternating dense (sharded) and row_sparse gradients
+    kw = dict(learning_rate=0.01, wd=1e-3, lazy_update=False)
+    kv5b = mx.kv.create("device")
+    kv5b.init("w", mx.nd.array(w0, ctx))
+    kv5b.set_optimizer(mx.optimizer.Adam(**kw))
+    okv = O.OracleKVStore("device")
+    okv.init("w", w0.copy())
+    okv.set_optimizer(O.OracleOptimizer("adam", **kw))
+    for step, kind in enumerate(["dense", "rsp", "dense", "rsp", "rsp"]):
+        if kind == "rsp":
+            i, v = rsp(10 + step, rank)
+            kv5b.push("w", mx.nd.row_sparse_array((v, i), shape=shape, ctx=ctx))
+            okv.push("w", [O.RowSparse(*rsp(10 + step, r), shape) for r in range(world)])
+        else:
+            kv5b.push("w", mx.nd.array(data(40 + step, shape, rank), ctx))
+            okv.push("w", [data(40 + step, shape, r) for r in range(world)])
+        o = mx.nd.empty(shape, ctx)
+        kv5b.pull("w", out=o)
+        assert bits_equal(o.asnumpy(), okv.local["w"]), ("dense key, rsp grads", step, kind)
+
     # 6. 2-bit gradient compression with error feedback, one code stream per rank
     E, thr = 30000, 0.5
     kv6 = mx.kv.create("device")

@@ -677,3 +677,61 @@ def test_sharding_threshold_and_chunking_change_between_calls():
     finally:
         check_call(_LIB.MXKVB200SetTwoShotBytes(ctypes.c_int64(262144)))
         check_call(_LIB.MXKVB200SetTuning(ctypes.c_int64(8192), 512, 0, -1))
+
+
+@pytest.mark.parametrize("seed", list(range(12 + _EXTRA)))
+def test_randomized_dense_keys_with_row_sparse_gradients(seed):
+    """Dense weights updated on the store by a random mix of dense and row_sparse gradients (Parameter(grad_stype=
+    'row_sparse') next to dense parameters): random device subsets and host values for both kinds, keys on either
+    side of the sharding threshold, one optimizer state serving both kinds of update."""
+    _need(2)
+    ngpu = min(mx.num_gpus(), 8)
+    rng = _rng(12000 + seed)
+    optname, kw = [("sgd", dict(learning_rate=0.1, momentum=0.9, wd=1e-3, lazy_update=True)),
+                   ("sgd", dict(learning_rate=0.1, wd=1e-3, lazy_update=False)),
+                   ("adam", dict(learning_rate=0.01, wd=1e-3, lazy_update=True)),
+                   ("adam", dict(learning_rate=0.01, wd=1e-3, lazy_update=False)),
+                   ("sgd", dict(learning_rate=0.05, momentum=0.5, lazy_update=False, rescale_grad=0.25,
+                                clip_gradient=0.4))][seed % 5]
+    shapes = [(int(rng.choice([30, 200])), int(rng.choice([4, 6]))), (1100, 64), (int(rng.choice([17, 500])),)]
+    keys = ["k%d" % i for i in range(len(shapes))]
+    w0 = [rng.uniform(-1, 1, s).astype(np.float32) for s in shapes]
+
+    def ctx_of(d):
+        return mx.cpu() if d < 0 else mx.gpu(d)
+
+    kv = mx.kv.create(["device", "local"][seed % 2])
+    kv.init(keys, [mx.nd.array(w, ctx_of(int(rng.integers(-1, ngpu)))) for w in w0])
+    kv.set_optimizer(mx.optimizer.create(optname, **kw))
+    okv = O.OracleKVStore(["device", "local"][seed % 2])
+    okv.init(keys, [w.copy() for w in w0])
+    okv.set_optimizer(O.OracleOptimizer(optname, **kw))
+    for step in range(8):
+        k = int(rng.integers(len(keys)))
+        shape, rows = shapes[k], shapes[k][0]
+        if rng.random() < 0.55:
+            devs = [int(x) for x in rng.choice(np.arange(-1, ngpu), size=int(rng.integers(1, min(5, ngpu + 2))),
+                                               replace=False)]
+            parts = []
+            for _ in devs:
+                nnz = int(rng.integers(0, rows // 2 + 1))
+                idx = np.sort(rng.choice(rows, nnz, replace=False)).astype(np.int64)
+                parts.append((idx, rng.uniform(-1, 1, (nnz,) + shape[1:]).astype(np.float32)))
+            kv.push(keys[k], [mx.nd.row_sparse_array((v, i), shape=shape, ctx=ctx_of(d))
+                              for (i, v), d in zip(parts, devs)])
+            okv.push(keys[k], [O.RowSparse(i, v, shape) for i, v in parts])
+            what = ("rsp", devs)
+        else:
+            devs = [int(x) for x in rng.choice(ngpu, size=int(rng.integers(1, ngpu + 1)), replace=False)]
+            gs = [rng.uniform(-1, 1, shape).astype(np.float32) for _ in devs]
+            vals = [mx.nd.array(g, mx.gpu(d)) for g, d in zip(gs, devs)]
+            if rng.random() < 0.5:
+                kv.push(keys[k], vals)
+            else:
+                kv.pushpull(keys[k], vals, out=[mx.nd.empty(shape, mx.gpu(d)) for d in devs[:3]])
+            okv.push(keys[k], gs)
+            what = ("dense", devs)
+        d = int(rng.integers(-1, ngpu))
+        o = mx.nd.empty(shape, ctx_of(d))
+        kv.pull(keys[k], out=o)
+        assert _bits_equal(o.asnumpy(), okv.local[keys[k]]), (optname, kw, seed, step, k, what, d)

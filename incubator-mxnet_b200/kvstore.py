@@ -130,6 +130,7 @@ class KVStore(KVStoreBase):
         self._last_lr = None
         self._keys = set()
         self._mults = {}
+        self._synced = set()
 
     def __del__(self):
         try:
@@ -152,8 +153,15 @@ class KVStore(KVStoreBase):
             opt_ = self._optimizer
             uniq = list(dict.fromkeys(keys))
             cnt, begin, top = opt_._index_update_count, opt_.begin_num_update, opt_.num_update
+            synced = self._synced
             for k in uniq:                      # Optimizer._update_count, inlined: hundreds of keys per step
                 c = cnt.get(k, begin) + 1
+                if k not in synced and k in self._keys:
+                    # the update count t of the bias corrections is the OPTIMIZER's (begin_num_update, an
+                    # optimizer that has already been stepping elsewhere, states loaded without their
+                    # optimizer: optimizer.py:445-462, adam.py:166-175): the engine's count follows it
+                    self._set_count(k, c - 1)
+                    synced.add(k)
                 cnt[k] = c
                 if c > top:
                     top = c
@@ -255,6 +263,7 @@ class KVStore(KVStoreBase):
         """Recognised optimizers run fused inside the reduce kernel; anything else goes through
         the Python updater callback like the reference (kvstore.py:559-606)."""
         self._optimizer = optimizer
+        self._synced = set()
         if getattr(optimizer, "fused_name", None):
             kw = optimizer.fused_kwargs()
             keys = list(kw.keys())
@@ -274,6 +283,12 @@ class KVStore(KVStoreBase):
         else:
             self._fused = False
             self._set_updater(opt.get_updater(optimizer, native=False))
+
+    def _set_count(self, key, count):
+        if isinstance(key, str):
+            check_call(_LIB.MXKVB200SetUpdateCount(self.handle, 0, c_str(key), ctypes.c_int64(count)))
+        else:
+            check_call(_LIB.MXKVB200SetUpdateCount(self.handle, int(key), None, ctypes.c_int64(count)))
 
     def _sync_mults(self, keys):
         """``Parameter.lr_mult`` / ``wd_mult`` are read at every update by the reference
@@ -409,10 +424,10 @@ class KVStore(KVStoreBase):
                         check_call(_LIB.MXKVB200SetState(self.handle, 0, c_str(k), which, v.handle))
                     else:
                         check_call(_LIB.MXKVB200SetState(self.handle, int(k), None, which, v.handle))
-            if isinstance(k, str):
-                check_call(_LIB.MXKVB200SetUpdateCount(self.handle, 0, c_str(k), ctypes.c_int64(ent["count"])))
-            else:
-                check_call(_LIB.MXKVB200SetUpdateCount(self.handle, int(k), None, ctypes.c_int64(ent["count"])))
+            self._set_count(k, ent["count"])
+        # whatever the file says, the next update counts from the current optimizer's table (updater.py:118-127
+        # restores the optimizer only when it was dumped along)
+        self._synced -= set(payload["states"])
         _nd.waitall()
 
 

@@ -414,6 +414,8 @@ class NativeUpdater(object):
             self.optimizer._update_count(i)
         self._sync()
         self._kv._sync_mults(index)
+        before = {i: self.optimizer._index_update_count[i] - 1 for i in dict.fromkeys(index)
+                  if i not in self._kv._synced}
         n = len(index)
         use_str = isinstance(index[0], str)
         wh = (ctypes.c_void_p * n)(*[w.handle.value for w in weight])
@@ -427,6 +429,13 @@ class NativeUpdater(object):
                 self._kv._load_fused_states(self._pending, only=set(have))
                 for i in have:
                     del self._pending["states"][i]
+                    before[i] = self.optimizer._index_update_count[i] - 1
+        if before:                       # the engine counts from where the optimizer stands (see KVStore._advance_counts)
+            if not set(before) <= self._kv._keys:
+                check_call(fn(self._kv.handle, n, keys, wh, None))          # make the indices known first
+            for i, c in before.items():
+                self._kv._set_count(i, c)
+                self._kv._synced.add(i)
         check_call(fn(self._kv.handle, n, keys, wh, gh))
         self._kv._keys.update(index)
 

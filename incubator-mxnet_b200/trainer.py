@@ -27,6 +27,10 @@ def _stype(x):
 class Trainer(object):
     def __init__(self, params, optimizer, optimizer_params=None, kvstore="device", compression_params=None,
                  update_on_kvstore=None, batched=True, symmetric=False):
+        if isinstance(params, dict):               # trainer.py:80-84: a dict is taken in the order of its keys
+            params = [params[k] for k in sorted(params.keys())]
+        if not isinstance(params, (list, tuple)):
+            raise ValueError("First argument must be a list or dict of Parameters, got %s." % type(params))
         self._params = [p if isinstance(p, (list, tuple)) else [p] for p in params]
         optimizer_params = dict(optimizer_params or {})
         self._scale = float(optimizer_params.get("rescale_grad", 1.0))
@@ -55,6 +59,21 @@ class Trainer(object):
         if pd:
             self._optimizer.param_dict = pd
 
+    def _reset_kvstore(self):
+        """trainer.py:178-186: forget the store (and the optimizer state it holds); the next step creates it
+        again and broadcasts the parameters as they are then -- what loading a checkpoint into the
+        parameters triggers in the reference."""
+        if self._kvstore is not None and "dist" in self._kvstore.type:
+            raise RuntimeError("Cannot reset distributed KVStore.")
+        self._kv_initialized = False
+        self._kvstore = None
+        self._update_on_kvstore = None
+        self._grads = None
+
+    @property
+    def optimizer(self):
+        return self._optimizer
+
     @property
     def learning_rate(self):
         return self._optimizer.learning_rate
@@ -68,7 +87,10 @@ class Trainer(object):
         ``update_on_kvstore`` (default: MXNET_UPDATE_ON_KVSTORE, on; off for 'local' with a parameter above 16M
         elements, model.py:88-130) as far as the store is capable of it.  Unlike the reference a store is kept
         for a single replica per parameter as well: in one-process-per-GPU mode that replica is one of many, and
-        the fused update inside the store is this engine's fast path either way."""
+        the fused update inside the store is this engine's fast path either way.  For the same reason the
+        reference's ``optimizer.aggregate_num > 1 -> update_on_kvstore=False`` rule (trainer.py:114-119) is not
+        applied: it exists because only the per-device updaters can aggregate tensors there, while this store
+        updates every key of a call in one launch (sequence)."""
         import os
         import numpy as np
         kv = self._kvstore_arg

@@ -409,8 +409,9 @@ class OracleOptimizer(object):
     def __init__(self, name, learning_rate=None, wd=0.0, rescale_grad=1.0, clip_gradient=None,
                  momentum=0.0, beta1=0.9, beta2=0.999, epsilon=None, eta=None, multi_precision=False,
                  lr_mult=None, wd_mult=None, lazy_update=True, lower_bound=None, upper_bound=None,
-                 bias_correction=True, norm_mode="seq", no_trust=(), correct_bias=True):
+                 bias_correction=True, norm_mode="seq", no_trust=(), correct_bias=True, begin_num_update=0):
         self.name = name.lower()
+        self.begin_num_update = begin_num_update     # optimizer.py:111-112, 445-462
         self.lower_bound, self.upper_bound, self.bias_correction = lower_bound, upper_bound, bias_correction
         self.norm_mode = norm_mode
         self.correct_bias = correct_bias    # AdamW (adamW.py:80-88)
@@ -445,7 +446,7 @@ class OracleOptimizer(object):
         """Updater.__call__ (updater.py:39-93): create state on first sight, then one
         fused step.  ``weight`` is a float32 ndarray updated in place; ``grad`` is a
         float32 ndarray or RowSparse."""
-        self.count[index] = t = self.count.get(index, 0) + 1
+        self.count[index] = t = self.count.get(index, self.begin_num_update) + 1
         lr, wd = self._lr(index), self._wd(index)
         n = self.name
         sparse = isinstance(grad, RowSparse)

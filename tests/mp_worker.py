@@ -114,7 +114,7 @@ def main():
         if optname == "adam":
             # sharded state: save on every rank (gathers), reload into a fresh store, continue
             f = os.path.join(tempfile.gettempdir(), "mxkv_states_%d_%d" % (world, rank))
-            kv2.save_optimizer_states(f)
+            kv2.save_optimizer_states(f, dump_optimizer=True)     # with its update counts
             mids = [o.asnumpy() for o in outs]
             kv3 = mx.kv.create("device")
             kv3.init(ks, [mx.nd.array(m, ctx) for m in mids])

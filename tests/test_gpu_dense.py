@@ -289,10 +289,60 @@ def test_save_load_optimizer_states(tmp_path):
     kv1 = mx.kv.create("device"); kv1.init(0, mx.nd.array(w0, mx.gpu(0))); kv1.set_optimizer(mx.optimizer.Adam(**kw))
     run(kv1, 2, 1)
     f = str(tmp_path / "states")
-    kv1.save_optimizer_states(f)
+    kv1.save_optimizer_states(f, dump_optimizer=True)     # the optimizer carries the update counts
     w_mid = mx.nd.empty((E,), mx.gpu(0)); kv1.pull(0, out=w_mid)
     ref = run(kv1, 2, 2)
     kv2 = mx.kv.create("device"); kv2.init(0, w_mid); kv2.set_optimizer(mx.optimizer.Adam(**kw))
     kv2.load_optimizer_states(f)
     got = run(kv2, 2, 2)
     assert_bits_equal(got, ref)
+
+
+def test_update_count_follows_the_python_optimizer(tmp_path):
+    """The t of Adam's bias correction is the optimizer's per-index update count (adam.py:166-175 via
+    optimizer.py:445-462): it starts at begin_num_update, carries over when an optimizer that has already been
+    stepping is handed to another store, and is NOT restored by states saved without their optimizer
+    (updater.py:118-127)."""
+    rng = np.random.default_rng(31)
+    E = 1000
+    w0 = rng.uniform(-1, 1, E).astype(np.float32)
+    gs = [rng.uniform(-1, 1, E).astype(np.float32) for _ in range(6)]
+    kw = dict(learning_rate=0.01, begin_num_update=7)
+
+    def push(kv, g):
+        kv.push(3, mx.nd.array(g, mx.gpu(0)))
+        o = mx.nd.empty((E,), mx.gpu(0))
+        kv.pull(3, out=o)
+        return o.asnumpy()
+
+    kv = mx.kv.create("device")
+    kv.init(3, mx.nd.array(w0, mx.gpu(0)))
+    opt = mx.optimizer.Adam(**kw)
+    kv.set_optimizer(opt)
+    oopt = O.OracleOptimizer("adam", **kw)
+    ow = w0.copy()
+    for g in gs[:2]:
+        oopt.update(3, ow, g)
+        assert_bits_equal(push(kv, g), ow, "t = 8, 9")
+    assert opt._index_update_count[3] == 9
+    # the same optimizer object on a fresh store: t goes on at 10 while the moments restart from zero
+    kv2 = mx.kv.create("device")
+    kv2.init(3, mx.nd.array(ow, mx.gpu(0)))
+    kv2.set_optimizer(opt)
+    oopt.states.pop(3, None)
+    for g in gs[2:4]:
+        oopt.update(3, ow, g)
+        assert_bits_equal(push(kv2, g), ow, "t = 10, 11 on a fresh store")
+    # states saved WITHOUT the optimizer, loaded into a store whose optimizer starts from scratch: the moments come
+    # back, t restarts at 1
+    f = str(tmp_path / "adam.states")
+    kv2.save_optimizer_states(f)
+    kv3 = mx.kv.create("device")
+    kv3.init(3, mx.nd.array(ow, mx.gpu(0)))
+    kv3.set_optimizer(mx.optimizer.Adam(learning_rate=0.01))
+    kv3.load_optimizer_states(f)
+    o3 = O.OracleOptimizer("adam", learning_rate=0.01)
+    o3.states[3] = oopt.states[3]
+    for g in gs[4:]:
+        o3.update(3, ow, g)
+        assert_bits_equal(push(kv3, g), ow, "loaded moments, t from 1")

@@ -273,7 +273,7 @@ def test_checkpoint_after_device_set_change(tmp_path):
         kv.push(0, [mx.nd.array(x, mx.gpu(d)) for d, x in enumerate(g)])
         okv.push(0, g)
     f = str(tmp_path / "adam.states")
-    kv.save_optimizer_states(f)
+    kv.save_optimizer_states(f, dump_optimizer=True)      # the optimizer carries the update counts
     mid = mx.nd.empty((E,), mx.gpu(0)); kv.pull(0, out=mid)
     kv2 = mx.kv.create("device")
     kv2.init(0, mx.nd.array(mid.asnumpy(), mx.gpu(1)))
@@ -502,7 +502,7 @@ def test_randomized_optimizers_store_types_and_checkpoints(seed, tmp_path):
     for step in range(8):
         if step == reload_at:
             f = str(tmp_path / ("states_%d" % seed))
-            kv.save_optimizer_states(f)
+            kv.save_optimizer_states(f, dump_optimizer=True)      # with its update counts
             cur = []
             for k, e in zip(keys, sizes):
                 o = mx.nd.empty((e,), mx.cpu())

@@ -333,3 +333,24 @@ def test_reference_trainer_sparse_grad_single_context():
     trainer.step(1)
     assert trainer._update_on_kvstore is False
     assert (x[0].data.asnumpy() == -1).all(), x[0].data.asnumpy()
+
+
+@pytest.mark.parametrize("kv", ["local", "device"])
+def test_reference_trainer_reset_kv(kv):
+    # test_gluon_trainer.py:213-245: parameters loaded from a checkpoint after the first step drop the store;
+    # the next step creates it again from the loaded values: 0 - 0.1 * 2 = -0.2 both times
+    x = _two_replicas((10, 1))
+    trainer = mx.Trainer({"x": x}, "sgd", {"learning_rate": 0.1}, kvstore=kv)
+    saved = x[0].data.asnumpy().copy()
+    _backward_of_w_plus_1(x)
+    trainer.step(1)
+    assert trainer._kvstore.type == kv
+    mx.nd.waitall()
+    for p in x:                              # x._load_init(...) -> trainer._reset_kvstore()
+        p.data[:] = saved
+    trainer._reset_kvstore()
+    assert trainer._kvstore is None and trainer._kv_initialized is False
+    _backward_of_w_plus_1(x)
+    trainer.step(1)
+    assert (x[0].data.asnumpy() == np.float32(-0.2)).all(), x[0].data.asnumpy()
+    assert (x[1].data.asnumpy() == np.float32(-0.2)).all()

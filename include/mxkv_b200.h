@@ -126,6 +126,12 @@ MXKV_DLL int MXKVStoreBarrier(KVStoreHandle handle);                            
 MXKV_DLL int MXKVStoreSetBarrierBeforeExit(KVStoreHandle handle, const int barrier_before_exit); /* :2777 */
 MXKV_DLL int MXKVStoreGetNumDeadNode(KVStoreHandle handle, const int node_id, int* number,
                                      const int timeout_sec);                             /* c_api.h:2822 */
+/* Server-side entry points: single-node stores take them as no-ops, exactly like KVStore::RunServer /
+ * SendCommandToServers of the local store (include/mxnet/kvstore.h:432,466). */
+typedef void (MXKVStoreServerController)(int head, const char* body, void* controller_handle); /* c_api.h:2786 */
+MXKV_DLL int MXKVStoreRunServer(KVStoreHandle handle, MXKVStoreServerController controller,
+                                void* controller_handle);                                /* c_api.h:2797 */
+MXKV_DLL int MXKVStoreSendCommmandToServers(KVStoreHandle handle, int cmd_id, const char* cmd_body); /* :2808 */
 
 /* ---- B200 extensions ------------------------------------------------------ */
 /* Fused optimizer: what Python's Updater + sgd_update/adam_update ops do per key in the

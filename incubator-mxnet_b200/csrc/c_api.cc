@@ -434,6 +434,18 @@ int MXKVStoreGetNumDeadNode(KVStoreHandle handle, const int node_id, int* number
   API_END();
 }
 
+int MXKVStoreRunServer(KVStoreHandle handle, MXKVStoreServerController controller, void* controller_handle) {
+  API_BEGIN();
+  (void)KV(handle); (void)controller; (void)controller_handle;   // kvstore.h:466: a no-op for single-node stores
+  API_END();
+}
+
+int MXKVStoreSendCommmandToServers(KVStoreHandle handle, int cmd_id, const char* cmd_body) {
+  API_BEGIN();
+  (void)KV(handle); (void)cmd_id; (void)cmd_body;                // kvstore.h:432: a no-op for single-node stores
+  API_END();
+}
+
 // ---------------------------------------------------------------------------
 // extensions
 // ---------------------------------------------------------------------------

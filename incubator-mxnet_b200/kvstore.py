@@ -334,6 +334,10 @@ class KVStore(KVStoreBase):
             self._optimizer.num_update = max([self._optimizer.begin_num_update] + list(cnt.values()))
         return bool(out.value)
 
+    def _send_command_to_servers(self, head, body):
+        """kvstore.py:714-729; a no-op for single-node stores (include/mxnet/kvstore.h:432)."""
+        check_call(_LIB.MXKVStoreSendCommmandToServers(self.handle, ctypes.c_int(head), c_str(body)))
+
     def _sync_lr(self):
         if self._fused and self._optimizer is not None:
             lr = self._optimizer.learning_rate

@@ -50,6 +50,13 @@ def test_host_only_entry_points():
     w = ctypes.c_int()
     check_call(_LIB.MXKVStoreIsWorkerNode(ctypes.byref(w)))
     assert w.value == 1
+    # server-side entry points are no-ops of a single-node store (include/mxnet/kvstore.h:432,466)
+    kv = mx.kv.create("device")
+    kv._send_command_to_servers(0, "")
+    check_call(_LIB.MXKVStoreRunServer(kv.handle, None, None))
+    n = ctypes.c_int(-1)
+    check_call(_LIB.MXKVStoreGetNumDeadNode(kv.handle, 0, ctypes.byref(n), 60))
+    assert n.value == 0
 
 
 def test_error_contract_and_key_rules_without_gpu():

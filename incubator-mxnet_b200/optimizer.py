@@ -92,8 +92,16 @@ class Optimizer(object):
         self._index_update_count = self._all_index_update_counts[device_id]
 
     def _update_count(self, index):
-        self._index_update_count[index] = self._index_update_count.get(index, self.begin_num_update) + 1
-        self.num_update = max(self._index_update_count[index], self.num_update)
+        """optimizer.py:445-462; ``index`` may be a list"""
+        for idx in (index if isinstance(index, (list, tuple)) else [index]):
+            self._index_update_count[idx] = self._index_update_count.get(idx, self.begin_num_update) + 1
+            self.num_update = max(self._index_update_count[idx], self.num_update)
+
+    def _get_lrs(self, indices):
+        return [self._get_lr(i) for i in indices]
+
+    def _get_wds(self, indices):
+        return [self._get_wd(i) for i in indices]
 
     def _mult(self, table, attr, index):
         """Per-parameter multiplier in the reference's order of precedence (optimizer.py:479-487,518-525):
@@ -136,12 +144,50 @@ class Optimizer(object):
             kw["clip_gradient"] = self.clip_gradient
         return kw
 
-    # non-fused path (torch ops on views of the native arrays)
+    # ---- the non-fused path: the reference's protocol for optimizers written in Python (optimizer.py:214-352),
+    # which is what a user-defined Optimizer subclass implements.  Everything takes LISTS; ``step`` counts the
+    # update itself (``self._update_count(indices)``) before it reads learning rates.
+    use_fused_step = False
+
     def create_state(self, index, weight):
         return None
 
-    def step(self, index, weight, grad, state):
+    def create_state_multi_precision(self, index, weight):
+        """optimizer.py:214-243: a float32 master copy in front of the state for float16 weights"""
+        if self.multi_precision and weight.dtype == np.float16:
+            master = weight.astype(np.float32)
+            return (master, self.create_state(index, master))
+        return self.create_state(index, weight)
+
+    def step(self, indices, weights, grads, states):
         raise NotImplementedError()
+
+    def fused_step(self, indices, weights, grads, states):
+        raise NotImplementedError()
+
+    def update(self, indices, weights, grads, states):
+        """optimizer.py:287-318"""
+        if not self.use_fused_step:
+            self.step(indices, weights, grads, states)
+        else:
+            self.fused_step(indices, weights, grads, states)
+
+    def update_multi_precision(self, indices, weights, grads, states):
+        """optimizer.py:320-352"""
+        masters, inner, grads32 = [], [], []
+        for weight, grad, state in zip(weights, grads, states):
+            if self.multi_precision and weight.dtype == np.float16:
+                masters.append(state[0])
+                inner.append(state[1])
+                grads32.append(grad.astype(np.float32))
+            else:
+                masters.append(weight)
+                inner.append(state)
+                grads32.append(grad)
+        self.update(indices, masters, grads32, inner)
+        for master, weight in zip(masters, weights):
+            if self.multi_precision and weight.dtype == np.float16:
+                weight[:] = master.asnumpy().astype(np.float16)
 
 
 register = Optimizer.register
@@ -176,15 +222,17 @@ class SGD(Optimizer):
         import torch
         return torch.zeros_like(weight.as_torch(), dtype=torch.float32) if self.momentum != 0.0 else None
 
-    def step(self, index, weight, grad, state):          # sgd.py:118-154
-        w, g = weight.as_torch(), grad.as_torch()
-        lr = self._get_lr(index)
-        g = _prep_grad(self, index, w, g)
-        if state is not None:
-            state.mul_(self.momentum).sub_(lr * g)
-            w.add_(state)
-        else:
-            w.sub_(lr * g)
+    def step(self, indices, weights, grads, states):     # sgd.py:118-154
+        self._update_count(indices)
+        lrs = self._get_lrs(indices)
+        for index, weight, grad, state, lr in zip(indices, weights, grads, states, lrs):
+            w, g = weight.as_torch(), grad.as_torch()
+            g = _prep_grad(self, index, w, g)
+            if state is not None:
+                state.mul_(self.momentum).sub_(lr * g)
+                w.add_(state)
+            else:
+                w.sub_(lr * g)
 
 
 @register
@@ -206,16 +254,19 @@ class Adam(Optimizer):
         w = weight.as_torch()
         return (torch.zeros_like(w, dtype=torch.float32), torch.zeros_like(w, dtype=torch.float32))
 
-    def step(self, index, weight, grad, state):          # adam.py:107-147
+    def step(self, indices, weights, grads, states):     # adam.py:107-147
         import torch
-        w, g = weight.as_torch(), grad.as_torch()
-        t = self._index_update_count[index]
-        lr = self._get_lr(index) * math.sqrt(1. - self.beta2 ** t) / (1. - self.beta1 ** t)
-        g = _prep_grad(self, index, w, g)
-        mean, var = state
-        mean.mul_(self.beta1).add_((1. - self.beta1) * g)
-        var.mul_(self.beta2).add_((1. - self.beta2) * g * g)
-        w.sub_(lr * mean / (torch.sqrt(var) + self.epsilon))
+        self._update_count(indices)
+        lrs = self._get_lrs(indices)
+        for index, weight, grad, state, lr in zip(indices, weights, grads, states, lrs):
+            w, g = weight.as_torch(), grad.as_torch()
+            t = self._index_update_count[index]
+            lr = lr * math.sqrt(1. - self.beta2 ** t) / (1. - self.beta1 ** t)
+            g = _prep_grad(self, index, w, g)
+            mean, var = state
+            mean.mul_(self.beta1).add_((1. - self.beta1) * g)
+            var.mul_(self.beta2).add_((1. - self.beta2) * g * g)
+            w.sub_(lr * mean / (torch.sqrt(var) + self.epsilon))
 
 
 @register
@@ -330,14 +381,23 @@ class Test(Optimizer):
     def create_state(self, index, weight):
         return None
 
-    def step(self, index, weight, grad, state):
-        w, g = weight.as_torch(), grad.as_torch()
-        w.sub_(self._get_lr(index) * (self.rescale_grad * g + self._get_wd(index) * w))
+    def step(self, indices, weights, grads, states):
+        self._update_count(indices)
+        for index, weight, grad in zip(indices, weights, grads):
+            w, g = weight.as_torch(), grad.as_torch()
+            w.sub_(self._get_lr(index) * (self.rescale_grad * g + self._get_wd(index) * w))
 
 
 def _device_id(weight):
     ctx = getattr(weight, "context", None)
     return getattr(ctx, "device_id", 0) if ctx is not None else 0
+
+
+class _SavedNDArray(object):
+    """an engine array inside a pickled Updater state"""
+
+    def __init__(self, value, dev_type, dev_id):
+        self.value, self.dev_type, self.dev_id = value, dev_type, dev_id
 
 
 class Updater(object):
@@ -346,21 +406,37 @@ class Updater(object):
     def __init__(self, optimizer):
         self.optimizer = optimizer
         self.states = {}
+        self.states_synced = {}
 
     def __call__(self, index, grad, weight):
-        self.optimizer._set_current_context(_device_id(weight))          # updater.py:50-51
-        if index not in self.states:
-            self.states[index] = self.optimizer.create_state(index, weight)
-        self.optimizer._update_count(index)
-        self.optimizer.step(index, weight, grad, self.states[index])
+        """updater.py:39-93: single values or lists; states are created on first sight with
+        ``create_state_multi_precision``; the optimizer's ``update_multi_precision`` does the rest (its
+        ``step`` counts the update)."""
+        if not isinstance(index, (list, tuple)):
+            indices, grads, weights = [index], [grad], [weight]
+        else:
+            indices, grads, weights = list(index), list(grad), list(weight)
+        if weights:
+            self.optimizer._set_current_context(_device_id(weights[0]))  # updater.py:50-51
+        for i, idx in enumerate(indices):
+            if isinstance(idx, bytes):
+                indices[i] = idx = idx.decode()
+            if idx not in self.states:
+                self.states[idx] = self.optimizer.create_state_multi_precision(idx, weights[i])
+                self.states_synced[idx] = True
+        self.optimizer.update_multi_precision(indices, weights, grads, [self.states[i] for i in indices])
 
     def get_states(self, dump_optimizer=False):
         def host(s):
             if s is None:
                 return None
-            if isinstance(s, tuple):
+            if isinstance(s, (tuple, list)):
                 return tuple(host(x) for x in s)
-            return s.detach().cpu().numpy()
+            if isinstance(s, NDArray):                       # e.g. a multi-precision master copy
+                return _SavedNDArray(s.asnumpy(), s.context.device_typeid, s.context.device_id)
+            if hasattr(s, "detach"):
+                return s.detach().cpu().numpy()
+            return s
         states = {k: host(v) for k, v in self.states.items()}
         return pickle.dumps((states, self.optimizer) if dump_optimizer else states)
 
@@ -375,9 +451,15 @@ class Updater(object):
                 return None
             if isinstance(s, tuple):
                 return tuple(dev(x) for x in s)
-            return torch.from_numpy(np.asarray(s))
+            if isinstance(s, _SavedNDArray):
+                from . import ndarray as _ndm
+                from .context import Context
+                return _ndm.array(s.value, Context(Context.devtype2str[s.dev_type], s.dev_id), dtype=s.value.dtype)
+            if isinstance(s, np.ndarray):
+                return torch.from_numpy(s)
+            return s
         self.states = {k: dev(v) for k, v in states.items()}
-        self._host_states = True
+        self.states_synced = dict.fromkeys(self.states, True)
 
 
 class NativeUpdater(object):

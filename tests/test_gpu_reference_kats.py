@@ -339,3 +339,33 @@ def test_row_sparse_pull_single_device_and_large_rowid():
     kv.row_sparse_pull("a", out=out, row_ids=mx.nd.array(np.arange(num_rows, dtype=np.int64), mx.gpu(0), dtype=np.int64))
     assert out.indices.shape[0] == num_rows
     assert np.all(out.data.asnumpy() == 1.0)
+
+
+def test_user_defined_python_optimizer_on_the_store():
+    # kvstore.py:559-606: an optimizer without a fused kernel runs through the updater callback, on the merged
+    # value, once per pushed key; written against the reference's Optimizer protocol (list-valued step that
+    # counts the update itself)
+    @mx.optimizer.register
+    class HalfStep(mx.optimizer.Optimizer):
+        def create_state(self, index, weight):
+            return mx.nd.zeros(weight.shape, weight.context)
+
+        def step(self, indices, weights, grads, states):
+            self._update_count(indices)
+            for i, w, g, s, lr in zip(indices, weights, grads, states, self._get_lrs(indices)):
+                s[:] = s.asnumpy() + 1
+                w[:] = w.asnumpy() - lr * self.rescale_grad * g.asnumpy() / s.asnumpy()
+
+    kv = mx.kv.create("device")
+    kv.init(keys, [mx.nd.ones(shape, mx.gpu(0))] * len(keys))
+    opt = mx.optimizer.create("halfstep", learning_rate=0.5, rescale_grad=0.25)
+    kv.set_optimizer(opt)
+    want = np.ones(shape, np.float32)
+    for step in (1, 2, 3):
+        kv.push(keys, [[mx.nd.ones(shape, mx.gpu(0)) * 2.0 for _ in range(4)]] * len(keys))
+        want = want - np.float32(0.5 * 0.25) * np.float32(8.0) / np.float32(step)
+        outs = [mx.nd.empty(shape, mx.gpu(0)) for _ in keys]
+        kv.pull(keys, out=outs)
+        for o in outs:
+            np.testing.assert_allclose(o.asnumpy(), want, rtol=1e-6)
+    assert opt._index_update_count == {k: 3 for k in keys} and opt.num_update == 3

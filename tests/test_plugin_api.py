@@ -129,3 +129,64 @@ def test_trainer_refuses_update_on_kvstore_for_a_plug_in_without_optimizer_suppo
             check_diff_to_scalar(p.grad, 2)
         for p in params[0]:
             p.grad[:] = 1
+
+
+# ---- the other plug-in point: optimizers written in Python against the reference's protocol ----------------------
+@mx.optimizer.register
+class SignSGD(mx.optimizer.Optimizer):
+    """a user-defined optimizer exactly as one is written for the reference (optimizer.py:214-352): list-valued
+    ``step`` that counts the update itself, a state per index, learning rates through ``_get_lrs``"""
+
+    def create_state(self, index, weight):
+        return mx.nd.zeros(weight.shape, weight.context)           # number of sign flips seen, say
+
+    def step(self, indices, weights, grads, states):
+        self._update_count(indices)
+        lrs = self._get_lrs(indices)
+        wds = self._get_wds(indices)
+        for w, g, s, lr, wd in zip(weights, grads, states, lrs, wds):
+            step = np.sign(g.asnumpy() * self.rescale_grad + wd * w.asnumpy())
+            w[:] = w.asnumpy() - lr * step
+            s[:] = s.asnumpy() + np.abs(step)
+
+
+def test_user_defined_optimizer_through_the_updater():
+    """updater.py:39-93 + optimizer.py:287-352 with host arrays: single and list calls, per-index states, update
+    counts taken by the optimizer's own ``step`` (once per call, not twice), lr multipliers by index."""
+    opt = mx.optimizer.create("signsgd", learning_rate=0.5, wd=0.0)
+    opt.set_lr_mult({1: 0.5})
+    upd = mx.optimizer.get_updater(opt)
+    assert type(upd).__name__ == "Updater"                      # no fused kernel of that name
+    w = [mx.nd.zeros((4,)), mx.nd.ones((3,))]
+    g = [mx.nd.array(np.array([1, -1, 2, -2], np.float32)), mx.nd.array(np.array([1, 1, -1], np.float32))]
+    upd(0, g[0], w[0])
+    assert np.array_equal(w[0].asnumpy(), [-0.5, 0.5, -0.5, 0.5])
+    upd([0, 1], g, w)
+    assert np.array_equal(w[0].asnumpy(), [-1, 1, -1, 1])
+    assert np.array_equal(w[1].asnumpy(), [0.75, 0.75, 1.25])
+    assert opt._index_update_count == {0: 2, 1: 1} and opt.num_update == 2
+    assert np.array_equal(upd.states[0].asnumpy(), [2, 2, 2, 2])
+    # states survive get_states / set_states, with and without the optimizer
+    blob = upd.get_states(dump_optimizer=True)
+    upd2 = mx.optimizer.get_updater(mx.optimizer.create("signsgd", learning_rate=0.5))
+    upd2.set_states(blob)
+    assert upd2.optimizer._index_update_count == {0: 2, 1: 1}
+    assert np.array_equal(upd2.states[1].asnumpy(), [1, 1, 1])
+    upd2(1, g[1], w[1])
+    assert np.array_equal(w[1].asnumpy(), [0.5, 0.5, 1.5])
+    assert np.array_equal(upd2.states[1].asnumpy(), [2, 2, 2])
+
+
+def test_multi_precision_protocol_of_python_optimizers():
+    """optimizer.py:214-243,320-352: float16 weights get a float32 master copy in front of the state; the update
+    runs on the master and is cast back"""
+    opt = mx.optimizer.create("signsgd", learning_rate=2.0 ** -12, multi_precision=True)
+    upd = mx.optimizer.get_updater(opt)
+    w = mx.nd.array(np.ones((4,), np.float16), dtype=np.float16)
+    g = mx.nd.array(np.ones((4,), np.float16), dtype=np.float16)
+    for _ in range(3):
+        upd(7, g, w)
+    master, state = upd.states[7]
+    assert master.dtype == np.float32 and np.all(master.asnumpy() == np.float32(1 - 3 * 2.0 ** -12))
+    assert w.dtype == np.float16 and np.all(w.asnumpy() == np.float16(1 - 3 * 2.0 ** -12))   # 1 - 2^-12 alone would round to 1
+    assert np.all(state.asnumpy() == 3)

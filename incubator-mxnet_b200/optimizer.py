@@ -42,6 +42,9 @@ class Optimizer(object):
         self._index_update_count = self._all_index_update_counts[0]
         self.clip_gradient = clip_gradient
         self.multi_precision = multi_precision
+        self.aggregate_num = 1 if aggregate_num is None else aggregate_num      # optimizer.py:118-121
+        if use_fused_step is not None:
+            self.use_fused_step = use_fused_step
         self.idx2name = dict(param_idx2name or {})
         self.param_dict = param_dict or {}
 
@@ -163,7 +166,9 @@ class Optimizer(object):
         raise NotImplementedError()
 
     def fused_step(self, indices, weights, grads, states):
-        raise NotImplementedError()
+        # the operator-backed flavour of the reference; in this package the fused kernels live in the engine
+        # (fused_name), so on the Python path it is the same as step
+        self.step(indices, weights, grads, states)
 
     def update(self, indices, weights, grads, states):
         """optimizer.py:287-318"""

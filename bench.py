@@ -412,6 +412,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-nvls", action="store_true", help="keep gradients/weights out of multicast memory")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--local-world", type=int, default=0,
+                    help="split the box into 'nodes' of this many GPUs and use kv.create('dist_device_sync'): NVLink "
+                         "peer memory inside a node, NCCL between nodes (not the driver's configuration)")
     args = ap.parse_args()
     if args.workload == "resnet50-train":
         return train_resnet50(args)
@@ -449,11 +452,13 @@ def main():
         local = int(os.environ.get("LOCAL_RANK", rank))
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        mx.dist.init_process_group(device=local)
+        hier = 0 < args.local_world < world
+        mx.dist.init_process_group(device=local, local_world=args.local_world if hier else world)
         dev = local
     else:
         assert args.gpus == 1, "launch with torchrun for --gpus > 1"
         dev = 0
+        hier = False
         torch.cuda.set_device(0)
     ctx = mx.gpu(dev)
 
@@ -463,7 +468,10 @@ def main():
     # plain device memory
     exchange = "nvlink-p2p"
     alloc = mx.nd.empty_symmetric
-    if world > 1 and not args.no_nvls:
+    if hier:
+        exchange = "hierarchical: nvlink-p2p in nodes of %d, nccl between %d nodes" % (
+            args.local_world, world // args.local_world)
+    if world > 1 and not args.no_nvls and not hier:
         try:
             probe = mx.nd.empty_multicast((1024,))
             if mx.nd.has_multicast(probe):
@@ -478,7 +486,7 @@ def main():
         g[:] = rng.uniform(-1, 1, s).astype(np.float32)
     config["exchange"] = exchange
     w0 = np.random.default_rng(99)
-    kv = mx.kv.create("device")
+    kv = mx.kv.create("dist_device_sync" if hier else "device")
     kv.init(keys, [mx.nd.array(w0.uniform(0, 1, s).astype(np.float32), ctx) for s in shapes])
     if args.optimizer == "sgd":
         kv.set_optimizer(mx.optimizer.SGD(learning_rate=0.01, momentum=0.9, wd=1e-4))

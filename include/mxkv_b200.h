@@ -221,6 +221,14 @@ MXKV_DLL int MXKVB200ShardRange(int64_t size, int world, int rank, int64_t* begi
 typedef int (*MXKVB200AllGatherFn)(const void* send, size_t bytes, void* recv, void* ctx);
 MXKV_DLL int MXKVB200CommInit(int rank, int world, int dev_id, MXKVB200AllGatherFn allgather, void* ctx);
 MXKV_DLL int MXKVB200CommDestroy(void);
+/* Multi-node (kv.create('dist_device_sync'), the hierarchical form of KVStoreDist's synchronous mode,
+ * src/kvstore/kvstore_dist.h:343-470): the group of MXKVB200CommInit is ONE node; `allreduce` sums `count`
+ * elements of `dtype` (mshadow type flag) in place, on the device, over the ranks that have this rank's local
+ * rank on every node, ordered on `cuda_stream` (e.g. ncclAllReduce on that stream).  Per push the engine runs
+ * reduce-scatter inside the node -> ONE such call per dtype over this rank's packed shards -> fused update +
+ * all-gather inside the node.  Returns non-zero on failure.  Call after MXKVB200CommInit, before creating stores. */
+typedef int (*MXKVB200AllReduceFn)(void* dev_ptr, int64_t count, int dtype, void* cuda_stream, void* ctx);
+MXKV_DLL int MXKVB200SetHierarchy(int node_rank, int num_nodes, MXKVB200AllReduceFn allreduce, void* ctx);
 /* Collective: every rank calls it in the same order with the same shape.  The array lives in the
  * peer-mapped arena, so push/pushpull read and write it over NVLink without staging. */
 MXKV_DLL int MXKVB200NDArrayCreateSymmetric(const int64_t* shape, int ndim, int dtype, NDArrayHandle* out);

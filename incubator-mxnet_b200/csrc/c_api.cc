@@ -644,6 +644,21 @@ int MXKVB200CommInit(int rank, int world, int dev_id, MXKVB200AllGatherFn allgat
 int MXKVB200CommDestroy(void) {
   API_BEGIN();
   Runtime::Get()->DestroyProcessGroup();
+  Runtime::Get()->hier = Hierarchy();
+  API_END();
+}
+
+int MXKVB200SetHierarchy(int node_rank, int num_nodes, MXKVB200AllReduceFn allreduce, void* ctx) {
+  API_BEGIN();
+  MXKV_CHECK(num_nodes >= 1 && node_rank >= 0 && node_rank < num_nodes) << "bad node rank " << node_rank << " of "
+                                                                        << num_nodes;
+  MXKV_CHECK(allreduce != nullptr || num_nodes == 1) << "a multi-node hierarchy needs an all-reduce callback";
+  Runtime* rt = Runtime::Get();
+  MXKV_CHECK(rt->pg() != nullptr) << "MXKVB200CommInit (the node-local group) comes first";
+  rt->hier.node_rank = node_rank;
+  rt->hier.num_nodes = num_nodes;
+  rt->hier.fn = reinterpret_cast<AllReduceFn>(allreduce);
+  rt->hier.ctx = ctx;
   API_END();
 }
 

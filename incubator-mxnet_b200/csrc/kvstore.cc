@@ -19,8 +19,19 @@ static std::string Lower(std::string s) {
 // local types select CommCPU's association order -- the arithmetic still runs on the GPU.
 KVStore::KVStore(const std::string& type) : type_(type) {
   const std::string t = Lower(type);
-  MXKV_CHECK(t.find("dist") == std::string::npos)
-      << "distributed kvstore types ('" << type << "') are out of scope of this library";
+  const bool dist = t.find("dist") != std::string::npos;
+  if (dist) {
+    // KVStoreDist's synchronous mode (src/kvstore/kvstore_dist.h:343-470) is served hierarchically, without
+    // servers, once the embedding job has described the nodes; the parameter-server machinery itself
+    // (ps-lite, asynchronous mode, server-side profiler commands) is out of scope of this library
+    Runtime* rt = Runtime::Get();
+    MXKV_CHECK(rt->hier.configured() && rt->pg() != nullptr)
+        << "distributed kvstore types ('" << type << "') are out of scope of this library unless a node hierarchy "
+           "is configured (MXKVB200SetHierarchy; mx.dist.init_process_group(local_world=...))";
+    MXKV_CHECK(t.find("async") == std::string::npos)
+        << "asynchronous distributed stores ('" << type << "') are out of scope of this library";
+    hier_ = rt->hier.num_nodes > 1;
+  }
   // 'nccl' (KVStoreNCCL, src/kvstore/kvstore_nccl.h:62-551: rooted ncclReduce + ncclBcast per key) is
   // served by the same engine: NCCL leaves its summation order unspecified, so the device order is a
   // conforming result for that name ("parity unpinned" for this one type).
@@ -28,7 +39,7 @@ KVStore::KVStore(const std::string& type) : type_(type) {
   // (python/mxnet/optimizer/updater.py:30-127): optimizer state + fused multi-tensor updates of
   // caller-owned weights (UpdaterStep), never collective even in one-process-per-GPU mode
   solo_ = t.find("updater") != std::string::npos;
-  device_mode_ = solo_ || t.find("device") != std::string::npos || t.find("nccl") != std::string::npos;
+  device_mode_ = solo_ || dist || t.find("device") != std::string::npos || t.find("nccl") != std::string::npos;
   order_ = device_mode_ ? ORDER_DEVICE : ORDER_COMMCPU;
 }
 
@@ -36,21 +47,52 @@ ProcessGroup* KVStore::PG() const { return solo_ ? nullptr : Runtime::Get()->pg(
 
 KVStore::~KVStore() {
   try { Runtime::Get()->WaitAll(); } catch (...) {}
+  for (auto& kv : hier_buf_) {
+    if (kv.second.ptr == nullptr) continue;
+    cudaSetDevice(kv.second.dev);
+    cudaFree(kv.second.ptr);
+  }
 }
 
+// workers are numbered node by node (kvstore_dist.h: get_rank = ps::MyRank)
 int KVStore::rank() const {
   ProcessGroup* pg = PG();
+  if (pg && hier_) return Runtime::Get()->hier.node_rank * pg->world() + pg->rank();
   return pg ? pg->rank() : 0;
 }
 int KVStore::group_size() const {
   ProcessGroup* pg = PG();
+  if (pg && hier_) return Runtime::Get()->hier.num_nodes * pg->world();
   return pg ? pg->world() : 1;
 }
 
 void KVStore::Barrier() {
-  Runtime::Get()->WaitAll();
+  Runtime* rt = Runtime::Get();
+  rt->WaitAll();
   ProcessGroup* pg = PG();
   if (pg) pg->Barrier();
+  if (pg && hier_) {
+    // every node's ranks have arrived; one element summed across the nodes completes the global barrier
+    HierBuf& hb = hier_buf_[kFloat32];
+    if (hb.ptr == nullptr) {
+      DeviceGuard g(pg->dev());
+      CUDA_CALL(cudaMalloc(&hb.ptr, 256));
+      CUDA_CALL(cudaMemset(hb.ptr, 0, 256));
+      hb.bytes = 256; hb.dev = pg->dev();
+    }
+    InterNodeSum(hb.ptr, 1, kFloat32, pg->dev());
+    rt->WaitAll();
+    pg->Barrier();
+  }
+}
+
+void KVStore::InterNodeSum(void* ptr, int64_t count, int dtype, int dev) {
+  Runtime* rt = Runtime::Get();
+  MXKV_CHECK(rt->hier.fn != nullptr) << "no inter-node all-reduce configured";
+  if (count <= 0) return;
+  DeviceGuard g(dev);
+  const int rc = rt->hier.fn(ptr, count, dtype, rt->Dev(dev).stream, rt->hier.ctx);
+  MXKV_CHECK(rc == 0) << "the inter-node all-reduce callback failed (" << rc << ")";
 }
 
 // ---------------------------------------------------------------------------
@@ -450,6 +492,15 @@ void KVStore::InitImpl(const std::vector<int>& keys, const std::vector<NDArray>&
       KeyState& k2 = keys_[keys[i]];
       Replica& r = EnsureReplica(k2, dev);
       if (pg && pg->world() > 1) BroadcastFromRank0(k2, r);
+      if (pg && hier_) {
+        // ... and every node adopts node 0's value (rank 0 of the job initialises, kvstore_dist.h:196-223):
+        // the other nodes contribute zeros to an inter-node sum
+        if (rt->hier.node_rank != 0) {
+          DeviceGuard g(dev);
+          CUDA_CALL(cudaMemsetAsync(r.local.data(), 0, r.local.nbytes(), rt->Dev(dev).stream));
+        }
+        InterNodeSum(r.local.data(), k2.size, k2.dtype, dev);
+      }
       rt->ReleaseToUser(dev);
     } else {
       // host value, devices unknown yet: keep a private host copy (values[i].Copy(pinned_ctx_))
@@ -1018,6 +1069,59 @@ void KVStore::ReduceUpdateCompressed(std::vector<Group>& groups, bool write_outs
   for (int dev : touched) rt->ReleaseToUser(dev);
 }
 
+// Multi-node push (see kvstore.h).  The staging slices of one call are packed per dtype so that the exchange
+// between the nodes is ONE all-reduce per dtype, whatever the number of keys; a slice starts on a 256-byte
+// boundary and is addressed through a base pointer shifted back by the byte offset of this rank's range, so the
+// kernels index it like any other array of the key (and keep their 16-byte vector paths).
+void KVStore::HierReduceUpdate(std::vector<Group>& groups, bool write_outs) {
+  Runtime* rt = Runtime::Get();
+  ProcessGroup* pg = PG();
+  MXKV_CHECK(pg != nullptr) << "multi-node stores run in one-process-per-GPU mode";
+  MXKV_CHECK(updater_ == nullptr)
+      << "dist_device_sync: a Python updater callback is not supported; set an optimizer (it runs inside the "
+         "store on every node) or none";
+  MXKV_CHECK(gc_bits_ == 0) << "dist_device_sync: gradient compression is not supported";
+  const int n = pg->world(), me = pg->rank(), dev = pg->dev();
+  struct Slice { int key; int dtype; size_t off; int64_t begin; };
+  std::vector<Slice> plan;
+  std::map<int, size_t> total;
+  for (auto& g : groups) {
+    KeyState& ks = GetKey(g.key);
+    MXKV_CHECK(ks.stype == kDefaultStorage) << "dist_device_sync: row_sparse keys are not supported (key " << g.key << ")";
+    const size_t esize = DTypeSize(ks.dtype);
+    const bool two_shot = n > 1 && static_cast<int64_t>(ks.size * esize) >= rt->twoshot_bytes &&
+                          ks.size >= static_cast<int64_t>(n) * 128;
+    const int64_t shard = two_shot ? ShardLen(ks.size, n) : ks.size;
+    const int64_t begin = two_shot ? std::min<int64_t>(ks.size, shard * me) : 0;
+    const int64_t end = two_shot ? std::min<int64_t>(ks.size, shard * (me + 1)) : ks.size;
+    size_t& t = total[ks.dtype];
+    plan.push_back(Slice{g.key, ks.dtype, t, begin});
+    t += (static_cast<size_t>(end - begin) * esize + 255) / 256 * 256;
+  }
+  for (auto& kv : total) {
+    HierBuf& hb = hier_buf_[kv.first];
+    if (hb.bytes >= kv.second) continue;
+    DeviceGuard g(dev);
+    rt->WaitDevice(dev);
+    if (hb.ptr != nullptr) CUDA_CALL(cudaFree(hb.ptr));
+    hb.bytes = kv.second + kv.second / 4;
+    hb.dev = dev;
+    CUDA_CALL(cudaMalloc(&hb.ptr, hb.bytes));
+    CUDA_CALL(cudaMemset(hb.ptr, 0, hb.bytes));      // the gaps between slices take part in the sums
+  }
+  hier_base_.clear();
+  for (auto& sl : plan)
+    hier_base_[sl.key] = static_cast<char*>(hier_buf_[sl.dtype].ptr) + sl.off -
+                         static_cast<size_t>(sl.begin) * DTypeSize(sl.dtype);
+  struct PhaseGuard { int* p; ~PhaseGuard() { *p = 0; } } guard{&hier_phase_};
+  hier_phase_ = 1;
+  ReduceUpdate(groups, false);
+  for (auto& kv : total)
+    InterNodeSum(hier_buf_[kv.first].ptr, static_cast<int64_t>(kv.second / DTypeSize(kv.first)), kv.first, dev);
+  hier_phase_ = 2;
+  ReduceUpdate(groups, write_outs);
+}
+
 // Where a key of a call is reduced: collectively on the GPUs its values live on (distinct,
 // P2P-reachable GPUs, single process), by every rank (one process per GPU), or on one root GPU that reads
 // and writes wherever the arrays are.
@@ -1069,14 +1173,17 @@ void KVStore::PlaceKey(const Group& g, KeyState& ks, std::vector<int>* devs_out,
 
 void KVStore::ReduceUpdate(std::vector<Group>& groups, bool write_outs) {
   // an overflow of the previous step is settled before this step's update counts are taken
-  if (opt_.enabled && updater_ == nullptr && opt_.skip_nonfinite) ResolveOverflow();
+  if (hier_phase_ == 0 && opt_.enabled && updater_ == nullptr && opt_.skip_nonfinite) ResolveOverflow();
+  if (hier_ && hier_phase_ == 0) { HierReduceUpdate(groups, write_outs); return; }
   if (gc_bits_ != 0) { ReduceUpdateCompressed(groups, write_outs); return; }
-  if (HostPipelined(groups, write_outs)) return;
+  if (hier_phase_ == 0 && HostPipelined(groups, write_outs)) return;
   Runtime* rt = Runtime::Get();
   ProcessGroup* pg = PG();
   const bool mp_mode = pg != nullptr;
   const bool callback = updater_ != nullptr;
-  const bool fused = opt_.enabled && !callback;
+  // multi-node: phase 1 only sums the node's values into the staging slices; phase 2 is the ordinary path with
+  // the (by then globally summed) slice as the only source
+  const bool fused = opt_.enabled && !callback && hier_phase_ != 1;
 
   // Keys of one call that reduce on different GPUs (e.g. host-resident values for keys whose stored
   // values live on different GPUs) are served group by group; the reference has no such restriction
@@ -1180,7 +1287,8 @@ void KVStore::ReduceUpdate(std::vector<Group>& groups, bool write_outs) {
 
     const bool two_shot = collective && static_cast<int64_t>(ks.size * esize) >= rt->twoshot_bytes &&
                           ks.size >= static_cast<int64_t>(n_part) * 128;
-    if (ks.local_world > 0 && (callback || !(two_shot && ks.local_world == n_part && ks.shard_devs == part_dev))) {
+    if (hier_phase_ != 1 && ks.local_world > 0 &&
+        (callback || !(two_shot && ks.local_world == n_part && ks.shard_devs == part_dev))) {
       GatherLocal(ks);
       for (int p = my_first; p <= my_last; ++p) rep[p] = &EnsureReplica(ks, part_dev[p]);
       for (int p = my_first; p <= my_last; ++p) rep[p] = FindReplica(ks, part_dev[p]);
@@ -1207,7 +1315,9 @@ void KVStore::ReduceUpdate(std::vector<Group>& groups, bool write_outs) {
     // ---- sources as addressable pointers ----------------------------------
     // srcptr[p][k]: address of source k for the kernel running as participant p
     std::vector<std::vector<const void*>> srcptr(n_part, std::vector<const void*>(collective ? n_part : n_src));
-    if (mp_mode) {
+    if (mp_mode && hier_phase_ == 2) {
+      srcptr[pg->rank()].assign(1, hier_base_.at(ks.key));
+    } else if (mp_mode) {
       const NDArray& v = g.vals[0];
       NDArray sym_src;
       if (v.symmetric() && collective) {
@@ -1321,7 +1431,7 @@ void KVStore::ReduceUpdate(std::vector<Group>& groups, bool write_outs) {
       // (auto: above 4 ranks.  Per direction the switch path moves S(1 + 1/n) against 2S(n-1)/n of
       // the peer path: 1.5x more at n=2, equal time measured at n=4 -- where the peer path is kept
       // because it is bit-exact --, 1.56x less at n=8: busbw 782 vs 641 GB/s, profiles/r01_tune_bulk.txt)
-      if (mp_mode && collective && (rt->nvls_mode >= 2 || (rt->nvls_mode == 1 && n_part > 4)) &&
+      if (mp_mode && collective && !hier_ && (rt->nvls_mode >= 2 || (rt->nvls_mode == 1 && n_part > 4)) &&
           !(fused && IsNormOpt(opt_.kind)) && ks.dtype == kFloat32 && ks.size % 4 == 0 &&
           g.vals[0].mc_data() != nullptr && Aligned16(g.vals[0].mc_data()) && !(two_shot && need_post)) {
         nvls_key = true;
@@ -1330,7 +1440,13 @@ void KVStore::ReduceUpdate(std::vector<Group>& groups, bool write_outs) {
             if (out_direct[oi] && g.outs[oi]->mc_data() == nullptr) nvls_key = false;
       }
       const bool shard_local = two_shot && !need_post;
-      if (mp_mode && collective) {
+      if (hier_phase_ == 1) {
+        // the node's sum of this rank's range (the whole key when it is not sharded) goes to the staging slice
+        Dest d; d.owner = collective ? -2 : -1; d.own_only = shard_local;
+        for (int p = 0; p < kMaxRanks; ++p) d.ptr[p] = hier_base_.at(ks.key);
+        if (!collective) d.owner = 0;
+        dests.push_back(d);
+      } else if (mp_mode && collective) {
         Dest d; d.owner = -2; d.own_only = shard_local;
         for (int p = 0; p < n_part; ++p) d.ptr[p] = rep[pg->rank()]->local.peer_data(p);
         dests.push_back(d);
@@ -1350,7 +1466,9 @@ void KVStore::ReduceUpdate(std::vector<Group>& groups, bool write_outs) {
           }
         }
       }
-      if (shard_local) { ks.local_world = n_part; ks.shard_devs = part_dev; }
+      if (hier_phase_ == 1) {
+        // the stored value is not touched in this phase
+      } else if (shard_local) { ks.local_world = n_part; ks.shard_devs = part_dev; }
       else ks.local_world = 0;
       if (write_outs) {
         for (size_t oi = 0; oi < g.outs.size(); ++oi) {

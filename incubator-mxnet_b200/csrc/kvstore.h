@@ -206,6 +206,18 @@ class KVStore {
   bool AdamWSkips() const;
   float KeyWD(const KeyState& ks) const;
 
+  // ---- multi-node ('dist_device_sync' over a configured Hierarchy, runtime.h) --------------------------
+  // A push runs as: phase 1 = reduce(-scatter) of the node's values into this rank's staging slices; ONE
+  // inter-node sum per dtype over the packed slices; phase 2 = fused update (+ all-gather) inside the node with
+  // the slice as the only source.  Every node computes the same update, so no parameter server is involved.
+  void HierReduceUpdate(std::vector<Group>& groups, bool write_outs);
+  void InterNodeSum(void* ptr, int64_t count, int dtype, int dev);
+  bool hier_ = false;
+  int hier_phase_ = 0;                       // 0: not inside a hierarchical push
+  struct HierBuf { void* ptr = nullptr; size_t bytes = 0; int dev = -1; };
+  std::map<int, HierBuf> hier_buf_;          // per dtype: packed staging slices of one call
+  std::unordered_map<int, void*> hier_base_; // per key: slice address minus the byte offset of this rank's range
+
   ProcessGroup* PG() const;     // the process group this store exchanges over (none for 'updater' stores)
   std::string type_;
   bool device_mode_ = false;

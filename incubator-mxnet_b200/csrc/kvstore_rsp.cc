@@ -42,6 +42,7 @@ static void PublishNnz(const NDArray& a) {
 }
 
 void KVStore::InitRowSparseKey(KeyState& ks, const NDArray& v) {
+  MXKV_CHECK(!hier_) << "dist_device_sync: row_sparse keys are not supported (key " << ks.key << ")";
   Runtime* rt = Runtime::Get();
   ProcessGroup* pg = PG();
   MXKV_CHECK(v.dtype() == kFloat32) << "row_sparse keys support float32 only";
@@ -96,6 +97,7 @@ static void EnsureRspWorkspace(KeyState& ks, Replica& r, int n, int64_t cap) {
 }
 
 void KVStore::PushRowSparse(KeyState& ks, const std::vector<NDArray>& vals) {
+  MXKV_CHECK(!hier_) << "dist_device_sync: row_sparse values are not supported (key " << ks.key << ")";
   Runtime* rt = Runtime::Get();
   ProcessGroup* pg = PG();
   const bool mp_mode = pg != nullptr;

@@ -66,6 +66,19 @@ struct DeviceState {
   size_t host_stage_bytes = 0;
 };
 
+// Multi-node jobs (dist_device_sync): the process group above spans ONE node (the GPUs that share an NVSwitch
+// domain and this library's peer-mapped arena); between the nodes the only thing the engine needs is a sum of a
+// device buffer over the ranks that hold the same local rank on every node.  The embedding framework provides
+// it (NCCL over the network in production), ordered on the CUDA stream it is handed.
+typedef int (*AllReduceFn)(void* dev_ptr, int64_t count, int dtype, void* cuda_stream, void* ctx);
+struct Hierarchy {
+  int node_rank = 0;
+  int num_nodes = 1;
+  AllReduceFn fn = nullptr;
+  void* ctx = nullptr;
+  bool configured() const { return fn != nullptr; }
+};
+
 struct SymPtr {                 // one symmetric allocation as seen from this process
   void* ptr[kMaxRanks] = {nullptr};
   bool valid = false;
@@ -117,6 +130,7 @@ class Runtime {
   void InitProcessGroup(int rank, int world, int dev, AllGatherFn fn, void* ctx);
   void DestroyProcessGroup();
   ProcessGroup* pg() { return pg_.get(); }
+  Hierarchy hier;                            // MXKVB200SetHierarchy
 
   std::recursive_mutex& mu() { return mu_; }
   bool auto_fence = true;

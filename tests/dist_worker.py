@@ -1,0 +1,205 @@
+"""Worker of the multi-node tests: `kv.create('dist_device_sync')` over WORLD_SIZE ranks split into nodes of
+MXKV_TEST_LOCAL_WORLD ranks (one box is enough: a "node" is whatever shares the engine's peer-memory group).
+On a GPU box it is launched by torchrun (tests/test_gpu_multi.py), the nodes are joined by NCCL; on the simulator
+(MXKV_SIM, tests/test_sim_host_logic.py) files stand in for both process groups.  Every rank regenerates every rank's
+data from seeds and checks itself against the oracle; the expected association is the hierarchy's: device order
+inside a node (src/ndarray/ndarray_function-inl.h:457-486), then node by node."""
+import ctypes
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+SIM = bool(os.environ.get("MXKV_SIM"))
+if not SIM:
+    import torch
+    import torch.distributed as dist
+import mxnet_b200 as mx          # noqa: E402
+from oracle import oracle as O   # noqa: E402
+
+NP_OF = {0: np.float32, 1: np.float64, 2: np.float16, 3: np.uint8, 4: np.int32, 5: np.int8, 6: np.int64}
+
+
+def bits_equal(a, b):
+    a, b = np.ascontiguousarray(a), np.ascontiguousarray(b)
+    return a.shape == b.shape and np.array_equal(a.view(np.uint8), b.view(np.uint8))
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    L = int(os.environ["MXKV_TEST_LOCAL_WORLD"])
+    node, nodes, lrank = mx.dist.node_layout(rank, world, L)
+    if SIM:
+        sys.path.insert(0, os.path.join(ROOT, "tests", "sim"))
+        from file_comm import FileComm
+        rdv = os.environ["MXKV_SIM_RDV"]
+        for d in ("node%d" % node, "inter%d" % lrank, "all"):
+            os.makedirs(os.path.join(rdv, d), exist_ok=True)
+        local_comm = FileComm(lrank, L, os.path.join(rdv, "node%d" % node))
+        inter_comm = FileComm(node, nodes, os.path.join(rdv, "inter%d" % lrank))
+        all_comm = FileComm(rank, world, os.path.join(rdv, "all"))
+        mx.dist.init_with_allgather(lrank, L, lrank, local_comm.allgather)
+
+        calls = []
+
+        def file_allreduce(ptr, count, dtype, _stream):
+            calls.append(count)
+            # "device" memory of the simulator is host memory; node order, element type arithmetic
+            if dtype == 12:                                  # bfloat16: sum in float32, round to nearest even
+                raw = np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctypes.c_uint16)), (count,))
+                parts = [np.frombuffer(b, np.uint16) for b in inter_comm.allgather(raw.tobytes())]
+                acc = O.bf16_to_f32(parts[0])
+                for p in parts[1:]:
+                    acc = O.bf16_to_f32(O.f32_to_bf16(acc + O.bf16_to_f32(p)))
+                raw[:] = O.f32_to_bf16(acc)
+                return
+            npt = NP_OF[dtype]
+            arr = np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(np.ctypeslib.as_ctypes_type(npt))), (count,))
+            parts = [np.frombuffer(b, npt) for b in inter_comm.allgather(arr.tobytes())]
+            acc = parts[0].copy()
+            for p in parts[1:]:
+                acc = (acc + p).astype(npt)
+            arr[:] = acc
+
+        mx.dist.set_hierarchy(node, nodes, file_allreduce)
+        device = lrank
+        barrier = all_comm.barrier
+    else:
+        device = int(os.environ.get("LOCAL_RANK", rank))
+        torch.cuda.set_device(device)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", device))
+        mx.dist.init_process_group(device=device, local_world=L)
+        barrier = dist.barrier
+    ctx = mx.gpu(device)
+
+    def data(seed, shape, r):
+        return np.random.default_rng(seed * 1000 + r).uniform(-1, 1, shape).astype(np.float32)
+
+    def hier_sum(per_rank):
+        """device order inside each node, then node by node"""
+        per_node = [O.sum_device(per_rank[n * L:(n + 1) * L]) if L > 1 else per_rank[n * L].copy() for n in range(nodes)]
+        acc = per_node[0].copy()
+        for s in per_node[1:]:
+            acc = (acc + s).astype(acc.dtype)
+        return acc
+
+    # single-node names still mean the node: the reference's 'device' store knows nothing about other machines
+    kv0 = mx.kv.create("device")
+    assert kv0.rank == lrank and kv0.num_workers == L
+
+    kv = mx.kv.create("dist_device_sync")
+    assert kv.type == "dist_device_sync"
+    assert kv.rank == rank and kv.num_workers == world, (kv.rank, kv.num_workers)
+
+    # 1. init / broadcast: the job's rank 0 wins on every rank of every node
+    shape = (300, 7)
+    out = mx.nd.empty(shape, ctx)
+    kv.broadcast("w", mx.nd.array(data(1, shape, rank), ctx), out=out)
+    assert bits_equal(out.asnumpy(), data(1, shape, 0)), "broadcast"
+
+    # 2. push / pull without optimizer: the stored value becomes the sum over every rank of every node
+    sizes = [5, 1000, 65536, 70001, (1 << 20) + 3]
+    keys = [str(k) for k in range(len(sizes))]
+    kv.init(keys, [mx.nd.zeros((e,), ctx) for e in sizes])
+    for mode in ("plain", "symmetric", "host"):
+        for step in range(2):
+            vals = []
+            for k, e in enumerate(sizes):
+                g = data(10 * step + k, (e,), rank)
+                if mode == "symmetric":
+                    a = mx.nd.empty_symmetric((e,))
+                    a[:] = g
+                elif mode == "host":
+                    a = mx.nd.array(g, mx.cpu())
+                else:
+                    a = mx.nd.array(g, ctx)
+                vals.append(a)
+            outs = [mx.nd.empty((e,), ctx) for e in sizes]
+            kv.pushpull(keys, vals, out=outs)
+            for k, e in enumerate(sizes):
+                want = hier_sum([data(10 * step + k, (e,), r) for r in range(world)])
+                assert bits_equal(outs[k].asnumpy(), want), ("allreduce", mode, step, e)
+            # a later pull sees the same value
+            o = mx.nd.empty((sizes[3],), ctx)
+            kv.pull(keys[3], out=o)
+            assert bits_equal(o.asnumpy(), hier_sum([data(10 * step + 3, (sizes[3],), r) for r in range(world)]))
+
+    # 3. the exact known answer of tests/nightly/dist_device_sync_kvstore.py:59-88 (every worker pushes rank + 1,
+    #    'test' optimizer on the store): w = 1 - lr * rate * sum(rank + 1) per push, small and big keys
+    rate, lr = 2, 0.5
+    kvt = mx.kv.create("dist_device_sync")
+    kat_shapes = {"9": (2, 3), "99": (1200, 1200)}
+    for k, s in kat_shapes.items():
+        kvt.init(k, mx.nd.ones(s, ctx))
+    kvt.set_optimizer(mx.optimizer.create("test", learning_rate=lr, rescale_grad=rate))
+    for i in range(3):
+        for k, s in kat_shapes.items():
+            val = mx.nd.empty(s, ctx)
+            kvt.push(k, mx.nd.array(np.full(s, rank + 1, np.float32), ctx))
+            kvt.pull(k, out=val)
+            num = 1 - lr * rate * (world + 1) * world / 2 * (i + 1)
+            assert np.all(val.asnumpy() == np.float32(num)), (k, i, val.asnumpy().ravel()[:3], num)
+
+    # 4. fused optimizers, several keys per call, outputs written by the kernel: bit-exact against the oracle fed
+    #    with the hierarchical sum
+    shapes = [(64, 33), (129,), (300007,), (1 << 18,)]
+    for optname, kw in (("sgd", dict(learning_rate=0.1, momentum=0.9, wd=1e-4)),
+                        ("adam", dict(learning_rate=0.01, wd=1e-3))):
+        kv2 = mx.kv.create("dist_device_sync")
+        ks = list(range(len(shapes)))
+        w0 = [data(50 + k, s, 0) for k, s in zip(ks, shapes)]
+        kv2.init(ks, [mx.nd.array(w, ctx) for w in w0])
+        kv2.set_optimizer(mx.optimizer.create(optname, **kw))
+        oopt = O.OracleOptimizer(optname, **kw)
+        ow = [w.copy() for w in w0]
+        outs = [mx.nd.empty(s, ctx) for s in shapes]
+        for step in range(3):
+            grads = [mx.nd.array(data(100 * step + k, s, rank), ctx) for k, s in zip(ks, shapes)]
+            kv2.pushpull(ks, grads, out=outs)
+            for k, s in zip(ks, shapes):
+                oopt.update(k, ow[k], hier_sum([data(100 * step + k, s, r) for r in range(world)]))
+                assert bits_equal(outs[k].asnumpy(), ow[k]), (optname, step, k)
+
+    # 5. LAMB: norms over the node's shards, identical on every node
+    kw = dict(learning_rate=0.01, wd=0.01)
+    kv3 = mx.kv.create("dist_device_sync")
+    w0 = [data(70 + k, s, 0) for k, s in enumerate(shapes)]
+    kv3.init(list(range(len(shapes))), [mx.nd.array(w, ctx) for w in w0])
+    kv3.set_optimizer(mx.optimizer.LAMB(**kw))
+    oopt = O.OracleOptimizer("lamb", norm_mode="f64", **kw)
+    ow = [w.copy() for w in w0]
+    outs = [mx.nd.empty(s, ctx) for s in shapes]
+    for step in range(2):
+        kv3.pushpull(list(range(len(shapes))), [mx.nd.array(data(200 * step + k, s, rank), ctx)
+                                                for k, s in enumerate(shapes)], out=outs)
+        for k, s in enumerate(shapes):
+            oopt.update(k, ow[k], hier_sum([data(200 * step + k, s, r) for r in range(world)]))
+            np.testing.assert_allclose(outs[k].asnumpy(), ow[k], rtol=5e-6, atol=5e-7, err_msg=str(("lamb", step, k)))
+            ow[k][...] = outs[k].asnumpy()
+
+    # 6. what the hierarchy does not serve is refused, not silently kept inside the node
+    kv4 = mx.kv.create("dist_device_sync")
+    for bad in (lambda: kv4.init("r", mx.nd.zeros((8, 4), ctx, stype="row_sparse")),
+                lambda: mx.kv.create("dist_async")):
+        try:
+            bad()
+        except mx.MXNetError:
+            pass
+        else:
+            raise AssertionError("expected an error")
+
+    kv._barrier()
+    barrier()
+    mx.nd.waitall()
+    if SIM:
+        # one inter-node sum per push (single dtype), whatever the number of keys, plus one per initialised key and
+        # per barrier: far fewer than keys x pushes
+        print("inter-node sums: %d calls, %d elements" % (len(calls), sum(calls)))
+        assert 40 <= len(calls) <= 80, len(calls)
+    print("DIST_WORKER_OK rank %d of %d (%d nodes of %d)" % (rank, world, nodes, L))
+
+
+if __name__ == "__main__":
+    main()

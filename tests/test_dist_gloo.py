@@ -55,3 +55,37 @@ def test_bootstrap_allgather_world2():
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+def _node_worker(rank, world, local_world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import mxnet_b200 as mx
+    node, nodes, lrank = mx.dist.node_layout(rank, world, local_world)
+    local_groups, inter_groups = mx.dist.make_node_groups(world, local_world)
+    # the node-local bootstrap all-gather sees the node only ...
+    ag = mx.dist.make_allgather(local_groups[node])
+    send = (ctypes.c_uint8 * 8)(*[rank] * 8)
+    recv = (ctypes.c_uint8 * (8 * local_world))()
+    ok = ag(ctypes.addressof(send), 8, ctypes.addressof(recv), None) == 0
+    ok = ok and [recv[i * 8] for i in range(local_world)] == list(range(node * local_world, (node + 1) * local_world))
+    # ... and the inter-node group joins the ranks of equal local rank: a sum over it is what the engine asks for
+    t = torch.tensor([float(rank + 1)])
+    dist.all_reduce(t, group=inter_groups[lrank])
+    ok = ok and float(t) == sum(r + 1 for r in range(lrank, world, local_world))
+    q.put((rank, ok))
+    dist.destroy_process_group()
+
+
+def test_node_groups_of_a_multi_node_job_world4():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_node_worker, args=(r, 4, 2, port, q)) for r in range(4)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(r, True) for r in range(4)]

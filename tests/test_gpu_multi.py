@@ -193,3 +193,23 @@ def test_mp_one_process_per_gpu(world):
     sys.stderr.write(r.stderr[-3000:])
     assert r.returncode == 0
     assert r.stdout.count("MP_WORKER_OK") == world
+
+
+@pytest.mark.parametrize("world,local_world", [(4, 2), (8, 4), (2, 1)])
+def test_one_process_per_gpu_multi_node_hierarchy(world, local_world):
+    """kv.create('dist_device_sync') with the box split into "nodes" of `local_world` GPUs: NVLink peer memory
+    inside a node (the engine's own kernels), NCCL all-reduces between the nodes -- the production layout, minus the
+    network.  tests/dist_worker.py checks itself against the oracle."""
+    if mx.num_gpus() < world:
+        pytest.skip("needs %d GPUs" % world)
+    env = dict(os.environ)
+    env["PYTHONPATH"] = ROOT + os.pathsep + env.get("PYTHONPATH", "")
+    env["MXKV_TEST_LOCAL_WORLD"] = str(local_world)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+           "--master-addr", "127.0.0.1", "--master-port", str(29600 + world),
+           os.path.join(ROOT, "tests", "dist_worker.py")]
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900)
+    sys.stdout.write(r.stdout[-3000:])
+    sys.stderr.write(r.stderr[-3000:])
+    assert r.returncode == 0
+    assert r.stdout.count("DIST_WORKER_OK") == world

@@ -259,6 +259,27 @@ def main():
                 assert bits_equal(o.asnumpy(), okv.local[k8[i]]), ("walk", walk, optname, step, i, where)
         check_call(_LIB.MXKVB200SetTwoShotBytes(ctypes.c_int64(262144)))
 
+    # 9. bfloat16 weights and gradients with float32 master weights: the node's sum is taken in float32 and
+    #    rounded once to cross the network in the key's own type; the update runs on the master
+    E = 50003
+    w0 = O.f32_to_bf16(data(900, (E,), 0))
+    w32, mom = O.bf16_to_f32(w0), np.zeros(E, np.float32)
+    kv9 = mx.kv.create("dist_device_sync")
+    kv9.init(0, mx.nd.array(w0, ctx, dtype="bfloat16"))
+    kv9.set_optimizer(mx.optimizer.SGD(learning_rate=0.1, momentum=0.9, wd=1e-4, multi_precision=True))
+    out = mx.nd.empty((E,), ctx, dtype="bfloat16")
+    want = np.zeros(E, np.uint16)
+    for step in range(3):
+        g = [O.f32_to_bf16(data(910 + step, (E,), r)) for r in range(world)]
+        kv9.pushpull(0, mx.nd.array(g[rank], ctx, dtype="bfloat16"), out=out)
+        per_node = [O.f32_to_bf16(O.sum_device_lp_f32out(g[n * L:(n + 1) * L], 2)) if L > 1 else g[n * L]
+                    for n in range(nodes)]
+        tot = per_node[0]
+        for x in per_node[1:]:
+            tot = O.f32_to_bf16(O.bf16_to_f32(tot) + O.bf16_to_f32(x))
+        O.mp_sgd_mom_update(want, 2, w32, mom, O.bf16_to_f32(tot), 0.1, 1e-4, 0.9)
+        assert bits_equal(out.asnumpy(raw=True), want), ("bf16 multi-precision", step)
+
     kv._barrier()
     barrier()
     mx.nd.waitall()

@@ -121,8 +121,14 @@ class Trainer(object):
                 uok = False
             else:
                 uok = uok and bool(kv.is_capable(_kv.KVStoreBase.OPTIMIZER))
+            distributed = kv is not None and "dist" in kv.type
             if sparse_grad:
-                uok = False                 # usually faster on one machine (trainer.py:204-236)
+                # one machine: per-device updates are usually faster; several machines: only the store can update,
+                # because row_sparse_pull of a gradient does not exist (trainer.py:204-236)
+                uok = distributed
+                if config_uok is False and distributed:
+                    raise ValueError("Cannot set update_on_kvstore=False on dist kvstore "
+                                     "when sparse gradients are present.")
                 if kv is not None and not isinstance(kv, _kv.KVStore):
                     raise ValueError("Cannot use {} for multi-device training with sparse gradients".format(type(kv)))
             if config_uok is not None and kv is not None:

@@ -55,8 +55,9 @@ def main():
                     acc = O.bf16_to_f32(O.f32_to_bf16(acc + O.bf16_to_f32(p)))
                 raw[:] = O.f32_to_bf16(acc)
                 return
-            npt = NP_OF[dtype]
-            arr = np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(np.ctypeslib.as_ctypes_type(npt))), (count,))
+            npt = np.dtype(NP_OF[dtype])
+            raw = (ctypes.c_char * (count * npt.itemsize)).from_address(ptr)
+            arr = np.frombuffer(raw, npt)                        # a writable view of the "device" buffer
             parts = [np.frombuffer(b, npt) for b in inter_comm.allgather(arr.tobytes())]
             acc = parts[0].copy()
             for p in parts[1:]:
@@ -142,6 +143,29 @@ def main():
             num = 1 - lr * rate * (world + 1) * world / 2 * (i + 1)
             assert np.all(val.asnumpy() == np.float32(num)), (k, i, val.asnumpy().ravel()[:3], num)
 
+    # 3b. tests/nightly/dist_sync_kvstore.py:428-449 (init with i, pull gives i; float32 and float16, small and
+    #     big, host and device values) and :102-112 with float16 keys and the multi-precision 'test' optimizer
+    kvi = mx.kv.create("dist_device_sync")
+    for j, (shp, where) in enumerate([((3, 3), mx.cpu()), ((1200, 1200), mx.cpu()), ((3, 3), ctx), ((1200, 1200), ctx)]):
+        for i in range(4):
+            dt = np.float32 if i < 2 else np.float16
+            name = "init_%d_%d" % (j, i)
+            kvi.init(name, mx.nd.array(np.full(shp, i, dt), where, dtype=dt))
+            val = mx.nd.empty(shp, where, dtype=dt)
+            kvi.pull(name, out=val)
+            assert np.all(val.asnumpy() == i), (name, val.asnumpy().ravel()[:3])
+    kvh = mx.kv.create("dist_device_sync")
+    for name, shp in (("h_small", (3, 3)), ("h_big", (1200, 1200))):
+        kvh.init(name, mx.nd.array(np.ones(shp, np.float16), ctx, dtype=np.float16))
+    kvh.set_optimizer(mx.optimizer.create("test", learning_rate=lr, rescale_grad=rate, multi_precision=True))
+    for i in range(3):
+        for name, shp in (("h_small", (3, 3)), ("h_big", (1200, 1200))):
+            kvh.push(name, mx.nd.array(np.full(shp, rank + 1, np.float16), ctx, dtype=np.float16))
+            val = mx.nd.empty(shp, ctx, dtype=np.float16)
+            kvh.pull(name, out=val)
+            num = 1 - lr * rate * (world + 1) * world / 2 * (i + 1)
+            assert np.all(val.asnumpy() == np.float16(num)), (name, i, val.asnumpy().ravel()[:3], num)
+
     # 4. fused optimizers, several keys per call, outputs written by the kernel: bit-exact against the oracle fed
     #    with the hierarchical sum
     shapes = [(64, 33), (129,), (300007,), (1 << 18,)]
@@ -213,6 +237,28 @@ def main():
             oopt.update(k, ow[k], hier_sum([data(400 + 10 * step + k, s, r) for r in range(world)]))
             assert bits_equal(p.data.asnumpy(), ow[k]), ("trainer", step, k)
     assert tr._update_on_kvstore is True and tr._kvstore.num_workers == world
+    # dist_sync_kvstore.py:499-514: ones, gradient rank + 1, sgd with lr 1 -> 1 - (1 + W) W / 2
+    x = Param(np.ones((10, 1), np.float32))
+    trainer = mx.Trainer([x], "sgd", {"learning_rate": 1.0, "multi_precision": False}, kvstore=mx.kv.create("dist_device_sync"))
+    x.grad[:] = float(rank + 1)
+    trainer.step(1)
+    assert np.all(x.data.asnumpy() == np.float32(1 - (1 + world) * world / 2)), x.data.asnumpy().ravel()[:3]
+    # dist_sync_kvstore.py:477-497: the storage-type rows of the decision table for a distributed store
+    class SP(object):
+        def __init__(self, stype, grad_stype):
+            self.data = mx.nd.zeros((10, 1), ctx, stype=stype)
+            self.grad = mx.nd.zeros((10, 1), ctx, stype=grad_stype)
+    for stype, gstype, uok, expected in (("default", "default", None, True), ("default", "default", True, True),
+                                         ("default", "default", False, False), ("default", "row_sparse", None, True),
+                                         ("default", "row_sparse", False, ValueError),
+                                         ("row_sparse", "row_sparse", False, ValueError)):
+        t = mx.Trainer([SP(stype, gstype)], "sgd", {"learning_rate": 0.1}, kvstore=mx.kv.create("dist_device_sync"),
+                       update_on_kvstore=uok)
+        try:
+            t._init_kvstore()
+            assert t._kv_initialized and t._update_on_kvstore is expected, (stype, gstype, uok, t._update_on_kvstore)
+        except ValueError:
+            assert expected is ValueError, (stype, gstype, uok)
 
     # 8. random walks (the same decisions on every rank): key subsets, push / pushpull / pull, values in device,
     #    peer-mapped or host memory, the sharding threshold moving between calls so that keys change between the

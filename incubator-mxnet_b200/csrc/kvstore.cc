@@ -898,7 +898,10 @@ void KVStore::ReduceUpdateCompressed(std::vector<Group>& groups, bool write_outs
   const bool callback = updater_ != nullptr;
   MXKV_CHECK(!callback) << "gradient compression together with a Python updater callback is not supported; "
                            "use a fused optimizer or no optimizer";
-  const bool fused = opt_.enabled;
+  // multi-node phase 1 (HierReduceUpdate): quantise, exchange the codes inside the node, sum the dequantised
+  // streams into the staging slice; nothing stored, nothing updated
+  const bool stage_only = hier_phase_ == 1;
+  const bool fused = opt_.enabled && !stage_only;
   const int opt_kind = fused ? opt_.kind : OPT_NONE;
   const int world = mp_mode ? pg->world() : 1;
   std::set<int> touched;
@@ -983,7 +986,7 @@ void KVStore::ReduceUpdateCompressed(std::vector<Group>& groups, bool write_outs
     for (int dev : consumers) {
       touch(dev);
       EnsureReplica(ks, dev);
-      if (ks.local_world > 0) GatherLocal(ks);
+      if (!stage_only && ks.local_world > 0) GatherLocal(ks);
       Replica& r = *FindReplica(ks, dev);
       if (fused) { if (ks.has_state) GatherState(ks); EnsureState(ks, r, mp); ks.state_world = 0; }
       DeviceGuard dg(dev);
@@ -1012,7 +1015,7 @@ void KVStore::ReduceUpdateCompressed(std::vector<Group>& groups, bool write_outs
         rt->launches++;
         tw.src[k] = out;
       }
-      tw.out[tw.n_out++] = r.local.data();
+      tw.out[tw.n_out++] = stage_only ? hier_base_.at(ks.key) : r.local.data();
       bool vec_ok = (ks.size % 4 == 0);          // scratch slices stay 16-byte aligned only then
       if (write_outs) {
         for (NDArray* o : g.outs) {
@@ -1034,7 +1037,7 @@ void KVStore::ReduceUpdateCompressed(std::vector<Group>& groups, bool write_outs
       tw.lr = lr; tw.wd = wd; tw.eta = KeyEta(ks); tw.reserved_ = ks.key;
       tw.pad_ = vec_ok ? 3 : 0;
       LaunchLocal(LaunchClassKey{SYNC_NONE, ks.dtype, mp ? 1 : 0}, tw, opt_kind, dev);
-      r.fresh = true;
+      if (!stage_only) r.fresh = true;
     }
     if (world > 1) {
       DeviceGuard dg(pg->dev());
@@ -1045,7 +1048,7 @@ void KVStore::ReduceUpdateCompressed(std::vector<Group>& groups, bool write_outs
         for (int dev : consumers) if (dev != src_dev[k]) rt->StreamWait(src_dev[k], dev);
     }
     for (auto& r : ks.reps) {
-      if (std::find(consumers.begin(), consumers.end(), r.dev) == consumers.end()) r.fresh = false;
+      if (!stage_only && std::find(consumers.begin(), consumers.end(), r.dev) == consumers.end()) r.fresh = false;
     }
     if (write_outs) {
       for (NDArray* o : g.outs) {
@@ -1080,7 +1083,10 @@ void KVStore::HierReduceUpdate(std::vector<Group>& groups, bool write_outs) {
   MXKV_CHECK(updater_ == nullptr)
       << "dist_device_sync: a Python updater callback is not supported; set an optimizer (it runs inside the "
          "store on every node) or none";
-  MXKV_CHECK(gc_bits_ == 0) << "dist_device_sync: gradient compression is not supported";
+  // Gradient compression: every worker quantises against its own residual and the values that are summed are
+  // the dequantised ones, as on KVStoreDist's servers (kvstore_dist_server.h:346-398).  The codes travel inside
+  // the node; what crosses the network is the node's float32 sum (a sum of codes is not a code), whole keys.
+  const bool compressed = gc_bits_ != 0;
   const int n = pg->world(), me = pg->rank(), dev = pg->dev();
   struct Slice { int key; int dtype; size_t off; int64_t begin; };
   std::vector<Slice> plan;
@@ -1089,7 +1095,7 @@ void KVStore::HierReduceUpdate(std::vector<Group>& groups, bool write_outs) {
     KeyState& ks = GetKey(g.key);
     MXKV_CHECK(ks.stype == kDefaultStorage) << "dist_device_sync: row_sparse keys are not supported (key " << g.key << ")";
     const size_t esize = DTypeSize(ks.dtype);
-    const bool two_shot = n > 1 && static_cast<int64_t>(ks.size * esize) >= rt->twoshot_bytes &&
+    const bool two_shot = !compressed && n > 1 && static_cast<int64_t>(ks.size * esize) >= rt->twoshot_bytes &&
                           ks.size >= static_cast<int64_t>(n) * 128;
     const int64_t shard = two_shot ? ShardLen(ks.size, n) : ks.size;
     const int64_t begin = two_shot ? std::min<int64_t>(ks.size, shard * me) : 0;
@@ -1175,7 +1181,8 @@ void KVStore::ReduceUpdate(std::vector<Group>& groups, bool write_outs) {
   // an overflow of the previous step is settled before this step's update counts are taken
   if (hier_phase_ == 0 && opt_.enabled && updater_ == nullptr && opt_.skip_nonfinite) ResolveOverflow();
   if (hier_ && hier_phase_ == 0) { HierReduceUpdate(groups, write_outs); return; }
-  if (gc_bits_ != 0) { ReduceUpdateCompressed(groups, write_outs); return; }
+  // (multi-node with compression: phase 1 is the compressed reduce, phase 2 the ordinary update from the slices)
+  if (gc_bits_ != 0 && hier_phase_ != 2) { ReduceUpdateCompressed(groups, write_outs); return; }
   if (hier_phase_ == 0 && HostPipelined(groups, write_outs)) return;
   Runtime* rt = Runtime::Get();
   ProcessGroup* pg = PG();

@@ -326,6 +326,32 @@ def main():
         O.mp_sgd_mom_update(want, 2, w32, mom, O.bf16_to_f32(tot), 0.1, 1e-4, 0.9)
         assert bits_equal(out.asnumpy(raw=True), want), ("bf16 multi-precision", step)
 
+    # 10. 2-bit gradient compression (tests/nightly/dist_sync_kvstore.py:330-426 in spirit): every worker quantises
+    #     against its own residual, the dequantised values are what is summed -- inside the node from the codes,
+    #     between the nodes as float32 -- with and without an optimizer on the store, small and sharded keys
+    thr = 0.5
+    for optname, kw in ((None, {}), ("sgd", dict(learning_rate=0.1, momentum=0.9))):
+        kvc = mx.kv.create("dist_device_sync")
+        kvc.set_gradient_compression({"type": "2bit", "threshold": thr})
+        csizes = [3000, 300000]
+        cw = [np.zeros(e, np.float32) for e in csizes]
+        kvc.init(["c0", "c1"], [mx.nd.zeros((e,), ctx) for e in csizes])
+        okv = O.OracleKVStore("device")
+        okv.init(["c0", "c1"], [w.copy() for w in cw])
+        if optname:
+            kvc.set_optimizer(mx.optimizer.create(optname, **kw))
+            okv.set_optimizer(O.OracleOptimizer(optname, **kw))
+        residual = [[np.zeros(e, np.float32) for _ in range(world)] for e in csizes]
+        for step in range(3):
+            outs = [mx.nd.empty((e,), ctx) for e in csizes]
+            kvc.pushpull(["c0", "c1"], [mx.nd.array(data(950 + 10 * step + j, (e,), rank), ctx)
+                                        for j, e in enumerate(csizes)], out=outs)
+            for j, e in enumerate(csizes):
+                deq = [O.dequantize_2bit(O.quantize_2bit(data(950 + 10 * step + j, (e,), r), residual[j][r], thr), e, thr)
+                       for r in range(world)]
+                okv.push("c%d" % j, hier_sum(deq))
+                assert bits_equal(outs[j].asnumpy(), okv.local["c%d" % j]), ("compression", optname, step, j)
+
     kv._barrier()
     barrier()
     mx.nd.waitall()

@@ -1080,14 +1080,51 @@ void KVStore::HierReduceUpdate(std::vector<Group>& groups, bool write_outs) {
   Runtime* rt = Runtime::Get();
   ProcessGroup* pg = PG();
   MXKV_CHECK(pg != nullptr) << "multi-node stores run in one-process-per-GPU mode";
-  MXKV_CHECK(updater_ == nullptr)
-      << "dist_device_sync: a Python updater callback is not supported; set an optimizer (it runs inside the "
-         "store on every node) or none";
   // Gradient compression: every worker quantises against its own residual and the values that are summed are
   // the dequantised ones, as on KVStoreDist's servers (kvstore_dist_server.h:346-398).  The codes travel inside
   // the node; what crosses the network is the node's float32 sum (a sum of codes is not a code), whole keys.
   const bool compressed = gc_bits_ != 0;
   const int n = pg->world(), me = pg->rank(), dev = pg->dev();
+  if (updater_ != nullptr) {
+    // A Python updater (a user-defined optimizer; on KVStoreDist it runs on the servers from a pickled copy,
+    // kvstore_dist_server.h:346-398): every rank receives the whole sum of the job in its `merged` array and runs
+    // the callback on its own replica, key by key -- the same update everywhere.
+    MXKV_CHECK(!compressed) << "gradient compression together with a Python updater callback is not supported";
+    hier_base_.clear();
+    rt->AcquireUser(dev);
+    for (auto& g : groups) {
+      KeyState& ks = GetKey(g.key);
+      MXKV_CHECK(ks.stype == kDefaultStorage) << "dist_device_sync: row_sparse keys are not supported (key " << g.key << ")";
+      EnsureReplica(ks, dev);
+      if (ks.local_world > 0) GatherLocal(ks);
+      Replica& root = *FindReplica(ks, dev);
+      if (root.merged.is_none()) root.merged = NDArray::Empty(ks.shape, Context{kGPU, dev}, ks.dtype, false);
+      hier_base_[g.key] = root.merged.data();
+    }
+    struct PhaseGuard { int* p; ~PhaseGuard() { *p = 0; } } guard{&hier_phase_};
+    const int64_t keep = rt->twoshot_bytes;
+    struct ThresholdGuard { int64_t* p; int64_t v; ~ThresholdGuard() { *p = v; } } tg{&rt->twoshot_bytes, keep};
+    rt->twoshot_bytes = INT64_MAX;           // whole keys on every rank in this mode
+    hier_phase_ = 1;
+    ReduceUpdate(groups, false);
+    hier_phase_ = 0;
+    rt->twoshot_bytes = keep;
+    for (auto& g : groups) {
+      KeyState& ks = GetKey(g.key);
+      Replica& root = *FindReplica(ks, dev);
+      InterNodeSum(root.merged.data(), ks.size, ks.dtype, dev);
+      RunCallbackUpdater(ks, root);
+      ks.local_world = 0;
+    }
+    rt->ReleaseToUser(dev);
+    if (write_outs) {
+      std::vector<int> okeys;
+      std::vector<NDArray*> outs;
+      for (auto& g : groups) for (NDArray* o : g.outs) { okeys.push_back(g.key); outs.push_back(o); }
+      if (!outs.empty()) PullImpl(okeys, outs, 0, true);
+    }
+    return;
+  }
   struct Slice { int key; int dtype; size_t off; int64_t begin; };
   std::vector<Slice> plan;
   std::map<int, size_t> total;
@@ -1187,7 +1224,7 @@ void KVStore::ReduceUpdate(std::vector<Group>& groups, bool write_outs) {
   Runtime* rt = Runtime::Get();
   ProcessGroup* pg = PG();
   const bool mp_mode = pg != nullptr;
-  const bool callback = updater_ != nullptr;
+  const bool callback = updater_ != nullptr && hier_phase_ != 1;
   // multi-node: phase 1 only sums the node's values into the staging slices; phase 2 is the ordinary path with
   // the (by then globally summed) slice as the only source
   const bool fused = opt_.enabled && !callback && hier_phase_ != 1;

@@ -226,7 +226,8 @@ MXKV_DLL int MXKVB200CommDestroy(void);
  * elements of `dtype` (mshadow type flag) in place, on the device, over the ranks that have this rank's local
  * rank on every node, ordered on `cuda_stream` (e.g. ncclAllReduce on that stream).  Per push the engine runs
  * reduce-scatter inside the node -> ONE such call per dtype over this rank's packed shards -> fused update +
- * all-gather inside the node.  Returns non-zero on failure.  Call after MXKVB200CommInit, before creating stores. */
+ * all-gather inside the node (row_sparse pushes: the node's merge, then a gather of the nodes' merged rows through
+ * the same callback with dtype int64 / float32).  Returns non-zero on failure.  Call after MXKVB200CommInit, before creating stores. */
 typedef int (*MXKVB200AllReduceFn)(void* dev_ptr, int64_t count, int dtype, void* cuda_stream, void* ctx);
 MXKV_DLL int MXKVB200SetHierarchy(int node_rank, int num_nodes, MXKVB200AllReduceFn allreduce, void* ctx);
 /* Collective: every rank calls it in the same order with the same shape.  The array lives in the

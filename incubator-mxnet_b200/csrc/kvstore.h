@@ -211,6 +211,7 @@ class KVStore {
   // inter-node sum per dtype over the packed slices; phase 2 = fused update (+ all-gather) inside the node with
   // the slice as the only source.  Every node computes the same update, so no parameter server is involved.
   void HierReduceUpdate(std::vector<Group>& groups, bool write_outs);
+  void HierPushRowSparse(KeyState& ks, const std::vector<NDArray>& vals);
   void InterNodeSum(void* ptr, int64_t count, int dtype, int dev);
   bool hier_ = false;
   int hier_phase_ = 0;                       // 0: not inside a hierarchical push

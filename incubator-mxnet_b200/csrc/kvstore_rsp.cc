@@ -42,7 +42,6 @@ static void PublishNnz(const NDArray& a) {
 }
 
 void KVStore::InitRowSparseKey(KeyState& ks, const NDArray& v) {
-  MXKV_CHECK(!hier_) << "dist_device_sync: row_sparse keys are not supported (key " << ks.key << ")";
   Runtime* rt = Runtime::Get();
   ProcessGroup* pg = PG();
   MXKV_CHECK(v.dtype() == kFloat32) << "row_sparse keys support float32 only";
@@ -79,6 +78,11 @@ void KVStore::InitRowSparseKey(KeyState& ks, const NDArray& v) {
   }
   ks.reps.push_back(r);
   if (pg && pg->world() > 1) BroadcastFromRank0(ks, ks.reps.back());
+  if (pg && hier_) {              // every node adopts node 0's table (see InitImpl)
+    Replica& me = ks.reps.back();
+    if (rt->hier.node_rank != 0) CUDA_CALL(cudaMemsetAsync(me.local.data(), 0, me.local.nbytes(), s));
+    InterNodeSum(me.local.data(), ks.size, kFloat32, dev);
+  }
   rt->WaitDevice(dev);            // the host-side source may be released by the caller
   rt->ReleaseToUser(dev);
 }
@@ -97,7 +101,7 @@ static void EnsureRspWorkspace(KeyState& ks, Replica& r, int n, int64_t cap) {
 }
 
 void KVStore::PushRowSparse(KeyState& ks, const std::vector<NDArray>& vals) {
-  MXKV_CHECK(!hier_) << "dist_device_sync: row_sparse values are not supported (key " << ks.key << ")";
+  if (hier_) { HierPushRowSparse(ks, vals); return; }
   Runtime* rt = Runtime::Get();
   ProcessGroup* pg = PG();
   const bool mp_mode = pg != nullptr;
@@ -334,6 +338,209 @@ void KVStore::PushRowSparse(KeyState& ks, const std::vector<NDArray>& vals) {
     for (auto& r : ks.reps) r.fresh = (&r == &root);
   }
   for (int d : touched) rt->ReleaseToUser(d);
+}
+
+// Multi-node row_sparse push (KVStoreDist pushes the rows to the servers, which merge them and run the sparse
+// update, kvstore_dist.h:343-470 / kvstore_dist_server.h).  Here: (1) the node's sorted-union merge of its ranks'
+// gradients, as in the single-node path, materialised on every rank; (2) the nodes' merged gradients are
+// gathered -- row counts first (one tiny inter-node sum, read back by the host, as the reference reads its row
+// counts), then ids and rows in buffers sized for the largest node, each node filling its section and the
+// others contributing zeros to the inter-node sum; (3) the same four kernels again with one source per node,
+// this time applying the lazy / standard update (or the assignment) to the rows of this rank's replica.
+// Association per row: rank order inside a node, then node order.
+void KVStore::HierPushRowSparse(KeyState& ks, const std::vector<NDArray>& vals) {
+  Runtime* rt = Runtime::Get();
+  ProcessGroup* pg = PG();
+  MXKV_CHECK(pg != nullptr) << "multi-node stores run in one-process-per-GPU mode";
+  MXKV_CHECK(updater_ == nullptr) << "dist_device_sync: row_sparse values with a Python updater are not supported";
+  const int nodes = rt->hier.num_nodes, node = rt->hier.node_rank;
+  MXKV_CHECK(nodes <= kMaxSrc) << "row_sparse push over " << nodes << " nodes (max " << kMaxSrc << ")";
+  MXKV_CHECK(vals.size() == 1) << "one-process-per-GPU mode: push exactly one value per key per rank";
+  const NDArray& v = vals[0];
+  if (ks.stype != kRowSparseStorage) {
+    MXKV_CHECK(ks.dtype == kFloat32 && !ks.shape.empty()) << "row_sparse values need a float32 key (key " << ks.key << ")";
+    if (ks.local_world > 0) GatherLocal(ks);
+    if (!opt_.enabled) ks.stype = kRowSparseStorage;
+    else if (ks.state_world > 0) { GatherState(ks); ks.state_world = 0; ks.state_devs.clear(); }
+  }
+  MXKV_CHECK(v.stype() == kRowSparseStorage && v.dtype() == kFloat32 && v.shape() == ks.shape)
+      << "row_sparse push: storage type / shape / dtype mismatch for key " << ks.key;
+  const bool fused = opt_.enabled;
+  if (fused)
+    MXKV_CHECK(opt_.kind == OPT_SGD || opt_.kind == OPT_SGD_MOM || opt_.kind == OPT_ADAM)
+        << "row_sparse gradients: only the lazy SGD / SGD-momentum / Adam updates are fused";
+  const int world = pg->world(), dev = pg->dev();
+  const int64_t L = ks.size / ks.shape[0];
+  DeviceGuard g(dev);
+  cudaStream_t s = rt->Dev(dev).stream;
+  rt->AcquireUser(dev);
+  if (v.ctx().is_gpu() && v.ctx().dev_id != dev) MXKV_CHECK(false) << "value must live on GPU " << dev << " or on the host";
+  PublishNnz(v);
+  EnsureReplica(ks, dev);
+  Replica& r = *FindReplica(ks, dev);
+  if (fused) { EnsureState(ks, r, false); SyncState(ks, r); ks.count += 1; }
+  const float lr = fused ? KeyLR(ks) : 0.f;
+  const float wd = fused ? KeyWD(ks) : 0.f;
+  std::vector<void*> temps;
+
+  // ---- (1) the node's merge ---------------------------------------------------------------------------------
+  RspSources S;
+  std::memset(&S, 0, sizeof(S));
+  int64_t cap = std::max<int64_t>(v.nnz(), 1);
+  SyncArgs sync;
+  std::memset(&sync, 0, sizeof(sync));
+  if (world > 1) {
+    const int64_t stage_rows = std::min<int64_t>(ks.shape[0], EnvInt("MXKV_B200_RSP_STAGE_ROWS", 131072));
+    if (r.stage_idx.is_none()) {
+      const Context ctx{kGPU, dev};
+      r.stage_idx = NDArray::Empty({stage_rows}, ctx, kInt64, true);
+      r.stage_val = NDArray::Empty({stage_rows * L}, ctx, kFloat32, true);
+      r.stage_nnz = NDArray::Empty({2}, ctx, kInt64, true);
+    }
+    MXKV_CHECK(v.nnz() <= r.stage_idx.size())
+        << "row_sparse gradient with " << v.nnz() << " rows exceeds the staging capacity of " << r.stage_idx.size()
+        << " rows; raise MXKV_B200_RSP_STAGE_ROWS";
+    cap = r.stage_idx.size();
+    sync.self = rt->Dev(dev).signal_pad;
+    for (int q = 0; q < world; ++q) sync.peers[q] = pg->signal_pad(q);
+    sync.world = world; sync.rank = pg->rank(); sync.mode = SYNC_WRITE_PEERS;
+    sync.timeout = rt->spin_timeout_cycles;
+    CheckLaunch(LaunchBarrier(sync, s), "barrier");      // peers are done with the previous push's staging
+    if (v.nnz() > 0) {
+      CopyBytes(v.idx_ptr(), v.ctx(), r.stage_idx.data(), r.stage_idx.ctx(), v.nnz() * 8);
+      CopyBytes(v.data(), v.ctx(), r.stage_val.data(), r.stage_val.ctx(), v.nnz() * L * 4);
+    }
+    CheckLaunch(LaunchSetI64(static_cast<int64_t*>(r.stage_nnz.data()), v.nnz(), s), "set_nnz");
+    CheckLaunch(LaunchBarrier(sync, s), "barrier");
+    S.n = world;
+    for (int q = 0; q < world; ++q) {
+      S.idx[q] = static_cast<const int64_t*>(r.stage_idx.peer_data(q));
+      S.val[q] = static_cast<const float*>(r.stage_val.peer_data(q));
+      S.nnz[q] = static_cast<const int64_t*>(r.stage_nnz.peer_data(q));
+    }
+  } else {
+    S.n = 1;
+    if (v.ctx().is_gpu()) {
+      S.idx[0] = v.idx_ptr(); S.val[0] = static_cast<const float*>(v.data()); S.nnz[0] = v.d_nnz();
+    } else {
+      void* ti = nullptr; void* tv = nullptr; int64_t* tn = nullptr;
+      CUDA_CALL(cudaMallocAsync(&ti, cap * 8, s));
+      CUDA_CALL(cudaMallocAsync(&tv, std::max<int64_t>(cap * L, 1) * 4, s));
+      CUDA_CALL(cudaMallocAsync(reinterpret_cast<void**>(&tn), 16, s));
+      if (v.nnz() > 0) {
+        CopyBytes(v.idx_ptr(), v.ctx(), ti, Context{kGPU, dev}, v.nnz() * 8);
+        CopyBytes(v.data(), v.ctx(), tv, Context{kGPU, dev}, v.nnz() * L * 4);
+      }
+      CheckLaunch(LaunchSetI64(tn, v.nnz(), s), "set_nnz");
+      temps.push_back(ti); temps.push_back(tv); temps.push_back(tn);
+      S.idx[0] = static_cast<const int64_t*>(ti); S.val[0] = static_cast<const float*>(tv); S.nnz[0] = tn;
+    }
+  }
+  EnsureRspWorkspace(ks, r, S.n, cap);
+  RspRowArgs A;
+  std::memset(&A, 0, sizeof(A));
+  A.out_idx = r.rsp_merged.idx_ptr();
+  A.out_val = static_cast<float*>(r.rsp_merged.data());
+  A.d_nnz_out = r.rsp_merged.d_nnz();
+  A.table = static_cast<float*>(r.local.data());
+  A.row_len = L;
+  A.opt = OPT_NONE;
+  A.assign = 0;
+  bool vec = (L % 4 == 0) && Aligned16(A.table) && Aligned16(A.out_val);
+  for (int k = 0; k < S.n; ++k) vec = vec && Aligned16(S.val[k]);
+  A.vec = vec ? 1 : 0;
+  CheckLaunch(LaunchRspSum(S, A, static_cast<int32_t*>(r.rsp_first.data()), static_cast<int32_t*>(r.rsp_pf.data()),
+                           r.rsp_cap, s), "rsp_sum");
+  rt->launches += 3;
+  r.rsp_merged.set_nnz_device();
+
+  // ---- (2) gather the nodes' merged gradients ------------------------------------------------------------------
+  int64_t* cnt = nullptr;                  // [nodes] row counts, device
+  CUDA_CALL(cudaMallocAsync(reinterpret_cast<void**>(&cnt), static_cast<size_t>(nodes) * 8, s));
+  temps.push_back(cnt);
+  CUDA_CALL(cudaMemsetAsync(cnt, 0, static_cast<size_t>(nodes) * 8, s));
+  CUDA_CALL(cudaMemcpyAsync(cnt + node, r.rsp_merged.d_nnz(), 8, cudaMemcpyDeviceToDevice, s));
+  InterNodeSum(cnt, nodes, kInt64, dev);
+  std::vector<int64_t> counts(nodes);
+  CUDA_CALL(cudaMemcpyAsync(counts.data(), cnt, static_cast<size_t>(nodes) * 8, cudaMemcpyDeviceToHost, s));
+  CUDA_CALL(cudaStreamSynchronize(s));
+  int64_t cap2 = 1;
+  for (int64_t c : counts) cap2 = std::max(cap2, c);
+  int64_t* idx_all = nullptr; float* val_all = nullptr;
+  const size_t idx_bytes = static_cast<size_t>(nodes) * cap2 * 8;
+  const size_t val_bytes = static_cast<size_t>(nodes) * cap2 * L * 4;
+  CUDA_CALL(cudaMallocAsync(reinterpret_cast<void**>(&idx_all), idx_bytes, s));
+  CUDA_CALL(cudaMallocAsync(reinterpret_cast<void**>(&val_all), val_bytes, s));
+  temps.push_back(idx_all); temps.push_back(val_all);
+  CUDA_CALL(cudaMemsetAsync(idx_all, 0, idx_bytes, s));
+  CUDA_CALL(cudaMemsetAsync(val_all, 0, val_bytes, s));
+  if (counts[node] > 0) {
+    CUDA_CALL(cudaMemcpyAsync(idx_all + static_cast<size_t>(node) * cap2, r.rsp_merged.idx_ptr(),
+                              static_cast<size_t>(counts[node]) * 8, cudaMemcpyDeviceToDevice, s));
+    CUDA_CALL(cudaMemcpyAsync(val_all + static_cast<size_t>(node) * cap2 * L, r.rsp_merged.data(),
+                              static_cast<size_t>(counts[node]) * L * 4, cudaMemcpyDeviceToDevice, s));
+  }
+  InterNodeSum(idx_all, static_cast<int64_t>(nodes) * cap2, kInt64, dev);
+  InterNodeSum(val_all, static_cast<int64_t>(nodes) * cap2 * L, kFloat32, dev);
+
+  // ---- (3) merge the nodes and update this rank's replica --------------------------------------------------------
+  RspSources S2;
+  std::memset(&S2, 0, sizeof(S2));
+  S2.n = nodes;
+  for (int q = 0; q < nodes; ++q) {
+    S2.idx[q] = idx_all + static_cast<size_t>(q) * cap2;
+    S2.val[q] = val_all + static_cast<size_t>(q) * cap2 * L;
+    S2.nnz[q] = cnt + q;
+  }
+  EnsureRspWorkspace(ks, r, nodes, cap2);
+  const bool std_update = fused && !opt_.lazy_update;
+  RspRowArgs B;
+  std::memset(&B, 0, sizeof(B));
+  B.out_idx = r.rsp_merged.idx_ptr();
+  B.out_val = (fused && !std_update) ? nullptr : static_cast<float*>(r.rsp_merged.data());
+  B.d_nnz_out = r.rsp_merged.d_nnz();
+  B.table = static_cast<float*>(r.local.data());
+  B.row_len = L;
+  B.opt = (fused && !std_update) ? opt_.kind : OPT_NONE;
+  B.assign = fused ? 0 : 1;
+  B.lr = lr; B.wd = wd; B.rescale = opt_.rescale; B.clip = opt_.clip; B.momentum = opt_.momentum;
+  B.beta1 = static_cast<float>(opt_.beta1); B.beta2 = static_cast<float>(opt_.beta2); B.eps = opt_.eps;
+  if (fused) {
+    B.s0 = r.s0.is_none() ? nullptr : static_cast<float*>(r.s0.data());
+    B.s1 = r.s1.is_none() ? nullptr : static_cast<float*>(r.s1.data());
+  }
+  bool vec2 = (L % 4 == 0) && Aligned16(B.table) && (B.out_val == nullptr || Aligned16(B.out_val)) &&
+              (B.s0 == nullptr || Aligned16(B.s0)) && (B.s1 == nullptr || Aligned16(B.s1));
+  for (int q = 0; q < nodes; ++q) vec2 = vec2 && Aligned16(S2.val[q]);
+  B.vec = vec2 ? 1 : 0;
+  if (B.assign) CUDA_CALL(cudaMemsetAsync(r.local.data(), 0, r.local.nbytes(), s));   // local = merged
+  CheckLaunch(LaunchRspSum(S2, B, static_cast<int32_t*>(r.rsp_first.data()), static_cast<int32_t*>(r.rsp_pf.data()),
+                           r.rsp_cap, s), "rsp_sum");
+  rt->launches += 3;
+  r.rsp_merged.set_nnz_device();
+  if (std_update) {
+    float* gd = nullptr;
+    CUDA_CALL(cudaMallocAsync(reinterpret_cast<void**>(&gd), static_cast<size_t>(ks.size) * 4, s));
+    CUDA_CALL(cudaMemsetAsync(gd, 0, static_cast<size_t>(ks.size) * 4, s));
+    CheckLaunch(LaunchRspScatter(gd, r.rsp_merged.idx_ptr(), r.rsp_merged.d_nnz(), r.rsp_merged.cap_rows(), L,
+                                 static_cast<const float*>(r.rsp_merged.data()), s), "rsp_scatter");
+    TensorWork tw;
+    std::memset(&tw, 0, sizeof(tw));
+    tw.src[0] = gd; tw.n_src = 1;
+    tw.out[0] = r.local.data(); tw.n_out = 1;
+    tw.w = r.local.data();
+    tw.s0 = B.s0; tw.s1 = B.s1;
+    tw.begin = 0; tw.end = ks.size;
+    tw.lr = lr; tw.wd = wd; tw.eta = KeyEta(ks); tw.reserved_ = ks.key;
+    tw.pad_ = (ks.size % 4 == 0 && Aligned16(r.local.data())) ? 1 : 0;
+    const int kind = opt_.kind == OPT_SGD ? OPT_SGD_STD : (opt_.kind == OPT_ADAM ? OPT_ADAM_STD : opt_.kind);
+    LaunchLocal(LaunchClassKey{SYNC_NONE, kFloat32, 0}, tw, kind, dev);
+    CUDA_CALL(cudaFreeAsync(gd, s));
+  }
+  for (void* t : temps) CUDA_CALL(cudaFreeAsync(t, s));
+  r.fresh = true;
+  ks.local_world = 0;
+  rt->ReleaseToUser(dev);
 }
 
 void KVStore::PullDenseFromRowSparse(KeyState& ks, const std::vector<NDArray*>& outs) {

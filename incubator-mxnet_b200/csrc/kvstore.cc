@@ -67,6 +67,7 @@ int KVStore::group_size() const {
 }
 
 void KVStore::Barrier() {
+  std::lock_guard<std::recursive_mutex> lk(mu_);
   Runtime* rt = Runtime::Get();
   rt->WaitAll();
   ProcessGroup* pg = PG();

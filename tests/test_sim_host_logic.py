@@ -47,7 +47,7 @@ def _passed(out):
 def test_single_gpu_paths(sim_lib):
     out = _run(sim_lib, 1, ["test_gpu_dense.py", "test_gpu_reference_kats.py", "test_gpu_rsp.py",
                             "test_gpu_norm_opt.py", "test_gpu_compression.py", "test_gpu_updater.py",
-                            "test_gpu_trainer_nd.py"])
+                            "test_gpu_trainer_nd.py", "test_gpu_zz_threads.py"])
     assert _passed(out) >= 100, out[-500:]
 
 
@@ -56,7 +56,7 @@ def test_single_process_multi_gpu_paths(sim_lib, devices):
     """one-shot and two-shot (sharded) exchange, sharded optimizer state, layer-wise optimizers with norms added
     across the shards, compression, the updater callback -- over 2, 4 and 8 simulated GPUs."""
     out = _run(sim_lib, devices, ["test_gpu_multi.py", "test_gpu_compression.py", "test_gpu_rsp.py",
-                                  "test_gpu_placement.py", "test_gpu_trainer_nd.py"],
+                                  "test_gpu_placement.py", "test_gpu_trainer_nd.py", "test_gpu_zz_threads.py"],
                extra=["-k", "not one_process_per_gpu"])
     assert _passed(out) >= 30, out[-500:]
 

@@ -1102,14 +1102,12 @@ void KVStore::HierReduceUpdate(std::vector<Group>& groups, bool write_outs) {
       if (root.merged.is_none()) root.merged = NDArray::Empty(ks.shape, Context{kGPU, dev}, ks.dtype, false);
       hier_base_[g.key] = root.merged.data();
     }
-    struct PhaseGuard { int* p; ~PhaseGuard() { *p = 0; } } guard{&hier_phase_};
-    const int64_t keep = rt->twoshot_bytes;
-    struct ThresholdGuard { int64_t* p; int64_t v; ~ThresholdGuard() { *p = v; } } tg{&rt->twoshot_bytes, keep};
-    rt->twoshot_bytes = INT64_MAX;           // whole keys on every rank in this mode
+    struct PhaseGuard { int* p; bool* w; ~PhaseGuard() { *p = 0; *w = false; } } guard{&hier_phase_, &hier_whole_keys_};
+    hier_whole_keys_ = true;                 // whole keys on every rank in this mode
     hier_phase_ = 1;
     ReduceUpdate(groups, false);
     hier_phase_ = 0;
-    rt->twoshot_bytes = keep;
+    hier_whole_keys_ = false;
     for (auto& g : groups) {
       KeyState& ks = GetKey(g.key);
       Replica& root = *FindReplica(ks, dev);
@@ -1330,7 +1328,8 @@ void KVStore::ReduceUpdate(std::vector<Group>& groups, bool write_outs) {
       for (int p = my_first; p <= my_last; ++p) EnsureState(ks, *rep[p], mp);
     }
 
-    const bool two_shot = collective && static_cast<int64_t>(ks.size * esize) >= rt->twoshot_bytes &&
+    const bool two_shot = collective && !hier_whole_keys_ &&
+                          static_cast<int64_t>(ks.size * esize) >= rt->twoshot_bytes &&
                           ks.size >= static_cast<int64_t>(n_part) * 128;
     if (hier_phase_ != 1 && ks.local_world > 0 &&
         (callback || !(two_shot && ks.local_world == n_part && ks.shard_devs == part_dev))) {

@@ -215,6 +215,7 @@ class KVStore {
   void InterNodeSum(void* ptr, int64_t count, int dtype, int dev);
   bool hier_ = false;
   int hier_phase_ = 0;                       // 0: not inside a hierarchical push
+  bool hier_whole_keys_ = false;             // phase 1 for a Python updater: no sharding, every rank gets the sum
   struct HierBuf { void* ptr = nullptr; size_t bytes = 0; int dev = -1; };
   std::map<int, HierBuf> hier_buf_;          // per dtype: packed staging slices of one call
   std::unordered_map<int, void*> hier_base_; // per key: slice address minus the byte offset of this rank's range

@@ -374,7 +374,7 @@ void KVStore::HierPushRowSparse(KeyState& ks, const std::vector<NDArray>& vals) 
   DeviceGuard g(dev);
   cudaStream_t s = rt->Dev(dev).stream;
   rt->AcquireUser(dev);
-  if (v.ctx().is_gpu() && v.ctx().dev_id != dev) MXKV_CHECK(false) << "value must live on GPU " << dev << " or on the host";
+  MXKV_CHECK(!v.ctx().is_gpu() || v.ctx().dev_id == dev) << "value must live on GPU " << dev << " or on the host";
   PublishNnz(v);
   EnsureReplica(ks, dev);
   Replica& r = *FindReplica(ks, dev);

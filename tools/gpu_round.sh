@@ -23,6 +23,9 @@ run 120 smoke_n$N.log python __graft_entry__.py smoke
 
 if [ "$N" = "1" ]; then
   run 400 bench_n1.json python bench.py --gpus 1
+  for seg in 1048576 2097152 8388608; do      # e2e pipeline segment (default 4 Mi elements): fill/drain vs launch count
+    MXKV_B200_HOST_SEG_ELEMS=$seg run 200 bench_n1_seg$seg.json python bench.py --gpus 1 --steps 40 --no-cpu-baseline
+  done
   run 300 bench_bert_adam_n1.json python bench.py --workload bert --optimizer adam --steps 40 --no-e2e --no-cpu-baseline
   run 300 bench_bert_lamb_n1.json python bench.py --workload bert --optimizer lamb --steps 40 --no-e2e --no-cpu-baseline
   run 300 launches_n1.txt ncu --metrics gpu__time_duration.sum --clock-control none -s 10 -c 80 --csv \

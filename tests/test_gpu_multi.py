@@ -69,6 +69,26 @@ def test_sp_test_device_kat():
             assert np.all(o.asnumpy() == len(devs))
 
 
+def test_sp_nccl_store_kat():
+    """tests/python/gpu/test_nccl.py:37-52 (skipped upstream unless libmxnet was built with NCCL): kv.create('nccl'),
+    string keys, ones pushed from 1 ... n GPUs and pulled back to all of them == the number of GPUs.  The name
+    is served by the same peer-memory kernels."""
+    shapes = [(10,), (100,), (1000,), (10000,), (100000,), (2, 2), (2, 3, 4, 5, 6, 7, 8)]
+    ngpu = min(mx.num_gpus(), 8)
+    for key, shape in enumerate(shapes, 1):
+        for n_gpus in range(1, ngpu + 1):
+            kv = mx.kv.create("nccl")
+            assert kv.type == "nccl"
+            cur_key = str(key * ngpu + n_gpus)
+            kv.init(cur_key, mx.nd.ones(shape, mx.gpu(0)))
+            arr_list = [mx.nd.ones(shape, mx.gpu(x)) for x in range(n_gpus)]
+            res = [mx.nd.zeros(shape, mx.gpu(x)) for x in range(n_gpus)]
+            kv.push(cur_key, arr_list)
+            kv.pull(cur_key, res)
+            for x in range(n_gpus):
+                assert np.sum(np.abs(res[x].asnumpy() - n_gpus)) == 0, (shape, n_gpus, x)
+
+
 @pytest.mark.parametrize("optname,kw", [
     ("sgd", dict(learning_rate=0.1, momentum=0.9, wd=1e-4, rescale_grad=0.5, clip_gradient=0.7)),
     ("adam", dict(learning_rate=0.01, wd=1e-3)),

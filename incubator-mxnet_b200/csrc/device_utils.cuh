@@ -103,6 +103,10 @@ template <> struct Cvt<__nv_bfloat16> {
   __device__ static __forceinline__ float to(__nv_bfloat16 v) { return __bfloat162float(v); }
   __device__ static __forceinline__ __nv_bfloat16 from(float v) { return __float2bfloat16_rn(v); }
 };
+template <> struct Cvt<double> {          // multi_sum_sq squares float64 inputs in float (multi_sum_sq.cc:50)
+  __device__ static __forceinline__ float to(double v) { return static_cast<float>(v); }
+  __device__ static __forceinline__ double from(float v) { return static_cast<double>(v); }
+};
 
 __device__ __forceinline__ uint2 ld8(const void* p) {
   uint2 v;

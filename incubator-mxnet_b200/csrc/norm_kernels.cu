@@ -492,6 +492,9 @@ int LaunchMultiSumSq(const SumSqItem* d_items, const int64_t* d_chunk_prefix, in
     else if (dtype == kBfloat16)
       kv_sumsq_kernel<__nv_bfloat16><<<grid, kNormThreads, 0, stream>>>(d_items, d_chunk_prefix, nitems, total_chunks,
                                                                         scale, d_psum, chunk_elems);
+    else if (dtype == kFloat64)
+      kv_sumsq_kernel<double><<<grid, kNormThreads, 0, stream>>>(d_items, d_chunk_prefix, nitems, total_chunks, scale,
+                                                                 d_psum, chunk_elems);
     else
       return static_cast<int>(cudaErrorInvalidValue);
     cudaError_t e = cudaGetLastError();

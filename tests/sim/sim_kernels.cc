@@ -108,6 +108,11 @@ template <> struct H<__nv_bfloat16> {
   static __nv_bfloat16 from(float v) { return __float2bfloat16_rn(v); }
 };
 
+template <> struct H<double> {
+  static float to(double v) { return static_cast<float>(v); }
+  static double from(float v) { return static_cast<double>(v); }
+};
+
 int ToInt(const std::string& s) { return s == "true" ? 1 : (s == "false" ? 0 : atoi(s.c_str())); }
 
 // gather the n replicas of element e and add them in the reference's association order
@@ -484,6 +489,7 @@ bool SumSq(const std::vector<std::string>& t, void** args) {   // (items, prefix
   if (t[0] == "float") SumSqT<float>(items, prefix, nitems, scale, psum, chunk);
   else if (t[0] == "__half") SumSqT<__half>(items, prefix, nitems, scale, psum, chunk);
   else if (t[0] == "__nv_bfloat16") SumSqT<__nv_bfloat16>(items, prefix, nitems, scale, psum, chunk);
+  else if (t[0] == "double") SumSqT<double>(items, prefix, nitems, scale, psum, chunk);
   else return false;
   return true;
 }

@@ -227,9 +227,9 @@ void KVStore::SetOptimizer(const std::string& name, const std::vector<std::pair<
   OptimizerConfig c;
   const std::string n = Lower(name);
   c.enabled = true;
-  if (n == "sgd") { c.kind = OPT_SGD; c.lr = 0.01; }
+  if (n == "sgd") { c.kind = OPT_SGD; c.lr = 0.1; }                             // sgd.py:95
   else if (n == "adam") { c.kind = OPT_ADAM; c.lr = 0.001; }
-  else if (n == "adamw") { c.kind = OPT_ADAMW; c.lr = 0.001; }
+  else if (n == "adamw") { c.kind = OPT_ADAMW; c.lr = 0.001; c.eps = 1e-6f; }  // adamW.py:80
   else if (n == "test") { c.kind = OPT_TEST; c.lr = 0.01; }
   else if (n == "lamb") { c.kind = OPT_LAMB; c.lr = 0.001; c.eps = 1e-6f; }    // lamb.py:66-68
   else if (n == "lans") { c.kind = OPT_LANS; c.lr = 0.001; c.eps = 1e-6f; }    // lans.py:61-63

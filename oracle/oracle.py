@@ -417,8 +417,9 @@ class OracleOptimizer(object):
         self.correct_bias = correct_bias    # AdamW (adamW.py:80-88)
         self.no_trust = set(no_trust)       # LARS: indices named *gamma / *beta / *bias
         if learning_rate is None:
-            learning_rate = {"adam": 0.001, "adamw": 0.001, "lamb": 0.001, "lans": 0.001, "lars": 0.1}.get(
-                self.name, 0.01)
+            # sgd.py:95, adam.py:85, adamW.py:80, lamb.py:66, lans.py:62, lars.py:77; optimizer.py:100-101 otherwise
+            learning_rate = {"sgd": 0.1, "adam": 0.001, "adamw": 0.001, "lamb": 0.001, "lans": 0.001,
+                             "lars": 0.1}.get(self.name, 0.01)
         self.lr = learning_rate
         self.wd = wd
         self.rescale_grad = rescale_grad

@@ -323,3 +323,22 @@ def test_per_key_hyper_parameters_follow_the_python_optimizers():
     # LAMB / LARS keep the plain learning rate (their ratios are taken on the device)
     kv.set_optimizer(mx.optimizer.LAMB(learning_rate=0.02))
     assert _key_hyper(kv, 0)[0] == np.float32(0.02)
+
+
+def test_engine_defaults_are_the_reference_optimizers():
+    """A C consumer that names an optimizer without arguments gets the reference classes' defaults: learning rates
+    sgd 0.1 (sgd.py:95), adam / adamw / lamb / lans 0.001 (adam.py:85, adamW.py:80, lamb.py:66, lans.py:62),
+    lars 0.1 (lars.py:77), test 0.01 (optimizer.py:100-101); and so do the Python classes of this package."""
+    kv = mx.kv.create("device")
+    kv.init(0, mx.nd.zeros((4,)))
+    for name, lr in (("sgd", 0.1), ("adam", 0.001), ("lamb", 0.001), ("lans", 0.001), ("lars", 0.1), ("test", 0.01)):
+        check_call(_LIB.MXKVB200SetOptimizer(kv.handle, name.encode(), 0, None, None))
+        _set_count(kv, 0, 10 ** 6)                              # Adam's bias correction -> 1
+        got = _key_hyper(kv, 0)
+        assert got[0] == np.float32(lr) and got[1] == 0.0, (name, got)
+        assert mx.optimizer.create(name).learning_rate == lr, name
+    check_call(_LIB.MXKVB200SetOptimizer(kv.handle, b"adamw", 0, None, None))
+    _set_count(kv, 0, 10 ** 6)
+    lr, wd, eta = _key_hyper(kv, 0)
+    assert lr == np.float32(1.0) and eta == np.float32(0.001), (lr, eta)     # operator lr = 1, eta = learning rate
+    assert mx.optimizer.create("adamw").epsilon == 1e-6 and mx.optimizer.create("adam").epsilon == 1e-8

@@ -8,6 +8,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 import mxnet_b200 as mx
+from oracle import oracle as O
 
 shape = (4, 4)
 keys = [5, 7, 11]
@@ -369,3 +370,44 @@ def test_user_defined_python_optimizer_on_the_store():
         for o in outs:
             np.testing.assert_allclose(o.asnumpy(), want, rtol=1e-6)
     assert opt._index_update_count == {k: 3 for k in keys} and opt.num_update == 3
+
+
+@pytest.mark.parametrize("kv_store,optimizer", [("device", None), ("device", "sgd"), ("local", None), ("local", "sgd")])
+def test_bandwidth_tool_results(kv_store, optimizer):
+    # tools/bandwidth/test_measure.py:30-44 over tools/bandwidth/measure.py:76-152: the ResNet-50 key set, one
+    # gradient per GPU, per-key push(i, g, priority=i) then pull(i, w, priority=i) for two batches; the relative L1
+    # error against numpy-summed gradients (and a host-side SGD updater when an optimizer is set) stays below 1e-4
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(os.path.dirname(__file__), "..", "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    shapes = bench.keyset("resnet50")
+    devs = [mx.gpu(i) for i in range(max(1, min(mx.num_gpus(), 8)))]
+    rng = np.random.default_rng(50)
+    kv = mx.kv.create(kv_store)
+    oopt = None
+    if optimizer is not None:
+        kv.set_optimizer(mx.optimizer.create(optimizer))
+        oopt = O.OracleOptimizer(optimizer)
+    for i, s in enumerate(shapes):
+        kv.init(i, mx.nd.zeros(s))
+    grads_val = [[rng.uniform(-1, 1, s).astype(np.float32) for _ in devs] for s in shapes]
+    grads = [[mx.nd.array(g, d) for g, d in zip(gs, devs)] for gs in grads_val]
+    weights = [[mx.nd.zeros(s, d) for d in devs] for s in shapes]
+    cpu_grads = [np.sum(np.stack(gs).astype(np.float64), axis=0).astype(np.float32) for gs in grads_val]
+    cpu_weights = [np.zeros(s, np.float32) for s in shapes]
+    for _ in range(2):
+        for i, g in enumerate(grads):
+            kv.push(i, g, i)
+        for i, w in enumerate(weights):
+            kv.pull(i, w, i)
+        if oopt is None:
+            want = cpu_grads
+        else:
+            for i in range(len(shapes)):
+                oopt.update(i, cpu_weights[i], cpu_grads[i])
+            want = cpu_weights
+        num = sum(np.sum(np.abs(a.asnumpy() - b)) for w, b in zip(weights, want) for a in w)
+        den = sum(np.sum(np.abs(b)) for b in want)
+        assert num / den < 1e-4, (kv_store, optimizer, num / den)

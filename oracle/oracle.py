@@ -408,7 +408,7 @@ class OracleOptimizer(object):
 
     def __init__(self, name, learning_rate=None, wd=0.0, rescale_grad=1.0, clip_gradient=None,
                  momentum=0.0, beta1=0.9, beta2=0.999, epsilon=None, eta=None, multi_precision=False,
-                 lr_mult=None, wd_mult=None, lazy_update=True, lower_bound=None, upper_bound=None,
+                 lr_mult=None, wd_mult=None, lazy_update=False, lower_bound=None, upper_bound=None,
                  bias_correction=True, norm_mode="seq", no_trust=(), correct_bias=True, begin_num_update=0):
         self.name = name.lower()
         self.begin_num_update = begin_num_update     # optimizer.py:111-112, 445-462

@@ -320,8 +320,8 @@ class LAMB(_LayerwiseAdaptive):
     fused_name = "lamb"
 
     def __init__(self, learning_rate=0.001, beta1=0.9, beta2=0.999, epsilon=1e-6, lower_bound=None,
-                 upper_bound=None, bias_correction=True, **kwargs):
-        super(LAMB, self).__init__(learning_rate=learning_rate, **kwargs)
+                 upper_bound=None, bias_correction=True, aggregate_num=4, **kwargs):
+        super(LAMB, self).__init__(learning_rate=learning_rate, aggregate_num=aggregate_num, **kwargs)
         self.beta1, self.beta2, self.epsilon = beta1, beta2, epsilon
         self.lower_bound, self.upper_bound, self.bias_correction = lower_bound, upper_bound, bias_correction
 
@@ -344,6 +344,7 @@ class LANS(_LayerwiseAdaptive):
 
     def __init__(self, learning_rate=0.001, beta1=0.9, beta2=0.999, epsilon=1e-6, lower_bound=None,
                  upper_bound=None, **kwargs):
+        kwargs.setdefault("aggregate_num", 4)                    # lans.py:63
         super(LANS, self).__init__(learning_rate=learning_rate, **kwargs)
         self.beta1, self.beta2, self.epsilon = beta1, beta2, epsilon
         self.lower_bound, self.upper_bound = lower_bound, upper_bound

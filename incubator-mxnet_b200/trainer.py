@@ -260,7 +260,7 @@ class Trainer(object):
                     "(lamb / lans / lars); otherwise use update_on_kvstore=False"
                 scaler.update(self._kvstore.overflow())
         if not self._update_on_kvstore:
-            self._update()
+            self._update(ignore_stale_grad)
 
     def allreduce_grads(self):
         if not self._kv_initialized:
@@ -278,10 +278,10 @@ class Trainer(object):
             "update() when parameters are updated on kvstore is not supported. " \
             "Try setting `update_on_kvstore` to False when creating trainer."
         self._optimizer.rescale_grad = self._scale / batch_size
-        self._update()
+        self._update(ignore_stale_grad)
 
-    def _update(self):
-        """trainer.py:444-480: per-device local updaters.  Optimizers with a fused kernel update every
+    def _update(self, ignore_stale_grad=False):
+        """trainer.py:444-480 (gradient freshness is not tracked here, so ``ignore_stale_grad`` has nothing to do): per-device local updaters.  Optimizers with a fused kernel update every
         parameter of a device in one native launch (the reference's aggregated multi_* operators);
         the others run the generic Python updater per parameter."""
         if not hasattr(self, "_updaters"):

@@ -28,10 +28,11 @@ class Optimizer(object):
                  aggregate_num=None, use_fused_step=None, **kwargs):
         self.rescale_grad = rescale_grad
         self.lr_scheduler = lr_scheduler
-        if learning_rate is None:
+        if self.lr_scheduler is None and learning_rate is None:
             learning_rate = 0.01
         self.lr = learning_rate
-        if self.lr_scheduler is not None:
+        # an explicit learning rate overrides the scheduler's base (optimizer.py:96-105); none leaves it alone
+        if self.lr_scheduler is not None and learning_rate is not None:
             self.lr_scheduler.base_lr = learning_rate
         self.wd = wd
         self.lr_mult = {}

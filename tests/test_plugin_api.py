@@ -190,3 +190,58 @@ def test_multi_precision_protocol_of_python_optimizers():
     assert master.dtype == np.float32 and np.all(master.asnumpy() == np.float32(1 - 3 * 2.0 ** -12))
     assert w.dtype == np.float16 and np.all(w.asnumpy() == np.float16(1 - 3 * 2.0 ** -12))   # 1 - 2^-12 alone would round to 1
     assert np.all(state.asnumpy() == 3)
+
+
+# ---- tests/python/unittest/test_optimizer.py: the learning-rate plumbing and the schedulers' closed-form points ---------
+def test_learning_rate():
+    # test_optimizer.py:30-43
+    o1 = mx.optimizer.Optimizer(learning_rate=0.01)
+    o1.set_learning_rate(0.2)
+    assert o1.learning_rate == 0.2
+    lr_s = mx.lr_scheduler.FactorScheduler(step=1)
+    o2 = mx.optimizer.Optimizer(lr_scheduler=lr_s, learning_rate=0.3)
+    assert o2.learning_rate == 0.3
+    o2.lr_scheduler.base_lr = 0.4
+    assert o2.learning_rate == 0.4
+    lr_s = mx.lr_scheduler.FactorScheduler(step=1, base_lr=1024)
+    o3 = mx.optimizer.Optimizer(lr_scheduler=lr_s)
+    assert o3.learning_rate == 1024
+
+
+def test_learning_rate_expect_user_warning():
+    # test_optimizer.py:46-51
+    o = mx.optimizer.Optimizer(lr_scheduler=mx.lr_scheduler.FactorScheduler(step=1), learning_rate=0.3)
+    with pytest.raises(UserWarning):
+        o.set_learning_rate(0.5)
+
+
+def test_scheduler_known_points():
+    # test_optimizer.py:951-1005
+    sched = mx.lr_scheduler.FactorScheduler(100, 0.1, stop_factor_lr=1e-4, base_lr=1, warmup_steps=20,
+                                            warmup_begin_lr=0.1, warmup_mode="constant")
+    assert sched(0) == 0.1
+    np.testing.assert_almost_equal(sched(10), 0.1)
+    assert sched(21) == 1
+    np.testing.assert_almost_equal(sched(101), 0.1)
+    np.testing.assert_almost_equal(sched(201), 0.01)
+    np.testing.assert_almost_equal(sched(1000), 1e-4)
+    sched = mx.lr_scheduler.MultiFactorScheduler([15, 25], 0.1, base_lr=0.1, warmup_steps=10, warmup_begin_lr=0.05,
+                                                 warmup_mode="linear")
+    assert sched(0) == 0.05
+    np.testing.assert_almost_equal(sched(5), 0.05 + (0.1 - 0.05) / 2)
+    np.testing.assert_almost_equal(sched(15), 0.1)
+    np.testing.assert_almost_equal(sched(16), 0.01)
+    np.testing.assert_almost_equal(sched(20), 0.01)
+    np.testing.assert_almost_equal(sched(26), 0.001)
+    np.testing.assert_almost_equal(sched(100), 0.001)
+    poly = mx.lr_scheduler.PolyScheduler(1000, base_lr=3, pwr=2, final_lr=0, warmup_steps=100, warmup_begin_lr=0,
+                                         warmup_mode="linear")
+    np.testing.assert_almost_equal(poly(0), 0)
+    np.testing.assert_almost_equal(poly(50), 1.5)
+    np.testing.assert_almost_equal(poly(100), 3)
+    assert poly(101) < poly(100) and poly(500) < 1.6
+    np.testing.assert_almost_equal(poly(1000), 0)
+    cos = mx.lr_scheduler.CosineScheduler(1000, base_lr=3, final_lr=0.1)
+    np.testing.assert_almost_equal(cos(0), 3)
+    np.testing.assert_almost_equal(cos(1000), 0.1)
+    assert cos(500) > 1.5

@@ -67,6 +67,7 @@ int KVStore::group_size() const {
 }
 
 void KVStore::Barrier() {
+  std::lock_guard<std::recursive_mutex> rl(Runtime::Get()->mu());
   std::lock_guard<std::recursive_mutex> lk(mu_);
   Runtime* rt = Runtime::Get();
   rt->WaitAll();
@@ -141,7 +142,11 @@ KeyState& KVStore::GetKey(int key) {
 // ---------------------------------------------------------------------------
 // public entry points: key-type handling then *Impl, as kvstore_local.h:95-219
 // ---------------------------------------------------------------------------
-#define LOCK() std::lock_guard<std::recursive_mutex> lk__(mu_)
+// Entry points serialise on the runtime first (per-device streams, descriptor rings, peer tables and signal pads
+// are shared by every store of the process), then on the store: callable from any thread, in this fixed order.
+#define LOCK()                                                                  \
+  std::lock_guard<std::recursive_mutex> rt_lk__(Runtime::Get()->mu());            \
+  std::lock_guard<std::recursive_mutex> lk__(mu_)
 
 void KVStore::Init(const std::vector<int>& keys, const std::vector<NDArray>& vals) {
   LOCK(); SetKeyType(kIntKey); InitImpl(keys, vals);

@@ -12,7 +12,11 @@
 
 namespace mxkv {
 
-#define LOCK() std::lock_guard<std::recursive_mutex> lock_(mu_)
+// Entry points serialise on the runtime first (per-device streams, descriptor rings, peer tables and signal pads
+// are shared by every store of the process), then on the store: callable from any thread, in this fixed order.
+#define LOCK()                                                                  \
+  std::lock_guard<std::recursive_mutex> rt_lock_(Runtime::Get()->mu());            \
+  std::lock_guard<std::recursive_mutex> lock_(mu_)
 
 void KVStore::LaunchNormWorks(std::vector<NormClass>& classes, int opt_kind, const std::vector<int>& part_dev) {
   Runtime* rt = Runtime::Get();

@@ -242,6 +242,7 @@ DeviceState& Runtime::Dev(int dev) {
 
 bool Runtime::PeerOK(int a, int b) {
   if (a == b) return true;
+  std::lock_guard<std::recursive_mutex> lk(mu_);
   auto it = peer_ok_.find((static_cast<int64_t>(a) << 32) | b);
   return it != peer_ok_.end() && it->second;
 }

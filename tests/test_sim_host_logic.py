@@ -33,8 +33,14 @@ def _run(sim_lib, devices, files, extra=()):
     cmd = [sys.executable, "-m", "pytest", "-q", "-m", "gpu", "-p", "no:cacheprovider"] + list(extra) + \
           [os.path.join(ROOT, "tests", f) for f in files]
     r = subprocess.run(cmd, env=env, cwd=ROOT, capture_output=True, text=True, timeout=1500)
-    tail = (r.stdout + r.stderr)[-3000:]
-    assert r.returncode == 0, tail
+    if r.returncode != 0:
+        # keep everything (a crash report's traceback sits ABOVE its long list of extension modules)
+        log = os.path.join(SIM, "_build", "last_failure_%d_devices.log" % devices)
+        with open(log, "w") as f:
+            f.write(r.stdout + "\n==== stderr ====\n" + r.stderr)
+        cut = r.stderr.find("Extension modules:")
+        err = r.stderr[:cut] if cut >= 0 else r.stderr
+        assert False, "exit code %d (full output in %s)\n%s\n%s" % (r.returncode, log, r.stdout[-1500:], err[-3000:])
     return r.stdout
 
 

@@ -27,10 +27,20 @@ def sim_lib():
     return lib
 
 
+def _workers():
+    """the inner runs are hundreds of independent small tests: spread them over a few processes (each has its own
+    simulated GPUs) when pytest-xdist is there"""
+    try:
+        import xdist  # noqa: F401
+    except ImportError:
+        return []
+    return ["-n", str(max(1, min(4, (os.cpu_count() or 2) // 2)))]
+
+
 def _run(sim_lib, devices, files, extra=()):
     env = dict(os.environ)
     env.update(MXKV_SIM="1", MXKV_B200_LIBRARY_PATH=sim_lib, MXKV_SIM_DEVICES=str(devices))
-    cmd = [sys.executable, "-m", "pytest", "-q", "-m", "gpu", "-p", "no:cacheprovider"] + list(extra) + \
+    cmd = [sys.executable, "-m", "pytest", "-q", "-m", "gpu", "-p", "no:cacheprovider"] + _workers() + list(extra) + \
           [os.path.join(ROOT, "tests", f) for f in files]
     r = subprocess.run(cmd, env=env, cwd=ROOT, capture_output=True, text=True, timeout=1500)
     if r.returncode != 0:
@@ -85,7 +95,7 @@ def test_host_code_under_address_and_ub_sanitizers():
     env.update(san)
     env.update(MXKV_SIM="1", MXKV_B200_LIBRARY_PATH=lib, MXKV_SIM_DEVICES="4")
     cmd = [sys.executable, "-m", "pytest", "-q", "-m", "gpu", "-p", "no:cacheprovider", "-x",
-           "-k", "not one_process_per_gpu"] + \
+           "-k", "not one_process_per_gpu"] + _workers() + \
           [os.path.join(ROOT, "tests", f) for f in ("test_gpu_placement.py", "test_gpu_multi.py", "test_gpu_rsp.py",
                                                     "test_gpu_updater.py")]
     r = subprocess.run(cmd, env=env, cwd=ROOT, capture_output=True, text=True, timeout=1500)

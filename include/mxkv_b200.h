@@ -11,6 +11,13 @@
  * bootstrap, symmetric allocation).
  *
  * Plain C: opaque handles, pointers and sizes only.
+ *
+ * Threading: every entry point may be called from any thread, like the reference's.  KVStore calls
+ * are serialised per process first (the per-GPU streams, descriptor rings and staging slots are shared by all
+ * stores) and per store second; they only ENQUEUE work and return -- results are ordered per array on the
+ * engine's streams, and MXNDArrayWaitToRead / WaitAll (or the caller's own stream, see MXKVB200SetStream)
+ * observe them.  The updater callback runs on the calling thread, inside the call.  The error string of
+ * MXGetLastError is per thread.
  */
 #ifndef MXKV_B200_H_
 #define MXKV_B200_H_

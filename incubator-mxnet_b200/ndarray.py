@@ -291,9 +291,16 @@ def empty(shape, ctx=None, dtype=np.float32, stype="default", capacity=None):
 
 
 def array(source, ctx=None, dtype=None):
-    src = np.asarray(source)
-    if dtype is None:
-        dtype = src.dtype if src.dtype in _DTYPE_NP_TO_MX and src.dtype != np.float64 else np.float32
+    """ndarray.py:3378-3418: an NDArray source keeps its dtype; anything else becomes float32 unless ``dtype`` says
+    otherwise (numpy's own dtype is NOT taken over)."""
+    if isinstance(source, NDArray):
+        if dtype is None:
+            dtype = source.dtype
+        src = source.asnumpy(raw=True) if source.dtype == "bfloat16" else source.asnumpy()
+    else:
+        src = np.asarray(source)
+        if dtype is None:
+            dtype = np.float32
     out = empty(src.shape, ctx, dtype)
     out._sync_copyfrom(src)
     return out

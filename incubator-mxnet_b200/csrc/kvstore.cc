@@ -232,6 +232,7 @@ void KVStore::SetOptimizer(const std::string& name, const std::vector<std::pair<
   OptimizerConfig c;
   const std::string n = Lower(name);
   c.enabled = true;
+  bool reset_states = false;
   if (n == "sgd") { c.kind = OPT_SGD; c.lr = 0.1; }                             // sgd.py:95
   else if (n == "adam") { c.kind = OPT_ADAM; c.lr = 0.001; }
   else if (n == "adamw") { c.kind = OPT_ADAMW; c.lr = 0.001; c.eps = 1e-6f; }  // adamW.py:80
@@ -262,6 +263,7 @@ void KVStore::SetOptimizer(const std::string& name, const std::vector<std::pair<
     else if (k == "lazy_update") c.lazy_update = (v == "True" || v == "true" || v == "1");
     else if (k == "correct_bias") c.correct_bias = (v == "True" || v == "true" || v == "1");
     else if (k == "multi_precision") c.multi_precision = (v == "True" || v == "true" || v == "1");
+    else if (k == "reset_states") reset_states = (v == "True" || v == "true" || v == "1");
     else MXKV_FATAL() << "unknown optimizer argument '" << k << "'";
   }
   if (c.kind == OPT_SGD && c.momentum != 0.f) c.kind = OPT_SGD_MOM;   // sgd.py:213-224
@@ -270,6 +272,23 @@ void KVStore::SetOptimizer(const std::string& name, const std::vector<std::pair<
   c.wd_mult = opt_.wd_mult;
   c.no_trust = opt_.no_trust;
   opt_ = c;
+  if (reset_states) {
+    // a NEW optimizer starts from fresh state, like the new Updater the reference creates in set_optimizer
+    // (kvstore.py:559-606); re-sending the hyper-parameters of the current one (rescale_grad per batch size,
+    // a scheduled learning rate) keeps it
+    Runtime::Get()->WaitAll();
+    for (auto& kv : keys_) {
+      KeyState& ks = kv.second;
+      for (auto& r : ks.reps) {
+        r.w32 = NDArray(); r.s0 = NDArray(); r.s1 = NDArray();
+        r.aux0 = NDArray(); r.aux1 = NDArray();
+        r.state_fresh = true;
+      }
+      ks.state_world = 0;
+      ks.state_devs.clear();
+      ks.has_state = false;
+    }
+  }
 }
 
 void KVStore::SetKeyFlag(bool str_key, int ikey, const std::string& skey, const std::string& name, int value) {

@@ -262,10 +262,13 @@ class KVStore(KVStoreBase):
     def set_optimizer(self, optimizer):
         """Recognised optimizers run fused inside the reduce kernel; anything else goes through
         the Python updater callback like the reference (kvstore.py:559-606)."""
+        fresh = optimizer is not self._optimizer          # a new optimizer object: new (empty) state, as in the reference
         self._optimizer = optimizer
         self._synced = set()
         if getattr(optimizer, "fused_name", None):
             kw = optimizer.fused_kwargs()
+            if fresh:
+                kw["reset_states"] = True
             keys = list(kw.keys())
             vals = [str(kw[k]) for k in keys]
             check_call(_LIB.MXKVB200SetOptimizer(self.handle, c_str(optimizer.fused_name), len(keys),

@@ -346,3 +346,43 @@ def test_update_count_follows_the_python_optimizer(tmp_path):
     for g in gs[4:]:
         o3.update(3, ow, g)
         assert_bits_equal(push(kv3, g), ow, "loaded moments, t from 1")
+
+
+def test_a_new_optimizer_starts_from_fresh_state():
+    """kvstore.py:559-606: set_optimizer installs a NEW updater, so the momentum of the previous optimizer is gone
+    (and never reinterpreted as another optimizer's state); handing the SAME optimizer object again (what the
+    Trainer does when rescale_grad changes with the batch size) keeps the state."""
+    rng = np.random.default_rng(77)
+    E = 4099
+    w0 = rng.uniform(-1, 1, E).astype(np.float32)
+    gs = [rng.uniform(-1, 1, E).astype(np.float32) for _ in range(6)]
+
+    def push(kv, g):
+        kv.push(0, mx.nd.array(g, mx.gpu(0)))
+        o = mx.nd.empty((E,), mx.gpu(0))
+        kv.pull(0, out=o)
+        return o.asnumpy()
+
+    kv = mx.kv.create("device")
+    kv.init(0, mx.nd.array(w0, mx.gpu(0)))
+    sgd = mx.optimizer.SGD(learning_rate=0.1, momentum=0.9)
+    kv.set_optimizer(sgd)
+    o1 = O.OracleOptimizer("sgd", learning_rate=0.1, momentum=0.9)
+    ow = w0.copy()
+    for g in gs[:2]:
+        o1.update(0, ow, g)
+        assert_bits_equal(push(kv, g), ow, "sgd momentum")
+    sgd.rescale_grad = 0.5                                  # same object, new hyper-parameter: momentum carries on
+    kv.set_optimizer(sgd)
+    o1.rescale_grad = 0.5
+    o1.update(0, ow, gs[2])
+    assert_bits_equal(push(kv, gs[2]), ow, "same optimizer again keeps its state")
+    kv.set_optimizer(mx.optimizer.Adam(learning_rate=0.01))   # a new optimizer: fresh mean / variance, t = 1
+    o2 = O.OracleOptimizer("adam", learning_rate=0.01)
+    for g in gs[3:5]:
+        o2.update(0, ow, g)
+        assert_bits_equal(push(kv, g), ow, "adam after sgd starts from zero moments")
+    kv.set_optimizer(mx.optimizer.SGD(learning_rate=0.1, momentum=0.9))   # and back: the old momentum is not revived
+    o3 = O.OracleOptimizer("sgd", learning_rate=0.1, momentum=0.9)
+    o3.update(0, ow, gs[5])
+    assert_bits_equal(push(kv, gs[5]), ow, "a second sgd starts with zero momentum")

@@ -208,20 +208,21 @@ void KVStore::SetUpdater(UpdaterFn fn, StrUpdaterFn sfn, void* handle) {
 
 void KVStore::SetGradientCompression(const std::vector<std::pair<std::string, std::string>>& kwargs) {
   LOCK();
-  // GradientCompression::SetParams, src/kvstore/gradient_compression.cc:45-60
+  // GradientCompression::SetParams (src/kvstore/gradient_compression.cc:40-52): `type` (default "none") and
+  // `threshold` (default 0.5) are read, other arguments are allowed and ignored (InitAllowUnknown), and a type
+  // other than 1bit / 2bit is an error -- "none" included
+  std::string type = "none";
+  float threshold = 0.5f;
   for (auto& kv : kwargs) {
-    if (kv.first == "type") {
-      MXKV_CHECK(kv.second == "1bit" || kv.second == "2bit" || kv.second == "none")
-          << "Unknown type for gradient compression " << kv.second;
-      gc_type_ = kv.second;
-    } else if (kv.first == "threshold") {
-      gc_threshold_ = std::stof(kv.second);
-      MXKV_CHECK(gc_threshold_ > 0 || gc_type_ == "1bit") << "threshold must be greater than 0";
-    } else {
-      MXKV_FATAL() << "Cannot find argument '" << kv.first << "' for gradient compression";
-    }
+    if (kv.first == "type") type = kv.second;
+    else if (kv.first == "threshold") threshold = std::stof(kv.second);
   }
-  gc_bits_ = gc_type_ == "2bit" ? 2 : (gc_type_ == "1bit" ? 1 : 0);
+  MXKV_CHECK(type == "1bit" || type == "2bit") << "Unknown type for gradient compression " << type;
+  if (type == "2bit") MXKV_CHECK(threshold > 0) << "threshold must be greater than 0 for two bit compression";
+  gc_type_ = type;
+  gc_threshold_ = threshold;
+  // only the device comm compresses (CommDevice::ReduceCompressed, comm.h:556-605); CommCPU sums what it is given
+  gc_bits_ = !device_mode_ ? 0 : (type == "2bit" ? 2 : 1);
 }
 
 // ---------------------------------------------------------------------------

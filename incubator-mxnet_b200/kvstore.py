@@ -250,6 +250,9 @@ class KVStore(KVStoreBase):
         return r.value
 
     def set_gradient_compression(self, compression_params):
+        """kvstore.py:505-557: 'device' and 'dist' stores only"""
+        if not (("device" in self.type) or ("dist" in self.type)):
+            raise Exception("Gradient compression is not supported for this type of kvstore")
         keys = list(compression_params.keys())
         vals = [str(compression_params[k]) for k in keys]
         check_call(_LIB.MXKVStoreSetGradientCompression(self.handle, len(keys), c_str_array(keys),

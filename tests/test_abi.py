@@ -118,6 +118,16 @@ def test_optimizer_descriptors():
     kv.set_gradient_compression({"type": "2bit", "threshold": 0.5})
     with pytest.raises(mx.MXNetError, match="Unknown type for gradient compression"):
         kv.set_gradient_compression({"type": "3bit"})
+    # gradient_compression.cc:40-52: no type means "none", which is refused; 2bit needs a positive threshold (given
+    # in any order); arguments the parameter struct does not know are allowed; kvstore.py:551-557: other store types
+    # refuse compression altogether
+    with pytest.raises(mx.MXNetError, match="Unknown type for gradient compression none"):
+        kv.set_gradient_compression({"threshold": 0.5})
+    with pytest.raises(mx.MXNetError, match="threshold must be greater than 0"):
+        kv.set_gradient_compression({"threshold": 0, "type": "2bit"})
+    kv.set_gradient_compression({"type": "1bit", "threshold": 0, "some_future_option": 3})
+    with pytest.raises(Exception, match="not supported for this type of kvstore"):
+        mx.kv.create("local").set_gradient_compression({"type": "2bit", "threshold": 0.5})
     assert mx.kv.KVStore.is_capable("optimizer")
     assert isinstance(mx.kv.create("b200device"), mx.kv.KVStore)      # registry path, base.py:450-452
 

@@ -17,7 +17,7 @@ static std::string Lower(std::string s) {
 // KVStore::Create, src/kvstore/kvstore.cc:42-85: substring dispatch on the lower-cased
 // type.  'device' selects the on-GPU reduce (CommDevice association order); the other
 // local types select CommCPU's association order -- the arithmetic still runs on the GPU.
-KVStore::KVStore(const std::string& type) : type_(type) {
+KVStore::KVStore(const std::string& type) : type_(Lower(type)) {   // kvstore.cc:43-44,83: the type is kept lower-cased
   const std::string t = Lower(type);
   const bool dist = t.find("dist") != std::string::npos;
   if (dist) {

@@ -45,6 +45,7 @@ def test_host_only_entry_points():
         kv = mx.kv.create(t)
         assert kv.type == t                 # tests/python/unittest/test_kvstore.py:276-279
         assert kv.rank == 0 and kv.num_workers == 1
+    assert mx.kv.create("Device").type == "device"          # src/kvstore/kvstore.cc:43-44,83: lower-cased
     with pytest.raises(mx.MXNetError):
         mx.kv.create("dist_sync")
     w = ctypes.c_int()

@@ -19,6 +19,8 @@ from . import kvstore as kv
 from .kvstore import KVStore, KVStoreBase, create
 from . import dist
 from .trainer import Trainer
+from . import gluon
+from . import context
 from . import amp
 
 __version__ = "0.1.0"

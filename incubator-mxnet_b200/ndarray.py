@@ -470,3 +470,15 @@ def multi_all_finite(*arrays, **kwargs):
 
 def waitall():
     check_call(_LIB.MXNDArrayWaitAll())
+
+
+class _SparseNamespace(object):
+    """``mx.nd.sparse``: the two constructors of python/mxnet/ndarray/sparse.py the KVStore tests use"""
+    row_sparse_array = staticmethod(row_sparse_array)
+
+    @staticmethod
+    def zeros(stype, shape, ctx=None, dtype=np.float32):
+        return zeros(shape, ctx, dtype, stype=stype)
+
+
+sparse = _SparseNamespace()

@@ -278,7 +278,7 @@ def main():
     #    host-resident gradients and outputs, pushes and fused pushpulls, pulls, every optimizer family
     opts = [(None, {}), ("sgd", dict(learning_rate=0.05, momentum=0.9, wd=1e-3)), ("adam", dict(learning_rate=0.01, wd=1e-3)),
             ("adamw", dict(learning_rate=0.01, wd=0.05)), ("lars", dict(learning_rate=0.1, momentum=0.9, wd=1e-3, eta=0.01))]
-    for walk in range(5):
+    for walk in range(5 * (1 + int(os.environ.get("MXKV_FUZZ_SEEDS", "0")))):      # soak runs: more walks
         wr = np.random.default_rng(31337 + walk)               # the walk itself: identical on every rank
         optname, kw = opts[walk % len(opts)]
         layerwise = optname == "lars"

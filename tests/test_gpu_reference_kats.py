@@ -222,56 +222,6 @@ def test_aggregator(stype):
     check_aggregator(init_kv_with_str("cpu"), "a", str_keys)
 
 
-@pytest.mark.parametrize("sparse_pull", [False, True])
-@pytest.mark.parametrize("dev", ["cpu", "gpu"])
-def test_sparse_aggregator(sparse_pull, dev):
-    # tests/python/unittest/test_kvstore.py:174-220: row_sparse keys, random row_sparse values on four contexts,
-    # pushed and then read back INTO THE SAME ARRAYS, either with row_sparse_pull of every row or with
-    # pull(ignore_sparse=False); single key, then the key list with one shared list of values
-    rng = np.random.default_rng(11 + int(sparse_pull))
-
-    def rand_rsp(ctx):
-        dense = rng.normal(size=shape).astype(np.float32)
-        dense[rng.random(shape[0]) < 0.5] = 0                     # rand_ndarray: random density
-        return mx.nd.array(dense, ctx).tostype("row_sparse")
-
-    kv = mx.kv.create("device")
-    kv.init("a", mx.nd.zeros(shape, stype="row_sparse"))
-    kv.init(str_keys, [mx.nd.zeros(shape, stype="row_sparse")] * len(keys))
-    num_devs = 4
-    devs = [ctx_of(dev, i) for i in range(num_devs)]
-    all_rows = mx.nd.array(np.arange(shape[0]), dtype=np.float32)
-
-    vals = [rand_rsp(d) for d in devs]
-    expected_sum = np.zeros(shape)
-    for v in vals:
-        expected_sum += v.todense_numpy()
-    kv.push("a", vals)
-    if sparse_pull:
-        kv.row_sparse_pull("a", out=vals, row_ids=[all_rows] * len(vals))
-    else:
-        kv.pull("a", out=vals, ignore_sparse=False)
-    result_sum = np.zeros(shape)
-    for v in vals:
-        result_sum += v.todense_numpy()
-    np.testing.assert_allclose(result_sum, expected_sum * num_devs, rtol=1e-5, atol=1e-6)
-
-    vals = [[rand_rsp(d) for d in devs]] * len(keys)
-    expected_sum = np.zeros(shape)
-    for v in vals[0]:
-        expected_sum += v.todense_numpy()
-    kv.push(str_keys, vals)
-    if sparse_pull:
-        kv.row_sparse_pull(str_keys, out=vals, row_ids=[[all_rows] * num_devs] * len(vals))
-    else:
-        kv.pull(str_keys, out=vals, ignore_sparse=False)
-    for vv in vals:
-        result_sum = np.zeros(shape)
-        for v in vv:
-            result_sum += v.todense_numpy()
-        np.testing.assert_allclose(result_sum, expected_sum * num_devs, rtol=1e-5, atol=1e-6)
-
-
 @pytest.mark.parametrize("kv_type", ["local", "device"])
 @pytest.mark.parametrize("push_on_gpu", [False, True])
 def test_rsp_push_pull(kv_type, push_on_gpu):
@@ -340,74 +290,3 @@ def test_row_sparse_pull_single_device_and_large_rowid():
     kv.row_sparse_pull("a", out=out, row_ids=mx.nd.array(np.arange(num_rows, dtype=np.int64), mx.gpu(0), dtype=np.int64))
     assert out.indices.shape[0] == num_rows
     assert np.all(out.data.asnumpy() == 1.0)
-
-
-def test_user_defined_python_optimizer_on_the_store():
-    # kvstore.py:559-606: an optimizer without a fused kernel runs through the updater callback, on the merged
-    # value, once per pushed key; written against the reference's Optimizer protocol (list-valued step that
-    # counts the update itself)
-    @mx.optimizer.register
-    class HalfStep(mx.optimizer.Optimizer):
-        def create_state(self, index, weight):
-            return mx.nd.zeros(weight.shape, weight.context)
-
-        def step(self, indices, weights, grads, states):
-            self._update_count(indices)
-            for i, w, g, s, lr in zip(indices, weights, grads, states, self._get_lrs(indices)):
-                s[:] = s.asnumpy() + 1
-                w[:] = w.asnumpy() - lr * self.rescale_grad * g.asnumpy() / s.asnumpy()
-
-    kv = mx.kv.create("device")
-    kv.init(keys, [mx.nd.ones(shape, mx.gpu(0))] * len(keys))
-    opt = mx.optimizer.create("halfstep", learning_rate=0.5, rescale_grad=0.25)
-    kv.set_optimizer(opt)
-    want = np.ones(shape, np.float32)
-    for step in (1, 2, 3):
-        kv.push(keys, [[mx.nd.ones(shape, mx.gpu(0)) * 2.0 for _ in range(4)]] * len(keys))
-        want = want - np.float32(0.5 * 0.25) * np.float32(8.0) / np.float32(step)
-        outs = [mx.nd.empty(shape, mx.gpu(0)) for _ in keys]
-        kv.pull(keys, out=outs)
-        for o in outs:
-            np.testing.assert_allclose(o.asnumpy(), want, rtol=1e-6)
-    assert opt._index_update_count == {k: 3 for k in keys} and opt.num_update == 3
-
-
-@pytest.mark.parametrize("kv_store,optimizer", [("device", None), ("device", "sgd"), ("local", None), ("local", "sgd")])
-def test_bandwidth_tool_results(kv_store, optimizer):
-    # tools/bandwidth/test_measure.py:30-44 over tools/bandwidth/measure.py:76-152: the ResNet-50 key set, one
-    # gradient per GPU, per-key push(i, g, priority=i) then pull(i, w, priority=i) for two batches; the relative L1
-    # error against numpy-summed gradients (and a host-side SGD updater when an optimizer is set) stays below 1e-4
-    import importlib.util
-    import os
-    spec = importlib.util.spec_from_file_location("bench", os.path.join(os.path.dirname(__file__), "..", "bench.py"))
-    bench = importlib.util.module_from_spec(spec)
-    spec.loader.exec_module(bench)
-    shapes = bench.keyset("resnet50")
-    devs = [mx.gpu(i) for i in range(max(1, min(mx.num_gpus(), 8)))]
-    rng = np.random.default_rng(50)
-    kv = mx.kv.create(kv_store)
-    oopt = None
-    if optimizer is not None:
-        kv.set_optimizer(mx.optimizer.create(optimizer))
-        oopt = O.OracleOptimizer(optimizer)
-    for i, s in enumerate(shapes):
-        kv.init(i, mx.nd.zeros(s))
-    grads_val = [[rng.uniform(-1, 1, s).astype(np.float32) for _ in devs] for s in shapes]
-    grads = [[mx.nd.array(g, d) for g, d in zip(gs, devs)] for gs in grads_val]
-    weights = [[mx.nd.zeros(s, d) for d in devs] for s in shapes]
-    cpu_grads = [np.sum(np.stack(gs).astype(np.float64), axis=0).astype(np.float32) for gs in grads_val]
-    cpu_weights = [np.zeros(s, np.float32) for s in shapes]
-    for _ in range(2):
-        for i, g in enumerate(grads):
-            kv.push(i, g, i)
-        for i, w in enumerate(weights):
-            kv.pull(i, w, i)
-        if oopt is None:
-            want = cpu_grads
-        else:
-            for i in range(len(shapes)):
-                oopt.update(i, cpu_weights[i], cpu_grads[i])
-            want = cpu_weights
-        num = sum(np.sum(np.abs(a.asnumpy() - b)) for w, b in zip(weights, want) for a in w)
-        den = sum(np.sum(np.abs(b)) for b in want)
-        assert num / den < 1e-4, (kv_store, optimizer, num / den)

@@ -156,41 +156,3 @@ def test_sp_multi_gpu_sources():
             want = O.sparse_retain(okv.local[0], O.unique(ids))
             assert np.array_equal(out.indices.asnumpy(), want.indices)
             assert _bits_equal(out.data.asnumpy(), want.data.reshape(-1, L)), (step, d)
-
-
-@pytest.mark.parametrize("lazy", [True, False])
-@pytest.mark.parametrize("optname,kw", [
-    ("sgd", dict(learning_rate=0.1, wd=1e-3, momentum=0.9)),
-    ("adam", dict(learning_rate=0.01, wd=1e-3)),
-])
-def test_dense_key_takes_row_sparse_and_dense_gradients(optname, kw, lazy):
-    """A DENSE weight updated on the store with row_sparse gradients (gluon Parameter(grad_stype='row_sparse')
-    with update_on_kvstore=True, trainer.py:204-236; SGDUpdateDnsRspImpl / SGDMomLazy... / AdamLazy... on a dense
-    weight): the key stays dense -- plain pull and pushpull keep working --, dense and row_sparse pushes may
-    alternate, the optimizer state is shared between the two kinds of update, and with several GPUs the sharded
-    state of a large dense push is gathered before the rows are updated."""
-    kw = dict(kw, lazy_update=lazy)
-    devs = list(range(min(mx.num_gpus(), 4)))
-    rng = np.random.default_rng(21)
-    rows, L, nnz = 3000, 64, 200                       # 768 KB: a dense push from several GPUs is sharded
-    shape = (rows, L)
-    w0 = rng.uniform(0, 1, shape).astype(np.float32)
-    kv = mx.kv.create("device")
-    kv.init(7, mx.nd.array(w0, mx.gpu(0)))
-    kv.set_optimizer(mx.optimizer.create(optname, **kw))
-    okv = O.OracleKVStore("device")
-    okv.init(7, w0.copy())
-    okv.set_optimizer(O.OracleOptimizer(optname, **kw))
-    for step, kind in enumerate(["rsp", "dense", "rsp", "rsp", "dense", "rsp"]):
-        if kind == "rsp":
-            srcs = [_rand_rsp(rng, rows, L, nnz) for _ in devs]
-            kv.push(7, [_mk(i, v, shape, mx.gpu(d)) for (i, v), d in zip(srcs, devs)])
-            okv.push(7, [O.RowSparse(i, v, shape) for i, v in srcs])
-        else:
-            gs = [rng.uniform(-1, 1, shape).astype(np.float32) for _ in devs]
-            kv.push(7, [mx.nd.array(g, mx.gpu(d)) for g, d in zip(gs, devs)])
-            okv.push(7, gs)
-        for d in devs:
-            out = mx.nd.empty(shape, mx.gpu(d))
-            kv.pull(7, out=out)
-            assert _bits_equal(out.asnumpy(), okv.local[7]), (optname, lazy, step, kind, d)

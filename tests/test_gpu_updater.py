@@ -138,28 +138,3 @@ def test_rejects_misuse():
     upd = mx.optimizer.get_updater(mx.optimizer.SGD(learning_rate=0.1))
     with pytest.raises(MXNetError):           # gradient on the host
         upd(0, mx.nd.zeros((8,), mx.cpu()), w)
-
-
-def test_update_count_is_the_optimizers():
-    """begin_num_update and an optimizer that has already been stepping: the native updater's t follows the
-    optimizer's table (optimizer.py:445-462), like the reference's Updater"""
-    rng = np.random.default_rng(12)
-    w0 = rng.uniform(-1, 1, 500).astype(np.float32)
-    gs = [rng.uniform(-1, 1, 500).astype(np.float32) for _ in range(4)]
-    kw = dict(learning_rate=0.01, begin_num_update=5)
-    opt = mx.optimizer.Adam(**kw)
-    oopt = O.OracleOptimizer("adam", **kw)
-    ow = w0.copy()
-    w = mx.nd.array(w0, mx.gpu(0))
-    upd = mx.optimizer.get_updater(opt)
-    for g in gs[:2]:
-        upd(0, mx.nd.array(g, mx.gpu(0)), w)
-        oopt.update(0, ow, g)
-        assert _bits_equal(w.asnumpy(), ow)
-    assert opt._index_update_count[0] == 7
-    upd2 = mx.optimizer.get_updater(opt)            # a second updater, same optimizer: t goes on, moments restart
-    oopt.states.pop(0)
-    for g in gs[2:]:
-        upd2(0, mx.nd.array(g, mx.gpu(0)), w)
-        oopt.update(0, ow, g)
-        assert _bits_equal(w.asnumpy(), ow)

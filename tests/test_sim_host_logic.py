@@ -63,7 +63,7 @@ def _passed(out):
 def test_single_gpu_paths(sim_lib):
     out = _run(sim_lib, 1, ["test_gpu_dense.py", "test_gpu_reference_kats.py", "test_gpu_rsp.py",
                             "test_gpu_norm_opt.py", "test_gpu_compression.py", "test_gpu_updater.py",
-                            "test_gpu_trainer_nd.py", "test_gpu_zz_threads.py"])
+                            "test_gpu_y_trainer_nd.py", "test_gpu_y_semantics.py", "test_gpu_zz_threads.py"])
     assert _passed(out) >= 100, out[-500:]
 
 
@@ -72,7 +72,7 @@ def test_single_process_multi_gpu_paths(sim_lib, devices):
     """one-shot and two-shot (sharded) exchange, sharded optimizer state, layer-wise optimizers with norms added
     across the shards, compression, the updater callback -- over 2, 4 and 8 simulated GPUs."""
     out = _run(sim_lib, devices, ["test_gpu_multi.py", "test_gpu_compression.py", "test_gpu_rsp.py",
-                                  "test_gpu_placement.py", "test_gpu_trainer_nd.py", "test_gpu_zz_threads.py"],
+                                  "test_gpu_y_placement.py", "test_gpu_y_trainer_nd.py", "test_gpu_y_semantics.py", "test_gpu_zz_threads.py"],
                extra=["-k", "not one_process_per_gpu"])
     assert _passed(out) >= 30, out[-500:]
 
@@ -96,7 +96,7 @@ def test_host_code_under_address_and_ub_sanitizers():
     env.update(MXKV_SIM="1", MXKV_B200_LIBRARY_PATH=lib, MXKV_SIM_DEVICES="4")
     cmd = [sys.executable, "-m", "pytest", "-q", "-m", "gpu", "-p", "no:cacheprovider", "-x",
            "-k", "not one_process_per_gpu"] + _workers() + \
-          [os.path.join(ROOT, "tests", f) for f in ("test_gpu_placement.py", "test_gpu_multi.py", "test_gpu_rsp.py",
+          [os.path.join(ROOT, "tests", f) for f in ("test_gpu_y_placement.py", "test_gpu_multi.py", "test_gpu_rsp.py",
                                                     "test_gpu_updater.py")]
     r = subprocess.run(cmd, env=env, cwd=ROOT, capture_output=True, text=True, timeout=1500)
     tail = (r.stdout + r.stderr)[-4000:]

@@ -273,6 +273,9 @@ void KVStore::SetOptimizer(const std::string& name, const std::vector<std::pair<
   c.wd_mult = opt_.wd_mult;
   c.no_trust = opt_.no_trust;
   opt_ = c;
+  // the reference's set_optimizer REPLACES the updater (python/mxnet/kvstore/kvstore.py:559-606): a callback
+  // installed for an earlier optimizer must not keep running in front of the fused kernel
+  updater_ = nullptr; str_updater_ = nullptr; updater_handle_ = nullptr;
   if (reset_states) {
     // a NEW optimizer starts from fresh state, like the new Updater the reference creates in set_optimizer
     // (kvstore.py:559-606); re-sending the hyper-parameters of the current one (rescale_grad per batch size,

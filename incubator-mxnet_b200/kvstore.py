@@ -268,7 +268,12 @@ class KVStore(KVStoreBase):
         fresh = optimizer is not self._optimizer          # a new optimizer object: new (empty) state, as in the reference
         self._optimizer = optimizer
         self._synced = set()
-        if getattr(optimizer, "fused_name", None):
+        if opt.fused_name_of(optimizer):
+            if self._updater is not None:
+                # the reference's set_optimizer always REPLACES the updater (kvstore.py:559-606): a callback
+                # left over from an earlier optimizer must not keep running
+                check_call(_LIB.MXKVStoreSetUpdaterEx(self.handle, None, None, None))
+                self._updater = None
             kw = optimizer.fused_kwargs()
             if fresh:
                 kw["reset_states"] = True

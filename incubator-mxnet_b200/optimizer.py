@@ -469,6 +469,31 @@ class Updater(object):
         self.states_synced = dict.fromkeys(self.states, True)
 
 
+_FUSED_METHODS = ("step", "fused_step", "update", "update_multi_precision", "create_state",
+                  "create_state_multi_precision", "fused_kwargs")
+
+
+def fused_name_of(optimizer):
+    """Name of the engine's fused kernel for ``optimizer``, or None when the Python path must run:
+    the class has no fused kernel, the caller asked for ``use_fused_step=False``
+    (optimizer.py:287-318), or a user subclass overrides a method the fused kernel stands in for
+    (its ``step`` would otherwise be silently ignored)."""
+    name = getattr(optimizer, "fused_name", None)
+    if not name:
+        return None
+    if optimizer.__dict__.get("use_fused_step", None) is False:
+        return None
+    cls = type(optimizer)
+    owner = next((c for c in cls.__mro__ if c.__dict__.get("fused_name") == name), None)
+    if owner is None:
+        return None
+    if cls is not owner:
+        for m in _FUSED_METHODS:
+            if getattr(cls, m, None) is not getattr(owner, m, None):
+                return None
+    return name
+
+
 class NativeUpdater(object):
     """Same call contract as :class:`Updater` (updater.py:39-93; ``index`` / ``grad`` / ``weight`` may be
     lists), but the whole list is updated IN PLACE by one fused launch (sequence) of the native engine
@@ -478,7 +503,7 @@ class NativeUpdater(object):
 
     def __init__(self, optimizer):
         from . import kvstore as _kvs
-        assert getattr(optimizer, "fused_name", None), "no fused kernel for %s" % type(optimizer).__name__
+        assert fused_name_of(optimizer), "no fused kernel for %s" % type(optimizer).__name__
         self.optimizer = optimizer
         self._kv = _kvs.KVStore("updater")
         self._kw = None
@@ -544,5 +569,5 @@ def get_updater(optimizer, native=None):
     """updater.py:130-143.  ``native`` (default: whenever the optimizer has a fused kernel) selects the
     engine-side multi-tensor updater; otherwise the generic Python one."""
     if native is None:
-        native = bool(getattr(optimizer, "fused_name", None))
+        native = bool(fused_name_of(optimizer))
     return NativeUpdater(optimizer) if native else Updater(optimizer)

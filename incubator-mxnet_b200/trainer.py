@@ -247,7 +247,10 @@ class Trainer(object):
         if not self._kv_initialized:
             self._init_kvstore()
         elif self._update_on_kvstore and self._kvstore is not None and \
+                getattr(self._kvstore, "_fused", False) and \
                 getattr(self._kvstore, "_last_rescale", None) != self._optimizer.rescale_grad:
+            # only the fused engine holds a COPY of the hyper-parameters; a Python Updater reads
+            # optimizer.rescale_grad live (updater.py:39-93), re-installing it would drop its states
             self._kvstore.set_optimizer(self._optimizer)
         scaler = getattr(self, "_amp_loss_scaler", None)
         if self._kvstore is not None:
@@ -306,6 +309,8 @@ class Trainer(object):
         if self._update_on_kvstore:
             self._kvstore.save_optimizer_states(fname, dump_optimizer=True)
         else:
+            if not hasattr(self, "_updaters"):      # before the first step: the reference creates them at init
+                self._updaters = [_opt.get_updater(self._optimizer) for _ in range(len(self._params[0]))]
             with open(fname, "wb") as f:
                 f.write(self._updaters[0].get_states(dump_optimizer=True))
 

@@ -365,3 +365,70 @@ def test_fused_adamw():
         kv.push(0, mx.nd.ones((E,), mx.gpu(0)))
         kv.pull(0, out=out)
         assert_bits_equal(out.asnumpy(), w0, "adamw rescale %r (push/pull)" % bad)
+
+
+def _halfstep_cls(name):
+    @mx.optimizer.register
+    class _HS(mx.optimizer.Optimizer):
+        def create_state(self, index, weight):
+            return mx.nd.zeros(weight.shape, weight.context)
+
+        def step(self, indices, weights, grads, states):
+            self._update_count(indices)
+            for i, w, g, s, lr in zip(indices, weights, grads, states, self._get_lrs(indices)):
+                s[:] = s.asnumpy() + 1          # "momentum": a state that must survive between steps
+                w[:] = w.asnumpy() - lr * self.rescale_grad * g.asnumpy() * s.asnumpy()
+    _HS.__name__ = name
+    return _HS
+
+
+def test_switch_from_custom_to_fused_optimizer_replaces_the_updater():
+    # kvstore.py:559-606 always replaces the updater; a callback left over from an earlier
+    # set_optimizer(custom) must not keep running once a fused optimizer is set
+    HS = _halfstep_cls("HalfStepA")
+    kv = mx.kv.create("device")
+    kv.init(3, mx.nd.ones(shape, mx.gpu(0)))
+    kv.set_optimizer(HS(learning_rate=0.5))
+    kv.push(3, mx.nd.ones(shape, mx.gpu(0)))
+    out = mx.nd.empty(shape, mx.gpu(0))
+    kv.pull(3, out=out)
+    np.testing.assert_allclose(out.asnumpy(), 0.5, rtol=1e-6)
+    kv.set_optimizer(mx.optimizer.SGD(learning_rate=0.5))          # plain SGD: w -= 0.5 * g
+    kv.push(3, mx.nd.ones(shape, mx.gpu(0)) * 4.0)
+    kv.pull(3, out=out)
+    np.testing.assert_allclose(out.asnumpy(), 0.5 - 0.5 * 4.0, rtol=1e-6)
+    assert kv._updater is None and kv._fused
+    # ... and back again
+    kv.set_optimizer(HS(learning_rate=1.0))
+    kv.push(3, mx.nd.ones(shape, mx.gpu(0)))
+    kv.pull(3, out=out)
+    np.testing.assert_allclose(out.asnumpy(), -1.5 - 1.0, rtol=1e-6)
+
+
+def test_subclass_overriding_step_is_not_sent_to_the_fused_kernel():
+    # fused_name is inherited; a subclass with its own step() (or use_fused_step=False) must run in Python
+    class MySGD(mx.optimizer.SGD):
+        def create_state(self, index, weight):
+            return None
+
+        def step(self, indices, weights, grads, states):
+            self._update_count(indices)
+            for w in weights:
+                w[:] = 42.0
+
+    assert mx.optimizer.fused_name_of(mx.optimizer.SGD(learning_rate=0.1)) == "sgd"
+    assert mx.optimizer.fused_name_of(MySGD(learning_rate=0.1)) is None
+    assert mx.optimizer.fused_name_of(mx.optimizer.SGD(learning_rate=0.1, use_fused_step=False)) is None
+
+    class Renamed(mx.optimizer.SGD):          # nothing overridden: still fused
+        pass
+    assert mx.optimizer.fused_name_of(Renamed(learning_rate=0.1)) == "sgd"
+
+    kv = mx.kv.create("device")
+    kv.init(3, mx.nd.ones(shape, mx.gpu(0)))
+    kv.set_optimizer(MySGD(learning_rate=0.1))
+    assert not kv._fused
+    kv.push(3, mx.nd.ones(shape, mx.gpu(0)))
+    out = mx.nd.empty(shape, mx.gpu(0))
+    kv.pull(3, out=out)
+    np.testing.assert_allclose(out.asnumpy(), 42.0)

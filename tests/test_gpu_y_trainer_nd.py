@@ -354,3 +354,38 @@ def test_reference_trainer_reset_kv(kv):
     trainer.step(1)
     assert (x[0].data.asnumpy() == np.float32(-0.2)).all(), x[0].data.asnumpy()
     assert (x[1].data.asnumpy() == np.float32(-0.2)).all()
+
+
+def test_rescale_change_keeps_python_updater_state():
+    # a smaller last batch changes rescale_grad; a Python (non-fused) optimizer on the store reads
+    # optimizer.rescale_grad live through its Updater (updater.py:39-93) and must keep its states
+    @mx.optimizer.register
+    class CountingStep(mx.optimizer.Optimizer):
+        def create_state(self, index, weight):
+            return mx.nd.zeros(weight.shape, weight.context)
+
+        def step(self, indices, weights, grads, states):
+            self._update_count(indices)
+            for i, w, g, s, lr in zip(indices, weights, grads, states, self._get_lrs(indices)):
+                s[:] = s.asnumpy() + 1
+                w[:] = w.asnumpy() - lr * self.rescale_grad * g.asnumpy() * s.asnumpy()
+
+    shape = (4, 4)
+    x = [Param(np.ones(shape, np.float32), mx.gpu(0))]
+    tr = mx.Trainer([x], CountingStep(learning_rate=1.0), kvstore="device", update_on_kvstore=True)
+    w = np.ones(shape, np.float32)
+    for k, bs in enumerate((1, 1, 2), start=1):
+        x[0].grad[:] = np.ones(shape, np.float32)
+        tr.step(bs)
+        w = w - np.float32(1.0 / bs) * np.float32(k)          # state = k: it survives the rescale change
+        np.testing.assert_allclose(x[0].data.asnumpy(), w, rtol=1e-6)
+
+
+def test_save_states_before_first_step(tmp_path):
+    # with update_on_kvstore=False the per-device updaters exist from initialisation on
+    x = [Param(np.ones((4, 4), np.float32), mx.gpu(0))]
+    tr = mx.Trainer([x], "sgd", {"learning_rate": 0.1, "momentum": 0.9}, kvstore="device", update_on_kvstore=False)
+    tr._init_kvstore()
+    f = str(tmp_path / "t.states")
+    tr.save_states(f)
+    tr.load_states(f)

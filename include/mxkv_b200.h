@@ -211,6 +211,10 @@ MXKV_DLL int MXKVB200GetEngineStream(int dev_id, void** out);
 MXKV_DLL int MXKVB200SetAutoFence(int auto_fence);
 MXKV_DLL int MXKVB200Fence(int dev_id);
 MXKV_DLL int MXKVB200GetLaunchCount(int64_t* out);
+/* Dense reduce(+update) launches so far by kernel variant: 0 = per-thread (kv_dense_kernel), 1 = shared-memory
+ * staged (kv_dense_bulk_kernel, cp.async.bulk + mbarrier), 2 = NVSwitch multicast (kv_dense_nvls_kernel).
+ * Test / bench instrumentation: proves which kernel a parity check has just exercised. */
+MXKV_DLL int MXKVB200GetVariantLaunchCount(int variant, int64_t* out);
 MXKV_DLL int MXKVB200SetTwoShotBytes(int64_t bytes);
 /* Kernel scheduling knobs (also MXKV_B200_CHUNK / _THREADS / _MAX_BLOCKS / _BULK): elements per
  * scheduling chunk, block size (128/256/512), cap on the grid (0 = resident capacity), and the

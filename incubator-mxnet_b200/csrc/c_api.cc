@@ -614,6 +614,13 @@ int MXKVB200GetLaunchCount(int64_t* out) {
   API_END();
 }
 
+int MXKVB200GetVariantLaunchCount(int variant, int64_t* out) {
+  API_BEGIN();
+  MXKV_CHECK(variant >= 0 && variant < 3) << "variant: 0 per-thread, 1 staged (bulk), 2 multicast (NVLS)";
+  *out = Runtime::Get()->variant_launches[variant];
+  API_END();
+}
+
 int MXKVB200SetTuning(int64_t chunk_elems, int threads, int max_blocks, int bulk) {
   API_BEGIN();
   Runtime::Get()->SetTuning(chunk_elems, threads, max_blocks, bulk);

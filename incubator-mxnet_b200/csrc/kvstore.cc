@@ -1774,6 +1774,7 @@ void KVStore::LaunchWorks(const LaunchClassKey& ck, std::vector<std::vector<Tens
     const int rc = LaunchDense(L, d.stream);
     MXKV_CHECK(rc == 0) << "kernel launch failed: " << cudaGetErrorString(static_cast<cudaError_t>(rc));
     rt->launches++;
+    rt->variant_launches[L.nvls ? 2 : (L.bulk ? 1 : 0)]++;
     d.ring.Commit(off, bytes, d.stream);
   }
 }

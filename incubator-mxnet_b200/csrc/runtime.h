@@ -135,6 +135,10 @@ class Runtime {
   std::recursive_mutex& mu() { return mu_; }
   bool auto_fence = true;
   int64_t launches = 0;                      // kernels launched by this library (bench "gpu_launches")
+  // dense launches by kernel variant: 0 per-thread (kv_dense_kernel / kv_sum_typed_kernel), 1 shared-memory
+  // staged (kv_dense_bulk_kernel), 2 NVSwitch multicast (kv_dense_nvls_kernel) -- lets a parity test prove
+  // which kernel it has just compared with the oracle (MXKVB200GetVariantLaunchCount)
+  int64_t variant_launches[3] = {0, 0, 0};
   int64_t twoshot_bytes = 256 * 1024;
   int64_t chunk_elems = kChunkElems;         // MXKV_B200_CHUNK
   int threads = 512;                         // MXKV_B200_THREADS

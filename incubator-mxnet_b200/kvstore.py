@@ -477,7 +477,26 @@ def set_auto_fence(flag):
     check_call(_LIB.MXKVB200SetAutoFence(ctypes.c_int(1 if flag else 0)))
 
 
-def launch_count():
+VARIANTS = {"per_thread": 0, "bulk": 1, "nvls": 2}
+
+
+def launch_count(variant=None):
+    """Kernels launched by the engine so far; with ``variant`` ('per_thread' | 'bulk' | 'nvls') the dense
+    reduce(+update) launches of that kernel variant only."""
     n = ctypes.c_int64()
-    check_call(_LIB.MXKVB200GetLaunchCount(ctypes.byref(n)))
+    if variant is None:
+        check_call(_LIB.MXKVB200GetLaunchCount(ctypes.byref(n)))
+    else:
+        check_call(_LIB.MXKVB200GetVariantLaunchCount(VARIANTS.get(variant, variant), ctypes.byref(n)))
     return n.value
+
+
+def set_tuning(chunk_elems=0, threads=0, max_blocks=-1, bulk=-1):
+    """MXKVB200SetTuning: chunk_elems / threads 0 keep the current value, max_blocks <= 0 = resident capacity.  ``bulk``: 0 never the staged kernel, 1 auto, 2 always
+    where eligible (float32, 16-byte aligned, sizes that are multiples of 4)."""
+    check_call(_LIB.MXKVB200SetTuning(ctypes.c_int64(chunk_elems), int(threads), int(max_blocks), int(bulk)))
+
+
+def set_nvls(mode):
+    """MXKVB200SetNvls: 0 never, 1 auto (above 4 ranks), 2 whenever the arrays have a multicast alias."""
+    check_call(_LIB.MXKVB200SetNvls(int(mode)))

@@ -208,8 +208,14 @@ def main():
         print("multicast unavailable:", repr(e), flush=True)
         nvls = False
     if nvls:
-        for optname, kw in ((None, {}), ("sgd", dict(learning_rate=0.1, momentum=0.9, wd=1e-4))):
-            shapes = [(1 << 10,), (3 * (1 << 16),), (1 << 21,)]
+        mx.kv.set_nvls(2)            # FORCE the multimem kernel at every world size (auto: above 4 ranks only)
+        nv0 = mx.kv.launch_count("nvls")
+        big = [1 << p for p in range(10, 25, 2)]          # the bench sweep's sizes up to 64 MB, one call
+        for optname, kw, shapes in ((None, {}, [(1 << 10,), (3 * (1 << 16),), (1 << 21,)]),
+                                    ("sgd", dict(learning_rate=0.1, momentum=0.9, wd=1e-4), [(1 << 10,), (3 * (1 << 16),), (1 << 21,)]),
+                                    ("sgd", dict(learning_rate=0.01, momentum=0.9, wd=1e-4), [(e,) for e in big]),
+                                    ("adam", dict(learning_rate=0.001, wd=1e-3), [(e,) for e in big]),
+                                    (None, {}, [(e,) for e in big])):
             ks = list(range(len(shapes)))
             kv7 = mx.kv.create("device")
             w0 = [data(41 + k, s, 0) for k, s in zip(ks, shapes)]
@@ -237,7 +243,45 @@ def main():
                     chk = int(got.view(np.int32).astype(np.int64).sum())
                     assert all(c == chk for c in allgather_int(chk)), ("nvls replicas differ", optname, step, k)
             assert mx.kv.launch_count() - before == 3, "one launch per pushpull expected"
+        assert mx.kv.launch_count("nvls") - nv0 == 15, "the multimem kernel did not serve every pushpull"
+        mx.kv.set_nvls(1)
         print("NVLS_OK rank", rank, flush=True)
+
+    # 7b. the peer-memory kernels, each variant FORCED: the shared-memory staged kernel
+    #     (cp.async.bulk from peer HBM) and the per-thread kernel over the bench sweep's sizes in one call and
+    #     one key per call, two-shot and one-shot, SGD momentum / Adam / plain sum, bit-exact
+    big = [1 << p for p in (range(10, 19, 2) if SIM else range(10, 25, 2))]
+    for variant, bulk in (("bulk", 2), ("per_thread", 0)):
+        mx.kv.set_tuning(bulk=bulk)
+        c0 = {v: mx.kv.launch_count(v) for v in ("bulk", "per_thread")}
+        for optname, kw in ((None, {}), ("sgd", dict(learning_rate=0.01, momentum=0.9, wd=1e-4)),
+                            ("adam", dict(learning_rate=0.001, wd=1e-3))):
+            for group in ([big] + [[e] for e in big[::2]]):
+                ks = list(range(len(group)))
+                kvb = mx.kv.create("device")
+                w0 = [data(51 + k, (e,), 0) for k, e in zip(ks, group)]
+                kvb.init(ks, [mx.nd.array(w, ctx) for w in w0])
+                okv = O.OracleKVStore("device")
+                okv.init(ks, [w.copy() for w in w0])
+                if optname:
+                    kvb.set_optimizer(mx.optimizer.create(optname, **kw))
+                    okv.set_optimizer(O.OracleOptimizer(optname, **kw))
+                gs = [mx.nd.empty_symmetric((e,)) for e in group]
+                outs = [mx.nd.empty_symmetric((e,)) for e in group]
+                for step in range(2):
+                    for k, e in zip(ks, group):
+                        gs[k][:] = data(400 + 10 * step + k, (e,), rank)
+                    device_sync(); barrier()
+                    kvb.pushpull(ks, gs, out=outs)
+                    okv.push(ks, [[data(400 + 10 * step + k, (e,), r) for r in range(world)] for k, e in zip(ks, group)])
+                    for k, e in zip(ks, group):
+                        want = np.empty(e, np.float32)
+                        okv.pull(k, want)
+                        assert bits_equal(outs[k].asnumpy(), want), ("forced", variant, optname, step, e)
+        other = "per_thread" if variant == "bulk" else "bulk"
+        assert mx.kv.launch_count(variant) > c0[variant] and mx.kv.launch_count(other) == c0[other], \
+            ("forced variant did not hold", variant)
+    mx.kv.set_tuning(bulk=1)
 
     # 8. layer-wise adaptive optimizers: sharded keys take the norms across the ranks' shards, small
     #    keys are updated redundantly; replicas must stay bit-identical across ranks

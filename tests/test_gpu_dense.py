@@ -276,3 +276,105 @@ def test_save_load_optimizer_states(tmp_path):
     kv2.load_optimizer_states(f)
     got = run(kv2, 2, 2)
     assert_bits_equal(got, ref)
+
+
+# ---------------------------------------------------------------------------
+# Forced kernel variants: the kernels bench.py times are the ones compared with the
+# oracle here -- the shared-memory staged kernel (kv_dense_bulk_kernel) and the per-thread kernel
+# (kv_dense_kernel) are each FORCED over BASELINE.json configs[1]'s sizes (2^10 ... 2^26 elements, one key
+# per size and the whole key set in one call), n = 1 and 2 values per key on one GPU, no optimizer / SGD
+# momentum / Adam, bit for bit; the variant launch counters prove which kernel ran.
+# ---------------------------------------------------------------------------
+import os
+
+_SIM = bool(os.environ.get("MXKV_SIM"))
+SWEEP_P = list(range(10, 19, 2)) if _SIM else list(range(10, 27, 2))      # the simulator runs on one CPU core
+_OPTS = {
+    "none": (None, {}),
+    "sgd_mom": ("sgd", dict(learning_rate=0.01, momentum=0.9, wd=1e-4)),      # bench.py's optimizer
+    "adam": ("adam", dict(learning_rate=0.001, wd=1e-3)),
+}
+
+
+class _forced(object):
+    """force one dense kernel variant for the duration of a test; restores the automatic choice"""
+
+    def __init__(self, variant):
+        self.variant = variant
+
+    def __enter__(self):
+        mx.kv.set_tuning(bulk={"bulk": 2, "per_thread": 0}[self.variant])
+        self.before = {v: mx.kv.launch_count(v) for v in ("per_thread", "bulk", "nvls")}
+        return self
+
+    def launched(self, v):
+        return mx.kv.launch_count(v) - self.before[v]
+
+    def __exit__(self, *a):
+        mx.kv.set_tuning(bulk=1)
+
+
+def _fill(rng, lo, hi, e):
+    """random float32 data; large arrays repeat a random block of 1 000 003 elements (a period that no tile,
+    chunk or shard boundary is a multiple of), because numpy draws only ~20 M values per second"""
+    if e <= (1 << 20):
+        return rng.uniform(lo, hi, e).astype(np.float32)
+    return np.resize(rng.uniform(lo, hi, 1000003).astype(np.float32), e)
+
+
+def _run_keyset(variant, optkey, n, sizes, steps=2, seed=0):
+    optname, kw = _OPTS[optkey]
+    rng = _rng(seed + n + len(sizes))
+    keys = list(range(len(sizes)))
+    w0 = [_fill(rng, 0, 1, e) for e in sizes]
+    with _forced(variant) as f:
+        kv = mx.kv.create("device")
+        kv.init(keys, [mx.nd.array(w, mx.gpu(0)) for w in w0])
+        okv = O.OracleKVStore("device")
+        okv.init(keys, [w.copy() for w in w0])
+        if optname:
+            kv.set_optimizer(mx.optimizer.create(optname, **kw))
+            okv.set_optimizer(O.OracleOptimizer(optname, **kw))
+        outs = [mx.nd.empty((e,), mx.gpu(0)) for e in sizes]
+        gdev = [[mx.nd.empty((e,), mx.gpu(0)) for _ in range(n)] for e in sizes]
+        big = sum(sizes) > (1 << 24)
+        for s in range(steps):
+            if s == 0 or not big:      # large key sets push the same gradients again (the state has moved on)
+                grads = [[_fill(rng, -1, 1, e) for _ in range(n)] for e in sizes]
+                for gd, gs in zip(gdev, grads):
+                    for d, g in zip(gd, gs):
+                        d[:] = g
+            kv.pushpull(keys, gdev, out=outs)
+            okv.push(keys, grads)
+            for k, e in enumerate(sizes):
+                want = np.empty(e, np.float32)
+                okv.pull(k, want)
+                assert_bits_equal(outs[k].asnumpy(), want, "%s %s n=%d E=%d step %d" % (variant, optkey, n, e, s))
+        mx.nd.waitall()
+        other = "per_thread" if variant == "bulk" else "bulk"
+        assert f.launched(variant) >= steps, "the %s kernel did not run (%d launches)" % (variant, f.launched(variant))
+        assert f.launched(other) == 0, "%d launches of the %s kernel under a forced %s" % (f.launched(other), other, variant)
+
+
+@pytest.mark.parametrize("optkey", ["none", "sgd_mom", "adam"])
+@pytest.mark.parametrize("n", [1, 2])
+@pytest.mark.parametrize("variant", ["bulk", "per_thread"])
+def test_forced_variant_every_sweep_size(variant, n, optkey):
+    for p in [q for q in SWEEP_P if q <= 22]:      # 2^24 and 2^26: the whole-key-set test below
+        _run_keyset(variant, optkey, n, [1 << p], steps=2, seed=p)
+
+
+@pytest.mark.parametrize("optkey", ["none", "sgd_mom", "adam"])
+@pytest.mark.parametrize("n", [1, 2])
+@pytest.mark.parametrize("variant", ["bulk", "per_thread"])
+def test_forced_variant_whole_sweep_key_set_in_one_call(variant, n, optkey):
+    """the bench workload itself: 9 keys 4 KB ... 256 MB in ONE pushpull = one launch"""
+    _run_keyset(variant, optkey, n, [1 << p for p in SWEEP_P], steps=2, seed=77)
+
+
+@pytest.mark.parametrize("variant", ["bulk", "per_thread"])
+def test_forced_variant_ragged_tiles(variant):
+    """sizes that are multiples of 4 but not of the 2048-element tile / 8192-element chunk: partial last tiles,
+    tiles of 4 elements, a key smaller than one tile next to a large one"""
+    _run_keyset(variant, "sgd_mom", 2, [4, 2052, 8196, 3 * 2048 + 12, (1 << 20) + 4, 12], steps=3, seed=5)
+    _run_keyset(variant, "adam", 1, [2048, 2044, 4096 + 8, 100004], steps=2, seed=6)

@@ -254,6 +254,11 @@ MXKV_DLL int MXKVB200NDArrayFromPeers(void* const* peer_ptrs, int world, void* m
 /* 0: never use the NVLS kernel; 1 (default): use it above 4 ranks when every array of a key has a
  * multicast alias; 2: whenever the arrays have one */
 MXKV_DLL int MXKVB200SetNvls(int mode);
+/* Scheduling of the NVLS kernel (also MXKV_B200_NVLS_U / _PIPE / _GRID / _THREADS): multimem.ld_reduce requests
+ * in flight per thread (1, 2, 4, 8; <= 0 keeps), software pipelining of the reduce-scatter half (0 / 1; < 0
+ * keeps), cap on the grid (0 = resident capacity; < 0 keeps), block size (128 / 256 / 512; anything else keeps).
+ * Every rank of the process group must use the same values. */
+MXKV_DLL int MXKVB200SetNvlsTuning(int unroll, int pipe, int grid, int threads);
 
 #ifdef __cplusplus
 }

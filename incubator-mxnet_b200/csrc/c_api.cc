@@ -584,6 +584,17 @@ int MXKVB200SetNvls(int mode) {
   API_END();
 }
 
+int MXKVB200SetNvlsTuning(int unroll, int pipe, int grid, int threads) {
+  API_BEGIN();
+  Runtime* rt = Runtime::Get();
+  rt->WaitAll();
+  if (unroll > 0) rt->nvls_unroll = unroll;
+  if (pipe >= 0) rt->nvls_pipe = pipe != 0;
+  if (grid >= 0) rt->nvls_grid = grid;
+  if (threads == 128 || threads == 256 || threads == 512) rt->nvls_threads = threads;
+  API_END();
+}
+
 int MXKVB200SetStream(int dev_id, void* cuda_stream) {
   API_BEGIN();
   Runtime::Get()->SetUserStream(dev_id, static_cast<cudaStream_t>(cuda_stream));

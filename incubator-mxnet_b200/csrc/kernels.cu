@@ -24,6 +24,8 @@
 
 namespace mxkv {
 
+static int sm_count(int device);
+
 // ---------------------------------------------------------------------------
 // U packets per thread: gather n sources, sum in order, update, scatter.  All loads of a batch are
 // issued before the first use so U * min(n, BATCH) 16-byte requests per thread are in flight
@@ -401,105 +403,174 @@ __device__ __forceinline__ void mm_st(void* p, const float4& v) {
                :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
-// U: 16-byte multimem.ld_reduce requests in flight per thread (MXKV_B200_NVLS_U; 2 is the measured
-// default, 4 / 8 exist for the light optimizers to explore the latency-bound reduce-scatter half)
-template <int OPT, bool MP, int U>
-__global__ void __launch_bounds__(kThreads, 2)
+// One scheduling chunk = ONE block iteration (blockDim * U 16-byte vectors), so `chunk c -> block c % grid`
+// is an exactly balanced grid-stride walk over the concatenated shards of the whole work list.
+//   U     multimem.ld_reduce requests (16 B each) a thread has in flight per iteration
+//   PIPE  software pipeline: the ld_reduce requests of the block's NEXT chunk are issued before the current
+//         chunk's state loads / update / multimem.st, so the reduce-scatter half never idles behind the
+//         all-gather half (the two halves use opposite link directions)
+// The SM side is never the limiter here (a GPU consumes ~80 GB/s of reduced data, i.e. < 1 KB/us per SM): what
+// these knobs and the grid size change is the REQUEST PATTERN the switch sees (how many reduce requests queue
+// in the fabric, how they interleave with the multicast stores).  Measured choices: profiles/r02_nvls_tune.txt.
+struct NvlsChunk {
+  const float* g;      // multicast address of the key's gradient
+  int64_t cb, ce;      // element range of the chunk
+  int lo;              // work entry
+};
+
+__device__ __forceinline__ NvlsChunk nvls_lookup(const DenseLaunch& L, int64_t c) {
+  int lo = 0, hi = L.nworks - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (static_cast<int64_t>(__ldg(reinterpret_cast<const long long*>(L.chunk_prefix + mid))) <= c) lo = mid; else hi = mid - 1;
+  }
+  const TensorWork* w = L.works + lo;
+  NvlsChunk k;
+  k.lo = lo;
+  k.g = reinterpret_cast<const float*>(__ldg(reinterpret_cast<const unsigned long long*>(&w->src[0])));
+  const int64_t begin = static_cast<int64_t>(__ldg(reinterpret_cast<const long long*>(&w->begin)));
+  const int64_t end = static_cast<int64_t>(__ldg(reinterpret_cast<const long long*>(&w->end)));
+  k.cb = begin + (c - static_cast<int64_t>(__ldg(reinterpret_cast<const long long*>(L.chunk_prefix + lo)))) * L.chunk_elems;
+  k.ce = (k.cb + L.chunk_elems < end) ? k.cb + L.chunk_elems : end;
+  return k;
+}
+
+template <int U>
+__device__ __forceinline__ void nvls_issue(const NvlsChunk& k, float4 (&g)[U]) {
+  const int64_t nvec = (k.ce - k.cb) >> 2;           // host guarantees multiples of 4 elements
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const int64_t vv = threadIdx.x + static_cast<int64_t>(u) * blockDim.x;
+    if (vv < nvec) g[u] = mm_ld_reduce(k.g + k.cb + vv * 4);
+  }
+}
+
+template <int OPT, bool MP, int U, bool PIPE>
+__global__ void __launch_bounds__(kThreads, (U >= 4 || PIPE) ? 1 : 2)
 kv_dense_nvls_kernel(DenseLaunch L) {
   __shared__ TensorWork tw;
   barrier_start(L.sync);
   constexpr bool HAS_S0 = OPT == OPT_SGD_MOM || OPT == OPT_ADAM || OPT == OPT_ADAMW;
   constexpr bool HAS_S1 = OPT == OPT_ADAM || OPT == OPT_ADAMW;
   int cur = -1;
-  for (int64_t c = blockIdx.x; c < L.total_chunks; c += gridDim.x) {
-    int lo = 0, hi = L.nworks - 1;
-    while (lo < hi) {
-      const int mid = (lo + hi + 1) >> 1;
-      if (L.chunk_prefix[mid] <= c) lo = mid; else hi = mid - 1;
+  int64_t c = blockIdx.x;
+  NvlsChunk k, kn;
+  float4 g[U], gn[U];
+  if (c < L.total_chunks) {
+    k = nvls_lookup(L, c);
+    if (PIPE) nvls_issue<U>(k, g);
+  }
+  while (c < L.total_chunks) {
+    const int64_t cn = c + gridDim.x;
+    if (cn < L.total_chunks) {
+      kn = nvls_lookup(L, cn);
+      if (PIPE) nvls_issue<U>(kn, gn);
     }
-    if (lo != cur) {
+    if (!PIPE) nvls_issue<U>(k, g);
+    if (k.lo != cur) {
       __syncthreads();
-      const uint4* src = reinterpret_cast<const uint4*>(L.works + lo);
+      const uint4* src = reinterpret_cast<const uint4*>(L.works + k.lo);
       uint4* dst = reinterpret_cast<uint4*>(&tw);
       for (int i = threadIdx.x; i < static_cast<int>(sizeof(TensorWork) / 16); i += blockDim.x) dst[i] = src[i];
       __syncthreads();
-      cur = lo;
+      cur = k.lo;
     }
     Hyper h;
     h.lr = tw.lr; h.wd = tw.wd; h.eta = tw.eta;
     h.rescale = L.rescale; h.clip = L.clip; h.momentum = L.momentum;
     h.beta1 = L.beta1; h.beta2 = L.beta2; h.eps = L.eps;
-    const int64_t cb = tw.begin + (c - L.chunk_prefix[lo]) * L.chunk_elems;
-    const int64_t ce = (cb + L.chunk_elems < tw.end) ? cb + L.chunk_elems : tw.end;
-    const int64_t nvec = (ce - cb) >> 2;           // host guarantees multiples of 4 elements
-    const float* gmc = static_cast<const float*>(tw.src[0]);
+    const int64_t nvec = (k.ce - k.cb) >> 2;
     const int n_plain = tw.n_out - tw.n_mc;
-    const int64_t nthr = blockDim.x;
-    for (int64_t v = threadIdx.x; v < nvec; v += U * nthr) {
-      int64_t e[U];
-      bool ok[U];
-      float4 g[U];
+    // state of all U packets first (independent HBM loads in flight together), then the arithmetic
+    float w[U][4], s0[U][4], s1[U][4];
+    if (OPT != OPT_NONE) {
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const int64_t vv = v + u * nthr;
-        ok[u] = vv < nvec;
-        e[u] = cb + (ok[u] ? vv : v) * 4;
-        if (ok[u]) g[u] = mm_ld_reduce(gmc + e[u]);
+        const int64_t vv = threadIdx.x + static_cast<int64_t>(u) * blockDim.x;
+        if (vv >= nvec) continue;
+        const int64_t e = k.cb + vv * 4;
+        ldf<4>(MP ? tw.w32 : static_cast<const float*>(tw.w), e, w[u]);
+        if (HAS_S0) ldf<4>(tw.s0, e, s0[u]);
+        if (HAS_S1) ldf<4>(tw.s1, e, s1[u]);
       }
-      float w[U][4], s0[U][4], s1[U][4];
-      if (OPT != OPT_NONE) {
+    }
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          if (!ok[u]) continue;
-          ldf<4>(MP ? tw.w32 : static_cast<const float*>(tw.w), e[u], w[u]);
-          if (HAS_S0) ldf<4>(tw.s0, e[u], s0[u]);
-          if (HAS_S1) ldf<4>(tw.s1, e[u], s1[u]);
-        }
+    for (int u = 0; u < U; ++u) {
+      const int64_t vv = threadIdx.x + static_cast<int64_t>(u) * blockDim.x;
+      if (vv >= nvec) continue;
+      const int64_t e = k.cb + vv * 4;
+      const float acc[4] = {g[u].x, g[u].y, g[u].z, g[u].w};
+      float wnew[4];
+      if (OPT == OPT_NONE) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) wnew[j] = acc[j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) wnew[j] = update_one<OPT>(acc[j], w[u][j], s0[u][j], s1[u][j], h);
+        if (HAS_S0) stf<4>(tw.s0, e, s0[u]);
+        if (HAS_S1) stf<4>(tw.s1, e, s1[u]);
+        if (MP) stf<4>(tw.w32, e, wnew);
       }
+      for (int j = 0; j < n_plain; ++j) stf<4>(static_cast<float*>(tw.out[j]), e, wnew);
+      const float4 o = make_float4(wnew[0], wnew[1], wnew[2], wnew[3]);
+      for (int j = n_plain; j < tw.n_out; ++j) mm_st(static_cast<float*>(tw.out[j]) + e, o);
+    }
+    c = cn;
+    k = kn;
+    if (PIPE) {
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        if (!ok[u]) continue;
-        const float acc[4] = {g[u].x, g[u].y, g[u].z, g[u].w};
-        float wnew[4];
-        if (OPT == OPT_NONE) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) wnew[j] = acc[j];
-        } else {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) wnew[j] = update_one<OPT>(acc[j], w[u][j], s0[u][j], s1[u][j], h);
-          if (HAS_S0) stf<4>(tw.s0, e[u], s0[u]);
-          if (HAS_S1) stf<4>(tw.s1, e[u], s1[u]);
-          if (MP) stf<4>(tw.w32, e[u], wnew);
-        }
-        for (int j = 0; j < n_plain; ++j) stf<4>(static_cast<float*>(tw.out[j]), e[u], wnew);
-        const float4 o = make_float4(wnew[0], wnew[1], wnew[2], wnew[3]);
-        for (int j = n_plain; j < tw.n_out; ++j) mm_st(static_cast<float*>(tw.out[j]) + e[u], o);
-      }
+      for (int u = 0; u < U; ++u) g[u] = gn[u];
     }
   }
   barrier_end(L.sync, true);
 }
 
 typedef void (*NvlsKernelFn)(DenseLaunch);
-static NvlsKernelFn pick_nvls(int opt, int mp, int unroll) {
-  if (unroll >= 8 && opt == OPT_NONE) return kv_dense_nvls_kernel<OPT_NONE, false, 8>;
-  if (unroll >= 4) {
-    switch (opt) {
-      case OPT_NONE: return kv_dense_nvls_kernel<OPT_NONE, false, 4>;
-      case OPT_SGD: return mp ? kv_dense_nvls_kernel<OPT_SGD, true, 4> : kv_dense_nvls_kernel<OPT_SGD, false, 4>;
-      case OPT_SGD_MOM: return mp ? kv_dense_nvls_kernel<OPT_SGD_MOM, true, 4> : kv_dense_nvls_kernel<OPT_SGD_MOM, false, 4>;
-      default: break;      // the heavier optimizers stay at two requests (register budget)
-    }
-  }
+
+template <int U, bool PIPE>
+static NvlsKernelFn pick_nvls_opt(int opt, int mp) {
   switch (opt) {
-    case OPT_NONE: return kv_dense_nvls_kernel<OPT_NONE, false, 2>;
-    case OPT_SGD: return mp ? kv_dense_nvls_kernel<OPT_SGD, true, 2> : kv_dense_nvls_kernel<OPT_SGD, false, 2>;
-    case OPT_SGD_MOM: return mp ? kv_dense_nvls_kernel<OPT_SGD_MOM, true, 2> : kv_dense_nvls_kernel<OPT_SGD_MOM, false, 2>;
-    case OPT_ADAM: return mp ? kv_dense_nvls_kernel<OPT_ADAM, true, 2> : kv_dense_nvls_kernel<OPT_ADAM, false, 2>;
-    case OPT_ADAMW: return mp ? kv_dense_nvls_kernel<OPT_ADAMW, true, 2> : kv_dense_nvls_kernel<OPT_ADAMW, false, 2>;
-    case OPT_TEST: return mp ? kv_dense_nvls_kernel<OPT_TEST, true, 2> : kv_dense_nvls_kernel<OPT_TEST, false, 2>;
+    case OPT_NONE: return kv_dense_nvls_kernel<OPT_NONE, false, U, PIPE>;
+    case OPT_SGD: return mp ? kv_dense_nvls_kernel<OPT_SGD, true, U, PIPE> : kv_dense_nvls_kernel<OPT_SGD, false, U, PIPE>;
+    case OPT_SGD_MOM: return mp ? kv_dense_nvls_kernel<OPT_SGD_MOM, true, U, PIPE> : kv_dense_nvls_kernel<OPT_SGD_MOM, false, U, PIPE>;
+    case OPT_ADAM: return mp ? kv_dense_nvls_kernel<OPT_ADAM, true, U, PIPE> : kv_dense_nvls_kernel<OPT_ADAM, false, U, PIPE>;
+    case OPT_ADAMW: return mp ? kv_dense_nvls_kernel<OPT_ADAMW, true, U, PIPE> : kv_dense_nvls_kernel<OPT_ADAMW, false, U, PIPE>;
+    case OPT_TEST: return mp ? kv_dense_nvls_kernel<OPT_TEST, true, U, PIPE> : kv_dense_nvls_kernel<OPT_TEST, false, U, PIPE>;
     default: return nullptr;
   }
+}
+
+// the instantiated (U, PIPE) points; anything else is rounded down to the nearest one
+// (Adam / AdamW carry three state packets per gradient packet: 8 requests would spill at 128 registers)
+static int nvls_round_unroll(int unroll, int opt) {
+  if ((opt == OPT_ADAM || opt == OPT_ADAMW) && unroll > 4) unroll = 4;
+  return unroll >= 8 ? 8 : (unroll >= 4 ? 4 : (unroll >= 2 ? 2 : 1));
+}
+
+static NvlsKernelFn pick_nvls(int opt, int mp, int unroll, int pipe) {
+  switch (nvls_round_unroll(unroll, opt)) {
+    case 8: return pipe ? pick_nvls_opt<8, true>(opt, mp) : pick_nvls_opt<8, false>(opt, mp);
+    case 4: return pipe ? pick_nvls_opt<4, true>(opt, mp) : pick_nvls_opt<4, false>(opt, mp);
+    case 2: return pipe ? pick_nvls_opt<2, true>(opt, mp) : pick_nvls_opt<2, false>(opt, mp);
+    default: return pipe ? pick_nvls_opt<1, true>(opt, mp) : pick_nvls_opt<1, false>(opt, mp);
+  }
+}
+
+int NvlsPlan(int device, int opt, int multi_precision, int unroll, int pipe, int threads, int* chunk_elems) {
+  NvlsKernelFn fn = pick_nvls(opt, multi_precision, unroll, pipe);
+  if (fn == nullptr) return 0;
+  if (threads != 128 && threads != 256 && threads != 512) threads = kThreads;
+  int prev = -1;
+  cudaGetDevice(&prev);
+  if (prev != device) cudaSetDevice(device);
+  int occ = 0;
+  const bool ok = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, threads, 0) == cudaSuccess && occ >= 1;
+  if (!ok) cudaGetLastError();
+  if (prev >= 0 && prev != device) cudaSetDevice(prev);
+  if (!ok) return 0;
+  *chunk_elems = threads * nvls_round_unroll(unroll, opt) * 4;
+  const int g = occ * sm_count(device);
+  return g > kMaxBlocks ? kMaxBlocks : g;
 }
 
 // ---------------------------------------------------------------------------
@@ -685,10 +756,13 @@ int BulkPlan(int device, int opt, int multi_precision, int arrays, int* tile_ele
 
 int LaunchDense(const DenseLaunch& L, cudaStream_t stream) {
   if (L.nvls) {
-    NvlsKernelFn nf = pick_nvls(L.opt, L.multi_precision, L.nvls_unroll);
+    NvlsKernelFn nf = pick_nvls(L.opt, L.multi_precision, L.nvls_unroll, L.nvls_pipe);
     if (nf == nullptr || L.dtype != kFloat32 || L.sync.mode == SYNC_NONE) return static_cast<int>(cudaErrorInvalidValue);
     int grid = L.grid < 1 ? 1 : (L.grid > kMaxBlocks ? kMaxBlocks : L.grid);
-    nf<<<grid, kThreads, 0, stream>>>(L);
+    int threads = L.threads;
+    if (threads != 128 && threads != 256 && threads != 512) threads = kThreads;
+    if (L.chunk_elems != threads * nvls_round_unroll(L.nvls_unroll, L.opt) * 4) return static_cast<int>(cudaErrorInvalidValue);
+    nf<<<grid, threads, 0, stream>>>(L);
     return static_cast<int>(cudaGetLastError());
   }
   if (L.bulk) {

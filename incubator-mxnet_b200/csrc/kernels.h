@@ -108,7 +108,8 @@ struct DenseLaunch {
   int bulk;                      // 1: shared-memory staged variant (cp.async.bulk + mbarrier pipeline)
   int bulk_stages;               // pipeline depth
   int bulk_arrays;               // input arrays staged per tile (max over the work list)
-  int nvls_unroll;               // NVLS variant: multimem.ld_reduce requests in flight per thread (2, 4 or 8)
+  int nvls_unroll;               // NVLS variant: multimem.ld_reduce requests in flight per thread (1, 2, 4 or 8)
+  int nvls_pipe;                 // NVLS variant: 1 = next chunk's ld_reduce issued before this chunk's update/stores
 };
 
 // returns cudaError_t as int; never throws
@@ -117,6 +118,9 @@ int DenseMaxGrid(int device, int threads);   // resident-block capacity of the d
 // Plan the shared-memory staged variant for a float32 launch with `arrays` staged input streams per
 // tile: picks tile elements / stages and returns the resident grid capacity (0: not applicable).
 int BulkPlan(int device, int opt, int multi_precision, int arrays, int* tile_elems, int* stages);
+// Plan the multicast (NVLS) variant: elements per scheduling chunk (= one block iteration) for the given
+// requests-in-flight / pipelining / block size, and the resident grid capacity (0: not available).
+int NvlsPlan(int device, int opt, int multi_precision, int unroll, int pipe, int threads, int* chunk_elems);
 
 int LaunchFill(void* ptr, int value_byte, size_t bytes, cudaStream_t s);
 // gradient compression codec (bits = 1 or 2); code stream = ceil(n / (32/bits)) 32-bit words

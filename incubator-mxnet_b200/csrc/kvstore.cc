@@ -1715,6 +1715,14 @@ void KVStore::LaunchWorks(const LaunchClassKey& ck, std::vector<std::vector<Tens
       if (cap > 0) { bulk = 1; bulk_stages = st; bulk_arrays = max_src + extra; bulk_cap = cap; chunk = tile; }
     }
   }
+  int nvls_cap = 0;
+  if (ck.nvls) {
+    int ce = 0;
+    nvls_cap = NvlsPlan(part_dev[my_first], opt_kind, ck.mp, rt->nvls_unroll, rt->nvls_pipe, rt->nvls_threads, &ce);
+    MXKV_CHECK(nvls_cap > 0) << "no multicast kernel for optimizer kind " << opt_kind;
+    chunk = ce;
+    if (rt->nvls_grid > 0) nvls_cap = std::min(nvls_cap, rt->nvls_grid);
+  }
   int64_t max_chunks = 0;
   for (int64_t len : busiest) max_chunks += (len + chunk - 1) / chunk;
   max_chunks = std::max<int64_t>(1, max_chunks);
@@ -1767,7 +1775,8 @@ void KVStore::LaunchWorks(const LaunchClassKey& ck, std::vector<std::vector<Tens
     L.bulk = bulk; L.bulk_stages = bulk_stages; L.bulk_arrays = bulk_arrays;
     L.nvls = ck.nvls;
     L.nvls_unroll = rt->nvls_unroll;
-    if (ck.nvls) { L.threads = 512; L.grid = static_cast<int>(std::min<int64_t>(DenseMaxGrid(dev, 512), max_chunks)); }
+    L.nvls_pipe = rt->nvls_pipe;
+    if (ck.nvls) { L.threads = rt->nvls_threads; L.grid = static_cast<int>(std::min<int64_t>(nvls_cap, max_chunks)); }
     int small_n = 1;
     for (auto& t : w) if (t.n_src > 2) small_n = 0;
     L.small_n = small_n;

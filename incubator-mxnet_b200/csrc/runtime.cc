@@ -170,7 +170,11 @@ Runtime::Runtime() {
   chunk_elems = (chunk_elems + 127) / 128 * 128;
   bulk_mode = static_cast<int>(EnvInt("MXKV_B200_BULK", 1));
   nvls_mode = static_cast<int>(EnvInt("MXKV_B200_NVLS", 1));
-  nvls_unroll = static_cast<int>(EnvInt("MXKV_B200_NVLS_U", 2));
+  nvls_unroll = static_cast<int>(EnvInt("MXKV_B200_NVLS_U", nvls_unroll));
+  nvls_pipe = static_cast<int>(EnvInt("MXKV_B200_NVLS_PIPE", nvls_pipe));
+  nvls_grid = static_cast<int>(EnvInt("MXKV_B200_NVLS_GRID", nvls_grid));
+  nvls_threads = static_cast<int>(EnvInt("MXKV_B200_NVLS_THREADS", nvls_threads));
+  if (nvls_threads != 128 && nvls_threads != 256 && nvls_threads != 512) nvls_threads = 512;
   spin_timeout_cycles = EnvInt("MXKV_B200_SPIN_TIMEOUT_S", 120) * 1900000000LL;   // ~1.9 GHz SM clock
   max_blocks = static_cast<int>(EnvInt("MXKV_B200_MAX_BLOCKS", 0));
   threads = static_cast<int>(EnvInt("MXKV_B200_THREADS", 512));

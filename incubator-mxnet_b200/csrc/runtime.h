@@ -145,7 +145,10 @@ class Runtime {
   long long spin_timeout_cycles = 0;         // MXKV_B200_SPIN_TIMEOUT_S (default 120 s) in SM cycles
   int max_blocks = 0;                        // MXKV_B200_MAX_BLOCKS (0: resident capacity)
   int nvls_mode = 1;                         // MXKV_B200_NVLS: use multimem kernels for multicast-bound arrays
-  int nvls_unroll = 2;                       // MXKV_B200_NVLS_U: ld_reduce requests in flight per thread (2 | 4 | 8)
+  int nvls_unroll = 2;                       // MXKV_B200_NVLS_U: ld_reduce requests in flight per thread (1 | 2 | 4 | 8)
+  int nvls_pipe = 0;                         // MXKV_B200_NVLS_PIPE: issue the next chunk's ld_reduce before this chunk's update
+  int nvls_grid = 0;                         // MXKV_B200_NVLS_GRID: cap on the multicast kernel's grid (0: resident capacity)
+  int nvls_threads = 512;                    // MXKV_B200_NVLS_THREADS: its block size (128 | 256 | 512)
   int bulk_mode = 1;                         // MXKV_B200_BULK: 0 off, 1 auto (<= 2 sources), 2 whenever eligible
  private:
   Runtime();

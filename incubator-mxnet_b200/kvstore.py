@@ -497,6 +497,11 @@ def set_tuning(chunk_elems=0, threads=0, max_blocks=-1, bulk=-1):
     check_call(_LIB.MXKVB200SetTuning(ctypes.c_int64(chunk_elems), int(threads), int(max_blocks), int(bulk)))
 
 
+def set_nvls_tuning(unroll=0, pipe=-1, grid=-1, threads=0):
+    """MXKVB200SetNvlsTuning (same values on every rank)."""
+    check_call(_LIB.MXKVB200SetNvlsTuning(int(unroll), int(pipe), int(grid), int(threads)))
+
+
 def set_nvls(mode):
     """MXKVB200SetNvls: 0 never, 1 auto (above 4 ranks), 2 whenever the arrays have a multicast alias."""
     check_call(_LIB.MXKVB200SetNvls(int(mode)))

@@ -210,47 +210,56 @@ def main():
     if nvls:
         mx.kv.set_nvls(2)            # FORCE the multimem kernel at every world size (auto: above 4 ranks only)
         nv0 = mx.kv.launch_count("nvls")
-        big = [1 << p for p in range(10, 25, 2)]          # the bench sweep's sizes up to 64 MB, one call
-        for optname, kw, shapes in ((None, {}, [(1 << 10,), (3 * (1 << 16),), (1 << 21,)]),
-                                    ("sgd", dict(learning_rate=0.1, momentum=0.9, wd=1e-4), [(1 << 10,), (3 * (1 << 16),), (1 << 21,)]),
-                                    ("sgd", dict(learning_rate=0.01, momentum=0.9, wd=1e-4), [(e,) for e in big]),
-                                    ("adam", dict(learning_rate=0.001, wd=1e-3), [(e,) for e in big]),
-                                    (None, {}, [(e,) for e in big])):
-            ks = list(range(len(shapes)))
-            kv7 = mx.kv.create("device")
-            w0 = [data(41 + k, s, 0) for k, s in zip(ks, shapes)]
-            kv7.init(ks, [mx.nd.array(w, ctx) for w in w0])
-            okv = O.OracleKVStore("device")
-            okv.init(ks, [w.copy() for w in w0])
-            if optname:
-                kv7.set_optimizer(mx.optimizer.create(optname, **kw))
-                okv.set_optimizer(O.OracleOptimizer(optname, **kw))
-            gm = [mx.nd.empty_multicast(s) for s in shapes]
-            om = [mx.nd.empty_multicast(s) for s in shapes]
-            before = mx.kv.launch_count()
-            for step in range(3):
-                for k, s in zip(ks, shapes):
-                    gm[k][:] = data(300 + 10 * step + k, s, rank)
-                device_sync(); barrier()
-                kv7.pushpull(ks, gm, out=om)
-                okv.push(ks, [[data(300 + 10 * step + k, s, r) for r in range(world)] for k, s in zip(ks, shapes)])
-                for k, s in zip(ks, shapes):
-                    want = np.empty(s, np.float32)
-                    okv.pull(k, want)
-                    got = om[k].asnumpy()
-                    err = np.abs(got.astype(np.float64) - want).sum() / max(np.abs(want).sum(), 1e-30)
-                    assert err < 1e-6, ("nvls", optname, step, k, err)
-                    chk = int(got.view(np.int32).astype(np.int64).sum())
-                    assert all(c == chk for c in allgather_int(chk)), ("nvls replicas differ", optname, step, k)
-            assert mx.kv.launch_count() - before == 3, "one launch per pushpull expected"
-        assert mx.kv.launch_count("nvls") - nv0 == 15, "the multimem kernel did not serve every pushpull"
+        # the bench sweep's sizes in one call (every rank regenerates every rank's data: bounded for large worlds)
+        big = [(1 << p,) for p in range(10, 25 if world <= 2 else 23, 2)]
+        small = [(1 << 10,), (3 * (1 << 16),), (1 << 21,)]
+        sgd = dict(learning_rate=0.1, momentum=0.9, wd=1e-4)
+        expected = 0
+        # (requests in flight per thread, pipelined, grid cap, block size): the default and the corners of the
+        # tuning space (tools/tune_nvls.py) -- every instantiation that may become the default is compared
+        for ci, cfg in enumerate([(2, 0, 0, 512), (4, 1, 0, 512), (1, 0, 32, 256), (8, 1, 64, 512), (2, 1, 148, 512)]):
+            mx.kv.set_nvls_tuning(*cfg)
+            cases = [(None, {}, small), ("sgd", sgd, small), ("sgd", dict(sgd, learning_rate=0.01), big),
+                     ("adam", dict(learning_rate=0.001, wd=1e-3), big), (None, {}, big)] if ci == 0 else \
+                    [("sgd", sgd, small), ("adam", dict(learning_rate=0.001, wd=1e-3), small), (None, {}, small)]
+            for optname, kw, shapes in cases:
+                ks = list(range(len(shapes)))
+                kv7 = mx.kv.create("device")
+                w0 = [data(41 + k, s, 0) for k, s in zip(ks, shapes)]
+                kv7.init(ks, [mx.nd.array(w, ctx) for w in w0])
+                okv = O.OracleKVStore("device")
+                okv.init(ks, [w.copy() for w in w0])
+                if optname:
+                    kv7.set_optimizer(mx.optimizer.create(optname, **kw))
+                    okv.set_optimizer(O.OracleOptimizer(optname, **kw))
+                gm = [mx.nd.empty_multicast(s) for s in shapes]
+                om = [mx.nd.empty_multicast(s) for s in shapes]
+                before = mx.kv.launch_count()
+                for step in range(3):
+                    for k, s in zip(ks, shapes):
+                        gm[k][:] = data(300 + 10 * step + k, s, rank)
+                    device_sync(); barrier()
+                    kv7.pushpull(ks, gm, out=om)
+                    okv.push(ks, [[data(300 + 10 * step + k, s, r) for r in range(world)] for k, s in zip(ks, shapes)])
+                    for k, s in zip(ks, shapes):
+                        want = np.empty(s, np.float32)
+                        okv.pull(k, want)
+                        got = om[k].asnumpy()
+                        err = np.abs(got.astype(np.float64) - want).sum() / max(np.abs(want).sum(), 1e-30)
+                        assert err < 1e-6, ("nvls", cfg, optname, step, k, err)
+                        chk = int(got.view(np.int32).astype(np.int64).sum())
+                        assert all(c == chk for c in allgather_int(chk)), ("nvls replicas differ", cfg, optname, step, k)
+                assert mx.kv.launch_count() - before == 3, "one launch per pushpull expected"
+                expected += 3
+        assert mx.kv.launch_count("nvls") - nv0 == expected, "the multimem kernel did not serve every pushpull"
+        mx.kv.set_nvls_tuning(2, 0, 0, 512)
         mx.kv.set_nvls(1)
         print("NVLS_OK rank", rank, flush=True)
 
     # 7b. the peer-memory kernels, each variant FORCED: the shared-memory staged kernel
     #     (cp.async.bulk from peer HBM) and the per-thread kernel over the bench sweep's sizes in one call and
     #     one key per call, two-shot and one-shot, SGD momentum / Adam / plain sum, bit-exact
-    big = [1 << p for p in (range(10, 19, 2) if SIM else range(10, 25, 2))]
+    big = [1 << p for p in (range(10, 19, 2) if SIM else range(10, 25 if world <= 2 else 23, 2))]
     for variant, bulk in (("bulk", 2), ("per_thread", 0)):
         mx.kv.set_tuning(bulk=bulk)
         c0 = {v: mx.kv.launch_count(v) for v in ("bulk", "per_thread")}

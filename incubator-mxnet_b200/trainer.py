@@ -26,7 +26,7 @@ def _stype(x):
 
 class Trainer(object):
     def __init__(self, params, optimizer, optimizer_params=None, kvstore="device", compression_params=None,
-                 update_on_kvstore=None, batched=True, symmetric=False):
+                 update_on_kvstore=None, batched=True, symmetric=False, overlap=False, bucket_bytes=32 << 20):
         if isinstance(params, dict):               # trainer.py:80-84: a dict is taken in the order of its keys
             params = [params[k] for k in sorted(params.keys())]
         if not isinstance(params, (list, tuple)):
@@ -48,6 +48,14 @@ class Trainer(object):
         self._update_on_kvstore = None
         self._batched = batched
         self._symmetric = symmetric      # rebind p.data / p.grad to peer-mapped arena memory (zero-copy)
+        # overlap: exchange + update a bucket of parameters as soon as backward has produced its gradients
+        # (torch post-accumulate-grad hooks), on the engine's high-priority stream, while backward goes on -- the
+        # role priority=-i plays on the reference's engine (trainer.py:386-409, threaded_engine_perdevice.cc:97-279)
+        self._overlap = bool(overlap)
+        self._bucket_bytes = int(bucket_bytes)
+        self._buckets = None
+        self._armed_batch = None
+        self.trace = None                # set to [] to collect (bucket, start, end) CUDA events on the engine stream
         self._grads = None
         self._weights = None
 
@@ -208,6 +216,97 @@ class Trainer(object):
         held = set(self._sparse_idx)
         self._dense_idx = [i for i in range(len(self._params)) if i not in held]
 
+    # -- overlap of the exchange with backward -----------------------------------------------------------------
+    def _build_buckets(self):
+        """Buckets in REVERSE parameter order (backward produces the last layers' gradients first), each about
+        ``bucket_bytes`` of gradient; bucket b is one ``pushpull`` of its keys with priority -b."""
+        import torch
+        assert all(len(reps) == 1 and isinstance(reps[0].grad, torch.Tensor) or reps[0].grad is None
+                   for reps in self._params), "overlap needs one torch replica per parameter"
+        if self._grads is None:
+            self._bind_grads()
+        order = [i for i in reversed(range(len(self._params))) if self._params[i][0].requires_grad]
+        buckets, cur, cur_bytes = [], [], 0
+        for i in order:
+            p = self._params[i][0]
+            cur.append(i)
+            cur_bytes += p.numel() * p.element_size()
+            if cur_bytes >= self._bucket_bytes:
+                buckets.append(sorted(cur)); cur, cur_bytes = [], 0
+        if cur:
+            buckets.append(sorted(cur))
+        self._buckets = buckets
+        self._bucket_of = {i: b for b, idx in enumerate(buckets) for i in idx}
+        self._pending = [len(idx) for idx in buckets]
+        self._fired = [False] * len(buckets)
+        for i in order:
+            self._params[i][0].register_post_accumulate_grad_hook(self._make_hook(i))
+
+    def _make_hook(self, i):
+        def hook(_param):
+            if self._armed_batch is None:
+                return
+            b = self._bucket_of[i]
+            self._pending[b] -= 1
+            if self._pending[b] == 0:
+                self._fire(b)
+        return hook
+
+    def _fire(self, b):
+        idx = self._buckets[b]
+        kv = self._kvstore
+        ev = None
+        if self.trace is not None:
+            import torch
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        _kv.set_auto_fence(False)           # the framework stream must NOT wait for this exchange: backward goes on
+        try:
+            if ev is not None:
+                ev[0].record(self._engine_stream())
+            kv.pushpull(idx, [self._grads[i] for i in idx], out=[self._weights[i] for i in idx], priority=-b)
+            if ev is not None:
+                ev[1].record(self._engine_stream())
+                self.trace.append((b, ev[0], ev[1]))
+        finally:
+            _kv.set_auto_fence(True)
+        self._fired[b] = True
+
+    def _engine_stream(self):
+        if getattr(self, "_estream", None) is None:
+            import ctypes
+            import torch
+            from .base import _LIB, check_call
+            dev = self._weights[0][0].context.device_id
+            sp = ctypes.c_void_p()
+            check_call(_LIB.MXKVB200GetEngineStream(dev, ctypes.byref(sp)))
+            self._estream = torch.cuda.ExternalStream(sp.value, device=torch.device("cuda", dev))
+        return self._estream
+
+    def arm(self, batch_size):
+        """Overlap mode: the batch size of the coming ``step`` (rescale_grad is part of the fused update, which
+        now starts during backward).  ``step`` arms the next iteration with its own batch size, so only a CHANGE
+        of batch size has to be announced before ``backward``."""
+        self._armed_batch = batch_size
+        rescale = self._scale / batch_size
+        if self._optimizer.rescale_grad != rescale or getattr(self._kvstore, "_last_rescale", None) != rescale:
+            self._optimizer.rescale_grad = rescale
+            if getattr(self._kvstore, "_fused", False):
+                self._kvstore.set_optimizer(self._optimizer)
+            self._kvstore._last_rescale = rescale
+
+    def _finish_overlapped(self, batch_size):
+        """the part of ``step`` that is left when the buckets were exchanged during backward"""
+        assert self._armed_batch == batch_size, \
+            "overlap mode: step(%r) after a backward armed for batch size %r; call trainer.arm(batch_size) before " \
+            "backward when the batch size changes" % (batch_size, self._armed_batch)
+        for b, fired in enumerate(self._fired):
+            if not fired:                    # parameters that received no gradient in this backward
+                self._fire(b)
+        dev = self._weights[0][0].context.device_id
+        _kv.fence(dev)                      # ONE stream wait: the framework stream sees every updated weight
+        self._pending = [len(idx) for idx in self._buckets]
+        self._fired = [False] * len(self._buckets)
+
     def _allreduce_grads(self):
         """trainer.py:385-409, with every parameter in ONE call when ``batched`` (one launch per
         GPU instead of one per parameter; the C ABI has always accepted key lists)."""
@@ -243,6 +342,9 @@ class Trainer(object):
 
     def step(self, batch_size, ignore_stale_grad=False):
         """trainer.py:334-361: rescale_grad = scale / batch_size, allreduce, update."""
+        if self._overlap and self._kv_initialized and self._buckets is not None and self._armed_batch is not None:
+            self._finish_overlapped(batch_size)
+            return
         self._optimizer.rescale_grad = self._scale / batch_size
         if not self._kv_initialized:
             self._init_kvstore()
@@ -264,6 +366,12 @@ class Trainer(object):
                 scaler.update(self._kvstore.overflow())
         if not self._update_on_kvstore:
             self._update(ignore_stale_grad)
+        if self._overlap and self._update_on_kvstore and self._batched and self._kvstore is not None and \
+                getattr(self._kvstore, "_fused", False) and not getattr(self, "_sparse_idx", []) and scaler is None:
+            # from the next backward on, buckets are exchanged as their gradients become ready
+            if self._buckets is None:
+                self._build_buckets()
+            self.arm(batch_size)
 
     def allreduce_grads(self):
         if not self._kv_initialized:

@@ -168,3 +168,41 @@ def test_amp_with_update_on_kvstore_and_device_side_skip():
     for p, b in zip(params, after_clean):
         assert torch.equal(p, b)
     assert t._amp_loss_scaler._next_loss_scale == 2. ** 15
+
+
+@pytest.mark.parametrize("optname,kw", [("sgd", dict(learning_rate=0.1, momentum=0.9, wd=1e-4)),
+                                        ("adam", dict(learning_rate=0.01, wd=1e-3))])
+def test_overlap_buckets_match_the_plain_step(optname, kw):
+    """overlap=True: buckets of parameters are exchanged + updated from grad-ready hooks while backward is still
+    running (priority = -bucket), `step` only fences.  Same bits as the plain step, every step, including a
+    change of batch size announced with arm()."""
+    import torch
+
+    def net():
+        torch.manual_seed(3)
+        return torch.nn.Sequential(torch.nn.Linear(64, 256), torch.nn.ReLU(), torch.nn.Linear(256, 256),
+                                   torch.nn.ReLU(), torch.nn.Linear(256, 10)).cuda()
+    ma, mb = net(), net()
+    ta = mx.Trainer(list(ma.parameters()), optname, dict(kw), kvstore="device")
+    tb = mx.Trainer(list(mb.parameters()), optname, dict(kw), kvstore="device", overlap=True, bucket_bytes=64 << 10)
+    tb.trace = []
+    torch.manual_seed(9)
+    for step, bs in enumerate([32, 32, 32, 16, 16]):
+        x = torch.randn(bs, 64, device="cuda")
+        for m, t in ((ma, ta), (mb, tb)):
+            m.zero_grad(set_to_none=False)
+            if t is tb and step > 0:
+                t.arm(bs)
+            m(x).square().mean().backward()
+            t.step(bs)
+        torch.cuda.synchronize()
+        for pa, pb in zip(ma.parameters(), mb.parameters()):
+            assert _bits_equal(pa.detach().cpu().numpy(), pb.detach().cpu().numpy()), (optname, step)
+    assert tb._buckets is not None and len(tb._buckets) >= 2
+    # every overlapped step fired every bucket from a hook (4 overlapped steps)
+    assert len(tb.trace) == 4 * len(tb._buckets)
+    # a step() with a batch size the backward was not armed for is refused
+    mb.zero_grad(set_to_none=False)
+    mb(torch.randn(8, 64, device="cuda")).square().mean().backward()
+    with pytest.raises(AssertionError):
+        tb.step(8)

@@ -1,47 +1,59 @@
 #!/bin/bash
 # One gpurun call's worth of validation + measurement for N GPUs, every step under its own timeout, everything
 # written to gpurun_out/ (merged back by gpurun).  Usage:
-#   gpurun --timeout 1500 -- 'bash tools/gpu_round.sh 1'
-#   gpurun --gpus 2 --timeout 1200 -- 'bash tools/gpu_round.sh 2'
-#   gpurun --gpus 8 --timeout 1800 -- 'bash tools/gpu_round.sh 8'
+#   gpurun --timeout 2400 -- 'bash tools/gpu_round.sh 1'
+#   gpurun --gpus 2 --timeout 1500 -- 'bash tools/gpu_round.sh 2'
+#   gpurun --gpus 8 --timeout 1800 -- 'bash tools/gpu_round.sh 8 [tune]'
 # Order = priority: parity first (all failures listed, not just the first), then the bench lines, then profiles.
 N=${1:-1}
+MODE=${2:-full}
 OUT=gpurun_out
 mkdir -p $OUT
 export PYTHONUNBUFFERED=1
+LIGHT="--no-e2e --no-cpu-baseline --no-sweep --no-secondary --no-parity"
 run() {   # run <seconds> <logfile> <command...>
   local t=$1 log=$2; shift 2
   echo "== $* (limit ${t}s)" | tee -a $OUT/round_n$N.log
-  timeout $t "$@" > $OUT/$log 2>&1
-  echo "   exit $? -> $OUT/$log" | tee -a $OUT/round_n$N.log
+  local t0=$(date +%s)
+  timeout $t "$@" > $OUT/$log 2>$OUT/$log.err
+  echo "   exit $? after $(( $(date +%s) - t0 ))s -> $OUT/$log" | tee -a $OUT/round_n$N.log
 }
-torchrun_() { python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29555 "$@"; }
-
-run 900 pytest_n$N.log python -m pytest tests -m gpu -q --maxfail=25 -p no:cacheprovider
-tail -n 15 $OUT/pytest_n$N.log
-run 120 smoke_n$N.log python __graft_entry__.py smoke
+torchrun_() { local n=$1; shift; python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29500 + RANDOM % 400)) "$@"; }
+nvidia-smi --query-gpu=index,name,clocks.sm,clocks.max.sm,power.draw --format=csv > $OUT/gpus_n$N.csv 2>&1
+nvidia-smi topo -m > $OUT/topo_n$N.txt 2>&1
 
 if [ "$N" = "1" ]; then
-  run 400 bench_n1.json python bench.py --gpus 1
-  for seg in 1048576 2097152 8388608; do      # e2e pipeline segment (default 4 Mi elements): fill/drain vs launch count
-    MXKV_B200_HOST_SEG_ELEMS=$seg run 200 bench_n1_seg$seg.json python bench.py --gpus 1 --steps 40 --no-cpu-baseline
-  done
-  run 300 bench_bert_adam_n1.json python bench.py --workload bert --optimizer adam --steps 40 --no-e2e --no-cpu-baseline
-  run 300 bench_bert_lamb_n1.json python bench.py --workload bert --optimizer lamb --steps 40 --no-e2e --no-cpu-baseline
-  run 300 launches_n1.txt ncu --metrics gpu__time_duration.sum --clock-control none -s 10 -c 80 --csv \
-      python bench.py --steps 20 --warmup 3 --no-e2e --no-cpu-baseline
-else
-  run 500 bench_n$N.json torchrun_ bench.py --gpus $N
-  run 300 bench_bert_adam_n$N.json torchrun_ bench.py --gpus $N --workload bert --optimizer adam --steps 40 --no-e2e --no-cpu-baseline
+  run 1500 pytest_n1.log python -m pytest tests -m gpu -q --maxfail=25 -p no:cacheprovider --durations=12
+  tail -n 25 $OUT/pytest_n1.log
+  run 200 smoke_n1.log python __graft_entry__.py smoke
+  run 700 bench_n1.json python bench.py --gpus 1
+  run 300 launches_n1.csv ncu --metrics gpu__time_duration.sum --clock-control none -s 10 -c 60 --csv \
+      python bench.py --steps 20 --warmup 3 $LIGHT
+  run 400 ncu_full_n1.log ncu --set full --clock-control none --import-source on -k regex:kv_dense_bulk -s 4 -c 2 \
+      -f -o $OUT/r02_n1_bulk python bench.py --steps 6 --warmup 3 $LIGHT
+  run 300 bench_bert_adam_n1.json python bench.py --workload bert --optimizer adam --steps 40 $LIGHT
+  run 300 bench_bert_lamb_n1.json python bench.py --workload bert --optimizer lamb --steps 40 $LIGHT
+  run 300 bench_resnet_sgd_n1.json python bench.py --workload resnet50 --optimizer sgd --steps 100 $LIGHT
+  run 300 bench_ref_n1.json python bench.py --impl reference --gpus 1 --steps 3 --warmup 1
+elif [ "$MODE" = "tune" ]; then
+  # kernel tuning only (8-GPU minutes are charged 8x): multicast kernel knobs, peer kernels, NCCL, then N=4 on the same box
+  run 600 tune_nvls_n$N.txt torchrun_ $N tools/tune_nvls.py
   if [ "$N" = "8" ]; then
-    for u in 4 8; do
-      MXKV_B200_NVLS_U=$u run 300 bench_n8_nvls_u$u.json torchrun_ bench.py --gpus 8 --steps 100 --no-e2e --no-cpu-baseline
-    done
-    MXKV_B200_NVLS_U=8 run 300 bench_n8_allreduce_u8.json torchrun_ bench.py --gpus 8 --steps 100 --optimizer none --no-e2e --no-cpu-baseline
-    run 400 bench_n8_hier_2x4.json torchrun_ bench.py --gpus 8 --local-world 4 --steps 100 --no-e2e --no-cpu-baseline
+    TUNE_GRIDS=0,148,64,32 TUNE_OPTS=sgd run 300 tune_nvls_n4.txt torchrun_ 4 tools/tune_nvls.py
+  fi
+else
+  run 1500 pytest_n$N.log python -m pytest tests -m gpu -q --maxfail=25 -p no:cacheprovider --durations=12
+  tail -n 25 $OUT/pytest_n$N.log
+  run 700 bench_n$N.json torchrun_ $N bench.py --gpus $N
+  run 300 bench_ref_n$N.json torchrun_ $N bench.py --impl reference --gpus $N --steps 3 --warmup 1
+  run 300 bench_bert_adam_n$N.json torchrun_ $N bench.py --gpus $N --workload bert --optimizer adam --steps 40 $LIGHT
+  if [ "$N" = "8" ]; then
+    run 400 bench_n8_hier_2x4.json torchrun_ 8 bench.py --gpus 8 --local-world 4 --steps 100 $LIGHT
+    run 500 bench_n4.json torchrun_ 4 bench.py --gpus 4
+    run 500 bench_n2.json torchrun_ 2 bench.py --gpus 2
   fi
   if [ "$N" = "4" ]; then
-    run 400 bench_n4_hier_2x2.json torchrun_ bench.py --gpus 4 --local-world 2 --steps 100 --no-e2e --no-cpu-baseline
+    run 400 bench_n4_hier_2x2.json torchrun_ 4 bench.py --gpus 4 --local-world 2 --steps 100 $LIGHT
   fi
 fi
-grep -h '"metric"' $OUT/bench*_n$N*.json 2>/dev/null | cut -c1-400
+grep -h '"metric"' $OUT/bench*_n$N*.json 2>/dev/null | cut -c1-600

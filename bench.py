@@ -264,7 +264,8 @@ def cpu_kvstore_step_factory(shapes, n_values, threads, optimizer):
 
 
 def ncu_dram_bytes(path):
-    """dram__bytes_read.sum + dram__bytes_write.sum of the first kernel in an `ncu --page raw` text dump."""
+    """dram__bytes_read.sum + dram__bytes_write.sum of the first kernel in an `ncu --page raw` text dump
+    (`metric  unit  value` or `metric  value  unit` columns)."""
     units = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
     got = {}
     try:
@@ -272,8 +273,11 @@ def ncu_dram_bytes(path):
             for line in f:
                 parts = line.split()
                 if len(parts) >= 3 and parts[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum") \
-                        and parts[0] not in got and parts[-1] in units:
-                    got[parts[0]] = float(parts[-2].replace(",", "")) * units[parts[-1]]
+                        and parts[0] not in got:
+                    unit = [x for x in parts[1:] if x in units]
+                    num = [x for x in parts[1:] if x.replace(",", "").replace(".", "", 1).isdigit()]
+                    if unit and num:
+                        got[parts[0]] = float(num[-1].replace(",", "")) * units[unit[0]]
     except OSError:
         return None
     return sum(got.values()) if len(got) == 2 else None
@@ -684,12 +688,18 @@ def train_steps(env, args, which):
         torch._foreach_zero_(gl)
         torch.cuda.synchronize()
         bw = eb0.elapsed_time(eb1)
+        # per bucket: when its gradients were ready (framework stream) and when its exchange + update had
+        # finished (engine stream), ms from the start of backward; an exchange can start at max(ready, previous end)
         rows = [[b, eb0.elapsed_time(s), eb0.elapsed_time(e)] for b, s, e in trainer.trace]
-        busy = sum(e - s for _, s, e in rows)
-        hidden = sum(max(0.0, min(e, bw) - min(s, bw)) for _, s, e in rows)
+        busy, prev_end = 0.0, None
+        for _, ready, end in rows:
+            start = ready if prev_end is None else max(ready, prev_end)
+            busy += max(0.0, end - start)
+            prev_end = end
         trace = {"backward_ms": bw, "step_call_ms_after_backward": eb1.elapsed_time(eb2),
-                 "buckets_ms_from_backward_start": [[b, round(s, 3), round(e, 3)] for b, s, e in rows],
-                 "exchange_busy_ms": busy, "exchange_ms_inside_backward": hidden}
+                 "buckets_ready_end_ms_from_backward_start": [[b, round(s, 3), round(e, 3)] for b, s, e in rows],
+                 "exchange_busy_ms_upper_bound": busy,
+                 "exchange_exposed_ms_after_backward": max(0.0, max(e for _, _, e in rows) - bw) if rows else None}
         trainer.trace = None
     out = {"metric": metric, "value": world * B / (ms * 1e-3), "unit": "samples/s", "n_gpus": world, "steps": steps,
            "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -897,8 +907,8 @@ def main():
         step()
         kern[i][1].record(engine_stream)
     ev1.record()
+    host_issue_ms = (time.time() - t_host0) * 1e3 / args.steps      # the host's share: calls are asynchronous
     torch.cuda.synchronize(); env.barrier()
-    t_host1 = time.time()
     launches = mx.kv.launch_count() - launches0
     variant = variant_since(env, variants0)
     ms_total = ev0.elapsed_time(ev1)
@@ -1018,6 +1028,7 @@ def main():
             "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
             "roofline": roof, "cpu_baseline": cpu_base, "e2e": e2e, "gpu_launches": launches,
+            "host_issue_ms_per_step": host_issue_ms,
             "clocks": clocks, "parity": parity,
             "busbw_gbs_per_gpu": (2.0 * S * (world - 1) / world) / (ms_step * 1e-3) / 1e9 if world > 1 else 0.0,
             "exchange": exchange, "numa": numa,      # (not in `config`: the reference arm prints the same config)

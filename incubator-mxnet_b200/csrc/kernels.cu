@@ -722,31 +722,28 @@ int BulkPlan(int device, int opt, int multi_precision, int arrays, int* tile_ele
   if (st < 2) return 0;
   if (st > kBulkMaxStages) st = kBulkMaxStages;
   const int smem = st * arrays * tile * 4;
-  // function attributes are per device: opt in to large dynamic shared memory on every GPU
+  // function attributes are per device: opt in to large dynamic shared memory on THIS launch's GPU only (a
+  // process that owns one GPU must not create contexts on the others)
   static bool attr_done[64][16] = {{false}};
   const int slot = (opt & 7) * 2 + (multi_precision ? 1 : 0);
-  int ndev = 0;
-  if (cudaGetDeviceCount(&ndev) != cudaSuccess) { cudaGetLastError(); return 0; }
   int prev = -1;
   cudaGetDevice(&prev);
+  if (prev != device) cudaSetDevice(device);
   bool ok = true;
-  for (int dv = 0; dv < ndev && dv < 64; ++dv) {
-    if (attr_done[dv][slot]) continue;
-    cudaSetDevice(dv);
+  if (device >= 0 && device < 64 && !attr_done[device][slot]) {
     if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) {
       cudaGetLastError();
       ok = false;
-      break;
+    } else {
+      attr_done[device][slot] = true;
     }
-    attr_done[dv][slot] = true;
   }
-  cudaSetDevice(device);
   int occ = 0;
   if (ok && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kBulkThreads, smem) != cudaSuccess || occ < 1)) {
     cudaGetLastError();
     ok = false;
   }
-  if (prev >= 0) cudaSetDevice(prev);
+  if (prev >= 0 && prev != device) cudaSetDevice(prev);
   if (!ok) return 0;
   *tile_elems = tile;
   *stages = st;

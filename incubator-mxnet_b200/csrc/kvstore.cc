@@ -775,7 +775,13 @@ class AliasIndex {
 bool KVStore::HostPipelined(std::vector<Group>& groups, bool write_outs) {
   Runtime* rt = Runtime::Get();
   ProcessGroup* pg = PG();
-  if (pg != nullptr && pg->world() > 1) return false;
+  // one process per GPU: every rank streams ITS host value through its own PCIe link into a peer-mapped slot, and
+  // every rank's kernel sums all ranks' slots for the segment (one-shot: NVLink carries (n-1) x the segment, which
+  // is still several times faster than the PCIe copy it hides behind) and updates its own complete replica -- the
+  // optimizer state stays replicated, nothing is written across GPUs.  The decision below must come out the same
+  // on every rank (the same call with host-resident values everywhere), like every other collective call.
+  const bool coll = pg != nullptr && pg->world() > 1;
+  if (coll && (hier_ || EnvInt("MXKV_B200_HOST_PIPELINE_MP", 1) == 0)) return false;
   if (updater_ != nullptr) return false;
   if (opt_.enabled && IsNormOpt(opt_.kind)) return false;   // per-key norms need the whole key in one launch
   if (EnvInt("MXKV_B200_HOST_PIPELINE", 1) == 0) return false;
@@ -784,6 +790,7 @@ bool KVStore::HostPipelined(std::vector<Group>& groups, bool write_outs) {
     KeyState& ks = GetKey(g.key);
     if (ks.stype != kDefaultStorage) return false;
     if (static_cast<int>(g.vals.size()) > kMaxSrc) return false;
+    if (coll && g.vals.size() != 1) return false;
     for (auto& v : g.vals) {
       if (v.ctx().is_gpu()) return false;
       if (v.size() != ks.size || v.dtype() != ks.dtype) return false;   // let the generic path report it
@@ -812,6 +819,9 @@ bool KVStore::HostPipelined(std::vector<Group>& groups, bool write_outs) {
     if (!ks.reps.empty()) { dev = ks.reps[0].dev; break; }
   }
   if (dev < 0) dev = DefaultDevice();
+  if (coll) dev = pg->dev();
+  const int world = coll ? pg->world() : 1;
+  const int me = coll ? pg->rank() : 0;
   DeviceState& d = rt->Dev(dev);
   DeviceGuard dg(dev);
   const int64_t seg_elems = std::max<int64_t>(rt->chunk_elems, EnvInt("MXKV_B200_HOST_SEG_ELEMS", 4 << 20)) /
@@ -823,7 +833,15 @@ bool KVStore::HostPipelined(std::vector<Group>& groups, bool write_outs) {
     const size_t seg_bytes = static_cast<size_t>(std::min<int64_t>(seg_elems, ks.size)) * DTypeSize(ks.dtype);
     need = std::max(need, ((seg_bytes + 255) / 256 * 256) * g.vals.size());
   }
-  if (need > d.host_stage_bytes) {
+  if (coll) {
+    if (need > d.host_stage_peer_bytes) {          // collective allocation: `need` follows from the key sizes alone
+      for (int i = 0; i < DeviceState::kHostSlots; ++i) {
+        SymPtr sp = pg->SymAlloc(need);
+        for (int q = 0; q < world; ++q) d.host_stage_peer[i][q] = sp.ptr[q];
+      }
+      d.host_stage_peer_bytes = need;
+    }
+  } else if (need > d.host_stage_bytes) {
     rt->WaitDevice(dev);
     CUDA_CALL(cudaStreamSynchronize(d.copy_in));
     CUDA_CALL(cudaStreamSynchronize(d.copy_out));
@@ -839,7 +857,7 @@ bool KVStore::HostPipelined(std::vector<Group>& groups, bool write_outs) {
   for (int i = 0; i < DeviceState::kHostSlots; ++i) CUDA_CALL(cudaStreamWaitEvent(d.copy_in, d.ev_kern[i], 0));
 
   int64_t seq = 0;
-  std::vector<int> part_dev(1, dev);
+  std::vector<int> part_dev(world, dev);
   for (auto& g : groups) {
     KeyState& ks = GetKey(g.key);
     const size_t esize = DTypeSize(ks.dtype);
@@ -872,7 +890,8 @@ bool KVStore::HostPipelined(std::vector<Group>& groups, bool write_outs) {
       // stage 1: H2D (the slot is free once the kernel that last read it has finished)
       if (seq >= DeviceState::kHostSlots) CUDA_CALL(cudaStreamWaitEvent(d.copy_in, d.ev_kern[slot], 0));
       for (int k = 0; k < n_src; ++k) {
-        char* dst = static_cast<char*>(d.host_stage[slot]) + k * slot_stride;
+        char* dst = coll ? static_cast<char*>(d.host_stage_peer[slot][me])
+                         : static_cast<char*>(d.host_stage[slot]) + k * slot_stride;
         const char* src = static_cast<const char*>(g.vals[k].data()) + static_cast<size_t>(b) * esize;
         CUDA_CALL(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, d.copy_in));
       }
@@ -881,9 +900,15 @@ bool KVStore::HostPipelined(std::vector<Group>& groups, bool write_outs) {
       CUDA_CALL(cudaStreamWaitEvent(d.stream, d.ev_h2d[slot], 0));
       TensorWork tw;
       std::memset(&tw, 0, sizeof(tw));
-      tw.n_src = n_src;
-      for (int k = 0; k < n_src; ++k)
-        tw.src[k] = static_cast<char*>(d.host_stage[slot]) + k * slot_stride - static_cast<size_t>(b) * esize;
+      if (coll) {               // rank q's slot as mapped here; the start rendezvous orders it after q's H2D
+        tw.n_src = world;
+        for (int q = 0; q < world; ++q)
+          tw.src[q] = static_cast<char*>(d.host_stage_peer[slot][q]) - static_cast<size_t>(b) * esize;
+      } else {
+        tw.n_src = n_src;
+        for (int k = 0; k < n_src; ++k)
+          tw.src[k] = static_cast<char*>(d.host_stage[slot]) + k * slot_stride - static_cast<size_t>(b) * esize;
+      }
       tw.out[tw.n_out++] = r->local.data();
       tw.w = r->local.data();
       tw.w32 = mp ? static_cast<float*>(r->w32.data()) : nullptr;
@@ -892,9 +917,10 @@ bool KVStore::HostPipelined(std::vector<Group>& groups, bool write_outs) {
       tw.begin = b; tw.end = e;
       tw.lr = lr; tw.wd = wd; tw.eta = KeyEta(ks); tw.reserved_ = ks.key;
       tw.pad_ = 1 | ((esize == 4 && ks.size % 4 == 0) ? 2 : 0);
-      std::vector<std::vector<TensorWork>> per_part(1);
-      per_part[0].push_back(tw);
-      LaunchClassKey ck{SYNC_NONE, ks.dtype, mp ? 1 : 0};
+      std::vector<std::vector<TensorWork>> per_part(world);
+      per_part[me].push_back(tw);
+      // (the end rendezvous of a collective launch also tells this rank that no peer still reads its slot)
+      LaunchClassKey ck{coll ? SYNC_WRITE_PEERS : SYNC_NONE, ks.dtype, mp ? 1 : 0};
       LaunchWorks(ck, per_part, {e - b}, opt_kind, part_dev);
       CUDA_CALL(cudaEventRecord(d.ev_kern[slot], d.stream));
       // stage 3: D2H of the freshly written range of the replica

@@ -64,6 +64,9 @@ struct DeviceState {
   cudaEvent_t ev_d2h_all = nullptr;
   void* host_stage[kHostSlots] = {nullptr};
   size_t host_stage_bytes = 0;
+  // one process per GPU: the slots live in the peer-mapped arena (every rank's kernel reads every rank's slot)
+  void* host_stage_peer[kHostSlots][kMaxRanks] = {{nullptr}};
+  size_t host_stage_peer_bytes = 0;
 };
 
 // Multi-node jobs (dist_device_sync): the process group above spans ONE node (the GPUs that share an NVSwitch

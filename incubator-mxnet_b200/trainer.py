@@ -55,7 +55,8 @@ class Trainer(object):
         self._bucket_bytes = int(bucket_bytes)
         self._buckets = None
         self._armed_batch = None
-        self.trace = None                # set to [] to collect (bucket, start, end) CUDA events on the engine stream
+        self.trace = None                # set to [] to collect (bucket, gradients-ready event on the framework stream,
+                                         # exchange-finished event on the engine stream)
         self._grads = None
         self._weights = None
 
@@ -262,7 +263,7 @@ class Trainer(object):
         _kv.set_auto_fence(False)           # the framework stream must NOT wait for this exchange: backward goes on
         try:
             if ev is not None:
-                ev[0].record(self._engine_stream())
+                ev[0].record()               # framework stream: the moment this bucket's gradients are complete
             kv.pushpull(idx, [self._grads[i] for i in idx], out=[self._weights[i] for i in idx], priority=-b)
             if ev is not None:
                 ev[1].record(self._engine_stream())

@@ -41,6 +41,8 @@ elif [ "$MODE" = "tune" ]; then
   if [ "$N" = "8" ]; then
     TUNE_GRIDS=0,148,64,32 TUNE_OPTS=sgd run 300 tune_nvls_n4.txt torchrun_ 4 tools/tune_nvls.py
   fi
+  run 900 pytest_mp_n$N.log python -m pytest tests/test_gpu_multi.py -m gpu -q -p no:cacheprovider -k "mp_one_process_per_gpu and $N"
+  tail -n 30 $OUT/pytest_mp_n$N.log
 else
   run 1500 pytest_n$N.log python -m pytest tests -m gpu -q --maxfail=25 -p no:cacheprovider --durations=12
   tail -n 25 $OUT/pytest_n$N.log

@@ -88,6 +88,45 @@ __device__ __forceinline__ void barrier_end(const SyncArgs& s, bool release) {
 }
 
 // ---------------------------------------------------------------------------
+// Barrier over ALL blocks of the grid (the launcher sizes the grid to the resident capacity, so every block
+// is on an SM) and, when s.world > 1, over the grids of all ranks: blocks arrive on a counter in this GPU's
+// signal pad; the last one to arrive exchanges an epoch with the other ranks (release / acquire at system
+// scope: everything any block of any rank wrote before the barrier is visible to every block after it) and
+// then opens the next generation for the blocks spinning locally.  Lets a kernel have phases that the
+// reference (and round 1 of this engine) expressed as separate launches.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void grid_barrier(const SyncArgs& s) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t* g = s.self + kSigGridOff;
+    const uint32_t gen = ld_flag_volatile(g + kSigGridGen);
+    __threadfence_system();                       // this block's writes, before it is counted
+    const uint32_t arrived = atomicAdd(g + kSigGridCount, 1u);
+    if (arrived == gridDim.x - 1) {
+      g[kSigGridCount] = 0;
+      if (s.world > 1) {
+        const uint32_t epoch = g[kSigGridEpoch] + 1;
+        g[kSigGridEpoch] = epoch;
+        const long long t0 = clock64();
+        for (int q = 0; q < s.world; ++q)
+          st_flag_release(s.peers[q] + kSigGridOff + kSigGridFlags + s.rank, epoch);
+        for (int q = 0; q < s.world; ++q) {
+          const uint32_t* mine = g + kSigGridFlags + q;
+          // a fast rank may already have published its NEXT epoch: compare with >= (wrap-safe)
+          while (static_cast<int32_t>(ld_flag_acquire(mine) - epoch) < 0) spin_check(t0, s.timeout);
+        }
+      }
+      __threadfence_system();
+      st_flag_release(g + kSigGridGen, gen + 1);
+    } else {
+      const long long t0 = clock64();
+      while (ld_flag_acquire(g + kSigGridGen) == gen) spin_check(t0, s.timeout);
+    }
+  }
+  __syncthreads();
+}
+
+// ---------------------------------------------------------------------------
 // packets: a 16-byte vector or a single element, exposed as N floats
 // ---------------------------------------------------------------------------
 template <typename T> struct Cvt;

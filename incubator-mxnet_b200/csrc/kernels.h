@@ -86,7 +86,12 @@ struct SyncArgs {
 constexpr int kSigStartOff = 0;
 constexpr int kSigEndOff = kMaxBlocks * kMaxRanks;
 constexpr int kSigFlagOff = 2 * kMaxBlocks * kMaxRanks;
-constexpr size_t kSignalPadBytes = (2 * kMaxBlocks * kMaxRanks + kMaxBlocks) * sizeof(uint32_t);
+// grid-wide barrier words (device_utils.cuh: grid_barrier): arrival counter, generation, epoch of the cross-GPU
+// exchange, one flag per rank
+constexpr int kSigGridOff = 2 * kMaxBlocks * kMaxRanks + kMaxBlocks;
+constexpr int kSigGridCount = 0, kSigGridGen = 1, kSigGridEpoch = 2, kSigGridFlags = 4;
+constexpr int kSigGridWords = 4 + kMaxRanks;
+constexpr size_t kSignalPadBytes = (2 * kMaxBlocks * kMaxRanks + kMaxBlocks + kSigGridWords) * sizeof(uint32_t);
 
 struct DenseLaunch {
   const TensorWork* works;       // device pointer, nworks entries

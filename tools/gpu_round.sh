@@ -18,7 +18,8 @@ run() {   # run <seconds> <logfile> <command...>
   timeout $t "$@" > $OUT/$log 2>$OUT/$log.err
   echo "   exit $? after $(( $(date +%s) - t0 ))s -> $OUT/$log" | tee -a $OUT/round_n$N.log
 }
-torchrun_() { local n=$1; shift; python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29500 + RANDOM % 400)) "$@"; }
+# (a plain word list, not a shell function: `timeout` execs its command)
+torchrun_() { echo python -m torch.distributed.run --nnodes=1 --nproc-per-node $1 --master-addr 127.0.0.1 --master-port $((29500 + RANDOM % 400)); }
 nvidia-smi --query-gpu=index,name,clocks.sm,clocks.max.sm,power.draw --format=csv > $OUT/gpus_n$N.csv 2>&1
 nvidia-smi topo -m > $OUT/topo_n$N.txt 2>&1
 
@@ -37,25 +38,23 @@ if [ "$N" = "1" ]; then
   run 300 bench_ref_n1.json python bench.py --impl reference --gpus 1 --steps 3 --warmup 1
 elif [ "$MODE" = "tune" ]; then
   # kernel tuning only (8-GPU minutes are charged 8x): multicast kernel knobs, peer kernels, NCCL, then N=4 on the same box
-  run 600 tune_nvls_n$N.txt torchrun_ $N tools/tune_nvls.py
+  run 600 tune_nvls_n$N.txt $(torchrun_ $N) tools/tune_nvls.py
   if [ "$N" = "8" ]; then
-    TUNE_GRIDS=0,148,64,32 TUNE_OPTS=sgd run 300 tune_nvls_n4.txt torchrun_ 4 tools/tune_nvls.py
+    TUNE_GRIDS=0,148,64,32 TUNE_OPTS=sgd run 300 tune_nvls_n4.txt $(torchrun_ 4) tools/tune_nvls.py
   fi
-  run 900 pytest_mp_n$N.log python -m pytest tests/test_gpu_multi.py -m gpu -q -p no:cacheprovider -k "mp_one_process_per_gpu and $N"
-  tail -n 30 $OUT/pytest_mp_n$N.log
 else
   run 1500 pytest_n$N.log python -m pytest tests -m gpu -q --maxfail=25 -p no:cacheprovider --durations=12
   tail -n 25 $OUT/pytest_n$N.log
-  run 700 bench_n$N.json torchrun_ $N bench.py --gpus $N
-  run 300 bench_ref_n$N.json torchrun_ $N bench.py --impl reference --gpus $N --steps 3 --warmup 1
-  run 300 bench_bert_adam_n$N.json torchrun_ $N bench.py --gpus $N --workload bert --optimizer adam --steps 40 $LIGHT
+  run 700 bench_n$N.json $(torchrun_ $N) bench.py --gpus $N
+  run 300 bench_ref_n$N.json $(torchrun_ $N) bench.py --impl reference --gpus $N --steps 3 --warmup 1
+  run 300 bench_bert_adam_n$N.json $(torchrun_ $N) bench.py --gpus $N --workload bert --optimizer adam --steps 40 $LIGHT
   if [ "$N" = "8" ]; then
-    run 400 bench_n8_hier_2x4.json torchrun_ 8 bench.py --gpus 8 --local-world 4 --steps 100 $LIGHT
-    run 500 bench_n4.json torchrun_ 4 bench.py --gpus 4
-    run 500 bench_n2.json torchrun_ 2 bench.py --gpus 2
+    run 400 bench_n8_hier_2x4.json $(torchrun_ 8) bench.py --gpus 8 --local-world 4 --steps 100 $LIGHT
+    run 500 bench_n4.json $(torchrun_ 4) bench.py --gpus 4
+    run 500 bench_n2.json $(torchrun_ 2) bench.py --gpus 2
   fi
   if [ "$N" = "4" ]; then
-    run 400 bench_n4_hier_2x2.json torchrun_ 4 bench.py --gpus 4 --local-world 2 --steps 100 $LIGHT
+    run 400 bench_n4_hier_2x2.json $(torchrun_ 4) bench.py --gpus 4 --local-world 2 --steps 100 $LIGHT
   fi
 fi
 grep -h '"metric"' $OUT/bench*_n$N*.json 2>/dev/null | cut -c1-600

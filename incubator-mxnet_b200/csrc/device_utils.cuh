@@ -89,13 +89,13 @@ __device__ __forceinline__ void barrier_end(const SyncArgs& s, bool release) {
 
 // ---------------------------------------------------------------------------
 // Barrier over ALL blocks of the grid (the launcher sizes the grid to the resident capacity, so every block
-// is on an SM) and, when s.world > 1, over the grids of all ranks: blocks arrive on a counter in this GPU's
+// is on an SM) and, when `cross` and s.world > 1, over the grids of all ranks: blocks arrive on a counter in this GPU's
 // signal pad; the last one to arrive exchanges an epoch with the other ranks (release / acquire at system
 // scope: everything any block of any rank wrote before the barrier is visible to every block after it) and
 // then opens the next generation for the blocks spinning locally.  Lets a kernel have phases that the
 // reference (and round 1 of this engine) expressed as separate launches.
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ void grid_barrier(const SyncArgs& s) {
+__device__ __forceinline__ void grid_barrier(const SyncArgs& s, bool cross) {
   __syncthreads();
   if (threadIdx.x == 0) {
     uint32_t* g = s.self + kSigGridOff;
@@ -104,7 +104,7 @@ __device__ __forceinline__ void grid_barrier(const SyncArgs& s) {
     const uint32_t arrived = atomicAdd(g + kSigGridCount, 1u);
     if (arrived == gridDim.x - 1) {
       g[kSigGridCount] = 0;
-      if (s.world > 1) {
+      if (cross && s.world > 1) {
         const uint32_t epoch = g[kSigGridEpoch] + 1;
         g[kSigGridEpoch] = epoch;
         const long long t0 = clock64();

@@ -62,6 +62,10 @@ struct Replica {
   // row_sparse keys: `local` is the dense-backed table [num_rows x row_len]
   NDArray rsp_merged;            // union ids + summed rows of the last push (capacity n * rsp_cap rows)
   NDArray rsp_first, rsp_pf;     // int32 workspaces of the union kernels
+  NDArray rsp_lidx;              // fused push: local copies of the sources' id lists [rsp_lidx_n x rsp_lidx_cap]
+  int64_t rsp_lidx_cap = 0;
+  int rsp_lidx_n = 0;
+  bool rsp_stage_guarded = false;   // MP: the last push ended with a cross-GPU barrier (nobody reads the staging area)
   int64_t rsp_cap = 0;           // rows per source the workspaces are sized for
   int rsp_n = 0;
   NDArray stage_idx, stage_val, stage_nnz;   // MP mode: symmetric staging of this rank's gradient

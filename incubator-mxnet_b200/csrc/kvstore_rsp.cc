@@ -159,9 +159,12 @@ void KVStore::PushRowSparse(KeyState& ks, const std::vector<NDArray>& vals) {
     if (work_devs.empty()) work_devs.push_back(DefaultDevice());
     rt->EnablePeerAccess(work_devs);
   }
+  // One launch instead of nine when the merged value itself is not needed (lazy fused update): publish, union,
+  // gather-sum and update in rsp_push_fused_kernel
+  const bool fused_path = fused && opt_.lazy_update && EnvInt("MXKV_B200_RSP_FUSED", 1) != 0;
   for (auto& v : vals) {
     if (v.ctx().is_gpu()) touch(v.ctx().dev_id);
-    PublishNnz(v);
+    if (!fused_path) PublishNnz(v);          // (the fused kernel takes the row counts by value)
   }
   for (int d : work_devs) { touch(d); EnsureReplica(ks, d); }
   if (fused) {
@@ -206,13 +209,16 @@ void KVStore::PushRowSparse(KeyState& ks, const std::vector<NDArray>& vals) {
     for (int q = 0; q < world; ++q) sync.peers[q] = pg->signal_pad(q);
     sync.world = world; sync.rank = pg->rank(); sync.mode = SYNC_WRITE_PEERS;
     sync.timeout = rt->spin_timeout_cycles;
-    CheckLaunch(LaunchBarrier(sync, s), "barrier");
-    if (v.nnz() > 0) {
-      CopyBytes(v.idx_ptr(), v.ctx(), r.stage_idx.data(), r.stage_idx.ctx(), v.nnz() * 8);
-      CopyBytes(v.data(), v.ctx(), r.stage_val.data(), r.stage_val.ctx(), v.nnz() * L * 4);
+    if (!fused_path || !r.rsp_stage_guarded) CheckLaunch(LaunchBarrier(sync, s), "barrier");
+    if (!fused_path) {
+      if (v.nnz() > 0) {
+        CopyBytes(v.idx_ptr(), v.ctx(), r.stage_idx.data(), r.stage_idx.ctx(), v.nnz() * 8);
+        CopyBytes(v.data(), v.ctx(), r.stage_val.data(), r.stage_val.ctx(), v.nnz() * L * 4);
+      }
+      CheckLaunch(LaunchSetI64(static_cast<int64_t*>(r.stage_nnz.data()), v.nnz(), s), "set_nnz");
+      CheckLaunch(LaunchBarrier(sync, s), "barrier");
     }
-    CheckLaunch(LaunchSetI64(static_cast<int64_t*>(r.stage_nnz.data()), v.nnz(), s), "set_nnz");
-    CheckLaunch(LaunchBarrier(sync, s), "barrier");
+    r.rsp_stage_guarded = fused_path;      // the fused kernel ends with a cross-GPU barrier
   }
 
   // ---- per computing GPU: sources as seen from it, then the four kernels -----------------------
@@ -259,13 +265,15 @@ void KVStore::PushRowSparse(KeyState& ks, const std::vector<NDArray>& vals) {
         }
       }
     }
-    EnsureRspWorkspace(ks, r, S.n, cap);
+    if (!fused_path) EnsureRspWorkspace(ks, r, S.n, cap);      // (the fused kernel materialises no union)
     RspRowArgs A;
     std::memset(&A, 0, sizeof(A));
-    A.out_idx = r.rsp_merged.idx_ptr();
     const bool std_update = fused && !opt_.lazy_update;   // dense pass over every row (reference default)
-    A.out_val = (fused && !std_update) ? nullptr : static_cast<float*>(r.rsp_merged.data());
-    A.d_nnz_out = r.rsp_merged.d_nnz();
+    if (!fused_path) {
+      A.out_idx = r.rsp_merged.idx_ptr();
+      A.out_val = (fused && !std_update) ? nullptr : static_cast<float*>(r.rsp_merged.data());
+      A.d_nnz_out = r.rsp_merged.d_nnz();
+    }
     A.table = static_cast<float*>(r.local.data());
     A.row_len = L;
     A.opt = (fused && !std_update) ? opt_.kind : OPT_NONE;
@@ -283,6 +291,63 @@ void KVStore::PushRowSparse(KeyState& ks, const std::vector<NDArray>& vals) {
     if (A.assign) {
       // push without updater: local = merged (kvstore_local.h:279-284) -- rows outside the union vanish
       CUDA_CALL(cudaMemsetAsync(r.local.data(), 0, r.local.nbytes(), s));
+    }
+    if (fused_path) {
+      RspStage St;
+      std::memset(&St, 0, sizeof(St));
+      SyncArgs sync;
+      std::memset(&sync, 0, sizeof(sync));
+      sync.self = rt->Dev(dev).signal_pad;
+      sync.world = 1; sync.rank = 0; sync.mode = SYNC_NONE;
+      sync.timeout = rt->spin_timeout_cycles;
+      int64_t est_rows = 0;
+      void* tmp_src[2] = {nullptr, nullptr};
+      if (world > 1) {
+        const NDArray& v = vals[0];
+        for (int q = 0; q < world; ++q) sync.peers[q] = pg->signal_pad(q);
+        sync.world = world; sync.rank = pg->rank(); sync.mode = SYNC_WRITE_PEERS;
+        St.publish = 1;
+        St.src_idx = v.idx_ptr();
+        St.src_val = static_cast<const float*>(v.data());
+        St.src_nnz = v.nnz();
+        if (!(v.ctx().is_gpu() && v.ctx().dev_id == dev) && v.nnz() > 0) {      // host-resident gradient: one hop first
+          CUDA_CALL(cudaMallocAsync(&tmp_src[0], v.nnz() * 8, s));
+          CUDA_CALL(cudaMallocAsync(&tmp_src[1], v.nnz() * L * 4, s));
+          CopyBytes(v.idx_ptr(), v.ctx(), tmp_src[0], Context{kGPU, dev}, v.nnz() * 8);
+          CopyBytes(v.data(), v.ctx(), tmp_src[1], Context{kGPU, dev}, v.nnz() * L * 4);
+          St.src_idx = static_cast<const int64_t*>(tmp_src[0]);
+          St.src_val = static_cast<const float*>(tmp_src[1]);
+        }
+        St.dst_idx = static_cast<int64_t*>(r.stage_idx.data());
+        St.dst_val = static_cast<float*>(r.stage_val.data());
+        St.dst_nnz = static_cast<int64_t*>(r.stage_nnz.data());
+        St.localize = 1;
+        est_rows = std::max<int64_t>(v.nnz(), 1) * world;
+        A.vec = (A.vec && Aligned16(St.src_val) && Aligned16(St.dst_val)) ? 1 : 0;
+      } else {
+        St.nnz_by_value = 1;
+        for (int k = 0; k < n_src; ++k) {
+          const Context c = vals[k].ctx();
+          if (c.is_gpu() && c.dev_id != dev && S.idx[k] == vals[k].idx_ptr()) St.localize = 1;
+          St.nnz_val[k] = vals[k].nnz();
+          est_rows += vals[k].nnz();
+        }
+      }
+      if (St.localize) {
+        const int64_t lcap = std::max<int64_t>(cap, 16);
+        if (r.rsp_lidx.is_none() || r.rsp_lidx_n < S.n || r.rsp_lidx_cap < lcap) {
+          r.rsp_lidx_n = std::max(r.rsp_lidx_n, S.n);
+          r.rsp_lidx_cap = std::max(r.rsp_lidx_cap, lcap);
+          r.rsp_lidx = NDArray::Empty({static_cast<int64_t>(r.rsp_lidx_n) * r.rsp_lidx_cap}, Context{kGPU, dev}, kInt64);
+        }
+        St.lidx = static_cast<int64_t*>(r.rsp_lidx.data());
+        St.lcap = r.rsp_lidx_cap;
+      }
+      CheckLaunch(LaunchRspPushFused(dev, S, A, St, sync, est_rows, s), "rsp_push_fused");
+      for (void* t : tmp_src) if (t) CUDA_CALL(cudaFreeAsync(t, s));
+      for (void* t : temps) CUDA_CALL(cudaFreeAsync(t, s));
+      r.fresh = true;
+      continue;
     }
     CheckLaunch(LaunchRspSum(S, A, static_cast<int32_t*>(r.rsp_first.data()),
                              static_cast<int32_t*>(r.rsp_pf.data()), r.rsp_cap, s), "rsp_sum");
@@ -623,11 +688,23 @@ void KVStore::PullRowSparseImpl(const std::vector<int>& keys,
     MXKV_CHECK(target.cap_rows() >= n) << "row_sparse_pull: output holds " << target.cap_rows() << " rows, "
                                        << n << " row ids requested";
     MXKV_CHECK(target.dtype() == kFloat32) << "row_sparse_pull: float32 outputs only";
-    CheckLaunch(LaunchRspUnique(ids, n, target.idx_ptr(), target.d_nnz(), s), "rsp_unique");
     const int vec = (L % 4 == 0 && Aligned16(r.local.data()) && Aligned16(target.data())) ? 1 : 0;
-    CheckLaunch(LaunchRspGather(static_cast<const float*>(r.local.data()), target.idx_ptr(), target.d_nnz(),
-                                std::max<int64_t>(n, 1), L, static_cast<float*>(target.data()), target.idx_ptr(),
-                                vec, s), "rsp_gather");
+    if (n >= 1 && n <= RspUniqueMax() && EnvInt("MXKV_B200_RSP_FUSED", 1) != 0) {
+      // unique | grid barrier | gather in one launch
+      SyncArgs sync;
+      std::memset(&sync, 0, sizeof(sync));
+      sync.self = rt->Dev(dev).signal_pad;
+      sync.world = 1; sync.rank = 0; sync.mode = SYNC_NONE;
+      sync.timeout = rt->spin_timeout_cycles;
+      CheckLaunch(LaunchRspPullFused(dev, static_cast<const float*>(r.local.data()), ids, n, target.idx_ptr(),
+                                     target.d_nnz(), L, static_cast<float*>(target.data()), vec, sync, s),
+                  "rsp_pull_fused");
+    } else {
+      CheckLaunch(LaunchRspUnique(ids, n, target.idx_ptr(), target.d_nnz(), s), "rsp_unique");
+      CheckLaunch(LaunchRspGather(static_cast<const float*>(r.local.data()), target.idx_ptr(), target.d_nnz(),
+                                  std::max<int64_t>(n, 1), L, static_cast<float*>(target.data()), target.idx_ptr(),
+                                  vec, s), "rsp_gather");
+    }
     target.set_nnz_device();
     if (tmp_ids) CUDA_CALL(cudaFreeAsync(tmp_ids, s));
     if (tmp_cast) CUDA_CALL(cudaFreeAsync(tmp_cast, s));

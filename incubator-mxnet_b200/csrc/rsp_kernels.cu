@@ -18,6 +18,7 @@
 // The row counts stay on the device (every kernel reads nnz through a pointer).
 #include "rsp_kernels.h"
 #include "rsp_math.h"
+#include "device_utils.cuh"
 
 namespace mxkv {
 
@@ -172,9 +173,7 @@ rsp_rows_kernel(RspSources S, RspRowArgs A) {
 // single-block bitonic sort + unique of up to kUniqueMax int64 ids in shared memory
 constexpr int kUniqueMax = 16384;
 
-__global__ void __launch_bounds__(1024)
-rsp_unique_kernel(const int64_t* in, int64_t n, int64_t* out, int64_t* d_count) {
-  extern __shared__ int64_t sm[];
+__device__ __forceinline__ void unique_block(const int64_t* in, int64_t n, int64_t* out, int64_t* d_count, int64_t* sm) {
   // fast path: ids that are already strictly increasing (e.g. the index array of a row_sparse
   // gradient) need neither the sort nor the compaction
   {
@@ -237,6 +236,12 @@ rsp_unique_kernel(const int64_t* in, int64_t n, int64_t* out, int64_t* d_count) 
     __syncthreads();
   }
   if (threadIdx.x == 0) *d_count = carry;
+}
+
+__global__ void __launch_bounds__(1024)
+rsp_unique_kernel(const int64_t* in, int64_t n, int64_t* out, int64_t* d_count) {
+  extern __shared__ int64_t sm[];
+  unique_block(in, n, out, d_count, sm);
 }
 
 // ---- large id lists (> kUniqueMax): bitonic sort in global memory, one launch per (k, j) step, then
@@ -331,6 +336,142 @@ rsp_scatter_kernel(float* table, const int64_t* idx, const int64_t* d_nnz, int64
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Fused row_sparse push: ONE launch for "publish my gradient to the peers, union of the ranks' row ids, gather-sum
+// in source order, lazy optimizer update of the touched rows" (round 1: two rendezvous kernels + two staging
+// copies + first / scan / rank / rows = up to nine launches, and every binary search of a peer's id list crossed
+// NVLink one dependent load at a time).  Phases, separated by the grid-wide barrier of device_utils.cuh:
+//   P0 (one process per GPU)  copy this rank's (ids, rows, count) into its peer-mapped staging area   | cross-GPU barrier
+//   P1 (any remote source)    pull every source's id list into LOCAL memory with coalesced reads       | local barrier
+//   P2                        one warp per candidate row (s, r): lane t searches source t's (local) id list; the
+//                             candidate is processed iff no source before s holds the id (so every union row is
+//                             summed exactly once, by its first holder's candidate) -- contributions added in
+//                             source order onto a zero accumulator (ndarray_function.cu:176-187), then the lazy
+//                             update of that row of the table (rsp_math.h).  No sorted union is materialised:
+//                             nothing downstream of a fused update needs it.
+//   P3 (one process per GPU)  cross-GPU barrier: no peer still reads this rank's staging area when it returns
+// ---------------------------------------------------------------------------------------------------
+template <int OPT, bool VEC>
+__global__ void __launch_bounds__(256)
+rsp_push_fused_kernel(RspSources S, RspRowArgs A, RspStage St, SyncArgs sync) {
+  __shared__ int64_t s_nnz[kMaxSrc + 1];     // exclusive prefix of the sources' row counts
+  const int lane = threadIdx.x & 31;
+  const int64_t nthreads = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  const int64_t gtid = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  const int64_t L = A.row_len;
+
+  if (St.publish) {                                    // ---- P0
+    const int64_t nnz = St.src_nnz;
+    for (int64_t i = gtid; i < nnz; i += nthreads) St.dst_idx[i] = St.src_idx[i];
+    if (VEC) {
+      const int64_t nv = nnz * L / 4;
+      const float4* sv = reinterpret_cast<const float4*>(St.src_val);
+      float4* dv = reinterpret_cast<float4*>(St.dst_val);
+      for (int64_t i = gtid; i < nv; i += nthreads) dv[i] = sv[i];
+    } else {
+      for (int64_t i = gtid; i < nnz * L; i += nthreads) St.dst_val[i] = St.src_val[i];
+    }
+    if (gtid == 0) *St.dst_nnz = nnz;
+    grid_barrier(sync, true);
+  }
+
+  __shared__ int64_t s_cnt[kMaxSrc];
+  if (threadIdx.x < S.n)                                                 // (peer memory: n round trips in parallel)
+    s_cnt[threadIdx.x] = St.nnz_by_value ? St.nnz_val[threadIdx.x] : *S.nnz[threadIdx.x];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int64_t run = 0;
+    for (int t = 0; t < S.n; ++t) { s_nnz[t] = run; run += s_cnt[t]; }
+    s_nnz[S.n] = run;
+  }
+  __syncthreads();
+
+  if (St.localize) {                                   // ---- P1
+    for (int t = 0; t < S.n; ++t) {
+      const int64_t nt = s_nnz[t + 1] - s_nnz[t];
+      int64_t* dst = St.lidx + static_cast<int64_t>(t) * St.lcap;
+      for (int64_t i = gtid; i < nt; i += nthreads) dst[i] = S.idx[t][i];
+    }
+    grid_barrier(sync, false);
+  }
+
+  // ---- P2
+  const int64_t total = s_nnz[S.n];
+  const int64_t warps_total = static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5);
+  for (int64_t j = blockIdx.x * static_cast<int64_t>(blockDim.x >> 5) + (threadIdx.x >> 5); j < total; j += warps_total) {
+    int s = 0;
+    while (s + 1 < S.n && j >= s_nnz[s + 1]) ++s;
+    const int64_t r = j - s_nnz[s];
+    const int64_t* my_ids = St.localize ? St.lidx + static_cast<int64_t>(s) * St.lcap : S.idx[s];
+    const int64_t id = my_ids[r];
+    int64_t mypos = -1;
+    if (lane < S.n) {
+      if (lane == s) {
+        mypos = r;
+      } else {
+        const int64_t nt = s_nnz[lane + 1] - s_nnz[lane];
+        const int64_t* ids_t = St.localize ? St.lidx + static_cast<int64_t>(lane) * St.lcap : S.idx[lane];
+        const int64_t p = lower_bound_i64(ids_t, nt, id);
+        if (p < nt && ids_t[p] == id) mypos = p;
+      }
+    }
+    const unsigned holders = __ballot_sync(0xffffffffu, mypos >= 0);
+    if (holders & ((1u << s) - 1u)) continue;          // an earlier source holds this id: its candidate does the row
+    constexpr int W = VEC ? 4 : 1;
+    for (int64_t c0 = 0; c0 < L; c0 += 32 * W) {
+      const int64_t c = c0 + static_cast<int64_t>(lane) * W;
+      const bool act = c < L;
+      float acc[W];
+#pragma unroll
+      for (int i = 0; i < W; ++i) acc[i] = 0.f;
+      for (int t = s; t < S.n; ++t) {
+        const int64_t p = __shfl_sync(0xffffffffu, mypos, t);
+        if (p < 0 || !act) continue;
+        const float* src = S.val[t] + p * L + c;
+        if (VEC) {
+          const float4 v = *reinterpret_cast<const float4*>(src);
+          acc[0] = __fadd_rn(acc[0], v.x); acc[1 % W] = __fadd_rn(acc[1 % W], v.y);
+          acc[2 % W] = __fadd_rn(acc[2 % W], v.z); acc[3 % W] = __fadd_rn(acc[3 % W], v.w);
+        } else {
+          acc[0] = __fadd_rn(acc[0], src[0]);
+        }
+      }
+      if (!act) continue;
+      float* w = A.table + id * L + c;
+#pragma unroll
+      for (int i = 0; i < W; ++i) w[i] = rsp_lazy_update<OPT>(acc[i], w[i], id * L + c + i, A);
+    }
+  }
+
+  if (St.publish) grid_barrier(sync, true);            // ---- P3
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Fused row_sparse_pull: unique (block 0: already-increasing fast path, else bitonic sort + compaction in shared
+// memory) | grid barrier | one warp per row gather -- one launch instead of two.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+rsp_pull_fused_kernel(const float* table, const int64_t* in, int64_t n, int64_t* out_idx, int64_t* d_count, int64_t L,
+                      float* out_val, int vec, SyncArgs sync) {
+  extern __shared__ int64_t sm[];
+  if (blockIdx.x == 0) unique_block(in, n, out_idx, d_count, sm);
+  grid_barrier(sync, false);
+  const int lane = threadIdx.x & 31;
+  const int64_t warps_total = static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5);
+  const int64_t cnt = *d_count;
+  for (int64_t j = blockIdx.x * static_cast<int64_t>(blockDim.x >> 5) + (threadIdx.x >> 5); j < cnt; j += warps_total) {
+    const int64_t id = out_idx[j];
+    const float* src = table + id * L;
+    float* dst = out_val + j * L;
+    if (vec) {
+      for (int64_t c = lane * 4; c < L; c += 128)
+        *reinterpret_cast<float4*>(dst + c) = *reinterpret_cast<const float4*>(src + c);
+    } else {
+      for (int64_t c = lane; c < L; c += 32) dst[c] = src[c];
+    }
+  }
+}
+
 __global__ void rsp_set_i64_kernel(int64_t* p, int64_t v) { *p = v; }
 
 }  // namespace
@@ -363,6 +504,66 @@ int LaunchRspSum(const RspSources& S, const RspRowArgs& A, int32_t* first, int32
     default: return static_cast<int>(cudaErrorInvalidValue);
   }
 #undef RSP_ROWS
+  return static_cast<int>(cudaGetLastError());
+}
+
+static int resident_grid(int device, const void* fn, int threads, size_t smem) {
+  int prev = -1;
+  cudaGetDevice(&prev);
+  if (prev != device) cudaSetDevice(device);
+  int occ = 0, sms = 0;
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessorWithFlags(&occ, fn, threads, smem, cudaOccupancyDefault);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  if (prev >= 0 && prev != device) cudaSetDevice(prev);
+  if (e != cudaSuccess || occ < 1 || sms < 1) { cudaGetLastError(); return 0; }
+  const int64_t g = static_cast<int64_t>(occ) * sms;
+  return static_cast<int>(g > kMaxBlocks ? kMaxBlocks : g);
+}
+
+int LaunchRspPushFused(int device, const RspSources& S, const RspRowArgs& A, const RspStage& St, const SyncArgs& sync,
+                       int64_t est_rows, cudaStream_t stream) {
+  if (S.n < 1 || S.n > kMaxSrc || A.out_val != nullptr || A.assign) return static_cast<int>(cudaErrorInvalidValue);
+  typedef void (*Fn)(RspSources, RspRowArgs, RspStage, SyncArgs);
+  Fn fn = nullptr;
+  const bool vec = A.vec != 0;
+  switch (A.opt) {
+    case OPT_SGD: fn = vec ? rsp_push_fused_kernel<OPT_SGD, true> : rsp_push_fused_kernel<OPT_SGD, false>; break;
+    case OPT_SGD_MOM: fn = vec ? rsp_push_fused_kernel<OPT_SGD_MOM, true> : rsp_push_fused_kernel<OPT_SGD_MOM, false>; break;
+    case OPT_ADAM: fn = vec ? rsp_push_fused_kernel<OPT_ADAM, true> : rsp_push_fused_kernel<OPT_ADAM, false>; break;
+    default: return static_cast<int>(cudaErrorInvalidValue);
+  }
+  // the grid barrier needs every block resident; more blocks than candidate rows / 8 warps would only spin
+  static int cap[64][8] = {{0}};
+  int& c = cap[device & 63][(A.opt & 3) * 2 + (vec ? 1 : 0)];
+  if (c == 0) c = resident_grid(device, reinterpret_cast<const void*>(fn), 256, 0);
+  if (c < 1) return static_cast<int>(cudaErrorLaunchOutOfResources);
+  int64_t want = (est_rows + 7) / 8;
+  if (St.publish) want = std::max<int64_t>(want, 148);      // the staging copy wants the whole machine
+  const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(c, want)));
+  fn<<<grid, 256, 0, stream>>>(S, A, St, sync);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int LaunchRspPullFused(int device, const float* table, const int64_t* ids, int64_t n, int64_t* out_idx, int64_t* d_count,
+                       int64_t L, float* out_val, int vec, const SyncArgs& sync, cudaStream_t stream) {
+  if (n < 1 || n > kUniqueMax) return static_cast<int>(cudaErrorInvalidValue);
+  int64_t npad = 1;
+  while (npad < n) npad <<= 1;
+  const size_t smem = static_cast<size_t>(npad) * sizeof(int64_t);
+  static bool attr_set[64] = {false};
+  if (!attr_set[device & 63]) {
+    int prev = -1;
+    cudaGetDevice(&prev);
+    if (prev != device) cudaSetDevice(device);
+    cudaFuncSetAttribute(rsp_pull_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         kUniqueMax * static_cast<int>(sizeof(int64_t)));
+    if (prev >= 0 && prev != device) cudaSetDevice(prev);
+    attr_set[device & 63] = true;
+  }
+  const int c = resident_grid(device, reinterpret_cast<const void*>(rsp_pull_fused_kernel), 1024, smem);
+  if (c < 1) return static_cast<int>(cudaErrorLaunchOutOfResources);
+  const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(c, (n + 31) / 32)));
+  rsp_pull_fused_kernel<<<grid, 1024, smem, stream>>>(table, ids, n, out_idx, d_count, L, out_val, vec, sync);
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -25,6 +25,31 @@ struct RspRowArgs {
   float lr, wd, rescale, clip, momentum, beta1, beta2, eps;
 };
 
+// fused push (rsp_push_fused_kernel): staging of this rank's gradient and local copies of the id lists
+struct RspStage {
+  const int64_t* src_idx;  // this rank's gradient as the caller holds it ...
+  const float* src_val;
+  int64_t src_nnz;
+  int64_t* dst_idx;        // ... and its peer-mapped staging area (one process per GPU)
+  float* dst_val;
+  int64_t* dst_nnz;
+  int64_t* lidx;           // [n x lcap] local copies of every source's id list
+  int64_t lcap;
+  int64_t nnz_val[kMaxSrc]; // row counts by value (single process: the host knows them; saves a launch per value)
+  int nnz_by_value;
+  int publish;             // 1: phase P0 / P3 (copy into the staging area, cross-GPU barriers)
+  int localize;            // 1: phase P1 (some source lives on another GPU)
+};
+
+// One launch: (publish) | (localize ids) | union + gather-sum + lazy update of the touched rows | (barrier).
+// Only for pushes that do not have to materialise the merged value (A.out_val == nullptr, A.assign == 0).
+// `est_rows`: the host's estimate of the candidate rows (sum of the sources' row counts), sizes the grid.
+int LaunchRspPushFused(int device, const RspSources& S, const RspRowArgs& A, const RspStage& St, const SyncArgs& sync,
+                       int64_t est_rows, cudaStream_t stream);
+// One launch: unique (n <= RspUniqueMax()) | gather
+int LaunchRspPullFused(int device, const float* table, const int64_t* ids, int64_t n, int64_t* out_idx, int64_t* d_count,
+                       int64_t L, float* out_val, int vec, const SyncArgs& sync, cudaStream_t stream);
+
 int LaunchRspSum(const RspSources& S, const RspRowArgs& A, int32_t* first, int32_t* pf, int64_t cap,
                  cudaStream_t stream);
 int RspUniqueMax();

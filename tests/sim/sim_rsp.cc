@@ -4,6 +4,9 @@
 #include <climits>
 #include <cstdint>
 #include <cstring>
+#include <ctime>
+#include <sched.h>
+#include <unistd.h>
 #include "sim.h"
 #include "rsp_math.h"
 
@@ -202,6 +205,102 @@ bool CastIds(const std::vector<std::string>& t, void** args) {   // rsp_cast_ids
   return true;
 }
 
+// grid barrier of device_utils.cuh for the one sequential "block" of an emulated kernel: locally a no-op; across
+// ranks (one process per GPU on the simulator) the real epoch exchange through the peer-mapped pads
+void GridBarrierCross(const SyncArgs& s) {
+  static const bool mp = getenv("MXKV_SIM_MP") != nullptr;
+  if (!mp || s.world <= 1) return;
+  uint32_t* g = s.self + kSigGridOff;
+  const uint32_t epoch = g[kSigGridEpoch] + 1;
+  g[kSigGridEpoch] = epoch;
+  for (int q = 0; q < s.world; ++q)
+    __atomic_store_n(s.peers[q] + kSigGridOff + kSigGridFlags + s.rank, epoch, __ATOMIC_RELEASE);
+  for (int q = 0; q < s.world; ++q) {
+    const uint32_t* mine = g + kSigGridFlags + q;
+    long spins = 0;
+    const time_t t0 = time(nullptr);
+    while (static_cast<int32_t>(__atomic_load_n(mine, __ATOMIC_ACQUIRE) - epoch) < 0) {
+      if ((++spins & 255) == 0) {
+        if (spins > 4096) usleep(100); else sched_yield();
+        if (time(nullptr) - t0 > 600) { fprintf(stderr, "[mxkv sim] grid barrier timed out\n"); abort(); }
+      }
+    }
+  }
+}
+
+template <int OPT>
+void PushFusedT(const RspSources& S, const RspRowArgs& A, const RspStage& St, const SyncArgs& sync) {
+  const int64_t L = A.row_len;
+  if (St.publish) {
+    if (St.src_nnz > 0) {
+      std::memcpy(St.dst_idx, St.src_idx, St.src_nnz * sizeof(int64_t));
+      std::memcpy(St.dst_val, St.src_val, St.src_nnz * L * sizeof(float));
+    }
+    *St.dst_nnz = St.src_nnz;
+    GridBarrierCross(sync);
+  }
+  std::vector<int64_t> nnz(S.n);
+  for (int t = 0; t < S.n; ++t) nnz[t] = St.nnz_by_value ? St.nnz_val[t] : *S.nnz[t];
+  std::vector<const int64_t*> ids(S.n);
+  for (int t = 0; t < S.n; ++t) {
+    ids[t] = S.idx[t];
+    if (St.localize) {
+      int64_t* dst = St.lidx + static_cast<int64_t>(t) * St.lcap;
+      if (nnz[t] > St.lcap) { fprintf(stderr, "[mxkv sim] id list exceeds the local workspace\n"); abort(); }
+      if (nnz[t] > 0) std::memcpy(dst, S.idx[t], nnz[t] * sizeof(int64_t));
+      ids[t] = dst;
+    }
+  }
+  for (int s = 0; s < S.n; ++s) {
+    for (int64_t r = 0; r < nnz[s]; ++r) {
+      const int64_t id = ids[s][r];
+      int64_t pos[kMaxSrc];
+      bool earlier = false;
+      for (int t = 0; t < S.n; ++t) {
+        const int64_t p = (t == s) ? r : LowerBound(ids[t], nnz[t], id);
+        pos[t] = (p < nnz[t] && ids[t][p] == id) ? p : -1;
+        if (t < s && pos[t] >= 0) earlier = true;
+      }
+      if (earlier) continue;
+      for (int64_t c = 0; c < L; ++c) {
+        float acc = 0.f;
+        for (int t = s; t < S.n; ++t)
+          if (pos[t] >= 0) acc = __fadd_rn(acc, S.val[t][pos[t] * L + c]);
+        float* w = A.table + id * L + c;
+        *w = rsp_lazy_update<OPT>(acc, *w, id * L + c, A);
+      }
+    }
+  }
+  if (St.publish) GridBarrierCross(sync);
+}
+
+bool PushFused(const std::vector<std::string>& t, void** args) {   // rsp_push_fused_kernel<OPT, VEC>(S, A, St, sync)
+  const RspSources& S = Arg<RspSources>(args, 0);
+  const RspRowArgs& A = Arg<RspRowArgs>(args, 1);
+  const RspStage& St = Arg<RspStage>(args, 2);
+  const SyncArgs& sync = Arg<SyncArgs>(args, 3);
+  switch (atoi(t[0].c_str())) {
+    case OPT_SGD: PushFusedT<OPT_SGD>(S, A, St, sync); break;
+    case OPT_SGD_MOM: PushFusedT<OPT_SGD_MOM>(S, A, St, sync); break;
+    case OPT_ADAM: PushFusedT<OPT_ADAM>(S, A, St, sync); break;
+    default: return false;
+  }
+  return true;
+}
+
+bool PullFused(void** args) {   // (table, in, n, out_idx, d_count, L, out_val, vec, sync)
+  const float* table = Arg<const float*>(args, 0);
+  const int64_t* in = Arg<const int64_t*>(args, 1);
+  const int64_t n = Arg<int64_t>(args, 2);
+  int64_t* out_idx = Arg<int64_t*>(args, 3);
+  int64_t* d_count = Arg<int64_t*>(args, 4);
+  const int64_t L = Arg<int64_t>(args, 5);
+  float* out_val = Arg<float*>(args, 6);
+  SortedUnique(std::vector<int64_t>(in, in + n), out_idx, d_count);
+  for (int64_t j = 0; j < *d_count; ++j) std::memcpy(out_val + j * L, table + out_idx[j] * L, L * sizeof(float));
+  return true;
+}
+
 }  // namespace
 
 bool DispatchRsp(const LaunchInfo&, const std::string& base, const std::vector<std::string>& t, void** args) {
@@ -211,6 +310,8 @@ bool DispatchRsp(const LaunchInfo&, const std::string& base, const std::vector<s
   if (k == "rsp_scan_kernel") return Scan(args);
   if (k == "rsp_rank_kernel") return Rank(args);
   if (k == "rsp_rows_kernel") return Rows(t, args);
+  if (k == "rsp_push_fused_kernel") return PushFused(t, args);
+  if (k == "rsp_pull_fused_kernel") return PullFused(args);
   if (k == "rsp_unique_kernel") return Unique(args);
   if (k == "rsp_pad_kernel") return Pad(args);
   if (k == "rsp_bitonic_step_kernel") return BitonicStep(args);

@@ -156,3 +156,51 @@ def test_sp_multi_gpu_sources():
             want = O.sparse_retain(okv.local[0], O.unique(ids))
             assert np.array_equal(out.indices.asnumpy(), want.indices)
             assert _bits_equal(out.data.asnumpy(), want.data.reshape(-1, L)), (step, d)
+
+
+@pytest.mark.parametrize("n", [1, 4])
+def test_c5_shape_fused_push_and_pull(n):
+    """BASELINE.json configs[4] at its exact shape -- one row_sparse key of 1 M x 256 float32, 10 000 distinct rows
+    per value, lazy SGD-momentum -- through the fused kernels (rsp_push_fused_kernel, rsp_pull_fused_kernel): n
+    values per push on one GPU (the cross-GPU form of the same kernels: tests/mp_worker.py scenario 5), three
+    pushes, row_sparse_pull of the touched rows after each; only the touched rows are compared (the oracle keeps
+    the table sparse; untouched rows are checked once by sampling)."""
+    import os
+    sim = bool(os.environ.get("MXKV_SIM"))
+    R, L, nnz = (20000, 64, 500) if sim else (1_000_000, 256, 10_000)
+    shape = (R, L)
+    rng = np.random.default_rng(55 + n)
+    kw = dict(learning_rate=0.01, momentum=0.9, wd=0.0, lazy_update=True)
+    kv = mx.kv.create("device")
+    kv.init("emb", mx.nd.row_sparse_array((np.zeros((1, L), np.float32), np.zeros(1, np.int64)), shape=shape, ctx=mx.gpu(0)))
+    kv.set_optimizer(mx.optimizer.SGD(**kw))
+    # host model of the touched rows only: weight and momentum per row id
+    w, m = {}, {}
+    before = mx.kv.launch_count()
+    for step in range(3):
+        srcs = [_rand_rsp(rng, R, L, nnz) for _ in range(n)]
+        kv.push("emb", [_mk(i, v, shape, mx.gpu(0)) for i, v in srcs])
+        merged = O.rsp_sum([O.RowSparse(i, v, shape) for i, v in srcs])
+        for j, rid in enumerate(merged.indices):
+            rid = int(rid)
+            g = merged.data.reshape(-1, L)[j]
+            wr = w.get(rid, np.zeros(L, np.float32))
+            mr = m.get(rid, np.zeros(L, np.float32))
+            O.sgd_mom_update(wr, g.copy(), mr, kw["learning_rate"], kw["wd"], kw["momentum"])
+            w[rid], m[rid] = wr, mr
+        ids = merged.indices.astype(np.int64)
+        if step == 1:                       # unsorted ids with repeats: the sort + compaction path of the pull kernel
+            ids = np.concatenate([ids[::-1][: min(len(ids), 16000)], ids[:100]])
+        out = mx.nd.empty(shape, mx.gpu(0), stype="row_sparse", capacity=len(ids))
+        kv.row_sparse_pull("emb", out=out, row_ids=mx.nd.array(ids, mx.gpu(0), dtype=np.int64))
+        got_idx, got = out.indices.asnumpy(), out.data.asnumpy().reshape(-1, L)
+        want_idx = np.unique(ids)
+        assert np.array_equal(got_idx, want_idx), (n, step)
+        want = np.stack([w[int(r)] for r in want_idx])
+        assert _bits_equal(got, want), (n, step)
+    assert mx.kv.launch_count() - before <= 3 * 2 + 2, "push and row_sparse_pull are one launch each"
+    # rows nobody pushed are still zero
+    probe = np.setdiff1d(rng.choice(R, 200, replace=False), np.fromiter(w.keys(), dtype=np.int64))
+    out = mx.nd.empty(shape, mx.gpu(0), stype="row_sparse", capacity=len(probe))
+    kv.row_sparse_pull("emb", out=out, row_ids=mx.nd.array(probe.astype(np.int64), mx.gpu(0), dtype=np.int64))
+    assert not out.data.asnumpy().any()

@@ -150,7 +150,10 @@ class Runtime {
   int nvls_mode = 1;                         // MXKV_B200_NVLS: use multimem kernels for multicast-bound arrays
   int nvls_unroll = 2;                       // MXKV_B200_NVLS_U: ld_reduce requests in flight per thread (1 | 2 | 4 | 8)
   int nvls_pipe = 0;                         // MXKV_B200_NVLS_PIPE: issue the next chunk's ld_reduce before this chunk's update
-  int nvls_grid = 0;                         // MXKV_B200_NVLS_GRID: cap on the multicast kernel's grid (0: resident capacity)
+  int nvls_grid = 48;                        // MXKV_B200_NVLS_GRID: cap on the multicast kernel's grid (0: resident capacity).
+                                             // The switch, not the SMs, bounds this kernel: 24-64 blocks are 3-4 % faster than
+                                             // a full grid at 8 ranks and leave 100 SMs to whatever else is running
+                                             // (profiles/r02_nvls_tune_n8.txt)
   int nvls_threads = 512;                    // MXKV_B200_NVLS_THREADS: its block size (128 | 256 | 512)
   int bulk_mode = 1;                         // MXKV_B200_BULK: 0 off, 1 auto (<= 2 sources), 2 whenever eligible
  private:

@@ -46,6 +46,9 @@ else
   run 1500 pytest_n$N.log python -m pytest tests -m gpu -q --maxfail=25 -p no:cacheprovider --durations=12
   tail -n 25 $OUT/pytest_n$N.log
   run 700 bench_n$N.json $(torchrun_ $N) bench.py --gpus $N
+  # NVLink byte counters of the exchange kernel (rank 0 under ncu, one pass; see tools/ncu_rank0.sh)
+  run 200 ncu_nvl_n$N.log $(torchrun_ $N) --no-python tools/ncu_rank0.sh bench.py --gpus $N --steps 12 --warmup 3 $LIGHT
+  NCU_TAG=_p2p run 200 ncu_nvl_p2p_n$N.log $(torchrun_ $N) --no-python tools/ncu_rank0.sh bench.py --gpus $N --steps 12 --warmup 3 --no-nvls $LIGHT
   run 300 bench_ref_n$N.json $(torchrun_ $N) bench.py --impl reference --gpus $N --steps 3 --warmup 1
   run 300 bench_bert_adam_n$N.json $(torchrun_ $N) bench.py --gpus $N --workload bert --optimizer adam --steps 40 $LIGHT
   if [ "$N" = "8" ]; then

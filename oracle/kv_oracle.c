@@ -23,10 +23,12 @@
  * this container (libmxnet needs a BLAS and ~1.5k translation units), but the
  * reference's non-fused Python `step()` methods -- its own oracle for its fused kernels,
  * tests/python/unittest/test_optimizer.py -- can be executed: tests/golden/make_golden.py runs
- * SGD / Adam / Test / LAMB / LANS / LARS `step` out of the reference tree and the optimizer
+ * SGD / Adam / AdamW / Test / LAMB / LANS / LARS `step` out of the reference tree and the optimizer
  * routines below are checked against those outputs (tests/golden/optimizer_steps.npz,
- * layerwise.npz) within that test's tolerances.  AdamW and the sparse update kernels are pinned
- * by a hand-written restatement only.
+ * layerwise.npz) within that test's tolerances.  The sparse (lazy and standard) update kernels are
+ * checked the same way against the classes the reference's tests hold them to -- PySparseSGD /
+ * PySparseAdam of tests/python/unittest/test_optimizer.py and SGD.step on the densified gradient --
+ * executed from the reference files (tests/golden/sparse_steps.npz).
  */
 #include <stdint.h>
 #include <stdlib.h>

@@ -13,6 +13,11 @@
 
 * optimizer_steps.npz -- the same for SGD / SGD-momentum / Adam / Test (sgd.py, adam.py, optimizer.py).
 
+* sparse_steps.npz -- row_sparse gradients: the reference's OWN Python references for its sparse kernels,
+                      ``PySparseSGD.step`` / ``PySparseAdam.step`` (tests/python/unittest/test_optimizer.py:90-159,
+                      372-437; lazy and standard), and ``SGD.step`` on the densified gradient for the standard SGD
+                      update (test_std_sparse_sgd, :183-203), executed from the reference files the same way.
+
 The GPU box has no /root/reference; tests read the committed fixtures instead.
 """
 import ast
@@ -246,6 +251,102 @@ def plain_steps():
     np.savez_compressed(os.path.join(HERE, "optimizer_steps.npz"), **out)
 
 
+def sparse_steps():
+    """sparse_steps.npz -- pins the restatement of the sparse (lazy and standard) kernels:
+    the classes the reference's tests compare those kernels with are executed from the reference's test file."""
+    import math
+    src = open(os.path.join(REF, "tests/python/unittest/test_optimizer.py")).read()
+    tree = ast.parse(src)
+
+    class _NDShim(object):
+        @staticmethod
+        def clip(x, lo, hi, out=None):
+            r = np.clip(np.asarray(x), np.float32(lo), np.float32(hi))
+            if out is not None:
+                out[...] = r
+                return out
+            return r.view(_F32)
+
+        @staticmethod
+        def square(x, out=None):
+            r = np.square(np.asarray(x))
+            if out is not None:
+                out[...] = r
+                return out
+            return r.view(_F32)
+
+        @staticmethod
+        def sqrt(x, out=None):
+            return np.sqrt(np.asarray(x)).view(_F32)
+
+    class _TestUtils(object):
+        @staticmethod
+        def almost_equal(a, b, rtol=None, atol=None):      # python/mxnet/test_utils.py:629-635,171-177 (float64 defaults)
+            return bool(np.allclose(a, b, rtol=1e-5 if rtol is None else rtol, atol=1e-20 if atol is None else atol))
+
+    class _MX(object):
+        nd = _NDShim
+        test_utils = _TestUtils
+
+    def grab(cls):
+        for node in tree.body:
+            if isinstance(node, ast.ClassDef) and node.name == cls:
+                for item in node.body:
+                    if isinstance(item, ast.FunctionDef) and item.name == "step":
+                        ns = {"mx": _MX, "np": np, "math": math}
+                        exec(compile(ast.Module([item], []), "reference:tests/python/unittest/test_optimizer.py", "exec"), ns)
+                        return {"step": ns["step"]}
+        raise KeyError(cls)
+
+    class _RowView(_F32):
+        """`x[row]` of an NDArray is a writable view with .asnumpy()"""
+        def asnumpy(self):
+            return np.asarray(self)
+
+    def nd(a):
+        return np.array(a, dtype=np.float32).view(_RowView)
+
+    py_sgd, py_adam = grab("PySparseSGD"), grab("PySparseAdam")
+    dense_sgd = _step_functions("sgd.py", "SGD", ["step"])
+    out, meta = {}, []
+    rng = np.random.default_rng(20260924)
+    cases = []
+    for mom in (0.0, 0.9):
+        for extra in (dict(), dict(clip_gradient=0.4, rescale_grad=0.14, wd=0.03)):
+            cases.append(("sgd_lazy", py_sgd, 0.1, dict(momentum=mom, **extra)))
+            cases.append(("sgd_std", dense_sgd, 0.1, dict(momentum=mom, **extra)))
+    for lazy in (True, False):
+        for extra in (dict(), dict(beta1=0.5, beta2=0.8, clip_gradient=0.4, rescale_grad=0.14, wd=0.03)):
+            cases.append(("adam_lazy" if lazy else "adam_std", py_adam, 0.01, dict(lazy_update=lazy, **extra)))
+    for ci, (name, fns, lr, kw) in enumerate(cases):
+        kw = dict(kw)
+        wd = kw.pop("wd", 0.0)
+        attrs = dict(beta1=0.9, beta2=0.999, epsilon=1e-8, momentum=0.0, lazy_update=False)
+        attrs.update(kw)
+        for si, shape in enumerate([(10, 4), (37, 6)]):
+            opt = _FakeOptimizer(fns, lr, wd, **attrs)
+            w = nd(rng.uniform(-1, 1, shape))
+            if name.startswith("sgd"):
+                state = nd(np.zeros(shape)) if attrs["momentum"] != 0.0 else None
+            else:
+                state = (nd(np.zeros(shape)), nd(np.zeros(shape)))
+            tag = "c%d_s%d" % (ci, si)
+            out["w0_" + tag] = np.asarray(w).copy()
+            for t in range(4):
+                rows = np.sort(rng.choice(shape[0], max(1, shape[0] // 3), replace=False))
+                g = np.zeros(shape, np.float32)
+                g[rows] = rng.uniform(-1, 1, (len(rows),) + shape[1:]).astype(np.float32)
+                # keep every present row clearly non-zero: the references skip rows that are `almost_equal` to zero
+                g[rows, 0] = np.where(np.abs(g[rows, 0]) < 0.05, 0.5, g[rows, 0])
+                out["rows%d_%s" % (t, tag)] = rows.astype(np.int64)
+                out["g%d_%s" % (t, tag)] = g.copy()
+                opt.step([0], [w], [nd(g)], [state])
+                out["w%d_%s" % (t + 1, tag)] = np.asarray(w).copy()
+        meta.append(repr((name, lr, wd, attrs)))
+    out["cases"] = np.array(meta)
+    np.savez_compressed(os.path.join(HERE, "sparse_steps.npz"), **out)
+
+
 LR_CASES = [
     ("FactorScheduler", dict(step=7, factor=0.5, base_lr=0.3)),
     ("FactorScheduler", dict(step=3, factor=0.1, stop_factor_lr=1e-4, base_lr=0.1, warmup_steps=5, warmup_begin_lr=0.01)),
@@ -280,5 +381,6 @@ if __name__ == "__main__":
     compression()
     layerwise()
     plain_steps()
+    sparse_steps()
     lr_schedules()
     print("wrote", sorted(f for f in os.listdir(HERE) if f.endswith(".npz")))

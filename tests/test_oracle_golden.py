@@ -508,3 +508,41 @@ def test_rsp_sum_and_retain_oracle_properties():
     assert _eq_bits(acc, s.data[0])
     ret = O.sparse_retain(s, O.unique([3, 3, 1, 49]))
     assert list(ret.indices) == [1, 3, 49]
+
+
+def test_sparse_optimizers_vs_reference_python_references_golden():
+    """tests/golden/sparse_steps.npz: weights produced by the classes the reference's OWN tests
+    hold its sparse kernels to -- `PySparseSGD.step`, `PySparseAdam.step` (lazy and standard;
+    tests/python/unittest/test_optimizer.py:90-159,372-437) and `SGD.step` on the densified gradient
+    (test_std_sparse_sgd :183-203) -- executed from the reference files by make_golden.py::sparse_steps.  The
+    restatements of SGDDnsRspKernel / SGDMomDnsRspDnsKernel / AdamDnsRspDnsKernel / the *Std* kernels in oracle/
+    must agree within the tolerances of those tests (SGD: compare_optimizer defaults rtol 1e-4 / atol 1e-5; Adam
+    rtol 1e-4 / atol 2e-5, :486-499); they in fact agree to a few ulp."""
+    gold = np.load(os.path.join(GOLD, "sparse_steps.npz"))
+    cases = [eval(c) for c in gold["cases"]]
+    worst = 0.0
+    seen = set()
+    for ci, (name, lr, wd, attrs) in enumerate(cases):
+        seen.add(name)
+        for si in range(2):
+            tag = "c%d_s%d" % (ci, si)
+            w = gold["w0_" + tag].copy()
+            kw = dict(learning_rate=lr, wd=wd, rescale_grad=attrs.get("rescale_grad", 1.0),
+                      clip_gradient=attrs.get("clip_gradient"), lazy_update=name.endswith("lazy"))
+            if name.startswith("sgd"):
+                opt = O.OracleOptimizer("sgd", momentum=attrs["momentum"], **kw)
+            else:
+                opt = O.OracleOptimizer("adam", beta1=attrs["beta1"], beta2=attrs["beta2"], epsilon=attrs["epsilon"], **kw)
+            for t in range(4):
+                rows = gold["rows%d_%s" % (t, tag)]
+                g = gold["g%d_%s" % (t, tag)]
+                grad = O.RowSparse(rows, g[rows].copy(), g.shape)
+                opt.update(0, w, grad)
+                want = gold["w%d_%s" % (t + 1, tag)]
+                if name.startswith("adam"):
+                    np.testing.assert_allclose(w, want, rtol=1e-4, atol=2e-5, err_msg=str((name, ci, si, t)))
+                else:
+                    np.testing.assert_allclose(w, want, rtol=1e-4, atol=1e-5, err_msg=str((name, ci, si, t)))
+                worst = max(worst, float(np.max(np.abs(w - want))))
+    assert seen == {"sgd_lazy", "sgd_std", "adam_lazy", "adam_std"}
+    assert worst < 2e-6, worst

@@ -151,6 +151,37 @@ def bind_to_gpu_numa(gpu_index):
 
 
 # ---------------------------------------------------------------------------
+# NVLink traffic as the hardware counts it (NVML field values, no profiler): DATA = payload bytes, RAW = payload +
+# protocol overhead, both directions, summed over the GPU's 18 links.  Read before and after the timed region,
+# the difference per step is the `traffic` of the N > 1 roofline (ncu cannot profile a kernel that rendezvous
+# with kernels on other GPUs: profiles/README.md).
+# ---------------------------------------------------------------------------
+_NVL_FIELDS = {"data_tx": 138, "data_rx": 139, "raw_tx": 140, "raw_rx": 141}     # NVML_FI_DEV_NVLINK_THROUGHPUT_*, KiB
+
+
+def nvlink_counters(gpu_index):
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        ids = list(_NVL_FIELDS.values())
+        try:
+            vals = pynvml.nvmlDeviceGetFieldValues(h, [(f, 0xFFFFFFFF) for f in ids])     # scope: all links
+        except Exception:
+            vals = pynvml.nvmlDeviceGetFieldValues(h, ids)
+        out = {}
+        for name, v in zip(_NVL_FIELDS, vals):
+            if v.nvmlReturn != 0:
+                return {"error": "nvml field %s: return %d" % (name, v.nvmlReturn)}
+            vt = v.valueType
+            val = {0: v.value.dVal, 1: v.value.uiVal, 2: v.value.ulVal, 3: v.value.ullVal, 4: v.value.sllVal}.get(vt, v.value.ullVal)
+            out[name] = float(val) * 1024.0
+        return out
+    except Exception as e:          # noqa: BLE001
+        return {"error": repr(e)[:120]}
+
+
+# ---------------------------------------------------------------------------
 # clocks
 # ---------------------------------------------------------------------------
 class ClockSampler(object):
@@ -900,6 +931,7 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kern = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     torch.cuda.synchronize(); env.barrier()
+    nvl0 = nvlink_counters(local) if world > 1 else None
     t_host0 = time.time()
     ev0.record()
     for i in range(args.steps):
@@ -909,6 +941,7 @@ def main():
     ev1.record()
     host_issue_ms = (time.time() - t_host0) * 1e3 / args.steps      # the host's share: calls are asynchronous
     torch.cuda.synchronize(); env.barrier()
+    nvl1 = nvlink_counters(local) if world > 1 else None
     launches = mx.kv.launch_count() - launches0
     variant = variant_since(env, variants0)
     ms_total = ev0.elapsed_time(ev1)
@@ -961,6 +994,17 @@ def main():
                 "note": "bytes that must cross this GPU's NVLink per direction; busbw_gbs_per_gpu is the "
                         "NCCL-comparable 2S(n-1)/n / t"}
     roof["frac"] = roof["achieved"] / roof["peak"]
+    if world > 1:
+        if nvl0 and nvl1 and "error" not in nvl0 and "error" not in nvl1:
+            per = {k: (nvl1[k] - nvl0[k]) / args.steps for k in _NVL_FIELDS}
+            # (the NVML counters tick in coarse units and lag by a sampling period: over 300 steps that is < 1 %)
+            roof["traffic"] = per["raw_tx"] + per["raw_rx"]
+            roof["traffic_source"] = "NVML NVLINK_THROUGHPUT_RAW_TX + RAW_RX of this rank's GPU over the timed region, per step"
+            roof["nvlink_bytes_per_step"] = per
+            roof["nvlink_raw_gbs_per_dir"] = {"tx": per["raw_tx"] / (ms_step * 1e-3) / 1e9, "rx": per["raw_rx"] / (ms_step * 1e-3) / 1e9}
+            roof["nvlink_payload_efficiency"] = {"tx": per["data_tx"] / max(per["raw_tx"], 1.0), "rx": per["data_rx"] / max(per["raw_rx"], 1.0)}
+        else:
+            roof["traffic_error"] = (nvl0 or {}).get("error") or (nvl1 or {}).get("error")
     # DRAM / NVLink bytes of the same kernel on the same workload from this round's ncu capture (bench.py
     # cannot run under ncu itself: a number printed under a profiler is never a bench value)
     tsrc = os.path.join(ROOT, "profiles", "r02_n%d_%s_ncu_full.txt" % (world, variant.replace("+", "_")))

@@ -215,6 +215,10 @@ MXKV_DLL int MXKVB200GetLaunchCount(int64_t* out);
  * staged (kv_dense_bulk_kernel, cp.async.bulk + mbarrier), 2 = NVSwitch multicast (kv_dense_nvls_kernel).
  * Test / bench instrumentation: proves which kernel a parity check has just exercised. */
 MXKV_DLL int MXKVB200GetVariantLaunchCount(int variant, int64_t* out);
+/* push / pushpull calls of this store served from a cached launch plan (a call whose keys and arrays repeat
+ * while nothing else touched its keys replays its recorded work lists; MXKV_B200_PLAN=0 turns the cache off,
+ * =2 builds every call both ways and aborts on a difference).  Instrumentation. */
+MXKV_DLL int MXKVB200GetPlanHits(KVStoreHandle handle, int64_t* out);
 MXKV_DLL int MXKVB200SetTwoShotBytes(int64_t bytes);
 /* Kernel scheduling knobs (also MXKV_B200_CHUNK / _THREADS / _MAX_BLOCKS / _BULK): elements per
  * scheduling chunk, block size (128/256/512), cap on the grid (0 = resident capacity), and the

@@ -299,9 +299,19 @@ int MXKVStoreInitEx(KVStoreHandle handle, uint32_t num, const char** keys, NDArr
   API_END();
 }
 
+namespace {
+// the fast path needs NDArray pointers; NDHandle IS an NDArray (ndarray.h)
+inline NDArray* const* AsArrays(NDArrayHandle* h) { return reinterpret_cast<NDArray* const*>(h); }
+struct PendingGuard { KVStore* kv; ~PendingGuard() { kv->ClearRawPending(); } };
+}  // namespace
+
 int MXKVStorePush(KVStoreHandle handle, uint32_t num, const int* keys, NDArrayHandle* vals, int priority) {
   API_BEGIN();
-  KV(handle)->Push(IKeys(keys, num), Vals(vals, num), priority);
+  KVStore* kv = KV(handle);
+  // a repeated call replays its cached launch plan straight from the raw arguments (kvstore.h: CallPlan)
+  if (kv->TryReplayRaw(0, num, keys, AsArrays(vals), 0, nullptr, nullptr)) return 0;
+  PendingGuard guard{kv};
+  kv->Push(IKeys(keys, num), Vals(vals, num), priority);
   API_END();
 }
 
@@ -368,7 +378,10 @@ int MXKVStoreBroadcastEx(KVStoreHandle handle, mx_uint vnum, const char** vkeys,
 int MXKVStorePushPull(KVStoreHandle handle, mx_uint vnum, const int* vkeys, mx_uint onum, const int* okeys,
                       NDArrayHandle* vals, NDArrayHandle* outs, int priority) {
   API_BEGIN();
-  KV(handle)->PushPull(IKeys(vkeys, vnum), IKeys(okeys, onum), Vals(vals, vnum), Outs(outs, onum), priority);
+  KVStore* kv = KV(handle);
+  if (kv->TryReplayRaw(1, vnum, vkeys, AsArrays(vals), onum, okeys, AsArrays(outs))) return 0;
+  PendingGuard guard{kv};
+  kv->PushPull(IKeys(vkeys, vnum), IKeys(okeys, onum), Vals(vals, vnum), Outs(outs, onum), priority);
   API_END();
 }
 
@@ -581,6 +594,7 @@ int MXKVB200NDArrayFromPeers(void* const* peer_ptrs, int world, void* mc_ptr, co
 int MXKVB200SetNvls(int mode) {
   API_BEGIN();
   Runtime::Get()->nvls_mode = mode;
+  Runtime::Get()->tuning_epoch++;
   API_END();
 }
 
@@ -588,6 +602,7 @@ int MXKVB200SetNvlsTuning(int unroll, int pipe, int grid, int threads) {
   API_BEGIN();
   Runtime* rt = Runtime::Get();
   rt->WaitAll();
+  rt->tuning_epoch++;
   if (unroll > 0) rt->nvls_unroll = unroll;
   if (pipe >= 0) rt->nvls_pipe = pipe != 0;
   if (grid >= 0) rt->nvls_grid = grid;
@@ -625,6 +640,12 @@ int MXKVB200GetLaunchCount(int64_t* out) {
   API_END();
 }
 
+int MXKVB200GetPlanHits(KVStoreHandle handle, int64_t* out) {
+  API_BEGIN();
+  *out = static_cast<KVStore*>(handle)->plan_hits();
+  API_END();
+}
+
 int MXKVB200GetVariantLaunchCount(int variant, int64_t* out) {
   API_BEGIN();
   MXKV_CHECK(variant >= 0 && variant < 3) << "variant: 0 per-thread, 1 staged (bulk), 2 multicast (NVLS)";
@@ -641,6 +662,7 @@ int MXKVB200SetTuning(int64_t chunk_elems, int threads, int max_blocks, int bulk
 int MXKVB200SetTwoShotBytes(int64_t bytes) {
   API_BEGIN();
   Runtime::Get()->twoshot_bytes = bytes;
+  Runtime::Get()->tuning_epoch++;
   API_END();
 }
 
@@ -673,6 +695,7 @@ int MXKVB200SetHierarchy(int node_rank, int num_nodes, MXKVB200AllReduceFn allre
   MXKV_CHECK(allreduce != nullptr || num_nodes == 1) << "a multi-node hierarchy needs an all-reduce callback";
   Runtime* rt = Runtime::Get();
   MXKV_CHECK(rt->pg() != nullptr) << "MXKVB200CommInit (the node-local group) comes first";
+  rt->tuning_epoch++;
   rt->hier.node_rank = node_rank;
   rt->hier.num_nodes = num_nodes;
   rt->hier.fn = reinterpret_cast<AllReduceFn>(allreduce);

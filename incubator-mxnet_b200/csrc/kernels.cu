@@ -689,6 +689,23 @@ int DenseMaxGrid(int device, int threads) {
   return g > kMaxBlocks ? kMaxBlocks : g;
 }
 
+// Function attributes are per device: opt in to large dynamic shared memory on the GPU a launch goes to -- and
+// only there (a process that owns one GPU must not create contexts on the others).  The device must be current.
+static bool EnsureBulkAttr(int device, int opt, int multi_precision) {
+  static bool attr_done[64][16] = {{false}};
+  if (device < 0 || device >= 64) return false;
+  const int slot = (opt & 7) * 2 + (multi_precision ? 1 : 0);
+  if (attr_done[device][slot]) return true;
+  BulkKernelFn fn = pick_bulk(opt, multi_precision);
+  if (fn == nullptr) return false;
+  if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  attr_done[device][slot] = true;
+  return true;
+}
+
 static int g_smem_budget = 0;   // MXKV_B200_BULK_SMEM_KB per block (default 100: two blocks per SM)
 
 int BulkPlan(int device, int opt, int multi_precision, int arrays, int* tile_elems, int* stages) {
@@ -722,22 +739,10 @@ int BulkPlan(int device, int opt, int multi_precision, int arrays, int* tile_ele
   if (st < 2) return 0;
   if (st > kBulkMaxStages) st = kBulkMaxStages;
   const int smem = st * arrays * tile * 4;
-  // function attributes are per device: opt in to large dynamic shared memory on THIS launch's GPU only (a
-  // process that owns one GPU must not create contexts on the others)
-  static bool attr_done[64][16] = {{false}};
-  const int slot = (opt & 7) * 2 + (multi_precision ? 1 : 0);
   int prev = -1;
   cudaGetDevice(&prev);
   if (prev != device) cudaSetDevice(device);
-  bool ok = true;
-  if (device >= 0 && device < 64 && !attr_done[device][slot]) {
-    if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) {
-      cudaGetLastError();
-      ok = false;
-    } else {
-      attr_done[device][slot] = true;
-    }
-  }
+  bool ok = EnsureBulkAttr(device, opt, multi_precision);
   int occ = 0;
   if (ok && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kBulkThreads, smem) != cudaSuccess || occ < 1)) {
     cudaGetLastError();
@@ -765,6 +770,9 @@ int LaunchDense(const DenseLaunch& L, cudaStream_t stream) {
   if (L.bulk) {
     BulkKernelFn bf = pick_bulk(L.opt, L.multi_precision);
     if (bf == nullptr || L.dtype != kFloat32) return static_cast<int>(cudaErrorInvalidValue);
+    int cur = -1;                      // single process, several GPUs: the plan was made on the first participant
+    cudaGetDevice(&cur);
+    if (!EnsureBulkAttr(cur, L.opt, L.multi_precision)) return static_cast<int>(cudaErrorInvalidValue);
     int grid = L.grid < 1 ? 1 : (L.grid > kMaxBlocks ? kMaxBlocks : L.grid);
     const size_t smem = static_cast<size_t>(L.bulk_stages) * L.bulk_arrays * L.chunk_elems * 4;
     bf<<<grid, kBulkThreads, smem, stream>>>(L);

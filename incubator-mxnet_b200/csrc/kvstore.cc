@@ -41,6 +41,7 @@ KVStore::KVStore(const std::string& type) : type_(Lower(type)) {   // kvstore.cc
   solo_ = t.find("updater") != std::string::npos;
   device_mode_ = solo_ || dist || t.find("device") != std::string::npos || t.find("nccl") != std::string::npos;
   order_ = device_mode_ ? ORDER_DEVICE : ORDER_COMMCPU;
+  plan_mode_ = static_cast<int>(EnvInt("MXKV_B200_PLAN", 1));
 }
 
 ProcessGroup* KVStore::PG() const { return solo_ ? nullptr : Runtime::Get()->pg(); }
@@ -136,6 +137,14 @@ int KVStore::ResolveKey(bool str_key, int ikey, const std::string& skey) {
 KeyState& KVStore::GetKey(int key) {
   auto it = keys_.find(key);
   MXKV_CHECK(it != keys_.end()) << "key " << key << " has not been inited";
+  it->second.epoch++;          // whoever asks for a key may change it: cached launch plans of the key expire
+  return it->second;
+}
+
+// for callers that only read the key's type / bump its update count (nothing a launch plan depends on)
+KeyState& KVStore::PeekKey(int key) {
+  auto it = keys_.find(key);
+  MXKV_CHECK(it != keys_.end()) << "key " << key << " has not been inited";
   return it->second;
 }
 
@@ -204,6 +213,7 @@ void KVStore::PullRowSparse(const std::vector<std::string>& str_keys,
 void KVStore::SetUpdater(UpdaterFn fn, StrUpdaterFn sfn, void* handle) {
   LOCK();
   updater_ = fn; str_updater_ = sfn; updater_handle_ = handle;
+  cfg_epoch_++;
 }
 
 void KVStore::SetGradientCompression(const std::vector<std::pair<std::string, std::string>>& kwargs) {
@@ -223,6 +233,7 @@ void KVStore::SetGradientCompression(const std::vector<std::pair<std::string, st
   gc_threshold_ = threshold;
   // only the device comm compresses (CommDevice::ReduceCompressed, comm.h:556-605); CommCPU sums what it is given
   gc_bits_ = !device_mode_ ? 0 : (type == "2bit" ? 2 : 1);
+  cfg_epoch_++;
 }
 
 // ---------------------------------------------------------------------------
@@ -276,6 +287,7 @@ void KVStore::SetOptimizer(const std::string& name, const std::vector<std::pair<
   // the reference's set_optimizer REPLACES the updater (python/mxnet/kvstore/kvstore.py:559-606): a callback
   // installed for an earlier optimizer must not keep running in front of the fused kernel
   updater_ = nullptr; str_updater_ = nullptr; updater_handle_ = nullptr;
+  cfg_epoch_++;
   if (reset_states) {
     // a NEW optimizer starts from fresh state, like the new Updater the reference creates in set_optimizer
     // (kvstore.py:559-606); re-sending the hyper-parameters of the current one (rescale_grad per batch size,
@@ -599,9 +611,9 @@ void KVStore::PushImpl(const std::vector<int>& keys, const std::vector<NDArray>&
   });
   std::vector<Group> dense;
   for (size_t i = 0; i < uniq.size(); ++i) {
-    KeyState& ks = GetKey(uniq[i]);
+    KeyState& ks = PeekKey(uniq[i]);
     if (grouped[i][0].stype() == kRowSparseStorage || ks.stype == kRowSparseStorage) {
-      PushRowSparse(ks, grouped[i]);
+      PushRowSparse(GetKey(uniq[i]), grouped[i]);
       continue;
     }
     if (AdamWSkips()) { ks.count += 1; continue; }
@@ -610,7 +622,9 @@ void KVStore::PushImpl(const std::vector<int>& keys, const std::vector<NDArray>&
     g.vals = grouped[i];
     dense.push_back(g);
   }
+  raw_single_ = dense.size() == uniq.size();        // the whole call as ONE reduce: a launch plan may be recorded
   if (!dense.empty()) ReduceUpdate(dense, false);
+  raw_single_ = false;
 }
 
 void KVStore::PullImpl(const std::vector<int>& keys, const std::vector<NDArray*>& outs, int priority,
@@ -680,7 +694,7 @@ void KVStore::PushPullImpl(const std::vector<int>& vkeys, const std::vector<int>
   });
   bool fusable = dense && vu == ou && updater_ == nullptr;
   if (fusable) {
-    for (int k : vu) if (GetKey(k).stype != kDefaultStorage) fusable = false;
+    for (int k : vu) if (PeekKey(k).stype != kDefaultStorage) fusable = false;
   }
   if (!fusable) {
     PushImpl(vkeys, vals, priority);
@@ -688,7 +702,7 @@ void KVStore::PushPullImpl(const std::vector<int>& vkeys, const std::vector<int>
     return;
   }
   if (AdamWSkips()) {
-    for (int key : vu) GetKey(key).count += 1;
+    for (int key : vu) PeekKey(key).count += 1;
     PullImpl(okeys, outs, priority, true);
     return;
   }
@@ -698,7 +712,9 @@ void KVStore::PushPullImpl(const std::vector<int>& vkeys, const std::vector<int>
     groups[i].vals = vg[i];
     groups[i].outs = og[i];
   }
+  raw_single_ = true;
   ReduceUpdate(groups, true);
+  raw_single_ = false;
 }
 
 // ---------------------------------------------------------------------------
@@ -1221,6 +1237,101 @@ void KVStore::HierReduceUpdate(std::vector<Group>& groups, bool write_outs) {
 // Where a key of a call is reduced: collectively on the GPUs its values live on (distinct,
 // P2P-reachable GPUs, single process), by every rank (one process per GPU), or on one root GPU that reads
 // and writes wherever the arrays are.
+// ---------------------------------------------------------------------------
+// cached launch plans (kvstore.h: CallPlan)
+// ---------------------------------------------------------------------------
+static uint64_t HashSig(const std::vector<uint64_t>& v) {
+  uint64_t h = 1469598103934665603ull;
+  for (uint64_t x : v) { h ^= x; h *= 1099511628211ull; }
+  return h;
+}
+
+// The call's raw arguments as a signature: keys in call order, array identities (address, bytes, device, dtype,
+// peer-mapped / multicast).  Not eligible (returns false, nothing pending): host-resident or sparse arrays,
+// string keys, stores with an updater callback / compression / a node hierarchy / a layer-wise optimizer.
+bool KVStore::TryReplayRaw(int kind, uint32_t vnum, const int* vkeys, NDArray* const* vals, uint32_t onum,
+                           const int* okeys, NDArray* const* outs) {
+  std::lock_guard<std::recursive_mutex> rt_lk(Runtime::Get()->mu());
+  std::lock_guard<std::recursive_mutex> lk(mu_);
+  raw_pending_ = false;
+  raw_single_ = false;
+  if (plan_mode_ == 0 || key_type_ == kStringKey || hier_ || updater_ != nullptr || gc_bits_ != 0 ||
+      (opt_.enabled && (IsNormOpt(opt_.kind) || AdamWSkips())))
+    return false;
+  std::vector<uint64_t>& sig = raw_sig_;
+  sig.clear();
+  sig.reserve(4 + 4 * (static_cast<size_t>(vnum) + onum));
+  sig.push_back(static_cast<uint64_t>(kind));
+  sig.push_back(vnum);
+  sig.push_back(onum);
+  auto add = [&sig](int key, const NDArray* a) -> bool {
+    if (a == nullptr) return false;
+    const Context c = a->ctx();
+    if (!c.is_gpu() || a->stype() != kDefaultStorage) return false;
+    sig.push_back(static_cast<uint64_t>(static_cast<uint32_t>(key)));
+    sig.push_back(reinterpret_cast<uintptr_t>(a->data()));
+    sig.push_back(static_cast<uint64_t>(a->nbytes()));
+    sig.push_back(static_cast<uint64_t>(c.dev_id) | (a->symmetric() ? 1ull << 32 : 0) |
+                  (a->mc_data() != nullptr ? 1ull << 33 : 0) | (static_cast<uint64_t>(a->dtype()) << 40));
+    return true;
+  };
+  for (uint32_t i = 0; i < vnum; ++i) if (!add(vkeys[i], vals[i])) return false;
+  for (uint32_t i = 0; i < onum; ++i) if (!add(okeys[i], outs[i])) return false;
+  raw_hash_ = HashSig(sig);
+  raw_pending_ = true;
+  auto it = plans_.find(raw_hash_);
+  if (plan_mode_ == 1 && it != plans_.end() && it->second.recorded && it->second.sig == sig &&
+      PlanEpochsMatch(it->second)) {
+    if (key_type_ == kUndefinedKey) key_type_ = kIntKey;
+    PlanReplay(it->second);
+    raw_pending_ = false;
+    return true;
+  }
+  return false;
+}
+
+bool KVStore::PlanEpochsMatch(const CallPlan& p) const {
+  if (p.cfg_epoch != cfg_epoch_ || p.tuning_epoch != Runtime::Get()->tuning_epoch) return false;
+  for (size_t i = 0; i < p.keys.size(); ++i) {
+    auto it = keys_.find(p.keys[i]);
+    if (it == keys_.end() || it->second.epoch != p.epochs[i]) return false;
+  }
+  return true;
+}
+
+// the only per-call data of a repeated call: update counts and the per-key scalars derived from them
+void KVStore::PlanPatch(CallPlan& p, bool commit_counts) {
+  if (!p.fused) return;
+  std::vector<std::array<float, 3>> hyper(p.keys.size());
+  for (size_t i = 0; i < p.keys.size(); ++i) {
+    KeyState& ks = keys_.find(p.keys[i])->second;    // (not GetKey: a replay does not expire its own plan)
+    ks.count += 1;
+    hyper[i] = {KeyLR(ks), KeyWD(ks), KeyEta(ks)};
+    if (!commit_counts) ks.count -= 1;
+  }
+  for (auto& l : p.launches)
+    for (size_t q = 0; q < l.per_part.size(); ++q)
+      for (size_t e = 0; e < l.per_part[q].size(); ++e) {
+        TensorWork& tw = l.per_part[q][e];
+        const auto& h = hyper[l.key_idx[q][e]];
+        tw.lr = h[0]; tw.wd = h[1]; tw.eta = h[2];
+      }
+}
+
+void KVStore::PlanReplay(CallPlan& p) {
+  Runtime* rt = Runtime::Get();
+  for (int dev : p.touched) rt->AcquireUser(dev);
+  PlanPatch(p, true);
+  for (auto& w : p.pre_waits) rt->StreamWait(w.first, w.second);
+  for (auto& c : p.pre_copies) CopyFromTo(c.first, c.second);
+  for (auto& l : p.launches) LaunchWorks(l.ck, l.per_part, l.busiest, p.opt_kind, p.part_dev);
+  if (!p.collective)
+    for (int dev : p.touched) if (dev != p.root_dev) rt->StreamWait(dev, p.root_dev);
+  for (auto& c : p.post_copies) CopyFromTo(c.first, c.second);
+  for (int dev : p.touched) rt->ReleaseToUser(dev);
+  plan_hits_++;
+}
+
 void KVStore::PlaceKey(const Group& g, KeyState& ks, std::vector<int>* devs_out, std::vector<int>* key_part_out,
                        bool* key_collective_out) {
   Runtime* rt = Runtime::Get();
@@ -1273,6 +1384,28 @@ void KVStore::ReduceUpdate(std::vector<Group>& groups, bool write_outs) {
   if (hier_ && hier_phase_ == 0) { HierReduceUpdate(groups, write_outs); return; }
   // (multi-node with compression: phase 1 is the compressed reduce, phase 2 the ordinary update from the slices)
   if (gc_bits_ != 0 && hier_phase_ != 2) { ReduceUpdateCompressed(groups, write_outs); return; }
+
+  // ---- a repeated call: replay its recorded work lists (only counts and lr / wd / eta are new) ------------
+  CallPlan rec;                         // what this call would record
+  bool rec_on = false, rec_repeat = false;
+  uint64_t rec_hash = 0;
+  std::unique_ptr<CallPlan> verify;     // MXKV_B200_PLAN=2: the plan as a replay would have patched it
+  if (plan_mode_ != 0 && raw_pending_ && raw_single_ && hier_phase_ == 0 && !hier_ && updater_ == nullptr &&
+      !(opt_.enabled && IsNormOpt(opt_.kind))) {
+    raw_pending_ = false;               // (consumed: a recursive or later call must not record under it)
+    rec_on = true;
+    rec.sig = raw_sig_;
+    rec_hash = raw_hash_;
+    auto it = plans_.find(rec_hash);
+    if (it != plans_.end() && it->second.sig == rec.sig && PlanEpochsMatch(it->second)) {
+      if (it->second.recorded) {        // (MXKV_B200_PLAN=1 replays in TryReplayRaw and never gets here)
+        // verify mode: run the full path below and compare what it builds
+        verify.reset(new CallPlan(it->second));
+        PlanPatch(*verify, false);
+      }
+      rec_repeat = true;                // nothing touched these keys since the last identical call: steady state
+    }
+  }
   if (hier_phase_ == 0 && HostPipelined(groups, write_outs)) return;
   Runtime* rt = Runtime::Get();
   ProcessGroup* pg = PG();
@@ -1331,6 +1464,11 @@ void KVStore::ReduceUpdate(std::vector<Group>& groups, bool write_outs) {
   std::set<int> touched;
   std::vector<KeyState*> callback_keys;
   auto touch = [&](int dev) { if (dev >= 0 && touched.insert(dev).second) rt->AcquireUser(dev); };
+  bool rec_bad = false;                 // this call did something a replay could not (temporaries, layout changes)
+  auto stream_wait = [&](int waiter, int signaler) {
+    rt->StreamWait(waiter, signaler);
+    if (waiter != signaler) rec.pre_waits.emplace_back(waiter, signaler);
+  };
 
   int n_part = 0;
   bool collective = false;
@@ -1388,6 +1526,7 @@ void KVStore::ReduceUpdate(std::vector<Group>& groups, bool write_outs) {
     if (hier_phase_ != 1 && ks.local_world > 0 &&
         (callback || !(two_shot && ks.local_world == n_part && ks.shard_devs == part_dev))) {
       GatherLocal(ks);
+      rec_bad = true;
       for (int p = my_first; p <= my_last; ++p) rep[p] = &EnsureReplica(ks, part_dev[p]);
       for (int p = my_first; p <= my_last; ++p) rep[p] = FindReplica(ks, part_dev[p]);
     }
@@ -1397,7 +1536,7 @@ void KVStore::ReduceUpdate(std::vector<Group>& groups, bool write_outs) {
       // now pushed from one GPU only)
       const int want = (collective && two_shot) ? n_part : 0;
       const bool same = ks.state_world == want && (want == 0 || ks.state_devs == part_dev);
-      if (ks.count > 0 && !same) GatherState(ks);
+      if (ks.count > 0 && !same) { GatherState(ks); rec_bad = true; }
       ks.state_world = want;
       if (want > 0) ks.state_devs = part_dev; else ks.state_devs.clear();
       // a replica that sat out earlier updates (its GPU did not take part) first takes over the state of
@@ -1424,6 +1563,7 @@ void KVStore::ReduceUpdate(std::vector<Group>& groups, bool write_outs) {
         Replica& r = *rep[pg->rank()];
         if (r.stage.is_none()) r.stage = NDArray::Empty(ks.shape, Context{kGPU, pg->dev()}, ks.dtype, true);
         CopyFromTo(v, r.stage);                       // D2D or H2D
+        rec.pre_copies.emplace_back(v, r.stage);
         sym_src = r.stage;
       }
       if (collective) {
@@ -1433,7 +1573,7 @@ void KVStore::ReduceUpdate(std::vector<Group>& groups, bool write_outs) {
           void* t = nullptr;
           DeviceGuard dg(pg->dev());
           CUDA_CALL(cudaMallocAsync(&t, v.nbytes() ? v.nbytes() : 16, rt->Dev(pg->dev()).stream));
-          temps.push_back(t); temp_dev.push_back(pg->dev());
+          temps.push_back(t); temp_dev.push_back(pg->dev()); rec_bad = true;
           CopyBytes(v.data(), v.ctx(), t, Context{kGPU, pg->dev()}, v.nbytes());
           srcptr[pg->rank()][0] = t;
         } else {
@@ -1451,7 +1591,7 @@ void KVStore::ReduceUpdate(std::vector<Group>& groups, bool write_outs) {
         if (direct) {
           if (devs[k] != root_dev) {              // foreign GPU read by the root kernel
             touch(devs[k]);
-            rt->StreamWait(root_dev, devs[k]);
+            stream_wait(root_dev, devs[k]);
           }
           srcptr[0][k] = v.data();
         } else {                                   // host value, or no P2P: stage on the root
@@ -1461,7 +1601,7 @@ void KVStore::ReduceUpdate(std::vector<Group>& groups, bool write_outs) {
             DeviceGuard dg(root_dev);
             CUDA_CALL(cudaMallocAsync(&t, v.nbytes() ? v.nbytes() : 16, rt->Dev(root_dev).stream));
           }
-          temps.push_back(t); temp_dev.push_back(root_dev);
+          temps.push_back(t); temp_dev.push_back(root_dev); rec_bad = true;
           CopyBytes(v.data(), v.ctx(), t, Context{kGPU, root_dev}, v.nbytes());
           srcptr[0][k] = t;
         }
@@ -1555,7 +1695,7 @@ void KVStore::ReduceUpdate(std::vector<Group>& groups, bool write_outs) {
           bool is_part = false;
           for (int p = 0; p < n_part; ++p) if (part_dev[p] == r.dev) is_part = true;
           if (is_part || (reachable && !collective)) {
-            if (!is_part) { touch(r.dev); rt->StreamWait(root_dev, r.dev); }
+            if (!is_part) { touch(r.dev); stream_wait(root_dev, r.dev); }
             add_dest_sp(r.local.data(), r.dev);
             dests.back().own_only = shard_local;
             r.fresh = true;
@@ -1670,6 +1810,50 @@ void KVStore::ReduceUpdate(std::vector<Group>& groups, bool write_outs) {
 
   // ---- launches: one per class per local participant --------------------------
   const int opt_kind = fused ? opt_.kind : OPT_NONE;
+  if (rec_on && !callback) {
+    rec.keys.clear();
+    for (auto& g : groups) rec.keys.push_back(g.key);
+    std::unordered_map<int, int> key_pos;
+    for (size_t i = 0; i < rec.keys.size(); ++i) key_pos[rec.keys[i]] = static_cast<int>(i);
+    for (auto& kv : classes) {
+      PlanLaunch pl{kv.first, kv.second.per_part, kv.second.busiest, {}};
+      pl.key_idx.resize(pl.per_part.size());
+      for (size_t q = 0; q < pl.per_part.size(); ++q)
+        for (auto& tw : pl.per_part[q]) pl.key_idx[q].push_back(key_pos.at(tw.reserved_));
+      rec.launches.push_back(std::move(pl));
+    }
+    rec.part_dev = part_dev;
+    rec.touched.assign(touched.begin(), touched.end());
+    for (auto& pc : post) rec.post_copies.emplace_back(pc.src, pc.dst);
+    rec.opt_kind = opt_kind; rec.fused = fused; rec.collective = collective; rec.root_dev = root_dev;
+    if (verify) {
+      // the replay of the recorded plan must be exactly what the full path has just built
+      const CallPlan& v = *verify;
+      bool same = v.launches.size() == rec.launches.size() && v.part_dev == rec.part_dev && v.opt_kind == rec.opt_kind &&
+                  v.fused == rec.fused && v.collective == rec.collective && v.root_dev == rec.root_dev &&
+                  v.pre_waits == rec.pre_waits && v.pre_copies.size() == rec.pre_copies.size() &&
+                  v.post_copies.size() == rec.post_copies.size() && !rec_bad && !temps.size();
+      std::set<int> vt(v.touched.begin(), v.touched.end());
+      same = same && vt == touched;
+      for (size_t i = 0; same && i < v.launches.size(); ++i) {
+        const PlanLaunch& a = v.launches[i];
+        const PlanLaunch& b = rec.launches[i];
+        same = !(a.ck < b.ck) && !(b.ck < a.ck) && a.busiest == b.busiest && a.per_part.size() == b.per_part.size();
+        for (size_t q = 0; same && q < a.per_part.size(); ++q)
+          same = a.per_part[q].size() == b.per_part[q].size() &&
+                 (a.per_part[q].empty() ||
+                  std::memcmp(a.per_part[q].data(), b.per_part[q].data(), a.per_part[q].size() * sizeof(TensorWork)) == 0);
+      }
+      for (size_t i = 0; same && i < v.pre_copies.size(); ++i)
+        same = v.pre_copies[i].first.data() == rec.pre_copies[i].first.data() &&
+               v.pre_copies[i].second.data() == rec.pre_copies[i].second.data();
+      for (size_t i = 0; same && i < v.post_copies.size(); ++i)
+        same = v.post_copies[i].first.data() == rec.post_copies[i].first.data() &&
+               v.post_copies[i].second.data() == rec.post_copies[i].second.data();
+      MXKV_CHECK(same) << "MXKV_B200_PLAN=2: the cached launch plan differs from the work lists of the full path";
+      plan_hits_++;
+    }
+  }
   if (IsNormOpt(opt_kind)) {
     // all classes together: the phases of every class are interleaved so that the overflow check
     // covers the whole push
@@ -1695,6 +1879,19 @@ void KVStore::ReduceUpdate(std::vector<Group>& groups, bool write_outs) {
   }
   for (auto& pc : post) CopyFromTo(pc.src, pc.dst);
   for (int dev : touched) rt->ReleaseToUser(dev);
+
+  // ---- remember this call: the second identical call in a row (nothing else touched its keys in between)
+  // leaves a plan behind, the third and later ones replay it
+  if (rec_on && !callback && !rec_bad && temps.empty()) {
+    rec.epochs.clear();
+    for (int key : rec.keys) rec.epochs.push_back(keys_.find(key)->second.epoch);
+    rec.cfg_epoch = cfg_epoch_;
+    rec.tuning_epoch = rt->tuning_epoch;
+    rec.recorded = rec_repeat;
+    if (!rec.recorded) { rec.launches.clear(); rec.pre_copies.clear(); rec.post_copies.clear(); }
+    if (plans_.size() > 256) plans_.clear();          // (a training loop has a handful of distinct calls)
+    plans_[rec_hash] = std::move(rec);
+  }
 }
 
 // One kernel launch per local participant for a list of work entries that share dtype /

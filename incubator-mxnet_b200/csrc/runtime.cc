@@ -330,6 +330,7 @@ void Runtime::WaitAll() {
 }
 
 void Runtime::SetTuning(int64_t chunk, int nthreads, int max_blocks, int bulk) {
+  tuning_epoch++;
   if (bulk >= 0) bulk_mode = bulk;
   std::lock_guard<std::recursive_mutex> lk(mu_);
   WaitAll();
@@ -360,6 +361,7 @@ void Runtime::DrainForFree() noexcept {
 }
 
 void Runtime::InitProcessGroup(int rank, int world, int dev, AllGatherFn fn, void* ctx) {
+  tuning_epoch++;
   std::lock_guard<std::recursive_mutex> lk(mu_);
   MXKV_CHECK(!pg_) << "process group already initialised";
   MXKV_CHECK(devs_.find(dev) == devs_.end())
@@ -369,6 +371,7 @@ void Runtime::InitProcessGroup(int rank, int world, int dev, AllGatherFn fn, voi
 }
 
 void Runtime::DestroyProcessGroup() {
+  tuning_epoch++;
   std::lock_guard<std::recursive_mutex> lk(mu_);
   WaitAll();
   if (pg_) {

@@ -138,6 +138,7 @@ class Runtime {
   std::recursive_mutex& mu() { return mu_; }
   bool auto_fence = true;
   int64_t launches = 0;                      // kernels launched by this library (bench "gpu_launches")
+  uint64_t tuning_epoch = 0;                 // bumped by every change of a knob that shapes launches (cached plans expire)
   // dense launches by kernel variant: 0 per-thread (kv_dense_kernel / kv_sum_typed_kernel), 1 shared-memory
   // staged (kv_dense_bulk_kernel), 2 NVSwitch multicast (kv_dense_nvls_kernel) -- lets a parity test prove
   // which kernel it has just compared with the oracle (MXKVB200GetVariantLaunchCount)

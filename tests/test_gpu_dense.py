@@ -378,3 +378,57 @@ def test_forced_variant_ragged_tiles(variant):
     tiles of 4 elements, a key smaller than one tile next to a large one"""
     _run_keyset(variant, "sgd_mom", 2, [4, 2052, 8196, 3 * 2048 + 12, (1 << 20) + 4, 12], steps=3, seed=5)
     _run_keyset(variant, "adam", 1, [2048, 2044, 4096 + 8, 100004], steps=2, seed=6)
+
+
+# ---------------------------------------------------------------------------
+# cached launch plans: the third identical pushpull in a row replays the recorded work lists
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("optkey", ["none", "sgd_mom", "adam"])
+def test_cached_launch_plan_replays_are_bit_exact(optkey):
+    optname, kw = _OPTS[optkey]
+    sizes = [8, 1000, 4096 + 4, 70001, 1 << 18]
+    rng = _rng(31)
+    keys = list(range(len(sizes)))
+    w0 = [rng.uniform(0, 1, e).astype(np.float32) for e in sizes]
+    kv = mx.kv.create("device")
+    kv.init(keys, [mx.nd.array(w, mx.gpu(0)) for w in w0])
+    okv = O.OracleKVStore("device")
+    okv.init(keys, [w.copy() for w in w0])
+    if optname:
+        kv.set_optimizer(mx.optimizer.create(optname, **kw))
+        okv.set_optimizer(O.OracleOptimizer(optname, **kw))
+    n = 2
+    gdev = [[mx.nd.empty((e,), mx.gpu(0)) for _ in range(n)] for e in sizes]
+    outs = [mx.nd.empty((e,), mx.gpu(0)) for e in sizes]
+
+    def step(check=True):
+        grads = [[rng.uniform(-1, 1, e).astype(np.float32) for _ in range(n)] for e in sizes]
+        for gd, gs in zip(gdev, grads):
+            for d, g in zip(gd, gs):
+                d[:] = g
+        kv.pushpull(keys, gdev, out=outs)
+        okv.push(keys, grads)
+        for k, e in enumerate(sizes):
+            want = np.empty(e, np.float32)
+            okv.pull(k, want)
+            assert_bits_equal(outs[k].asnumpy(), want, "%s key %d" % (optkey, k))
+
+    h0 = kv.plan_hits()
+    for _ in range(6):                  # calls 1, 2 build (2 records the plan); 3 ... 6 replay it
+        step()
+    assert kv.plan_hits() - h0 == 4, kv.plan_hits() - h0
+    # anything else that touches a key expires the plan: a pull in between, then two more calls to re-record
+    tmp = mx.nd.empty((sizes[1],), mx.gpu(0))
+    kv.pull(1, out=tmp)
+    h1 = kv.plan_hits()
+    step(); step()
+    assert kv.plan_hits() == h1
+    step()
+    assert kv.plan_hits() == h1 + 1
+    # a learning-rate change between replays takes effect (the scalars are patched at every call)
+    if optname:
+        h2 = kv.plan_hits()
+        kv._optimizer.set_learning_rate(kv._optimizer.learning_rate * 0.5)
+        okv.optimizer.lr = okv.optimizer.lr * 0.5
+        step()
+        assert kv.plan_hits() == h2 + 1

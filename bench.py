@@ -413,12 +413,20 @@ class Env(object):
         else:
             assert args.gpus == 1, "launch with torchrun for --gpus > 1"
         self.ctx = mx.gpu(self.local)
-        self.multicast = False
-        if self.world > 1 and not args.no_nvls and not self.hier:
-            try:
-                self.multicast = bool(mx.nd.has_multicast(mx.nd.empty_multicast((1024,))))
-            except Exception as e:                         # noqa: BLE001 -- torch symmetric memory unavailable
-                sys.stderr.write("multicast allocation unavailable (%r): peer-load kernels\n" % (e,))
+        # multicast-capable arrays: the engine's own arena (VMM allocations bound to a multicast object,
+        # csrc/vmm_arena.cc) when the GPUs support it, else torch's symmetric-memory allocator, else none
+        self.multicast = None
+        if self.world > 1 and not self.hier:
+            if args.no_nvls:
+                mx.kv.set_nvls(0)
+            elif mx.nd.has_multicast(mx.nd.empty_symmetric((1024,))):
+                self.multicast = "engine"
+            else:
+                try:
+                    if mx.nd.has_multicast(mx.nd.empty_multicast((1024,))):
+                        self.multicast = "torch"
+                except Exception as e:                     # noqa: BLE001 -- torch symmetric memory unavailable
+                    sys.stderr.write("multicast allocation unavailable (%r): peer-load kernels\n" % (e,))
 
     def barrier(self):
         if self.world > 1:
@@ -898,9 +906,11 @@ def main():
         exchange = "hierarchical: nvlink-p2p in nodes of %d, nccl between %d nodes" % (
             args.local_world, world // args.local_world)
     if env.multicast:
-        alloc = mx.nd.empty_multicast          # NVSwitch multicast-capable arrays
+        if env.multicast == "torch":
+            alloc = mx.nd.empty_multicast      # NVSwitch multicast-capable arrays from torch's allocator
         # the engine switches to the multimem kernel above 4 ranks (MXKVB200SetNvls)
-        exchange = "nvls-multicast" if world > 4 else "nvlink-p2p (multicast-capable arrays)"
+        exchange = ("nvls-multicast" if world > 4 else "nvlink-p2p (multicast-capable arrays)") + \
+                   " [%s-owned multicast memory]" % env.multicast
     grads = [alloc(s) for s in shapes]
     weights = [alloc(s) for s in shapes]
     for g, a in zip(grads, rank_grads(rank, shapes)):

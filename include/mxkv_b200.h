@@ -249,6 +249,11 @@ MXKV_DLL int MXKVB200SetHierarchy(int node_rank, int num_nodes, MXKVB200AllReduc
  * peer-mapped arena, so push/pushpull read and write it over NVLink without staging. */
 MXKV_DLL int MXKVB200NDArrayCreateSymmetric(const int64_t* shape, int ndim, int dtype, NDArrayHandle* out);
 
+/* 1 if the array has an NVSwitch multicast alias (arrays of MXKVB200NDArrayCreateSymmetric on a machine whose GPUs
+ * support multicast: the arena is then built from CUDA VMM allocations bound to a multicast object, vmm_arena.cc;
+ * arrays wrapped with a multicast pointer by MXKVB200NDArrayFromPeers), i.e. the NVLS kernel can serve it. */
+MXKV_DLL int MXKVB200NDArrayHasMulticast(NDArrayHandle handle, int* out);
+
 /* Wrap peer-mapped memory owned by the embedding framework (one process per GPU): peer_ptrs[r] is
  * the address of rank r's copy as mapped in THIS process, mc_ptr the NVSwitch multicast alias of all
  * copies (NULL when none).  With a multicast alias the exchange uses the NVLS kernel

@@ -591,6 +591,12 @@ int MXKVB200NDArrayFromPeers(void* const* peer_ptrs, int world, void* mc_ptr, co
   API_END();
 }
 
+int MXKVB200NDArrayHasMulticast(NDArrayHandle handle, int* out) {
+  API_BEGIN();
+  *out = ND(handle)->mc_data() != nullptr ? 1 : 0;
+  API_END();
+}
+
 int MXKVB200SetNvls(int mode) {
   API_BEGIN();
   Runtime::Get()->nvls_mode = mode;

@@ -44,6 +44,7 @@ static std::shared_ptr<Chunk> AllocChunk(size_t bytes, Context ctx, bool symmetr
       MXKV_CHECK(rt->pg()->dev() == ctx.dev_id) << "symmetric arrays live on the process group's GPU";
       c->sym = rt->pg()->SymAlloc(alloc);
       c->ptr = c->sym.ptr[rt->pg()->rank()];
+      c->mc_ptr = c->sym.mc;                 // engine-owned multicast alias (null on the cudaIpc fallback)
       c->kind = Chunk::kSymmetric;
     } else {
       DeviceGuard g(ctx.dev_id);

@@ -87,6 +87,7 @@ ProcessGroup::ProcessGroup(int rank, int world, int dev, AllGatherFn fn, void* c
 
 ProcessGroup::~ProcessGroup() {
   for (auto& s : segs_) {
+    if (s.vmm) { FreeSegmentVmm(s); continue; }
     for (int r = 0; r < world_; ++r) {
       if (s.base[r] == nullptr) continue;
       if (r == rank_) cudaFree(s.base[r]);
@@ -113,6 +114,15 @@ void ProcessGroup::NewSegment(size_t min_bytes) {
   if (bytes < min_bytes) bytes = (min_bytes + (size_t(64) << 20) - 1) & ~((size_t(64) << 20) - 1);
   Segment s;
   std::memset(&s, 0, sizeof(s));
+  if (world_ > 1 && vmm_mode_ != 0) {
+    // engine-owned multicast memory (vmm_arena.cc); the first segment decides for the life of the group
+    const bool want = vmm_mode_ == 1 || EnvInt("MXKV_B200_ARENA_VMM", 1) != 0;
+    const bool got = want && NewSegmentVmm(bytes, &s);
+    MXKV_CHECK(got || vmm_mode_ != 1) << "could not extend the multicast arena by " << bytes << " bytes";
+    vmm_mode_ = got ? 1 : 0;
+    if (got) { segs_.push_back(s); return; }
+    std::memset(&s, 0, sizeof(s));
+  }
   s.bytes = bytes; s.used = 0;
   char* mine = nullptr;
   CUDA_CALL(cudaMalloc(reinterpret_cast<void**>(&mine), bytes));
@@ -155,6 +165,7 @@ SymPtr ProcessGroup::SymAlloc(size_t bytes) {
   }
   SymPtr p;
   for (int r = 0; r < world_; ++r) p.ptr[r] = s.base[r] + off;
+  p.mc = s.mc ? s.mc + off : nullptr;
   p.valid = true;
   return p;
 }

@@ -84,6 +84,7 @@ struct Hierarchy {
 
 struct SymPtr {                 // one symmetric allocation as seen from this process
   void* ptr[kMaxRanks] = {nullptr};
+  void* mc = nullptr;           // NVSwitch multicast alias of all copies (engine-owned VMM arena, vmm_arena.cc)
   bool valid = false;
 };
 
@@ -102,7 +103,14 @@ class ProcessGroup {
   size_t arena_used() const { return used_total_; }
  private:
   void NewSegment(size_t min_bytes);
-  struct Segment { char* base[kMaxRanks]; size_t bytes; size_t used; };
+  struct Segment { char* base[kMaxRanks]; size_t bytes; size_t used; char* mc; bool vmm; };
+  // vmm_arena.cc: cuMemCreate + POSIX-fd exchange + cuMulticast*; collective, all ranks succeed or all fail
+  bool NewSegmentVmm(size_t min_bytes, Segment* out);
+  void FreeSegmentVmm(Segment& s);
+  int vmm_mode_ = -1;           // -1 not decided yet, 0 cudaMalloc + cudaIpc, 1 VMM + multicast
+ public:
+  bool has_multicast() const { return vmm_mode_ == 1; }
+ private:
   int rank_, world_, dev_;
   AllGatherFn fn_;
   void* ctx_;

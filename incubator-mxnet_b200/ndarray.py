@@ -437,8 +437,10 @@ def empty_multicast(shape, dtype=np.float32, group=None):
 
 
 def has_multicast(nd_array):
-    keep = nd_array._keep
-    return bool(keep) and isinstance(keep, tuple) and bool(getattr(keep[1], "multicast_ptr", 0))
+    """True if the array has an NVSwitch multicast alias (engine-owned arena memory, or memory wrapped with one)."""
+    out = ctypes.c_int(0)
+    check_call(_LIB.MXKVB200NDArrayHasMulticast(nd_array.handle, ctypes.byref(out)))
+    return bool(out.value)
 
 
 def multi_sum_sq(*arrays, **kwargs):

@@ -162,6 +162,13 @@ API cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr attr, int) {
 API cudaError_t cudaDeviceGetDefaultMemPool(cudaMemPool_t* pool, int) { *pool = nullptr; return cudaSuccess; }
 API cudaError_t cudaMemPoolSetAttribute(cudaMemPool_t, cudaMemPoolAttr, void*) { return cudaSuccess; }
 API cudaError_t cudaFuncSetAttribute(const void*, cudaFuncAttribute, int) { return cudaSuccess; }
+// no driver behind the simulated runtime: the engine-owned multicast arena (csrc/vmm_arena.cc) falls back to the IPC one
+API cudaError_t cudaGetDriverEntryPoint(const char*, void** fn, unsigned long long, cudaDriverEntryPointQueryResult* status) {
+  if (fn) *fn = nullptr;
+  if (status) *status = cudaDriverEntryPointSymbolNotFound;
+  return cudaErrorNotSupported;
+}
+
 API cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessorWithFlags(int* n, const void*, int, size_t, unsigned) {
   *n = 2;
   return cudaSuccess;

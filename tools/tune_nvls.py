@@ -47,11 +47,14 @@ def main():
     steps = int(os.environ.get("TUNE_STEPS", 30))
     base = [np.random.default_rng(7 + k).uniform(-1, 1, s).astype(np.float32) for k, s in enumerate(shapes)]
     have_mc = False
+    engine_mc = mx.nd.has_multicast(mx.nd.empty_symmetric((1024,)))      # engine-owned multicast arena
     try:
-        have_mc = mx.nd.has_multicast(mx.nd.empty_multicast((1024,)))
+        have_mc = engine_mc or mx.nd.has_multicast(mx.nd.empty_multicast((1024,)))
     except Exception as e:      # noqa: BLE001
         if rank == 0:
             print("multicast unavailable:", repr(e), flush=True)
+    if rank == 0:
+        print("multicast memory:", "engine-owned (VMM arena)" if engine_mc else ("torch" if have_mc else "none"), flush=True)
 
     def say(tag, ms):
         if rank == 0:
@@ -72,7 +75,7 @@ def main():
 
     for optname in os.environ.get("TUNE_OPTS", "none,sgd").split(","):
         for alloc_name in (("multicast", "symmetric") if have_mc else ("symmetric",)):
-            alloc = mx.nd.empty_multicast if alloc_name == "multicast" else mx.nd.empty_symmetric
+            alloc = mx.nd.empty_multicast if (alloc_name == "multicast" and not engine_mc) else mx.nd.empty_symmetric
             grads = [alloc(s) for s in shapes]
             weights = [alloc(s) for s in shapes]
             for g, b in zip(grads, base):

@@ -120,7 +120,9 @@ __device__ __forceinline__ void grid_barrier(const SyncArgs& s, bool cross) {
       st_flag_release(g + kSigGridGen, gen + 1);
     } else {
       const long long t0 = clock64();
-      while (ld_flag_acquire(g + kSigGridGen) == gen) spin_check(t0, s.timeout);
+      // (relaxed polling -- hundreds of blocks spin here -- and one fence once the generation has moved)
+      while (ld_flag_volatile(g + kSigGridGen) == gen) spin_check(t0, s.timeout);
+      __threadfence_system();
     }
   }
   __syncthreads();

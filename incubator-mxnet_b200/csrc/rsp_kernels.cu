@@ -539,7 +539,8 @@ int LaunchRspPushFused(int device, const RspSources& S, const RspRowArgs& A, con
   if (c < 1) return static_cast<int>(cudaErrorLaunchOutOfResources);
   int64_t want = (est_rows + 7) / 8;
   if (St.publish) want = std::max<int64_t>(want, 148);      // the staging copy wants the whole machine
-  const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(c, want)));
+  // two blocks per SM are plenty for a gather, and every block more makes the in-kernel barriers dearer
+  const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(c, 296), want)));
   fn<<<grid, 256, 0, stream>>>(S, A, St, sync);
   return static_cast<int>(cudaGetLastError());
 }

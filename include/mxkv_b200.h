@@ -219,6 +219,16 @@ MXKV_DLL int MXKVB200GetVariantLaunchCount(int variant, int64_t* out);
  * while nothing else touched its keys replays its recorded work lists; MXKV_B200_PLAN=0 turns the cache off,
  * =2 builds every call both ways and aborts on a difference).  Instrumentation. */
 MXKV_DLL int MXKVB200GetPlanHits(KVStoreHandle handle, int64_t* out);
+/* Deferred issue -- what `priority` (include/mxnet/c_api.h:2592-2760) means on this engine.  The reference's
+ * dependency engine runs the ops that are ready in priority order (src/engine/threaded_engine_perdevice.cc:97-279);
+ * an in-order CUDA stream has no queue to reorder, so the store keeps one: with on = 1, MXKVStorePush /
+ * MXKVStorePushPull calls with dense GPU values and integer keys are recorded instead of launched, and
+ * MXKVB200Flush -- or any call that reads or changes the store, or waits for / copies an array -- issues them
+ * highest priority first (never ahead of an earlier call on the same key) with neighbouring calls on disjoint keys
+ * merged into one launch.  MXKVB200GetDeferredBatches: launches (sequences) issued that way so far. */
+MXKV_DLL int MXKVB200SetDeferred(KVStoreHandle handle, int on);
+MXKV_DLL int MXKVB200Flush(KVStoreHandle handle);
+MXKV_DLL int MXKVB200GetDeferredBatches(KVStoreHandle handle, int64_t* out);
 MXKV_DLL int MXKVB200SetTwoShotBytes(int64_t bytes);
 /* Kernel scheduling knobs (also MXKV_B200_CHUNK / _THREADS / _MAX_BLOCKS / _BULK): elements per
  * scheduling chunk, block size (128/256/512), cap on the grid (0 = resident capacity), and the

@@ -112,12 +112,14 @@ int MXNDArrayFree(NDArrayHandle handle) {
 
 int MXNDArraySyncCopyFromCPU(NDArrayHandle handle, const void* data, size_t size) {
   API_BEGIN();
+  FlushAllDeferred();      // deferred pushes may read or write this array
   ND(handle)->SyncCopyFromCPU(data, size);
   API_END();
 }
 
 int MXNDArraySyncCopyToCPU(NDArrayHandle handle, void* data, size_t size) {
   API_BEGIN();
+  FlushAllDeferred();      // deferred pushes may read or write this array
   ND(handle)->SyncCopyToCPU(data, size);
   API_END();
 }
@@ -145,18 +147,21 @@ int MXNDArraySyncCopyFromNDArray(NDArrayHandle handle_dst, const NDArrayHandle h
 
 int MXNDArrayWaitToRead(NDArrayHandle handle) {
   API_BEGIN();
+  FlushAllDeferred();      // deferred pushes may read or write this array
   ND(handle)->WaitToRead();
   API_END();
 }
 
 int MXNDArrayWaitToWrite(NDArrayHandle handle) {
   API_BEGIN();
+  FlushAllDeferred();      // deferred pushes may read or write this array
   ND(handle)->WaitToWrite();
   API_END();
 }
 
 int MXNDArrayWaitAll(void) {
   API_BEGIN();
+  FlushAllDeferred();      // deferred pushes may read or write this array
   Runtime::Get()->WaitAll();
   API_END();
 }
@@ -636,6 +641,7 @@ int MXKVB200SetAutoFence(int auto_fence) {
 
 int MXKVB200Fence(int dev_id) {
   API_BEGIN();
+  FlushAllDeferred();      // deferred pushes may read or write this array
   Runtime::Get()->Fence(dev_id);
   API_END();
 }
@@ -643,6 +649,24 @@ int MXKVB200Fence(int dev_id) {
 int MXKVB200GetLaunchCount(int64_t* out) {
   API_BEGIN();
   *out = Runtime::Get()->launches;
+  API_END();
+}
+
+int MXKVB200SetDeferred(KVStoreHandle handle, int on) {
+  API_BEGIN();
+  KV(handle)->SetDeferred(on != 0);
+  API_END();
+}
+
+int MXKVB200Flush(KVStoreHandle handle) {
+  API_BEGIN();
+  KV(handle)->Flush();
+  API_END();
+}
+
+int MXKVB200GetDeferredBatches(KVStoreHandle handle, int64_t* out) {
+  API_BEGIN();
+  *out = KV(handle)->deferred_batches();
   API_END();
 }
 

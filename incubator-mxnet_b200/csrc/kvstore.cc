@@ -9,6 +9,8 @@
 
 namespace mxkv {
 
+static std::set<KVStore*>& DeferredStores();
+
 static std::string Lower(std::string s) {
   std::transform(s.begin(), s.end(), s.begin(), ::tolower);
   return s;
@@ -47,6 +49,8 @@ KVStore::KVStore(const std::string& type) : type_(Lower(type)) {   // kvstore.cc
 ProcessGroup* KVStore::PG() const { return solo_ ? nullptr : Runtime::Get()->pg(); }
 
 KVStore::~KVStore() {
+  try { Flush(); } catch (...) {}
+  DeferredStores().erase(this);
   try { Runtime::Get()->WaitAll(); } catch (...) {}
   for (auto& kv : hier_buf_) {
     if (kv.second.ptr == nullptr) continue;
@@ -70,6 +74,7 @@ int KVStore::group_size() const {
 void KVStore::Barrier() {
   std::lock_guard<std::recursive_mutex> rl(Runtime::Get()->mu());
   std::lock_guard<std::recursive_mutex> lk(mu_);
+  if (!pending_.empty()) Flush();
   Runtime* rt = Runtime::Get();
   rt->WaitAll();
   ProcessGroup* pg = PG();
@@ -153,9 +158,92 @@ KeyState& KVStore::PeekKey(int key) {
 // ---------------------------------------------------------------------------
 // Entry points serialise on the runtime first (per-device streams, descriptor rings, peer tables and signal pads
 // are shared by every store of the process), then on the store: callable from any thread, in this fixed order.
-#define LOCK()                                                                  \
+#define LOCK_ONLY()                                                             \
   std::lock_guard<std::recursive_mutex> rt_lk__(Runtime::Get()->mu());            \
   std::lock_guard<std::recursive_mutex> lk__(mu_)
+// every entry point that reads or changes the store issues the deferred calls first
+#define LOCK() LOCK_ONLY(); if (!pending_.empty()) Flush()
+
+// ---------------------------------------------------------------------------
+// deferred issue (kvstore.h)
+// ---------------------------------------------------------------------------
+static std::set<KVStore*>& DeferredStores() { static std::set<KVStore*> s; return s; }
+
+void FlushAllDeferred() {
+  std::lock_guard<std::recursive_mutex> rl(Runtime::Get()->mu());
+  std::vector<KVStore*> stores(DeferredStores().begin(), DeferredStores().end());
+  for (KVStore* s : stores) s->Flush();
+}
+
+void KVStore::SetDeferred(bool on) {
+  LOCK();
+  deferred_ = on;
+  if (on) DeferredStores().insert(this); else DeferredStores().erase(this);
+}
+
+bool KVStore::Defer(int kind, const std::vector<int>& vkeys, const std::vector<int>& okeys,
+                    const std::vector<NDArray>& vals, const std::vector<NDArray*>& outs, int priority) {
+  if (!deferred_ || hier_ || updater_ != nullptr || gc_bits_ != 0) return false;
+  for (auto& v : vals) if (!v.ctx().is_gpu() || v.stype() != kDefaultStorage) return false;
+  for (NDArray* o : outs) if (!o->ctx().is_gpu() || o->stype() != kDefaultStorage) return false;
+  for (int k : vkeys) { auto it = keys_.find(k); if (it == keys_.end() || it->second.stype != kDefaultStorage) return false; }
+  Deferred d;
+  d.kind = kind; d.vkeys = vkeys; d.okeys = okeys; d.vals = vals; d.priority = priority;
+  for (NDArray* o : outs) d.outs.push_back(*o);        // views of the caller's arrays (same memory)
+  pending_.push_back(std::move(d));
+  return true;
+}
+
+void KVStore::Flush() {
+  LOCK_ONLY();
+  if (pending_.empty()) return;
+  std::vector<Deferred> calls;
+  calls.swap(pending_);
+  // issue order: highest priority first among the calls that no EARLIER pending call shares a key with
+  std::vector<char> done(calls.size(), 0);
+  std::vector<size_t> order;
+  for (size_t n = 0; n < calls.size(); ++n) {
+    int best = -1;
+    std::unordered_set<int> blocked;         // keys of earlier calls that are still pending
+    for (size_t i = 0; i < calls.size(); ++i) {
+      if (done[i]) continue;
+      bool free_ = true;
+      for (int k : calls[i].vkeys) if (blocked.count(k)) { free_ = false; break; }
+      if (free_ && (best < 0 || calls[i].priority > calls[best].priority)) best = static_cast<int>(i);
+      for (int k : calls[i].vkeys) blocked.insert(k);
+    }
+    done[best] = 1;
+    order.push_back(static_cast<size_t>(best));
+  }
+  // merge neighbours of that order with the same kind and disjoint keys into one call
+  size_t i = 0;
+  while (i < order.size()) {
+    Deferred batch = calls[order[i]];
+    std::unordered_set<int> keys(batch.vkeys.begin(), batch.vkeys.end());
+    size_t j = i + 1;
+    for (; j < order.size(); ++j) {
+      const Deferred& c = calls[order[j]];
+      bool disjoint = c.kind == batch.kind;
+      for (int k : c.vkeys) if (keys.count(k)) { disjoint = false; break; }
+      if (!disjoint) break;
+      batch.vkeys.insert(batch.vkeys.end(), c.vkeys.begin(), c.vkeys.end());
+      batch.okeys.insert(batch.okeys.end(), c.okeys.begin(), c.okeys.end());
+      batch.vals.insert(batch.vals.end(), c.vals.begin(), c.vals.end());
+      batch.outs.insert(batch.outs.end(), c.outs.begin(), c.outs.end());
+      keys.insert(c.vkeys.begin(), c.vkeys.end());
+    }
+    i = j;
+    deferred_batches_++;
+    if (batch.kind == 0) {
+      PushImpl(batch.vkeys, batch.vals, batch.priority);
+    } else {
+      std::vector<NDArray*> outs;
+      for (auto& o : batch.outs) outs.push_back(&o);
+      PushPullImpl(batch.vkeys, batch.okeys, batch.vals, outs, batch.priority);
+    }
+  }
+}
+
 
 void KVStore::Init(const std::vector<int>& keys, const std::vector<NDArray>& vals) {
   LOCK(); SetKeyType(kIntKey); InitImpl(keys, vals);
@@ -165,7 +253,10 @@ void KVStore::Init(const std::vector<std::string>& str_keys, const std::vector<N
   std::vector<int> keys; NewStrKeys(str_keys, &keys); InitImpl(keys, vals);
 }
 void KVStore::Push(const std::vector<int>& keys, const std::vector<NDArray>& vals, int priority) {
-  LOCK(); SetKeyType(kIntKey); PushImpl(keys, vals, priority);
+  LOCK_ONLY(); SetKeyType(kIntKey);
+  if (Defer(0, keys, keys, vals, {}, priority)) return;
+  if (!pending_.empty()) Flush();
+  PushImpl(keys, vals, priority);
 }
 void KVStore::Push(const std::vector<std::string>& str_keys, const std::vector<NDArray>& vals, int priority) {
   LOCK(); SetKeyType(kStringKey);
@@ -181,7 +272,10 @@ void KVStore::Pull(const std::vector<std::string>& str_keys, const std::vector<N
 }
 void KVStore::PushPull(const std::vector<int>& vkeys, const std::vector<int>& okeys,
                        const std::vector<NDArray>& vals, const std::vector<NDArray*>& outs, int priority) {
-  LOCK(); SetKeyType(kIntKey); PushPullImpl(vkeys, okeys, vals, outs, priority);
+  LOCK_ONLY(); SetKeyType(kIntKey);
+  if (Defer(1, vkeys, okeys, vals, outs, priority)) return;
+  if (!pending_.empty()) Flush();
+  PushPullImpl(vkeys, okeys, vals, outs, priority);
 }
 void KVStore::PushPull(const std::vector<std::string>& svkeys, const std::vector<std::string>& sokeys,
                        const std::vector<NDArray>& vals, const std::vector<NDArray*>& outs, int priority) {
@@ -317,9 +411,21 @@ void KVStore::SetKeyFlag(bool str_key, int ikey, const std::string& skey, const 
   }
 }
 
+void KVStore::SetLearningRate(double lr) {
+  LOCK();                 // (deferred calls were made under the old learning rate)
+  opt_.lr = lr;
+}
+
+// per-key scalars: only a deferred call on THAT key has to be issued first
+void KVStore::FlushIfPending(int key) {
+  for (auto& d : pending_)
+    for (int k : d.vkeys) if (k == key) { Flush(); return; }
+}
+
 void KVStore::SetOptimizerMult(bool str_key, int ikey, const std::string& skey, float lr_mult, float wd_mult) {
-  LOCK();
+  LOCK_ONLY();
   const int key = ResolveKey(str_key, ikey, skey);
+  FlushIfPending(key);
   opt_.lr_mult[key] = lr_mult;
   opt_.wd_mult[key] = wd_mult;
 }
@@ -601,7 +707,7 @@ static void GroupPairs(const std::vector<int>& keys, const std::vector<V>& vals,
 }
 
 void KVStore::PushImpl(const std::vector<int>& keys, const std::vector<NDArray>& vals, int priority) {
-  (void)priority;
+  (void)priority;      // consumed by the deferred queue (Flush): by the time a call gets here its turn has come
   std::vector<int> uniq;
   std::vector<std::vector<NDArray>> grouped;
   GroupPairs<NDArray>(keys, vals, &uniq, &grouped, [](int, const NDArray& nd) {
@@ -1255,6 +1361,7 @@ bool KVStore::TryReplayRaw(int kind, uint32_t vnum, const int* vkeys, NDArray* c
   std::lock_guard<std::recursive_mutex> lk(mu_);
   raw_pending_ = false;
   raw_single_ = false;
+  if (deferred_ || !pending_.empty()) return false;      // the call joins (or must follow) the deferred queue
   if (plan_mode_ == 0 || key_type_ == kStringKey || hier_ || updater_ != nullptr || gc_bits_ != 0 ||
       (opt_.enabled && (IsNormOpt(opt_.kind) || AdamWSkips())))
     return false;
@@ -2273,8 +2380,10 @@ int64_t KVStore::GetUpdateCount(bool str_key, int ikey, const std::string& skey)
   return GetKey(ResolveKey(str_key, ikey, skey)).count;
 }
 void KVStore::SetUpdateCount(bool str_key, int ikey, const std::string& skey, int64_t c) {
-  LOCK();
-  GetKey(ResolveKey(str_key, ikey, skey)).count = c;
+  LOCK_ONLY();
+  const int key = ResolveKey(str_key, ikey, skey);
+  FlushIfPending(key);
+  PeekKey(key).count = c;          // (the count is read live by every launch: no plan depends on it)
 }
 
 }  // namespace mxkv

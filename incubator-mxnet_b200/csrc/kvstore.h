@@ -133,6 +133,18 @@ class KVStore {
   void PullRowSparse(const std::vector<std::string>& keys,
                      const std::vector<std::pair<NDArray*, NDArray>>& val_rowids, int priority);
 
+  // ---- deferred issue: what `priority` means on this engine -------------------------------------------------
+  // The reference's engine runs the ops that are ready in priority order (threaded_engine_perdevice.cc:97-279;
+  // the Trainer pushes parameter i with priority -i, gluon/trainer.py:386-409).  An in-order stream has no queue
+  // to reorder, so the queue is kept here: with deferral on, push / pushpull calls (dense GPU values, integer
+  // keys) are recorded instead of launched; Flush() -- explicit, or implied by any call that reads or changes
+  // the store or waits for an array -- issues them highest priority first, never moving a call ahead of an
+  // earlier one that shares a key with it (the engine's write-after-write order), and merges calls that are
+  // adjacent in that order and touch disjoint keys into ONE launch (sequence).
+  void SetDeferred(bool on);
+  void Flush();
+  int64_t deferred_batches() const { return deferred_batches_; }
+
   void SetUpdater(UpdaterFn fn, StrUpdaterFn sfn, void* handle);
   void SetGradientCompression(const std::vector<std::pair<std::string, std::string>>& kwargs);
   void Barrier();
@@ -143,7 +155,7 @@ class KVStore {
   // type 'updater' only: in-place fused update of caller-owned (weight, grad) pairs (kvstore.cc)
   void UpdaterStep(bool str_keys, const std::vector<int>& ikeys, const std::vector<std::string>& skeys,
                    const std::vector<NDArray>& weights, const std::vector<NDArray>& grads);
-  void SetLearningRate(double lr) { opt_.lr = lr; }
+  void SetLearningRate(double lr);
   bool has_fused_optimizer() const { return opt_.enabled; }
   // which: 0 stored value, 1 fp32 master, 2 state0, 3 state1; gathers shards so the result is complete
   NDArray GetState(bool str_key, int ikey, const std::string& skey, int which);
@@ -265,6 +277,18 @@ class KVStore {
   bool PlanEpochsMatch(const CallPlan& p) const;
   void PlanPatch(CallPlan& p, bool commit_counts);
   void PlanReplay(CallPlan& p);
+  struct Deferred {
+    int kind;                               // 0 push, 1 pushpull
+    std::vector<int> vkeys, okeys;
+    std::vector<NDArray> vals, outs;
+    int priority;
+  };
+  std::vector<Deferred> pending_;
+  void FlushIfPending(int key);
+  bool deferred_ = false;
+  int64_t deferred_batches_ = 0;            // launches (sequences) issued by Flush so far
+  bool Defer(int kind, const std::vector<int>& vkeys, const std::vector<int>& okeys, const std::vector<NDArray>& vals,
+             const std::vector<NDArray*>& outs, int priority);
   std::unordered_map<uint64_t, CallPlan> plans_;       // by hash of the signature
   uint64_t cfg_epoch_ = 0;                   // optimizer kind / updater / compression / hierarchy changes
   int plan_mode_ = 1;                        // MXKV_B200_PLAN: 0 off, 1 on, 2 verify (build both ways, compare, abort on a difference)
@@ -300,6 +324,9 @@ class KVStore {
   std::vector<int> last_norm_keys_;     // keys of the last skip_nonfinite push (count roll-back)
   std::recursive_mutex mu_;
 };
+
+// issues the deferred calls of every store that has some (array reads and waits are flush points)
+void FlushAllDeferred();
 
 // multi_sum_sq / multi_all_finite over a list of dense arrays on one GPU (kvstore_norm.cc)
 void MultiSumSq(const std::vector<NDArray>& arrays, float scale, NDArray* out_sumsq, NDArray* all_finite,

@@ -289,6 +289,19 @@ class KVStore(KVStoreBase):
         check_call(_LIB.MXKVStoreGetGroupSize(self.handle, ctypes.byref(r)))
         return r.value
 
+    def set_deferred(self, on=True):
+        """Queue push / pushpull calls and issue them at the next flush point in priority order, merged
+        (MXKVB200SetDeferred): the engine-side meaning of ``priority``."""
+        check_call(_LIB.MXKVB200SetDeferred(self.handle, 1 if on else 0))
+
+    def flush(self):
+        check_call(_LIB.MXKVB200Flush(self.handle))
+
+    def deferred_batches(self):
+        n = ctypes.c_int64()
+        check_call(_LIB.MXKVB200GetDeferredBatches(self.handle, ctypes.byref(n)))
+        return n.value
+
     def plan_hits(self):
         """push / pushpull calls served from a cached launch plan (MXKVB200GetPlanHits)"""
         n = ctypes.c_int64()

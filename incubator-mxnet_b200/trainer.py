@@ -335,11 +335,19 @@ class Trainer(object):
             else:
                 kv.pushpull(idx, grads, priority=0)
         else:
+            # the reference's loop (trainer.py:386-409): one call per parameter, priority -i.  On this engine the
+            # calls are queued and issued at the flush in priority order, merged into one launch (MXKVB200SetDeferred)
+            native = isinstance(kv, _kv.KVStore)
+            if native:
+                kv.set_deferred(True)
             for i in idx:
                 if self._update_on_kvstore:
                     kv.pushpull(i, self._grads[i], out=self._weights[i], priority=-i)
                 else:
                     kv.pushpull(i, self._grads[i], priority=-i)
+            if native:
+                kv.flush()
+                kv.set_deferred(False)
 
     def step(self, batch_size, ignore_stale_grad=False):
         """trainer.py:334-361: rescale_grad = scale / batch_size, allreduce, update."""

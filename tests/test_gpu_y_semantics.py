@@ -432,3 +432,56 @@ def test_subclass_overriding_step_is_not_sent_to_the_fused_kernel():
     out = mx.nd.empty(shape, mx.gpu(0))
     kv.pull(3, out=out)
     np.testing.assert_allclose(out.asnumpy(), 42.0)
+
+
+def test_deferred_issue_orders_by_priority_and_merges():
+    """`priority` on this engine (MXKVB200SetDeferred): queued calls are issued highest priority first, never ahead
+    of an earlier call on the same key, neighbours on disjoint keys merged into one launch -- the reference's
+    per-parameter loop `for i: kv.pushpull(i, g_i, out=w_i, priority=-i)` (gluon/trainer.py:386-409) becomes ONE
+    launch, with the results of the immediate form."""
+    n = 12
+    ks = list(range(n))
+    sizes = [5, 64, 1000, 4099, 1 << 14, 7, 300, 2052, 9, 1 << 12, 33, 70001]
+    rng = _rng(77)
+    w0 = [rng.uniform(0, 1, e).astype(np.float32) for e in sizes]
+    kw = dict(learning_rate=0.05, momentum=0.9, wd=1e-3)
+
+    def run(deferred):
+        kv = mx.kv.create("device")
+        kv.init(ks, [mx.nd.array(w, mx.gpu(0)) for w in w0])
+        kv.set_optimizer(mx.optimizer.SGD(**kw))
+        if deferred:
+            kv.set_deferred(True)
+        r = _rng(78)
+        outs = [mx.nd.empty((e,), mx.gpu(0)) for e in sizes]
+        launches = []
+        for step in range(3):
+            grads = [mx.nd.array(r.uniform(-1, 1, e).astype(np.float32), mx.gpu(0)) for e in sizes]
+            l0 = mx.kv.launch_count()
+            for i in ks:
+                kv.pushpull(i, grads[i], out=outs[i], priority=-i)
+            if deferred:
+                assert mx.kv.launch_count() == l0, "deferred calls must not launch before the flush point"
+            got = [o.asnumpy() for o in outs]          # reading an array is a flush point
+            launches.append(mx.kv.launch_count() - l0)
+        return got, launches, kv
+
+    want, imm_launches, _ = run(False)
+    got, def_launches, kv = run(True)
+    for a, b in zip(got, want):
+        assert_bits_equal(a, b, "deferred vs immediate")
+    assert imm_launches == [n, n, n] and def_launches == [1, 1, 1], (imm_launches, def_launches)
+    assert kv.deferred_batches() == 3
+
+    # two pushes of the SAME key keep their program order whatever their priorities (the engine's write-after-write
+    # dependency); an independent key with a higher priority goes first but changes nothing else
+    kv2 = mx.kv.create("device")
+    kv2.init([0, 1], [mx.nd.zeros((8,), mx.gpu(0)), mx.nd.zeros((8,), mx.gpu(0))])
+    kv2.set_deferred(True)
+    a, b, c = (mx.nd.ones((8,), mx.gpu(0)) * v for v in (1.0, 2.0, 3.0))
+    kv2.push(0, a, priority=-5)
+    kv2.push(0, b, priority=0)          # later call on key 0: must stay after the first
+    kv2.push(1, c, priority=9)
+    out0, out1 = mx.nd.empty((8,), mx.gpu(0)), mx.nd.empty((8,), mx.gpu(0))
+    kv2.pull([0, 1], out=[out0, out1])  # a pull is a flush point
+    assert (out0.asnumpy() == 2.0).all() and (out1.asnumpy() == 3.0).all()

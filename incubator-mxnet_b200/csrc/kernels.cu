@@ -244,17 +244,23 @@ kv_dense_bulk_kernel(DenseLaunch L) {
   __syncthreads();
   if (sync) barrier_start(L.sync);     // no peer byte may be requested before the rendezvous
 
-  // tiles of this block: a CONTIGUOUS range [first, first + ntiles) of the work list's tiles (the first `rem`
-  // blocks take one tile more).  A block then meets only the few keys its range spans -- with a strided
-  // assignment every block walks the whole key list and reloads a 400-byte descriptor per key, which on a
-  // 199-key model (BERT-base) cost a fifth of the kernel time (profiles/r02: 0.78 -> of the HBM peak) -- and its
-  // consecutive tiles continue the same DRAM pages.
-  const int64_t per = L.total_chunks / gridDim.x, rem = L.total_chunks % gridDim.x;
-  const int64_t first = blockIdx.x * per + (blockIdx.x < rem ? blockIdx.x : rem);
-  const int64_t ntiles = per + (blockIdx.x < rem ? 1 : 0);
-
+  // tiles of this block: groups of G consecutive tiles, block-cyclic -- tile(i) = ((i / G) * grid + block) * G + i % G.
+  // G = 1 is the plain strided walk: all blocks stream through one narrow window of every array (best for DRAM:
+  // 0.945 of the measured HBM peak on the 256 MB sweep keys) but every block meets every key of the work list and
+  // reloads a 400-byte descriptor each time, which cost a fifth of the kernel on a 199-key model (BERT-base:
+  // 0.78).  A contiguous range per block has the opposite profile (0.83 / 0.90).  Small groups keep the window
+  // narrow and divide the descriptor switches by G (profiles/r02_tune_bulk_group.txt).
+  const int64_t G = L.bulk_group > 0 ? L.bulk_group : 1;
+  const int64_t ngroups = (L.total_chunks + G - 1) / G;
+  const int64_t my_groups = static_cast<int64_t>(blockIdx.x) < ngroups ? (ngroups - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  int64_t ntiles = my_groups * G;
+  if (my_groups > 0) {      // the very last group of the list may be short
+    const int64_t last_group = blockIdx.x + (my_groups - 1) * gridDim.x;
+    if (last_group == ngroups - 1) ntiles -= ngroups * G - L.total_chunks;
+  }
+  auto tile_of = [&](int64_t i) -> int64_t { return ((i / G) * gridDim.x + blockIdx.x) * G + i % G; };
   auto issue = [&](int64_t i) {       // thread 0 only: request every input stream of tile i
-    const int64_t c = first + i;
+    const int64_t c = tile_of(i);
     int lo = 0, hi = L.nworks - 1;
     while (lo < hi) {
       const int mid = (lo + hi + 1) >> 1;
@@ -292,7 +298,7 @@ kv_dense_bulk_kernel(DenseLaunch L) {
 
   int cur = -1;
   for (int64_t i = 0; i < ntiles; ++i) {
-    const int64_t c = first + i;
+    const int64_t c = tile_of(i);
     int lo = 0, hi = L.nworks - 1;
     while (lo < hi) {
       const int mid = (lo + hi + 1) >> 1;

@@ -113,6 +113,7 @@ struct DenseLaunch {
   int bulk;                      // 1: shared-memory staged variant (cp.async.bulk + mbarrier pipeline)
   int bulk_stages;               // pipeline depth
   int bulk_arrays;               // input arrays staged per tile (max over the work list)
+  int bulk_group;                // consecutive tiles a block takes before it strides on by grid * bulk_group tiles
   int nvls_unroll;               // NVLS variant: multimem.ld_reduce requests in flight per thread (1, 2, 4 or 8)
   int nvls_pipe;                 // NVLS variant: 1 = next chunk's ld_reduce issued before this chunk's update/stores
 };

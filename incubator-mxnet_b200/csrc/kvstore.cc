@@ -2102,7 +2102,7 @@ void KVStore::LaunchWorks(const LaunchClassKey& ck, std::vector<std::vector<Tens
                                                      : d.max_grid, max_chunks));
     L.chunk_elems = static_cast<int>(chunk);
     L.threads = rt->threads;
-    L.bulk = bulk; L.bulk_stages = bulk_stages; L.bulk_arrays = bulk_arrays;
+    L.bulk = bulk; L.bulk_stages = bulk_stages; L.bulk_arrays = bulk_arrays; L.bulk_group = rt->bulk_group;
     L.nvls = ck.nvls;
     L.nvls_unroll = rt->nvls_unroll;
     L.nvls_pipe = rt->nvls_pipe;

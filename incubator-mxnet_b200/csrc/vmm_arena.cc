@@ -16,7 +16,10 @@
 // cudaIpc (peer pointers, no multicast alias).
 #include "runtime.h"
 #include <cuda.h>
+#include <cerrno>
+#include <cstdio>
 #include <cstring>
+#include <string>
 #include <sys/syscall.h>
 #include <unistd.h>
 
@@ -91,6 +94,18 @@ int DupFromPeer(int pid, int fd) {
   return got;
 }
 
+// first failure of this process, for the one-line note on the fallback (MXKV_B200_ARENA_VMM_VERBOSE=1)
+std::string g_why;
+bool Ok(const char* what, CUresult r) {
+  if (r == CUDA_SUCCESS) return true;
+  if (g_why.empty()) g_why = std::string(what) + " -> CUresult " + std::to_string(static_cast<int>(r));
+  return false;
+}
+bool Ok(const char* what, bool v) {
+  if (!v && g_why.empty()) g_why = std::string(what) + " failed (errno " + std::to_string(errno) + ")";
+  return v;
+}
+
 struct Msg {            // one rank's contribution to a step of the protocol
   int64_t ok;
   int64_t pid, fd_mem, fd_mc;
@@ -129,8 +144,9 @@ bool ProcessGroup::NewSegmentVmm(size_t min_bytes, Segment* out) {
   // ---- step 1: capability, granularity, my allocation + its fd; rank 0: the multicast object + its fd
   if (ok) {
     int mc_ok = 0;
-    ok = a.DeviceGet(&cudev, dev_) == CUDA_SUCCESS &&
-         a.DeviceGetAttribute(&mc_ok, CU_DEVICE_ATTRIBUTE_MULTICAST_SUPPORTED, cudev) == CUDA_SUCCESS && mc_ok != 0;
+    ok = Ok("cuDeviceGet", a.DeviceGet(&cudev, dev_)) &&
+         Ok("cuDeviceGetAttribute(MULTICAST_SUPPORTED)", a.DeviceGetAttribute(&mc_ok, CU_DEVICE_ATTRIBUTE_MULTICAST_SUPPORTED, cudev)) &&
+         Ok("device reports multicast support", mc_ok != 0);
   }
   if (ok) {
     prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
@@ -141,8 +157,8 @@ bool ProcessGroup::NewSegmentVmm(size_t min_bytes, Segment* out) {
     mcprop.handleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
     size_t g_mem = 0, g_mc = 0;
     mcprop.size = size_t(2) << 20;
-    ok = a.MemGetGranularity(&g_mem, &prop, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED) == CUDA_SUCCESS &&
-         a.MulticastGetGranularity(&g_mc, &mcprop, CU_MULTICAST_GRANULARITY_RECOMMENDED) == CUDA_SUCCESS &&
+    ok = Ok("cuMemGetAllocationGranularity", a.MemGetGranularity(&g_mem, &prop, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED)) &&
+         Ok("cuMulticastGetGranularity", a.MulticastGetGranularity(&g_mc, &mcprop, CU_MULTICAST_GRANULARITY_RECOMMENDED)) &&
          g_mem > 0 && g_mc > 0;
     if (ok) {
       const size_t g = std::max(g_mem, g_mc);
@@ -150,11 +166,11 @@ bool ProcessGroup::NewSegmentVmm(size_t min_bytes, Segment* out) {
       mcprop.size = bytes;
     }
   }
-  if (ok) ok = a.MemCreate(&h_mem[rank_], bytes, &prop, 0) == CUDA_SUCCESS;
-  if (ok) ok = a.MemExport(&fd_mem, h_mem[rank_], CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0) == CUDA_SUCCESS;
+  if (ok) ok = Ok("cuMemCreate", a.MemCreate(&h_mem[rank_], bytes, &prop, 0));
+  if (ok) ok = Ok("cuMemExportToShareableHandle", a.MemExport(&fd_mem, h_mem[rank_], CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0));
   if (ok && rank_ == 0) {
-    ok = a.MulticastCreate(&h_mc, &mcprop) == CUDA_SUCCESS &&
-         a.MemExport(&fd_mc, h_mc, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0) == CUDA_SUCCESS;
+    ok = Ok("cuMulticastCreate", a.MulticastCreate(&h_mc, &mcprop)) &&
+         Ok("cuMemExportToShareableHandle(multicast)", a.MemExport(&fd_mc, h_mc, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0));
   }
   std::vector<Msg> peers(world_);
   bool all_ok = agree(ok, peers.data(), static_cast<int64_t>(getpid()), fd_mem, fd_mc);
@@ -164,14 +180,16 @@ bool ProcessGroup::NewSegmentVmm(size_t min_bytes, Segment* out) {
     for (int r = 0; r < world_ && ok; ++r) {
       if (r != rank_) {
         const int fd = DupFromPeer(static_cast<int>(peers[r].pid), static_cast<int>(peers[r].fd_mem));
-        ok = fd >= 0 && a.MemImport(&h_mem[r], reinterpret_cast<void*>(static_cast<intptr_t>(fd)),
-                                    CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR) == CUDA_SUCCESS;
+        ok = Ok("pidfd_open / pidfd_getfd", fd >= 0) &&
+             Ok("cuMemImportFromShareableHandle", a.MemImport(&h_mem[r], reinterpret_cast<void*>(static_cast<intptr_t>(fd)),
+                                                              CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR));
         if (fd >= 0) close(fd);
       }
       if (r == 0 && rank_ != 0 && ok) {
         const int fd = DupFromPeer(static_cast<int>(peers[0].pid), static_cast<int>(peers[0].fd_mc));
-        ok = fd >= 0 && a.MemImport(&h_mc, reinterpret_cast<void*>(static_cast<intptr_t>(fd)),
-                                    CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR) == CUDA_SUCCESS;
+        ok = Ok("pidfd_getfd(multicast)", fd >= 0) &&
+             Ok("cuMemImportFromShareableHandle(multicast)", a.MemImport(&h_mc, reinterpret_cast<void*>(static_cast<intptr_t>(fd)),
+                                                                         CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR));
         if (fd >= 0) close(fd);
       }
     }
@@ -181,8 +199,8 @@ bool ProcessGroup::NewSegmentVmm(size_t min_bytes, Segment* out) {
   if (fd_mc >= 0) close(fd_mc);
 
   // ---- step 3: every GPU joins the multicast object, then binds its allocation
-  if (all_ok) { ok = a.MulticastAddDevice(h_mc, cudev) == CUDA_SUCCESS; all_ok = agree(ok); }
-  if (all_ok) { ok = a.MulticastBindMem(h_mc, 0, h_mem[rank_], 0, bytes, 0) == CUDA_SUCCESS; all_ok = agree(ok); }
+  if (all_ok) { ok = Ok("cuMulticastAddDevice", a.MulticastAddDevice(h_mc, cudev)); all_ok = agree(ok); }
+  if (all_ok) { ok = Ok("cuMulticastBindMem", a.MulticastBindMem(h_mc, 0, h_mem[rank_], 0, bytes, 0)); all_ok = agree(ok); }
 
   // ---- step 4: map everything for this GPU
   CUdeviceptr va[kMaxRanks] = {0};
@@ -194,17 +212,22 @@ bool ProcessGroup::NewSegmentVmm(size_t min_bytes, Segment* out) {
     acc.location.id = dev_;
     acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
     for (int r = 0; r < world_ && ok; ++r) {
-      ok = a.MemAddressReserve(&va[r], bytes, 0, 0, 0) == CUDA_SUCCESS &&
-           a.MemMap(va[r], bytes, 0, h_mem[r], 0) == CUDA_SUCCESS &&
-           a.MemSetAccess(va[r], bytes, &acc, 1) == CUDA_SUCCESS;
+      ok = Ok("cuMemAddressReserve", a.MemAddressReserve(&va[r], bytes, 0, 0, 0)) &&
+           Ok("cuMemMap", a.MemMap(va[r], bytes, 0, h_mem[r], 0)) &&
+           Ok("cuMemSetAccess", a.MemSetAccess(va[r], bytes, &acc, 1));
     }
     if (ok) {
-      ok = a.MemAddressReserve(&va_mc, bytes, 0, 0, 0) == CUDA_SUCCESS &&
-           a.MemMap(va_mc, bytes, 0, h_mc, 0) == CUDA_SUCCESS && a.MemSetAccess(va_mc, bytes, &acc, 1) == CUDA_SUCCESS;
+      ok = Ok("cuMemAddressReserve(multicast)", a.MemAddressReserve(&va_mc, bytes, 0, 0, 0)) &&
+           Ok("cuMemMap(multicast)", a.MemMap(va_mc, bytes, 0, h_mc, 0)) &&
+           Ok("cuMemSetAccess(multicast)", a.MemSetAccess(va_mc, bytes, &acc, 1));
     }
     all_ok = agree(ok);
   }
   if (!all_ok) {
+    if (!a.ok && g_why.empty()) g_why = "a CUDA driver entry point is missing";
+    if (std::getenv("MXKV_B200_ARENA_VMM_VERBOSE") != nullptr || rank_ == 0)
+      std::fprintf(stderr, "[mxkv_b200] rank %d: no engine-owned multicast arena (%s); using cudaMalloc + cudaIpc\n", rank_,
+                   g_why.empty() ? "another rank could not set it up" : g_why.c_str());
     // undo whatever this rank got as far as (mappings die with the address ranges; handles are reference counted)
     for (int r = 0; r < world_; ++r) {
       if (va[r]) { a.MemUnmap(va[r], bytes); a.MemAddressFree(va[r], bytes); }

@@ -4,7 +4,8 @@
 // Here the engine builds them itself, so that every array of the peer-mapped arena -- and therefore any consumer
 // of the C ABI, torch or not -- can take the NVLS kernel (multimem.ld_reduce / multimem.st):
 //   * a segment is a CUDA VMM allocation (cuMemCreate) per rank, exported as a POSIX file descriptor, duplicated
-//     into every peer with pidfd_getfd(2) (the bootstrap all-gather carries pid + fd number, nothing else), imported
+//     into every peer with pidfd_getfd(2) -- or, where the container forbids that, passed over an abstract unix
+//     socket with SCM_RIGHTS -- (the bootstrap all-gather carries pid + fd number, nothing else), imported
 //     and mapped there (cuMemImportFromShareableHandle / cuMemMap / cuMemSetAccess): the peer pointers that
 //     cudaIpcOpenMemHandle used to provide;
 //   * rank 0 creates ONE multicast object per segment (cuMulticastCreate), every rank adds its GPU
@@ -20,7 +21,12 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <cstddef>
+#include <sys/prctl.h>
+#include <sys/socket.h>
 #include <sys/syscall.h>
+#include <sys/uio.h>
+#include <sys/un.h>
 #include <unistd.h>
 
 #ifndef SYS_pidfd_open
@@ -106,6 +112,66 @@ bool Ok(const char* what, bool v) {
   return v;
 }
 
+// ---- descriptor transport #2: abstract unix sockets + SCM_RIGHTS (what survives a locked-down ptrace policy) ----
+void FdSockName(int pid, uint64_t tag, sockaddr_un* addr, socklen_t* len) {
+  std::memset(addr, 0, sizeof(*addr));
+  addr->sun_family = AF_UNIX;
+  const int n = std::snprintf(addr->sun_path + 1, sizeof(addr->sun_path) - 1, "mxkv_b200_%d_%llu", pid,
+                              static_cast<unsigned long long>(tag));      // leading NUL: abstract namespace
+  *len = static_cast<socklen_t>(offsetof(sockaddr_un, sun_path) + 1 + n);
+}
+int FdServerOpen(int pid, uint64_t tag) {
+  const int s = socket(AF_UNIX, SOCK_STREAM, 0);
+  if (s < 0) return -1;
+  sockaddr_un addr; socklen_t len;
+  FdSockName(pid, tag, &addr, &len);
+  if (bind(s, reinterpret_cast<sockaddr*>(&addr), len) != 0 || listen(s, 64) != 0) { close(s); return -1; }
+  return s;
+}
+int FdClientConnect(int pid, uint64_t tag) {
+  const int s = socket(AF_UNIX, SOCK_STREAM, 0);
+  if (s < 0) return -1;
+  sockaddr_un addr; socklen_t len;
+  FdSockName(pid, tag, &addr, &len);
+  if (connect(s, reinterpret_cast<sockaddr*>(&addr), len) != 0) { close(s); return -1; }
+  return s;
+}
+bool FdServerSendOne(int srv, const int* fds, int n) {       // accept one peer, hand it n descriptors
+  const int c = accept(srv, nullptr, nullptr);
+  if (c < 0) return false;
+  char byte = 'x';
+  iovec iov{&byte, 1};
+  alignas(cmsghdr) char ctl[CMSG_SPACE(2 * sizeof(int))];
+  std::memset(ctl, 0, sizeof(ctl));
+  msghdr msg;
+  std::memset(&msg, 0, sizeof(msg));
+  msg.msg_iov = &iov; msg.msg_iovlen = 1;
+  msg.msg_control = ctl; msg.msg_controllen = CMSG_SPACE(n * sizeof(int));
+  cmsghdr* cm = CMSG_FIRSTHDR(&msg);
+  cm->cmsg_level = SOL_SOCKET; cm->cmsg_type = SCM_RIGHTS; cm->cmsg_len = CMSG_LEN(n * sizeof(int));
+  std::memcpy(CMSG_DATA(cm), fds, n * sizeof(int));
+  const bool ok = sendmsg(c, &msg, 0) == 1;
+  close(c);
+  return ok;
+}
+bool FdClientRecv(int c, int* fds, int n) {
+  char byte = 0;
+  iovec iov{&byte, 1};
+  alignas(cmsghdr) char ctl[CMSG_SPACE(2 * sizeof(int))];
+  std::memset(ctl, 0, sizeof(ctl));
+  msghdr msg;
+  std::memset(&msg, 0, sizeof(msg));
+  msg.msg_iov = &iov; msg.msg_iovlen = 1;
+  msg.msg_control = ctl; msg.msg_controllen = sizeof(ctl);
+  if (recvmsg(c, &msg, 0) != 1) return false;
+  cmsghdr* cm = CMSG_FIRSTHDR(&msg);
+  if (cm == nullptr || cm->cmsg_level != SOL_SOCKET || cm->cmsg_type != SCM_RIGHTS ||
+      cm->cmsg_len != CMSG_LEN(n * sizeof(int)))
+    return false;
+  std::memcpy(fds, CMSG_DATA(cm), n * sizeof(int));
+  return true;
+}
+
 struct Msg {            // one rank's contribution to a step of the protocol
   int64_t ok;
   int64_t pid, fd_mem, fd_mc;
@@ -175,26 +241,73 @@ bool ProcessGroup::NewSegmentVmm(size_t min_bytes, Segment* out) {
   std::vector<Msg> peers(world_);
   bool all_ok = agree(ok, peers.data(), static_cast<int64_t>(getpid()), fd_mem, fd_mc);
 
-  // ---- step 2: duplicate the peers' descriptors into this process and import them
+  // ---- step 2: get the peers' descriptors into this process (pidfd_getfd; where the container forbids it --
+  // EPERM under a restrictive ptrace policy -- an abstract unix socket per rank and SCM_RIGHTS), then import them
+  int got_mem[kMaxRanks];
+  int got_mc = -1;
+  for (int r = 0; r < kMaxRanks; ++r) got_mem[r] = -1;
+  if (all_ok) {
+    prctl(PR_SET_PTRACER, PR_SET_PTRACER_ANY, 0, 0, 0);      // Yama ptrace_scope = 1: let the peers duplicate from us
+    all_ok = agree(true);                                     // (everybody has opted in before anybody tries)
+  }
+  bool have_fds = false;
+  if (all_ok) {
+    bool mine = true;
+    for (int r = 0; r < world_ && mine; ++r) {
+      if (r == rank_) continue;
+      got_mem[r] = DupFromPeer(static_cast<int>(peers[r].pid), static_cast<int>(peers[r].fd_mem));
+      mine = got_mem[r] >= 0;
+      if (mine && r == 0) { got_mc = DupFromPeer(static_cast<int>(peers[0].pid), static_cast<int>(peers[0].fd_mc)); mine = got_mc >= 0; }
+    }
+    const int err = errno;
+    have_fds = agree(mine);
+    if (!have_fds) {
+      for (int r = 0; r < world_; ++r) if (got_mem[r] >= 0) { close(got_mem[r]); got_mem[r] = -1; }
+      if (got_mc >= 0) { close(got_mc); got_mc = -1; }
+      // second transport: every rank serves its descriptors over an abstract unix socket
+      const uint64_t tag = static_cast<uint64_t>(segs_.size());
+      const int srv = FdServerOpen(static_cast<int>(getpid()), tag);
+      bool up = agree(srv >= 0);                              // all sockets are listening
+      int conn[kMaxRanks];
+      for (int r = 0; r < kMaxRanks; ++r) conn[r] = -1;
+      mine = up;
+      if (up) {
+        for (int r = 0; r < world_ && mine; ++r) {            // connects complete out of the listen backlog
+          if (r == rank_) continue;
+          conn[r] = FdClientConnect(static_cast<int>(peers[r].pid), tag);
+          mine = conn[r] >= 0;
+        }
+        const int fds[2] = {fd_mem, rank_ == 0 ? fd_mc : -1};
+        for (int k = 0; k < world_ - 1 && mine; ++k) mine = FdServerSendOne(srv, fds, rank_ == 0 ? 2 : 1);
+        for (int r = 0; r < world_ && mine; ++r) {
+          if (r == rank_) continue;
+          int in[2] = {-1, -1};
+          mine = FdClientRecv(conn[r], in, r == 0 ? 2 : 1);
+          got_mem[r] = in[0];
+          if (r == 0) got_mc = in[1];
+        }
+      }
+      for (int r = 0; r < world_; ++r) if (conn[r] >= 0) close(conn[r]);
+      if (srv >= 0) close(srv);
+      if (!mine && g_why.empty())
+        g_why = "descriptor exchange failed: pidfd_getfd errno " + std::to_string(err) + ", unix socket errno " + std::to_string(errno);
+      have_fds = agree(mine);
+    }
+    all_ok = have_fds;
+  }
   if (all_ok) {
     for (int r = 0; r < world_ && ok; ++r) {
-      if (r != rank_) {
-        const int fd = DupFromPeer(static_cast<int>(peers[r].pid), static_cast<int>(peers[r].fd_mem));
-        ok = Ok("pidfd_open / pidfd_getfd", fd >= 0) &&
-             Ok("cuMemImportFromShareableHandle", a.MemImport(&h_mem[r], reinterpret_cast<void*>(static_cast<intptr_t>(fd)),
-                                                              CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR));
-        if (fd >= 0) close(fd);
-      }
-      if (r == 0 && rank_ != 0 && ok) {
-        const int fd = DupFromPeer(static_cast<int>(peers[0].pid), static_cast<int>(peers[0].fd_mc));
-        ok = Ok("pidfd_getfd(multicast)", fd >= 0) &&
-             Ok("cuMemImportFromShareableHandle(multicast)", a.MemImport(&h_mc, reinterpret_cast<void*>(static_cast<intptr_t>(fd)),
-                                                                         CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR));
-        if (fd >= 0) close(fd);
-      }
+      if (r == rank_) continue;
+      ok = Ok("cuMemImportFromShareableHandle", a.MemImport(&h_mem[r], reinterpret_cast<void*>(static_cast<intptr_t>(got_mem[r])),
+                                                            CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR));
     }
+    if (ok && rank_ != 0)
+      ok = Ok("cuMemImportFromShareableHandle(multicast)", a.MemImport(&h_mc, reinterpret_cast<void*>(static_cast<intptr_t>(got_mc)),
+                                                                       CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR));
     all_ok = agree(ok);          // (the exporters keep their descriptors open until everybody has imported)
   }
+  for (int r = 0; r < world_; ++r) if (got_mem[r] >= 0) close(got_mem[r]);
+  if (got_mc >= 0) close(got_mc);
   if (fd_mem >= 0) close(fd_mem);
   if (fd_mc >= 0) close(fd_mc);
 

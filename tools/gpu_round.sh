@@ -42,25 +42,30 @@ elif [ "$MODE" = "tune" ]; then
   if [ "$N" = "8" ]; then
     TUNE_GRIDS=0,148,64,32 TUNE_OPTS=sgd run 300 tune_nvls_n4.txt $(torchrun_ 4) tools/tune_nvls.py
   fi
+elif [ "$N" = "8" ]; then
+  # 8-GPU minutes are charged 8x: every multi-GPU test at HEAD (the single-GPU forced-variant sweeps ran on the
+  # 1- and 2-GPU boxes), the bench line, the hierarchy on hardware, engine-owned vs torch-owned multicast memory
+  run 900 pytest_n8.log python -m pytest tests -m gpu -q --maxfail=25 -p no:cacheprovider --durations=8 -k "not forced_variant"
+  tail -n 14 $OUT/pytest_n8.log
+  run 500 bench_n8.json $(torchrun_ 8) bench.py --gpus 8
+  run 200 bench_ref_n8.json $(torchrun_ 8) bench.py --impl reference --gpus 8 --steps 3 --warmup 1
+  run 200 bench_n8_hier_2x4.json $(torchrun_ 8) bench.py --gpus 8 --local-world 4 --steps 100 $LIGHT
+  MXKV_B200_ARENA_VMM=0 run 200 bench_n8_torch_multicast.json $(torchrun_ 8) bench.py --gpus 8 --steps 200 $LIGHT
+  run 200 bench_bert_adam_n8.json $(torchrun_ 8) bench.py --gpus 8 --workload bert --optimizer adam --steps 40 $LIGHT
 else
   run 1500 pytest_n$N.log python -m pytest tests -m gpu -q --maxfail=25 -p no:cacheprovider --durations=12
   tail -n 25 $OUT/pytest_n$N.log
   run 700 bench_n$N.json $(torchrun_ $N) bench.py --gpus $N
-  # (NVLink bytes come from NVML counters inside bench.py: ncu cannot profile a kernel that rendezvous with peers --
-  #  "UnknownError / Failed to profile kv_dense_bulk_kernel", r02 call 4, tools/ncu_rank0.sh)
   run 300 bench_ref_n$N.json $(torchrun_ $N) bench.py --impl reference --gpus $N --steps 3 --warmup 1
   run 300 bench_bert_adam_n$N.json $(torchrun_ $N) bench.py --gpus $N --workload bert --optimizer adam --steps 40 $LIGHT
-  if [ "$N" = "8" ]; then
-    run 400 bench_n8_hier_2x4.json $(torchrun_ 8) bench.py --gpus 8 --local-world 4 --steps 100 $LIGHT
-    run 500 bench_n4.json $(torchrun_ 4) bench.py --gpus 4
-    run 500 bench_n2.json $(torchrun_ 2) bench.py --gpus 2
-  fi
   if [ "$N" = "2" ]; then      # the box has the time: the single-GPU lines of this commit as well
     run 400 bench_n1.json python bench.py --gpus 1
     run 200 bench_bert_adam_n1.json python bench.py --workload bert --optimizer adam --steps 40 $LIGHT
     run 200 bench_resnet_sgd_n1.json python bench.py --workload resnet50 --optimizer sgd --steps 100 $LIGHT
     run 200 launches_bert_n1.csv ncu --metrics gpu__time_duration.sum --clock-control none -s 10 -c 20 --csv \
         python bench.py --workload bert --optimizer adam --steps 12 --warmup 3 $LIGHT
+    MXKV_B200_ARENA_VMM=0 run 200 bench_n2_ipc_arena.json $(torchrun_ 2) bench.py --gpus 2 --steps 300 $LIGHT
+    run 200 bench_n2_vmm_arena.json $(torchrun_ 2) bench.py --gpus 2 --steps 300 $LIGHT
   fi
   if [ "$N" = "4" ]; then
     run 400 bench_n4_hier_2x2.json $(torchrun_ 4) bench.py --gpus 4 --local-world 2 --steps 100 $LIGHT

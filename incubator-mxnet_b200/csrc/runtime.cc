@@ -118,7 +118,8 @@ void ProcessGroup::NewSegment(size_t min_bytes) {
     // engine-owned multicast memory (vmm_arena.cc); the first segment decides for the life of the group
     const bool want = vmm_mode_ == 1 || EnvInt("MXKV_B200_ARENA_VMM", 1) != 0;
     const bool got = want && NewSegmentVmm(bytes, &s);
-    MXKV_CHECK(got || vmm_mode_ != 1) << "could not extend the multicast arena by " << bytes << " bytes";
+    // a later segment that cannot be had (multicast objects are a finite resource) is an ordinary IPC segment:
+    // its arrays simply have no multicast alias; no further attempts are made
     vmm_mode_ = got ? 1 : 0;
     if (got) { segs_.push_back(s); return; }
     std::memset(&s, 0, sizeof(s));

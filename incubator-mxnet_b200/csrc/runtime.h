@@ -107,9 +107,9 @@ class ProcessGroup {
   // vmm_arena.cc: cuMemCreate + POSIX-fd exchange + cuMulticast*; collective, all ranks succeed or all fail
   bool NewSegmentVmm(size_t min_bytes, Segment* out);
   void FreeSegmentVmm(Segment& s);
-  int vmm_mode_ = -1;           // -1 not decided yet, 0 cudaMalloc + cudaIpc, 1 VMM + multicast
+  int vmm_mode_ = -1;           // -1 not decided yet, 0 cudaMalloc + cudaIpc from now on, 1 VMM + multicast so far
  public:
-  bool has_multicast() const { return vmm_mode_ == 1; }
+  bool has_multicast() const { for (auto& s : segs_) if (s.vmm) return true; return false; }
  private:
   int rank_, world_, dev_;
   AllGatherFn fn_;

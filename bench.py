@@ -846,6 +846,8 @@ def main():
     ap.add_argument("--no-sweep", action="store_true", help="skip the per-size sweep array")
     ap.add_argument("--no-secondary", action="store_true", help="skip the ResNet-50 / BERT / row_sparse secondaries")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-clocks", action="store_true", help="do not run the nvidia-smi clock sampler (diagnosis)")
+    ap.add_argument("--no-nvml", action="store_true", help="do not read the NVML NVLink counters (diagnosis)")
     ap.add_argument("--local-world", type=int, default=0,
                     help="split the box into 'nodes' of this many GPUs and use kv.create('dist_device_sync'): NVLink "
                          "peer memory inside a node, NCCL between nodes (not the driver's configuration)")
@@ -890,7 +892,7 @@ def main():
         return
 
     sampler = ClockSampler(local)
-    if rank == 0:
+    if rank == 0 and not args.no_clocks:
         sampler.start()                      # nvidia-smi needs about a second before its first sample
     numa = bind_to_gpu_numa(local)
     env = Env(args)
@@ -941,7 +943,7 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kern = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     torch.cuda.synchronize(); env.barrier()
-    nvl0 = nvlink_counters(local) if world > 1 else None
+    nvl0 = nvlink_counters(local) if (world > 1 and not args.no_nvml) else None
     t_host0 = time.time()
     ev0.record()
     for i in range(args.steps):
@@ -951,7 +953,7 @@ def main():
     ev1.record()
     host_issue_ms = (time.time() - t_host0) * 1e3 / args.steps      # the host's share: calls are asynchronous
     torch.cuda.synchronize(); env.barrier()
-    nvl1 = nvlink_counters(local) if world > 1 else None
+    nvl1 = nvlink_counters(local) if (world > 1 and not args.no_nvml) else None
     launches = mx.kv.launch_count() - launches0
     variant = variant_since(env, variants0)
     ms_total = ev0.elapsed_time(ev1)

@@ -54,7 +54,7 @@ __device__ __forceinline__ void spin_check(long long t0, long long timeout) {
 }
 
 __device__ __forceinline__ void barrier_start(const SyncArgs& s) {
-  const uint32_t flag = s.self[kSigFlagOff + blockIdx.x] + 1;
+  const uint32_t flag = s.epoch;
   if (threadIdx.x < s.world) {
     uint32_t* peer = s.peers[threadIdx.x] + kSigStartOff + blockIdx.x * kMaxRanks + s.rank;
     const uint32_t* mine = s.self + kSigStartOff + blockIdx.x * kMaxRanks + threadIdx.x;
@@ -63,14 +63,13 @@ __device__ __forceinline__ void barrier_start(const SyncArgs& s) {
     while (ld_flag_volatile(mine) != flag) spin_check(t0, s.timeout);
   }
   __syncthreads();
-  if (threadIdx.x == 0) s.self[kSigFlagOff + blockIdx.x] = flag;
 }
 
 // release == true: this block stored into peer memory; make those stores visible
 // system-wide before signalling (two-shot all-gather half).
 __device__ __forceinline__ void barrier_end(const SyncArgs& s, bool release) {
   __syncthreads();
-  const uint32_t flag = s.self[kSigFlagOff + blockIdx.x] + 1;
+  const uint32_t flag = s.epoch;
   if (threadIdx.x < s.world) {
     uint32_t* peer = s.peers[threadIdx.x] + kSigEndOff + blockIdx.x * kMaxRanks + s.rank;
     const uint32_t* mine = s.self + kSigEndOff + blockIdx.x * kMaxRanks + threadIdx.x;
@@ -84,7 +83,6 @@ __device__ __forceinline__ void barrier_end(const SyncArgs& s, bool release) {
     }
   }
   __syncthreads();
-  if (threadIdx.x == 0) s.self[kSigFlagOff + blockIdx.x] = flag;
 }
 
 // ---------------------------------------------------------------------------

@@ -80,6 +80,11 @@ struct SyncArgs {
   int rank;
   int mode;                      // SyncMode
   long long timeout;             // spin limit in SM clock cycles (0: wait for ever)
+  // The value this launch's blocks exchange: the same on every participant of the launch, different from every
+  // earlier launch that used these pads (Runtime::NextSyncEpoch).  Round 1 derived it from a per-device counter
+  // in the pad, which only agrees across GPUs as long as every collective launch has the same participants --
+  // a single-process store pushed from {0,1}, then {0,1,2} dead-locked (found on the first 8-GPU run of round 2).
+  uint32_t epoch;
 };
 
 // signal pad layout in uint32 words

@@ -1151,6 +1151,7 @@ void KVStore::ReduceUpdateCompressed(std::vector<Group>& groups, bool write_outs
       sync.world = world; sync.rank = pg->rank(); sync.mode = SYNC_WRITE_PEERS;
       sync.timeout = rt->spin_timeout_cycles;
       DeviceGuard dg(pg->dev());
+      sync.epoch = rt->NextSyncEpoch(pg);
       MXKV_CHECK(LaunchBarrier(sync, rt->Dev(pg->dev()).stream) == 0) << "barrier launch failed";   // codes published
       rt->launches++;
     }
@@ -1218,6 +1219,7 @@ void KVStore::ReduceUpdateCompressed(std::vector<Group>& groups, bool write_outs
     }
     if (world > 1) {
       DeviceGuard dg(pg->dev());
+      sync.epoch = rt->NextSyncEpoch(pg);
       MXKV_CHECK(LaunchBarrier(sync, rt->Dev(pg->dev()).stream) == 0) << "barrier launch failed";   // codes consumed
       rt->launches++;
     } else {
@@ -2057,6 +2059,8 @@ void KVStore::LaunchWorks(const LaunchClassKey& ck, std::vector<std::vector<Tens
   for (int64_t len : busiest) max_chunks += (len + chunk - 1) / chunk;
   max_chunks = std::max<int64_t>(1, max_chunks);
 
+  // one flag value for the rendezvous of this launch, the same on every participant (SyncArgs::epoch)
+  const uint32_t sync_epoch = ck.sync_mode != SYNC_NONE ? rt->NextSyncEpoch(pg) : 0;
   for (int p = my_first; p <= my_last; ++p) {
     auto& w = per_part[p];
     if (w.empty()) continue;
@@ -2096,6 +2100,7 @@ void KVStore::LaunchWorks(const LaunchClassKey& ck, std::vector<std::vector<Tens
     L.sync.rank = p;
     L.sync.self = d.signal_pad;
     L.sync.timeout = rt->spin_timeout_cycles;
+    L.sync.epoch = sync_epoch;
     for (int q = 0; q < n_part; ++q)
       L.sync.peers[q] = mp_mode ? pg->signal_pad(q) : rt->Dev(part_dev[q]).signal_pad;
     L.grid = static_cast<int>(std::min<int64_t>(bulk ? std::min(bulk_cap, rt->max_blocks > 0 ? rt->max_blocks : bulk_cap)

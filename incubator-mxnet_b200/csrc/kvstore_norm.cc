@@ -37,6 +37,7 @@ void KVStore::LaunchNormWorks(std::vector<NormClass>& classes, int opt_kind, con
   struct Part {
     int dev = -1;
     bool collective = false;
+    int cls = 0;                 // index of the launch class (one rendezvous value per class and phase)
     NormLaunch L;
     float* psum = nullptr;
     size_t off = 0, bytes = 0;
@@ -45,7 +46,9 @@ void KVStore::LaunchNormWorks(std::vector<NormClass>& classes, int opt_kind, con
   // per device: where the non-finite counts of every key of the push live (as mapped on that device)
   std::map<int, std::vector<const float*>> bad_ptrs;
 
+  int cls_index = -1;
   for (auto& cls : classes) {
+    ++cls_index;
     const LaunchClassKey& ck = cls.ck;
     MXKV_CHECK(!ck.nvls) << "the multicast variant has no layer-wise optimizers";
     const bool collective = ck.sync_mode != SYNC_NONE;
@@ -69,6 +72,7 @@ void KVStore::LaunchNormWorks(std::vector<NormClass>& classes, int opt_kind, con
       Part part;
       part.dev = dev;
       part.collective = collective;
+      part.cls = cls_index;
       CUDA_CALL(cudaMallocAsync(reinterpret_cast<void**>(&part.psum),
                                 std::max<size_t>(16, static_cast<size_t>(acc) * kPsumStride * sizeof(float)), d.stream));
 
@@ -182,10 +186,17 @@ void KVStore::LaunchNormWorks(std::vector<NormClass>& classes, int opt_kind, con
   // phase-major issue order: a rank's kernel spins until its peers' kernel of the same phase runs,
   // and no class may decide about an overflow before every class has counted
   auto phase = [&](int sync_mode, const std::function<int(const NormLaunch&, cudaStream_t)>& fn) {
+    // one rendezvous value per launch class of this phase, the same on every participant (SyncArgs::epoch);
+    // every rank walks the classes in the same order, so the counters advance alike
+    std::map<int, uint32_t> epoch_of_class;
+    if (sync_mode != SYNC_NONE)
+      for (auto& part : parts)
+        if (part.collective && !epoch_of_class.count(part.cls)) epoch_of_class[part.cls] = rt->NextSyncEpoch(pg);
     for (auto& part : parts) {
       DeviceGuard dg(part.dev);
       NormLaunch L = part.L;
       L.sync.mode = part.collective ? sync_mode : SYNC_NONE;
+      L.sync.epoch = (part.collective && sync_mode != SYNC_NONE) ? epoch_of_class[part.cls] : 0;
       const int rc = fn(L, rt->Dev(part.dev).stream);
       MXKV_CHECK(rc == 0) << "kernel launch failed: " << cudaGetErrorString(static_cast<cudaError_t>(rc));
       rt->launches++;

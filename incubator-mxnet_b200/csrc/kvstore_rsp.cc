@@ -209,6 +209,7 @@ void KVStore::PushRowSparse(KeyState& ks, const std::vector<NDArray>& vals) {
     for (int q = 0; q < world; ++q) sync.peers[q] = pg->signal_pad(q);
     sync.world = world; sync.rank = pg->rank(); sync.mode = SYNC_WRITE_PEERS;
     sync.timeout = rt->spin_timeout_cycles;
+    sync.epoch = rt->NextSyncEpoch(pg);
     if (!fused_path || !r.rsp_stage_guarded) CheckLaunch(LaunchBarrier(sync, s), "barrier");
     if (!fused_path) {
       if (v.nnz() > 0) {
@@ -216,6 +217,7 @@ void KVStore::PushRowSparse(KeyState& ks, const std::vector<NDArray>& vals) {
         CopyBytes(v.data(), v.ctx(), r.stage_val.data(), r.stage_val.ctx(), v.nnz() * L * 4);
       }
       CheckLaunch(LaunchSetI64(static_cast<int64_t*>(r.stage_nnz.data()), v.nnz(), s), "set_nnz");
+      sync.epoch = rt->NextSyncEpoch(pg);
       CheckLaunch(LaunchBarrier(sync, s), "barrier");
     }
     r.rsp_stage_guarded = fused_path;      // the fused kernel ends with a cross-GPU barrier
@@ -470,12 +472,14 @@ void KVStore::HierPushRowSparse(KeyState& ks, const std::vector<NDArray>& vals) 
     for (int q = 0; q < world; ++q) sync.peers[q] = pg->signal_pad(q);
     sync.world = world; sync.rank = pg->rank(); sync.mode = SYNC_WRITE_PEERS;
     sync.timeout = rt->spin_timeout_cycles;
+    sync.epoch = rt->NextSyncEpoch(pg);
     CheckLaunch(LaunchBarrier(sync, s), "barrier");      // peers are done with the previous push's staging
     if (v.nnz() > 0) {
       CopyBytes(v.idx_ptr(), v.ctx(), r.stage_idx.data(), r.stage_idx.ctx(), v.nnz() * 8);
       CopyBytes(v.data(), v.ctx(), r.stage_val.data(), r.stage_val.ctx(), v.nnz() * L * 4);
     }
     CheckLaunch(LaunchSetI64(static_cast<int64_t*>(r.stage_nnz.data()), v.nnz(), s), "set_nnz");
+    sync.epoch = rt->NextSyncEpoch(pg);
     CheckLaunch(LaunchBarrier(sync, s), "barrier");
     S.n = world;
     for (int q = 0; q < world; ++q) {

@@ -101,7 +101,9 @@ class ProcessGroup {
   void Barrier();
   uint32_t* signal_pad(int r) const { return pads_.ptr[r] ? static_cast<uint32_t*>(pads_.ptr[r]) : nullptr; }
   size_t arena_used() const { return used_total_; }
+  uint32_t NextSyncEpoch() { return ++sync_epoch_; }     // every rank issues the same collective launches in order
  private:
+  uint32_t sync_epoch_ = 0;
   void NewSegment(size_t min_bytes);
   struct Segment { char* base[kMaxRanks]; size_t bytes; size_t used; char* mc; bool vmm; };
   // vmm_arena.cc: cuMemCreate + POSIX-fd exchange + cuMulticast*; collective, all ranks succeed or all fail
@@ -143,6 +145,9 @@ class Runtime {
   ProcessGroup* pg() { return pg_.get(); }
   Hierarchy hier;                            // MXKVB200SetHierarchy
 
+  // the flag value of the next collective launch (kernels.h: SyncArgs::epoch): the group's counter in
+  // one-process-per-GPU mode, a process-wide one for single-process launches over any subset of the GPUs
+  uint32_t NextSyncEpoch(ProcessGroup* pg) { return pg != nullptr ? pg->NextSyncEpoch() : ++sync_epoch_; }
   std::recursive_mutex& mu() { return mu_; }
   bool auto_fence = true;
   int64_t launches = 0;                      // kernels launched by this library (bench "gpu_launches")
@@ -174,6 +179,7 @@ class Runtime {
   std::unique_ptr<ProcessGroup> pg_;
   int ndev_ = -1;
   int max_blocks_override_ = 0;
+  uint32_t sync_epoch_ = 0;
 };
 
 }  // namespace mxkv

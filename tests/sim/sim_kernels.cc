@@ -36,9 +36,10 @@ static bool MultiProcess() {
 }
 
 static void Rendezvous(const SyncArgs& s, int offset) {
-  if (!MultiProcess() || s.mode == SYNC_NONE || s.world <= 1) return;
-  uint32_t* counter = s.self + kSigFlagOff;          // block 0
-  const uint32_t flag = __atomic_load_n(counter, __ATOMIC_RELAXED) + 1;
+  if (s.mode == SYNC_NONE || s.world <= 1) return;
+  const uint32_t flag = s.epoch;                     // host-provided, the same on every participant
+  if (flag == 0) { fprintf(stderr, "[mxkv sim] collective launch without a rendezvous epoch\n"); abort(); }
+  if (!MultiProcess()) return;                       // single process: kernels run one after another
   for (int r = 0; r < s.world; ++r)
     __atomic_store_n(s.peers[r] + offset + s.rank, flag, __ATOMIC_RELEASE);
   for (int r = 0; r < s.world; ++r) {
@@ -57,7 +58,6 @@ static void Rendezvous(const SyncArgs& s, int offset) {
       }
     }
   }
-  __atomic_store_n(counter, flag, __ATOMIC_RELAXED);
 }
 static void RendezvousStart(const SyncArgs& s) { Rendezvous(s, kSigStartOff); }
 static void RendezvousEnd(const SyncArgs& s) { Rendezvous(s, kSigEndOff); }

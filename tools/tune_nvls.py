@@ -112,9 +112,10 @@ def main():
             else:
                 mx.kv.set_nvls(2)
                 grids = [int(x) for x in os.environ.get("TUNE_GRIDS", "0,148,96,64,48,32,24,16").split(",")]
-                for threads in (512, 256):
-                    for pipe in (0, 1):
-                        for unroll in (1, 2, 4, 8):
+                quick = bool(os.environ.get("TUNE_QUICK"))      # the default configuration only
+                for threads in ((512,) if quick else (512, 256)):
+                    for pipe in ((0,) if quick else (0, 1)):
+                        for unroll in ((2,) if quick else (1, 2, 4, 8)):
                             for grid in grids:
                                 if threads == 256 and grid not in (0, 148, 32):
                                     continue

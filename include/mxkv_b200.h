@@ -202,6 +202,39 @@ MXKV_DLL int MXKVB200NDArrayFromPtr(void* data, const int64_t* shape, int ndim, 
 /* Stream the embedding framework computes on for GPU dev_id (default: the legacy default
  * stream).  Engine work is ordered after what is queued there at call time. */
 MXKV_DLL int MXKVB200SetStream(int dev_id, void* cuda_stream);
+/* ---- engine ops (include/mxnet/c_api.h:3010-3127) ---------------------------------------------------------
+ * Horovod-style plug-ins wrap their work in engine ops so that it is ordered with the framework's reads and writes
+ * of the arrays involved.  This engine has no dependency graph -- ordering is by CUDA streams -- so the four entry
+ * points are served conservatively: deferred calls are issued, every engine stream is drained (a superset of the
+ * named dependencies), then the function runs on the calling thread; the Async flavours wait until the function
+ * has called `on_complete`.  `ctx_handle` points at {int dev_type; int dev_id} (mxnet::Context's layout);
+ * variable handles, `prop_handle`, `priority`, `opr_name` and `wait` are accepted and not interpreted. */
+typedef void (*EngineAsyncFunc)(void* rctx, void* on_complete, void* param);
+typedef void (*EngineSyncFunc)(void* rctx, void* param);
+typedef void (*EngineFuncParamDeleter)(void* param);
+typedef const void* ContextHandle;
+typedef void* EngineVarHandle;
+typedef const void* EngineFnPropertyHandle;
+MXKV_DLL int MXEnginePushAsync(EngineAsyncFunc async_func, void* func_param, EngineFuncParamDeleter deleter,
+                               ContextHandle ctx_handle, EngineVarHandle const_vars_handle, int num_const_vars,
+                               EngineVarHandle mutable_vars_handle, int num_mutable_vars,
+                               EngineFnPropertyHandle prop_handle, int priority, const char* opr_name, bool wait);
+MXKV_DLL int MXEnginePushSync(EngineSyncFunc sync_func, void* func_param, EngineFuncParamDeleter deleter,
+                              ContextHandle ctx_handle, EngineVarHandle const_vars_handle, int num_const_vars,
+                              EngineVarHandle mutable_vars_handle, int num_mutable_vars,
+                              EngineFnPropertyHandle prop_handle, int priority, const char* opr_name);
+MXKV_DLL int MXEnginePushAsyncND(EngineAsyncFunc async_func, void* func_param, EngineFuncParamDeleter deleter,
+                                 ContextHandle ctx_handle, NDArrayHandle* const_nds_handle, int num_const_nds,
+                                 NDArrayHandle* mutable_nds_handle, int num_mutable_nds,
+                                 EngineFnPropertyHandle prop_handle, int priority, const char* opr_name, bool wait);
+MXKV_DLL int MXEnginePushSyncND(EngineSyncFunc sync_func, void* func_param, EngineFuncParamDeleter deleter,
+                                ContextHandle ctx_handle, NDArrayHandle* const_nds_handle, int num_const_nds,
+                                NDArrayHandle* mutable_nds_handle, int num_mutable_nds,
+                                EngineFnPropertyHandle prop_handle, int priority, const char* opr_name);
+/* The callback an EngineAsyncFunc receives as `on_complete`: call it once, from any thread, when the work is done
+ * (the reference hands out an engine::CallbackOnComplete*; its one operation is this call). */
+MXKV_DLL void MXKVB200EngineOnComplete(void* on_complete);
+
 /* The engine's own CUDA stream for GPU dev_id (cudaStream_t), e.g. to record timing events on the
  * stream the kernels are launched on. */
 MXKV_DLL int MXKVB200GetEngineStream(int dev_id, void** out);

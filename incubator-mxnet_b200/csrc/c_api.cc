@@ -1,6 +1,8 @@
 // c_api.cc -- extern "C" shims: marshal C arrays into the engine and translate exceptions
 // into the 0 / -1 + MXGetLastError() contract (API_BEGIN/API_END,
 // include/mxnet/c_api_error.h:40-58; KVStore marshalling src/c_api/c_api.cc:2771-3204).
+#include <condition_variable>
+#include <mutex>
 #include "../../include/mxkv_b200.h"
 #include <algorithm>
 #include <cstring>
@@ -619,6 +621,65 @@ int MXKVB200SetNvlsTuning(int unroll, int pipe, int grid, int threads) {
   if (grid >= 0) rt->nvls_grid = grid;
   if (threads == 128 || threads == 256 || threads == 512) rt->nvls_threads = threads;
   API_END();
+}
+
+// ---- engine ops: include/mxnet/c_api.h:3010-3127, served without a dependency graph (include/mxkv_b200.h) ----
+namespace {
+struct OnComplete {
+  std::mutex mu;
+  std::condition_variable cv;
+  bool done = false;
+};
+void DrainForEngineOp() {
+  FlushAllDeferred();
+  Runtime::Get()->WaitAll();
+}
+int RunSync(EngineSyncFunc fn, void* param, EngineFuncParamDeleter deleter) {
+  API_BEGIN();
+  MXKV_CHECK(fn != nullptr) << "null engine function";
+  DrainForEngineOp();
+  fn(nullptr, param);
+  if (deleter) deleter(param);
+  API_END();
+}
+int RunAsync(EngineAsyncFunc fn, void* param, EngineFuncParamDeleter deleter) {
+  API_BEGIN();
+  MXKV_CHECK(fn != nullptr) << "null engine function";
+  DrainForEngineOp();
+  OnComplete oc;
+  fn(nullptr, &oc, param);
+  {
+    std::unique_lock<std::mutex> lk(oc.mu);
+    oc.cv.wait(lk, [&oc] { return oc.done; });
+  }
+  if (deleter) deleter(param);
+  API_END();
+}
+}  // namespace
+
+void MXKVB200EngineOnComplete(void* on_complete) {
+  OnComplete* oc = static_cast<OnComplete*>(on_complete);
+  if (oc == nullptr) return;
+  std::lock_guard<std::mutex> lk(oc->mu);
+  oc->done = true;
+  oc->cv.notify_all();
+}
+
+int MXEnginePushAsync(EngineAsyncFunc async_func, void* func_param, EngineFuncParamDeleter deleter, ContextHandle,
+                      EngineVarHandle, int, EngineVarHandle, int, EngineFnPropertyHandle, int, const char*, bool) {
+  return RunAsync(async_func, func_param, deleter);
+}
+int MXEnginePushSync(EngineSyncFunc sync_func, void* func_param, EngineFuncParamDeleter deleter, ContextHandle,
+                     EngineVarHandle, int, EngineVarHandle, int, EngineFnPropertyHandle, int, const char*) {
+  return RunSync(sync_func, func_param, deleter);
+}
+int MXEnginePushAsyncND(EngineAsyncFunc async_func, void* func_param, EngineFuncParamDeleter deleter, ContextHandle,
+                        NDArrayHandle*, int, NDArrayHandle*, int, EngineFnPropertyHandle, int, const char*, bool) {
+  return RunAsync(async_func, func_param, deleter);
+}
+int MXEnginePushSyncND(EngineSyncFunc sync_func, void* func_param, EngineFuncParamDeleter deleter, ContextHandle,
+                       NDArrayHandle*, int, NDArrayHandle*, int, EngineFnPropertyHandle, int, const char*) {
+  return RunSync(sync_func, func_param, deleter);
 }
 
 int MXKVB200SetStream(int dev_id, void* cuda_stream) {

@@ -389,3 +389,36 @@ def test_prototypes_match_the_reference_header():
     assert len(shared) >= 50, len(shared)
     for n in shared:
         assert mine[n] == ref[n], (n, mine[n], ref[n])
+
+
+def test_engine_ops_run_in_order_on_the_calling_thread():
+    """MXEnginePushSync[ND] / MXEnginePushAsync[ND] (include/mxnet/c_api.h:3010-3127; what the Horovod-style plug-ins
+    wrap their work in): served conservatively -- drain, then run on the calling thread; the Async flavours return
+    only after the function has called on_complete (here from another thread)."""
+    import ctypes
+    import threading
+    import mxnet_b200  # noqa: F401
+    from mxnet_b200.base import _LIB
+    seen = []
+    SYNC = ctypes.CFUNCTYPE(None, ctypes.c_void_p, ctypes.c_void_p)
+    ASYNC = ctypes.CFUNCTYPE(None, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p)
+    DEL = ctypes.CFUNCTYPE(None, ctypes.c_void_p)
+    ctx = (ctypes.c_int * 2)(1, 0)                       # {dev_type = cpu, dev_id = 0}
+
+    sync_fn = SYNC(lambda rctx, param: seen.append(("sync", param)))
+    deleter = DEL(lambda param: seen.append(("deleted", param)))
+    rc = _LIB.MXEnginePushSyncND(sync_fn, ctypes.c_void_p(7), deleter, ctx, None, 0, None, 0, None, 0, b"op")
+    assert rc == 0 and seen == [("sync", 7), ("deleted", 7)]
+
+    def later(on_complete):
+        seen.append("worker")
+        _LIB.MXKVB200EngineOnComplete(ctypes.c_void_p(on_complete))
+
+    def async_body(rctx, on_complete, param):
+        seen.append(("async", param))
+        threading.Thread(target=later, args=(on_complete,)).start()
+    _LIB.MXKVB200EngineOnComplete.restype = None
+    async_fn = ASYNC(async_body)
+    rc = _LIB.MXEnginePushAsync(async_fn, ctypes.c_void_p(9), None, ctx, None, 0, None, 0, None, 0, None, False)
+    assert rc == 0 and seen[2:] == [("async", 9), "worker"]
+    assert _LIB.MXEnginePushSync(None, None, None, ctx, None, 0, None, 0, None, 0, None) != 0     # null function: an error, not a crash

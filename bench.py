@@ -185,63 +185,109 @@ def nvlink_counters(gpu_index):
 # clocks
 # ---------------------------------------------------------------------------
 class ClockSampler(object):
+    """SM clock, max clock and throttle reasons of one GPU while the timed region runs.
+
+    The samples come from NVML calls made by a thread of this process (clock info + current clocks-event reasons,
+    every 100 ms) -- NOT from an `nvidia-smi -lms` loop: on 8 GPUs that loop, at the 20 ms period round 2 first
+    used, slowed the NVSwitch-multicast exchange from 0.79 to 1.21 ms per step (profiles/r02_diag_n8_sampler.txt;
+    one GPU's queries stall all eight through the rendezvous), while at N = 1 / 2 it cost nothing.  Only when
+    pynvml is missing does the sampler fall back to `nvidia-smi -lms 250`."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    PERIOD_S = 0.1
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
-        self.lines = []          # (host time, csv line)
+        self.samples = []        # (host time, sm MHz, max sm MHz, set of reasons)
         self.proc = None
+        self.thread = None
+        self.stop_flag = False
+        self.how = None
 
-    def start(self):
+    def _nvml_loop(self, pynvml, h):
+        masks = [("hw_slowdown", getattr(pynvml, "nvmlClocksEventReasonHwSlowdown", 0x8)),
+                 ("hw_thermal_slowdown", getattr(pynvml, "nvmlClocksEventReasonHwThermalSlowdown", 0x40)),
+                 ("sw_thermal_slowdown", getattr(pynvml, "nvmlClocksEventReasonSwThermalSlowdown", 0x20)),
+                 ("sw_power_cap", getattr(pynvml, "nvmlClocksEventReasonSwPowerCap", 0x4))]
+        get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            getattr(pynvml, "nvmlDeviceGetCurrentClocksThrottleReasons")
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "20"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
+            mx_clock = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
         except Exception:
-            self.proc = None
+            mx_clock = None
+        while not self.stop_flag:
+            try:
+                sm = float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                bits = int(get_reasons(h))
+                self.samples.append((time.time(), sm, mx_clock, {n for n, m in masks if bits & m}))
+            except Exception:
+                pass
+            time.sleep(self.PERIOD_S)
 
-    def _read(self):
+    def _smi_loop(self):
         for line in self.proc.stdout:
-            self.lines.append((time.time(), line.strip()))
-
-    def wait_first(self, timeout=10.0):
-        """nvidia-smi needs ~1 s before its first line: do not start the timed region before it samples"""
-        t0 = time.time()
-        while self.proc is not None and not self.lines and time.time() - t0 < timeout:
-            time.sleep(0.02)
-
-    def count(self, t0, t1):
-        return sum(1 for t, _ in self.lines if t0 <= t <= t1)
-
-    def stop(self, t0, t1):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            pass
-        sm, mx_, reasons = [], [], set()
-        for t, ln in self.lines:
-            if not (t0 <= t <= t1):
-                continue
-            f = [x.strip() for x in ln.split(",")]
+            f = [x.strip() for x in line.split(",")]
             if len(f) < 9:
                 continue
             try:
-                sm.append(float(f[1])); mx_.append(float(f[2]))
+                sm, mxc = float(f[1]), float(f[2])
             except ValueError:
                 continue
             names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-            for name, val in zip(names, f[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx_) if mx_ else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+            self.samples.append((time.time(), sm, mxc, {n for n, v in zip(names, f[5:9]) if v.lower().startswith("active")}))
+
+    def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+            self.how = "NVML calls from a thread of this process, every %d ms" % int(self.PERIOD_S * 1e3)
+            self.thread = threading.Thread(target=self._nvml_loop, args=(pynvml, h), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "250"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.how = "nvidia-smi -lms 250"
+            self.thread = threading.Thread(target=self._smi_loop, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def active(self):
+        return self.thread is not None
+
+    def wait_first(self, timeout=10.0):
+        """do not start the timed region before the sampler delivers (nvidia-smi needs ~1 s for its first line)"""
+        t0 = time.time()
+        while self.active() and not self.samples and time.time() - t0 < timeout:
+            time.sleep(0.02)
+
+    def count(self, t0, t1):
+        return sum(1 for s in self.samples if t0 <= s[0] <= t1)
+
+    def stop(self, t0, t1):
+        if not self.active():
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock sampler available"], "samples": 0}
+        self.stop_flag = True
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                pass
+        win = [s for s in self.samples if t0 <= s[0] <= t1]
+        sm = [s[1] for s in win]
+        mxc = [s[2] for s in win if s[2] is not None]
+        reasons = set()
+        for s in win:
+            reasons |= s[3]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mxc) if mxc else None,
+                "reasons": sorted(reasons), "samples": len(sm), "how": self.how}
 
 
 # ---------------------------------------------------------------------------
@@ -962,9 +1008,9 @@ def main():
     ms_step = ms_total / args.steps
     value = world * 2 * S / (ms_step * 1e-3) / 1e9
     # clocks: the timed window is a few hundred ms at most -- every rank keeps the SAME steps running (untimed)
-    # until the GPU has been under this load for ~0.4 s, so that nvidia-smi's 20 ms sampling sees it; the record
-    # covers both windows and says so
-    soak_steps = int(min(5000, max(0.0, 400.0 - ms_total) / max(ms_step, 1e-3)))
+    # until the GPU has been under this load for ~0.6 s, so that the 100 ms sampler sees it several times; the
+    # record covers both windows and says so
+    soak_steps = int(min(5000, max(0.0, 600.0 - ms_total) / max(ms_step, 1e-3)))
     for _ in range(soak_steps):
         step()
     torch.cuda.synchronize(); env.barrier()
@@ -973,7 +1019,7 @@ def main():
     if rank == 0:
         clocks = sampler.stop(t_host0, t_host2)
         clocks["window"] = "timed region (%d steps)%s" % (
-            args.steps, " + %d identical untimed steps (the sampler needs ~0.4 s under load)" % soak_steps if soak_steps else "")
+            args.steps, " + %d identical untimed steps (~0.6 s under load for the 100 ms sampler)" % soak_steps if soak_steps else "")
 
     # ---- roofline for the dominant (only) kernel ------------------------------------------------
     peaks = measured_peaks()

@@ -249,16 +249,24 @@ kv_dense_bulk_kernel(DenseLaunch L) {
   // 0.945 of the measured HBM peak on the 256 MB sweep keys) but every block meets every key of the work list and
   // reloads a 400-byte descriptor each time, which cost a fifth of the kernel on a 199-key model (BERT-base:
   // 0.78).  A contiguous range per block has the opposite profile (0.83 / 0.90).  Small groups keep the window
-  // narrow and divide the descriptor switches by G (profiles/r02_tune_bulk_group.txt).
+  // narrow and divide the descriptor switches by G (profiles/r02_tune_bulk_group.txt); the host groups only work
+  // lists of many keys (kvstore.cc: LaunchWorks) and keeps G = 1 for the rest.
   const int64_t G = L.bulk_group > 0 ? L.bulk_group : 1;
-  const int64_t ngroups = (L.total_chunks + G - 1) / G;
-  const int64_t my_groups = static_cast<int64_t>(blockIdx.x) < ngroups ? (ngroups - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-  int64_t ntiles = my_groups * G;
-  if (my_groups > 0) {      // the very last group of the list may be short
-    const int64_t last_group = blockIdx.x + (my_groups - 1) * gridDim.x;
-    if (last_group == ngroups - 1) ntiles -= ngroups * G - L.total_chunks;
+  int64_t ntiles;
+  if (G == 1) {             // the plain strided walk, without the divisions of the grouped one
+    ntiles = static_cast<int64_t>(blockIdx.x) < L.total_chunks ? (L.total_chunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  } else {
+    const int64_t ngroups = (L.total_chunks + G - 1) / G;
+    const int64_t my_groups = static_cast<int64_t>(blockIdx.x) < ngroups ? (ngroups - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    ntiles = my_groups * G;
+    if (my_groups > 0) {      // the very last group of the list may be short
+      const int64_t last_group = blockIdx.x + (my_groups - 1) * gridDim.x;
+      if (last_group == ngroups - 1) ntiles -= ngroups * G - L.total_chunks;
+    }
   }
-  auto tile_of = [&](int64_t i) -> int64_t { return ((i / G) * gridDim.x + blockIdx.x) * G + i % G; };
+  auto tile_of = [&](int64_t i) -> int64_t {
+    return G == 1 ? blockIdx.x + i * gridDim.x : ((i / G) * gridDim.x + blockIdx.x) * G + i % G;
+  };
   auto issue = [&](int64_t i) {       // thread 0 only: request every input stream of tile i
     const int64_t c = tile_of(i);
     int lo = 0, hi = L.nworks - 1;

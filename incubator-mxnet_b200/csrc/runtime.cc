@@ -181,6 +181,7 @@ Runtime::Runtime() {
   if (chunk_elems < 128) chunk_elems = 128;
   chunk_elems = (chunk_elems + 127) / 128 * 128;
   bulk_mode = static_cast<int>(EnvInt("MXKV_B200_BULK", 1));
+  bulk_group_forced = std::getenv("MXKV_B200_BULK_GROUP") != nullptr;
   bulk_group = static_cast<int>(EnvInt("MXKV_B200_BULK_GROUP", bulk_group));
   if (bulk_group < 1) bulk_group = 1;
   nvls_mode = static_cast<int>(EnvInt("MXKV_B200_NVLS", 1));

@@ -170,7 +170,8 @@ class Runtime {
                                              // (profiles/r02_nvls_tune_n8.txt)
   int nvls_threads = 512;                    // MXKV_B200_NVLS_THREADS: its block size (128 | 256 | 512)
   int bulk_mode = 1;                         // MXKV_B200_BULK: 0 off, 1 auto (<= 2 sources), 2 whenever eligible
-  int bulk_group = 4;                        // MXKV_B200_BULK_GROUP: consecutive tiles per block of the staged kernel
+  int bulk_group = 4;                        // MXKV_B200_BULK_GROUP: consecutive tiles per block of the staged kernel,
+  bool bulk_group_forced = false;            // for work lists of >= 32 keys (always when the variable is set)
  private:
   Runtime();
   std::recursive_mutex mu_;

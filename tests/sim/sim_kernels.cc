@@ -39,7 +39,24 @@ static void Rendezvous(const SyncArgs& s, int offset) {
   if (s.mode == SYNC_NONE || s.world <= 1) return;
   const uint32_t flag = s.epoch;                     // host-provided, the same on every participant
   if (flag == 0) { fprintf(stderr, "[mxkv sim] collective launch without a rendezvous epoch\n"); abort(); }
-  if (!MultiProcess()) return;                       // single process: kernels run one after another
+  if (!MultiProcess()) {
+    // single process: kernels run one after another, so nobody can wait -- but the protocol can be CHECKED: the n
+    // participants of a collective launch must all carry the same flag value, a value this pad has not seen before
+    // (round 1's per-device counters violated the first rule as soon as the set of GPUs changed between launches;
+    // the first 8-GPU hardware run dead-locked on it)
+    static std::map<const uint32_t*, uint32_t> last_on_pad[2];
+    static std::map<uint32_t, std::pair<int, int>> open_launch[2];      // epoch -> (world, participants seen)
+    const int which = offset == kSigStartOff ? 0 : 1;
+    uint32_t& last = last_on_pad[which][s.self];
+    if (flag <= last) { fprintf(stderr, "[mxkv sim] rendezvous epoch %u reused on a pad (last %u)\n", flag, last); abort(); }
+    last = flag;
+    auto& ol = open_launch[which][flag];
+    if (ol.second == 0) ol.first = s.world;
+    if (ol.first != s.world) { fprintf(stderr, "[mxkv sim] participants of one launch disagree on its size\n"); abort(); }
+    if (++ol.second == s.world) open_launch[which].erase(flag);
+    if (open_launch[which].size() > 64) { fprintf(stderr, "[mxkv sim] collective launches left incomplete\n"); abort(); }
+    return;
+  }
   for (int r = 0; r < s.world; ++r)
     __atomic_store_n(s.peers[r] + offset + s.rank, flag, __ATOMIC_RELEASE);
   for (int r = 0; r < s.world; ++r) {

@@ -245,3 +245,51 @@ def test_scheduler_known_points():
     np.testing.assert_almost_equal(cos(0), 3)
     np.testing.assert_almost_equal(cos(1000), 0.1)
     assert cos(500) > 1.5
+
+
+def test_bench_helpers_without_a_gpu():
+    """bench.py's host-side pieces: deterministic synthetic data (what lets rank 0 regenerate every rank's gradients for
+    the parity check), the workload key sets, and the in-process NVML clock sampler driven by a stand-in module."""
+    import importlib
+    import os
+    import sys
+    import time
+    import types
+    import numpy as np
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    bench = importlib.import_module("bench")
+    sweep = bench.keyset("sweep")
+    assert [bench.nelem(s) for s in sweep] == [1 << p for p in range(10, 27, 2)]
+    assert len(bench.keyset("resnet50")) == 193 and sum(bench.nelem(s) for s in bench.keyset("resnet50")) == 25575912
+    assert len(bench.keyset("bert")) == 199
+    small = [(1000,), (1 << 21,)]
+    a, b = bench.rank_grads(3, small), bench.rank_grads(3, small)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b)) and not np.array_equal(a[1], bench.rank_grads(4, small)[1])
+    big = a[1]                                         # above 2^20 elements: a random block of 1 000 003 elements, repeated
+    assert np.array_equal(big[:1000003][:1000], big[1000003:1000003 + 1000]) and big.dtype == np.float32
+    # clock sampler on a stand-in pynvml
+    fake = types.ModuleType("pynvml")
+    fake.NVML_CLOCK_SM = 1
+    fake.nvmlInit = lambda: None
+    fake.nvmlDeviceGetHandleByIndex = lambda i: i
+    fake.nvmlDeviceGetMaxClockInfo = lambda h, c: 1965
+    fake.nvmlDeviceGetClockInfo = lambda h, c: 1950
+    fake.nvmlDeviceGetCurrentClocksEventReasons = lambda h: 0x4 | 0x40
+    saved = sys.modules.get("pynvml")
+    sys.modules["pynvml"] = fake
+    try:
+        s = bench.ClockSampler(0)
+        s.start()
+        s.wait_first()
+        t0 = time.time(); time.sleep(0.35); t1 = time.time()
+        rec = s.stop(t0, t1)
+    finally:
+        if saved is not None:
+            sys.modules["pynvml"] = saved
+        else:
+            del sys.modules["pynvml"]
+    assert rec["samples"] >= 2 and rec["sm_mhz"] == 1950.0 and rec["sm_max_mhz"] == 1965.0
+    assert rec["reasons"] == ["hw_thermal_slowdown", "sw_power_cap"] and "NVML" in rec["how"]
+    info = bench.bind_to_gpu_numa(0)                   # no driver here: a description, never an exception
+    assert info["gpu"] == 0

@@ -312,6 +312,43 @@ MXKV_DLL int MXKVB200SetNvls(int mode);
  * Every rank of the process group must use the same values. */
 MXKV_DLL int MXKVB200SetNvlsTuning(int unroll, int pipe, int grid, int threads);
 
+
+/* ---- MXNET_KVSTORE_USETREE=1: the reduction trees of CommDeviceTree (src/kvstore/comm_tree.h:50-325) ----------
+ * A store of a `device` type created with MXNET_KVSTORE_USETREE=1 adds the values of a key pairwise up the binary
+ * trees the reference's solver builds from the GPUs' link matrix (src/kvstore/gpu_topology.h:1111-1157), slice by
+ * slice for keys above MXNET_KVSTORE_TREE_ARRAY_BOUND elements (comm_tree.h:203-234) -- same bits as the reference's
+ * tree mode; the transport stays this library's one-pass kernel.  MXNET_KVSTORE_TREE_BACKTRACK and
+ * MXNET_KVSTORE_TREE_LINK_USAGE_PENALTY are read like the reference reads them (comm_tree.h:52-57).
+ * The entry points below expose the pieces so that a test (or a maintainer) can compare them with the reference:
+ * the link matrix GetP2PWeight would produce from the driver's answers (gpu_topology.h:137-253) ... */
+MXKV_DLL int MXKVB200TopologyLinkWeights(int n, const int* perf_rank, const int* can_access, float* weights_out);
+/* ... the same, querying the driver for the CUDA devices devs[0..n) (MXKV_B200_TREE_LINKS overrides) ... */
+MXKV_DLL int MXKVB200TopologyQueryLinks(int n, const int* devs, float* weights_out);
+/* ... ComputeTrees: n trees in array form, tree r at topo_out[r * *topo_len ...] (2^(depth+1) - 1 entries each),
+ * level starts at scan_out[r * *scan_len ...] (depth + 2 entries each); caps are in entries ... */
+MXKV_DLL int MXKVB200TopologyComputeTrees(const float* weights, int n, float alpha, int backtrack, uint64_t* topo_out,
+                                          int topo_cap, int* topo_len, uint64_t* scan_out, int scan_cap, int* scan_len,
+                                          int* depth);
+/* ... one Kernighan-Lin pass (KernighanLin, gpu_topology.h:326-480) with std::mt19937(seed): returns *stop,
+ * updates partition[0..n) and *num_partitions, writes (first, second) pairs ... */
+MXKV_DLL int MXKVB200TopologyBisect(const float* weights, int n, int* partition, int* num_partitions, int* pairs_out,
+                                    int pairs_cap, int* n_pairs, uint32_t seed, int* stop);
+/* ... Postprocess (:746-770), ComputeTreeWeight (:778-813), IsValid (:727-791), IsConnected (:96-121) ... */
+MXKV_DLL int MXKVB200TopologyFoldRepeats(int* leaves, int len, int n, int depth);
+MXKV_DLL int MXKVB200TopologyTreeWeight(const float* weights, const int* leaves, int len, int n, int depth, int penalty,
+                                        float* out);
+MXKV_DLL int MXKVB200TopologyAdmissible(const float* weights, const int* state, int len, int n, int row, int depth,
+                                        int* out);
+MXKV_DLL int MXKVB200TopologyConnected(const float* weights, int n, int* out);
+/* ... and the order in which the kernel adds the n values of an element for one tree (topology.h: ReduceProgram):
+ * leaves_out[0..n) = participants in the order their values are taken, *prog_out = the add schedule. */
+MXKV_DLL int MXKVB200TopologyReduceProgram(const uint64_t* topo, int topo_len, const uint64_t* scan, int scan_len, int n,
+                                           int* leaves_out, uint32_t* prog_out);
+/* Evaluates a reduce program on the host with the kernel's own code (csrc/tree_math.h compiled for the CPU):
+ * out[e] = the tree sum of srcs[leaf k][e] taken in program order, float32.  Test instrumentation. */
+MXKV_DLL int MXKVB200TopologyRunProgram(const float* const* srcs_in_leaf_order, int n, uint32_t prog, int64_t count,
+                                        float* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -18,6 +18,7 @@ from . import kvstore
 from . import kvstore as kv
 from .kvstore import KVStore, KVStoreBase, create
 from . import dist
+from . import topology
 from .trainer import Trainer
 from . import gluon
 from . import context

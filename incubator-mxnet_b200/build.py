@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libmxkv_b200.so")
-SOURCES = ["kernels.cu", "rsp_kernels.cu", "norm_kernels.cu", "kvstore_norm.cc", "runtime.cc", "vmm_arena.cc", "ndarray.cc", "kvstore.cc", "kvstore_rsp.cc", "c_api.cc"]
+SOURCES = ["kernels.cu", "tree_kernels.cu", "rsp_kernels.cu", "norm_kernels.cu", "kvstore_norm.cc", "runtime.cc", "vmm_arena.cc", "topology.cc", "ndarray.cc", "kvstore.cc", "kvstore_rsp.cc", "c_api.cc"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC,-fvisibility=hidden,-Wall", "--threads", "4"]

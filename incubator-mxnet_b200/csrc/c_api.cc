@@ -8,6 +8,9 @@
 #include <cstring>
 #include "dlpack_abi.h"
 #include "kvstore.h"
+#include <random>
+#include "topology.h"
+#include "tree_math.h"
 
 using namespace mxkv;
 
@@ -739,7 +742,7 @@ int MXKVB200GetPlanHits(KVStoreHandle handle, int64_t* out) {
 
 int MXKVB200GetVariantLaunchCount(int variant, int64_t* out) {
   API_BEGIN();
-  MXKV_CHECK(variant >= 0 && variant < 3) << "variant: 0 per-thread, 1 staged (bulk), 2 multicast (NVLS)";
+  MXKV_CHECK(variant >= 0 && variant < 4) << "variant: 0 per-thread, 1 staged (bulk), 2 multicast (NVLS), 3 tree order";
   *out = Runtime::Get()->variant_launches[variant];
   API_END();
 }
@@ -800,6 +803,116 @@ int MXKVB200NDArrayCreateSymmetric(const int64_t* shape, int ndim, int dtype, ND
   std::vector<int64_t> s(shape, shape + ndim);
   const int dev = pg ? pg->dev() : 0;
   *out = new NDHandle(NDArray::Empty(s, Context{kGPU, dev}, dtype, /*symmetric=*/pg != nullptr));
+  API_END();
+}
+
+
+// ---- MXNET_KVSTORE_USETREE: the solver's pieces (topology.h) ------------------------------------------------
+static std::vector<float> LinkMatrixArg(const float* w, int n) {
+  MXKV_CHECK(n >= 1 && n <= 64 && w != nullptr) << "link matrix of " << n << " GPUs";
+  return std::vector<float>(w, w + static_cast<size_t>(n) * n);
+}
+
+int MXKVB200TopologyLinkWeights(int n, const int* perf_rank, const int* can_access, float* out) {
+  API_BEGIN();
+  MXKV_CHECK(n >= 1 && n <= 64);
+  const size_t nn = static_cast<size_t>(n) * n;
+  const std::vector<float> W = topo::LinkWeights(n, std::vector<int>(perf_rank, perf_rank + nn),
+                                                 std::vector<int>(can_access, can_access + nn));
+  std::copy(W.begin(), W.end(), out);
+  API_END();
+}
+
+int MXKVB200TopologyQueryLinks(int n, const int* devs, float* out) {
+  API_BEGIN();
+  MXKV_CHECK(n >= 1 && n <= 64);
+  const std::vector<float> W = topo::QueryLinkWeights(std::vector<int>(devs, devs + n));
+  std::copy(W.begin(), W.end(), out);
+  API_END();
+}
+
+int MXKVB200TopologyComputeTrees(const float* weights, int n, float alpha, int backtrack, uint64_t* topo_out, int topo_cap,
+                                 int* topo_len, uint64_t* scan_out, int scan_cap, int* scan_len, int* depth) {
+  API_BEGIN();
+  topo::TreeSet ts;
+  topo::ComputeTrees(LinkMatrixArg(weights, n), n, alpha, backtrack != 0, &ts);
+  const size_t tl = ts.topo[0].size(), sl = ts.scan[0].size();
+  MXKV_CHECK(static_cast<size_t>(topo_cap) >= tl * n && static_cast<size_t>(scan_cap) >= sl * n) << "output too small";
+  for (int r = 0; r < n; ++r) {
+    MXKV_CHECK(ts.topo[r].size() == tl && ts.scan[r].size() == sl) << "trees of different depth";
+    std::copy(ts.topo[r].begin(), ts.topo[r].end(), topo_out + r * tl);
+    std::copy(ts.scan[r].begin(), ts.scan[r].end(), scan_out + r * sl);
+  }
+  *topo_len = static_cast<int>(tl);
+  *scan_len = static_cast<int>(sl);
+  *depth = ts.depth;
+  API_END();
+}
+
+int MXKVB200TopologyBisect(const float* weights, int n, int* partition, int* num_partitions, int* pairs_out, int pairs_cap,
+                           int* n_pairs, uint32_t seed, int* stop) {
+  API_BEGIN();
+  std::vector<int> color(partition, partition + n);
+  std::vector<std::pair<int, int>> pairs;
+  std::mt19937 gen(seed);
+  *stop = topo::BisectClusters(LinkMatrixArg(weights, n), &color, num_partitions, &pairs, &gen) ? 1 : 0;
+  MXKV_CHECK(static_cast<int>(pairs.size()) <= pairs_cap);
+  std::copy(color.begin(), color.end(), partition);
+  for (size_t i = 0; i < pairs.size(); ++i) { pairs_out[2 * i] = pairs[i].first; pairs_out[2 * i + 1] = pairs[i].second; }
+  *n_pairs = static_cast<int>(pairs.size());
+  API_END();
+}
+
+int MXKVB200TopologyFoldRepeats(int* leaves, int len, int n, int depth) {
+  API_BEGIN();
+  std::vector<int> r(leaves, leaves + len);
+  topo::FoldRepeats(&r, n, depth);
+  std::copy(r.begin(), r.end(), leaves);
+  API_END();
+}
+
+int MXKVB200TopologyTreeWeight(const float* weights, const int* leaves, int len, int n, int depth, int penalty, float* out) {
+  API_BEGIN();
+  *out = topo::TreeWeight(LinkMatrixArg(weights, n), std::vector<int>(leaves, leaves + len), n, depth, penalty != 0);
+  API_END();
+}
+
+int MXKVB200TopologyAdmissible(const float* weights, const int* state, int len, int n, int row, int depth, int* out) {
+  API_BEGIN();
+  *out = topo::Admissible(LinkMatrixArg(weights, n), std::vector<int>(state, state + len), n, row, depth) ? 1 : 0;
+  API_END();
+}
+
+int MXKVB200TopologyConnected(const float* weights, int n, int* out) {
+  API_BEGIN();
+  *out = topo::LinksConnected(LinkMatrixArg(weights, n), n) ? 1 : 0;
+  API_END();
+}
+
+int MXKVB200TopologyReduceProgram(const uint64_t* topo_row, int topo_len, const uint64_t* scan_row, int scan_len, int n,
+                                  int* leaves_out, uint32_t* prog_out) {
+  API_BEGIN();
+  const topo::ReduceProgram rp = topo::ReduceProgramOf(std::vector<size_t>(topo_row, topo_row + topo_len),
+                                                       std::vector<size_t>(scan_row, scan_row + scan_len), scan_len - 2, n);
+  for (int i = 0; i < rp.n; ++i) leaves_out[i] = rp.leaf[i];
+  *prog_out = rp.prog;
+  API_END();
+}
+
+int MXKVB200TopologyRunProgram(const float* const* srcs, int n, uint32_t prog, int64_t count, float* out) {
+  API_BEGIN();
+  MXKV_CHECK(n >= 1 && n <= kMaxRanks);
+  for (int64_t e = 0; e < count; ++e) {
+    TreeSum<float, 1> ts;
+    ts.begin(prog);
+    for (int k = 0; k < n; ++k) {
+      const float x[1] = {srcs[k][e]};
+      ts.take(x, TreeAddF32());
+    }
+    float y[1];
+    ts.result(y);
+    out[e] = y[0];
+  }
   API_END();
 }
 

@@ -776,6 +776,7 @@ int BulkPlan(int device, int opt, int multi_precision, int arrays, int* tile_ele
 }
 
 int LaunchDense(const DenseLaunch& L, cudaStream_t stream) {
+  if (L.order == ORDER_TREE) return LaunchDenseTree(L, stream);
   if (L.nvls) {
     NvlsKernelFn nf = pick_nvls(L.opt, L.multi_precision, L.nvls_unroll, L.nvls_pipe);
     if (nf == nullptr || L.dtype != kFloat32 || L.sync.mode == SYNC_NONE) return static_cast<int>(cudaErrorInvalidValue);

@@ -44,8 +44,10 @@ inline bool IsNormOpt(int kind) { return kind == OPT_LAMB || kind == OPT_LANS ||
 
 enum SumOrder : int {
   ORDER_DEVICE = 0,  // ((in0+in1)+in2)+...                  ndarray_function-inl.h:457-486
-  ORDER_COMMCPU = 1  // in0 + (((in1+in2)+in3)+in4), groups of 4   comm.h:359-393
+  ORDER_COMMCPU = 1, // in0 + (((in1+in2)+in3)+in4), groups of 4   comm.h:359-393
+  ORDER_TREE = 2     // pairwise up a binary tree, per entry: TensorWork::tree_prog   comm_tree.h:91-177 (topology.h)
 };
+constexpr int kTreeStack = 3;   // partial sums pending at once in a reduction tree over <= kMaxRanks values (tree_math.h)
 
 enum SyncMode : int {
   SYNC_NONE = 0,      // all pointers local to this launch's device
@@ -68,7 +70,10 @@ struct alignas(16) TensorWork {
   int n_src;
   int n_out;
   int pad_;          // bit 0: every pointer 16-byte aligned; bit 1: eligible for the staged variant
-  int n_mc;          // NVLS launches: the last n_mc entries of out[] are multicast addresses
+  union {
+    int n_mc;            // NVLS launches: the last n_mc entries of out[] are multicast addresses
+    uint32_t tree_prog;  // ORDER_TREE launches (never NVLS): when to add which partial sums, src[] being in the
+  };                     //   tree's leaf order (topology.h: ReduceProgram)
   int reserved_;     // host side only: the key this entry belongs to
 };
 static_assert(sizeof(TensorWork) == 400, "TensorWork layout");
@@ -126,6 +131,10 @@ struct DenseLaunch {
 // returns cudaError_t as int; never throws
 int LaunchDense(const DenseLaunch& L, cudaStream_t stream);
 int DenseMaxGrid(int device, int threads);   // resident-block capacity of the dense kernel
+// L.order == ORDER_TREE (tree_kernels.cu; LaunchDense forwards): per-thread transport, additions in the order of
+// every entry's tree_prog.  Same residency as kv_dense_kernel (DenseMaxGrid), never the staged or multicast variant.
+int LaunchDenseTree(const DenseLaunch& L, cudaStream_t stream);
+int TreeKernelAvailable(int dtype, int opt, int multi_precision);
 // Plan the shared-memory staged variant for a float32 launch with `arrays` staged input streams per
 // tile: picks tile elements / stages and returns the resident grid capacity (0: not applicable).
 int BulkPlan(int device, int opt, int multi_precision, int arrays, int* tile_elems, int* stages);

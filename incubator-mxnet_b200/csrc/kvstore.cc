@@ -4,6 +4,8 @@
 #include "norm_kernels.h"
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <set>
 
@@ -44,6 +46,91 @@ KVStore::KVStore(const std::string& type) : type_(Lower(type)) {   // kvstore.cc
   device_mode_ = solo_ || dist || t.find("device") != std::string::npos || t.find("nccl") != std::string::npos;
   order_ = device_mode_ ? ORDER_DEVICE : ORDER_COMMCPU;
   plan_mode_ = static_cast<int>(EnvInt("MXKV_B200_PLAN", 1));
+  // kvstore_local.h:74-82: a store with device-side reduction takes CommDeviceTree instead of CommDevice when
+  // MXNET_KVSTORE_USETREE is set; its knobs are read once, where the reference's constructor reads them
+  // (comm_tree.h:52-57).  Multi-node stores keep their own two-phase sum.
+  if (!solo_ && !hier_ && t.find("device") != std::string::npos && EnvInt("MXNET_KVSTORE_USETREE", 0) != 0) {
+    tree_ = true;
+    tree_bound_ = EnvInt("MXNET_KVSTORE_TREE_ARRAY_BOUND", 10000000);
+    tree_backtrack_ = EnvInt("MXNET_KVSTORE_TREE_BACKTRACK", 0) != 0;
+    if (const char* v = std::getenv("MXNET_KVSTORE_TREE_LINK_USAGE_PENALTY")) tree_penalty_ = static_cast<float>(std::atof(v));
+  }
+}
+
+const KVStore::TreePlan& KVStore::TreePlanFor(const std::vector<int>& devs) {
+  auto it = tree_plans_.find(devs);
+  if (it != tree_plans_.end()) return it->second;
+  const int n = static_cast<int>(devs.size());
+  TreePlan plan;
+  const std::vector<float> W = topo::QueryLinkWeights(devs);
+  topo::ComputeTrees(W, n, tree_penalty_, tree_backtrack_, &plan.trees);
+  uint64_t digest = 1469598103934665603ull;
+  auto mix = [&](uint64_t v) { digest = (digest ^ v) * 1099511628211ull; };
+  for (int r = 0; r < n; ++r) {
+    plan.prog.push_back(topo::ReduceProgramOf(plan.trees.topo[r], plan.trees.scan[r], plan.trees.depth, n));
+    for (int k = 0; k < n; ++k) mix(static_cast<uint64_t>(plan.prog[r].leaf[k]));
+    mix(plan.prog[r].prog);
+  }
+  if (EnvInt("MXNET_KVSTORE_LOGTREE", 0) != 0) {     // gpu_topology.h:46: print what was built
+    for (int r = 0; r < n; ++r) {
+      std::string line = "mxkv_b200: tree " + std::to_string(r) + ":";
+      for (size_t v : plan.trees.topo[r]) line += " " + std::to_string(v);
+      line += "  | add order";
+      for (int k = 0; k < n; ++k) line += " " + std::to_string(plan.prog[r].leaf[k]);
+      fprintf(stderr, "%s  (schedule 0x%x)\n", line.c_str(), plan.prog[r].prog);
+    }
+  }
+  if (ProcessGroup* pg = PG()) {
+    // one process per GPU: every rank must add in the same order, i.e. must have seen the same link matrix
+    std::vector<uint64_t> all(pg->world());
+    pg->AllGather(&digest, sizeof(digest), all.data());
+    for (uint64_t d : all)
+      MXKV_CHECK(d == digest) << "MXNET_KVSTORE_USETREE: the ranks derived different reduction trees (do they all see the "
+                                 "same GPUs, in the same order?)";
+  }
+  return tree_plans_.emplace(devs, std::move(plan)).first->second;
+}
+
+// One work entry of a key, cut where the tree changes: a key above MXNET_KVSTORE_TREE_ARRAY_BOUND elements with
+// at least 2n rows is n row slices, slice i summed up the tree rooted at GPU i (comm_tree.h:203-234: slice_size =
+// rows / n, the last slice takes the remainder); any other key goes up tree 0 whole (:236-240).  The sources are
+// handed to the kernel in the tree's leaf order.
+void KVStore::AppendTreeWorks(const TensorWork& tw, const TreePlan& tp, bool sliced, const KeyState& ks, int n_part,
+                              std::vector<TensorWork>* out) {
+  const size_t before = out->size();
+  auto emit = [&](int64_t pb, int64_t pe, int root) {
+    const topo::ReduceProgram& rp = tp.prog[root];
+    TensorWork t = tw;
+    for (int k = 0; k < rp.n; ++k) t.src[k] = tw.src[rp.leaf[k]];
+    t.tree_prog = rp.prog;
+    t.pad_ &= ~2;
+    // the vector path wants its first element on a packet boundary: a slice that begins inside a packet is led
+    // in by a few scalar elements
+    const int64_t aligned = std::min<int64_t>(pe, (pb + 7) / 8 * 8);
+    if (pb < aligned) {
+      TensorWork h = t;
+      h.begin = pb; h.end = aligned; h.pad_ &= ~1;
+      out->push_back(h);
+      pb = aligned;
+    }
+    if (pb < pe) { t.begin = pb; t.end = pe; out->push_back(t); }
+  };
+  if (!sliced) {
+    emit(tw.begin, tw.end, 0);
+  } else {
+    const int64_t rows = ks.shape[0], row_len = ks.size / rows, slice_rows = rows / n_part;
+    for (int i = 0; i < n_part; ++i) {
+      const int64_t lo = i * slice_rows * row_len, hi = i == n_part - 1 ? ks.size : (i + 1) * slice_rows * row_len;
+      const int64_t pb = std::max(tw.begin, lo), pe = std::min(tw.end, hi);
+      if (pb < pe) emit(pb, pe, i);
+    }
+  }
+  if (out->size() == before) {          // an empty range still takes part in the launch's rendezvous
+    TensorWork t = tw;
+    t.tree_prog = tp.prog[0].prog;
+    t.end = t.begin;
+    out->push_back(t);
+  }
 }
 
 ProcessGroup* KVStore::PG() const { return solo_ ? nullptr : Runtime::Get()->pg(); }
@@ -1717,6 +1804,23 @@ void KVStore::ReduceUpdate(std::vector<Group>& groups, bool write_outs) {
       }
     }
 
+    // ---- MXNET_KVSTORE_USETREE: which tree(s) this key's sum goes up ------------------------------------
+    // Two values add the same way in any order, and the integer dtypes wrap: only three or more floating-point
+    // values are order-sensitive.  Host-resident values and multi-node stores keep the plain order (the
+    // reference's tree needs every value on its own GPU, comm_tree.h:108-121).
+    const TreePlan* tree_plan = nullptr;
+    bool tree_sliced = false;
+    if (tree_ && collective && n_part >= 3 && hier_phase_ == 0 &&
+        (ks.dtype == kFloat32 || ks.dtype == kFloat16 || ks.dtype == kBfloat16 || ks.dtype == kFloat64)) {
+      MXKV_CHECK(!(fused && IsNormOpt(opt_.kind)))
+          << "MXNET_KVSTORE_USETREE=1: the layer-wise optimizers (LAMB / LANS / LARS) are not served in tree order";
+      MXKV_CHECK(TreeKernelAvailable(ks.dtype, fused ? opt_.kind : OPT_NONE, mp ? 1 : 0))
+          << "MXNET_KVSTORE_USETREE=1: no tree kernel for dtype " << ks.dtype << " with optimizer kind " << opt_.kind;
+      tree_plan = &TreePlanFor(mp_mode ? pg->rank_devs() : part_dev);
+      const int64_t rows = ks.shape.empty() ? 1 : ks.shape[0];
+      tree_sliced = ks.size > tree_bound_ && rows >= 2 * static_cast<int64_t>(n_part);
+    }
+
     // ---- destinations -------------------------------------------------------
     bool nvls_key = false;
     std::vector<Dest> dests;
@@ -1778,7 +1882,8 @@ void KVStore::ReduceUpdate(std::vector<Group>& groups, bool write_outs) {
       // (auto: above 4 ranks.  Per direction the switch path moves S(1 + 1/n) against 2S(n-1)/n of
       // the peer path: 1.5x more at n=2, equal time measured at n=4 -- where the peer path is kept
       // because it is bit-exact --, 1.56x less at n=8: busbw 782 vs 641 GB/s, profiles/r01_tune_bulk.txt)
-      if (mp_mode && collective && !hier_ && (rt->nvls_mode >= 2 || (rt->nvls_mode == 1 && n_part > 4)) &&
+      if (mp_mode && collective && !hier_ && tree_plan == nullptr &&
+          (rt->nvls_mode >= 2 || (rt->nvls_mode == 1 && n_part > 4)) &&
           !(fused && IsNormOpt(opt_.kind)) && ks.dtype == kFloat32 && ks.size % 4 == 0 &&
           g.vals[0].mc_data() != nullptr && Aligned16(g.vals[0].mc_data()) && !(two_shot && need_post)) {
         nvls_key = true;
@@ -1861,6 +1966,7 @@ void KVStore::ReduceUpdate(std::vector<Group>& groups, bool write_outs) {
     const int sync_mode = !collective ? SYNC_NONE : SYNC_WRITE_PEERS;
     LaunchClassKey ck{sync_mode, ks.dtype, mp ? 1 : 0};
     ck.nvls = nvls_key ? 1 : 0;
+    ck.tree = tree_plan != nullptr ? 1 : 0;
     LaunchClass& lc = classes[ck];
     auto& cls = lc.per_part;
     if (cls.empty()) cls.resize(n_part);
@@ -1913,7 +2019,8 @@ void KVStore::ReduceUpdate(std::vector<Group>& groups, bool write_outs) {
       }
       tw.lr = lr; tw.wd = wd; tw.eta = KeyEta(ks); tw.reserved_ = ks.key;
       tw.pad_ = (vec_ok ? 1 : 0) | ((vec_ok && esize == 4 && ks.size % 4 == 0) ? 2 : 0);
-      cls[p].push_back(tw);
+      if (tree_plan != nullptr) AppendTreeWorks(tw, *tree_plan, tree_sliced, ks, n_part, &cls[p]);
+      else cls[p].push_back(tw);
     }
   }
 
@@ -2025,7 +2132,7 @@ void KVStore::LaunchWorks(const LaunchClassKey& ck, std::vector<std::vector<Tens
   // that is a multiple of 4 elements (rank-independent facts only)
   int64_t chunk = rt->chunk_elems;
   int bulk = 0, bulk_stages = 0, bulk_arrays = 0, bulk_cap = 0;
-  if (rt->bulk_mode != 0 && ck.dtype == kFloat32 && !ck.nvls) {
+  if (rt->bulk_mode != 0 && ck.dtype == kFloat32 && !ck.nvls && !ck.tree) {
     bool ok = true;
     int max_src = 1;
     for (int p = my_first; p <= my_last; ++p)
@@ -2090,7 +2197,7 @@ void KVStore::LaunchWorks(const LaunchClassKey& ck, std::vector<std::vector<Tens
     L.dtype = ck.dtype;
     L.opt = opt_kind;
     L.multi_precision = ck.mp;
-    L.order = order_;
+    L.order = ck.tree ? ORDER_TREE : order_;
     L.fp32_accum = (opt_kind != OPT_NONE || ck.dtype == kBfloat16 ||
                     EnvInt("MXKV_B200_FP16_FP32_ACCUM", 0) != 0) ? 1 : 0;
     L.rescale = opt_.rescale; L.clip = opt_.clip; L.momentum = opt_.momentum;
@@ -2121,7 +2228,7 @@ void KVStore::LaunchWorks(const LaunchClassKey& ck, std::vector<std::vector<Tens
     const int rc = LaunchDense(L, d.stream);
     MXKV_CHECK(rc == 0) << "kernel launch failed: " << cudaGetErrorString(static_cast<cudaError_t>(rc));
     rt->launches++;
-    rt->variant_launches[L.nvls ? 2 : (L.bulk ? 1 : 0)]++;
+    rt->variant_launches[ck.tree ? 3 : (L.nvls ? 2 : (L.bulk ? 1 : 0))]++;
     d.ring.Commit(off, bytes, d.stream);
   }
 }

@@ -21,6 +21,7 @@
 #include <unordered_map>
 #include <unordered_set>
 #include "ndarray.h"
+#include "topology.h"
 
 namespace mxkv {
 
@@ -98,11 +99,13 @@ int64_t ShardLen(int64_t size, int world);
 struct LaunchClassKey {
   int sync_mode, dtype, mp;
   int nvls = 0;      // 1: multicast (multimem) kernel
+  int tree = 0;      // 1: sums in the order of a reduction tree (MXNET_KVSTORE_USETREE; tree_kernels.cu)
   bool operator<(const LaunchClassKey& o) const {
     if (sync_mode != o.sync_mode) return sync_mode < o.sync_mode;
     if (dtype != o.dtype) return dtype < o.dtype;
     if (mp != o.mp) return mp < o.mp;
-    return nvls < o.nvls;
+    if (nvls != o.nvls) return nvls < o.nvls;
+    return tree < o.tree;
   }
 };
 
@@ -301,6 +304,22 @@ class KVStore {
                     NDArray* const* outs);
   void ClearRawPending() { raw_pending_ = false; raw_single_ = false; }
  private:
+
+  // ---- MXNET_KVSTORE_USETREE=1 (CommDeviceTree, src/kvstore/comm_tree.h:50-325; topology.h) -----------------
+  // The trees are built once per set of GPUs a key is pushed from (the reference builds them for the devices of
+  // its first push, comm_tree.h:66-82) and turned into the add schedules the tree kernel executes.
+  struct TreePlan {
+    topo::TreeSet trees;
+    std::vector<topo::ReduceProgram> prog;   // per root
+  };
+  bool tree_ = false;
+  int64_t tree_bound_ = 10000000;            // MXNET_KVSTORE_TREE_ARRAY_BOUND: keys above it are summed slice by slice
+  bool tree_backtrack_ = false;              // MXNET_KVSTORE_TREE_BACKTRACK
+  float tree_penalty_ = 0.7f;                // MXNET_KVSTORE_TREE_LINK_USAGE_PENALTY
+  std::map<std::vector<int>, TreePlan> tree_plans_;
+  const TreePlan& TreePlanFor(const std::vector<int>& devs);
+  void AppendTreeWorks(const TensorWork& tw, const TreePlan& tp, bool sliced, const KeyState& ks, int n_part,
+                       std::vector<TensorWork>* out);
 
   ProcessGroup* PG() const;     // the process group this store exchanges over (none for 'updater' stores)
   std::string type_;

@@ -82,7 +82,12 @@ ProcessGroup::ProcessGroup(int rank, int world, int dev, AllGatherFn fn, void* c
   pads_ = SymAlloc(kSignalPadBytes);
   CUDA_CALL(cudaMemset(pads_.ptr[rank_], 0, kSignalPadBytes));
   CUDA_CALL(cudaDeviceSynchronize());
-  Barrier();   // nobody may signal into a pad that has not been zeroed yet
+  // nobody may signal into a pad that has not been zeroed yet: this exchange (who sits on which GPU -- the link
+  // matrix of MXNET_KVSTORE_USETREE is asked for by device ordinal) doubles as the barrier
+  std::vector<int64_t> all(world_);
+  const int64_t mine = dev_;
+  AllGather(&mine, sizeof(mine), all.data());
+  rank_devs_.assign(all.begin(), all.end());
 }
 
 ProcessGroup::~ProcessGroup() {

@@ -95,6 +95,7 @@ class ProcessGroup {
   int rank() const { return rank_; }
   int world() const { return world_; }
   int dev() const { return dev_; }
+  const std::vector<int>& rank_devs() const { return rank_devs_; }   // CUDA device ordinal of every rank
   // collective: every rank must call with the same byte count, in the same order
   SymPtr SymAlloc(size_t bytes);
   void AllGather(const void* send, size_t bytes, void* recv);
@@ -114,6 +115,7 @@ class ProcessGroup {
   bool has_multicast() const { for (auto& s : segs_) if (s.vmm) return true; return false; }
  private:
   int rank_, world_, dev_;
+  std::vector<int> rank_devs_;
   AllGatherFn fn_;
   void* ctx_;
   std::vector<Segment> segs_;
@@ -155,7 +157,8 @@ class Runtime {
   // dense launches by kernel variant: 0 per-thread (kv_dense_kernel / kv_sum_typed_kernel), 1 shared-memory
   // staged (kv_dense_bulk_kernel), 2 NVSwitch multicast (kv_dense_nvls_kernel) -- lets a parity test prove
   // which kernel it has just compared with the oracle (MXKVB200GetVariantLaunchCount)
-  int64_t variant_launches[3] = {0, 0, 0};
+  // 3: the tree-order kernels of MXNET_KVSTORE_USETREE (kv_dense_tree_kernel / kv_sum_tree_f64_kernel)
+  int64_t variant_launches[4] = {0, 0, 0, 0};
   int64_t twoshot_bytes = 256 * 1024;
   int64_t chunk_elems = kChunkElems;         // MXKV_B200_CHUNK
   int threads = 512;                         // MXKV_B200_THREADS

@@ -536,11 +536,11 @@ def set_auto_fence(flag):
     check_call(_LIB.MXKVB200SetAutoFence(ctypes.c_int(1 if flag else 0)))
 
 
-VARIANTS = {"per_thread": 0, "bulk": 1, "nvls": 2}
+VARIANTS = {"per_thread": 0, "bulk": 1, "nvls": 2, "tree": 3}
 
 
 def launch_count(variant=None):
-    """Kernels launched by the engine so far; with ``variant`` ('per_thread' | 'bulk' | 'nvls') the dense
+    """Kernels launched by the engine so far; with ``variant`` ('per_thread' | 'bulk' | 'nvls' | 'tree') the dense
     reduce(+update) launches of that kernel variant only."""
     n = ctypes.c_int64()
     if variant is None:

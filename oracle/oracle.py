@@ -125,6 +125,96 @@ def sum_cpu_inplace(bufs, nthreads=4, bigarray_bound=1000 * 1000):
                           ctypes.c_int(nthreads), _I64(bigarray_bound))
 
 
+# ---------------------------------------------------------------------------
+# MXNET_KVSTORE_USETREE=1: CommDeviceTree (src/kvstore/comm_tree.h)
+# ---------------------------------------------------------------------------
+def tree_reduce(srcs, topo_row, scan_row, depth, add=None):
+    """CommDeviceTree::ReduceInner (comm_tree.h:91-177), level by level on per-GPU merge buffers.
+
+    ``srcs[g]`` is GPU g's value; ``topo_row`` / ``scan_row`` one tree in the reference's array form.  Every GPU of the
+    leaf level copies its value into its merge buffer (:108-121); from the deepest level up, nodes are visited in
+    pairs (dest, from): a `from` different from `dest` is copied into dest's receive buffer (:137-145), then every
+    parent whose two children differ sets its merge buffer to (own buffer + receive buffer) (:151-166).  Returns the
+    root's buffer."""
+    add = add or (lambda a, b: a + b)
+    n = len(srcs)
+    topo = [int(v) for v in topo_row]
+    scan = [int(v) for v in scan_row]
+    merged = [None] * n
+    for j in range(scan[depth], scan[depth + 1]):
+        g = topo[j]
+        merged[g] = np.array(srcs[g], copy=True)
+    for level in range(depth, 0, -1):
+        reduce_lists = [[] for _ in range(n)]
+        copy_buf = [None] * n
+        is_dest, dest_id = 0, 0
+        for j in range(scan[level], scan[level + 1]):
+            topo_id = topo[j]
+            if is_dest == 0:
+                dest_id = topo_id
+                if not reduce_lists[dest_id]:
+                    reduce_lists[dest_id].append(("merged", dest_id))
+            elif dest_id != topo_id:
+                assert copy_buf[dest_id] is None, "two sends into one receive buffer"
+                copy_buf[dest_id] = merged[topo_id].copy()
+                reduce_lists[dest_id].append(("copy", dest_id))
+            is_dest = 0 if is_dest == 1 else 1          # kBranch = 2
+        source = scan[level]
+        for i in range(scan[level - 1], scan[level]):
+            gpu_id = topo[i]
+            dest, frm = topo[source], topo[source + 1]
+            source += 2
+            if len(reduce_lists[gpu_id]) > 1 and dest != frm:
+                acc = None
+                for kind, g in reduce_lists[gpu_id]:
+                    v = merged[g] if kind == "merged" else copy_buf[g]
+                    acc = v if acc is None else add(acc, v)
+                merged[gpu_id] = acc
+    return merged[topo[0]]
+
+
+def sum_tree(srcs, topo, scan, depth, bound=10000000, add=None):
+    """CommDeviceTree::Reduce + Broadcast (comm_tree.h:179-250, :283-325) as seen by a pull: keys above ``bound``
+    elements whose first dimension is at least 2n are cut into n row slices (slice_size = rows // n, the last slice
+    takes the remainder), slice i reduced up the tree rooted at GPU i; everything else goes up tree 0 whole."""
+    n = len(srcs)
+    shape = srcs[0].shape
+    rows = shape[0] if len(shape) else 1
+    if srcs[0].size > bound and rows >= 2 * n:
+        out = np.empty_like(srcs[0])
+        step = rows // n
+        for i in range(n):
+            lo, hi = i * step, (rows if i == n - 1 else (i + 1) * step)
+            out[lo:hi] = tree_reduce([s[lo:hi] for s in srcs], topo[i], scan[i], depth, add)
+        return out
+    return tree_reduce(srcs, topo[0], scan[0], depth, add)
+
+
+def ref_topology_lib():
+    """oracle/_ref/libkvref_topo.so: the reference's own gpu_topology.h compiled in place (oracle/ref_topology.cc)."""
+    path = os.path.join(_HERE, "_ref", "libkvref_topo.so")
+    return ctypes.CDLL(path) if os.path.exists(path) else None
+
+
+def ref_compute_trees(W, alpha=0.7, backtrack=False):
+    """ComputeTrees of the reference (gpu_topology.h:1111-1157) on link matrix W -> (topo [n, 2^(d+1)-1],
+    scan [n, d+2]); None where the reference aborts."""
+    lib_ = ref_topology_lib()
+    W = np.ascontiguousarray(W, np.float32)
+    n = W.shape[0]
+    topo = np.zeros(n * 64, np.uint64)
+    scan = np.zeros(n * 16, np.uint64)
+    tl, sl = ctypes.c_int(), ctypes.c_int()
+    rc = lib_.kvref_topo_compute_trees(ctypes.c_void_p(W.ctypes.data), ctypes.c_int(n), ctypes.c_float(alpha),
+                                       ctypes.c_int(1 if backtrack else 0), ctypes.c_void_p(topo.ctypes.data),
+                                       ctypes.c_void_p(scan.ctypes.data), ctypes.byref(tl), ctypes.byref(sl))
+    if rc == -2:
+        return None
+    assert rc == 0
+    return (topo[:n * tl.value].reshape(n, tl.value).astype(np.int64),
+            scan[:n * sl.value].reshape(n, sl.value).astype(np.int64))
+
+
 def ref_sum_device(srcs):
     r = ref_lib()
     srcs = [np.ascontiguousarray(s) for s in srcs]
@@ -529,9 +619,11 @@ class OracleKVStore(object):
     association: names containing 'device' use CommDevice order, others CommCPU
     (kvstore.cc:42-85)."""
 
-    def __init__(self, type="local"):
+    def __init__(self, type="local", tree=None):
         self.type = type
         self.device = "device" in type.lower()
+        # MXNET_KVSTORE_USETREE=1 (kvstore_local.h:74-82): dict(topo=, scan=, depth=, bound=) of CommDeviceTree
+        self.tree = tree if self.device else None
         self.local = {}
         self.key_type = None
         self.updater = None
@@ -579,6 +671,9 @@ class OracleKVStore(object):
             return vals[0]
         if isinstance(vals[0], RowSparse):
             return rsp_sum(vals)
+        if self.device and self.tree is not None and len(vals) == self.tree["topo"].shape[0]:
+            t = self.tree
+            return sum_tree(vals, t["topo"], t["scan"], t["depth"], t.get("bound", 10000000))
         if self.device:
             return sum_device(vals)
         return sum_cpu(vals, self.nthreads).reshape(vals[0].shape)

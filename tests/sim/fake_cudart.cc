@@ -149,6 +149,8 @@ API cudaError_t cudaSetDevice(int d) {
 API cudaError_t cudaDeviceSynchronize(void) { return cudaSuccess; }
 API cudaError_t cudaDeviceCanAccessPeer(int* can, int a, int b) { *can = (a != b) ? 1 : 0; return cudaSuccess; }
 API cudaError_t cudaDeviceEnablePeerAccess(int, unsigned) { return cudaSuccess; }
+// every pair behind one switch: performance rank 0 (what an NVSwitch machine reports)
+API cudaError_t cudaDeviceGetP2PAttribute(int* value, cudaDeviceP2PAttr, int, int) { *value = 0; return cudaSuccess; }
 API cudaError_t cudaDeviceGetStreamPriorityRange(int* lo, int* hi) { *lo = 0; *hi = -5; return cudaSuccess; }
 API cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr attr, int) {
   switch (attr) {

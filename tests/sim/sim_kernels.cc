@@ -18,6 +18,7 @@
 #include <map>
 #include "sim.h"
 #include "optim_math.h"
+#include "tree_math.h"
 #include "norm_math.h"
 #include "rsp_kernels.h"
 
@@ -134,7 +135,22 @@ int ToInt(const std::string& s) { return s == "true" ? 1 : (s == "false" ? 0 : a
 
 // gather the n replicas of element e and add them in the reference's association order
 template <typename T>
-float OrderedSum(const void* const* src, int n, int64_t e, int order, bool native_half_add) {
+float OrderedSum(const void* const* src, int n, int64_t e, int order, bool native_half_add, uint32_t tree_prog = 0) {
+  if (order == ORDER_TREE) {          // the device's own evaluator (csrc/tree_math.h), compiled for the host
+    TreeSum<float, 1> sum;
+    sum.begin(tree_prog);
+    for (int k = 0; k < n; ++k) {
+      const float x[1] = {H<T>::to(static_cast<const T*>(src[k])[e])};
+      sum.take(x, [native_half_add](float l, float r) {
+        float s = __fadd_rn(l, r);
+        if (native_half_add) s = H<T>::to(H<T>::from(s));
+        return s;
+      });
+    }
+    float y[1];
+    sum.result(y);
+    return y[0];
+  }
   float acc = 0.f, grp = 0.f;
   for (int k = 0; k < n; ++k) {
     const float x = H<T>::to(static_cast<const T*>(src[k])[e]);
@@ -163,7 +179,7 @@ void DenseEntry(const DenseLaunch& L, const TensorWork& tw, bool mp) {
   constexpr bool HAS_S0 = OPT == OPT_SGD_MOM || OPT == OPT_ADAM || OPT == OPT_ADAMW || OPT == OPT_ADAM_STD;
   constexpr bool HAS_S1 = OPT == OPT_ADAM || OPT == OPT_ADAMW || OPT == OPT_ADAM_STD;
   for (int64_t e = tw.begin; e < tw.end; ++e) {
-    const float acc = OrderedSum<T>(tw.src, tw.n_src, e, L.order, native_half_add);
+    const float acc = OrderedSum<T>(tw.src, tw.n_src, e, L.order, native_half_add, tw.tree_prog);
     float wnew = acc;
     if (OPT != OPT_NONE) {
       const float w = mp ? tw.w32[e] : H<T>::to(static_cast<const T*>(tw.w)[e]);
@@ -206,6 +222,34 @@ bool Dense(const std::vector<std::string>& t, void** args) {          // kv_dens
   if (t[0] == "__half") return DenseT<__half>(L, opt, mp);
   if (t[0] == "__nv_bfloat16") return DenseT<__nv_bfloat16>(L, opt, mp);
   return false;
+}
+
+bool DenseTree(const std::vector<std::string>& t, void** args) {      // kv_dense_tree_kernel<T, OPT, MP>
+  const DenseLaunch& L = *static_cast<const DenseLaunch*>(args[0]);
+  if (L.order != ORDER_TREE || L.bulk || L.nvls) return false;
+  return Dense(t, args);
+}
+
+bool SumTreeF64(void** args) {                                         // kv_sum_tree_f64_kernel
+  const DenseLaunch& L = *static_cast<const DenseLaunch*>(args[0]);
+  if (L.order != ORDER_TREE || L.dtype != kFloat64) return false;
+  RendezvousStart(L.sync);
+  struct AtExit { const SyncArgs& s; ~AtExit() { RendezvousEnd(s); } } at_exit{L.sync};
+  for (int i = 0; i < L.nworks; ++i) {
+    const TensorWork& tw = L.works[i];
+    for (int64_t e = tw.begin; e < tw.end; ++e) {
+      TreeSum<double, 1> sum;
+      sum.begin(tw.tree_prog);
+      for (int k = 0; k < tw.n_src; ++k) {
+        const double x[1] = {static_cast<const double*>(tw.src[k])[e]};
+        sum.take(x, [](double l, double r) { return l + r; });
+      }
+      double y[1];
+      sum.result(y);
+      for (int j = 0; j < tw.n_out; ++j) static_cast<double*>(tw.out[j])[e] = y[0];
+    }
+  }
+  return true;
 }
 
 bool DenseBulk(const std::vector<std::string>& t, void** args) {      // kv_dense_bulk_kernel<OPT, MP>
@@ -549,6 +593,8 @@ bool Dispatch(const LaunchInfo& info, void** args) {
   ParseName(info.name, &base, &t);
   if (base == "mxkv::kv_dense_kernel") return Dense(t, args);
   if (base == "mxkv::kv_dense_bulk_kernel") return DenseBulk(t, args);
+  if (base == "mxkv::kv_dense_tree_kernel") return DenseTree(t, args);
+  if (base == "mxkv::kv_sum_tree_f64_kernel") return SumTreeF64(args);
   if (base == "mxkv::kv_sum_typed_kernel") return SumTyped(t, args);
   if (base == "mxkv::kv_cast_f32_kernel") return CastF32(t, args);
   if (base == "mxkv::kv_quantize_kernel") return Quantize(t, args);

@@ -18,6 +18,12 @@
                       372-437; lazy and standard), and ``SGD.step`` on the densified gradient for the standard SGD
                       update (test_std_sparse_sgd, :183-203), executed from the reference files the same way.
 
+* tree_topology.npz -- MXNET_KVSTORE_USETREE: the trees the reference's OWN solver (src/kvstore/gpu_topology.h,
+                      compiled where it lies into oracle/_ref/libkvref_topo.so by oracle/ref_topology.cc) builds
+                      from link matrices -- one switch (uniform weights, 2 ... 8 GPUs), the NVLink hybrid cube
+                      mesh of its comments, random matrices of 2 ... 16 GPUs with and without missing links --
+                      by Kernighan-Lin and by the exhaustive search; plus the outcome of one Kernighan-Lin pass.
+
 The GPU box has no /root/reference; tests read the committed fixtures instead.
 """
 import ast
@@ -376,11 +382,83 @@ def lr_schedules():
     np.savez_compressed(os.path.join(HERE, "lr_schedules.npz"), **out)
 
 
+P3_16XLARGE = [[0, 2, 2, 3, 3, 1, 1, 1], [2, 0, 3, 2, 1, 3, 1, 1], [2, 3, 0, 3, 1, 1, 2, 1], [3, 2, 3, 0, 1, 1, 1, 2],
+               [3, 1, 1, 1, 0, 2, 2, 3], [1, 3, 1, 1, 2, 0, 3, 2], [1, 1, 2, 1, 2, 3, 0, 3], [1, 1, 1, 2, 3, 2, 3, 0]]
+
+
+def tree_topology():
+    """Link matrices and what the reference's solver makes of them.  case_i_W / _alpha / _backtrack -> _topo / _scan
+    (or _fails = 1 where the reference aborts: no balanced binary tree over those links)."""
+    import ctypes
+    from oracle import oracle as O
+    lib = O.ref_topology_lib()
+    assert lib is not None, "build oracle/_ref first (make -C oracle)"
+    rng = np.random.default_rng(20260921)
+    cases = []
+    for n in range(2, 9):                                   # behind one switch: every pair alike
+        for w in (1.0, 2.0, 3.0):
+            for bt in (0, 1):
+                cases.append((w * (np.ones((n, n)) - np.eye(n)), 0.7, bt))
+    p3 = np.array(P3_16XLARGE, np.float64)
+    for bt in (0, 1):                                       # gpu_topology.h:181-190, PCI-E kept (1) and dropped (0)
+        cases.append((p3, 0.7, bt))
+        cases.append((np.where(p3 == 1, 0.0, p3), 0.7, bt))
+        cases.append((p3, 0.5, bt))
+    for n in range(2, 17):                                  # the shape of TestComputeTrees1/2's random matrices
+        for rep in range(4):
+            u = rng.uniform(0, 1, (n, n))
+            W = np.where(u < 0.33, 1.0, np.where(u < 0.66, 2.0, 3.0))
+            if rep == 3:
+                W = np.where(rng.uniform(0, 1, (n, n)) < 0.25, 0.0, W)
+            W = np.triu(W, 1)
+            W = W + W.T
+            for bt in ((0, 1) if n <= 8 else (0,)):
+                cases.append((W, 0.7, bt))
+    out = {"n_cases": np.array(len(cases))}
+    fails = 0
+    for i, (W, alpha, bt) in enumerate(cases):
+        out["case_%d_W" % i] = W.astype(np.float32)
+        out["case_%d_alpha" % i] = np.float32(alpha)
+        out["case_%d_backtrack" % i] = np.array(bt)
+        r = O.ref_compute_trees(W, alpha, bool(bt))
+        if r is None:
+            out["case_%d_fails" % i] = np.array(1)
+            fails += 1
+        else:
+            out["case_%d_topo" % i], out["case_%d_scan" % i] = r[0].astype(np.int16), r[1].astype(np.int16)
+    # one Kernighan-Lin pass from a single cluster, seeds 1 ... 4 (TestKernighanLin1/2 call it with seed 1)
+    kl = []
+    for n in (5, 6, 8, 11, 16):
+        for seed in (1, 2, 3, 4):
+            u = rng.uniform(0, 1, (n, n))
+            W = np.triu(np.where(u < 0.4, 1.0, np.where(u < 0.7, 2.0, 4.0)), 1)
+            W = (W + W.T).astype(np.float32)
+            P = np.zeros(n, np.int32)
+            npart = ctypes.c_int(1)
+            pairs = np.zeros(4 * n, np.int32)
+            npairs = ctypes.c_int()
+            stop = lib.kvref_topo_kernighan_lin(ctypes.c_void_p(W.ctypes.data), n, ctypes.c_void_p(P.ctypes.data),
+                                                ctypes.byref(npart), ctypes.c_void_p(pairs.ctypes.data),
+                                                ctypes.byref(npairs), ctypes.c_uint32(seed))
+            kl.append((W, seed, P.copy(), npart.value, pairs[:2 * npairs.value].copy(), stop))
+    out["n_kl"] = np.array(len(kl))
+    for i, (W, seed, P, npart, pairs, stop) in enumerate(kl):
+        out["kl_%d_W" % i], out["kl_%d_seed" % i], out["kl_%d_P" % i] = W, np.array(seed), P
+        out["kl_%d_npart" % i], out["kl_%d_pairs" % i], out["kl_%d_stop" % i] = np.array(npart), pairs, np.array(stop)
+    np.savez_compressed(os.path.join(HERE, "tree_topology.npz"), **out)
+    print("tree_topology: %d matrices (%d without a tree), %d Kernighan-Lin passes" % (len(cases), fails, len(kl)))
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1:                 # e.g. `make_golden.py tree_topology`: only the named fixtures
+        for name in sys.argv[1:]:
+            globals()[name]()
+        sys.exit(0)
     dense_sums()
     compression()
     layerwise()
     plain_steps()
     sparse_steps()
     lr_schedules()
+    tree_topology()
     print("wrote", sorted(f for f in os.listdir(HERE) if f.endswith(".npz")))

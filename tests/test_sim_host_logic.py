@@ -72,7 +72,8 @@ def test_single_process_multi_gpu_paths(sim_lib, devices):
     """one-shot and two-shot (sharded) exchange, sharded optimizer state, layer-wise optimizers with norms added
     across the shards, compression, the updater callback -- over 2, 4 and 8 simulated GPUs."""
     out = _run(sim_lib, devices, ["test_gpu_multi.py", "test_gpu_compression.py", "test_gpu_rsp.py",
-                                  "test_gpu_y_placement.py", "test_gpu_y_trainer_nd.py", "test_gpu_y_semantics.py", "test_gpu_zz_threads.py"],
+                                  "test_gpu_y_placement.py", "test_gpu_y_trainer_nd.py", "test_gpu_y_semantics.py", "test_gpu_zz_threads.py",
+                                  "test_gpu_zzz_tree.py"],
                extra=["-k", "not one_process_per_gpu"])
     assert _passed(out) >= 30, out[-500:]
 
@@ -97,7 +98,7 @@ def test_host_code_under_address_and_ub_sanitizers():
     cmd = [sys.executable, "-m", "pytest", "-q", "-m", "gpu", "-p", "no:cacheprovider", "-x",
            "-k", "not one_process_per_gpu"] + _workers() + \
           [os.path.join(ROOT, "tests", f) for f in ("test_gpu_y_placement.py", "test_gpu_multi.py", "test_gpu_rsp.py",
-                                                    "test_gpu_updater.py")]
+                                                    "test_gpu_updater.py", "test_gpu_zzz_tree.py")]
     r = subprocess.run(cmd, env=env, cwd=ROOT, capture_output=True, text=True, timeout=1500)
     tail = (r.stdout + r.stderr)[-4000:]
     assert r.returncode == 0, tail

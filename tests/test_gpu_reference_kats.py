@@ -222,13 +222,17 @@ def test_aggregator(stype):
     check_aggregator(init_kv_with_str("cpu"), "a", str_keys)
 
 
+@pytest.mark.parametrize("usetree", [None, "1"])
 @pytest.mark.parametrize("kv_type", ["local", "device"])
 @pytest.mark.parametrize("push_on_gpu", [False, True])
-def test_rsp_push_pull(kv_type, push_on_gpu):
+def test_rsp_push_pull(kv_type, push_on_gpu, usetree, monkeypatch):
     # tests/python/gpu/test_kvstore_gpu.py:48-110 on one GPU: row_sparse key of ones, two row_sparse
     # pushes of ones (stored value becomes 2), then row_sparse_pull with random -- repeated, unsorted,
     # FLOAT32 -- row ids into outputs on the GPU and on cpu contexts, one id array per output or a
-    # shared one, and the dense pull of the whole value
+    # shared one, and the dense pull of the whole value; with and without MXNET_KVSTORE_USETREE like the
+    # reference's loop (:100-109; row_sparse keys take CommDevice's own reduce under the tree, comm_tree.h:246-249)
+    if usetree is not None:
+        monkeypatch.setenv("MXNET_KVSTORE_USETREE", usetree)
     rshape = (20, 6)
     num_rows = rshape[0]
     kv = mx.kv.create(kv_type)

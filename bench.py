@@ -500,7 +500,7 @@ class Env(object):
         return self.torch.cuda.ExternalStream(sp.value, device=self.torch.device("cuda", self.local))
 
     def variant_counts(self):
-        return {v: self.mx.kv.launch_count(v) for v in ("per_thread", "bulk", "nvls")}
+        return {v: self.mx.kv.launch_count(v) for v in ("per_thread", "bulk", "nvls", "tree")}
 
     def finish(self):
         self.mx.nd.waitall()
@@ -509,7 +509,21 @@ class Env(object):
             self.dist.destroy_process_group()
 
 
-KERNEL_NAMES = {"per_thread": "kv_dense_kernel", "bulk": "kv_dense_bulk_kernel", "nvls": "kv_dense_nvls_kernel"}
+KERNEL_NAMES = {"per_thread": "kv_dense_kernel", "bulk": "kv_dense_bulk_kernel", "nvls": "kv_dense_nvls_kernel",
+                "tree": "kv_dense_tree_kernel"}
+
+
+def oracle_tree(env, kvtype):
+    """MXNET_KVSTORE_USETREE=1 in the environment (three ranks or more, a `device` store): the trees the engine builds
+    for this job's GPUs, in the form the oracle store takes; None otherwise."""
+    if os.environ.get("MXNET_KVSTORE_USETREE", "0") in ("", "0") or env.world < 3 or "device" not in kvtype or \
+            getattr(env, "hier", False):
+        return None
+    T = env.mx.topology
+    topo, scan, depth = T.compute_trees(T.query_links(env.allgather_int(env.local)),
+                                        float(os.environ.get("MXNET_KVSTORE_TREE_LINK_USAGE_PENALTY", 0.7)),
+                                        os.environ.get("MXNET_KVSTORE_TREE_BACKTRACK", "0") not in ("", "0"))
+    return dict(topo=topo, scan=scan, depth=depth, bound=int(os.environ.get("MXNET_KVSTORE_TREE_ARRAY_BOUND", 10000000)))
 
 
 def variant_since(env, before):
@@ -550,10 +564,13 @@ def parity_check(env, args, shapes, keys, grads, weights, kvtype, keep=False):
     replicas_equal = len(set(env.allgather_int(chk))) == 1
     res = {"checked": True, "variant": variant, "replicas_bit_identical": replicas_equal, "keys": len(keys)}
     kept = None
+    tree = oracle_tree(env, kvtype)
+    if tree is not None:
+        res["sum_order"] = "MXNET_KVSTORE_USETREE"
     if env.rank == 0:
         _, kw, oname, _ = OPTIMIZERS[args.optimizer]
         all_g = [rank_grads(r, shapes) for r in range(env.world)]
-        okv = O.OracleKVStore("device")
+        okv = O.OracleKVStore("device", tree=tree)
         okv.init(keys, [w.copy() for w in w0])
         layerwise = oname in ("lamb", "lans", "lars")
         if oname:
@@ -574,7 +591,7 @@ def parity_check(env, args, shapes, keys, grads, weights, kvtype, keep=False):
         res.update({"max_rel_l1": worst, "bit_exact": exact, "tolerance": 0.0 if must_be_exact else 1e-6,
                     "ok": bool(replicas_equal and (exact or (not must_be_exact and worst <= 1e-6)))})
         if keep:
-            gsum = [O.sum_device([all_g[r][k] for r in range(env.world)]).reshape(shapes[k]) if env.world > 1
+            gsum = [okv._reduce([all_g[r][k] for r in range(env.world)]).reshape(shapes[k]) if env.world > 1
                     else all_g[0][k] for k in keys]
             kept = {"fused": wants, "allreduce": gsum}
     ok = env.allgather_int(1 if (env.rank != 0 or res.get("ok")) else 0)

@@ -810,6 +810,23 @@ void KVStore::PushImpl(const std::vector<int>& keys, const std::vector<NDArray>&
       continue;
     }
     if (AdamWSkips()) { ks.count += 1; continue; }
+    // BASELINE configs[0], the reference's CPU-runnable case: ONE host-resident value pushed to a key that has
+    // never met a GPU, nothing to run on it (no updater, no optimizer, no compression).  The reference does no
+    // arithmetic here either -- Reduce hands a single value back as it is (comm.h:128-131) and the store copies it
+    // over the stored value (kvstore_local.h:279-284) -- so this is plumbing, served without a device.  Anything
+    // that would need a sum or an update still fails loudly without a GPU (DefaultDevice).
+    if (grouped[i].size() == 1 && !grouped[i][0].ctx().is_gpu() && ks.reps.empty() && !ks.init_value.is_none() &&
+        !ks.init_value.ctx().is_gpu() && updater_ == nullptr && !opt_.enabled && gc_bits_ == 0 && !hier_ &&
+        PG() == nullptr && Runtime::Get()->NumDevices() == 0) {
+      const NDArray& v = grouped[i][0];
+      MXKV_CHECK(v.size() == ks.size) << "push: value has " << v.size() << " elements, key " << ks.key
+                                      << " was initialised with " << ks.size;
+      MXKV_CHECK(v.dtype() == ks.dtype) << "push: dtype mismatch for key " << ks.key
+                                        << " (Only support input/output with the same data type)";
+      GetKey(uniq[i]);                               // (a change of the key: cached plans of it expire)
+      std::memcpy(ks.init_value.data(), v.data(), v.nbytes());
+      continue;
+    }
     Group g;
     g.key = uniq[i];
     g.vals = grouped[i];
@@ -889,6 +906,8 @@ void KVStore::PushPullImpl(const std::vector<int>& vkeys, const std::vector<int>
   if (fusable) {
     for (int k : vu) if (PeekKey(k).stype != kDefaultStorage) fusable = false;
   }
+  // no device at all: literally push then pull, so that the one case that is pure plumbing (PushImpl) is served
+  if (fusable && PG() == nullptr && Runtime::Get()->NumDevices() == 0) fusable = false;
   if (!fusable) {
     PushImpl(vkeys, vals, priority);
     PullImpl(okeys, outs, priority, true);

@@ -85,6 +85,40 @@ def test_error_contract_and_key_rules_without_gpu():
     assert np.array_equal(out.asnumpy(), big.asnumpy())
 
 
+@pytest.mark.skipif(mx.num_gpus() > 0, reason="the no-GPU plumbing case")
+@pytest.mark.parametrize("kv_type", ["local", "device"])
+def test_baseline_config0_push_pull_of_one_cpu_array_without_gpu(kv_type):
+    """BASELINE.json configs[0]: kv.create('local') push / pull of one 1024 x 1024 float32 array on the CPU, world
+    size 1 -- the reference's own CPU-runnable case.  One value and no updater is a copy in the reference too
+    (comm.h:128-131, kvstore_local.h:279-284): served without a device, compared with the oracle store; a second
+    value (a sum) or an optimizer (an update) is compute and still refuses to run without a GPU."""
+    from oracle import oracle as O
+    rng = np.random.default_rng(0)
+    w0 = rng.uniform(-1, 1, (1024, 1024)).astype(np.float32)
+    g = rng.uniform(-1, 1, (1024, 1024)).astype(np.float32)
+    kv = mx.kv.create(kv_type)
+    okv = O.OracleKVStore(kv_type)
+    kv.init(0, mx.nd.array(w0))
+    okv.init(0, w0.copy())
+    out = mx.nd.zeros((1024, 1024))
+    for val in (g, 2 * g):
+        kv.push(0, mx.nd.array(val))
+        okv.push(0, val)
+        kv.pull(0, out=out)
+        want = np.empty_like(w0)
+        okv.pull(0, want)
+        assert np.array_equal(out.asnumpy().view(np.uint32), want.view(np.uint32))
+    kv.pushpull(0, mx.nd.array(g), out=out)                 # push then pull (kvstore_local.h:358-365)
+    assert np.array_equal(out.asnumpy(), g)
+    with pytest.raises(mx.MXNetError, match="dtype mismatch"):
+        kv.push(0, mx.nd.array(g.astype(np.float64), dtype=np.float64))
+    with pytest.raises(mx.MXNetError, match="no CPU fallback"):
+        kv.push(0, [mx.nd.array(g), mx.nd.array(g)])
+    kv.set_optimizer(mx.optimizer.SGD(learning_rate=0.1))
+    with pytest.raises(mx.MXNetError, match="no CPU fallback"):
+        kv.push(0, mx.nd.array(g))
+
+
 @pytest.mark.skipif(mx.num_gpus() > 0, reason="checks the no-GPU failure mode")
 def test_compute_fails_loudly_without_gpu():
     kv = mx.kv.create("device")

@@ -6,6 +6,12 @@
 #include "optim_math.h"
 #include <cuda_fp16.h>
 #include <cuda_bf16.h>
+// MXKV_HOST_EMU (tests/sim/hostemu_tree.cc only): a kernel's own source compiled by g++ and run on the CPU -- the
+// handful of PTX accesses below get plain C++ bodies, everything else in this file and in the kernel is the
+// source the device executes.  Never defined in the product build.
+#if defined(MXKV_HOST_EMU)
+#include "host_emu.h"
+#endif
 
 namespace mxkv {
 
@@ -15,30 +21,54 @@ constexpr int kThreads = 512;
 // memory helpers
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ uint4 ld16(const void* p) {
+#if defined(MXKV_HOST_EMU)
+  return *static_cast<const uint4*>(hostemu::Aligned(p, 16));
+#else
   uint4 v;
   asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
                : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
   return v;
+#endif
 }
 __device__ __forceinline__ void st16(void* p, const uint4& v) {
+#if defined(MXKV_HOST_EMU)
+  *static_cast<uint4*>(hostemu::Aligned(p, 16)) = v;
+#else
   asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};"
                :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+#endif
 }
 __device__ __forceinline__ void st_flag_volatile(uint32_t* p, uint32_t v) {
+#if defined(MXKV_HOST_EMU)
+  __atomic_store_n(p, v, __ATOMIC_RELAXED);
+#else
   asm volatile("st.volatile.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+#endif
 }
 __device__ __forceinline__ uint32_t ld_flag_volatile(const uint32_t* p) {
+#if defined(MXKV_HOST_EMU)
+  return __atomic_load_n(p, __ATOMIC_RELAXED);
+#else
   uint32_t v;
   asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
+#endif
 }
 __device__ __forceinline__ void st_flag_release(uint32_t* p, uint32_t v) {
+#if defined(MXKV_HOST_EMU)
+  __atomic_store_n(p, v, __ATOMIC_RELEASE);
+#else
   asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+#endif
 }
 __device__ __forceinline__ uint32_t ld_flag_acquire(const uint32_t* p) {
+#if defined(MXKV_HOST_EMU)
+  return __atomic_load_n(p, __ATOMIC_ACQUIRE);
+#else
   uint32_t v;
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
+#endif
 }
 
 // ---------------------------------------------------------------------------
@@ -148,12 +178,20 @@ template <> struct Cvt<double> {          // multi_sum_sq squares float64 inputs
 };
 
 __device__ __forceinline__ uint2 ld8(const void* p) {
+#if defined(MXKV_HOST_EMU)
+  return *static_cast<const uint2*>(hostemu::Aligned(p, 8));
+#else
   uint2 v;
   asm volatile("ld.global.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
   return v;
+#endif
 }
 __device__ __forceinline__ void st8(void* p, const uint2& v) {
+#if defined(MXKV_HOST_EMU)
+  *static_cast<uint2*>(hostemu::Aligned(p, 8)) = v;
+#else
   asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1,%2};" :: "l"(p), "r"(v.x), "r"(v.y) : "memory");
+#endif
 }
 
 // Packet<T, N>: N consecutive elements (N*sizeof(T) in {16, 8} bytes, or N == 1)

@@ -230,8 +230,14 @@ int LaunchDenseTree(const DenseLaunch& L, cudaStream_t stream) {
   if (grid > kMaxBlocks) grid = kMaxBlocks;
   int threads = L.threads;
   if (threads != 128 && threads != 256 && threads != 512) threads = kThreads;
+#if defined(MXKV_HOST_EMU)       // tests/sim/hostemu_tree.cc: this file compiled by g++, blocks run as CPU threads
+  (void)stream;
+  hostemu::RunGrid(fn, L, grid, threads);
+  return 0;
+#else
   fn<<<grid, threads, 0, stream>>>(L);
   return static_cast<int>(cudaGetLastError());
+#endif
 }
 
 }  // namespace mxkv

@@ -22,6 +22,8 @@
 #include "norm_math.h"
 #include "rsp_kernels.h"
 
+namespace sim { bool HostEmuTreeLaunch(const void* launch); }   // hostemu_tree.cc
+
 using namespace mxkv;
 
 namespace sim {
@@ -224,15 +226,30 @@ bool Dense(const std::vector<std::string>& t, void** args) {          // kv_dens
   return false;
 }
 
+// The tree-order kernels run from their OWN source (hostemu_tree.cc: csrc/tree_kernels.cu compiled for the host)
+// unless MXKV_SIM_TREE=semantic asks for the independent emulators below.  The cross-GPU rendezvous stays here.
+bool TreeFromSource(const DenseLaunch& L) {
+  static const bool semantic = [] { const char* v = getenv("MXKV_SIM_TREE"); return v != nullptr && std::string(v) == "semantic"; }();
+  if (semantic) return false;
+  RendezvousStart(L.sync);
+  struct AtExit { const SyncArgs& s; ~AtExit() { RendezvousEnd(s); } } at_exit{L.sync};
+  DenseLaunch local = L;
+  local.sync.mode = SYNC_NONE;
+  if (!::sim::HostEmuTreeLaunch(&local)) { fprintf(stderr, "sim: the tree kernel's launcher refused the launch\n"); abort(); }
+  return true;
+}
+
 bool DenseTree(const std::vector<std::string>& t, void** args) {      // kv_dense_tree_kernel<T, OPT, MP>
   const DenseLaunch& L = *static_cast<const DenseLaunch*>(args[0]);
   if (L.order != ORDER_TREE || L.bulk || L.nvls) return false;
+  if (TreeFromSource(L)) return true;
   return Dense(t, args);
 }
 
 bool SumTreeF64(void** args) {                                         // kv_sum_tree_f64_kernel
   const DenseLaunch& L = *static_cast<const DenseLaunch*>(args[0]);
   if (L.order != ORDER_TREE || L.dtype != kFloat64) return false;
+  if (TreeFromSource(L)) return true;
   RendezvousStart(L.sync);
   struct AtExit { const SyncArgs& s; ~AtExit() { RendezvousEnd(s); } } at_exit{L.sync};
   for (int i = 0; i < L.nworks; ++i) {

@@ -3,7 +3,7 @@
 # written to gpurun_out/ (merged back by gpurun).  Usage:
 #   gpurun --timeout 2400 -- 'bash tools/gpu_round.sh 1'
 #   gpurun --gpus 2 --timeout 1500 -- 'bash tools/gpu_round.sh 2'
-#   gpurun --gpus 8 --timeout 1800 -- 'bash tools/gpu_round.sh 8 [tune]'
+#   gpurun --gpus 8 --timeout 1800 -- 'bash tools/gpu_round.sh 8 [tune|tree]'
 # Order = priority: parity first (all failures listed, not just the first), then the bench lines, then profiles.
 N=${1:-1}
 MODE=${2:-full}
@@ -36,6 +36,15 @@ if [ "$N" = "1" ]; then
   run 300 bench_bert_lamb_n1.json python bench.py --workload bert --optimizer lamb --steps 40 $LIGHT
   run 300 bench_resnet_sgd_n1.json python bench.py --workload resnet50 --optimizer sgd --steps 100 $LIGHT
   run 300 bench_ref_n1.json python bench.py --impl reference --gpus 1 --steps 3 --warmup 1
+elif [ "$MODE" = "tree" ]; then
+  # MXNET_KVSTORE_USETREE=1: written after round 2's GPU minutes were spent -- first hardware run.
+  # Parity first (single process 3..N GPUs, then one process per GPU), then the bench line in tree order (its parity
+  # object follows the variable) next to the default order on the same box.   gpurun --gpus 4 -- 'bash tools/gpu_round.sh 4 tree'
+  run 600 pytest_tree_n$N.log python -m pytest tests/test_gpu_zzz_tree.py -m gpu -q --maxfail=25 -p no:cacheprovider --durations=8
+  tail -n 12 $OUT/pytest_tree_n$N.log
+  run 600 pytest_mp_n$N.log python -m pytest tests/test_gpu_multi.py -m gpu -q -p no:cacheprovider -k "one_process_per_gpu and not hierarchy"
+  MXNET_KVSTORE_USETREE=1 MXNET_KVSTORE_LOGTREE=1 run 300 bench_tree_n$N.json $(torchrun_ $N) bench.py --gpus $N --steps 200 --no-e2e --no-cpu-baseline --no-sweep --no-secondary
+  MXKV_B200_NVLS=0 run 300 bench_plain_n$N.json $(torchrun_ $N) bench.py --gpus $N --steps 200 --no-e2e --no-cpu-baseline --no-sweep --no-secondary
 elif [ "$MODE" = "tune" ]; then
   # kernel tuning only (8-GPU minutes are charged 8x): multicast kernel knobs, peer kernels, NCCL, then N=4 on the same box
   run 600 tune_nvls_n$N.txt $(torchrun_ $N) tools/tune_nvls.py

@@ -7,6 +7,10 @@ link matrix; the trees themselves are pinned to the reference's compiled solver 
 Needs three GPUs or more: two values add the same way in any order, and the engine does not switch kernels for them.
 (File name: written against the simulated runtime after the last hardware session of round 2; sorts after the
 hardware-validated files so that `pytest -x` reaches those first.)"""
+import os
+import subprocess
+import sys
+
 import numpy as np
 import pytest
 
@@ -247,3 +251,24 @@ def test_what_the_tree_mode_leaves_alone(monkeypatch):
     kvt.set_optimizer(mx.optimizer.LAMB(learning_rate=0.01))
     with pytest.raises(mx.MXNetError, match="USETREE"):
         kvt.push(0, [mx.nd.array(v, mx.gpu(d)) for d, v in enumerate(vals)])
+
+
+@pytest.mark.parametrize("world", [3, 4, 8])
+def test_one_process_per_gpu_under_the_tree(world):
+    """the torchrun deployment shape: tests/mp_worker.py's tree scenario alone (plain and arena-resident arrays, keys
+    the ranks shard, SGD-momentum and Adam on the store), every rank checking itself against the oracle."""
+    if os.environ.get("MXKV_SIM"):
+        pytest.skip("the simulated runtime launches its workers itself (test_sim_host_logic.py)")
+    if mx.num_gpus() < world:
+        pytest.skip("needs %d GPUs" % world)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ)
+    env["PYTHONPATH"] = root + os.pathsep + env.get("PYTHONPATH", "")
+    env["MXKV_MP_TREE_ONLY"] = "1"
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+           "--master-addr", "127.0.0.1", "--master-port", str(29700 + world), os.path.join(root, "tests", "mp_worker.py")]
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    sys.stdout.write(r.stdout[-3000:])
+    sys.stderr.write(r.stderr[-3000:])
+    assert r.returncode == 0
+    assert r.stdout.count("MP_WORKER_OK") == world

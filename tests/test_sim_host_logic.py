@@ -138,6 +138,37 @@ def test_one_process_per_gpu_on_simulator(sim_lib, world, tmp_path):
         assert "MP_WORKER_OK rank %d" % r in out, out[-2000:]
 
 
+@pytest.mark.parametrize("world", [3, 5, 8])
+def test_one_process_per_gpu_under_the_tree_on_simulator(sim_lib, world, tmp_path):
+    """MXNET_KVSTORE_USETREE=1 in the torchrun shape (tests/mp_worker.py, tree scenario only): 3, 5 and 8 ranks -- a
+    full tree, one with GPUs sitting levels out, the 8-leaf tree -- each running the tree kernel from its own source
+    (tests/sim/hostemu_tree.cc) on its shard, with the real flag rendezvous between the ranks."""
+    import glob
+    env = dict(os.environ)
+    env.update(MXKV_SIM="1", MXKV_SIM_MP="1", MXKV_SIM_RDV=str(tmp_path), MXKV_B200_LIBRARY_PATH=sim_lib,
+               MXKV_SIM_DEVICES=str(world), MXKV_B200_ARENA_MB="256", WORLD_SIZE=str(world), MXKV_MP_TREE_ONLY="1")
+    procs = []
+    for r in range(world):
+        e = dict(env, RANK=str(r), LOCAL_RANK=str(r))
+        procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "mp_worker.py")], env=e, cwd=ROOT,
+                                      stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    outs = []
+    try:
+        for p in procs:
+            out, _ = p.communicate(timeout=900)
+            outs.append(out)
+    finally:
+        for p in procs:
+            if p.poll() is None:
+                p.kill()
+        for p in procs:
+            for f in glob.glob("/dev/shm/mxkvsim_%d_*" % p.pid):
+                os.unlink(f)
+    for r, (p, out) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0, "rank %d:\n%s" % (r, out[-3000:])
+        assert "MP_WORKER_OK rank %d" % r in out, out[-2000:]
+
+
 @pytest.mark.parametrize("world,local_world", [(4, 2), (8, 4), (6, 2), (3, 1)])
 def test_multi_node_hierarchy_on_simulator(sim_lib, world, local_world, tmp_path):
     """kv.create('dist_device_sync'): `world` processes grouped into nodes of `local_world` (2 x 2, 2 x 4, 3 x 2

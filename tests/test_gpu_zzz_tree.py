@@ -253,6 +253,77 @@ def test_what_the_tree_mode_leaves_alone(monkeypatch):
         kvt.push(0, [mx.nd.array(v, mx.gpu(d)) for d, v in enumerate(vals)])
 
 
+_EXTRA = int(os.environ.get("MXKV_FUZZ_SEEDS", "0"))     # more random walks on demand (soak runs on the simulator)
+
+
+@pytest.mark.parametrize("seed", list(range(12 + _EXTRA)))
+def test_randomized_call_sequences_under_the_tree(monkeypatch, seed):
+    """The random walk of test_gpu_y_placement.py::test_randomized_call_sequences with the tree on: keys of one-shot and
+    two-shot size, some of them sliced, pushed from random subsets of the GPUs -- three or more distinct GPUs add in the
+    order of THAT subset's trees, fewer (or a value from the host) in the plain order --, pushes and fused pushpulls
+    interleaved with pulls to random devices, a fused optimizer switched on part-way (its state re-laid out when the
+    subset changes); compared with the oracle after every call."""
+    _need(3)
+    ngpu = _ngpu()
+    bound = 3000
+    trees = {n: _trees(n, bound=bound) for n in range(3, ngpu + 1)}
+    rng = np.random.default_rng(7000 + seed)
+    all_shapes = [(5,), (64, 10), (4099,), (70001,), (1200, 251), (37, 13)]
+    shapes = [all_shapes[i] for i in rng.choice(len(all_shapes), size=3, replace=False)]
+    keys = list(range(len(shapes)))
+    w0 = [rng.uniform(-1, 1, s).astype(np.float32) for s in shapes]
+    kv = _tree_store(monkeypatch, bound=bound)
+    okv = O.OracleKVStore("device")
+    kv.init(keys, [mx.nd.array(w, mx.gpu(int(rng.integers(ngpu)))) for w in w0])
+    okv.init(keys, [w.copy() for w in w0])
+    optname = [None, "sgd", "adam"][seed % 3]
+    kw = {"sgd": dict(learning_rate=0.05, momentum=0.9, wd=1e-3), "adam": dict(learning_rate=0.01, wd=1e-3)}.get(optname)
+    switch_at = int(rng.integers(0, 4))
+    tree_calls = 0
+
+    def ctx_of(d):
+        return mx.cpu() if d < 0 else mx.gpu(d)
+
+    def want_of(k):
+        want = np.empty(shapes[k], np.float32)
+        okv.pull(k, want)
+        return want
+
+    for step in range(10):
+        if optname and step == switch_at:
+            kv.set_optimizer(mx.optimizer.create(optname, **kw))
+            okv.set_optimizer(O.OracleOptimizer(optname, **kw))
+        ks = sorted(int(x) for x in rng.choice(keys, size=int(rng.integers(1, len(keys) + 1)), replace=False))
+        devs = [int(x) for x in rng.choice(ngpu, size=int(rng.integers(1, ngpu + 1)), replace=False)]
+        if rng.random() < 0.15:
+            devs = [-1] + devs[: max(0, len(devs) - 1)]          # one value from the host: no tree for this call
+        on_tree = len(devs) >= 3 and min(devs) >= 0
+        okv.tree = trees[len(devs)] if on_tree else None
+        tree_calls += int(on_tree)
+        grads = [[rng.uniform(-1, 1, shapes[k]).astype(np.float32) for _ in devs] for k in ks]
+        vals = [[mx.nd.array(g, ctx_of(d)) for g, d in zip(gs, devs)] for gs in grads]
+        before = mx.kv.launch_count("tree")
+        if rng.random() < 0.5:
+            kv.push(ks, vals)
+            okv.push(ks, grads)
+        else:
+            odevs = [int(x) for x in rng.choice(ngpu, size=int(rng.integers(1, ngpu + 1)), replace=False)]
+            outs = [[mx.nd.empty(shapes[k], mx.gpu(d)) for d in odevs] for k in ks]
+            kv.pushpull(ks, vals, out=outs)
+            okv.push(ks, grads)
+            for k, oo in zip(ks, outs):
+                want = want_of(k)
+                for o in oo:
+                    assert _bits_equal(o.asnumpy(), want), ("pushpull", seed, step, k, devs)
+        assert (mx.kv.launch_count("tree") > before) == on_tree, (seed, step, devs)
+        for k in ks:
+            d = int(rng.integers(-1, ngpu))
+            o = mx.nd.empty(shapes[k], ctx_of(d))
+            kv.pull(k, out=o)
+            assert _bits_equal(o.asnumpy(), want_of(k)), ("pull", seed, step, k, d, devs)
+    assert tree_calls > 0 or ngpu < 4
+
+
 @pytest.mark.parametrize("world", [3, 4, 8])
 def test_one_process_per_gpu_under_the_tree(world):
     """the torchrun deployment shape: tests/mp_worker.py's tree scenario alone (plain and arena-resident arrays, keys

@@ -24,7 +24,9 @@
 
 namespace mxkv {
 
+#if !defined(MXKV_HOST_EMU)
 static int sm_count(int device);
+#endif
 
 // ---------------------------------------------------------------------------
 // U packets per thread: gather n sources, sum in order, update, scatter.  All loads of a batch are
@@ -195,6 +197,14 @@ kv_dense_kernel(DenseLaunch L) {
 constexpr int kBulkThreads = 256;
 constexpr int kBulkMaxStages = 8;
 
+#if defined(MXKV_HOST_EMU)     // tests/sim/host_emu.h: the same protocol on a CPU (phase, byte count, parity wait)
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t) { hostemu::MbarInit(bar); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) { hostemu::MbarExpectTx(bar, bytes); }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) { hostemu::MbarWait(bar, parity); }
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  hostemu::BulkCopy(dst_smem, src_gmem, bytes, bar);
+}
+#else
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
@@ -220,10 +230,16 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                :: "r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+#endif
+
 template <int OPT, bool MP>
 __global__ void __launch_bounds__(kBulkThreads, 2)
 kv_dense_bulk_kernel(DenseLaunch L) {
+#if defined(MXKV_HOST_EMU)
+  unsigned char* const bulk_smem = hostemu::DynamicSmem();
+#else
   extern __shared__ __align__(128) unsigned char bulk_smem[];
+#endif
   __shared__ TensorWork tw;        // descriptor of the tile being computed (all threads)
   __shared__ TensorWork twp;       // descriptor of the tile being requested (thread 0 only)
   __shared__ __align__(8) uint64_t full[kBulkMaxStages];
@@ -239,7 +255,9 @@ kv_dense_bulk_kernel(DenseLaunch L) {
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; ++s) mbar_init(&full[s], 1);
+#if !defined(MXKV_HOST_EMU)
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#endif
   }
   __syncthreads();
   if (sync) barrier_start(L.sync);     // no peer byte may be requested before the rendezvous
@@ -401,6 +419,7 @@ static BulkKernelFn pick_bulk(int opt, int mp) {
   }
 }
 
+#if !defined(MXKV_HOST_EMU)     // (multimem: no CPU model of the switch; the simulated runtime never takes this variant)
 // ---------------------------------------------------------------------------
 // NVLS variant (float32, one process per GPU, arrays bound to an NVSwitch multicast object):
 // the reduce-scatter half is ONE multimem.ld_reduce per 16 bytes -- the switch adds the n replicas
@@ -592,6 +611,8 @@ int NvlsPlan(int device, int opt, int multi_precision, int unroll, int pipe, int
   return g > kMaxBlocks ? kMaxBlocks : g;
 }
 
+#endif  // !MXKV_HOST_EMU
+
 // ---------------------------------------------------------------------------
 // plain typed sum for the dtypes the reference's ElementwiseSum also accepts
 // (MSHADOW_TYPE_SWITCH: f64, u8, i32, i8, i64); native arithmetic, device order.
@@ -688,6 +709,7 @@ static DenseKernelFn pick_kernel(const DenseLaunch& L) {
   }
 }
 
+#if !defined(MXKV_HOST_EMU)
 static int g_num_sms[64] = {0};
 
 static int sm_count(int device) {
@@ -890,5 +912,25 @@ int LaunchFill(void* ptr, int value_byte, size_t bytes, cudaStream_t s) {
   if (bytes == 0) return 0;
   return static_cast<int>(cudaMemsetAsync(ptr, value_byte, bytes, s));
 }
+
+#else   // MXKV_HOST_EMU
+// tests/sim/hostemu_dense.cc: this file compiled by g++ -- the per-thread, the staged and the typed-sum kernels run
+// as CPU threads from the source above.  The instantiation is chosen by the same pick_* code the device launch uses.
+int LaunchDenseHostEmu(const DenseLaunch& L) {
+  if (L.order == ORDER_TREE || L.nvls) return 1;
+  const int grid = L.grid < 1 ? 1 : (L.grid > kMaxBlocks ? kMaxBlocks : L.grid);
+  if (L.bulk) {
+    BulkKernelFn bf = pick_bulk(L.opt, L.multi_precision);
+    if (bf == nullptr || L.dtype != kFloat32) return 1;
+    const size_t smem = static_cast<size_t>(L.bulk_stages) * L.bulk_arrays * L.chunk_elems * 4;
+    hostemu::RunGrid(bf, L, grid, kBulkThreads, smem);
+    return 0;
+  }
+  DenseKernelFn fn = pick_kernel(L);
+  if (fn == nullptr) return 1;
+  hostemu::RunGrid(fn, L, grid, L.threads);
+  return 0;
+}
+#endif  // MXKV_HOST_EMU
 
 }  // namespace mxkv

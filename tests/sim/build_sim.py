@@ -22,7 +22,7 @@ def build(verbose=False):
     b.build()                                   # the product library and its object files
     os.makedirs(OUT, exist_ok=True)
     fake = os.path.join(OUT, "libcudart.so.12")
-    srcs = [os.path.join(HERE, f) for f in ("fake_cudart.cc", "sim_kernels.cc", "sim_rsp.cc", "hostemu_tree.cc")]
+    srcs = [os.path.join(HERE, f) for f in ("fake_cudart.cc", "sim_kernels.cc", "sim_rsp.cc", "hostemu_tree.cc", "hostemu_dense.cc")]
     cmd = ["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-Wall", "-Wno-unknown-pragmas", "-pthread", "-fno-strict-aliasing",
            "-I", os.path.join(PKG, "csrc"), "-I", os.path.join(CUDA, "include"), "-I", HERE] + srcs + \
           ["-o", fake, "-Wl,-soname,libcudart.so.12", "-Wl,--version-script=" + os.path.join(HERE, "cudart.map")]
@@ -56,7 +56,7 @@ def build_sanitized(verbose=False):
     san = ["-fsanitize=address", "-fsanitize=undefined", "-fno-sanitize=vptr", "-fno-omit-frame-pointer",
            "-fno-sanitize-recover=undefined"]
     fake = os.path.join(out, "libcudart.so.12")
-    srcs = [os.path.join(HERE, f) for f in ("fake_cudart.cc", "sim_kernels.cc", "sim_rsp.cc", "hostemu_tree.cc")]
+    srcs = [os.path.join(HERE, f) for f in ("fake_cudart.cc", "sim_kernels.cc", "sim_rsp.cc", "hostemu_tree.cc", "hostemu_dense.cc")]
     deps = srcs + [os.path.join(PKG, "csrc", f) for f in os.listdir(os.path.join(PKG, "csrc"))] + \
            [os.path.join(HERE, "sim.h"), os.path.abspath(__file__)]
     sim = os.path.join(out, "libmxkv_b200_sim.so")

@@ -22,7 +22,10 @@
 #include "norm_math.h"
 #include "rsp_kernels.h"
 
-namespace sim { bool HostEmuTreeLaunch(const void* launch); }   // hostemu_tree.cc
+namespace sim {
+bool HostEmuTreeLaunch(const void* launch);    // hostemu_tree.cc
+bool HostEmuDenseLaunch(const void* launch);   // hostemu_dense.cc
+}
 
 using namespace mxkv;
 
@@ -216,8 +219,22 @@ bool DenseT(const DenseLaunch& L, int opt, bool mp) {
   return true;
 }
 
+// The per-thread, staged and typed-sum kernels run from their OWN source (hostemu_dense.cc: csrc/kernels.cu compiled
+// for the host) unless MXKV_SIM_DENSE=semantic asks for the independent emulators.  The cross-GPU rendezvous stays here.
+bool DenseFromSource(const DenseLaunch& L) {
+  static const bool semantic = [] { const char* v = getenv("MXKV_SIM_DENSE"); return v != nullptr && std::string(v) == "semantic"; }();
+  if (semantic) return false;
+  RendezvousStart(L.sync);
+  struct AtExit { const SyncArgs& s; ~AtExit() { RendezvousEnd(s); } } at_exit{L.sync};
+  DenseLaunch local = L;
+  local.sync.mode = SYNC_NONE;
+  if (!::sim::HostEmuDenseLaunch(&local)) { fprintf(stderr, "sim: kernels.cu's launcher refused the launch\n"); abort(); }
+  return true;
+}
+
 bool Dense(const std::vector<std::string>& t, void** args) {          // kv_dense_kernel<T, OPT, MP, SMALLN>
   const DenseLaunch& L = *static_cast<const DenseLaunch*>(args[0]);
+  if (L.order != ORDER_TREE && DenseFromSource(L)) return true;
   const int opt = ToInt(t[1]);
   const bool mp = ToInt(t[2]) != 0;
   if (t[0] == "float") return DenseT<float>(L, opt, mp);
@@ -271,6 +288,7 @@ bool SumTreeF64(void** args) {                                         // kv_sum
 
 bool DenseBulk(const std::vector<std::string>& t, void** args) {      // kv_dense_bulk_kernel<OPT, MP>
   const DenseLaunch& L = *static_cast<const DenseLaunch*>(args[0]);
+  if (DenseFromSource(L)) return true;
   return DenseT<float>(L, ToInt(t[0]), ToInt(t[1]) != 0);
 }
 
@@ -290,6 +308,7 @@ void TypedSum(const DenseLaunch& L) {
 
 bool SumTyped(const std::vector<std::string>& t, void** args) {       // kv_sum_typed_kernel<T>
   const DenseLaunch& L = *static_cast<const DenseLaunch*>(args[0]);
+  if (DenseFromSource(L)) return true;
   const std::string& n = t[0];
   if (n == "double") TypedSum<double>(L);
   else if (n == "int") TypedSum<int32_t>(L);

@@ -47,7 +47,7 @@ __device__ __forceinline__ void st_flag_volatile(uint32_t* p, uint32_t v) {
 }
 __device__ __forceinline__ uint32_t ld_flag_volatile(const uint32_t* p) {
 #if defined(MXKV_HOST_EMU)
-  return __atomic_load_n(p, __ATOMIC_RELAXED);
+  return hostemu::PoliteLoad(p, __ATOMIC_RELAXED);
 #else
   uint32_t v;
   asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -63,7 +63,7 @@ __device__ __forceinline__ void st_flag_release(uint32_t* p, uint32_t v) {
 }
 __device__ __forceinline__ uint32_t ld_flag_acquire(const uint32_t* p) {
 #if defined(MXKV_HOST_EMU)
-  return __atomic_load_n(p, __ATOMIC_ACQUIRE);
+  return hostemu::PoliteLoad(p, __ATOMIC_ACQUIRE);
 #else
   uint32_t v;
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");

@@ -14,6 +14,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cstdint>
 #include <cstdio>
@@ -49,6 +50,13 @@ inline P* Aligned(P* p, uintptr_t bytes) {
     std::abort();
   }
   return p;
+}
+
+// a flag load of a spin loop: the peer it waits for may need this core (several ranks of 8 threads share the machine)
+inline uint32_t PoliteLoad(const uint32_t* p, int order) {
+  const uint32_t v = __atomic_load_n(p, order);
+  std::this_thread::yield();
+  return v;
 }
 
 struct Coords { uint3 thread_idx, block_idx; dim3 block_dim, grid_dim; };
@@ -190,7 +198,11 @@ inline void MbarWait(const uint64_t* bar, uint32_t parity) {
 #define gridDim (::hostemu::Me().grid_dim)
 
 inline void __syncthreads() { ::hostemu::Pool::Get().barrier().Wait(); }
-inline long long clock64() { return 0; }
+// ~SM cycles: the kernels' spin timeouts (MXKV_B200_SPIN_TIMEOUT_S at 1.9 GHz) then mean what they say
+inline long long clock64() {
+  return static_cast<long long>(std::chrono::duration_cast<std::chrono::nanoseconds>(
+      std::chrono::steady_clock::now().time_since_epoch()).count() * 1.9);
+}
 inline void __trap() { std::abort(); }
 inline void __threadfence_system() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 inline uint32_t atomicAdd(uint32_t* p, uint32_t v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }

@@ -224,6 +224,10 @@ bool DenseT(const DenseLaunch& L, int opt, bool mp) {
 bool DenseFromSource(const DenseLaunch& L) {
   static const bool semantic = [] { const char* v = getenv("MXKV_SIM_DENSE"); return v != nullptr && std::string(v) == "semantic"; }();
   if (semantic) return false;
+  if (MultiProcess() && L.sync.mode != SYNC_NONE) {        // (as in TreeFromSource: the kernels' own rendezvous)
+    if (!::sim::HostEmuDenseLaunch(&L)) { fprintf(stderr, "sim: kernels.cu's launcher refused the launch\n"); abort(); }
+    return true;
+  }
   RendezvousStart(L.sync);
   struct AtExit { const SyncArgs& s; ~AtExit() { RendezvousEnd(s); } } at_exit{L.sync};
   DenseLaunch local = L;
@@ -248,6 +252,12 @@ bool Dense(const std::vector<std::string>& t, void** args) {          // kv_dens
 bool TreeFromSource(const DenseLaunch& L) {
   static const bool semantic = [] { const char* v = getenv("MXKV_SIM_TREE"); return v != nullptr && std::string(v) == "semantic"; }();
   if (semantic) return false;
+  if (MultiProcess() && L.sync.mode != SYNC_NONE) {
+    // one process per simulated GPU: the pads are shared memory and every rank runs the same grid block by block, so
+    // the kernel's OWN rendezvous (device_utils.cuh: barrier_start / barrier_end, every block's flag slots) runs for real
+    if (!::sim::HostEmuTreeLaunch(&L)) { fprintf(stderr, "sim: the tree kernel's launcher refused the launch\n"); abort(); }
+    return true;
+  }
   RendezvousStart(L.sync);
   struct AtExit { const SyncArgs& s; ~AtExit() { RendezvousEnd(s); } } at_exit{L.sync};
   DenseLaunch local = L;

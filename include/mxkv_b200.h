@@ -245,7 +245,8 @@ MXKV_DLL int MXKVB200SetAutoFence(int auto_fence);
 MXKV_DLL int MXKVB200Fence(int dev_id);
 MXKV_DLL int MXKVB200GetLaunchCount(int64_t* out);
 /* Dense reduce(+update) launches so far by kernel variant: 0 = per-thread (kv_dense_kernel), 1 = shared-memory
- * staged (kv_dense_bulk_kernel, cp.async.bulk + mbarrier), 2 = NVSwitch multicast (kv_dense_nvls_kernel).
+ * staged (kv_dense_bulk_kernel, cp.async.bulk + mbarrier), 2 = NVSwitch multicast (kv_dense_nvls_kernel),
+ * 3 = tree order (kv_dense_tree_kernel / kv_sum_tree_f64_kernel, MXNET_KVSTORE_USETREE=1).
  * Test / bench instrumentation: proves which kernel a parity check has just exercised. */
 MXKV_DLL int MXKVB200GetVariantLaunchCount(int variant, int64_t* out);
 /* push / pushpull calls of this store served from a cached launch plan (a call whose keys and arrays repeat

@@ -5,7 +5,7 @@
 #include "norm_kernels.h"
 #include "optim_math.h"
 
-#if !defined(__CUDACC__)
+#if !defined(__CUDACC__) && !defined(MXKV_HOST_EMU)     // (tests/sim/host_emu.h brings its own)
 #include <cstring>
 static inline unsigned int __float_as_uint(float x) { unsigned int u; std::memcpy(&u, &x, 4); return u; }
 #endif

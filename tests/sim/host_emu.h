@@ -23,6 +23,7 @@
 #include <functional>
 #include <mutex>
 #include <thread>
+#include <ucontext.h>
 #include <vector>
 
 #undef __device__
@@ -60,7 +61,7 @@ inline uint32_t PoliteLoad(const uint32_t* p, int order) {
 }
 
 struct Coords { uint3 thread_idx, block_idx; dim3 block_dim, grid_dim; };
-inline Coords& Me() { static thread_local Coords c; return c; }
+inline Coords& ThreadCoords() { static thread_local Coords c; return c; }
 
 // sense-reversing barrier: a few spins, then yield (the suite runs several processes of these threads on few cores)
 class BlockBarrier {
@@ -142,7 +143,7 @@ void RunGridSmem(void (*kernel)(P...), int grid, size_t smem_bytes, const A&... 
   std::lock_guard<std::mutex> one_launch(pool.launch_mutex());
   pool.current_smem() = pool.dynamic_smem(smem_bytes);
   pool.Run([&](int t) {                 // one hand-over per launch; the blocks are separated by the block barrier
-    Coords& c = Me();
+    Coords& c = ThreadCoords();
     c.thread_idx = make_uint3(t, 0, 0);
     c.block_dim = dim3(kHostEmuThreads, 1, 1);
     c.grid_dim = dim3(grid, 1, 1);
@@ -156,6 +157,201 @@ void RunGridSmem(void (*kernel)(P...), int grid, size_t smem_bytes, const A&... 
 template <typename Launch>
 void RunGrid(void (*kernel)(Launch), const Launch& L, int grid, int /*threads_asked*/, size_t smem_bytes = 0) {
   RunGridSmem(kernel, grid, smem_bytes, L);
+}
+
+// ---- fibers: a block with its REAL number of threads, for kernels that talk inside warps ------------------------------
+// The layer-wise-optimizer kernels reduce with __shfl_xor_sync over 32 lanes and add the warps' totals in warp order:
+// their sums are only the hardware's sums when a block has the hardware's 512 (256) threads.  Those blocks run here as
+// that many user-level contexts on the calling OS thread, switched round-robin at barriers and warp exchanges
+// (deterministic; one block at a time, so `static` still stands in for __shared__).
+// A context switch that saves what the SysV x86-64 ABI says a call preserves (rbx, rbp, r12-r15, the stack pointer)
+// and nothing else: swapcontext also saves the signal mask, a system call per switch, and these kernels switch
+// hundreds of thousands of times per launch.  Other architectures keep swapcontext.
+#if defined(__x86_64__)
+#define MXKV_FAST_FIBERS 1
+extern "C" void mxkv_hostemu_switch(void** save_sp, void* load_sp);
+asm(R"(
+.text
+.weak mxkv_hostemu_switch
+.type mxkv_hostemu_switch,@function
+mxkv_hostemu_switch:
+  pushq %rbp
+  pushq %rbx
+  pushq %r12
+  pushq %r13
+  pushq %r14
+  pushq %r15
+  movq %rsp, (%rdi)
+  movq %rsi, %rsp
+  popq %r15
+  popq %r14
+  popq %r13
+  popq %r12
+  popq %rbx
+  popq %rbp
+  ret
+.size mxkv_hostemu_switch,.-mxkv_hostemu_switch
+)");
+#endif
+
+class FiberBlock {
+ public:
+  static FiberBlock*& Current() { static FiberBlock* b = nullptr; return b; }
+  struct Fiber {
+#if defined(MXKV_FAST_FIBERS)
+    void* sp = nullptr;
+#else
+    ucontext_t ctx;
+#endif
+    Coords coords;
+    bool done = false;
+  };
+  FiberBlock(int threads) : fibers_(threads), warp_arrived_((threads + 31) / 32, 0), warp_gen_((threads + 31) / 32, 0),
+                            slots_(2 * static_cast<size_t>(threads)), bank_of_(threads, 0) {}
+  Fiber& cur() { return fibers_[cur_]; }
+  void Yield() {
+#if defined(MXKV_FAST_FIBERS)
+    mxkv_hostemu_switch(&fibers_[cur_].sp, sched_sp_);
+#else
+    swapcontext(&fibers_[cur_].ctx, &sched_);
+#endif
+  }
+  void SyncThreads() {
+    const unsigned gen = gen_;
+    if (++arrived_ == live_) { arrived_ = 0; ++gen_; return; }
+    while (gen_ == gen) Yield();
+  }
+  // all lanes of the calling fiber's warp (the kernels only use full masks outside divergent code)
+  void SyncWarp() {
+    const int w = cur_ >> 5;
+    const int lanes = std::min<int>(32, static_cast<int>(fibers_.size()) - w * 32);
+    const unsigned gen = warp_gen_[w];
+    if (++warp_arrived_[w] == lanes) { warp_arrived_[w] = 0; ++warp_gen_[w]; return; }
+    while (warp_gen_[w] == gen) Yield();
+  }
+  // Two banks of slots, used alternately: a lane can only write the bank being read by a slower lane of its warp after
+  // it has passed the NEXT exchange's barrier, which that slower lane must reach first -- one barrier per exchange.
+  template <typename T>
+  T Exchange(T v, int src_lane) {           // value of lane `src_lane` of my warp (own value when that lane does not exist)
+    static_assert(sizeof(T) <= 8, "shuffles move up to 8 bytes");
+    const int w = cur_ >> 5, lane = cur_ & 31;
+    uint64_t bits = 0;
+    std::memcpy(&bits, &v, sizeof(T));
+    uint64_t* bank = slots_.data() + (bank_of_[cur_] ^= 1) * fibers_.size();
+    bank[cur_] = bits;
+    SyncWarp();
+    const int lanes = std::min<int>(32, static_cast<int>(fibers_.size()) - w * 32);
+    const int src = (src_lane >= 0 && src_lane < lanes) ? src_lane : lane;
+    T out;
+    std::memcpy(&out, &bank[w * 32 + src], sizeof(T));
+    return out;
+  }
+  unsigned Ballot(bool pred) {
+    const int w = cur_ >> 5;
+    uint64_t* bank = slots_.data() + (bank_of_[cur_] ^= 1) * fibers_.size();
+    bank[cur_] = pred ? 1 : 0;
+    SyncWarp();
+    const int lanes = std::min<int>(32, static_cast<int>(fibers_.size()) - w * 32);
+    unsigned m = 0;
+    for (int l = 0; l < lanes; ++l) if (bank[w * 32 + l]) m |= 1u << l;
+    return m;
+  }
+  template <typename F>
+  void Run(int block, int grid, F&& body) {
+    static std::vector<unsigned char> stacks;             // reused from launch to launch
+    constexpr size_t kStack = 128 * 1024;
+    if (stacks.size() < fibers_.size() * kStack) stacks.resize(fibers_.size() * kStack);
+    body_ = [&body] { body(); };
+    live_ = static_cast<int>(fibers_.size());
+    for (size_t t = 0; t < fibers_.size(); ++t) {
+      Fiber& f = fibers_[t];
+      f.coords.thread_idx = make_uint3(static_cast<unsigned>(t), 0, 0);
+      f.coords.block_idx = make_uint3(block, 0, 0);
+      f.coords.block_dim = dim3(static_cast<unsigned>(fibers_.size()), 1, 1);
+      f.coords.grid_dim = dim3(grid, 1, 1);
+      unsigned char* top = stacks.data() + (t + 1) * kStack;
+#if defined(MXKV_FAST_FIBERS)
+      // a fresh stack as mxkv_hostemu_switch expects to find one: six saved registers, then the address to `ret` to.
+      // 16-byte alignment: at Entry's first instruction rsp % 16 == 8, as after a call
+      void** sp = reinterpret_cast<void**>(reinterpret_cast<uintptr_t>(top) & ~uintptr_t(15));
+      *--sp = nullptr;                                   // (keeps the alignment; Entry never returns)
+      *--sp = reinterpret_cast<void*>(&FiberBlock::Entry);
+      for (int r = 0; r < 6; ++r) *--sp = nullptr;
+      f.sp = sp;
+#else
+      getcontext(&f.ctx);
+      f.ctx.uc_stack.ss_sp = top - kStack;
+      f.ctx.uc_stack.ss_size = kStack;
+      f.ctx.uc_link = &sched_;
+      makecontext(&f.ctx, reinterpret_cast<void (*)()>(&FiberBlock::Entry), 0);
+#endif
+    }
+    FiberBlock* prev = Current();
+    Current() = this;
+    int remaining = live_;
+    while (remaining > 0) {
+      for (cur_ = 0; cur_ < static_cast<int>(fibers_.size()); ++cur_) {
+        if (fibers_[cur_].done) continue;
+#if defined(MXKV_FAST_FIBERS)
+        mxkv_hostemu_switch(&sched_sp_, fibers_[cur_].sp);
+#else
+        swapcontext(&sched_, &fibers_[cur_].ctx);
+#endif
+        if (fibers_[cur_].done) { --remaining; --live_; }
+      }
+    }
+    Current() = prev;
+  }
+ private:
+  static void Entry() {
+    FiberBlock* b = Current();
+    b->body_();
+    b->fibers_[b->cur_].done = true;
+#if defined(MXKV_FAST_FIBERS)
+    for (;;) b->Yield();                    // back to the scheduler for good (a finished fiber is never resumed)
+#endif                                      // (ucontext: uc_link takes the context back to the scheduler)
+  }
+  std::vector<Fiber> fibers_;
+#if !defined(MXKV_FAST_FIBERS)
+  ucontext_t sched_;
+#endif
+  std::function<void()> body_;
+  int cur_ = 0, arrived_ = 0, live_ = 0;
+  unsigned gen_ = 0;
+  std::vector<int> warp_arrived_;
+  std::vector<unsigned> warp_gen_;
+  std::vector<uint64_t> slots_;
+  std::vector<unsigned char> bank_of_;
+#if defined(MXKV_FAST_FIBERS)
+  void* sched_sp_ = nullptr;
+#endif
+};
+
+// every block of the grid, one after another, each with `threads` fibers
+template <typename... P, typename... A>
+void RunGridFibers(void (*kernel)(P...), int grid, int threads, size_t smem_bytes, const A&... args) {
+  Pool& pool = Pool::Get();
+  std::lock_guard<std::mutex> one_launch(pool.launch_mutex());
+  pool.current_smem() = pool.dynamic_smem(smem_bytes);
+  for (int b = 0; b < grid; ++b) {
+    FiberBlock block(threads);
+    block.Run(b, grid, [&] { kernel(args...); });
+  }
+}
+
+// `kernel<<<grid, threads, smem, stream>>>(args)` of a .cu file compiled for the host: build_sim.py rewrites the launch
+// into hostemu::Launch(kernel, grid, threads, smem)(args)
+template <typename... P>
+struct Launcher {
+  void (*kernel)(P...);
+  int grid, threads;
+  size_t smem;
+  template <typename... A>
+  void operator()(const A&... args) const { RunGridFibers(kernel, grid, threads, smem, static_cast<P>(args)...); }
+};
+template <typename... P>
+Launcher<P...> Launch(void (*kernel)(P...), int64_t grid, int threads, size_t smem) {
+  return Launcher<P...>{kernel, static_cast<int>(grid), threads, smem};
 }
 
 // ---- mbarrier with a transaction count + cp.async.bulk (staged kernel) ------------------------------------------------
@@ -192,12 +388,34 @@ inline void MbarWait(const uint64_t* bar, uint32_t parity) {
 
 }  // namespace hostemu
 
+namespace hostemu {
+inline Coords& Me() { FiberBlock* b = FiberBlock::Current(); return b != nullptr ? b->cur().coords : ThreadCoords(); }
+}
 #define threadIdx (::hostemu::Me().thread_idx)
 #define blockIdx (::hostemu::Me().block_idx)
 #define blockDim (::hostemu::Me().block_dim)
 #define gridDim (::hostemu::Me().grid_dim)
 
-inline void __syncthreads() { ::hostemu::Pool::Get().barrier().Wait(); }
+inline void __syncthreads() {
+  if (::hostemu::FiberBlock* b = ::hostemu::FiberBlock::Current()) b->SyncThreads();
+  else ::hostemu::Pool::Get().barrier().Wait();
+}
+// warp exchanges (fiber blocks only; every lane of the warp calls)
+template <typename T> inline T __shfl_xor_sync(unsigned, T v, int lane_mask) {
+  ::hostemu::FiberBlock* b = ::hostemu::FiberBlock::Current();
+  return b->Exchange(v, static_cast<int>(threadIdx.x & 31) ^ lane_mask);
+}
+template <typename T> inline T __shfl_up_sync(unsigned, T v, unsigned delta) {
+  ::hostemu::FiberBlock* b = ::hostemu::FiberBlock::Current();
+  return b->Exchange(v, static_cast<int>(threadIdx.x & 31) - static_cast<int>(delta));
+}
+template <typename T> inline T __shfl_sync(unsigned, T v, int src_lane) {
+  return ::hostemu::FiberBlock::Current()->Exchange(v, src_lane & 31);
+}
+inline unsigned __ballot_sync(unsigned, int pred) { return ::hostemu::FiberBlock::Current()->Ballot(pred != 0); }
+// occupancy queries of a launcher compiled for the host (the C++ overloads exist under nvcc only)
+template <typename... P>
+inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int* n, void (*)(P...), int, size_t) { *n = 2; return cudaSuccess; }
 // ~SM cycles: the kernels' spin timeouts (MXKV_B200_SPIN_TIMEOUT_S at 1.9 GHz) then mean what they say
 inline long long clock64() {
   return static_cast<long long>(std::chrono::duration_cast<std::chrono::nanoseconds>(

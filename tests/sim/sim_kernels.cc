@@ -25,6 +25,15 @@
 namespace sim {
 bool HostEmuTreeLaunch(const void* launch);    // hostemu_tree.cc
 bool HostEmuDenseLaunch(const void* launch);   // hostemu_dense.cc
+// hostemu_norm.cc
+bool HostEmuNormFirst(const void* launch, int grad_only);
+bool HostEmuNormMid(const void* launch);
+bool HostEmuNormApply(const void* launch);
+bool HostEmuNormFinalize(const void* works, const int64_t* prefix, int nworks, int nslots, int s0, int s1, int s2);
+void HostEmuSumSq(int type, const void* items, const int64_t* prefix, int nitems, int64_t total_chunks, float scale, float* psum,
+                  int chunk_elems, int grid);
+void HostEmuSumSqFinalize(const int64_t* prefix, const float* psum, float* out_sumsq, float* out_bad, int nitems);
+void HostEmuAllFiniteFlag(const float* bad, int n, float* out, int init);
 }
 
 using namespace mxkv;
@@ -432,9 +441,28 @@ bool NormFirstT(const NormLaunch& L, bool mp, bool grad_only) {
   return true;
 }
 
+// The layer-wise-optimizer kernels run from their OWN source with their real thread counts (hostemu_norm.cc) unless
+// MXKV_SIM_NORM=semantic asks for the independent emulators.  phase: 0 first, 1 mid, 2 apply.
+bool NormFromSource() {
+  static const bool semantic = [] { const char* v = getenv("MXKV_SIM_NORM"); return v != nullptr && std::string(v) == "semantic"; }();
+  return !semantic;
+}
+bool NormLaunchFromSource(const NormLaunch& L, int phase, int grad_only) {
+  if (!NormFromSource()) return false;
+  NormLaunch local = L;
+  const bool own_rendezvous = MultiProcess() && L.sync.mode != SYNC_NONE;   // (as for the dense kernels)
+  if (!own_rendezvous) { RendezvousStart(L.sync); local.sync.mode = SYNC_NONE; }
+  const bool ok = phase == 0 ? ::sim::HostEmuNormFirst(&local, grad_only)
+                             : (phase == 1 ? ::sim::HostEmuNormMid(&local) : ::sim::HostEmuNormApply(&local));
+  if (!own_rendezvous) RendezvousEnd(L.sync);
+  if (!ok) { fprintf(stderr, "sim: norm_kernels.cu's launcher refused the launch\n"); abort(); }
+  return true;
+}
+
 bool NormFirst(const std::vector<std::string>& t, void** args) {      // kv_norm_first_kernel<T, MP, GRAD_ONLY>
   const NormLaunch& L = *static_cast<const NormLaunch*>(args[0]);
   const bool mp = ToInt(t[1]) != 0, go = ToInt(t[2]) != 0;
+  if (NormLaunchFromSource(L, 0, go ? 1 : 0)) return true;
   if (t[0] == "float") return NormFirstT<float>(L, mp, go);
   if (t[0] == "__half") return NormFirstT<__half>(L, mp, go);
   if (t[0] == "__nv_bfloat16") return NormFirstT<__nv_bfloat16>(L, mp, go);
@@ -447,6 +475,10 @@ bool NormFinalize(const LaunchInfo& info, void** args) {   // (works, prefix, ns
   const int nslots = *static_cast<const int*>(args[2]);
   const int slots[3] = {*static_cast<const int*>(args[3]), *static_cast<const int*>(args[4]),
                         *static_cast<const int*>(args[5])};
+  if (NormFromSource()) {
+    if (!::sim::HostEmuNormFinalize(works, prefix, static_cast<int>(info.grid), nslots, slots[0], slots[1], slots[2])) abort();
+    return true;
+  }
   for (unsigned b = 0; b < info.grid; ++b) {
     const NormWork& w = works[b];
     const int64_t nchunks = prefix[b + 1] - prefix[b];
@@ -503,6 +535,7 @@ bool NormMid(const std::vector<std::string>& t, void** args) {        // kv_norm
   const NormLaunch& L = *static_cast<const NormLaunch*>(args[0]);
   const bool mp = ToInt(t[1]) != 0;
   const int kind = ToInt(t[2]);
+  if (NormLaunchFromSource(L, 1, 0)) return true;
   if (t[0] == "float") return NormMidT<float>(L, mp, kind);
   if (t[0] == "__half") return NormMidT<__half>(L, mp, kind);
   if (t[0] == "__nv_bfloat16") return NormMidT<__nv_bfloat16>(L, mp, kind);
@@ -559,6 +592,7 @@ bool NormApply(const std::vector<std::string>& t, void** args) {      // kv_norm
   const NormLaunch& L = *static_cast<const NormLaunch*>(args[0]);
   const bool mp = ToInt(t[1]) != 0;
   const int flavor = ToInt(t[2]);
+  if (NormLaunchFromSource(L, 2, 0)) return true;
   if (t[0] == "float") return NormApplyT<float>(L, mp, flavor);
   if (t[0] == "__half") return NormApplyT<__half>(L, mp, flavor);
   if (t[0] == "__nv_bfloat16") return NormApplyT<__nv_bfloat16>(L, mp, flavor);
@@ -586,13 +620,20 @@ void SumSqT(const SumSqItem* items, const int64_t* prefix, int nitems, float sca
   }
 }
 
-bool SumSq(const std::vector<std::string>& t, void** args) {   // (items, prefix, nitems, total_chunks, scale, psum, chunk)
+bool SumSq(const std::vector<std::string>& t, void** args, unsigned sumsq_grid) {   // (items, prefix, nitems, total_chunks, scale, psum, chunk)
   const SumSqItem* items = *static_cast<const SumSqItem* const*>(args[0]);
   const int64_t* prefix = *static_cast<const int64_t* const*>(args[1]);
   const int nitems = *static_cast<const int*>(args[2]);
   const float scale = *static_cast<const float*>(args[4]);
   float* psum = *static_cast<float* const*>(args[5]);
   const int chunk = *static_cast<const int*>(args[6]);
+  if (NormFromSource()) {
+    const int64_t total_chunks = *static_cast<const int64_t*>(args[3]);
+    const int type = t[0] == "float" ? 0 : (t[0] == "__half" ? 1 : (t[0] == "__nv_bfloat16" ? 2 : (t[0] == "double" ? 3 : -1)));
+    if (type < 0) return false;
+    ::sim::HostEmuSumSq(type, items, prefix, nitems, total_chunks, scale, psum, chunk, static_cast<int>(sumsq_grid));
+    return true;
+  }
   if (t[0] == "float") SumSqT<float>(items, prefix, nitems, scale, psum, chunk);
   else if (t[0] == "__half") SumSqT<__half>(items, prefix, nitems, scale, psum, chunk);
   else if (t[0] == "__nv_bfloat16") SumSqT<__nv_bfloat16>(items, prefix, nitems, scale, psum, chunk);
@@ -606,6 +647,7 @@ bool SumSqFinalize(const LaunchInfo& info, void** args) {   // (prefix, psum, ou
   const float* psum = *static_cast<const float* const*>(args[1]);
   float* out_sumsq = *static_cast<float* const*>(args[2]);
   float* out_bad = *static_cast<float* const*>(args[3]);
+  if (NormFromSource()) { ::sim::HostEmuSumSqFinalize(prefix, psum, out_sumsq, out_bad, static_cast<int>(info.grid)); return true; }
   for (unsigned b = 0; b < info.grid; ++b) {
     float ps[256] = {0.f}, pb[256] = {0.f};
     for (int64_t i = prefix[b]; i < prefix[b + 1]; ++i) {
@@ -623,6 +665,7 @@ bool AllFiniteFlag(void** args) {   // (bad, n, out, init)
   const int n = *static_cast<const int*>(args[1]);
   float* out = *static_cast<float* const*>(args[2]);
   const int init = *static_cast<const int*>(args[3]);
+  if (NormFromSource()) { ::sim::HostEmuAllFiniteFlag(bad, n, out, init); return true; }
   float v = init ? 1.0f : out[0];
   for (int i = 0; i < n; ++i) if (bad[i] > 0.f) v = 0.0f;
   out[0] = v;
@@ -655,7 +698,7 @@ bool Dispatch(const LaunchInfo& info, void** args) {
   if (base == "mxkv::kv_norm_finalize_kernel") return NormFinalize(info, args);
   if (base == "mxkv::kv_norm_mid_kernel") return NormMid(t, args);
   if (base == "mxkv::kv_norm_apply_kernel") return NormApply(t, args);
-  if (base == "mxkv::kv_sumsq_kernel") return SumSq(t, args);
+  if (base == "mxkv::kv_sumsq_kernel") return SumSq(t, args, info.grid);
   if (base == "mxkv::kv_sumsq_finalize_kernel") return SumSqFinalize(info, args);
   if (base == "mxkv::kv_all_finite_flag_kernel") return AllFiniteFlag(args);
   return DispatchRsp(info, base, t, args);

@@ -129,7 +129,7 @@ API cudaError_t cudaLaunchKernel(const void* func, dim3 grid, dim3 block, void**
   if (noexec) return cudaSuccess;
   sim::LaunchInfo info;
   info.name = name;
-  info.grid = grid.x; info.block = block.x; info.smem = smem;
+  info.grid = grid.x; info.grid_y = grid.y; info.block = block.x; info.smem = smem;
   info.device = g_device;
   if (!sim::Dispatch(info, args)) {
     fprintf(stderr, "[mxkv sim] no emulator for kernel: %s\n", name.c_str());

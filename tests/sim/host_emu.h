@@ -221,6 +221,15 @@ class FiberBlock {
     if (++arrived_ == live_) { arrived_ = 0; ++gen_; return; }
     while (gen_ == gen) Yield();
   }
+  // __syncthreads_and / _or: two banks chosen by the barrier generation; the bank of the NEXT generation is reset before
+  // this barrier, while nobody can be writing it yet
+  int SyncThreadsVote(int pred, bool is_and) {
+    const unsigned g = gen_ & 1;
+    vote_[g ^ 1][0] = 1; vote_[g ^ 1][1] = 0;
+    if (!pred) vote_[g][0] = 0; else vote_[g][1] = 1;
+    SyncThreads();
+    return is_and ? vote_[g][0] : vote_[g][1];
+  }
   // all lanes of the calling fiber's warp (the kernels only use full masks outside divergent code)
   void SyncWarp() {
     const int w = cur_ >> 5;
@@ -257,7 +266,7 @@ class FiberBlock {
     return m;
   }
   template <typename F>
-  void Run(int block, int grid, F&& body) {
+  void Run(dim3 block, dim3 grid, F&& body) {
     static std::vector<unsigned char> stacks;             // reused from launch to launch
     constexpr size_t kStack = 128 * 1024;
     if (stacks.size() < fibers_.size() * kStack) stacks.resize(fibers_.size() * kStack);
@@ -266,9 +275,9 @@ class FiberBlock {
     for (size_t t = 0; t < fibers_.size(); ++t) {
       Fiber& f = fibers_[t];
       f.coords.thread_idx = make_uint3(static_cast<unsigned>(t), 0, 0);
-      f.coords.block_idx = make_uint3(block, 0, 0);
+      f.coords.block_idx = make_uint3(block.x, block.y, 0);
       f.coords.block_dim = dim3(static_cast<unsigned>(fibers_.size()), 1, 1);
-      f.coords.grid_dim = dim3(grid, 1, 1);
+      f.coords.grid_dim = grid;
       unsigned char* top = stacks.data() + (t + 1) * kStack;
 #if defined(MXKV_FAST_FIBERS)
       // a fresh stack as mxkv_hostemu_switch expects to find one: six saved registers, then the address to `ret` to.
@@ -322,20 +331,23 @@ class FiberBlock {
   std::vector<unsigned> warp_gen_;
   std::vector<uint64_t> slots_;
   std::vector<unsigned char> bank_of_;
+  int vote_[2][2] = {{1, 0}, {1, 0}};       // [bank][and, or]
 #if defined(MXKV_FAST_FIBERS)
   void* sched_sp_ = nullptr;
 #endif
 };
 
-// every block of the grid, one after another, each with `threads` fibers
+// every block of the grid (x fastest), one after another, each with `threads` fibers
 template <typename... P, typename... A>
-void RunGridFibers(void (*kernel)(P...), int grid, int threads, size_t smem_bytes, const A&... args) {
+void RunGridFibers(void (*kernel)(P...), dim3 grid, int threads, size_t smem_bytes, const A&... args) {
   Pool& pool = Pool::Get();
   std::lock_guard<std::mutex> one_launch(pool.launch_mutex());
   pool.current_smem() = pool.dynamic_smem(smem_bytes);
-  for (int b = 0; b < grid; ++b) {
-    FiberBlock block(threads);
-    block.Run(b, grid, [&] { kernel(args...); });
+  for (unsigned by = 0; by < grid.y; ++by) {
+    for (unsigned bx = 0; bx < grid.x; ++bx) {
+      FiberBlock block(threads);
+      block.Run(dim3(bx, by, 1), grid, [&] { kernel(args...); });
+    }
   }
 }
 
@@ -344,14 +356,19 @@ void RunGridFibers(void (*kernel)(P...), int grid, int threads, size_t smem_byte
 template <typename... P>
 struct Launcher {
   void (*kernel)(P...);
-  int grid, threads;
+  dim3 grid;
+  int threads;
   size_t smem;
   template <typename... A>
   void operator()(const A&... args) const { RunGridFibers(kernel, grid, threads, smem, static_cast<P>(args)...); }
 };
 template <typename... P>
+Launcher<P...> Launch(void (*kernel)(P...), dim3 grid, int threads, size_t smem) {
+  return Launcher<P...>{kernel, grid, threads, smem};
+}
+template <typename... P>
 Launcher<P...> Launch(void (*kernel)(P...), int64_t grid, int threads, size_t smem) {
-  return Launcher<P...>{kernel, static_cast<int>(grid), threads, smem};
+  return Launcher<P...>{kernel, dim3(static_cast<unsigned>(grid), 1, 1), threads, smem};
 }
 
 // ---- mbarrier with a transaction count + cp.async.bulk (staged kernel) ------------------------------------------------
@@ -400,6 +417,11 @@ inline void __syncthreads() {
   if (::hostemu::FiberBlock* b = ::hostemu::FiberBlock::Current()) b->SyncThreads();
   else ::hostemu::Pool::Get().barrier().Wait();
 }
+inline int __syncthreads_and(int pred) { return ::hostemu::FiberBlock::Current()->SyncThreadsVote(pred, true); }
+inline int __syncthreads_or(int pred) { return ::hostemu::FiberBlock::Current()->SyncThreadsVote(pred, false); }
+inline int __popc(unsigned v) { return __builtin_popcount(v); }
+inline int __ffs(int v) { return __builtin_ffs(v); }
+inline int __clz(int v) { return v == 0 ? 32 : __builtin_clz(static_cast<unsigned>(v)); }
 // warp exchanges (fiber blocks only; every lane of the warp calls)
 template <typename T> inline T __shfl_xor_sync(unsigned, T v, int lane_mask) {
   ::hostemu::FiberBlock* b = ::hostemu::FiberBlock::Current();
@@ -416,6 +438,8 @@ inline unsigned __ballot_sync(unsigned, int pred) { return ::hostemu::FiberBlock
 // occupancy queries of a launcher compiled for the host (the C++ overloads exist under nvcc only)
 template <typename... P>
 inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int* n, void (*)(P...), int, size_t) { *n = 2; return cudaSuccess; }
+template <typename... P>
+inline cudaError_t cudaFuncSetAttribute(void (*)(P...), cudaFuncAttribute, int) { return cudaSuccess; }
 // ~SM cycles: the kernels' spin timeouts (MXKV_B200_SPIN_TIMEOUT_S at 1.9 GHz) then mean what they say
 inline long long clock64() {
   return static_cast<long long>(std::chrono::duration_cast<std::chrono::nanoseconds>(

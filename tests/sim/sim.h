@@ -9,6 +9,7 @@ namespace sim {
 struct LaunchInfo {
   std::string name;        // demangled kernel name, e.g. "void mxkv::kv_dense_kernel<float, 2, false, true>(mxkv::DenseLaunch)"
   unsigned grid = 1, block = 1;
+  unsigned grid_y = 1;
   size_t smem = 0;
   int device = 0;
 };

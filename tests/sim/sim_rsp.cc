@@ -303,9 +303,20 @@ bool PullFused(void** args) {   // (table, in, n, out_idx, d_count, L, out_val, 
 
 }  // namespace
 
-bool DispatchRsp(const LaunchInfo&, const std::string& base, const std::vector<std::string>& t, void** args) {
+// hostemu_rsp.cc: csrc/rsp_kernels.cu compiled for the host
+bool HostEmuRspLaunch(const std::string& kernel, const std::vector<std::string>& targs, void** args, unsigned gx, unsigned gy,
+                      unsigned block, size_t smem);
+
+bool DispatchRsp(const LaunchInfo& info, const std::string& base, const std::vector<std::string>& t, void** args) {
   const size_t p = base.rfind("::");
   const std::string k = p == std::string::npos ? base : base.substr(p + 2);
+  // the kernels run from their OWN source unless MXKV_SIM_RSP=semantic asks for the independent emulators below
+  static const bool semantic = [] { const char* v = getenv("MXKV_SIM_RSP"); return v != nullptr && std::string(v) == "semantic"; }();
+  if (!semantic && k.compare(0, 4, "rsp_") == 0) {
+    if (HostEmuRspLaunch(k, t, args, info.grid, info.grid_y, info.block, info.smem)) return true;
+    fprintf(stderr, "[mxkv sim] rsp_kernels.cu from source: no entry for %s\n", info.name.c_str());
+    abort();
+  }
   if (k == "rsp_first_kernel") return First(args);
   if (k == "rsp_scan_kernel") return Scan(args);
   if (k == "rsp_rank_kernel") return Rank(args);

@@ -141,6 +141,22 @@ def test_one_process_per_gpu_on_simulator(sim_lib, world, tmp_path):
         assert "MP_WORKER_OK rank %d" % r in out, out[-2000:]
 
 
+def test_layerwise_kernels_from_source_match_the_emulators_bit_for_bit(sim_lib):
+    """csrc/norm_kernels.cu run from its own source -- 512-thread blocks as user-level contexts, __shfl_xor_sync as a
+    lane exchange -- against the emulators of tests/sim/sim_kernels.cc, which restate the hardware's summation order
+    (thread-strided partials, xor tree inside a warp, warps in order): LAMB / LANS / LARS over 1 ... 3 simulated
+    GPUs must come out bit for bit the same.  Each side confirms the other."""
+    digests = []
+    for mode in ("source", "semantic"):
+        env = dict(os.environ)
+        env.update(MXKV_SIM="1", MXKV_B200_LIBRARY_PATH=sim_lib, MXKV_SIM_DEVICES="4", MXKV_SIM_NORM=mode)
+        r = subprocess.run([sys.executable, os.path.join(SIM, "norm_bits_worker.py")], env=env, cwd=ROOT,
+                           capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+        digests.append([l for l in r.stdout.splitlines() if l.startswith("DIGEST")][-1])
+    assert digests[0] == digests[1]
+
+
 @pytest.mark.parametrize("world", [3, 5, 8])
 def test_one_process_per_gpu_under_the_tree_on_simulator(sim_lib, world, tmp_path):
     """MXNET_KVSTORE_USETREE=1 in the torchrun shape (tests/mp_worker.py, tree scenario only): 3, 5 and 8 ranks -- a

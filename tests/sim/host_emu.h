@@ -22,6 +22,7 @@
 #include <cstring>
 #include <functional>
 #include <mutex>
+#include <string>
 #include <thread>
 #include <ucontext.h>
 #include <vector>
@@ -54,8 +55,10 @@ inline P* Aligned(P* p, uintptr_t bytes) {
 }
 
 // a flag load of a spin loop: the peer it waits for may need this core (several ranks of 8 threads share the machine)
+void FiberYieldIfAny();      // (defined with FiberBlock)
 inline uint32_t PoliteLoad(const uint32_t* p, int order) {
   const uint32_t v = __atomic_load_n(p, order);
+  FiberYieldIfAny();
   std::this_thread::yield();
   return v;
 }
@@ -154,9 +157,19 @@ void RunGridSmem(void (*kernel)(P...), int grid, size_t smem_bytes, const A&... 
     }
   });
 }
+// (declared below) every block with its real thread count, as user-level contexts
+template <typename... P, typename... A>
+void RunGridFibers(void (*kernel)(P...), dim3 grid, int threads, size_t smem_bytes, const A&... args);
+
+// Dense and tree kernels only stride by blockDim.x, so either engine runs them: the block's real thread count as
+// user-level contexts on the calling thread (default: deterministic, no oversubscription when several test processes
+// share the machine), or 8 pooled OS threads that really run concurrently (MXKV_SIM_ENGINE=threads).
 template <typename Launch>
-void RunGrid(void (*kernel)(Launch), const Launch& L, int grid, int /*threads_asked*/, size_t smem_bytes = 0) {
-  RunGridSmem(kernel, grid, smem_bytes, L);
+void RunGrid(void (*kernel)(Launch), const Launch& L, int grid, int threads_asked, size_t smem_bytes = 0) {
+  static const bool os_threads = [] { const char* v = getenv("MXKV_SIM_ENGINE"); return v != nullptr && std::string(v) == "threads"; }();
+  if (os_threads) { RunGridSmem(kernel, grid, smem_bytes, L); return; }
+  if (threads_asked != 128 && threads_asked != 256 && threads_asked != 512 && threads_asked != 1024) threads_asked = 512;
+  RunGridFibers(kernel, dim3(static_cast<unsigned>(grid), 1, 1), threads_asked, smem_bytes, L);
 }
 
 // ---- fibers: a block with its REAL number of threads, for kernels that talk inside warps ------------------------------
@@ -337,6 +350,8 @@ class FiberBlock {
 #endif
 };
 
+inline void FiberYieldIfAny() { if (FiberBlock* b = FiberBlock::Current()) b->Yield(); }
+
 // every block of the grid (x fastest), one after another, each with `threads` fibers
 template <typename... P, typename... A>
 void RunGridFibers(void (*kernel)(P...), dim3 grid, int threads, size_t smem_bytes, const A&... args) {
@@ -399,7 +414,7 @@ inline void MbarWait(const uint64_t* bar, uint32_t parity) {
       std::lock_guard<std::mutex> lk(MbarMutex());
       if (((*bar >> 33) & 1) != parity) return;     // the phase with this parity has completed
     }
-    std::this_thread::yield();
+    if (FiberBlock::Current() != nullptr) FiberYieldIfAny(); else std::this_thread::yield();
   }
 }
 

@@ -94,10 +94,11 @@ def test_host_code_under_address_and_ub_sanitizers():
     lib, _ = b.build_sanitized()
     env = dict(os.environ)
     env.update(san)
-    # (the layer-wise-optimizer and row_sparse kernels run on user-level contexts that switch stacks behind the
-    # sanitizer's back: they take the independent emulators here; the thread-pool kernels -- dense, tree -- run from
-    # source as usual)
-    env.update(MXKV_SIM="1", MXKV_B200_LIBRARY_PATH=lib, MXKV_SIM_DEVICES="4", MXKV_SIM_NORM="semantic", MXKV_SIM_RSP="semantic")
+    # (user-level contexts switch stacks behind the sanitizer's back: the dense and tree kernels run from source on
+    # the OS-thread engine here -- which also makes a block's threads truly concurrent --, the layer-wise-optimizer and
+    # row_sparse kernels, which need their real thread counts, take the independent emulators)
+    env.update(MXKV_SIM="1", MXKV_B200_LIBRARY_PATH=lib, MXKV_SIM_DEVICES="4", MXKV_SIM_ENGINE="threads",
+               MXKV_SIM_NORM="semantic", MXKV_SIM_RSP="semantic")
     cmd = [sys.executable, "-m", "pytest", "-q", "-m", "gpu", "-p", "no:cacheprovider", "-x",
            "-k", "not one_process_per_gpu"] + _workers() + \
           [os.path.join(ROOT, "tests", f) for f in ("test_gpu_y_placement.py", "test_gpu_multi.py", "test_gpu_rsp.py",

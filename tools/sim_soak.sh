@@ -18,6 +18,9 @@ run 1 MXKV_B200_BULK_GROUP=4 $P tests/test_gpu_dense.py
 run 1 MXKV_B200_BULK_GROUP=3 MXKV_B200_BULK_TILE=256 MXKV_B200_BULK_STAGES=3 $P tests/test_gpu_dense.py
 run 1 MXKV_B200_BULK_TILE=512 MXKV_B200_BULK_STAGES=8 MXKV_B200_CHUNK=1024 $P tests/test_gpu_dense.py tests/test_gpu_y_semantics.py
 run 1 MXKV_B200_BULK=2 MXKV_B200_THREADS=128 $P tests/test_gpu_dense.py tests/test_gpu_reference_kats.py
+# the same dense kernels on the OS-thread engine: a block's threads really run at the same time
+run 1 MXKV_SIM_ENGINE=threads $P tests/test_gpu_dense.py
+run 4 MXKV_SIM_ENGINE=threads MXKV_B200_BULK=2 $P tests/test_gpu_multi.py -k "not one_process_per_gpu"
 run 4 MXKV_B200_BULK=2 MXKV_B200_BULK_GROUP=4 MXKV_B200_BULK_TILE=256 $P tests/test_gpu_multi.py tests/test_gpu_y_placement.py -k "not one_process_per_gpu"
 run 4 MXKV_B200_BULK=0 MXKV_B200_CHUNK=256 $P tests/test_gpu_multi.py tests/test_gpu_y_placement.py -k "not one_process_per_gpu"
 run 3 MXKV_FUZZ_SEEDS=60 $P tests/test_gpu_y_placement.py -k randomized

@@ -2,13 +2,15 @@
 // CPU (test infrastructure; included by csrc/device_utils.cuh only when MXKV_HOST_EMU is defined, which only the
 // tests/sim/hostemu_*.cc translation units do).
 //
-// A block is a handful of OS threads (kHostEmuThreads, whatever block size the launch asked for: the kernels
-// stride by blockDim.x), __syncthreads is a real barrier between them, __shared__ variables are statics and the
-// dynamic shared memory one buffer (blocks run one after another, launches are serialised), threadIdx / blockIdx /
-// blockDim / gridDim are per-thread values.  16- and 8-byte accesses are checked for alignment, so a packet the
-// kernel addresses wrongly aborts here as it would fault on the device.  The mbarrier / bulk-copy pair of the staged
-// kernel is modelled as what the PTX says: expect_tx arms a phase with a byte count, every copy completes its bytes,
-// the phase flips when the count is back to zero, waiters spin on the phase parity.
+// A block is its real number of threads, run as user-level contexts on the calling OS thread and switched round-robin
+// at barriers, warp exchanges and spin loops (FiberBlock) -- or, for kernels that only stride by blockDim.x, a handful
+// of pooled OS threads that really run concurrently (MXKV_SIM_ENGINE=threads).  __syncthreads is a real barrier,
+// __shared__ variables are statics and the dynamic shared memory one buffer (blocks run one after another, launches
+// are serialised), threadIdx / blockIdx / blockDim / gridDim are per-context values.  16- and 8-byte accesses are
+// checked for alignment, so a packet the kernel addresses wrongly aborts here as it would fault on the device.  Warp
+// shuffles, ballots and block votes are exchanges between the 32 contexts of a warp.  The mbarrier / bulk-copy pair of
+// the staged kernel is modelled as what the PTX says: expect_tx arms a phase with a byte count, every copy completes
+// its bytes, the phase flips when the count is back to zero, waiters spin on the phase parity.
 // What this cannot show: anything about registers, occupancy, asynchrony of the copy engine, memory ordering between
 // GPUs, or speed.
 #pragma once

@@ -1,5 +1,6 @@
 // hostemu_tree.cc -- csrc/tree_kernels.cu, the file the device executes, compiled by g++ and run on the CPU
-// (host_emu.h): blocks of a few OS threads with a real barrier for __syncthreads, aligned 16-byte accesses.  The
+// (host_emu.h): blocks with their real thread count as user-level contexts (or a few concurrent OS threads,
+// MXKV_SIM_ENGINE=threads), a real barrier for __syncthreads, aligned 16-byte accesses.  The
 // simulated runtime hands the tree-order launches to THIS code instead of a semantic emulator, so every tree test of
 // the CPU suite walks the kernel's own chunk search, vector / scalar split, load batches, add schedule, optimizer
 // and stores.  (Test infrastructure.  MXKV_SIM_TREE=semantic selects the independent emulator of sim_kernels.cc.)

@@ -171,7 +171,10 @@ void RunGrid(void (*kernel)(Launch), const Launch& L, int grid, int threads_aske
   static const bool os_threads = [] { const char* v = getenv("MXKV_SIM_ENGINE"); return v != nullptr && std::string(v) == "threads"; }();
   if (os_threads) { RunGridSmem(kernel, grid, smem_bytes, L); return; }
   if (threads_asked != 128 && threads_asked != 256 && threads_asked != 512 && threads_asked != 1024) threads_asked = 512;
-  RunGridFibers(kernel, dim3(static_cast<unsigned>(grid), 1, 1), threads_asked, smem_bytes, L);
+  // these kernels never look at a neighbour's registers: 64 contexts walk the same indices as 512 at an eighth of the
+  // switches (MXKV_SIM_REAL_THREADS=1: the launch's own block size)
+  static const bool real = getenv("MXKV_SIM_REAL_THREADS") != nullptr;
+  RunGridFibers(kernel, dim3(static_cast<unsigned>(grid), 1, 1), real ? threads_asked : 64, smem_bytes, L);
 }
 
 // ---- fibers: a block with its REAL number of threads, for kernels that talk inside warps ------------------------------

@@ -419,7 +419,6 @@ static BulkKernelFn pick_bulk(int opt, int mp) {
   }
 }
 
-#if !defined(MXKV_HOST_EMU)     // (multimem: no CPU model of the switch; the simulated runtime never takes this variant)
 // ---------------------------------------------------------------------------
 // NVLS variant (float32, one process per GPU, arrays bound to an NVSwitch multicast object):
 // the reduce-scatter half is ONE multimem.ld_reduce per 16 bytes -- the switch adds the n replicas
@@ -431,14 +430,22 @@ static BulkKernelFn pick_bulk(int opt, int mp) {
 // receives identical bits (each shard is produced by exactly one rank).
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ float4 mm_ld_reduce(const void* p) {
+#if defined(MXKV_HOST_EMU)     // tests/sim: the n copies behind a multicast address, added on the CPU
+  return hostemu::MultimemLoadReduce(p);
+#else
   float4 v;
   asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
                : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
   return v;
+#endif
 }
 __device__ __forceinline__ void mm_st(void* p, const float4& v) {
+#if defined(MXKV_HOST_EMU)
+  hostemu::MultimemStore(p, v);
+#else
   asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};"
                :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+#endif
 }
 
 // One scheduling chunk = ONE block iteration (blockDim * U 16-byte vectors), so `chunk c -> block c % grid`
@@ -594,6 +601,7 @@ static NvlsKernelFn pick_nvls(int opt, int mp, int unroll, int pipe) {
   }
 }
 
+#if !defined(MXKV_HOST_EMU)
 int NvlsPlan(int device, int opt, int multi_precision, int unroll, int pipe, int threads, int* chunk_elems) {
   NvlsKernelFn fn = pick_nvls(opt, multi_precision, unroll, pipe);
   if (fn == nullptr) return 0;
@@ -610,8 +618,7 @@ int NvlsPlan(int device, int opt, int multi_precision, int unroll, int pipe, int
   const int g = occ * sm_count(device);
   return g > kMaxBlocks ? kMaxBlocks : g;
 }
-
-#endif  // !MXKV_HOST_EMU
+#endif
 
 // ---------------------------------------------------------------------------
 // plain typed sum for the dtypes the reference's ElementwiseSum also accepts
@@ -917,8 +924,17 @@ int LaunchFill(void* ptr, int value_byte, size_t bytes, cudaStream_t s) {
 // tests/sim/hostemu_dense.cc: this file compiled by g++ -- the per-thread, the staged and the typed-sum kernels run
 // as CPU threads from the source above.  The instantiation is chosen by the same pick_* code the device launch uses.
 int LaunchDenseHostEmu(const DenseLaunch& L) {
-  if (L.order == ORDER_TREE || L.nvls) return 1;
+  if (L.order == ORDER_TREE) return 1;
   const int grid = L.grid < 1 ? 1 : (L.grid > kMaxBlocks ? kMaxBlocks : L.grid);
+  if (L.nvls) {      // a chunk is exactly blockDim * U vectors: this kernel needs the launch's own block size
+    NvlsKernelFn nf = pick_nvls(L.opt, L.multi_precision, L.nvls_unroll, L.nvls_pipe);
+    int threads = L.threads;
+    if (threads != 128 && threads != 256 && threads != 512) threads = kThreads;
+    if (nf == nullptr || L.dtype != kFloat32 || L.sync.mode == SYNC_NONE ||
+        L.chunk_elems != threads * nvls_round_unroll(L.nvls_unroll, L.opt) * 4) return 1;
+    hostemu::RunGridFibers(nf, dim3(static_cast<unsigned>(grid), 1, 1), threads, 0, L);
+    return 0;
+  }
   if (L.bulk) {
     BulkKernelFn bf = pick_bulk(L.opt, L.multi_precision);
     if (bf == nullptr || L.dtype != kFloat32) return 1;

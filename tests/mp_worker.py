@@ -288,13 +288,15 @@ def main():
         mx.kv.set_nvls(2)            # FORCE the multimem kernel at every world size (auto: above 4 ranks only)
         nv0 = mx.kv.launch_count("nvls")
         # the bench sweep's sizes in one call (every rank regenerates every rank's data: bounded for large worlds)
-        big = [(1 << p,) for p in range(10, 25 if world <= 2 else 23, 2)]
+        big = [(1 << p,) for p in range(10, (25 if world <= 2 else 23) if not SIM else 19, 2)]   # (CPU: up to 2^18)
         small = [(1 << 10,), (3 * (1 << 16),), (1 << 21,)]
         sgd = dict(learning_rate=0.1, momentum=0.9, wd=1e-4)
         expected = 0
         # (requests in flight per thread, pipelined, grid cap, block size): the default and the corners of the
         # tuning space (tools/tune_nvls.py) -- every instantiation that may become the default is compared
         cfgs = [(2, 0, 48, 512), (4, 1, 0, 512), (1, 0, 32, 256), (8, 1, 64, 512), (2, 1, 148, 512)]
+        if SIM:
+            cfgs = cfgs[:4]
         for ci, cfg in enumerate(cfgs if alloc_name == allocs[0][0] else cfgs[:1]):
             mx.kv.set_nvls_tuning(*cfg)
             cases = [(None, {}, small), ("sgd", sgd, small), ("sgd", dict(sgd, learning_rate=0.01), big),

@@ -164,11 +164,14 @@ API cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr attr, int) {
 API cudaError_t cudaDeviceGetDefaultMemPool(cudaMemPool_t* pool, int) { *pool = nullptr; return cudaSuccess; }
 API cudaError_t cudaMemPoolSetAttribute(cudaMemPool_t, cudaMemPoolAttr, void*) { return cudaSuccess; }
 API cudaError_t cudaFuncSetAttribute(const void*, cudaFuncAttribute, int) { return cudaSuccess; }
-// no driver behind the simulated runtime: the engine-owned multicast arena (csrc/vmm_arena.cc) falls back to the IPC one
-API cudaError_t cudaGetDriverEntryPoint(const char*, void** fn, unsigned long long, cudaDriverEntryPointQueryResult* status) {
-  if (fn) *fn = nullptr;
-  if (status) *status = cudaDriverEntryPointSymbolNotFound;
-  return cudaErrorNotSupported;
+// the driver entry points of csrc/vmm_arena.cc (VMM allocations, multicast objects) are served by fake_driver.cc;
+// anything else is "not found", as on a machine without a driver
+namespace sim { void* DriverEntry(const char* name); }
+API cudaError_t cudaGetDriverEntryPoint(const char* name, void** fn, unsigned long long, cudaDriverEntryPointQueryResult* status) {
+  void* p = sim::DriverEntry(name);
+  if (fn) *fn = p;
+  if (status) *status = p ? cudaDriverEntryPointSuccess : cudaDriverEntryPointSymbolNotFound;
+  return p ? cudaSuccess : cudaErrorNotSupported;
 }
 
 API cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessorWithFlags(int* n, const void*, int, size_t, unsigned) {

@@ -471,3 +471,26 @@ inline uint32_t atomicAdd(uint32_t* p, uint32_t v) { return __atomic_fetch_add(p
 inline float __uint_as_float(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
 inline uint32_t __float_as_uint(float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; }
 inline double __dadd_rn(double a, double b) { return a + b; }
+template <typename T> inline T __ldg(const T* p) { return *p; }
+
+// multimem.ld_reduce / multimem.st on an address of a multicast mapping (fake_driver.cc resolves it into the local
+// mappings of every device's bound allocation): the sum of the n copies, added in device order -- the switch's own
+// order is unspecified, results agree with any order to float32 rounding --, and a store into all of them
+extern "C" int mxkv_sim_multimem(const void* p, void** out);
+namespace hostemu {
+inline float4 MultimemLoadReduce(const void* p) {
+  void* c[8];
+  const int n = mxkv_sim_multimem(Aligned(p, 16), c);
+  float4 s = *static_cast<const float4*>(c[0]);
+  for (int i = 1; i < n; ++i) {
+    const float4 v = *static_cast<const float4*>(c[i]);
+    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+  }
+  return s;
+}
+inline void MultimemStore(void* p, const float4& v) {
+  void* c[8];
+  const int n = mxkv_sim_multimem(Aligned(p, 16), c);
+  for (int i = 0; i < n; ++i) *static_cast<float4*>(c[i]) = v;
+}
+}  // namespace hostemu

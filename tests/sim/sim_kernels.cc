@@ -682,6 +682,8 @@ bool Dispatch(const LaunchInfo& info, void** args) {
   ParseName(info.name, &base, &t);
   if (base == "mxkv::kv_dense_kernel") return Dense(t, args);
   if (base == "mxkv::kv_dense_bulk_kernel") return DenseBulk(t, args);
+  if (base == "mxkv::kv_dense_nvls_kernel")        // (from source only: multimem resolved by fake_driver.cc)
+    return DenseFromSource(*static_cast<const DenseLaunch*>(args[0]));
   if (base == "mxkv::kv_dense_tree_kernel") return DenseTree(t, args);
   if (base == "mxkv::kv_sum_tree_f64_kernel") return SumTreeF64(args);
   if (base == "mxkv::kv_sum_typed_kernel") return SumTyped(t, args);

@@ -107,6 +107,32 @@ def main():
     def data(seed, shape, r):
         return np.random.default_rng(seed * 1000 + r).uniform(-1, 1, shape).astype(np.float32)
 
+    if os.environ.get("MXKV_MP_ARENA_ONLY"):
+        # tests/test_sim_host_logic.py::test_engine_owned_arena_and_its_fallbacks: which arena came up (every rank must
+        # agree), and that it works: symmetric arrays of several segments' worth, a sharded and an unsharded key
+        have = [bool(mx.nd.has_multicast(mx.nd.empty_symmetric((1024,)))) for _ in range(2)]
+        assert all(h == have[0] for h in have)
+        assert len(set(allgather_int(int(have[0])))) == 1, "the ranks disagree on the kind of arena"
+        want_mc = os.environ["MXKV_MP_ARENA_ONLY"] == "multicast"
+        assert have[0] == want_mc, ("arena kind", have[0], want_mc)
+        kva = mx.kv.create("device")
+        shapes = [(3000,), (1 << 20,), ((1 << 22) + 12,)]
+        kva.init(list(range(len(shapes))), [mx.nd.zeros(s, ctx) for s in shapes])
+        for rep in range(3):                      # (more arena than one 16 MB segment: a later segment is created)
+            vals = [mx.nd.empty_symmetric(s) for s in shapes]
+            outs = [mx.nd.empty_symmetric(s) for s in shapes]
+            for k, s in enumerate(shapes):
+                vals[k][:] = data(1200 + 10 * rep + k, s, rank)
+            device_sync(); barrier()
+            kva.pushpull(list(range(len(shapes))), vals, out=outs)
+            for k, s in enumerate(shapes):
+                want = O.sum_device([data(1200 + 10 * rep + k, s, r) for r in range(world)])
+                assert bits_equal(outs[k].asnumpy(), want), ("arena", rep, k)
+        mx.nd.waitall()
+        barrier()
+        print("MP_WORKER_OK rank", rank, "multicast" if have[0] else "ipc", flush=True)
+        return
+
     if os.environ.get("MXKV_MP_TREE_ONLY"):
         # tests/test_gpu_zzz_tree.py::test_one_process_per_gpu_under_the_tree: scenario 10 alone (it has not met
         # hardware yet; the scenarios below have, and stay as they ran)

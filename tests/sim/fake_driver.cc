@@ -62,6 +62,27 @@ uint64_t g_next = 1;
 std::vector<Mapping> g_maps;
 std::map<uintptr_t, size_t> g_reserved;
 
+// MXKV_SIM_VMM_FAIL="<entry point>[#k]:<rank>": that entry point fails on that rank (its k-th call; every call without
+// #k) -- what the arena's agree-or-fall-back protocol exists for (tests/test_sim_host_logic.py)
+bool Inject(const char* name) {
+  static const char* spec = getenv("MXKV_SIM_VMM_FAIL");
+  if (spec == nullptr) return false;
+  static std::map<std::string, int> calls;
+  std::string s = spec;
+  const size_t colon = s.rfind(':');
+  if (colon == std::string::npos) return false;
+  const char* rank_env = getenv("RANK");
+  if (rank_env == nullptr || atoi(rank_env) != atoi(s.c_str() + colon + 1)) return false;
+  std::string sym = s.substr(0, colon);
+  int kth = 0;
+  const size_t hash = sym.find('#');
+  if (hash != std::string::npos) { kth = atoi(sym.c_str() + hash + 1); sym = sym.substr(0, hash); }
+  if (sym != name) return false;
+  std::lock_guard<std::mutex> lk(g_mu);
+  const int n = ++calls[sym];
+  return kth == 0 || n == kth;
+}
+
 bool Identify(int fd, uint64_t* ino, uint64_t* dev, size_t* size) {
   struct stat st;
   if (fstat(fd, &st) != 0) return false;
@@ -72,6 +93,7 @@ bool Identify(int fd, uint64_t* ino, uint64_t* dev, size_t* size) {
 }
 
 CUresult MemCreate(CUmemGenericAllocationHandle* out, size_t bytes, const CUmemAllocationProp* prop, unsigned long long) {
+  if (Inject("cuMemCreate")) return CUDA_ERROR_UNKNOWN;
   if (bytes == 0 || bytes % kGranularity != 0) return CUDA_ERROR_INVALID_VALUE;
   const int fd = memfd_create("mxkvsim_vmm", MFD_CLOEXEC);
   if (fd < 0 || ftruncate(fd, static_cast<off_t>(bytes)) != 0) { if (fd >= 0) close(fd); return CUDA_ERROR_OUT_OF_MEMORY; }
@@ -95,6 +117,7 @@ CUresult MemRelease(CUmemGenericAllocationHandle h) {
 }
 
 CUresult MemExport(void* out, CUmemGenericAllocationHandle h, CUmemAllocationHandleType type, unsigned long long) {
+  if (Inject("cuMemExportToShareableHandle")) return CUDA_ERROR_UNKNOWN;
   if (type != CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR) return CUDA_ERROR_NOT_SUPPORTED;
   std::lock_guard<std::mutex> lk(g_mu);
   auto it = g_handles.find(h);
@@ -111,6 +134,7 @@ McCtrl* MapCtrl(int fd) {
 }
 
 CUresult MemImport(CUmemGenericAllocationHandle* out, void* os_handle, CUmemAllocationHandleType type) {
+  if (Inject("cuMemImportFromShareableHandle")) return CUDA_ERROR_UNKNOWN;
   if (type != CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR) return CUDA_ERROR_NOT_SUPPORTED;
   const int theirs = static_cast<int>(reinterpret_cast<intptr_t>(os_handle));
   Handle h;
@@ -137,6 +161,7 @@ CUresult MemGetGranularity(size_t* g, const CUmemAllocationProp*, CUmemAllocatio
 }
 
 CUresult MemAddressReserve(CUdeviceptr* out, size_t size, size_t, CUdeviceptr, unsigned long long) {
+  if (Inject("cuMemAddressReserve")) return CUDA_ERROR_UNKNOWN;
   void* p = mmap(nullptr, size, PROT_NONE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
   if (p == MAP_FAILED) return CUDA_ERROR_OUT_OF_MEMORY;
   std::lock_guard<std::mutex> lk(g_mu);
@@ -153,6 +178,7 @@ CUresult MemAddressFree(CUdeviceptr va, size_t size) {
 }
 
 CUresult MemMap(CUdeviceptr va, size_t size, size_t offset, CUmemGenericAllocationHandle h, unsigned long long) {
+  if (Inject("cuMemMap")) return CUDA_ERROR_UNKNOWN;
   std::lock_guard<std::mutex> lk(g_mu);
   auto it = g_handles.find(h);
   if (it == g_handles.end() || offset != 0 || size > it->second.bytes) return CUDA_ERROR_INVALID_VALUE;
@@ -182,6 +208,7 @@ CUresult MemUnmap(CUdeviceptr va, size_t size) {
 CUresult MemSetAccess(CUdeviceptr, size_t, const CUmemAccessDesc*, size_t) { return CUDA_SUCCESS; }
 
 CUresult MulticastCreate(CUmemGenericAllocationHandle* out, const CUmulticastObjectProp* prop) {
+  if (Inject("cuMulticastCreate")) return CUDA_ERROR_UNKNOWN;
   if (prop->numDevices < 1 || prop->numDevices > kMaxDev || prop->size % kGranularity != 0) return CUDA_ERROR_INVALID_VALUE;
   const int fd = memfd_create("mxkvsim_mc", MFD_CLOEXEC);
   if (fd < 0 || ftruncate(fd, kCtrlBytes) != 0) { if (fd >= 0) close(fd); return CUDA_ERROR_OUT_OF_MEMORY; }
@@ -202,6 +229,7 @@ CUresult MulticastCreate(CUmemGenericAllocationHandle* out, const CUmulticastObj
 }
 
 CUresult MulticastAddDevice(CUmemGenericAllocationHandle mc, CUdevice dev) {
+  if (Inject("cuMulticastAddDevice")) return CUDA_ERROR_UNKNOWN;
   std::lock_guard<std::mutex> lk(g_mu);
   auto it = g_handles.find(mc);
   if (it == g_handles.end() || !it->second.multicast || dev < 0 || dev >= kMaxDev) return CUDA_ERROR_INVALID_VALUE;
@@ -211,6 +239,7 @@ CUresult MulticastAddDevice(CUmemGenericAllocationHandle mc, CUdevice dev) {
 
 CUresult MulticastBindMem(CUmemGenericAllocationHandle mc, size_t mc_offset, CUmemGenericAllocationHandle mem, size_t mem_offset,
                           size_t size, unsigned long long) {
+  if (Inject("cuMulticastBindMem")) return CUDA_ERROR_UNKNOWN;
   std::lock_guard<std::mutex> lk(g_mu);
   auto im = g_handles.find(mc);
   auto ia = g_handles.find(mem);

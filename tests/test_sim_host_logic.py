@@ -158,6 +158,58 @@ def test_layerwise_kernels_from_source_match_the_emulators_bit_for_bit(sim_lib):
     assert digests[0] == digests[1]
 
 
+_ARENA_CASES = [
+    (None, "multicast"),
+    ("cuMemExportToShareableHandle:1", "ipc"), ("cuMulticastCreate:0", "ipc"), ("cuMulticastBindMem:0", "ipc"),
+    ("cuMemMap:1", "ipc"),
+    ("cuMemCreate#2:1", "multicast"),            # a LATER segment fails on one rank: that segment is an IPC one everywhere
+    ("no_pidfd", "multicast"),                   # pidfd_open refused (EPERM): descriptors travel over unix sockets instead
+]
+if int(os.environ.get("MXKV_FUZZ_SEEDS", "0")) > 0:      # soak runs: every other stage of the protocol as well
+    _ARENA_CASES += [("cuMemCreate:0", "ipc"), ("cuMemImportFromShareableHandle:2", "ipc"), ("cuMulticastAddDevice:1", "ipc"),
+                     ("cuMemAddressReserve:2", "ipc"), ("cuMemMap#3:0", "ipc"), ("cuMulticastBindMem:2", "ipc")]
+
+
+@pytest.mark.parametrize("fail,expect", _ARENA_CASES)
+def test_engine_owned_arena_and_its_fallbacks(sim_lib, fail, expect, tmp_path):
+    """csrc/vmm_arena.cc on the CPU (tests/sim/fake_driver.cc): three processes build the engine-owned multicast arena
+    -- VMM allocations, descriptors handed between the processes with pidfd_getfd or SCM_RIGHTS, one multicast object
+    per segment -- and exchange through it; then the same with one driver call failing on one rank at every stage of
+    the protocol: every rank must fall back to the cudaMalloc + cudaIpc arena TOGETHER (nobody hangs, nobody keeps a
+    half-built segment) and the exchange must still be right."""
+    import glob
+    world = 3
+    env = dict(os.environ)
+    env.update(MXKV_SIM="1", MXKV_SIM_MP="1", MXKV_SIM_RDV=str(tmp_path), MXKV_B200_LIBRARY_PATH=sim_lib,
+               MXKV_SIM_DEVICES=str(world), MXKV_B200_ARENA_MB="16", WORLD_SIZE=str(world), MXKV_MP_ARENA_ONLY=expect)
+    if fail == "no_pidfd":
+        shim = os.path.join(os.path.dirname(sim_lib), "libno_pidfd.so")
+        env["LD_PRELOAD"] = (env.get("LD_PRELOAD", "") + ":" + shim).strip(":")
+        env["MXKV_B200_ARENA_VMM_VERBOSE"] = "1"
+    elif fail:
+        env["MXKV_SIM_VMM_FAIL"] = fail
+    procs = []
+    for r in range(world):
+        e = dict(env, RANK=str(r), LOCAL_RANK=str(r))
+        procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "mp_worker.py")], env=e, cwd=ROOT,
+                                      stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    outs = []
+    try:
+        for p in procs:
+            out, _ = p.communicate(timeout=300)
+            outs.append(out)
+    finally:
+        for p in procs:
+            if p.poll() is None:
+                p.kill()
+        for p in procs:
+            for f in glob.glob("/dev/shm/mxkvsim_%d_*" % p.pid):
+                os.unlink(f)
+    for r, (p, out) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0, "rank %d:\n%s" % (r, out[-3000:])
+        assert "MP_WORKER_OK rank %d %s" % (r, expect) in out, out[-2000:]
+
+
 @pytest.mark.parametrize("world", [3, 5, 8])
 def test_one_process_per_gpu_under_the_tree_on_simulator(sim_lib, world, tmp_path):
     """MXNET_KVSTORE_USETREE=1 in the torchrun shape (tests/mp_worker.py, tree scenario only): 3, 5 and 8 ranks -- a

@@ -26,5 +26,9 @@ run 4 MXKV_B200_BULK=0 MXKV_B200_CHUNK=256 $P tests/test_gpu_multi.py tests/test
 run 3 MXKV_FUZZ_SEEDS=60 $P tests/test_gpu_y_placement.py -k randomized
 run 8 MXKV_FUZZ_SEEDS=60 MXKV_B200_BULK=2 MXKV_B200_TWOSHOT_BYTES=4096 $P tests/test_gpu_y_placement.py -k randomized
 for D in 3 5 8; do run $D MXKV_FUZZ_SEEDS=150 MXKV_B200_CHUNK=512 $P tests/test_gpu_zzz_tree.py; done
+# the multicast arena's agree-or-fall-back protocol with a driver call failing at every stage (three processes each)
+echo "== multicast arena: every failure stage"
+env -u MXKV_SIM -u MXKV_B200_LIBRARY_PATH MXKV_FUZZ_SEEDS=1 timeout 1500 python -m pytest -q -p no:cacheprovider tests/test_sim_host_logic.py -k arena_and_its_fallbacks 2>&1 | tail -2
+[ "${PIPESTATUS[0]}" = "0" ] || FAIL=1
 [ $FAIL = 0 ] && echo SOAK_OK || echo SOAK_FAILED
 exit $FAIL
